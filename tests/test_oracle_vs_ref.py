@@ -1,0 +1,80 @@
+"""Oracle restatement vs the unmodified reference, live (larger, freshly drawn batches).
+Runs where oracle/_ref/libgbp_ref.so exists (built from /root/reference in the build container and
+shipped to the GPU box with the snapshot); otherwise the golden tests carry the pin."""
+import numpy as np
+import pytest
+
+import pyoracle as po
+from conftest import assert_bits_equal, load_terrain
+
+pytestmark = pytest.mark.skipif(not po.Ref.available(), reason="oracle/_ref not built (no /root/reference)")
+
+
+@pytest.fixture(scope="module", params=["rough_terrain", "slope", "synth_nan"])
+def pair(request):
+    T = load_terrain(request.param)
+    return po.Oracle(T), po.Ref(T), T
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_pairs_large(pair, adaptive):
+    o, r, T = pair
+    q = o.sample_states(101, 1, 0, 60000)
+    v, _ = o.valid_states(q, po.STANCE)
+    s = q[v == 1][:20000]
+    a = o.sample_actions(101, 2, 0, len(s))
+    d = (np.arange(len(s)) // 3 % 2).astype(np.uint8)
+    vo, fo, sno, tno, _ = o.validate_pairs(s, a, d, adaptive=adaptive, nthreads=4)
+    vr, snr, tnr = r.validate_pairs(s, a, d, adaptive=adaptive, nthreads=4)
+    ing = (fo & po.FLAG_OOG) == 0
+    assert (vo[ing] == vr[ing]).all()
+    assert_bits_equal(sno, snr, where=ing, what="s_new")
+    assert_bits_equal(tno, tnr, where=ing, what="t_new")
+
+
+def test_states_and_lookups(pair):
+    o, r, T = pair
+    q = o.sample_states(202, 1, 0, 30000)
+    for ph in (po.STANCE, po.FLIGHT):
+        v, fl = o.valid_states(q, ph)
+        ing = (fl & po.FLAG_OOG) == 0
+        assert (v[ing] == r.valid_states(q, ph)[ing]).all()
+    rng = np.random.default_rng(5)
+    x = rng.uniform(T.x[0], T.x[-1] - 1e-9, 5000); y = rng.uniform(T.y[0], T.y[-1] - 1e-9, 5000)
+    assert_bits_equal(o.ground_height(x, y)[0], r.ground_height(x, y), what="height")
+    assert_bits_equal(o.surface_normal(x, y), r.surface_normal(x, y), what="normal")
+    assert (o.height_is_nan(x, y) == r.height_is_nan(x, y)).all()
+
+
+def test_connect_and_postprocess(pair):
+    o, r, T = pair
+    q = o.sample_states(303, 1, 0, 30000)
+    v, fl = o.valid_states(q, po.STANCE)
+    s = q[(v == 1)][:3000]
+    rng = np.random.default_rng(3)
+    tgt = s[rng.permutation(len(s))].copy()
+    tgt[::2, :3] = s[::2, :3] + rng.normal(0, 0.3, (len(s[::2]), 3)) * np.array([1, 1, 0.05])
+    d = (np.arange(len(s)) % 2).astype(np.uint8)
+    for adaptive in (False, True):
+        so, sno, ano, fl = o.attempt_connect(s, tgt, d, adaptive)
+        sr, snr, anr = r.attempt_connect(s, tgt, d, adaptive)
+        ing = (fl & po.FLAG_OOG) == 0
+        assert (so[ing] == sr[ing]).all()
+        hit = (so != po.TRAPPED) & ing
+        assert_bits_equal(sno[hit], snr[hit], what="connect s_new")
+        assert_bits_equal(ano[hit], anr[hit], what="connect a_new")
+
+
+def test_gridmap_ingest_matches_loaddata():
+    """fast_terrain_map.cpp:31-91: index flip + float layers; pins the layout used by the C-ABI loader."""
+    rng = np.random.default_rng(1)
+    nx, ny, res = 12, 9, 0.25
+    elev = rng.normal(0, 0.1, (nx, ny)).astype(np.float32)
+    r = po.Ref()
+    r.set_terrain_gridmap(nx, ny, res, 1.0, -0.5, elev)
+    x, y = r.axes()
+    assert (np.diff(x) > 0).all() and (np.diff(y) > 0).all()
+    T = po.Terrain(x, y, elev[::-1, ::-1].astype(np.float64))
+    r2 = po.Ref(T)
+    px = rng.uniform(x[0], x[-1] - 1e-9, 500); py = rng.uniform(y[0], y[-1] - 1e-9, 500)
+    assert_bits_equal(r.ground_height(px, py), r2.ground_height(px, py), what="gridmap vs loadData")
