@@ -1,0 +1,711 @@
+// extern "C" layer of libgbp_b200.so (include/gbp_b200.h).  Host side: handle lifetime, staging of
+// HOST buffers through a chunked copy/compute pipeline, kernel selection and launch geometry.
+// No torch types, no CPU fallback: without a CUDA device every compute entry point fails with
+// GBP_E_CUDA.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gbp_kernels.cuh"
+#include "gbp_planner.cuh"
+
+using namespace gbp;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                                          \
+	do {                                                                                                  \
+		cudaError_t e_ = (call);                                                                          \
+		if (e_ != cudaSuccess) return fail(GBP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+	} while (0)
+
+int sm_count() {
+	static int sms = 0;
+	if (!sms) {
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+			sms = 148;
+	}
+	return sms;
+}
+
+// stream-ordered device scratch; the pool keeps freed blocks, so repeated calls do not hit the driver
+struct Dev {
+	void *p = nullptr;
+	cudaStream_t st;
+	explicit Dev(cudaStream_t s) : st(s) {}
+	cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+	~Dev() { if (p) cudaFreeAsync(p, st); }
+	template <class T> T *as() { return (T *) p; }
+};
+
+cudaStream_t lib_stream() {
+	static thread_local cudaStream_t s = nullptr;
+	if (!s) {
+		if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
+		int dev = 0;
+		cudaMemPool_t pool;
+		if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+			unsigned long long keep = ~0ull;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+	}
+	return s;
+}
+
+template <class T>
+int upload(Dev &d, const T *host, size_t n, cudaStream_t st) {
+	CU(d.alloc(n * sizeof(T)));
+	if (n) CU(cudaMemcpyAsync(d.p, host, n * sizeof(T), cudaMemcpyHostToDevice, st));
+	return GBP_OK;
+}
+
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned) ((n + threads - 1) / threads); }
+
+}  // namespace
+
+struct gbp_terrain {
+	TerrainView view;
+	double *d_x = nullptr, *d_y = nullptr;
+	void *d_z = nullptr;
+	void *d_n = nullptr;
+	unsigned long long *d_cnt = nullptr;  // 6 work counters of the last validate launch
+	std::vector<double> hx, hy;
+	int cell_bytes = 8;
+};
+
+struct gbp_tree {
+	TreeView view;
+	int *d_n = nullptr;
+	double *d_v = nullptr, *d_act = nullptr, *d_g = nullptr, *d_y = nullptr;
+	int *d_parent = nullptr;
+	// scratch of extend/connect
+	ExtendScratch S;
+	int k_cap = 0;
+	double *d_target = nullptr;
+};
+
+extern "C" {
+
+const char *gbp_last_error(void) { return g_err.c_str(); }
+const char *gbp_version(void) { return "gbp_b200 0.1 (sm_100a, fp64 exact path)"; }
+int gbp_device_count(int *count) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) { *count = 0; return fail(GBP_E_CUDA, cudaGetErrorString(e)); }
+	*count = n;
+	return GBP_OK;
+}
+int gbp_set_device(int device) { CU(cudaSetDevice(device)); return GBP_OK; }
+
+// ------------------------------------------------------------------------------------- terrain
+static bool lossless_f32(const double *a, size_t n) {
+	for (size_t i = 0; i < n; ++i) {
+		double v = a[i];
+		if (v != v) continue;  // NaN stays NaN
+		if ((double) (float) v != v) return false;
+	}
+	return true;
+}
+
+int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const double *z, const double *dx, const double *dy,
+					   const double *dz, gbp_terrain **out) {
+	if (!out) return fail(GBP_E_INVALID, "out is NULL");
+	*out = nullptr;
+	if (nx < 2 || ny < 2 || !x || !y || !z) return fail(GBP_E_INVALID, "terrain needs nx,ny >= 2 and x,y,z");
+	for (int i = 0; i + 1 < nx; ++i) if (!(x[i] < x[i + 1])) return fail(GBP_E_INVALID, "x axis must be strictly increasing");
+	for (int i = 0; i + 1 < ny; ++i) if (!(y[i] < y[i + 1])) return fail(GBP_E_INVALID, "y axis must be strictly increasing");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(GBP_E_CUDA, "no CUDA device (this library has no CPU fallback)");
+	gbp_terrain *t = new gbp_terrain();
+	const size_t cells = (size_t) nx * ny;
+	t->hx.assign(x, x + nx);
+	t->hy.assign(y, y + ny);
+	TerrainView &v = t->view;
+	memset(&v, 0, sizeof v);
+	v.nx = nx; v.ny = ny;
+	cudaError_t e;
+#define TRY(call) if ((e = (call)) != cudaSuccess) { gbp_terrain_destroy(t); return fail(GBP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e)); }
+	TRY(cudaMalloc(&t->d_x, nx * sizeof(double)));
+	TRY(cudaMalloc(&t->d_y, ny * sizeof(double)));
+	TRY(cudaMemcpy(t->d_x, x, nx * sizeof(double), cudaMemcpyHostToDevice));
+	TRY(cudaMemcpy(t->d_y, y, ny * sizeof(double), cudaMemcpyHostToDevice));
+	v.x = t->d_x; v.y = t->d_y;
+	v.cell_f32 = lossless_f32(z, cells) ? 1 : 0;
+	t->cell_bytes = v.cell_f32 ? 4 : 8;
+	if (v.cell_f32) {
+		std::vector<float> zf(cells);
+		for (size_t i = 0; i < cells; ++i) zf[i] = (float) z[i];
+		TRY(cudaMalloc(&t->d_z, cells * sizeof(float)));
+		TRY(cudaMemcpy(t->d_z, zf.data(), cells * sizeof(float), cudaMemcpyHostToDevice));
+	} else {
+		TRY(cudaMalloc(&t->d_z, cells * sizeof(double)));
+		TRY(cudaMemcpy(t->d_z, z, cells * sizeof(double), cudaMemcpyHostToDevice));
+	}
+	v.z = t->d_z;
+	if (dx && dy && dz) {
+		bool f32 = lossless_f32(dx, cells) && lossless_f32(dy, cells) && lossless_f32(dz, cells);
+		const double *src[3] = {dx, dy, dz};
+		if (f32) {
+			std::vector<float> nf(3 * cells);
+			for (int k = 0; k < 3; ++k) for (size_t i = 0; i < cells; ++i) nf[k * cells + i] = (float) src[k][i];
+			TRY(cudaMalloc(&t->d_n, 3 * cells * sizeof(float)));
+			TRY(cudaMemcpy(t->d_n, nf.data(), 3 * cells * sizeof(float), cudaMemcpyHostToDevice));
+			v.nz3 = (const float *) t->d_n;
+		} else {
+			TRY(cudaMalloc(&t->d_n, 3 * cells * sizeof(double)));
+			for (int k = 0; k < 3; ++k) TRY(cudaMemcpy((double *) t->d_n + k * cells, src[k], cells * sizeof(double), cudaMemcpyHostToDevice));
+			v.nz3d = (const double *) t->d_n;
+		}
+	}
+	TRY(cudaMalloc(&t->d_cnt, 6 * sizeof(unsigned long long)));
+	TRY(cudaMemset(t->d_cnt, 0, 6 * sizeof(unsigned long long)));
+#undef TRY
+	v.x0 = x[0]; v.y0 = y[0]; v.x_last = x[nx - 1]; v.y_last = y[ny - 1];
+	v.inv_dx = (nx - 1) / (x[nx - 1] - x[0]);
+	v.inv_dy = (ny - 1) / (y[ny - 1] - y[0]);
+	*out = t;
+	return GBP_OK;
+}
+
+int gbp_terrain_create_gridmap(int nx, int ny, double res, double cx, double cy, const float *elev, const float *dxl,
+							   const float *dyl, const float *dzl, gbp_terrain **out) {
+	if (nx < 2 || ny < 2 || !elev || !(res > 0)) return fail(GBP_E_INVALID, "bad grid map");
+	// fast_terrain_map.cpp:43-54: x_data[i] = position of index (nx-1-i, 0); layers flipped likewise
+	std::vector<double> x(nx), y(ny), z((size_t) nx * ny), a, b, c;
+	for (int i = 0; i < nx; ++i) x[i] = cx + (0.5 * (nx - 1) - ((nx - 1) - i)) * res;
+	for (int j = 0; j < ny; ++j) y[j] = cy + (0.5 * (ny - 1) - ((ny - 1) - j)) * res;
+	const bool normals = dxl && dyl && dzl;
+	if (normals) { a.resize(z.size()); b.resize(z.size()); c.resize(z.size()); }
+	for (int i = 0; i < nx; ++i)
+		for (int j = 0; j < ny; ++j) {
+			size_t src = (size_t) ((nx - 1) - i) * ny + ((ny - 1) - j), dst = (size_t) i * ny + j;
+			z[dst] = (double) elev[src];
+			if (normals) { a[dst] = (double) dxl[src]; b[dst] = (double) dyl[src]; c[dst] = (double) dzl[src]; }
+		}
+	return gbp_terrain_create(nx, ny, x.data(), y.data(), z.data(), normals ? a.data() : nullptr, normals ? b.data() : nullptr,
+							  normals ? c.data() : nullptr, out);
+}
+
+void gbp_terrain_destroy(gbp_terrain *t) {
+	if (!t) return;
+	cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z); cudaFree(t->d_n); cudaFree(t->d_cnt);
+	delete t;
+}
+int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes) {
+	if (!t) return fail(GBP_E_INVALID, "terrain is NULL");
+	if (nx) *nx = t->view.nx;
+	if (ny) *ny = t->view.ny;
+	if (cell_bytes) *cell_bytes = t->cell_bytes;
+	return GBP_OK;
+}
+int gbp_terrain_axes(const gbp_terrain *t, double *x, double *y) {
+	if (!t) return fail(GBP_E_INVALID, "terrain is NULL");
+	if (x) memcpy(x, t->hx.data(), t->hx.size() * sizeof(double));
+	if (y) memcpy(y, t->hy.data(), t->hy.size() * sizeof(double));
+	return GBP_OK;
+}
+
+static int terrain_query(const gbp_terrain *t, int64_t n, const double *x, const double *y, int what, double *out, uint8_t *out8) {
+	if (!t || n < 0 || (n && (!x || !y))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev dx(st), dy(st), dout(st), dout8(st);
+	int rc;
+	if ((rc = upload(dx, x, n, st)) || (rc = upload(dy, y, n, st))) return rc;
+	const size_t per = what == 2 ? 3 : 1;
+	if (out) CU(dout.alloc(n * per * sizeof(double)));
+	if (out8) CU(dout8.alloc(n));
+	if (t->view.cell_f32) k_terrain_query<float><<<blocks_for(n, 256), 256, 0, st>>>(t->view, n, dx.as<double>(), dy.as<double>(), what, dout.as<double>(), dout8.as<uint8_t>());
+	else k_terrain_query<double><<<blocks_for(n, 256), 256, 0, st>>>(t->view, n, dx.as<double>(), dy.as<double>(), what, dout.as<double>(), dout8.as<uint8_t>());
+	CU(cudaGetLastError());
+	if (out) CU(cudaMemcpyAsync(out, dout.p, n * per * sizeof(double), cudaMemcpyDeviceToHost, st));
+	if (out8) CU(cudaMemcpyAsync(out8, dout8.p, n, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_ground_height(const gbp_terrain *t, int64_t n, const double *x, const double *y, double *h, uint8_t *flags) {
+	if (!h) return fail(GBP_E_INVALID, "h is NULL");
+	return terrain_query(t, n, x, y, 0, h, flags);
+}
+int gbp_height_is_nan(const gbp_terrain *t, int64_t n, const double *x, const double *y, uint8_t *is_nan) {
+	if (!is_nan) return fail(GBP_E_INVALID, "is_nan is NULL");
+	return terrain_query(t, n, x, y, 1, nullptr, is_nan);
+}
+int gbp_surface_normal(const gbp_terrain *t, int64_t n, const double *x, const double *y, double *normal3) {
+	if (!normal3) return fail(GBP_E_INVALID, "normal3 is NULL");
+	return terrain_query(t, n, x, y, 2, normal3, nullptr);
+}
+
+// ---------------------------------------------------------------------------------- primitives
+int gbp_propagate(int kind, int64_t n, const double *states, const double *actions, const double *t, double *out) {
+	if (kind < 0 || kind > 2 || n < 0 || (n && (!states || !t || !out || (kind != 1 && !actions)))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev ds(st), da(st), dt(st), dout(st);
+	int rc;
+	if ((rc = upload(ds, states, 8 * n, st)) || (rc = upload(dt, t, n, st))) return rc;
+	if (kind != 1 && (rc = upload(da, actions, 10 * n, st))) return rc;
+	CU(dout.alloc(8 * n * sizeof(double)));
+	k_propagate<<<blocks_for(n, 256), 256, 0, st>>>(kind, n, ds.as<double>(), da.as<double>(), dt.as<double>(), dout.as<double>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out, dout.p, 8 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_valid_actions(int64_t n, const double *actions, uint8_t *verdict) {
+	if (n < 0 || (n && (!actions || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev da(st), dv(st);
+	int rc;
+	if ((rc = upload(da, actions, 10 * n, st))) return rc;
+	CU(dv.alloc(n));
+	k_valid_actions<<<blocks_for(n, 256), 256, 0, st>>>(n, da.as<double>(), dv.as<uint8_t>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(verdict, dv.p, n, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_valid_states(const gbp_terrain *t, int64_t n, const double *states, const uint8_t *phase, uint8_t *verdict, uint8_t *flags) {
+	if (!t || n < 0 || (n && (!states || !phase || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev ds(st), dp(st), dv(st), df(st);
+	int rc;
+	if ((rc = upload(ds, states, 8 * n, st)) || (rc = upload(dp, phase, n, st))) return rc;
+	CU(dv.alloc(n));
+	if (flags) CU(df.alloc(n));
+	if (t->view.cell_f32) k_valid_states<float><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, ds.as<double>(), dp.as<uint8_t>(), dv.as<uint8_t>(), df.as<uint8_t>());
+	else k_valid_states<double><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, ds.as<double>(), dp.as<uint8_t>(), dv.as<uint8_t>(), df.as<uint8_t>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(verdict, dv.p, n, cudaMemcpyDeviceToHost, st));
+	if (flags) CU(cudaMemcpyAsync(flags, df.p, n, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_distance(int kind, int64_t n, const double *q1, const double *q2, double *out) {
+	if (kind < 0 || kind > 2 || n < 0 || (n && (!q1 || !q2 || !out))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev a(st), b(st), o(st);
+	int rc;
+	if ((rc = upload(a, q1, 8 * n, st)) || (rc = upload(b, q2, 8 * n, st))) return rc;
+	CU(o.alloc(n * sizeof(double)));
+	k_distance<<<blocks_for(n, 256), 256, 0, st>>>(kind, n, a.as<double>(), b.as<double>(), o.as<double>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out, o.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+
+// ------------------------------------------------------------------------------ validate_pairs
+int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
+						   int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream) {
+	if (!t || n < 0 || (n && (!states || !actions || !direction || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
+	if (variant < 0 || variant > 3) return fail(GBP_E_INVALID, "variant must be 0..3");
+	if (variant == 2 && adaptive) return fail(GBP_E_INVALID, "variant 2 (warp per action) supports the fixed step only");
+	cudaStream_t st = (cudaStream_t) stream;
+	CU(cudaMemsetAsync(t->d_cnt, 0, 6 * sizeof(unsigned long long), st));
+	if (n == 0) return GBP_OK;
+	if (variant == 0) variant = 3;
+	const bool f32 = t->view.cell_f32 != 0;
+	if (variant == 1) {
+		if (f32) k_validate_thread<float><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
+		else k_validate_thread<double><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
+	} else if (variant == 2) {
+		const int64_t warps_per_block = 4;
+		unsigned grid = (unsigned) ((n + warps_per_block - 1) / warps_per_block);
+		if (f32) k_validate_warp<float><<<grid, 128, 0, st>>>(t->view, n, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt);
+		else k_validate_warp<double><<<grid, 128, 0, st>>>(t->view, n, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt);
+	} else {
+		// persistent-style geometry: a multiple of the SM count; each warp owns a contiguous range
+		const int threads = 128, warps_per_block = threads / 32;
+		int64_t max_warps = (int64_t) sm_count() * 16;  // 16 resident warps per SM at this register budget
+		int64_t per_warp = (n + max_warps - 1) / max_warps;
+		if (per_warp < 64) per_warp = 64;
+		int64_t warps = (n + per_warp - 1) / per_warp;
+		unsigned grid = (unsigned) ((warps + warps_per_block - 1) / warps_per_block);
+		if (f32) k_validate_refill<float><<<grid, threads, 0, st>>>(t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
+		else k_validate_refill<double><<<grid, threads, 0, st>>>(t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
+	}
+	CU(cudaGetLastError());
+	return GBP_OK;
+}
+
+int gbp_validate_counters(const gbp_terrain *t, int64_t counters6[6]) {
+	if (!t || !counters6) return fail(GBP_E_INVALID, "bad arguments");
+	CU(cudaDeviceSynchronize());
+	unsigned long long h[6];
+	CU(cudaMemcpy(h, t->d_cnt, sizeof h, cudaMemcpyDeviceToHost));
+	for (int i = 0; i < 6; ++i) counters6[i] = (int64_t) h[i];
+	return GBP_OK;
+}
+
+// HOST buffers: chunks of candidates flow through NBUF device buffer sets, each on its own stream, so
+// the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap.
+int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
+					   int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new) {
+	if (!t || n < 0 || (n && (!states || !actions || !direction || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	constexpr int NBUF = 3;
+	const int64_t chunk = n < (1 << 20) ? n : (1 << 20);
+	struct Set { cudaStream_t st = nullptr; char *in = nullptr, *out = nullptr; unsigned long long *cnt = nullptr; } sets[NBUF];
+	const size_t in_bytes = (size_t) chunk * (64 + 80 + 1), out_bytes = (size_t) chunk * (64 + 8 + 1 + 1);
+	const int nsets = (int) ((n + chunk - 1) / chunk < NBUF ? (n + chunk - 1) / chunk : NBUF);
+	int rc = GBP_OK;
+	unsigned long long total[6] = {0, 0, 0, 0, 0, 0};
+	std::vector<unsigned long long> hcnt((size_t) 6 * ((n + chunk - 1) / chunk));
+	gbp_terrain shadow = *t;  // per-set counter buffers, same view
+	auto cleanup = [&]() {
+		for (int k = 0; k < NBUF; ++k) {
+			if (sets[k].st) cudaStreamSynchronize(sets[k].st);
+			cudaFree(sets[k].in); cudaFree(sets[k].out); cudaFree(sets[k].cnt);
+			if (sets[k].st) cudaStreamDestroy(sets[k].st);
+		}
+	};
+#define TRYC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(GBP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+	for (int k = 0; k < nsets; ++k) {
+		TRYC(cudaStreamCreateWithFlags(&sets[k].st, cudaStreamNonBlocking));
+		TRYC(cudaMalloc(&sets[k].in, in_bytes));
+		TRYC(cudaMalloc(&sets[k].out, out_bytes));
+		TRYC(cudaMalloc(&sets[k].cnt, 6 * sizeof(unsigned long long)));
+	}
+	int64_t ci = 0;
+	for (int64_t off = 0; off < n; off += chunk, ++ci) {
+		Set &S = sets[ci % nsets];
+		const int64_t m = n - off < chunk ? n - off : chunk;
+		double *d_s = (double *) S.in, *d_a = (double *) (S.in + (size_t) chunk * 64);
+		uint8_t *d_d = (uint8_t *) (S.in + (size_t) chunk * 144);
+		double *d_sn = (double *) S.out, *d_tn = (double *) (S.out + (size_t) chunk * 64);
+		uint8_t *d_v = (uint8_t *) (S.out + (size_t) chunk * 72), *d_f = d_v + chunk;
+		TRYC(cudaMemcpyAsync(d_s, states + 8 * off, (size_t) m * 64, cudaMemcpyHostToDevice, S.st));
+		TRYC(cudaMemcpyAsync(d_a, actions + 10 * off, (size_t) m * 80, cudaMemcpyHostToDevice, S.st));
+		TRYC(cudaMemcpyAsync(d_d, direction + off, (size_t) m, cudaMemcpyHostToDevice, S.st));
+		shadow.d_cnt = S.cnt;
+		rc = gbp_validate_pairs_dev(&shadow, m, d_s, d_a, d_d, adaptive, variant, d_v, flags ? d_f : nullptr, s_new ? d_sn : nullptr,
+									t_new ? d_tn : nullptr, S.st);
+		if (rc) { cleanup(); return rc; }
+		TRYC(cudaMemcpyAsync(verdict + off, d_v, (size_t) m, cudaMemcpyDeviceToHost, S.st));
+		if (flags) TRYC(cudaMemcpyAsync(flags + off, d_f, (size_t) m, cudaMemcpyDeviceToHost, S.st));
+		if (s_new) TRYC(cudaMemcpyAsync(s_new + 8 * off, d_sn, (size_t) m * 64, cudaMemcpyDeviceToHost, S.st));
+		if (t_new) TRYC(cudaMemcpyAsync(t_new + off, d_tn, (size_t) m * 8, cudaMemcpyDeviceToHost, S.st));
+		TRYC(cudaMemcpyAsync(hcnt.data() + 6 * ci, S.cnt, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, S.st));
+	}
+	for (int k = 0; k < nsets; ++k) TRYC(cudaStreamSynchronize(sets[k].st));
+	for (int64_t c = 0; c < ci; ++c) for (int i = 0; i < 6; ++i) total[i] += hcnt[6 * c + i];
+	TRYC(cudaMemcpy(t->d_cnt, total, sizeof total, cudaMemcpyHostToDevice));
+#undef TRYC
+	cleanup();
+	return GBP_OK;
+}
+
+// ------------------------------------------------------------------------------------ samplers
+int gbp_sample_actions_dev(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, const double *normal3_host, double *actions,
+						   void *cuda_stream) {
+	if (n < 0 || (n && !actions)) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	double n0 = 0, n1 = 0, n2 = 1;
+	if (normal3_host) { n0 = normal3_host[0]; n1 = normal3_host[1]; n2 = normal3_host[2]; }
+	k_sample_actions<<<blocks_for(n, 256), 256, 0, (cudaStream_t) cuda_stream>>>(seed, stream, idx0, n, n0, n1, n2, 0, 0.0, nullptr, nullptr, actions);
+	CU(cudaGetLastError());
+	return GBP_OK;
+}
+int gbp_sample_actions(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, const double *normal3, const double *s_from,
+					   const double *s_to, double dir_threshold, double *actions) {
+	if (n < 0 || (n && !actions)) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev da(st), df(st), dt(st);
+	CU(da.alloc(10 * n * sizeof(double)));
+	const int dir = (s_from && s_to) ? 1 : 0;
+	int rc;
+	if (dir && ((rc = upload(df, s_from, 8, st)) || (rc = upload(dt, s_to, 8, st)))) return rc;
+	double n0 = 0, n1 = 0, n2 = 1;
+	if (normal3) { n0 = normal3[0]; n1 = normal3[1]; n2 = normal3[2]; }
+	k_sample_actions<<<blocks_for(n, 256), 256, 0, st>>>(seed, stream, idx0, n, n0, n1, n2, dir, dir_threshold, df.as<double>(), dt.as<double>(), da.as<double>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(actions, da.p, 10 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+static int sample_states_launch(const gbp_terrain *t, uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, int dir, double thr,
+								int speed, const double *d_from, const double *d_to, double *d_out, cudaStream_t st) {
+	if (t->view.cell_f32) k_sample_states<float><<<blocks_for(n, 256), 256, 0, st>>>(t->view, seed, stream, idx0, n, dir, thr, speed, d_from, d_to, d_out);
+	else k_sample_states<double><<<blocks_for(n, 256), 256, 0, st>>>(t->view, seed, stream, idx0, n, dir, thr, speed, d_from, d_to, d_out);
+	CU(cudaGetLastError());
+	return GBP_OK;
+}
+int gbp_sample_states_dev(const gbp_terrain *t, uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, double *states, void *cuda_stream) {
+	if (!t || n < 0 || (n && !states)) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	return sample_states_launch(t, seed, stream, idx0, n, 0, 0.0, 0, nullptr, nullptr, states, (cudaStream_t) cuda_stream);
+}
+int gbp_sample_states(const gbp_terrain *t, uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, const double *s_from,
+					  const double *s_to, double dir_threshold, int speed_direction, double *states) {
+	if (!t || n < 0 || (n && !states)) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev ds(st), df(st), dt(st);
+	CU(ds.alloc(8 * n * sizeof(double)));
+	const int dir = (s_from && s_to) ? 1 : 0;
+	int rc;
+	if (dir && ((rc = upload(df, s_from, 8, st)) || (rc = upload(dt, s_to, 8, st)))) return rc;
+	if ((rc = sample_states_launch(t, seed, stream, idx0, n, dir, dir_threshold, speed_direction, df.as<double>(), dt.as<double>(), ds.as<double>(), st))) return rc;
+	CU(cudaMemcpyAsync(states, ds.p, 8 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+
+// --------------------------------------------------------------------------------- tree store
+void gbp_tree_destroy(gbp_tree *T) {
+	if (!T) return;
+	cudaFree(T->d_n); cudaFree(T->d_v); cudaFree(T->d_act); cudaFree(T->d_g); cudaFree(T->d_y); cudaFree(T->d_parent);
+	cudaFree(T->S.near_idx); cudaFree(T->S.near_dist); cudaFree(T->S.valid); cudaFree(T->S.dist); cudaFree(T->S.s_test); cudaFree(T->S.result);
+	cudaFree(T->d_target);
+	delete T;
+}
+int gbp_tree_create(int capacity, gbp_tree **out) {
+	if (!out || capacity < 1) return fail(GBP_E_INVALID, "bad arguments");
+	*out = nullptr;
+	gbp_tree *T = new gbp_tree();
+	memset(&T->S, 0, sizeof T->S);
+	cudaError_t e;
+#define TRY(call) if ((e = (call)) != cudaSuccess) { gbp_tree_destroy(T); return fail(GBP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e)); }
+	TRY(cudaMalloc(&T->d_n, sizeof(int)));
+	TRY(cudaMemset(T->d_n, 0, sizeof(int)));
+	TRY(cudaMalloc(&T->d_v, sizeof(double) * 8 * capacity));
+	TRY(cudaMalloc(&T->d_act, sizeof(double) * 10 * capacity));
+	TRY(cudaMalloc(&T->d_g, sizeof(double) * capacity));
+	TRY(cudaMalloc(&T->d_y, sizeof(double) * capacity));
+	TRY(cudaMalloc(&T->d_parent, sizeof(int) * capacity));
+	TRY(cudaMalloc(&T->S.near_idx, sizeof(int)));
+	TRY(cudaMalloc(&T->S.near_dist, sizeof(double)));
+	TRY(cudaMalloc(&T->S.result, 4 * sizeof(int)));
+	TRY(cudaMalloc(&T->d_target, 18 * sizeof(double)));
+#undef TRY
+	T->view.cap = capacity; T->view.n = T->d_n; T->view.v = T->d_v; T->view.act = T->d_act; T->view.parent = T->d_parent;
+	T->view.g = T->d_g; T->view.y = T->d_y;
+	*out = T;
+	return GBP_OK;
+}
+int gbp_tree_init(gbp_tree *T, const double *root_state) {
+	if (!T || !root_state) return fail(GBP_E_INVALID, "bad arguments");
+	cudaStream_t st = lib_stream();
+	CU(cudaMemcpyAsync(T->d_target, root_state, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+	k_tree_init<<<1, 32, 0, st>>>(T->view, T->d_target);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_tree_size(const gbp_tree *T, int *n) {
+	if (!T || !n) return fail(GBP_E_INVALID, "bad arguments");
+	CU(cudaMemcpy(n, T->d_n, sizeof(int), cudaMemcpyDeviceToHost));
+	return GBP_OK;
+}
+int gbp_tree_append(gbp_tree *T, int parent, const double *state, const double *action, int *new_id) {
+	if (!T || !state || !action) return fail(GBP_E_INVALID, "bad arguments");
+	cudaStream_t st = lib_stream();
+	CU(cudaMemcpyAsync(T->d_target, state, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(T->d_target + 8, action, 10 * sizeof(double), cudaMemcpyHostToDevice, st));
+	k_tree_append<<<1, 32, 0, st>>>(T->view, parent, T->d_target, T->d_target + 8, T->S.result);
+	CU(cudaGetLastError());
+	int id = -1;
+	CU(cudaMemcpyAsync(&id, T->S.result, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (id < 0) return fail(GBP_E_CAPACITY, "tree full or bad parent");
+	if (new_id) *new_id = id;
+	return GBP_OK;
+}
+int gbp_tree_load(gbp_tree *T, int n, const double *states, const double *actions, const int *parent) {
+	if (!T || n < 1 || !states || (n > 1 && !parent)) return fail(GBP_E_INVALID, "bad arguments");
+	if (n > T->view.cap) return fail(GBP_E_CAPACITY, "tree capacity exceeded");
+	for (int i = 1; i < n; ++i) if (parent[i] < 0 || parent[i] >= i) return fail(GBP_E_INVALID, "parent ids must precede their children");
+	cudaStream_t st = lib_stream();
+	Dev ds(st), da(st), dp(st);
+	int rc;
+	if ((rc = upload(ds, states, (size_t) 8 * n, st))) return rc;
+	if (actions && (rc = upload(da, actions, (size_t) 10 * n, st))) return rc;
+	if (n > 1) { if ((rc = upload(dp, parent, (size_t) n, st))) return rc; }
+	k_tree_load<<<blocks_for(n, 256), 256, 0, st>>>(T->view, n, ds.as<double>(), actions ? da.as<double>() : nullptr, dp.as<int>());
+	k_tree_gy<<<1, 32, 0, st>>>(T->view, n);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_tree_read(const gbp_tree *T, int first, int n, double *states, double *actions, int *parent, double *g, double *yaw) {
+	if (!T || first < 0 || n < 0) return fail(GBP_E_INVALID, "bad arguments");
+	int have = 0;
+	CU(cudaMemcpy(&have, T->d_n, sizeof(int), cudaMemcpyDeviceToHost));
+	if (first + n > have) return fail(GBP_E_INVALID, "range exceeds tree size");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev ds(st), da(st), dp(st), dg(st), dy(st);
+	if (states) CU(ds.alloc(sizeof(double) * 8 * n));
+	if (actions) CU(da.alloc(sizeof(double) * 10 * n));
+	if (parent) CU(dp.alloc(sizeof(int) * n));
+	if (g) CU(dg.alloc(sizeof(double) * n));
+	if (yaw) CU(dy.alloc(sizeof(double) * n));
+	k_tree_read<<<blocks_for(n, 256), 256, 0, st>>>(T->view, first, n, ds.as<double>(), da.as<double>(), dp.as<int>(), dg.as<double>(), dy.as<double>());
+	CU(cudaGetLastError());
+	if (states) CU(cudaMemcpyAsync(states, ds.p, sizeof(double) * 8 * n, cudaMemcpyDeviceToHost, st));
+	if (actions) CU(cudaMemcpyAsync(actions, da.p, sizeof(double) * 10 * n, cudaMemcpyDeviceToHost, st));
+	if (parent) CU(cudaMemcpyAsync(parent, dp.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+	if (g) CU(cudaMemcpyAsync(g, dg.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	if (yaw) CU(cudaMemcpyAsync(yaw, dy.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_nearest_dev(const gbp_tree *T, int64_t m, const double *queries, int *idx, double *dist, void *stream) {
+	if (!T || m < 0 || (m && (!queries || !idx))) return fail(GBP_E_INVALID, "bad arguments");
+	if (m == 0) return GBP_OK;
+	unsigned grid = (unsigned) (m < 65535 ? m : 65535);
+	k_nearest<<<grid, 256, 0, (cudaStream_t) stream>>>(T->view, m, queries, idx, dist);
+	CU(cudaGetLastError());
+	return GBP_OK;
+}
+int gbp_nearest(const gbp_tree *T, int64_t m, const double *queries, int *idx, double *dist) {
+	if (!T || m < 0 || (m && (!queries || !idx))) return fail(GBP_E_INVALID, "bad arguments");
+	if (m == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev dq(st), di(st), dd(st);
+	int rc;
+	if ((rc = upload(dq, queries, (size_t) 8 * m, st))) return rc;
+	CU(di.alloc(sizeof(int) * m));
+	CU(dd.alloc(sizeof(double) * m));
+	if ((rc = gbp_nearest_dev(T, m, dq.as<double>(), di.as<int>(), dd.as<double>(), st))) return rc;
+	CU(cudaMemcpyAsync(idx, di.p, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+	if (dist) CU(cudaMemcpyAsync(dist, dd.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_near(const gbp_tree *T, const double *query, double radius, int *ids, int cap, int *count) {
+	if (!T || !query || !count || cap < 0 || (cap && !ids)) return fail(GBP_E_INVALID, "bad arguments");
+	cudaStream_t st = lib_stream();
+	Dev dq(st), di(st), dc(st);
+	int rc;
+	if ((rc = upload(dq, query, 8, st))) return rc;
+	CU(di.alloc(sizeof(int) * (cap ? cap : 1)));
+	CU(dc.alloc(sizeof(int)));
+	k_near<<<1, 32, 0, st>>>(T->view, dq.as<double>(), radius, di.as<int>(), cap, dc.as<int>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(count, dc.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	int m = *count < cap ? *count : cap;
+	if (m > 0) CU(cudaMemcpy(ids, di.p, sizeof(int) * m, cudaMemcpyDeviceToHost));
+	return GBP_OK;
+}
+
+// -------------------------------------------------------------------------- extend / connect
+static int ensure_k(gbp_tree *T, int K) {
+	if (K <= T->k_cap) return GBP_OK;
+	cudaFree(T->S.valid); cudaFree(T->S.dist); cudaFree(T->S.s_test);
+	T->S.valid = nullptr; T->S.dist = nullptr; T->S.s_test = nullptr; T->k_cap = 0;
+	CU(cudaMalloc(&T->S.valid, K));
+	CU(cudaMalloc(&T->S.dist, sizeof(double) * K));
+	CU(cudaMalloc(&T->S.s_test, sizeof(double) * 8 * K));
+	T->k_cap = K;
+	return GBP_OK;
+}
+int gbp_extend(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int K, int best_of_k, int adaptive,
+			   uint64_t seed, uint64_t stream, uint64_t idx0, int *status, int *new_id, int64_t *pair_checks) {
+	if (!T || !t || !target || K < 1 || (direction != GBP_FORWARD && direction != GBP_REVERSE)) return fail(GBP_E_INVALID, "bad arguments");
+	int rc;
+	if ((rc = ensure_k(T, K))) return rc;
+	cudaStream_t st = lib_stream();
+	CU(cudaMemcpyAsync(T->d_target, target, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+	k_nearest<<<1, 256, 0, st>>>(T->view, 1, T->d_target, T->S.near_idx, T->S.near_dist);
+	if (t->view.cell_f32) k_extend_candidates<float><<<blocks_for(K, 128), 128, 0, st>>>(t->view, T->view, T->d_target, direction, K, adaptive, seed, stream, idx0, T->S);
+	else k_extend_candidates<double><<<blocks_for(K, 128), 128, 0, st>>>(t->view, T->view, T->d_target, direction, K, adaptive, seed, stream, idx0, T->S);
+	k_extend_select<<<1, 256, 0, st>>>(t->view, T->view, T->d_target, K, best_of_k, seed, stream, idx0, T->S);
+	CU(cudaGetLastError());
+	int res[4] = {0, -1, 0, 0};
+	CU(cudaMemcpyAsync(res, T->S.result, sizeof res, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (status) *status = res[0];
+	if (new_id) *new_id = res[1];
+	if (pair_checks) *pair_checks = res[2];
+	return GBP_OK;
+}
+int gbp_attempt_connect(const gbp_terrain *t, int64_t n, const double *s_existing, const double *s, const uint8_t *direction,
+						int adaptive, int *status, double *s_new, double *a_new, uint8_t *flags) {
+	if (!t || n < 0 || (n && (!s_existing || !s || !direction || !status || !s_new || !a_new))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev de(st), ds(st), dd(st), dst(st), dsn(st), dan(st), dfl(st);
+	int rc;
+	if ((rc = upload(de, s_existing, (size_t) 8 * n, st)) || (rc = upload(ds, s, (size_t) 8 * n, st)) || (rc = upload(dd, direction, (size_t) n, st))) return rc;
+	CU(dst.alloc(sizeof(int) * n));
+	CU(dsn.alloc(sizeof(double) * 8 * n));
+	CU(dan.alloc(sizeof(double) * 10 * n));
+	if (flags) CU(dfl.alloc(n));
+	if (t->view.cell_f32) k_attempt_connect<float><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, de.as<double>(), ds.as<double>(), dd.as<uint8_t>(), adaptive, dst.as<int>(), dsn.as<double>(), dan.as<double>(), dfl.as<uint8_t>());
+	else k_attempt_connect<double><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, de.as<double>(), ds.as<double>(), dd.as<uint8_t>(), adaptive, dst.as<int>(), dsn.as<double>(), dan.as<double>(), dfl.as<uint8_t>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(status, dst.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(s_new, dsn.p, sizeof(double) * 8 * n, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(a_new, dan.p, sizeof(double) * 10 * n, cudaMemcpyDeviceToHost, st));
+	if (flags) CU(cudaMemcpyAsync(flags, dfl.p, n, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_connect(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int adaptive, int *status, int *new_id) {
+	if (!T || !t || !target || (direction != GBP_FORWARD && direction != GBP_REVERSE)) return fail(GBP_E_INVALID, "bad arguments");
+	cudaStream_t st = lib_stream();
+	CU(cudaMemcpyAsync(T->d_target, target, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+	k_nearest<<<1, 256, 0, st>>>(T->view, 1, T->d_target, T->S.near_idx, T->S.near_dist);
+	if (t->view.cell_f32) k_connect<float><<<1, 32, 0, st>>>(t->view, T->view, T->d_target, direction, adaptive, T->S);
+	else k_connect<double><<<1, 32, 0, st>>>(t->view, T->view, T->d_target, direction, adaptive, T->S);
+	CU(cudaGetLastError());
+	int res[4] = {0, -1, 0, 0};
+	CU(cudaMemcpyAsync(res, T->S.result, sizeof res, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (status) *status = res[0];
+	if (new_id) *new_id = res[1];
+	return GBP_OK;
+}
+
+// ------------------------------------------------------------------------------ batch planner
+int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+					   const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap,
+					   void *stream) {
+	if (!t || nq < 0 || !p || (nq && (!starts || !goals || !stats))) return fail(GBP_E_INVALID, "bad arguments");
+	if (p->k_candidates < 1 || p->max_iters < 0 || p->max_vertices < 2) return fail(GBP_E_INVALID, "bad plan parameters");
+	if (nq == 0) return GBP_OK;
+	std::string err;
+	int rc = plan_batch_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, (cudaStream_t) stream, err);
+	if (rc) return fail(rc, err);
+	return GBP_OK;
+}
+int gbp_plan_batch(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+				   const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap) {
+	if (!t || nq < 0 || !p || (nq && (!starts || !goals || !stats))) return fail(GBP_E_INVALID, "bad arguments");
+	if (nq == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev ds(st), dg(st), dst(st), dps(st), dpa(st);
+	int rc;
+	if ((rc = upload(ds, starts, (size_t) 8 * nq, st)) || (rc = upload(dg, goals, (size_t) 8 * nq, st))) return rc;
+	CU(dst.alloc(sizeof(gbp_plan_stats) * nq));
+	const bool want_paths = path_states && path_actions && path_cap > 0;
+	if (want_paths) {
+		CU(dps.alloc(sizeof(double) * 8 * (size_t) path_cap * nq));
+		CU(dpa.alloc(sizeof(double) * 10 * (size_t) path_cap * nq));
+	}
+	if ((rc = gbp_plan_batch_dev(t, nq, ds.as<double>(), dg.as<double>(), seed, query0, p, dst.as<gbp_plan_stats>(),
+								 want_paths ? dps.as<double>() : nullptr, want_paths ? dpa.as<double>() : nullptr, path_cap, st)))
+		return rc;
+	CU(cudaMemcpyAsync(stats, dst.p, sizeof(gbp_plan_stats) * nq, cudaMemcpyDeviceToHost, st));
+	if (want_paths) {
+		CU(cudaMemcpyAsync(path_states, dps.p, sizeof(double) * 8 * (size_t) path_cap * nq, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(path_actions, dpa.p, sizeof(double) * 10 * (size_t) path_cap * nq, cudaMemcpyDeviceToHost, st));
+	}
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,417 @@
+// Device-side building blocks of the extend path (sm_100a).  fp64, no FMA contraction (the
+// translation unit is compiled with -fmad=false), expressions in the reference's operation order so
+// that propagated states, distances and indices are bit-identical to the reference's x86-64 results.
+// Citations: file:line under the reference root (LiuShenLan/global_body_planner).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gbp_b200.h"
+
+namespace gbp {
+
+// ---- robot / planner constants (include/global_body_planner/planning_utils.h:21-54)
+constexpr double H_MAX = 0.4, H_MIN = 0.075, V_MAX = 2.0, V_NOM = 0.75, P_MAX = 1.0, ANG_ACC_MAX = 7.0;
+constexpr double ROBOT_L = 0.3, ROBOT_W = 0.3, ROBOT_H = 0.05;
+constexpr double M_CONST = 13.0, G_CONST = 9.81, F_MAX = 637.0, MU = 1.0, T_F_MIN = 0.0, T_F_MAX = 0.5;
+constexpr double KINEMATICS_RES = 0.05, BACKUP_RATIO = 0.5, GOAL_BOUNDS = 0.5, MY_PI = 3.14159;
+constexpr double RRT_STAR_DELTA = 3.0;  // rrt_star_connect.h:59
+constexpr double NEAR_MARGIN = 1e-9;    // GBP_FLAG_NEAR guard band, metres
+
+// ---- device-resident FastTerrainMap (fast_terrain_map.h:97-118) as SoA grids.
+// Height cells are CellT = float when the fp64 input converts losslessly, else double.
+struct TerrainView {
+	int nx, ny;
+	const double *x, *y;  // axes, strictly increasing
+	const void *z;        // [nx][ny] x-major, float or double (cell_f32)
+	const float *nz3;     // [3][nx][ny] normal layers dx, dy, dz (fp32 when lossless) or null
+	const double *nz3d;   // fp64 normal layers when not lossless
+	int cell_f32;
+	double x0, y0, x_last, y_last;  // axis end points (bounds test of isValidState, OOG test)
+	double inv_dx, inv_dy;          // O(1) cell guess: i ~ (v - x0) * inv_dx
+};
+
+struct Counters {  // work under the reference's early-exit semantics, per candidate
+	unsigned substates, lookups, nanprobes, flags;
+};
+
+// ---- Philox4x32-10 stream spec (see include/gbp_b200.h)
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+											  uint32_t w[4]) {
+#pragma unroll
+	for (int r = 0; r < 10; ++r) {
+		uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+		uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+		uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+		c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+		k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+	}
+	w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+	return ((double) (hi >> 5) * 67108864.0 + (double) (lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+// uniforms 2*block and 2*block+1 of cell (seed, stream, idx, purpose)
+__device__ __forceinline__ void uniform_pair(uint64_t seed, uint64_t stream, uint64_t idx, int purpose, int block, double &ua,
+											 double &ub) {
+	uint32_t w[4];
+	philox4x32_10((uint32_t) idx, (uint32_t) (idx >> 32), (uint32_t) stream,
+				  ((uint32_t) (stream >> 32) & 0x00ffffffu) | ((uint32_t) block << 24) | ((uint32_t) purpose << 28),
+				  (uint32_t) seed, (uint32_t) (seed >> 32), w);
+	ua = u53(w[0], w[1]);
+	ub = u53(w[2], w[3]);
+}
+
+// ---- deterministic elementary functions of the sampler spec (+ - * / only; oracle/gbp_oracle.c has
+// the same operation sequence, so both sides produce identical bits).
+__device__ __forceinline__ double det_log(double x) {
+	long long b = __double_as_longlong(x);
+	int e = (int) ((b >> 52) & 0x7ff) - 1023;
+	double m = __longlong_as_double((b & 0x000fffffffffffffll) | 0x3ff0000000000000ll);
+	if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+	double f = m - 1.0, s = f / (2.0 + f), z = s * s;
+	double p = 1.0 / 23.0;
+	p = p * z + 1.0 / 21.0; p = p * z + 1.0 / 19.0; p = p * z + 1.0 / 17.0; p = p * z + 1.0 / 15.0;
+	p = p * z + 1.0 / 13.0; p = p * z + 1.0 / 11.0; p = p * z + 1.0 / 9.0;  p = p * z + 1.0 / 7.0;
+	p = p * z + 1.0 / 5.0;  p = p * z + 1.0 / 3.0;  p = p * z + 1.0;
+	double lm = 2.0 * s * p;
+	return (double) e * 6.93147180369123816490e-01 + ((double) e * 1.90821492927058770002e-10 + lm);
+}
+__device__ __forceinline__ void det_sincos(double x, double &sn, double &cs) {
+	double qf = floor(x * 0.63661977236758134308 + 0.5);
+	int q = (int) qf;
+	double r = (x - qf * 1.57079632673412561417e+00) - qf * 6.07710050650619224932e-11;
+	double z = r * r;
+	double ps = -1.0 / 355687428096000.0;
+	ps = ps * z + 1.0 / 1307674368000.0; ps = ps * z - 1.0 / 6227020800.0; ps = ps * z + 1.0 / 39916800.0;
+	ps = ps * z - 1.0 / 362880.0; ps = ps * z + 1.0 / 5040.0; ps = ps * z - 1.0 / 120.0; ps = ps * z + 1.0 / 6.0;
+	double s = r - r * z * ps;
+	double pc = 1.0 / 20922789888000.0;
+	pc = pc * z - 1.0 / 87178291200.0; pc = pc * z + 1.0 / 479001600.0; pc = pc * z - 1.0 / 3628800.0;
+	pc = pc * z + 1.0 / 40320.0; pc = pc * z - 1.0 / 720.0; pc = pc * z + 1.0 / 24.0; pc = pc * z - 0.5;
+	double c = 1.0 + z * pc;
+	switch (q & 3) {
+	case 0: sn = s; cs = c; break;
+	case 1: sn = c; cs = -s; break;
+	case 2: sn = -s; cs = -c; break;
+	default: sn = -c; cs = s; break;
+	}
+}
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ void box_muller(double ua, double ub, double &z0, double &z1) {
+	double r = sqrt(-2.0 * det_log(1.0 - ua)), sn, cs;
+	det_sincos(6.283185307179586 * ub, sn, cs);
+	z0 = r * cs;
+	z1 = r * sn;
+}
+
+// ---- terrain lookups (src/fast_terrain_map.cpp)
+// Cell search of :101-117 — first i with ax[i] <= v < ax[i+1] — done as an O(1) guess plus a
+// compare fix-up against the same fp64 axis values (bisection if the axis is not uniform), so the
+// chosen cell is exactly the reference's.  Out of [ax[0], ax[n-1]) -> cell 0 + GBP_FLAG_OOG.
+__device__ __forceinline__ int find_cell(const double *__restrict__ ax, int n, double v, double a0, double alast, double inv,
+										 unsigned &flags, double &lo_v, double &hi_v) {
+	int i = 0;
+	if (!(v >= a0) || !(v < alast)) {
+		flags |= GBP_FLAG_OOG;
+	} else {
+		double g = (v - a0) * inv;
+		i = (int) g;
+		i = max(0, min(i, n - 2));
+		double a = __ldg(ax + i), b = __ldg(ax + i + 1);
+		if (a <= v && v < b) { lo_v = a; hi_v = b; return i; }
+		if (v < a && i > 0 && __ldg(ax + i - 1) <= v) { --i; }
+		else if (v >= b && i < n - 2 && v < __ldg(ax + i + 2)) { ++i; }
+		else {  // non-uniform axis: bisection on ax[lo] <= v < ax[hi]
+			int lo = 0, hi = n - 1;
+			while (hi - lo > 1) {
+				int mid = (lo + hi) >> 1;
+				if (__ldg(ax + mid) <= v) lo = mid; else hi = mid;
+			}
+			i = lo;
+		}
+	}
+	lo_v = __ldg(ax + i);
+	hi_v = __ldg(ax + i + 1);
+	return i;
+}
+
+template <typename CellT>
+struct Quad { double f11, f12, f21, f22; };
+
+template <typename CellT>
+__device__ __forceinline__ void load_quad(const CellT *__restrict__ layer, int ny, int ix, int iy, double &f11, double &f12,
+										  double &f21, double &f22) {
+	const CellT *p = layer + (size_t) ix * ny + iy;
+	f11 = (double) __ldg(p);
+	f12 = (double) __ldg(p + 1);
+	f21 = (double) __ldg(p + ny);
+	f22 = (double) __ldg(p + ny + 1);
+}
+// bilinear form of :120-126, left to right as written
+__device__ __forceinline__ double bilinear(double f11, double f12, double f21, double f22, double x1, double x2, double y1,
+										   double y2, double x, double y) {
+	return 1.0 / ((x2 - x1) * (y2 - y1)) *
+		   (f11 * (x2 - x) * (y2 - y) + f21 * (x - x1) * (y2 - y) + f12 * (x2 - x) * (y - y1) + f22 * (x - x1) * (y - y1));
+}
+
+template <typename CellT>
+__device__ __forceinline__ double ground_height(const TerrainView &T, double x, double y, unsigned &flags) {  // :94-132
+	double x1, x2, y1, y2, f11, f12, f21, f22;
+	int ix = find_cell(T.x, T.nx, x, T.x0, T.x_last, T.inv_dx, flags, x1, x2);
+	int iy = find_cell(T.y, T.ny, y, T.y0, T.y_last, T.inv_dy, flags, y1, y2);
+	load_quad<CellT>((const CellT *) T.z, T.ny, ix, iy, f11, f12, f21, f22);
+	return bilinear(f11, f12, f21, f22, x1, x2, y1, y2, x, y);
+}
+// heightIsNan (:135-157) and getGroundHeight of the SAME point share one cell search and one quad
+template <typename CellT>
+__device__ __forceinline__ bool nan_and_height(const TerrainView &T, double x, double y, unsigned &flags, double &h) {
+	double x1, x2, y1, y2, f11, f12, f21, f22;
+	int ix = find_cell(T.x, T.nx, x, T.x0, T.x_last, T.inv_dx, flags, x1, x2);
+	int iy = find_cell(T.y, T.ny, y, T.y0, T.y_last, T.inv_dy, flags, y1, y2);
+	load_quad<CellT>((const CellT *) T.z, T.ny, ix, iy, f11, f12, f21, f22);
+	h = bilinear(f11, f12, f21, f22, x1, x2, y1, y2, x, y);
+	return (f11 != f11) || (f12 != f12) || (f21 != f21) || (f22 != f22);
+}
+template <typename CellT>
+__device__ __forceinline__ bool height_is_nan(const TerrainView &T, double x, double y, unsigned &flags) {
+	double h;
+	return nan_and_height<CellT>(T, x, y, flags, h);
+}
+__device__ __forceinline__ void surface_normal(const TerrainView &T, double x, double y, double n[3], unsigned &flags) {  // :160-213
+	double x1, x2, y1, y2, f11, f12, f21, f22;
+	int ix = find_cell(T.x, T.nx, x, T.x0, T.x_last, T.inv_dx, flags, x1, x2);
+	int iy = find_cell(T.y, T.ny, y, T.y0, T.y_last, T.inv_dy, flags, y1, y2);
+	size_t plane = (size_t) T.nx * T.ny;
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		if (T.nz3) load_quad<float>(T.nz3 + k * plane, T.ny, ix, iy, f11, f12, f21, f22);
+		else if (T.nz3d) load_quad<double>(T.nz3d + k * plane, T.ny, ix, iy, f11, f12, f21, f22);
+		else { f11 = f12 = f21 = f22 = (k == 2) ? 1.0 : 0.0; }
+		n[k] = bilinear(f11, f12, f21, f22, x1, x2, y1, y2, x, y);
+	}
+}
+
+// ---- primitives (src/planning_utils.cpp)
+__device__ __forceinline__ void apply_stance(const double s[8], const double a[10], double t, double o[8]) {  // :237-274
+	double ts = a[6];
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		o[d] = s[d] + s[3 + d] * t + 0.5 * a[d] * t * t + (a[3 + d] - a[d]) * (t * t * t) / (6.0 * ts);
+		o[3 + d] = s[3 + d] + a[d] * t + (a[3 + d] - a[d]) * t * t / (2.0 * ts);
+	}
+	o[6] = s[6] + s[7] * t + 0.5 * a[8] * t * t + (a[9] - a[8]) * (t * t * t) / (6.0 * ts);
+	o[7] = s[7] + a[8] * t + (a[9] - a[8]) * t * t / (2.0 * ts);
+}
+__device__ __forceinline__ void apply_flight(const double s[8], double t, double o[8]) {  // :282-306 (literal g = 9.81)
+	double g = 9.81;
+	o[0] = s[0] + s[3] * t;
+	o[1] = s[1] + s[4] * t;
+	o[2] = s[2] + s[5] * t - 0.5 * g * t * t;
+	o[3] = s[3];
+	o[4] = s[4];
+	o[5] = s[5] - g * t;
+	o[6] = s[6] + s[7] * t;
+	o[7] = s[7];
+}
+__device__ __forceinline__ void apply_stance_reverse(const double s[8], const double a[10], double t, double o[8]) {  // :324-367
+	double ts = a[6];
+#pragma unroll
+	for (int d = 0; d < 4; ++d) {
+		const int ip = d < 3 ? d : 6, iv = d < 3 ? 3 + d : 7, itd = d < 3 ? d : 8, ito = d < 3 ? 3 + d : 9;
+		double c = s[iv] - a[itd] * ts - 0.5 * (a[ito] - a[itd]) * ts;
+		o[ip] = s[ip] - c * (ts - t) - 0.5 * a[itd] * (ts * ts - t * t) - (a[ito] - a[itd]) * (ts * ts * ts - t * t * t) / (6.0 * ts);
+		o[iv] = s[iv] - a[itd] * (ts - t) - (a[ito] - a[itd]) * (ts * ts - t * t) / (2.0 * ts);
+	}
+}
+
+// rotate_grf (:198-231): Rodrigues matrix taking +z to n, built once per extend.
+__device__ __forceinline__ void grf_rotation(const double n[3], double R[9]) {
+	double zs0 = 0.0, zs1 = 0.0, zs2 = 1.0;
+	double v0 = n[1] * zs2 - n[2] * zs1, v1 = n[2] * zs0 - n[0] * zs2, v2 = n[0] * zs1 - n[1] * zs0;
+	double s = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+	double c = n[0] * zs0 + n[1] * zs1 + n[2] * zs2;
+	R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+	if (!(s < 0.000001)) {
+		double K[9] = {0, -v2, v1, v2, 0, -v0, -v1, v0, 0}, KK[9];
+#pragma unroll
+		for (int i = 0; i < 3; ++i)
+#pragma unroll
+			for (int j = 0; j < 3; ++j) KK[3 * i + j] = K[3 * i] * K[j] + K[3 * i + 1] * K[3 + j] + K[3 * i + 2] * K[6 + j];
+#pragma unroll
+		for (int i = 0; i < 9; ++i) R[i] = (R[i] + K[i]) + KK[i] * (1 - c) / (s * s);
+	}
+}
+__device__ __forceinline__ void mat3_apply(const double R[9], const double f[3], double o[3]) {
+#pragma unroll
+	for (int i = 0; i < 3; ++i) o[i] = R[3 * i] * f[0] + R[3 * i + 1] * f[1] + R[3 * i + 2] * f[2];
+}
+
+__device__ __forceinline__ bool is_valid_action(const double a[10]) {  // :519-556
+	if (a[6] <= 0 || a[7] < 0) return false;
+	double m = M_CONST, g = G_CONST, mu = MU;
+	double fxd = m * a[0], fyd = m * a[1], fzd = m * (a[2] + g), fxo = m * a[3], fyo = m * a[4], fzo = m * (a[5] + g);
+	if (sqrt(fxd * fxd + fyd * fyd + fzd * fzd) >= F_MAX || sqrt(fxo * fxo + fyo * fyo + fzo * fzo) >= F_MAX || fzd < 0 ||
+		fzo < 0 || a[8] >= F_MAX || a[9] >= F_MAX)  // sic (:543): pitch accel against F_MAX, no abs
+		return false;
+	if (sqrt(fxd * fxd + fyd * fyd) >= mu * fzd || sqrt(fxo * fxo + fyo * fyo) >= mu * fzo) return false;
+	return true;
+}
+
+__device__ __forceinline__ void note_margin(double m, unsigned &flags) {
+	if (fabs(m) < NEAR_MARGIN) flags |= GBP_FLAG_NEAR;
+}
+
+// isValidState (:562-635).  Check order and early returns follow the reference, so the counters
+// and the OOG flag describe exactly the probes the reference would have made.
+template <typename CellT>
+__device__ __forceinline__ bool is_valid_state(const TerrainView &T, const double s[8], int phase, Counters &c) {
+	c.substates++;
+	c.nanprobes++;
+	double h_c;
+	// the centre cell search also serves the map-bounds test below
+	if (nan_and_height<CellT>(T, s[0], s[1], c.flags, h_c)) return false;
+	if (s[0] < T.x0 || s[0] > T.x_last || s[1] < T.y0 || s[1] > T.y_last || fabs(s[6]) >= P_MAX)
+		return false;
+	if (sqrt(s[3] * s[3] + s[4] * s[4]) > V_MAX) return false;
+	double yaw = atan2(s[4], s[3]);
+	double sy, cy, sp, cp;
+	sincos(yaw, &sy, &cy);
+	sincos(s[6], &sp, &cp);
+	double R11 = cy * cp, R12 = -sy, R13 = cy * sp, R21 = sy * cp, R22 = cy, R23 = sy * sp, R31 = -sp, R32 = 0, R33 = cp;
+	const double zb = -ROBOT_H;
+#pragma unroll
+	for (int i = 0; i < 2; ++i) {
+#pragma unroll
+		for (int j = 0; j < 2; ++j) {
+			const double xb = i == 0 ? -0.5 * ROBOT_L : 0.5 * ROBOT_L, yb = j == 0 ? -0.5 * ROBOT_W : 0.5 * ROBOT_W;
+			double xl = s[0] + R11 * xb + R12 * yb, yl = s[1] + R21 * xb + R22 * yb, zl = s[2] + R31 * xb + R32 * yb;
+			double xc = xl + R13 * zb, yc = yl + R23 * zb, zc = zl + R33 * zb;
+			double h_leg;
+			c.nanprobes++;
+			if (nan_and_height<CellT>(T, xl, yl, c.flags, h_leg)) return false;
+			c.lookups += 2;
+			double leg_h = zl - h_leg;
+			double cor_h = zc - ground_height<CellT>(T, xc, yc, c.flags);
+			note_margin(cor_h - H_MIN, c.flags);
+			if (phase == GBP_STANCE) note_margin(leg_h - H_MAX, c.flags);
+			if (cor_h < H_MIN || (phase == GBP_STANCE && leg_h > H_MAX)) return false;
+		}
+	}
+	c.lookups += 1;
+	double h = (s[2] + R33 * zb) - ground_height<CellT>(T, s[0] + R13 * zb, s[1] + R23 * zb, c.flags);
+	note_margin(h - H_MIN, c.flags);
+	return !(h < H_MIN);
+}
+
+// ---- distances (:106-127, planning_utils.h:133-145)
+__device__ __forceinline__ double pose_distance(const double a[8], const double b[8]) {
+	double sum = 0;
+#pragma unroll
+	for (int i = 0; i < 3; ++i) sum = sum + (b[i] - a[i]) * (b[i] - a[i]);
+	return sqrt(sum);
+}
+__device__ __forceinline__ double state_distance(const double a[8], const double b[8]) {
+	double sum = 0;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) sum = sum + 1.0 * (b[i] - a[i]) * (b[i] - a[i]);
+	return sqrt(sum);
+}
+__device__ __forceinline__ double yaw_distance(const double a[8], const double b[8]) {
+	double y1 = atan2(a[4], a[3]), y2 = atan2(b[4], b[3]);
+	double lo = y1 < y2 ? y1 : y2, hi = y1 < y2 ? y2 : y1;
+	double d1 = hi - lo, d2 = lo + 2 * MY_PI - hi;
+	return d2 < d1 ? d2 : d1;
+}
+
+// ---- samplers on the Philox stream (draw layout documented in oracle/gbp_oracle.c and DESIGN.md)
+// getRandomAction (:392-442) / getRandomActionDirection (:443-515); R = grf_rotation(normal)
+__device__ __forceinline__ void sample_action(uint64_t seed, uint64_t stream, uint64_t idx, const double R[9], bool dir_flag,
+											  double dir_thresh, const double *s_from, const double *s_to, double a[10]) {
+	double u0, u1, u2, u3, u4, u5, u6, u7, u8, u9;
+	uniform_pair(seed, stream, idx, 1, 0, u0, u1);
+	uniform_pair(seed, stream, idx, 1, 1, u2, u3);
+	uniform_pair(seed, stream, idx, 1, 2, u4, u5);
+	uniform_pair(seed, stream, idx, 1, 3, u6, u7);
+	uniform_pair(seed, stream, idx, 1, 4, u8, u9);
+	double fzd = F_MAX * u0, fzo = F_MAX * u1, fxd, fxo, fyd, fyo;
+	if (dir_flag && u9 <= dir_thresh) {
+		double frd = MU * fzd, fro = MU * fzo;
+		if (s_to[3] > s_from[3]) { fxd = frd * u2; fxo = fro * u3; } else { fxd = frd * u2 - frd; fxo = fro * u3 - fro; }
+		if (s_to[4] > s_from[4]) { fyd = frd * u4; fyo = fro * u5; } else { fyd = frd * u4 - frd; fyo = fro * u5 - fro; }
+	} else {
+		fxd = 2 * MU * fzd * u2 - MU * fzd;
+		fxo = 2 * MU * fzo * u3 - MU * fzo;
+		fyd = 2 * MU * fzd * u4 - MU * fzd;
+		fyo = 2 * MU * fzo * u5 - MU * fzo;
+	}
+	double ftd[3] = {fxd, fyd, fzd}, fto[3] = {fxo, fyo, fzo}, rtd[3], rto[3];
+	mat3_apply(R, ftd, rtd);
+	mat3_apply(R, fto, rto);
+	a[0] = rtd[0] / M_CONST;
+	a[1] = rtd[1] / M_CONST;
+	a[2] = rtd[2] / M_CONST - G_CONST;
+	a[3] = rto[0] / M_CONST;
+	a[4] = rto[1] / M_CONST;
+	a[5] = rto[2] / M_CONST - G_CONST;
+	a[6] = 0.3;
+	a[7] = (T_F_MAX - T_F_MIN) * u6 + T_F_MIN;
+	double z0, z1;
+	const double sd = ANG_ACC_MAX / 4.0;
+	box_muller(u7, u8, z0, z1);
+	a[8] = clampd(sd * z0, -ANG_ACC_MAX, ANG_ACC_MAX);
+	a[9] = clampd(sd * z1, -ANG_ACC_MAX, ANG_ACC_MAX);
+}
+// PlannerClass::randomState (planner_class.cpp:38-76) / randomStateDirection (:82-148)
+template <typename CellT>
+__device__ __forceinline__ void sample_state(const TerrainView &T, uint64_t seed, uint64_t stream, uint64_t idx, bool dir_flag,
+											 double dir_thresh, bool speed_dir, const double *s_from, const double *s_to,
+											 double q[8]) {
+	double u0, u1, u2, u3, u4, u5, u6, u7, u8, u9;
+	uniform_pair(seed, stream, idx, 2, 0, u0, u1);
+	uniform_pair(seed, stream, idx, 2, 1, u2, u3);
+	uniform_pair(seed, stream, idx, 2, 2, u4, u5);
+	uniform_pair(seed, stream, idx, 2, 3, u6, u7);
+	bool directional = false;
+	if (dir_flag) { uniform_pair(seed, stream, idx, 2, 4, u8, u9); directional = u8 <= dir_thresh; }
+	double x_min = T.x0, x_max = T.x_last, y_min = T.y0, y_max = T.y_last;
+	if (directional) {
+		x_min = s_from[0] < s_to[0] ? s_from[0] : s_to[0];
+		x_max = s_from[0] < s_to[0] ? s_to[0] : s_from[0];
+		y_min = s_from[1] < s_to[1] ? s_from[1] : s_to[1];
+		y_max = s_from[1] < s_to[1] ? s_to[1] : s_from[1];
+	}
+	const double z_min_rel = H_MIN + ROBOT_H, z_max_rel = H_MAX + ROBOT_H;
+	const double mean = 0.5 * (z_max_rel + z_min_rel), sd = (z_max_rel - z_min_rel) * (1.0 / (2 * 3.0));
+	double z0, z1, sn, cs;
+	box_muller(u2, u3, z0, z1);
+	unsigned fl = 0;
+	q[0] = (x_max - x_min) * u0 + x_min;
+	q[1] = (y_max - y_min) * u1 + y_min;
+	q[2] = clampd(mean + sd * z0, z_min_rel, z_max_rel) + ground_height<CellT>(T, q[0], q[1], fl);
+	double cos_theta = 2.0 * u5 - 1.0, sin_theta = sqrt(1.0 - cos_theta * cos_theta), v = u6 * V_MAX;
+	if (directional && speed_dir) {
+		double ddx = s_to[0] - s_from[0], ddy = s_to[1] - s_from[1], nrm = sqrt(ddx * ddx + ddy * ddy);
+		if (nrm > 0) { cs = ddx / nrm; sn = ddy / nrm; } else { cs = 1.0; sn = 0.0; }
+	} else {
+		det_sincos((2.0 * MY_PI) * u4, sn, cs);
+	}
+	q[3] = v * sin_theta * cs;
+	q[4] = v * sin_theta * sn;
+	q[5] = v * cos_theta;
+	q[6] = 2 * P_MAX * u7 - P_MAX;
+	q[7] = 0.0;
+}
+
+// ---- attemptConnect (src/rrt_connect.cpp:20-91), recursion unrolled into a loop (see oracle)
+__device__ __forceinline__ void connect_action(const double st[8], const double go[8], double ts, double a[10]) {  // :53-63
+#pragma unroll
+	for (int d = 0; d < 4; ++d) {
+		const int ip = d < 3 ? d : 6, iv = d < 3 ? 3 + d : 7, itd = d < 3 ? d : 8, ito = d < 3 ? 3 + d : 9;
+		a[itd] = -(2.0 * (3.0 * st[ip] - 3.0 * go[ip] + 2.0 * st[iv] * ts + go[iv] * ts)) / (ts * ts);
+		a[ito] = (2.0 * (3.0 * st[ip] - 3.0 * go[ip] + st[iv] * ts + 2.0 * go[iv] * ts)) / (ts * ts);
+	}
+	a[6] = ts;
+	a[7] = 0;
+}
+}  // namespace gbp

@@ -1,0 +1,788 @@
+// Kernels of the extend path (sm_100a).  See DESIGN.md for the data layout and the roofline of each.
+#pragma once
+#include "gbp_device.cuh"
+
+namespace gbp {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// device-resident GraphClass/PlannerClass store (graph_class.h:155-170) as SoA
+struct TreeView {
+	int cap;
+	int *n;          // vertex count (device)
+	double *v;       // [8][cap]
+	double *act;     // [10][cap]
+	int *parent;     // [cap]
+	double *g, *y;   // [cap]
+};
+
+__device__ __forceinline__ void tree_get(const TreeView &T, int i, double s[8]) {
+#pragma unroll
+	for (int d = 0; d < 8; ++d) s[d] = T.v[(size_t) d * T.cap + i];
+}
+// addVertex + addEdge + addAction + updateGYValue (rrt.cpp:87-92, graph_class.cpp:36-42)
+__device__ __forceinline__ int tree_push(const TreeView &T, int parent, const double s[8], const double a[10]) {
+	int i = *T.n;
+	*T.n = i + 1;
+	double p[8];
+	tree_get(T, parent, p);
+#pragma unroll
+	for (int d = 0; d < 8; ++d) T.v[(size_t) d * T.cap + i] = s[d];
+#pragma unroll
+	for (int d = 0; d < 10; ++d) T.act[(size_t) d * T.cap + i] = a[d];
+	T.parent[i] = parent;
+	T.g[i] = T.g[parent] + pose_distance(p, s);
+	T.y[i] = T.y[parent] + yaw_distance(p, s);
+	return i;
+}
+
+// ------------------------------------------------------------------ small batched queries
+template <typename CellT>
+__global__ void k_terrain_query(TerrainView T, int64_t n, const double *__restrict__ x, const double *__restrict__ y, int what,
+								double *__restrict__ out, uint8_t *__restrict__ out8) {
+	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	unsigned fl = 0;
+	if (what == 0) {
+		out[i] = ground_height<CellT>(T, x[i], y[i], fl);
+		if (out8) out8[i] = (uint8_t) fl;
+	} else if (what == 1) {
+		out8[i] = height_is_nan<CellT>(T, x[i], y[i], fl) ? 1 : 0;
+	} else {
+		double nn[3];
+		surface_normal(T, x[i], y[i], nn, fl);
+		out[3 * i] = nn[0]; out[3 * i + 1] = nn[1]; out[3 * i + 2] = nn[2];
+	}
+}
+
+__global__ void k_propagate(int kind, int64_t n, const double *__restrict__ s, const double *__restrict__ a,
+							const double *__restrict__ t, double *__restrict__ out) {
+	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double ss[8], aa[10], o[8];
+#pragma unroll
+	for (int d = 0; d < 8; ++d) ss[d] = s[8 * i + d];
+	if (kind != 1) {
+#pragma unroll
+		for (int d = 0; d < 10; ++d) aa[d] = a[10 * i + d];
+	}
+	if (kind == 0) apply_stance(ss, aa, t[i], o);
+	else if (kind == 1) apply_flight(ss, t[i], o);
+	else apply_stance_reverse(ss, aa, t[i], o);
+#pragma unroll
+	for (int d = 0; d < 8; ++d) out[8 * i + d] = o[d];
+}
+
+__global__ void k_valid_actions(int64_t n, const double *__restrict__ a, uint8_t *__restrict__ out) {
+	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double aa[10];
+#pragma unroll
+	for (int d = 0; d < 10; ++d) aa[d] = a[10 * i + d];
+	out[i] = is_valid_action(aa) ? 1 : 0;
+}
+
+template <typename CellT>
+__global__ void k_valid_states(TerrainView T, int64_t n, const double *__restrict__ s, const uint8_t *__restrict__ phase,
+							   uint8_t *__restrict__ out, uint8_t *__restrict__ flags) {
+	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double ss[8];
+#pragma unroll
+	for (int d = 0; d < 8; ++d) ss[d] = s[8 * i + d];
+	Counters c = {0, 0, 0, 0};
+	bool ok = is_valid_state<CellT>(T, ss, phase[i], c);
+	out[i] = ok ? 1 : 0;
+	if (flags) flags[i] = (uint8_t) (c.flags | (ok ? GBP_FLAG_VALID : 0));
+}
+
+__global__ void k_distance(int kind, int64_t n, const double *__restrict__ q1, const double *__restrict__ q2,
+						   double *__restrict__ out) {
+	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double a[8], b[8];
+#pragma unroll
+	for (int d = 0; d < 8; ++d) { a[d] = q1[8 * i + d]; b[d] = q2[8 * i + d]; }
+	out[i] = kind == 0 ? pose_distance(a, b) : kind == 1 ? state_distance(a, b) : yaw_distance(a, b);
+}
+
+// ------------------------------------------------------------------ counters
+__device__ __forceinline__ void flush_counters(unsigned long long *cnt, unsigned long long k, unsigned long long L,
+											   unsigned long long np, unsigned long long oog, unsigned long long near,
+											   unsigned long long valid) {
+	// warp-reduce then one atomic per warp per counter
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		k += __shfl_down_sync(FULL, k, o);
+		L += __shfl_down_sync(FULL, L, o);
+		np += __shfl_down_sync(FULL, np, o);
+		oog += __shfl_down_sync(FULL, oog, o);
+		near += __shfl_down_sync(FULL, near, o);
+		valid += __shfl_down_sync(FULL, valid, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(cnt + 0, k); atomicAdd(cnt + 1, L); atomicAdd(cnt + 2, np);
+		atomicAdd(cnt + 3, oog); atomicAdd(cnt + 4, near); atomicAdd(cnt + 5, valid);
+	}
+}
+
+__device__ __forceinline__ void load_state(const double *__restrict__ p, double s[8]) {
+	const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+	for (int d = 0; d < 4; ++d) { double2 v = __ldg(q + d); s[2 * d] = v.x; s[2 * d + 1] = v.y; }
+}
+__device__ __forceinline__ void load_action(const double *__restrict__ p, double a[10]) {
+	const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+	for (int d = 0; d < 5; ++d) { double2 v = __ldg(q + d); a[2 * d] = v.x; a[2 * d + 1] = v.y; }
+}
+__device__ __forceinline__ void store_state(double *__restrict__ p, const double s[8]) {
+	double2 *q = reinterpret_cast<double2 *>(p);
+#pragma unroll
+	for (int d = 0; d < 4; ++d) q[d] = make_double2(s[2 * d], s[2 * d + 1]);
+}
+
+// ------------------------------------------------------------------ the pair-check cursor machine
+// Lane-per-action with warp-level refill: every lane walks the sub-states of its own candidate in
+// the reference's order, ONE sub-state per loop trip, so the expensive isValidState is executed
+// convergently by all 32 lanes on 32 different candidates; a lane whose candidate finished (early
+// exit or fully valid) pulls the next candidate of the warp's contiguous range.  Work done equals
+// the reference's early-exit work (k sub-states per candidate), unlike the warp-per-action form.
+enum : int { PH_FWD_ST = 0, PH_FWD_FL = 1, PH_FWD_LAND = 2, PH_REV_FL = 3, PH_REV_ST = 4, PH_REV_START = 5, PH_IDLE = 6 };
+
+struct Cursor {
+	double s[8], a[10];
+	double t, step, t_ok, t_new, t_ls;  // t_ls: time of the last valid stance sample (s_new on flight failure)
+	int phase, have_ls;
+	Counters c;
+};
+
+__device__ __forceinline__ void cursor_start(Cursor &q, int dir) {
+	q.step = KINEMATICS_RES;
+	q.t_ok = 0;
+	q.t_new = 0;
+	q.t_ls = 0;
+	q.have_ls = 0;
+	q.c = {0, 0, 0, 0};
+	const double ts = q.a[6], tf = q.a[7];
+	if (dir == GBP_FORWARD) {
+		q.t = 0;
+		q.phase = (0 <= ts) ? PH_FWD_ST : ((0 < tf) ? PH_FWD_FL : PH_FWD_LAND);
+	} else {
+		q.t = 0;
+		if (0 < tf) q.phase = PH_REV_FL;
+		else { q.t = ts; q.phase = (ts >= 0) ? PH_REV_ST : PH_REV_START; }
+	}
+}
+// state to check at the cursor
+__device__ __forceinline__ void cursor_state(const Cursor &q, double chk[8]) {
+	double tmp[8];
+	switch (q.phase) {
+	case PH_FWD_ST: apply_stance(q.s, q.a, q.t, chk); break;
+	case PH_FWD_FL: apply_stance(q.s, q.a, q.a[6], tmp); apply_flight(tmp, q.t, chk); break;
+	case PH_FWD_LAND: apply_stance(q.s, q.a, q.a[6], tmp); apply_flight(tmp, q.a[7], chk); break;
+	case PH_REV_FL: apply_flight(q.s, -q.t, chk); break;
+	case PH_REV_ST: apply_flight(q.s, -q.a[7], tmp); apply_stance_reverse(tmp, q.a, q.t, chk); break;
+	default: apply_flight(q.s, -q.a[7], tmp); apply_stance_reverse(tmp, q.a, 0, chk); break;
+	}
+}
+// Advance after the verdict of the current sub-state.  Returns 0 = continue, 1 = finished invalid,
+// 2 = finished valid.  On finish, s_new / t_new hold the reference's outputs.
+__device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, const double chk[8], bool adaptive, double s_new[8]) {
+	const double ts = q.a[6], tf = q.a[7];
+	switch (q.phase) {
+	case PH_FWD_ST:
+		if (!valid) {
+			if (!adaptive || (KINEMATICS_RES - 0.01 <= q.step && q.step <= KINEMATICS_RES + 0.01)) {
+				apply_stance(q.s, q.a, (1.0 - BACKUP_RATIO) * q.t, s_new);
+				return 1;
+			}
+			q.step = KINEMATICS_RES;
+			q.t = q.t_ok;
+		} else {
+			q.t_new = q.t; q.t_ls = q.t; q.have_ls = 1;
+			if (adaptive) { q.step += KINEMATICS_RES; q.t_ok = q.t; }
+		}
+		q.t += q.step;
+		if (!(q.t <= ts)) { q.t = 0; q.step = KINEMATICS_RES; q.phase = (0 < tf) ? PH_FWD_FL : PH_FWD_LAND; }
+		return 0;
+	case PH_FWD_FL:
+		if (!valid) {
+			if (q.have_ls) apply_stance(q.s, q.a, q.t_ls, s_new);
+			else { for (int i = 0; i < 8; ++i) s_new[i] = q.s[i]; }
+			return 1;
+		}
+		if (adaptive) q.step += KINEMATICS_RES;
+		q.t += q.step;
+		if (!(q.t < tf)) q.phase = PH_FWD_LAND;
+		return 0;
+	case PH_FWD_LAND:
+		if (!valid) {
+			if (q.have_ls) apply_stance(q.s, q.a, q.t_ls, s_new);
+			else { for (int i = 0; i < 8; ++i) s_new[i] = q.s[i]; }
+			return 1;
+		}
+		for (int i = 0; i < 8; ++i) s_new[i] = chk[i];
+		q.t_new = ts + tf;
+		return 2;
+	case PH_REV_FL:
+		if (!valid) { for (int i = 0; i < 8; ++i) s_new[i] = q.s[i]; return 1; }
+		if (adaptive) q.step += KINEMATICS_RES;
+		q.t += q.step;
+		if (!(q.t < tf)) { q.t = ts; q.step = KINEMATICS_RES; q.phase = (ts >= 0) ? PH_REV_ST : PH_REV_START; }
+		return 0;
+	case PH_REV_ST:
+		if (!valid) {
+			if (!adaptive || (KINEMATICS_RES - 0.01 <= q.step && q.step <= KINEMATICS_RES + 0.01)) {
+				apply_stance(q.s, q.a, q.t + BACKUP_RATIO * (ts - q.t), s_new);
+				return 1;
+			}
+			q.step = KINEMATICS_RES;
+			q.t = q.t_ok;
+		} else {
+			q.t_new = ts - q.t; q.t_ls = q.t; q.have_ls = 1;
+			if (adaptive) { q.step += KINEMATICS_RES; q.t_ok = q.t; }
+		}
+		q.t -= q.step;
+		if (!(q.t >= 0)) q.phase = PH_REV_START;
+		return 0;
+	default:  // PH_REV_START
+		if (!valid) {
+			if (q.have_ls) { double tmp[8]; apply_flight(q.s, -tf, tmp); apply_stance_reverse(tmp, q.a, q.t_ls, s_new); }
+			else { for (int i = 0; i < 8; ++i) s_new[i] = q.s[i]; }
+			return 1;
+		}
+		for (int i = 0; i < 8; ++i) s_new[i] = chk[i];
+		q.t_new = ts;
+		return 2;
+	}
+}
+
+// Sequential walk of one pair by one thread: the cursor machine below run to completion.  Same
+// semantics as planning_utils.cpp:651-753 (forward) and :774-876 (reverse).
+template <typename CellT>
+__device__ __forceinline__ bool validate_pair_seq(const TerrainView &T, const double s[8], const double a[10], int direction,
+												  bool adaptive, double s_new[8], double &t_new, Counters &c) {
+	Cursor q;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) q.s[i] = s[i];
+#pragma unroll
+	for (int i = 0; i < 10; ++i) q.a[i] = a[i];
+	cursor_start(q, direction);
+	int r = 0;
+	while (true) {
+		double chk[8];
+		cursor_state(q, chk);
+		const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
+		bool valid = is_valid_state<CellT>(T, chk, ph, q.c);
+		r = cursor_advance(q, valid, chk, adaptive, s_new);
+		if (r) break;
+	}
+	t_new = q.t_new;
+	c.substates += q.c.substates; c.lookups += q.c.lookups; c.nanprobes += q.c.nanprobes; c.flags |= q.c.flags;
+	return r == 2;
+}
+
+// attemptConnect (src/rrt_connect.cpp:20-91), recursion unrolled into a loop (see oracle/gbp_oracle.c)
+template <typename CellT>
+__device__ int attempt_connect(const TerrainView &T, const double s_existing[8], const double s_in[8], int direction,
+							   bool adaptive, double s_new[8], double a_new[10], Counters &c, unsigned &pair_checks) {
+	double target[8], ts = pose_distance(s_in, s_existing) / V_NOM;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) target[i] = s_in[i];
+	for (int depth = 0;; ++depth) {
+		if (ts <= KINEMATICS_RES) return GBP_TRAPPED;
+		if (direction == GBP_FORWARD) connect_action(s_existing, target, ts, a_new);
+		else connect_action(target, s_existing, ts, a_new);
+		if (!is_valid_action(a_new)) return GBP_TRAPPED;
+		double out[8], tn;
+		++pair_checks;
+		bool ok = validate_pair_seq<CellT>(T, s_existing, a_new, direction, adaptive, out, tn, c);
+#pragma unroll
+		for (int i = 0; i < 8; ++i) { s_new[i] = out[i]; target[i] = out[i]; }
+		if (ok) return depth == 0 ? GBP_REACHED : GBP_ADVANCED;
+		ts = tn;
+	}
+}
+
+// ------------------------------------------------------------------ validate_pairs, variant 1
+// One thread per action, sub-states walked sequentially in the reference's order.
+template <typename CellT>
+__global__ void __launch_bounds__(128) k_validate_thread(TerrainView T, int64_t n, const double *__restrict__ states,
+														  const double *__restrict__ actions, const uint8_t *__restrict__ dir,
+														  int adaptive, uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
+														  double *__restrict__ s_new, double *__restrict__ t_new,
+														  unsigned long long *__restrict__ cnt) {
+	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	Counters c = {0, 0, 0, 0};
+	bool ok = false;
+	if (i < n) {
+		double s[8], a[10], sn[8], tn;
+		load_state(states + 8 * i, s);
+		load_action(actions + 10 * i, a);
+		ok = validate_pair_seq<CellT>(T, s, a, dir[i], adaptive != 0, sn, tn, c);
+		verdict[i] = ok ? 1 : 0;
+		if (flags) flags[i] = (uint8_t) (c.flags | (ok ? GBP_FLAG_VALID : 0));
+		if (s_new) store_state(s_new + 8 * i, sn);
+		if (t_new) t_new[i] = tn;
+	}
+	flush_counters(cnt, c.substates, c.lookups, c.nanprobes, (c.flags & GBP_FLAG_OOG) ? 1 : 0, (c.flags & GBP_FLAG_NEAR) ? 1 : 0, ok ? 1 : 0);
+}
+
+// ------------------------------------------------------------------ validate_pairs, variant 2
+// One warp per action, one lane per interpolated sub-state (fixed step only).  Lane l of a round
+// evaluates sub-state 32*round + l of the reference's sequence (stance samples, flight samples,
+// landing / exact start); the sample times are the reference's fp64-ACCUMULATED values, obtained by
+// walking l steps from the round's base cursor.  __ballot_sync finds the first failing lane, which
+// reproduces the sequential early-exit outputs; lanes past it are speculative work that the
+// counters do not include.  Lowest latency per action: used for connect primitives (t_s = d/0.75
+// can span hundreds of sub-states) and inside the per-query planner warp.
+enum : int { PH_DONE = 7 };
+__device__ __forceinline__ void walk_step(int &ph, double &t, double ts, double tf) {
+	switch (ph) {
+	case PH_FWD_ST: t += KINEMATICS_RES; if (!(t <= ts)) { t = 0; ph = (0 < tf) ? PH_FWD_FL : PH_FWD_LAND; } break;
+	case PH_FWD_FL: t += KINEMATICS_RES; if (!(t < tf)) ph = PH_FWD_LAND; break;
+	case PH_REV_FL: t += KINEMATICS_RES; if (!(t < tf)) { t = ts; ph = (ts >= 0) ? PH_REV_ST : PH_REV_START; } break;
+	case PH_REV_ST: t -= KINEMATICS_RES; if (!(t >= 0)) ph = PH_REV_START; break;
+	default: ph = PH_DONE; break;  // LAND / START are terminal
+	}
+}
+// All 32 lanes call this with identical (warp-uniform) s, a, direction; outputs are uniform too.
+template <typename CellT>
+__device__ bool validate_pair_warp(const TerrainView &T, const double s[8], const double a[10], int direction, double s_new[8],
+								   double &t_new, Counters &c) {
+	const int lane = threadIdx.x & 31;
+	const double ts = a[6], tf = a[7];
+	Cursor q;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) { q.s[i] = s[i]; s_new[i] = s[i]; }
+#pragma unroll
+	for (int i = 0; i < 10; ++i) q.a[i] = a[i];
+	cursor_start(q, direction);
+	int bph = q.phase;
+	double bt = q.t, t_ls = 0;
+	bool have_ls = false;
+	t_new = 0;
+	while (true) {
+		int ph = bph;
+		double t = bt;
+		for (int i = 0; i < lane && ph != PH_DONE; ++i) walk_step(ph, t, ts, tf);
+		const bool active = ph != PH_DONE;
+		double chk[8];
+		Counters lc = {0, 0, 0, 0};
+		bool valid = true;
+		if (active) {
+			q.phase = ph;
+			q.t = t;
+			cursor_state(q, chk);
+			valid = is_valid_state<CellT>(T, chk, (ph == PH_FWD_FL || ph == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE, lc);
+		}
+		const unsigned bad = __ballot_sync(FULL, active && !valid);
+		const int f = bad ? __ffs(bad) - 1 : 32;
+		const bool counted = active && lane <= f;  // the sub-states the reference would have started
+		c.substates += __reduce_add_sync(FULL, counted ? lc.substates : 0u);
+		c.lookups += __reduce_add_sync(FULL, counted ? lc.lookups : 0u);
+		c.nanprobes += __reduce_add_sync(FULL, counted ? lc.nanprobes : 0u);
+		c.flags |= __reduce_or_sync(FULL, counted ? lc.flags : 0u);
+		const unsigned st_ok = __ballot_sync(FULL, active && lane < f && (ph == PH_FWD_ST || ph == PH_REV_ST));
+		if (st_ok) {
+			t_ls = __shfl_sync(FULL, t, 31 - __clz(st_ok));
+			have_ls = true;
+			t_new = direction == GBP_FORWARD ? t_ls : ts - t_ls;
+		}
+		if (f < 32) {  // reference outputs at the first failing sub-state
+			const int pf = __shfl_sync(FULL, ph, f);
+			const double tfail = __shfl_sync(FULL, t, f);
+			double tmp[8];
+			switch (pf) {
+			case PH_FWD_ST: apply_stance(s, a, (1.0 - BACKUP_RATIO) * tfail, s_new); break;
+			case PH_FWD_FL:
+			case PH_FWD_LAND: if (have_ls) apply_stance(s, a, t_ls, s_new); break;
+			case PH_REV_FL: break;
+			case PH_REV_ST: apply_stance(s, a, tfail + BACKUP_RATIO * (ts - tfail), s_new); break;
+			default: if (have_ls) { apply_flight(s, -tf, tmp); apply_stance_reverse(tmp, a, t_ls, s_new); } break;
+			}
+			return false;
+		}
+		const unsigned term = __ballot_sync(FULL, active && (ph == PH_FWD_LAND || ph == PH_REV_START));
+		if (term) {  // landing / exact start state reached and valid
+			const int src = __ffs(term) - 1;
+#pragma unroll
+			for (int i = 0; i < 8; ++i) s_new[i] = __shfl_sync(FULL, chk[i], src);
+			t_new = direction == GBP_FORWARD ? ts + tf : ts;
+			return true;
+		}
+		bph = __shfl_sync(FULL, ph, 31);
+		bt = __shfl_sync(FULL, t, 31);
+		walk_step(bph, bt, ts, tf);
+	}
+}
+template <typename CellT>
+__global__ void __launch_bounds__(128) k_validate_warp(TerrainView T, int64_t n, const double *__restrict__ states,
+														const double *__restrict__ actions, const uint8_t *__restrict__ dir,
+														uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
+														double *__restrict__ s_new, double *__restrict__ t_new,
+														unsigned long long *__restrict__ cnt) {
+	const int64_t i = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+	if (i >= n) return;  // warp-uniform
+	double s[8], a[10], sn[8], tn;
+	load_state(states + 8 * i, s);
+	load_action(actions + 10 * i, a);
+	Counters c = {0, 0, 0, 0};
+	const bool ok = validate_pair_warp<CellT>(T, s, a, dir[i], sn, tn, c);
+	if ((threadIdx.x & 31) == 0) {
+		verdict[i] = ok ? 1 : 0;
+		if (flags) flags[i] = (uint8_t) (c.flags | (ok ? GBP_FLAG_VALID : 0));
+		if (s_new) store_state(s_new + 8 * i, sn);
+		if (t_new) t_new[i] = tn;
+		atomicAdd(cnt + 0, (unsigned long long) c.substates); atomicAdd(cnt + 1, (unsigned long long) c.lookups);
+		atomicAdd(cnt + 2, (unsigned long long) c.nanprobes); atomicAdd(cnt + 3, (c.flags & GBP_FLAG_OOG) ? 1ull : 0ull);
+		atomicAdd(cnt + 4, (c.flags & GBP_FLAG_NEAR) ? 1ull : 0ull); atomicAdd(cnt + 5, ok ? 1ull : 0ull);
+	}
+}
+
+// ------------------------------------------------------------------ validate_pairs, variant 3 (refill)
+template <typename CellT>
+__global__ void __launch_bounds__(128) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
+														  const double *__restrict__ states, const double *__restrict__ actions,
+														  const uint8_t *__restrict__ dir, int adaptive,
+														  uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
+														  double *__restrict__ s_new, double *__restrict__ t_new,
+														  unsigned long long *__restrict__ cnt) {
+	const int lane = threadIdx.x & 31;
+	const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+	int64_t next = warp * per_warp;
+	const int64_t end = min(n, next + per_warp);
+	Cursor q;
+	q.phase = PH_IDLE;
+	int64_t mine = -1;
+	unsigned long long k = 0, L = 0, np = 0, oog = 0, near = 0, nvalid = 0;
+	while (true) {
+		// refill idle lanes from the warp's range, in lane order
+		unsigned need = __ballot_sync(FULL, q.phase == PH_IDLE);
+		if (need) {
+			if (q.phase == PH_IDLE) {
+				int64_t idx = next + __popc(need & ((1u << lane) - 1));
+				if (idx < end) {
+					mine = idx;
+					load_state(states + 8 * idx, q.s);
+					load_action(actions + 10 * idx, q.a);
+					cursor_start(q, dir[idx]);
+				}
+			}
+			next += __popc(need);
+		}
+		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) break;
+		double chk[8];
+		bool valid = true;
+		if (q.phase != PH_IDLE) {
+			cursor_state(q, chk);
+			const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
+			valid = is_valid_state<CellT>(T, chk, ph, q.c);
+		}
+		if (q.phase != PH_IDLE) {
+			double sn[8];
+			int r = cursor_advance(q, valid, chk, adaptive != 0, sn);
+			if (r) {
+				const bool ok = r == 2;
+				verdict[mine] = ok ? 1 : 0;
+				if (flags) flags[mine] = (uint8_t) (q.c.flags | (ok ? GBP_FLAG_VALID : 0));
+				if (s_new) store_state(s_new + 8 * mine, sn);
+				if (t_new) t_new[mine] = q.t_new;
+				k += q.c.substates; L += q.c.lookups; np += q.c.nanprobes;
+				oog += (q.c.flags & GBP_FLAG_OOG) ? 1 : 0; near += (q.c.flags & GBP_FLAG_NEAR) ? 1 : 0; nvalid += ok ? 1 : 0;
+				q.phase = PH_IDLE;
+			}
+		}
+	}
+	flush_counters(cnt, k, L, np, oog, near, nvalid);
+}
+
+// ------------------------------------------------------------------ samplers
+__global__ void k_sample_actions(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, double n0, double n1, double n2,
+								 int dir_flag, double dir_thresh, const double *__restrict__ s_from, const double *__restrict__ s_to,
+								 double *__restrict__ out) {
+	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double nn[3] = {n0, n1, n2}, R[9], a[10], sf[8], st[8];
+	grf_rotation(nn, R);
+	if (dir_flag) {
+#pragma unroll
+		for (int d = 0; d < 8; ++d) { sf[d] = s_from[d]; st[d] = s_to[d]; }
+	}
+	sample_action(seed, stream, idx0 + (uint64_t) i, R, dir_flag != 0, dir_thresh, sf, st, a);
+	double2 *q = reinterpret_cast<double2 *>(out + 10 * i);
+#pragma unroll
+	for (int d = 0; d < 5; ++d) q[d] = make_double2(a[2 * d], a[2 * d + 1]);
+}
+template <typename CellT>
+__global__ void k_sample_states(TerrainView T, uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, int dir_flag,
+								double dir_thresh, int speed_dir, const double *__restrict__ s_from, const double *__restrict__ s_to,
+								double *__restrict__ out) {
+	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double q[8], sf[8], st[8];
+	if (dir_flag) {
+#pragma unroll
+		for (int d = 0; d < 8; ++d) { sf[d] = s_from[d]; st[d] = s_to[d]; }
+	}
+	sample_state<CellT>(T, seed, stream, idx0 + (uint64_t) i, dir_flag != 0, dir_thresh, speed_dir != 0, sf, st, q);
+	store_state(out + 8 * i, q);
+}
+
+// ------------------------------------------------------------------ tree queries
+// getNearestNeighbor (planner_class.cpp:185-200): one CTA per query, fp64 distances in the
+// reference's accumulation order, (distance, id) lexicographic argmin by warp shuffles.
+__device__ __forceinline__ void argmin_combine(double &d, int &i, double od, int oi) {
+	if (od < d || (od == d && oi < i)) { d = od; i = oi; }
+}
+__device__ __forceinline__ double vertex_distance(const TreeView &T, int j, const double q[8]) {
+	double sum = 0;
+#pragma unroll
+	for (int d = 0; d < 8; ++d) {
+		double vd = T.v[(size_t) d * T.cap + j];
+		sum = sum + 1.0 * (vd - q[d]) * (vd - q[d]);
+	}
+	return sqrt(sum);
+}
+__device__ __forceinline__ void warp_argmin(double &d, int &i) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		double od = __shfl_xor_sync(FULL, d, o);
+		int oi = __shfl_xor_sync(FULL, i, o);
+		argmin_combine(d, i, od, oi);
+	}
+}
+__global__ void __launch_bounds__(256) k_nearest(TreeView T, int64_t m, const double *__restrict__ queries, int *__restrict__ idx,
+												  double *__restrict__ dist) {
+	__shared__ double sd[8];
+	__shared__ int si[8];
+	const int nv = *T.n;
+	for (int64_t qi = blockIdx.x; qi < m; qi += gridDim.x) {
+		double q[8];
+#pragma unroll
+		for (int d = 0; d < 8; ++d) q[d] = queries[8 * qi + d];
+		double bd = INFINITY;
+		int bi = 0x7fffffff;
+		for (int j = threadIdx.x; j < nv; j += blockDim.x) argmin_combine(bd, bi, vertex_distance(T, j, q), j);
+		warp_argmin(bd, bi);
+		if ((threadIdx.x & 31) == 0) { sd[threadIdx.x >> 5] = bd; si[threadIdx.x >> 5] = bi; }
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			bd = threadIdx.x < (blockDim.x >> 5) ? sd[threadIdx.x] : INFINITY;
+			bi = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+			warp_argmin(bd, bi);
+			if (threadIdx.x == 0) {
+				idx[qi] = bi == 0x7fffffff ? 0 : bi;  // reference default index 0 (planner_class.cpp:186)
+				if (dist) dist[qi] = bd;
+			}
+		}
+		__syncthreads();
+	}
+}
+// neighborhoodDist (planner_class.cpp:173-182): one warp, ballot/popc compaction keeps ascending ids
+__global__ void k_near(TreeView T, const double *__restrict__ query, double radius, int *__restrict__ ids, int cap,
+					   int *__restrict__ count) {
+	const int nv = *T.n, lane = threadIdx.x;
+	double q[8];
+#pragma unroll
+	for (int d = 0; d < 8; ++d) q[d] = query[d];
+	int base = 0;
+	for (int j0 = 0; j0 < nv; j0 += 32) {
+		int j = j0 + lane;
+		bool in = false;
+		if (j < nv) {
+			double d = vertex_distance(T, j, q);
+			in = (d <= radius) && (d > 0);
+		}
+		unsigned m = __ballot_sync(FULL, in);
+		int pos = base + __popc(m & ((1u << lane) - 1));
+		if (in && pos < cap) ids[pos] = j;
+		base += __popc(m);
+	}
+	if (lane == 0) *count = base;
+}
+
+__global__ void k_tree_init(TreeView T, const double *__restrict__ root) {
+	if (threadIdx.x == 0) {
+		*T.n = 1;
+		for (int d = 0; d < 8; ++d) T.v[(size_t) d * T.cap] = root[d];
+		for (int d = 0; d < 10; ++d) T.act[(size_t) d * T.cap] = 0.0;
+		T.parent[0] = -1;
+		T.g[0] = 0;
+		T.y[0] = 0;
+	}
+}
+__global__ void k_tree_append(TreeView T, int parent, const double *__restrict__ s, const double *__restrict__ a, int *__restrict__ out) {
+	if (threadIdx.x == 0) {
+		double ss[8], aa[10];
+		for (int d = 0; d < 8; ++d) ss[d] = s[d];
+		for (int d = 0; d < 10; ++d) aa[d] = a[d];
+		int n = *T.n;
+		if (n >= T.cap || parent < 0 || parent >= n) { *out = -1; return; }
+		*out = tree_push(T, parent, ss, aa);
+	}
+}
+// bulk load: AoS host layout -> SoA, g / yaw rebuilt in id order (parents precede children)
+__global__ void k_tree_load(TreeView T, int n, const double *__restrict__ s, const double *__restrict__ a, const int *__restrict__ parent) {
+	for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < n; i += blockDim.x * gridDim.x) {
+		for (int d = 0; d < 8; ++d) T.v[(size_t) d * T.cap + i] = s[8 * (size_t) i + d];
+		for (int d = 0; d < 10; ++d) T.act[(size_t) d * T.cap + i] = a ? a[10 * (size_t) i + d] : 0.0;
+		T.parent[i] = i == 0 ? -1 : parent[i];
+	}
+}
+__global__ void k_tree_gy(TreeView T, int n) {
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		*T.n = n;
+		T.g[0] = 0;
+		T.y[0] = 0;
+		for (int i = 1; i < n; ++i) {
+			int p = T.parent[i];
+			double a[8], b[8];
+			tree_get(T, p, a);
+			tree_get(T, i, b);
+			T.g[i] = T.g[p] + pose_distance(a, b);
+			T.y[i] = T.y[p] + yaw_distance(a, b);
+		}
+	}
+}
+__global__ void k_tree_read(TreeView T, int first, int n, double *__restrict__ s, double *__restrict__ a, int *__restrict__ parent,
+							double *__restrict__ g, double *__restrict__ y) {
+	for (int k = threadIdx.x + blockIdx.x * blockDim.x; k < n; k += blockDim.x * gridDim.x) {
+		int i = first + k;
+		if (s) for (int d = 0; d < 8; ++d) s[8 * (size_t) k + d] = T.v[(size_t) d * T.cap + i];
+		if (a) for (int d = 0; d < 10; ++d) a[10 * (size_t) k + d] = T.act[(size_t) d * T.cap + i];
+		if (parent) parent[k] = T.parent[i];
+		if (g) g[k] = T.g[i];
+		if (y) y[k] = T.y[i];
+	}
+}
+
+// ------------------------------------------------------------------ extend (rrt.cpp:20-102)
+// Stage 2 of gbp_extend: candidate j = ACTION cell idx0 + j from s_near; one thread per candidate.
+struct ExtendScratch {
+	int *near_idx;       // [1] result of k_nearest
+	double *near_dist;   // [1]
+	uint8_t *valid;      // [K]
+	double *dist;        // [K] stateDistance(s_test, target)
+	double *s_test;      // [K][8]
+	int *result;         // [4] status, new id, first-valid index / checks, pad
+};
+template <typename CellT>
+__global__ void __launch_bounds__(128) k_extend_candidates(TerrainView T, TreeView tree, const double *__restrict__ target,
+															int direction, int K, int adaptive, uint64_t seed, uint64_t stream,
+															uint64_t idx0, ExtendScratch S) {
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= K) return;
+	double tg[8], s_near[8], nn[3], R[9], a[10], sn[8], tn;
+#pragma unroll
+	for (int d = 0; d < 8; ++d) tg[d] = target[d];
+	tree_get(tree, *S.near_idx, s_near);
+	unsigned fl = 0;
+	surface_normal(T, tg[0], tg[1], nn, fl);  // rrt.cpp:25 — normal at the TARGET sample
+	grf_rotation(nn, R);
+	sample_action(seed, stream, idx0 + (uint64_t) j, R, false, 0.0, nullptr, nullptr, a);
+	Counters c = {0, 0, 0, 0};
+	bool ok = validate_pair_seq<CellT>(T, s_near, a, direction, adaptive != 0, sn, tn, c);
+	S.valid[j] = ok ? 1 : 0;
+	S.dist[j] = ok ? state_distance(sn, tg) : INFINITY;
+	store_state(S.s_test + 8 * (size_t) j, sn);
+}
+// Stage 3: selection + acceptance + append + status (single CTA)
+__global__ void __launch_bounds__(256) k_extend_select(TerrainView T, TreeView tree, const double *__restrict__ target, int K,
+														int best_of_k, uint64_t seed, uint64_t stream, uint64_t idx0, ExtendScratch S) {
+	__shared__ double sd[8];
+	__shared__ int si[8];
+	// best_of_k: argmin of dist (ties: lowest j); first-valid: lowest valid j
+	double bd = INFINITY;
+	int bi = 0x7fffffff;
+	for (int j = threadIdx.x; j < K; j += blockDim.x) {
+		if (!S.valid[j]) continue;
+		if (best_of_k) argmin_combine(bd, bi, S.dist[j], j);
+		else if (j < bi) { bi = j; bd = S.dist[j]; }
+	}
+	if (!best_of_k) {  // reduce on index only
+		for (int o = 16; o > 0; o >>= 1) {
+			double od = __shfl_xor_sync(FULL, bd, o);
+			int oi = __shfl_xor_sync(FULL, bi, o);
+			if (oi < bi) { bi = oi; bd = od; }
+		}
+	} else {
+		warp_argmin(bd, bi);
+	}
+	if ((threadIdx.x & 31) == 0) { sd[threadIdx.x >> 5] = bd; si[threadIdx.x >> 5] = bi; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < (blockDim.x >> 5); ++w) {
+			if (best_of_k) argmin_combine(bd, bi, sd[w], si[w]);
+			else if (si[w] < bi) { bi = si[w]; bd = sd[w]; }
+		}
+		int status = GBP_TRAPPED, new_id = -1;
+		int checks = best_of_k ? K : (bi == 0x7fffffff ? K : bi + 1);
+		if (bi != 0x7fffffff && *tree.n < tree.cap) {
+			double tg[8], s_near[8], sn[8];
+			for (int d = 0; d < 8; ++d) { tg[d] = target[d]; sn[d] = S.s_test[8 * (size_t) bi + d]; }
+			int near = *S.near_idx;
+			tree_get(tree, near, s_near);
+			if (bd < state_distance(s_near, tg)) {  // rrt.cpp:55-66
+				double nn[3], R[9], a[10];
+				unsigned fl = 0;
+				surface_normal(T, tg[0], tg[1], nn, fl);
+				grf_rotation(nn, R);
+				sample_action(seed, stream, idx0 + (uint64_t) bi, R, false, 0.0, nullptr, nullptr, a);
+				new_id = tree_push(tree, near, sn, a);
+				status = state_distance(sn, tg) <= GOAL_BOUNDS ? GBP_REACHED : GBP_ADVANCED;  // rrt.cpp:96-99
+			}
+		}
+		S.result[0] = status;
+		S.result[1] = new_id;
+		S.result[2] = checks;
+	}
+}
+
+// ------------------------------------------------------------------ attemptConnect / connect
+template <typename CellT>
+__global__ void __launch_bounds__(128) k_attempt_connect(TerrainView T, int64_t n, const double *__restrict__ s_existing,
+														  const double *__restrict__ s, const uint8_t *__restrict__ dir, int adaptive,
+														  int *__restrict__ status, double *__restrict__ s_new,
+														  double *__restrict__ a_new, uint8_t *__restrict__ flags) {
+	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double se[8], sg[8], sn[8], an[10];
+	load_state(s_existing + 8 * i, se);
+	load_state(s + 8 * i, sg);
+#pragma unroll
+	for (int d = 0; d < 8; ++d) sn[d] = sg[d];
+#pragma unroll
+	for (int d = 0; d < 10; ++d) an[d] = 0;
+	Counters c = {0, 0, 0, 0};
+	unsigned checks = 0;
+	status[i] = attempt_connect<CellT>(T, se, sg, dir[i], adaptive != 0, sn, an, c, checks);
+	store_state(s_new + 8 * i, sn);
+#pragma unroll
+	for (int d = 0; d < 10; ++d) a_new[10 * i + d] = an[d];
+	if (flags) flags[i] = (uint8_t) c.flags;
+}
+// connect (rrt_connect.cpp:98-120) after k_nearest put the neighbour into S.near_idx
+template <typename CellT>
+__global__ void k_connect(TerrainView T, TreeView tree, const double *__restrict__ target, int direction, int adaptive,
+						  ExtendScratch S) {
+	if (threadIdx.x != 0) return;
+	double tg[8], s_near[8], sn[8], an[10];
+	for (int d = 0; d < 8; ++d) tg[d] = target[d];
+	int near = *S.near_idx;
+	tree_get(tree, near, s_near);
+	Counters c = {0, 0, 0, 0};
+	unsigned checks = 0;
+	int r = attempt_connect<CellT>(T, s_near, tg, direction, adaptive != 0, sn, an, c, checks);
+	int new_id = -1;
+	if (r != GBP_TRAPPED) {
+		if (*tree.n < tree.cap) new_id = tree_push(tree, near, sn, an);
+		else r = GBP_TRAPPED;
+	}
+	S.result[0] = r;
+	S.result[1] = new_id;
+	S.result[2] = (int) checks;
+}
+
+}  // namespace gbp

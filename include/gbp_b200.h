@@ -1,0 +1,206 @@
+/* gbp_b200.h — C ABI of the B200-native RRT-Connect extend path (libgbp_b200.so).
+ *
+ * Drop-in boundary for the hot path of LiuShenLan/global_body_planner.  The reference has no FFI of
+ * its own (plain C++ classes); each entry point below names the reference interface it
+ * replaces (file:line under the reference root).  The C++ classes in include/global_body_planner/
+ * (same names and signatures as the reference headers) are thin RAII wrappers over these calls; see
+ * INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   State  = 8 doubles {x,y,z,dx,dy,dz,pitch,dpitch}, Action = 10 doubles
+ *            {ax_td,ay_td,az_td,ax_to,ay_to,az_to,t_stance,t_flight,apitch_td,apitch_to}
+ *            (planning_utils.h:57-62); arrays of them are dense row-major [n][8] / [n][10].
+ *   direction: 0 FORWARD, 1 REVERSE; phase: 0 FLIGHT, 1 STANCE (planning_utils.h:43-49).
+ *   extend/connect status: 0 TRAPPED, 1 ADVANCED, 2 REACHED (rrt.h:7-9).
+ *   Every function returns 0 (GBP_OK) or a negative GBP_E_* code and never throws; the message of
+ *   the last failure on the calling thread is gbp_last_error().
+ *   Functions without a suffix take HOST pointers (borrowed for the call; copies happen inside).
+ *   Functions ending in _dev take DEVICE pointers plus a cudaStream_t passed as void* (NULL = the
+ *   legacy default stream), enqueue work and return without synchronising.
+ *   All arithmetic that decides a verdict, an index or a propagated state is fp64 without FMA
+ *   contraction, in the reference's operation order (bit-exact by construction except for libm
+ *   atan2/sin/cos inside isValidState, see GBP_FLAG_NEAR).  There is no CPU fallback.
+ */
+#ifndef GBP_B200_H
+#define GBP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBP_OK 0
+#define GBP_E_INVALID (-1)  /* bad argument */
+#define GBP_E_CUDA (-2)     /* CUDA runtime error (no device, launch failure, out of memory) */
+#define GBP_E_CAPACITY (-3) /* tree or output buffer full */
+
+#define GBP_FORWARD 0
+#define GBP_REVERSE 1
+#define GBP_FLIGHT 0
+#define GBP_STANCE 1
+#define GBP_TRAPPED 0
+#define GBP_ADVANCED 1
+#define GBP_REACHED 2
+
+/* per-candidate flag bits (optional `flags` outputs) */
+#define GBP_FLAG_VALID 1u /* copy of the verdict */
+#define GBP_FLAG_OOG 2u   /* a terrain probe reached under the reference's sequential semantics fell outside
+                             [x_0,x_last) x [y_0,y_last); the reference has undefined behaviour there, this
+                             library uses cell-(0,0)-anchored extrapolation */
+#define GBP_FLAG_NEAR 4u  /* a clearance/reach comparison was decided by a margin below 1e-9 m: the only
+                             place where a <=2 ulp libm difference (CUDA vs glibc atan2/sin/cos) could
+                             change the verdict */
+
+typedef struct gbp_terrain gbp_terrain; /* device-resident FastTerrainMap */
+typedef struct gbp_tree gbp_tree;       /* device-resident GraphClass/PlannerClass store */
+
+const char *gbp_last_error(void);
+const char *gbp_version(void);
+int gbp_device_count(int *count);
+int gbp_set_device(int device);
+
+/* ------------------------------------------------------------------------------------- terrain */
+/* FastTerrainMap::loadData (fast_terrain_map.cpp:10-28).  Axes must be strictly increasing
+ * (GBP_E_INVALID otherwise); layers are x-major [ix*ny + iy] exactly like z_data_[ix][iy]
+ * (fast_terrain_map.h:97-118); dx/dy/dz may be NULL (normal (0,0,1)).  Heights are stored on the
+ * device as fp32 when every value converts losslessly (always true for the ROS GridMap ingest,
+ * fast_terrain_map.cpp:60-66), else as fp64; results are identical either way. */
+int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const double *z, const double *dx,
+                       const double *dy, const double *dz, gbp_terrain **out);
+/* FastTerrainMap::loadDataFromGridMap (fast_terrain_map.cpp:31-91): float layers in grid_map index
+ * order [i*ny + j], index (0,0) = largest x and y, cell position = centre + (0.5(n-1) - i)*res. */
+int gbp_terrain_create_gridmap(int nx, int ny, double resolution, double centre_x, double centre_y,
+                               const float *elevation, const float *dx, const float *dy, const float *dz,
+                               gbp_terrain **out);
+void gbp_terrain_destroy(gbp_terrain *t);
+int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes);
+/* FastTerrainMap::getXData / getYData (fast_terrain_map.cpp:216-223) */
+int gbp_terrain_axes(const gbp_terrain *t, double *x, double *y);
+/* getGroundHeight (:94-132), heightIsNan (:135-157), getSurfaceNormal (:160-213, not renormalised) */
+int gbp_ground_height(const gbp_terrain *t, int64_t n, const double *x, const double *y, double *h, uint8_t *flags);
+int gbp_height_is_nan(const gbp_terrain *t, int64_t n, const double *x, const double *y, uint8_t *is_nan);
+int gbp_surface_normal(const gbp_terrain *t, int64_t n, const double *x, const double *y, double *normal3);
+
+/* ---------------------------------------------------------------------------------- primitives */
+/* applyStance (planning_utils.cpp:237-277), applyFlight (:282-306), applyStanceReverse (:324-370);
+ * t has n entries.  kind: 0 stance, 1 flight (actions ignored, may be NULL), 2 stance-reverse. */
+int gbp_propagate(int kind, int64_t n, const double *states, const double *actions, const double *t, double *out);
+/* isValidAction (planning_utils.cpp:519-556) */
+int gbp_valid_actions(int64_t n, const double *actions, uint8_t *verdict);
+/* isValidState (planning_utils.cpp:562-635); phase has n entries */
+int gbp_valid_states(const gbp_terrain *t, int64_t n, const double *states, const uint8_t *phase, uint8_t *verdict,
+                     uint8_t *flags);
+/* poseDistance / stateDistance / stateYawDistance (planning_utils.cpp:106-127, planning_utils.h:133-145);
+ * kind 0 / 1 / 2 */
+int gbp_distance(int kind, int64_t n, const double *q1, const double *q2, double *out);
+
+/* isValidStateActionPair / isValidStateActionPairReverse through the 6-argument dispatchers
+ * (planning_utils.cpp:645-650, 768-773): fixed step (:713-753, :837-876) or adaptive step
+ * (:651-712, :774-836).  direction has n entries.  Outputs the reference leaves unwritten are
+ * defined: s_new starts as the input state, t_new as 0.  flags / s_new / t_new may be NULL.
+ * `variant` selects the kernel: 0 = default (currently the refill kernel), 1 = one thread per
+ * action, 2 = one warp per action / one lane per sub-state (fixed step only), 3 = lane-per-action
+ * with warp-level refill.  All variants return identical results. */
+int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, const double *actions,
+                       const uint8_t *direction, int adaptive, int variant, uint8_t *verdict, uint8_t *flags,
+                       double *s_new, double *t_new);
+int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states, const double *actions,
+                           const uint8_t *direction, int adaptive, int variant, uint8_t *verdict, uint8_t *flags,
+                           double *s_new, double *t_new, void *stream);
+/* per-launch work counters of the last gbp_validate_pairs[_dev] call on this terrain handle, summed
+ * over candidates under the REFERENCE's early-exit semantics: {sub-states k, getGroundHeight calls L,
+ * heightIsNan calls, candidates flagged OOG, candidates flagged NEAR, valid}.  Synchronises. */
+int gbp_validate_counters(const gbp_terrain *t, int64_t counters6[6]);
+
+/* ------------------------------------------------------------------------------------ samplers */
+/* Philox4x32-10 stream spec (shared with the CPU harness, oracle/gbp_oracle.c):
+ *   key = (seed lo, seed hi); counter = (idx lo, idx hi, stream lo, (stream hi & 0xffffff) | block<<24 | purpose<<28)
+ *   uniform j = words (2(j&1), 2(j&1)+1) of block j/2:  u = ((w_hi>>5)*2^26 + (w_lo>>6)) * 2^-53
+ * purpose 1 = ACTION cell, 2 = STATE cell.  Candidate i of a call uses idx = idx0 + i. */
+/* getRandomAction (planning_utils.cpp:379-442) and getRandomActionDirection (:443-515).
+ * normal3: one surface normal for the whole batch (rrt.cpp:25).  s_from/s_to: NULL disables
+ * directional sampling; otherwise one State each and dir_threshold as in rrt.h:198-199. */
+int gbp_sample_actions(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, const double *normal3,
+                       const double *s_from, const double *s_to, double dir_threshold, double *actions);
+int gbp_sample_actions_dev(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, const double *normal3_host,
+                           double *actions, void *cuda_stream);
+/* PlannerClass::randomState (planner_class.cpp:22-76) and randomStateDirection (:82-148) */
+int gbp_sample_states(const gbp_terrain *t, uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n,
+                      const double *s_from, const double *s_to, double dir_threshold, int speed_direction,
+                      double *states);
+int gbp_sample_states_dev(const gbp_terrain *t, uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n,
+                          double *states, void *cuda_stream);
+
+/* --------------------------------------------------------------------------------- tree store */
+/* GraphClass / PlannerClass storage (graph_class.h:155-170) as a device SoA arena: vertex
+ * components in 8 arrays of `capacity` doubles, actions in 10, plus parent, g and yaw-sum.
+ * Vertex ids are dense 0..n-1 in insertion order, as rrt.cpp:87 allocates them. */
+int gbp_tree_create(int capacity, gbp_tree **out);
+void gbp_tree_destroy(gbp_tree *T);
+int gbp_tree_init(gbp_tree *T, const double *root_state);            /* GraphClass::init (graph_class.cpp:140-152) */
+int gbp_tree_size(const gbp_tree *T, int *n);                         /* getNumVertices (:23-25) */
+/* addVertex + addEdge + addAction + updateGYValue as rrt.cpp:87-92; returns the new id */
+int gbp_tree_append(gbp_tree *T, int parent, const double *state, const double *action, int *new_id);
+/* bulk load of n vertices (ids 0..n-1); parent[0] = -1.  g/yaw are rebuilt as addEdge would. */
+int gbp_tree_load(gbp_tree *T, int n, const double *states, const double *actions, const int *parent);
+/* read back n vertices starting at id first; any output may be NULL */
+int gbp_tree_read(const gbp_tree *T, int first, int n, double *states, double *actions, int *parent, double *g,
+                  double *yaw);
+/* PlannerClass::getNearestNeighbor (planner_class.cpp:185-200) for m queries.  Ties: lowest id
+ * (the reference's order is that of std::unordered_map). */
+int gbp_nearest(const gbp_tree *T, int64_t m, const double *queries, int *idx, double *dist);
+int gbp_nearest_dev(const gbp_tree *T, int64_t m, const double *queries, int *idx, double *dist, void *stream);
+/* PlannerClass::neighborhoodDist (planner_class.cpp:173-182): ids with 0 < d <= radius in ascending
+ * id order; *count receives the total (may exceed cap, in which case only cap ids are written). */
+int gbp_near(const gbp_tree *T, const double *query, double radius, int *ids, int cap, int *count);
+
+/* -------------------------------------------------------------------------- extend / connect */
+/* RRTClass::extend (rrt.cpp:77-102) with newConfig (rrt.cpp:20-70) generalised to K candidates:
+ * nearest neighbour, K actions from ACTION cells idx0..idx0+K-1 of (seed, stream), pair checks from
+ * s_near in `direction`, selection (best_of_k 0: first valid in stream order decides, the reference's
+ * behaviour with K = 6; 1: closest valid), acceptance iff closer to `target` than s_near, append.
+ * One launch; everything stays on the device.  *status, *new_id, checks may be NULL. */
+int gbp_extend(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int k_candidates,
+               int best_of_k, int adaptive, uint64_t seed, uint64_t stream, uint64_t idx0, int *status,
+               int *new_id, int64_t *pair_checks);
+/* RRTConnectClass::attemptConnect (rrt_connect.cpp:20-91), n independent (s_existing, s) pairs */
+int gbp_attempt_connect(const gbp_terrain *t, int64_t n, const double *s_existing, const double *s,
+                        const uint8_t *direction, int adaptive, int *status, double *s_new, double *a_new,
+                        uint8_t *flags);
+/* RRTConnectClass::connect (rrt_connect.cpp:98-120) */
+int gbp_connect(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int adaptive, int *status,
+                int *new_id);
+
+/* ------------------------------------------------------------------------------ batch planner */
+/* runRRTConnect (rrt_connect.cpp:230-314) / the RRT*-Connect loop (rrt_star_connect.cpp:130-165)
+ * for nq independent queries resident on the device, with the wall-clock budget replaced by an
+ * iteration budget.  STATE cell idx = 2*iter + half, ACTION cells idx = (2*iter + half)*K + j,
+ * stream = query0 + i. */
+typedef struct {
+	int k_candidates; /* actions per extend; 6 = NUM_GEN_STATES (planning_utils.h:48) */
+	int best_of_k;    /* 0 first valid (reference), 1 closest valid */
+	int max_iters;
+	int max_vertices; /* per-tree capacity */
+	int adaptive;
+	int rrt_star;     /* RRTStarConnectClass::extend (rrt_star_connect.cpp:12-75), delta = 3.0 */
+	int post_process; /* postProcessPath (rrt_connect.cpp:139-227) on solved queries */
+} gbp_plan_params;
+
+typedef struct {
+	int solved, iters, nv_a, nv_b, path_states, pad;
+	double path_length, path_yaw, path_duration;
+	int64_t pair_checks, nn_queries;
+} gbp_plan_stats; /* 64 bytes; what the final NCCL gather carries per query */
+
+int gbp_plan_batch(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed,
+                   uint64_t query0, const gbp_plan_params *params, gbp_plan_stats *stats, double *path_states,
+                   double *path_actions, int path_cap);
+int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed,
+                       uint64_t query0, const gbp_plan_params *params, gbp_plan_stats *stats, double *path_states,
+                       double *path_actions, int path_cap, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBP_B200_H */
