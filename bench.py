@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native RRT-Connect extend path.
+
+Metric (BASELINE.json): validated actions/s (+ solved plans/s as a secondary key) on N B200s.
+Workload at every N (weak scaling): the validity microbench of BASELINE.json configs[3] —
+16,777,216 stance/flight action candidates PER GPU on a synthetic 4096x4096 height map
+(z = 0.05 sin(0.7x) cos(0.5y), 0.05 m pitch, fp32-representable heights), start states from the
+Philox randomState recipe filtered to valid STANCE poses >= 0.5 m inside the border, actions from
+the Philox getRandomAction recipe with normal (0,0,1), alternating FORWARD / REVERSE.
+A "step" = one isValidStateActionPair[Reverse] pass over the whole candidate batch.
+
+  value : candidates resident in HBM, one kernel launch per step, CUDA-event timed.
+  e2e   : the same batch through the host-pointer C-ABI call gbp_validate_pairs (pinned host
+          buffers, chunked H2D / kernel / D2H pipeline inside the call).
+  --impl reference : the UNMODIFIED reference (oracle/_ref/libgbp_ref.so) on the host cores, on a
+          bounded sample of the same candidates; falls back to the oracle restatement ("port")
+          only if the reference build is absent.
+
+Only the cpu_baseline / --impl reference legs touch oracle/ (as the timed CPU baseline, never as the
+thing shipped).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CAND = 16_777_216
+MAP_N, MAP_PITCH = 4096, 0.05
+B_IO = 64 + 80 + 1 + 1 + 1 + 64 + 8  # state, action, direction in; verdict, flags, s_new, t_new out
+
+
+def synthetic_map(n=MAP_N, pitch=MAP_PITCH):
+    ax = np.arange(n, dtype=np.float64) * pitch
+    z = 0.05 * np.sin(0.7 * ax)[:, None] * np.cos(0.5 * ax)[None, :]
+    return ax, ax.copy(), z.astype(np.float32).astype(np.float64)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (pynvml, else nvidia-smi)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.th = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake", 0x2: "applications_clocks", 0x10: "sync_boost"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.01)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.th.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------ CPU reference / oracle
+_CPU = {}
+
+
+def inside_border(q, x, y, margin=0.5):
+    return (q[:, 0] >= x[0] + margin) & (q[:, 0] <= x[-1] - margin) & (q[:, 1] >= y[0] + margin) & (q[:, 1] <= y[-1] - margin)
+
+
+def cpu_engine(want):
+    """Terrain + engines on the host, built once: the unmodified reference (oracle/_ref) when its
+    library is present, else the oracle restatement."""
+    if not _CPU:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle as po
+        x, y, z = synthetic_map()
+        T = po.Terrain(x, y, z)
+        _CPU.update(po=po, T=T, oracle=po.Oracle(T), ref=None, x=x, y=y)
+        if want == "reference" and po.Ref.available():
+            _CPU["ref"] = po.Ref(T)
+    return _CPU
+
+
+def cpu_candidates(n_sample, seed, stream):
+    """The first n_sample candidates of the rank-0 batch, regenerated on the host with the oracle's
+    Philox samplers (bit-identical to the device sampler, tests/test_gpu_parity.py)."""
+    E = cpu_engine("reference")
+    po, o, x, y = E["po"], E["oracle"], E["x"], E["y"]
+    states, idx0, have = [], 0, 0
+    while have < n_sample:
+        m = max(3 * n_sample, 1 << 15)
+        q = o.sample_states(seed, stream, idx0, m)
+        idx0 += m
+        v, _ = o.valid_states(q, po.STANCE)
+        keep = (v == 1) & inside_border(q, x, y)
+        states.append(q[keep])
+        have += int(keep.sum())
+    s = np.concatenate(states)[:n_sample]
+    a = o.sample_actions(seed, stream + 1, 0, n_sample)
+    d = (np.arange(n_sample) % 2).astype(np.uint8)
+    return s, a, d
+
+
+def run_cpu(seed, stream, target_seconds, cores, want="reference"):
+    """Times the reference's isValidStateActionPair[Reverse] (all host threads, disjoint slices of the
+    candidate arrays, shared read-only terrain) over a bounded sample of the workload."""
+    E = cpu_engine(want)
+    kind = "reference" if E["ref"] is not None else "port"
+    eng = E["ref"] if kind == "reference" else E["oracle"]
+    run = (lambda S, A, D: eng.validate_pairs(S, A, D, False, cores))
+    probe = 64 * cores
+    s, a, d = cpu_candidates(probe, seed, stream)
+    t0 = time.perf_counter(); run(s, a, d); dt = time.perf_counter() - t0
+    n_sample = int(min(max(probe / dt * target_seconds * 0.2, probe), 1 << 18))  # ~20% pilot (the probe pays thread start-up)
+    s, a, d = cpu_candidates(n_sample, seed, stream)
+    t0 = time.perf_counter(); out = run(s, a, d); dt = time.perf_counter() - t0
+    if dt < 0.5 * target_seconds:
+        n_sample = int(min(max(n_sample / dt * target_seconds, n_sample), 1 << 20))
+        s, a, d = cpu_candidates(n_sample, seed, stream)
+        t0 = time.perf_counter(); out = run(s, a, d); dt = time.perf_counter() - t0
+    return {"value": n_sample / dt, "unit": "validated actions/s", "cores": cores, "kind": kind,
+            "sample": f"first {n_sample} of the rank-0 candidate batch (same map, same Philox stream), {dt:.2f} s"}, out, (s, a, d)
+
+
+# ------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", type=int, default=0, help="validate kernel variant (0 default, 1 thread, 2 warp, 3 refill)")
+    ap.add_argument("--candidates", type=int, default=N_CAND)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-plans", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    seed = 1
+    cores = os.cpu_count() or 1
+    config = {"workload": "validity microbench (BASELINE configs[3]): 16,777,216 stance/flight action candidates per GPU on a "
+                          "synthetic 4096x4096 height map, half FORWARD half REVERSE, fixed step",
+              "candidates_per_gpu": args.candidates, "map": f"{MAP_N}x{MAP_N} @ {MAP_PITCH} m, fp32-representable heights",
+              "l2_policy": "inputs (3.7 GB per step) larger than L2; no flush needed", "seed": seed}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        base = None
+        for i in range(args.warmup + args.steps):
+            base, _, _ = run_cpu(seed, 100, args.cpu_seconds / 2, cores, "reference")
+            if i >= args.warmup:
+                vals.append(base["value"])
+        v = float(np.mean(vals))
+        base["value"] = v
+        line = {"impl": "reference", "metric": "validated_actions_per_s", "value": v, "unit": "validated actions/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
+                "e2e": {"value": v, "unit": "validated actions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import global_body_planner_b200 as gbp
+    from global_body_planner_b200 import capi
+
+    if not torch.cuda.is_available() or gbp.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    gbp.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- terrain + candidate batch, generated on the device with the Philox samplers
+    x, y, z = synthetic_map()
+    t = gbp.Terrain(x, y, z)
+    n = args.candidates
+    stream_id = 100 + 2 * rank  # disjoint Philox streams per rank
+    cur = torch.cuda.current_stream().cuda_stream
+    states = torch.empty((n, 8), dtype=torch.float64, device=dev)
+    have, idx0 = 0, 0
+    chunk = min(max(n, 1 << 16) * 2, 1 << 25)
+    buf = torch.empty((chunk, 8), dtype=torch.float64, device=dev)
+    ph = torch.ones(chunk, dtype=torch.uint8, device=dev)
+    ver = torch.empty(chunk, dtype=torch.uint8, device=dev)
+    while have < n:
+        t.sample_states_dev(seed, stream_id, idx0, chunk, buf.data_ptr(), cur)
+        t.valid_states_dev(chunk, buf.data_ptr(), ph.data_ptr(), ver.data_ptr(), 0, cur)
+        keep = (ver == 1) & (buf[:, 0] >= x[0] + 0.5) & (buf[:, 0] <= x[-1] - 0.5) & (buf[:, 1] >= y[0] + 0.5) & (buf[:, 1] <= y[-1] - 0.5)
+        sel = buf[keep]
+        m = min(len(sel), n - have)
+        states[have:have + m] = sel[:m]
+        have += m
+        idx0 += chunk
+    del buf, ph, ver, keep, sel
+    actions = torch.empty((n, 10), dtype=torch.float64, device=dev)
+    capi.sample_actions_dev(seed, stream_id + 1, 0, n, actions.data_ptr(), (0.0, 0.0, 1.0), cur)
+    direction = (torch.arange(n, device=dev) % 2).to(torch.uint8)
+    verdict = torch.empty(n, dtype=torch.uint8, device=dev)
+    flags = torch.empty(n, dtype=torch.uint8, device=dev)
+    s_new = torch.empty((n, 8), dtype=torch.float64, device=dev)
+    t_new = torch.empty(n, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        t.validate_pairs_dev(n, states.data_ptr(), actions.data_ptr(), direction.data_ptr(), 0, args.variant, verdict.data_ptr(),
+                             flags.data_ptr(), s_new.data_ptr(), t_new.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clk:
+        ev[0].record()
+        for i in range(args.steps):
+            step()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    cnt = t.validate_counters()
+    n_valid = int(verdict.sum().item())
+    assert n_valid == cnt["valid"], "verdict array and kernel counters disagree"
+
+    # ---- final gather of per-rank statistics over NCCL (NVLink): {valid, k, L, oog, near}
+    stats = torch.tensor([cnt["valid"], cnt["substates"], cnt["lookups"], cnt["oog"], cnt["near"], n], dtype=torch.int64, device=dev)
+    if world > 1:
+        gathered = [torch.empty_like(stats) for _ in range(world)] if rank == 0 else None
+        dist.gather(stats, gathered, dst=0)
+        all_stats = torch.stack(gathered).cpu().numpy() if rank == 0 else None
+    else:
+        all_stats = stats.cpu().numpy()[None]
+
+    # ---- e2e: host buffers through the host-pointer C-ABI call (copies inside the timed region)
+    e2e = None
+    if args.e2e_steps > 0:
+        hs = torch.empty((n, 8), dtype=torch.float64, pin_memory=True); hs.copy_(states)
+        ha = torch.empty((n, 10), dtype=torch.float64, pin_memory=True); ha.copy_(actions)
+        hd = torch.empty(n, dtype=torch.uint8, pin_memory=True); hd.copy_(direction)
+        hv = torch.empty(n, dtype=torch.uint8, pin_memory=True); hf = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        hsn = torch.empty((n, 8), dtype=torch.float64, pin_memory=True); htn = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        torch.cuda.synchronize()
+        import ctypes as C
+        L = gbp.lib()
+        vp = lambda tt: C.c_void_p(tt.data_ptr())
+
+        def e2e_step():
+            rc = L.gbp_validate_pairs(t.h, C.c_int64(n), vp(hs), vp(ha), vp(hd), 0, args.variant, vp(hv), vp(hf), vp(hsn), vp(htn))
+            assert rc == 0, L.gbp_last_error()
+
+        e2e_step()  # warm-up (allocations, page locking effects)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert int(hv.sum().item()) == n_valid and torch.equal(hv, verdict.cpu()), "e2e verdicts differ from the resident run"
+        e2e = {"value": world * n * args.e2e_steps / float(te.item()), "unit": "validated actions/s",
+               "h2d_bytes_per_step": n * (64 + 80 + 1), "d2h_bytes_per_step": n * (1 + 1 + 64 + 8), "steps": args.e2e_steps,
+               "api": "gbp_validate_pairs (host pointers, pinned), 3-deep chunked H2D/kernel/D2H pipeline"}
+        del hs, ha, hd, hv, hf, hsn, htn
+
+    # ---- secondary metric: solved plans/s (BASELINE configs[4], scaled to a short run)
+    plans = None
+    if not args.no_plans:
+        try:
+            import bench_plans
+            plans = bench_plans.run(gbp, torch, dist, dev, rank, world)
+        except Exception as e:  # the secondary metric must never take the headline down
+            plans = {"error": f"{type(e).__name__}: {e}"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_validate_refill): algorithmic bytes / launch duration
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    cell_bytes = t.cell_bytes
+    k_tot, L_tot = cnt["substates"], cnt["lookups"]
+    alg_bytes = n * B_IO + 4 * cell_bytes * (L_tot + k_tot)
+    launch_ms = float(np.mean(per_launch_ms))
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_validate_refill<float>" if args.variant in (0, 3) else f"variant {args.variant}",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
+                "bytes_per_candidate": alg_bytes / n, "k_mean": k_tot / n, "L_mean": L_tot / n,
+                "note": "fp64-issue/latency-bound gather pipeline; see DESIGN.md for the fp64 ceiling"}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    cpu = None
+    if not args.no_cpu:
+        cpu, ref_out, (cs, ca, cd) = run_cpu(seed, 100, args.cpu_seconds, cores, "reference")
+        # the sample is the head of rank 0's batch: verdict bits must agree with the GPU's
+        m = len(cs)
+        same_inputs = bool(np.array_equal(states[:m].cpu().numpy().view(np.uint64), cs.view(np.uint64)))
+        agree = bool(np.array_equal(np.asarray(ref_out[0]), verdict[:m].cpu().numpy()))
+        cpu["gpu_verdicts_equal_on_sample"] = agree and same_inputs
+
+    value = world * n * args.steps / (total_ms_max * 1e-3)
+    line = {"metric": "validated_actions_per_s", "value": value, "unit": "validated actions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clk.summary(),
+            "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "valid_fraction": float(all_stats[:, 0].sum() / all_stats[:, 5].sum()),
+            "flagged": {"out_of_grid": int(all_stats[:, 3].sum()), "libm_guard_band": int(all_stats[:, 4].sum())},
+            "per_rank_valid": [int(v) for v in all_stats[:, 0]], "plans": plans}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -171,6 +171,10 @@ class Terrain:
         _check(lib().gbp_valid_states(self.h, C.c_int64(n), _p(s), _p(ph), _p(v), _p(fl)))
         return v, fl
 
+    def valid_states_dev(self, n, states_ptr, phase_ptr, verdict_ptr, flags_ptr=0, stream=0):
+        vp = lambda p: C.c_void_p(p) if p else None
+        _check(lib().gbp_valid_states_dev(self.h, C.c_int64(n), vp(states_ptr), vp(phase_ptr), vp(verdict_ptr), vp(flags_ptr), vp(stream)))
+
     def validate_pairs(self, states, actions, direction, adaptive=False, variant=0):
         """isValidStateActionPair[Reverse] on HOST arrays -> verdict, flags, s_new, t_new."""
         s, a = _f64(states, (-1, 8)), _f64(actions, (-1, 10)); n = len(s); d = _u8(direction, n)

@@ -289,6 +289,16 @@ int gbp_valid_states(const gbp_terrain *t, int64_t n, const double *states, cons
 	CU(cudaStreamSynchronize(st));
 	return GBP_OK;
 }
+int gbp_valid_states_dev(const gbp_terrain *t, int64_t n, const double *states, const uint8_t *phase, uint8_t *verdict, uint8_t *flags,
+						 void *stream) {
+	if (!t || n < 0 || (n && (!states || !phase || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = (cudaStream_t) stream;
+	if (t->view.cell_f32) k_valid_states<float><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, states, phase, verdict, flags);
+	else k_valid_states<double><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, states, phase, verdict, flags);
+	CU(cudaGetLastError());
+	return GBP_OK;
+}
 int gbp_distance(int kind, int64_t n, const double *q1, const double *q2, double *out) {
 	if (kind < 0 || kind > 2 || n < 0 || (n && (!q1 || !q2 || !out))) return fail(GBP_E_INVALID, "bad arguments");
 	if (n == 0) return GBP_OK;

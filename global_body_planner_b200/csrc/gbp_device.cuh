@@ -258,50 +258,220 @@ __device__ __forceinline__ bool is_valid_action(const double a[10]) {  // :519-5
 	return true;
 }
 
-__device__ __forceinline__ void note_margin(double m, unsigned &flags) {
-	if (fabs(m) < NEAR_MARGIN) flags |= GBP_FLAG_NEAR;
+// =====================================================================================================
+// Fast validity path.  Everything computed INSIDE isValidState only feeds threshold comparisons, so it
+// needs guard-band accuracy, not bit equality: each clearance / reach comparison records whether its
+// margin is below NEAR_MARGIN (1e-9 m, GBP_FLAG_NEAR), and the arithmetic below is accurate to
+// ~1e-12 m (fp64 with explicit FMAs, IEEE reciprocal, algebraic yaw, polynomial sin/cos on |pitch|<1).
+// A candidate that is not flagged NEAR therefore has the same verdict as the reference's libm-based
+// evaluation, by an error bound instead of by instruction order.  Exact (bit-identical) arithmetic is
+// kept for everything that is OUTPUT: s_new, t_new, the time grid, distances, tree values.
+// Control flow: branch-free over the 10 terrain probes (all loads issued up front, no intra-warp
+// divergence); the reference's early-exit order is reproduced afterwards, in integer logic, for the
+// verdict, the OOG/NEAR flags and the k / L work counters.
+struct Pose6 { double x, y, z, dx, dy, pitch; };  // the components isValidState reads
+
+struct Probe {
+	double h;       // bilinear ground height
+	bool nan;       // any of the 4 cells NaN
+	bool oog;       // outside [x0,x_last) x [y0,y_last)
+};
+
+__device__ __forceinline__ int find_cell_fast(const double *__restrict__ ax, int n, double v, double a0, double alast, double inv,
+											  bool &oog, double &lo_v, double &hi_v) {
+	oog = !(v >= a0) || !(v < alast);
+	double g = (v - a0) * inv;
+	int i = oog ? 0 : (int) g;
+	i = max(0, min(i, n - 2));
+	double a = __ldg(ax + i), b = __ldg(ax + i + 1);
+	if (!oog && !(a <= v && v < b)) {  // rare: rounding of the guess, or a non-uniform axis
+		if (v < a && i > 0 && __ldg(ax + i - 1) <= v) --i;
+		else if (v >= b && i < n - 2 && v < __ldg(ax + i + 2)) ++i;
+		else {
+			int lo = 0, hi = n - 1;
+			while (hi - lo > 1) {
+				int mid = (lo + hi) >> 1;
+				if (__ldg(ax + mid) <= v) lo = mid; else hi = mid;
+			}
+			i = lo;
+		}
+		a = __ldg(ax + i);
+		b = __ldg(ax + i + 1);
+	}
+	lo_v = a;
+	hi_v = b;
+	return i;
 }
 
-// isValidState (:562-635).  Check order and early returns follow the reference, so the counters
-// and the OOG flag describe exactly the probes the reference would have made.
 template <typename CellT>
-__device__ __forceinline__ bool is_valid_state(const TerrainView &T, const double s[8], int phase, Counters &c) {
-	c.substates++;
-	c.nanprobes++;
-	double h_c;
-	// the centre cell search also serves the map-bounds test below
-	if (nan_and_height<CellT>(T, s[0], s[1], c.flags, h_c)) return false;
-	if (s[0] < T.x0 || s[0] > T.x_last || s[1] < T.y0 || s[1] > T.y_last || fabs(s[6]) >= P_MAX)
-		return false;
-	if (sqrt(s[3] * s[3] + s[4] * s[4]) > V_MAX) return false;
-	double yaw = atan2(s[4], s[3]);
-	double sy, cy, sp, cp;
-	sincos(yaw, &sy, &cy);
-	sincos(s[6], &sp, &cp);
-	double R11 = cy * cp, R12 = -sy, R13 = cy * sp, R21 = sy * cp, R22 = cy, R23 = sy * sp, R31 = -sp, R32 = 0, R33 = cp;
-	const double zb = -ROBOT_H;
-#pragma unroll
-	for (int i = 0; i < 2; ++i) {
-#pragma unroll
-		for (int j = 0; j < 2; ++j) {
-			const double xb = i == 0 ? -0.5 * ROBOT_L : 0.5 * ROBOT_L, yb = j == 0 ? -0.5 * ROBOT_W : 0.5 * ROBOT_W;
-			double xl = s[0] + R11 * xb + R12 * yb, yl = s[1] + R21 * xb + R22 * yb, zl = s[2] + R31 * xb + R32 * yb;
-			double xc = xl + R13 * zb, yc = yl + R23 * zb, zc = zl + R33 * zb;
-			double h_leg;
-			c.nanprobes++;
-			if (nan_and_height<CellT>(T, xl, yl, c.flags, h_leg)) return false;
-			c.lookups += 2;
-			double leg_h = zl - h_leg;
-			double cor_h = zc - ground_height<CellT>(T, xc, yc, c.flags);
-			note_margin(cor_h - H_MIN, c.flags);
-			if (phase == GBP_STANCE) note_margin(leg_h - H_MAX, c.flags);
-			if (cor_h < H_MIN || (phase == GBP_STANCE && leg_h > H_MAX)) return false;
-		}
+__device__ __forceinline__ Probe probe_fast(const TerrainView &T, double x, double y) {
+	Probe p;
+	bool ox, oy;
+	double x1, x2, y1, y2, f11, f12, f21, f22;
+	int ix = find_cell_fast(T.x, T.nx, x, T.x0, T.x_last, T.inv_dx, ox, x1, x2);
+	int iy = find_cell_fast(T.y, T.ny, y, T.y0, T.y_last, T.inv_dy, oy, y1, y2);
+	load_quad<CellT>((const CellT *) T.z, T.ny, ix, iy, f11, f12, f21, f22);
+	p.oog = ox || oy;
+	p.nan = (f11 != f11) || (f12 != f12) || (f21 != f21) || (f22 != f22);
+	const double ax = x2 - x, bx = x - x1, ay = y2 - y, by = y - y1;
+	const double w = __drcp_rn((x2 - x1) * (y2 - y1));
+	const double lo = __fma_rn(f21, bx, f11 * ax), hi = __fma_rn(f22, bx, f12 * ax);
+	p.h = w * __fma_rn(hi, by, lo * ay);
+	return p;
+}
+
+// sin / cos on |x| < 1 (pitch is rejected at |pitch| >= P_MAX = 1 before it is used): Taylor to x^19 / x^18
+__device__ __forceinline__ void sincos_small(double x, double &sn, double &cs) {
+	const double z = x * x;
+	double ps = -1.0 / 121645100408832000.0;  // -1/19!
+	ps = __fma_rn(ps, z, 1.0 / 355687428096000.0);
+	ps = __fma_rn(ps, z, -1.0 / 1307674368000.0);
+	ps = __fma_rn(ps, z, 1.0 / 6227020800.0);
+	ps = __fma_rn(ps, z, -1.0 / 39916800.0);
+	ps = __fma_rn(ps, z, 1.0 / 362880.0);
+	ps = __fma_rn(ps, z, -1.0 / 5040.0);
+	ps = __fma_rn(ps, z, 1.0 / 120.0);
+	ps = __fma_rn(ps, z, -1.0 / 6.0);
+	sn = __fma_rn(x * z, ps, x);
+	double pc = -1.0 / 6402373705728000.0;  // -1/18!
+	pc = __fma_rn(pc, z, 1.0 / 20922789888000.0);
+	pc = __fma_rn(pc, z, -1.0 / 87178291200.0);
+	pc = __fma_rn(pc, z, 1.0 / 479001600.0);
+	pc = __fma_rn(pc, z, -1.0 / 3628800.0);
+	pc = __fma_rn(pc, z, 1.0 / 40320.0);
+	pc = __fma_rn(pc, z, -1.0 / 720.0);
+	pc = __fma_rn(pc, z, 1.0 / 24.0);
+	pc = __fma_rn(pc, z, -0.5);
+	cs = __fma_rn(z, pc, 1.0);
+}
+// cos / sin of yaw = atan2(dy, dx) without libm: the unit vector (dx, dy) / r
+__device__ __forceinline__ void yaw_cs(double dx, double dy, double r, double &cy, double &sy) {
+	if (r > 1e-150) {
+		const double inv = 1.0 / r;
+		cy = dx * inv;
+		sy = dy * inv;
+	} else if (dx == 0.0 && dy == 0.0) {  // atan2(+-0, +0) = +-0, atan2(+-0, -0) = +-pi
+		const bool neg = __double_as_longlong(dx) < 0;
+		cy = neg ? -1.0 : 1.0;
+		sy = neg ? copysign(1.2246467991473532e-16, dy) : dy;
+	} else {  // r underflowed: rescale
+		const double m = fmax(fabs(dx), fabs(dy)), ux = dx / m, uy = dy / m, inv = 1.0 / sqrt(ux * ux + uy * uy);
+		cy = ux * inv;
+		sy = uy * inv;
 	}
-	c.lookups += 1;
-	double h = (s[2] + R33 * zb) - ground_height<CellT>(T, s[0] + R13 * zb, s[1] + R23 * zb, c.flags);
-	note_margin(h - H_MIN, c.flags);
-	return !(h < H_MIN);
+}
+
+template <typename CellT>
+__device__ __forceinline__ bool is_valid_state_fast(const TerrainView &T, const Pose6 &s, int phase, Counters &c) {
+	// ---- stage A: everything the reference would compute, without early exits
+	const Probe pc = probe_fast<CellT>(T, s.x, s.y);
+	const bool pre_bad = (s.x < T.x0) || (s.x > T.x_last) || (s.y < T.y0) || (s.y > T.y_last) || (fabs(s.pitch) >= P_MAX);
+	const double r = sqrt(s.dx * s.dx + s.dy * s.dy);  // exact: the speed test is a hard comparison (:572)
+	const bool speed_bad = r > V_MAX;
+	double cy, sy, sp, cp;
+	yaw_cs(s.dx, s.dy, r, cy, sy);
+	sincos_small(pre_bad ? 0.0 : s.pitch, sp, cp);
+	const double R11 = cy * cp, R12 = -sy, R13 = cy * sp, R21 = sy * cp, R22 = cy, R23 = sy * sp, R31 = -sp, R33 = cp;
+	const double zb = -ROBOT_H;
+	Probe pl[4], pk[4];
+	double zl[4], zc[4];
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const double xb = (k & 2) ? 0.5 * ROBOT_L : -0.5 * ROBOT_L, yb = (k & 1) ? 0.5 * ROBOT_W : -0.5 * ROBOT_W;
+		const double xl = __fma_rn(R12, yb, __fma_rn(R11, xb, s.x)), yl = __fma_rn(R22, yb, __fma_rn(R21, xb, s.y));
+		zl[k] = __fma_rn(R31, xb, s.z);
+		zc[k] = __fma_rn(R33, zb, zl[k]);
+		pl[k] = probe_fast<CellT>(T, xl, yl);
+		pk[k] = probe_fast<CellT>(T, __fma_rn(R13, zb, xl), __fma_rn(R23, zb, yl));
+	}
+	const Probe pb = probe_fast<CellT>(T, __fma_rn(R13, zb, s.x), __fma_rn(R23, zb, s.y));
+	// ---- stage B: the reference's check order (:564-634) replayed on the precomputed pieces, as
+	// straight-line predicate arithmetic (no branches: the compiler must not sink the probe loads
+	// behind early exits, and the warp must not diverge).
+	const bool stance = phase == GBP_STANCE;
+	unsigned flags = pc.oog ? GBP_FLAG_OOG : 0u, nanprobes = 1, lookups = 0;
+	bool alive = !(pc.nan || pre_bad || speed_bad);
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		nanprobes += alive ? 1u : 0u;
+		flags |= (alive && pl[k].oog) ? GBP_FLAG_OOG : 0u;
+		const bool reached = alive && !pl[k].nan;
+		lookups += reached ? 2u : 0u;
+		flags |= (reached && pk[k].oog) ? GBP_FLAG_OOG : 0u;
+		const double leg_h = zl[k] - pl[k].h, cor_h = zc[k] - pk[k].h;
+		const bool near = (fabs(cor_h - H_MIN) < NEAR_MARGIN) || (stance && fabs(leg_h - H_MAX) < NEAR_MARGIN);
+		flags |= (reached && near) ? GBP_FLAG_NEAR : 0u;
+		const bool bad = (cor_h < H_MIN) || (stance && leg_h > H_MAX);
+		alive = reached && !bad;
+	}
+	lookups += alive ? 1u : 0u;
+	flags |= (alive && pb.oog) ? GBP_FLAG_OOG : 0u;
+	const double h = __fma_rn(R33, zb, s.z) - pb.h;
+	flags |= (alive && fabs(h - H_MIN) < NEAR_MARGIN) ? GBP_FLAG_NEAR : 0u;
+	c.substates += 1;
+	c.nanprobes += nanprobes;
+	c.lookups += lookups;
+	c.flags |= flags;
+	return alive && !(h < H_MIN);
+}
+__device__ __forceinline__ Pose6 pose6(const double s[8]) {
+	Pose6 p;
+	p.x = s[0]; p.y = s[1]; p.z = s[2]; p.dx = s[3]; p.dy = s[4]; p.pitch = s[6];
+	return p;
+}
+
+// Fast propagation of the 6 components isValidState reads.  c3* = (a_to - a_td) / (6 ts), precomputed per candidate.
+struct FastPrim {
+	double inv6ts, inv2ts;
+};
+__device__ __forceinline__ Pose6 stance_fast(const double s[8], const double a[10], const FastPrim &f, double t) {
+	Pose6 o;
+	const double t2 = t * t;
+	const double jx = (a[3] - a[0]), jy = (a[4] - a[1]), jz = (a[5] - a[2]), jp = (a[9] - a[8]);
+	o.x = __fma_rn(jx * f.inv6ts, t2 * t, __fma_rn(0.5 * a[0], t2, __fma_rn(s[3], t, s[0])));
+	o.y = __fma_rn(jy * f.inv6ts, t2 * t, __fma_rn(0.5 * a[1], t2, __fma_rn(s[4], t, s[1])));
+	o.z = __fma_rn(jz * f.inv6ts, t2 * t, __fma_rn(0.5 * a[2], t2, __fma_rn(s[5], t, s[2])));
+	o.pitch = __fma_rn(jp * f.inv6ts, t2 * t, __fma_rn(0.5 * a[8], t2, __fma_rn(s[7], t, s[6])));
+	o.dx = __fma_rn(jx * f.inv2ts, t2, __fma_rn(a[0], t, s[3]));
+	o.dy = __fma_rn(jy * f.inv2ts, t2, __fma_rn(a[1], t, s[4]));
+	return o;
+}
+// full 8-component fast stance end state (needed as the take-off state of the flight phase)
+__device__ __forceinline__ void stance_fast8(const double s[8], const double a[10], const FastPrim &f, double t, double o[8]) {
+	const double t2 = t * t;
+#pragma unroll
+	for (int d = 0; d < 4; ++d) {
+		const int ip = d < 3 ? d : 6, iv = d < 3 ? 3 + d : 7, itd = d < 3 ? d : 8, ito = d < 3 ? 3 + d : 9;
+		const double j = a[ito] - a[itd];
+		o[ip] = __fma_rn(j * f.inv6ts, t2 * t, __fma_rn(0.5 * a[itd], t2, __fma_rn(s[iv], t, s[ip])));
+		o[iv] = __fma_rn(j * f.inv2ts, t2, __fma_rn(a[itd], t, s[iv]));
+	}
+}
+__device__ __forceinline__ Pose6 flight_fast(const double s[8], double t) {
+	Pose6 o;
+	o.x = __fma_rn(s[3], t, s[0]);
+	o.y = __fma_rn(s[4], t, s[1]);
+	o.z = __fma_rn(-0.5 * 9.81 * t, t, __fma_rn(s[5], t, s[2]));
+	o.dx = s[3];
+	o.dy = s[4];
+	o.pitch = __fma_rn(s[7], t, s[6]);
+	return o;
+}
+// applyStanceReverse (:324-367) restricted to the 6 components, from the take-off state `s`
+__device__ __forceinline__ Pose6 stance_reverse_fast(const double s[8], const double a[10], const FastPrim &f, double t) {
+	Pose6 o;
+	const double ts = a[6], dt = ts - t, d2 = ts * ts - t * t, d3 = ts * ts * ts - t * t * t;
+	double p[4], v[2];
+#pragma unroll
+	for (int d = 0; d < 4; ++d) {
+		const int ip = d < 3 ? d : 6, iv = d < 3 ? 3 + d : 7, itd = d < 3 ? d : 8, ito = d < 3 ? 3 + d : 9;
+		const double j = a[ito] - a[itd];
+		const double cc = s[iv] - a[itd] * ts - 0.5 * j * ts;
+		p[d] = s[ip] - cc * dt - 0.5 * a[itd] * d2 - j * d3 * f.inv6ts;
+		if (d < 2) v[d] = s[iv] - a[itd] * dt - j * d2 * f.inv2ts;
+	}
+	o.x = p[0]; o.y = p[1]; o.z = p[2]; o.pitch = p[3]; o.dx = v[0]; o.dy = v[1];
+	return o;
 }
 
 // ---- distances (:106-127, planning_utils.h:133-145)

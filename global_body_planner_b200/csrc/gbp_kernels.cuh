@@ -91,7 +91,7 @@ __global__ void k_valid_states(TerrainView T, int64_t n, const double *__restric
 #pragma unroll
 	for (int d = 0; d < 8; ++d) ss[d] = s[8 * i + d];
 	Counters c = {0, 0, 0, 0};
-	bool ok = is_valid_state<CellT>(T, ss, phase[i], c);
+	bool ok = is_valid_state_fast<CellT>(T, pose6(ss), phase[i], c);
 	out[i] = ok ? 1 : 0;
 	if (flags) flags[i] = (uint8_t) (c.flags | (ok ? GBP_FLAG_VALID : 0));
 }
@@ -154,6 +154,7 @@ struct Cursor {
 	double s[8], a[10];
 	double t, step, t_ok, t_new, t_ls;  // t_ls: time of the last valid stance sample (s_new on flight failure)
 	int phase, have_ls;
+	FastPrim f;
 	Counters c;
 };
 
@@ -165,6 +166,8 @@ __device__ __forceinline__ void cursor_start(Cursor &q, int dir) {
 	q.have_ls = 0;
 	q.c = {0, 0, 0, 0};
 	const double ts = q.a[6], tf = q.a[7];
+	q.f.inv6ts = 1.0 / (6.0 * ts);
+	q.f.inv2ts = 1.0 / (2.0 * ts);
 	if (dir == GBP_FORWARD) {
 		q.t = 0;
 		q.phase = (0 <= ts) ? PH_FWD_ST : ((0 < tf) ? PH_FWD_FL : PH_FWD_LAND);
@@ -174,21 +177,25 @@ __device__ __forceinline__ void cursor_start(Cursor &q, int dir) {
 		else { q.t = ts; q.phase = (ts >= 0) ? PH_REV_ST : PH_REV_START; }
 	}
 }
-// state to check at the cursor
-__device__ __forceinline__ void cursor_state(const Cursor &q, double chk[8]) {
+// isValidState of the sub-state at the cursor, through the fast validity path (guard-band accuracy;
+// the exact propagation is only used for outputs, see cursor_advance)
+template <typename CellT>
+__device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q) {
+	Pose6 p;
 	double tmp[8];
 	switch (q.phase) {
-	case PH_FWD_ST: apply_stance(q.s, q.a, q.t, chk); break;
-	case PH_FWD_FL: apply_stance(q.s, q.a, q.a[6], tmp); apply_flight(tmp, q.t, chk); break;
-	case PH_FWD_LAND: apply_stance(q.s, q.a, q.a[6], tmp); apply_flight(tmp, q.a[7], chk); break;
-	case PH_REV_FL: apply_flight(q.s, -q.t, chk); break;
-	case PH_REV_ST: apply_flight(q.s, -q.a[7], tmp); apply_stance_reverse(tmp, q.a, q.t, chk); break;
-	default: apply_flight(q.s, -q.a[7], tmp); apply_stance_reverse(tmp, q.a, 0, chk); break;
+	case PH_FWD_ST: p = stance_fast(q.s, q.a, q.f, q.t); break;
+	case PH_FWD_FL:
+	case PH_FWD_LAND: stance_fast8(q.s, q.a, q.f, q.a[6], tmp); p = flight_fast(tmp, q.phase == PH_FWD_FL ? q.t : q.a[7]); break;
+	case PH_REV_FL: p = flight_fast(q.s, -q.t); break;
+	default: apply_flight(q.s, -q.a[7], tmp); p = stance_reverse_fast(tmp, q.a, q.f, q.phase == PH_REV_ST ? q.t : 0.0); break;
 	}
+	const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
+	return is_valid_state_fast<CellT>(T, p, ph, q.c);
 }
 // Advance after the verdict of the current sub-state.  Returns 0 = continue, 1 = finished invalid,
 // 2 = finished valid.  On finish, s_new / t_new hold the reference's outputs.
-__device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, const double chk[8], bool adaptive, double s_new[8]) {
+__device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, bool adaptive, double s_new[8]) {
 	const double ts = q.a[6], tf = q.a[7];
 	switch (q.phase) {
 	case PH_FWD_ST:
@@ -222,7 +229,7 @@ __device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, const doubl
 			else { for (int i = 0; i < 8; ++i) s_new[i] = q.s[i]; }
 			return 1;
 		}
-		for (int i = 0; i < 8; ++i) s_new[i] = chk[i];
+		{ double tmp[8]; apply_stance(q.s, q.a, ts, tmp); apply_flight(tmp, tf, s_new); }  // exact s_land (:743-749)
 		q.t_new = ts + tf;
 		return 2;
 	case PH_REV_FL:
@@ -252,7 +259,7 @@ __device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, const doubl
 			else { for (int i = 0; i < 8; ++i) s_new[i] = q.s[i]; }
 			return 1;
 		}
-		for (int i = 0; i < 8; ++i) s_new[i] = chk[i];
+		{ double tmp[8]; apply_flight(q.s, -tf, tmp); apply_stance_reverse(tmp, q.a, 0, s_new); }  // exact s_start (:866-872)
 		q.t_new = ts;
 		return 2;
 	}
@@ -271,11 +278,8 @@ __device__ __forceinline__ bool validate_pair_seq(const TerrainView &T, const do
 	cursor_start(q, direction);
 	int r = 0;
 	while (true) {
-		double chk[8];
-		cursor_state(q, chk);
-		const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
-		bool valid = is_valid_state<CellT>(T, chk, ph, q.c);
-		r = cursor_advance(q, valid, chk, adaptive, s_new);
+		const bool valid = cursor_check<CellT>(T, q);
+		r = cursor_advance(q, valid, adaptive, s_new);
 		if (r) break;
 	}
 	t_new = q.t_new;
@@ -368,14 +372,14 @@ __device__ bool validate_pair_warp(const TerrainView &T, const double s[8], cons
 		double t = bt;
 		for (int i = 0; i < lane && ph != PH_DONE; ++i) walk_step(ph, t, ts, tf);
 		const bool active = ph != PH_DONE;
-		double chk[8];
 		Counters lc = {0, 0, 0, 0};
 		bool valid = true;
 		if (active) {
 			q.phase = ph;
 			q.t = t;
-			cursor_state(q, chk);
-			valid = is_valid_state<CellT>(T, chk, (ph == PH_FWD_FL || ph == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE, lc);
+			q.c = {0, 0, 0, 0};
+			valid = cursor_check<CellT>(T, q);
+			lc = q.c;
 		}
 		const unsigned bad = __ballot_sync(FULL, active && !valid);
 		const int f = bad ? __ffs(bad) - 1 : 32;
@@ -405,11 +409,10 @@ __device__ bool validate_pair_warp(const TerrainView &T, const double s[8], cons
 			return false;
 		}
 		const unsigned term = __ballot_sync(FULL, active && (ph == PH_FWD_LAND || ph == PH_REV_START));
-		if (term) {  // landing / exact start state reached and valid
-			const int src = __ffs(term) - 1;
-#pragma unroll
-			for (int i = 0; i < 8; ++i) s_new[i] = __shfl_sync(FULL, chk[i], src);
-			t_new = direction == GBP_FORWARD ? ts + tf : ts;
+		if (term) {  // landing / exact start state reached and valid: exact outputs
+			double tmp[8];
+			if (direction == GBP_FORWARD) { apply_stance(s, a, ts, tmp); apply_flight(tmp, tf, s_new); t_new = ts + tf; }
+			else { apply_flight(s, -tf, tmp); apply_stance_reverse(tmp, a, 0, s_new); t_new = ts; }
 			return true;
 		}
 		bph = __shfl_sync(FULL, ph, 31);
@@ -473,16 +476,11 @@ __global__ void __launch_bounds__(128) k_validate_refill(TerrainView T, int64_t 
 			next += __popc(need);
 		}
 		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) break;
-		double chk[8];
 		bool valid = true;
-		if (q.phase != PH_IDLE) {
-			cursor_state(q, chk);
-			const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
-			valid = is_valid_state<CellT>(T, chk, ph, q.c);
-		}
+		if (q.phase != PH_IDLE) valid = cursor_check<CellT>(T, q);
 		if (q.phase != PH_IDLE) {
 			double sn[8];
-			int r = cursor_advance(q, valid, chk, adaptive != 0, sn);
+			int r = cursor_advance(q, valid, adaptive != 0, sn);
 			if (r) {
 				const bool ok = r == 2;
 				verdict[mine] = ok ? 1 : 0;

@@ -91,6 +91,8 @@ int gbp_valid_actions(int64_t n, const double *actions, uint8_t *verdict);
 /* isValidState (planning_utils.cpp:562-635); phase has n entries */
 int gbp_valid_states(const gbp_terrain *t, int64_t n, const double *states, const uint8_t *phase, uint8_t *verdict,
                      uint8_t *flags);
+int gbp_valid_states_dev(const gbp_terrain *t, int64_t n, const double *states, const uint8_t *phase, uint8_t *verdict,
+                         uint8_t *flags, void *stream);
 /* poseDistance / stateDistance / stateYawDistance (planning_utils.cpp:106-127, planning_utils.h:133-145);
  * kind 0 / 1 / 2 */
 int gbp_distance(int kind, int64_t n, const double *q1, const double *q2, double *out);
