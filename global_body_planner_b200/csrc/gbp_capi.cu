@@ -335,10 +335,13 @@ int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states
 		else k_validate_warp<double><<<grid, 128, 0, st>>>(t->view, n, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt);
 	} else {
 		// persistent-style geometry: a multiple of the SM count; each warp owns a contiguous range
-		const int threads = 128, warps_per_block = threads / 32;
-		int64_t max_warps = (int64_t) sm_count() * 16;  // 16 resident warps per SM at this register budget
+		const int threads = RF_WARPS * 32, warps_per_block = RF_WARPS;
+		int64_t max_warps = (int64_t) sm_count() * 12;  // 16 resident warps per SM at this register budget
 		int64_t per_warp = (n + max_warps - 1) / max_warps;
 		if (per_warp < 64) per_warp = 64;
+		per_warp = (per_warp + RF_CHUNK - 1) / RF_CHUNK * RF_CHUNK;  // chunks of the TMA ring are 32-aligned
+		if ((((uintptr_t) states) | ((uintptr_t) actions) | ((uintptr_t) direction)) & 15)
+			return fail(GBP_E_INVALID, "states/actions/direction must be 16-byte aligned (TMA bulk copies)");
 		int64_t warps = (n + per_warp - 1) / per_warp;
 		unsigned grid = (unsigned) ((warps + warps_per_block - 1) / warps_per_block);
 		if (f32) k_validate_refill<float><<<grid, threads, 0, st>>>(t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);

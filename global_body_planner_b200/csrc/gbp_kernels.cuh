@@ -445,35 +445,109 @@ __global__ void __launch_bounds__(128) k_validate_warp(TerrainView T, int64_t n,
 }
 
 // ------------------------------------------------------------------ validate_pairs, variant 3 (refill)
+// Candidate inputs are streamed through shared memory by the TMA (1-D bulk copies, cp.async.bulk ->
+// SASS UBLKCP): each warp owns a contiguous, 32-aligned range of candidates and keeps a 2-deep ring
+// of 32-candidate chunks {states 2 KiB, actions 2.5 KiB, directions 32 B}; one elected lane issues
+// the copies two chunks ahead and an mbarrier per ring slot signals arrival, so a lane that refills
+// reads its next candidate from shared memory instead of stalling on an HBM round trip.
+constexpr int RF_CHUNK = 32, RF_NBUF = 2, RF_WARPS = 4;
+constexpr int RF_SLOT_BYTES = RF_CHUNK * (64 + 80) + RF_CHUNK;  // 4640
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_LOOP:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra WAIT_DONE;\n"
+		"bra WAIT_LOOP;\n"
+		"WAIT_DONE:\n"
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+				 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+				 : "memory");
+}
+
 template <typename CellT>
-__global__ void __launch_bounds__(128) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
-														  const double *__restrict__ states, const double *__restrict__ actions,
-														  const uint8_t *__restrict__ dir, int adaptive,
-														  uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
-														  double *__restrict__ s_new, double *__restrict__ t_new,
-														  unsigned long long *__restrict__ cnt) {
-	const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(RF_WARPS * 32, 3) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
+																   const double *__restrict__ states, const double *__restrict__ actions,
+																   const uint8_t *__restrict__ dir, int adaptive,
+																   uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
+																   double *__restrict__ s_new, double *__restrict__ t_new,
+																   unsigned long long *__restrict__ cnt) {
+	__shared__ __align__(128) unsigned char ring[RF_WARPS][RF_NBUF][RF_SLOT_BYTES + 112];  // slots padded to 128 B multiples
+	__shared__ __align__(8) uint64_t bars[RF_WARPS][RF_NBUF];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
-	int64_t next = warp * per_warp;
-	const int64_t end = min(n, next + per_warp);
+	const int64_t wbase = warp * per_warp;  // per_warp is a multiple of RF_CHUNK
+	const int64_t end = min(n, wbase + per_warp);
+	const int nchunks = wbase < end ? (int) ((end - wbase + RF_CHUNK - 1) / RF_CHUNK) : 0;
+	int64_t next = wbase;
+	int issued = 0;
+	if (lane == 0) {
+		for (int k = 0; k < RF_NBUF; ++k) mbar_init(&bars[wib][k], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+	auto issue = [&](int c) {  // lane 0 only: chunk c -> ring slot c % RF_NBUF
+		const int slot = c % RF_NBUF;
+		const int64_t c0 = wbase + (int64_t) c * RF_CHUNK;
+		const int m = (int) min((int64_t) RF_CHUNK, end - c0);
+		unsigned char *dst = ring[wib][slot];
+		const unsigned dbytes = (m == RF_CHUNK) ? RF_CHUNK : 0;  // a partial (tail) chunk reads its directions from global memory
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of this slot precede the async write
+		mbar_expect_tx(&bars[wib][slot], (unsigned) m * (64 + 80) + dbytes);
+		tma_load_1d(dst, states + 8 * c0, (unsigned) m * 64, &bars[wib][slot]);
+		tma_load_1d(dst + RF_CHUNK * 64, actions + 10 * c0, (unsigned) m * 80, &bars[wib][slot]);
+		if (dbytes) tma_load_1d(dst + RF_CHUNK * 144, dir + c0, dbytes, &bars[wib][slot]);
+	};
+	if (lane == 0) {
+		for (; issued < nchunks && issued < RF_NBUF; ++issued) issue(issued);
+	}
+	issued = __shfl_sync(FULL, issued, 0);
 	Cursor q;
 	q.phase = PH_IDLE;
 	int64_t mine = -1;
 	unsigned long long k = 0, L = 0, np = 0, oog = 0, near = 0, nvalid = 0;
 	while (true) {
 		// refill idle lanes from the warp's range, in lane order
-		unsigned need = __ballot_sync(FULL, q.phase == PH_IDLE);
-		if (need) {
+		const unsigned need = __ballot_sync(FULL, q.phase == PH_IDLE);
+		if (need && next < end) {
 			if (q.phase == PH_IDLE) {
-				int64_t idx = next + __popc(need & ((1u << lane) - 1));
+				const int64_t idx = next + __popc(need & ((1u << lane) - 1));
 				if (idx < end) {
+					const int c = (int) ((idx - wbase) / RF_CHUNK), slot = c % RF_NBUF, j = (int) ((idx - wbase) % RF_CHUNK);
+					mbar_wait(&bars[wib][slot], (unsigned) ((c / RF_NBUF) & 1));
+					const unsigned char *src = ring[wib][slot];
+					const double2 *ps = reinterpret_cast<const double2 *>(src + j * 64);
+					const double2 *pa = reinterpret_cast<const double2 *>(src + RF_CHUNK * 64 + j * 80);
+#pragma unroll
+					for (int d = 0; d < 4; ++d) { double2 v = ps[d]; q.s[2 * d] = v.x; q.s[2 * d + 1] = v.y; }
+#pragma unroll
+					for (int d = 0; d < 5; ++d) { double2 v = pa[d]; q.a[2 * d] = v.x; q.a[2 * d + 1] = v.y; }
+					const bool full_chunk = (wbase + (int64_t) (c + 1) * RF_CHUNK) <= end;
+					const int dv = full_chunk ? (int) src[RF_CHUNK * 144 + j] : (int) __ldg(dir + idx);
 					mine = idx;
-					load_state(states + 8 * idx, q.s);
-					load_action(actions + 10 * idx, q.a);
-					cursor_start(q, dir[idx]);
+					cursor_start(q, dv);
 				}
 			}
-			next += __popc(need);
+			next = min(end, next + (int64_t) __popc(need));
+			__syncwarp();
+			// ring slots whose chunk is fully consumed are refilled two chunks ahead
+			const int consumed = next >= end ? nchunks : (int) ((next - wbase) / RF_CHUNK);
+			if (lane == 0) {
+				for (; issued < nchunks && issued < consumed + RF_NBUF; ++issued) issue(issued);
+			}
+			issued = __shfl_sync(FULL, issued, 0);
 		}
 		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) break;
 		bool valid = true;
@@ -485,8 +559,12 @@ __global__ void __launch_bounds__(128) k_validate_refill(TerrainView T, int64_t 
 				const bool ok = r == 2;
 				verdict[mine] = ok ? 1 : 0;
 				if (flags) flags[mine] = (uint8_t) (q.c.flags | (ok ? GBP_FLAG_VALID : 0));
-				if (s_new) store_state(s_new + 8 * mine, sn);
-				if (t_new) t_new[mine] = q.t_new;
+				if (s_new) {
+					double2 *o = reinterpret_cast<double2 *>(s_new + 8 * mine);
+#pragma unroll
+					for (int d = 0; d < 4; ++d) __stcs(o + d, make_double2(sn[2 * d], sn[2 * d + 1]));
+				}
+				if (t_new) __stcs(t_new + mine, q.t_new);
 				k += q.c.substates; L += q.c.lookups; np += q.c.nanprobes;
 				oog += (q.c.flags & GBP_FLAG_OOG) ? 1 : 0; near += (q.c.flags & GBP_FLAG_NEAR) ? 1 : 0; nvalid += ok ? 1 : 0;
 				q.phase = PH_IDLE;
