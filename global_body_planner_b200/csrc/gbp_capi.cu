@@ -65,6 +65,20 @@ int upload(Dev &d, const T *host, size_t n, cudaStream_t st) {
 	return GBP_OK;
 }
 
+// kernel instantiation by map kind: fp32 / fp64 cells x uniform / general axes
+#define GBP_LAUNCH_(K, M, CFG, ST, ...) K<M><<<GBP_UNPACK CFG, 0, ST>>>(__VA_ARGS__)
+#define GBP_UNPACK(...) __VA_ARGS__
+#define GBP_DISPATCH(VIEW, K, CFG, ST, ...)                                                  \
+	do {                                                                                     \
+		if ((VIEW).cell_f32) {                                                               \
+			if ((VIEW).uniform) GBP_LAUNCH_(K, MapF32U, CFG, ST, __VA_ARGS__);               \
+			else GBP_LAUNCH_(K, MapF32N, CFG, ST, __VA_ARGS__);                              \
+		} else {                                                                             \
+			if ((VIEW).uniform) GBP_LAUNCH_(K, MapF64U, CFG, ST, __VA_ARGS__);               \
+			else GBP_LAUNCH_(K, MapF64N, CFG, ST, __VA_ARGS__);                              \
+		}                                                                                    \
+	} while (0)
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned) ((n + threads - 1) / threads); }
 
 }  // namespace
@@ -169,6 +183,12 @@ int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const d
 	v.x0 = x[0]; v.y0 = y[0]; v.x_last = x[nx - 1]; v.y_last = y[ny - 1];
 	v.inv_dx = (nx - 1) / (x[nx - 1] - x[0]);
 	v.inv_dy = (ny - 1) / (y[ny - 1] - y[0]);
+	// uniform axes (every shipped / synthetic / GridMap terrain): edges are recomputed instead of loaded
+	v.step_x = (x[nx - 1] - x[0]) / (nx - 1);
+	v.step_y = (y[ny - 1] - y[0]) / (ny - 1);
+	v.uniform = 1;
+	for (int i = 0; i < nx && v.uniform; ++i) if (fabs(x[i] - (x[0] + i * v.step_x)) > 1e-12) v.uniform = 0;
+	for (int i = 0; i < ny && v.uniform; ++i) if (fabs(y[i] - (y[0] + i * v.step_y)) > 1e-12) v.uniform = 0;
 	*out = t;
 	return GBP_OK;
 }
@@ -221,8 +241,7 @@ static int terrain_query(const gbp_terrain *t, int64_t n, const double *x, const
 	const size_t per = what == 2 ? 3 : 1;
 	if (out) CU(dout.alloc(n * per * sizeof(double)));
 	if (out8) CU(dout8.alloc(n));
-	if (t->view.cell_f32) k_terrain_query<float><<<blocks_for(n, 256), 256, 0, st>>>(t->view, n, dx.as<double>(), dy.as<double>(), what, dout.as<double>(), dout8.as<uint8_t>());
-	else k_terrain_query<double><<<blocks_for(n, 256), 256, 0, st>>>(t->view, n, dx.as<double>(), dy.as<double>(), what, dout.as<double>(), dout8.as<uint8_t>());
+	GBP_DISPATCH(t->view, k_terrain_query, (blocks_for(n, 256), 256), st, t->view, n, dx.as<double>(), dy.as<double>(), what, dout.as<double>(), dout8.as<uint8_t>());
 	CU(cudaGetLastError());
 	if (out) CU(cudaMemcpyAsync(out, dout.p, n * per * sizeof(double), cudaMemcpyDeviceToHost, st));
 	if (out8) CU(cudaMemcpyAsync(out8, dout8.p, n, cudaMemcpyDeviceToHost, st));
@@ -281,8 +300,7 @@ int gbp_valid_states(const gbp_terrain *t, int64_t n, const double *states, cons
 	if ((rc = upload(ds, states, 8 * n, st)) || (rc = upload(dp, phase, n, st))) return rc;
 	CU(dv.alloc(n));
 	if (flags) CU(df.alloc(n));
-	if (t->view.cell_f32) k_valid_states<float><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, ds.as<double>(), dp.as<uint8_t>(), dv.as<uint8_t>(), df.as<uint8_t>());
-	else k_valid_states<double><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, ds.as<double>(), dp.as<uint8_t>(), dv.as<uint8_t>(), df.as<uint8_t>());
+	GBP_DISPATCH(t->view, k_valid_states, (blocks_for(n, 128), 128), st, t->view, n, ds.as<double>(), dp.as<uint8_t>(), dv.as<uint8_t>(), df.as<uint8_t>());
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(verdict, dv.p, n, cudaMemcpyDeviceToHost, st));
 	if (flags) CU(cudaMemcpyAsync(flags, df.p, n, cudaMemcpyDeviceToHost, st));
@@ -294,8 +312,7 @@ int gbp_valid_states_dev(const gbp_terrain *t, int64_t n, const double *states, 
 	if (!t || n < 0 || (n && (!states || !phase || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
 	if (n == 0) return GBP_OK;
 	cudaStream_t st = (cudaStream_t) stream;
-	if (t->view.cell_f32) k_valid_states<float><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, states, phase, verdict, flags);
-	else k_valid_states<double><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, states, phase, verdict, flags);
+	GBP_DISPATCH(t->view, k_valid_states, (blocks_for(n, 128), 128), st, t->view, n, states, phase, verdict, flags);
 	CU(cudaGetLastError());
 	return GBP_OK;
 }
@@ -326,13 +343,11 @@ int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states
 	if (variant == 0) variant = 3;
 	const bool f32 = t->view.cell_f32 != 0;
 	if (variant == 1) {
-		if (f32) k_validate_thread<float><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
-		else k_validate_thread<double><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
+		GBP_DISPATCH(t->view, k_validate_thread, (blocks_for(n, 128), 128), st, t->view, n, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
 	} else if (variant == 2) {
 		const int64_t warps_per_block = 4;
 		unsigned grid = (unsigned) ((n + warps_per_block - 1) / warps_per_block);
-		if (f32) k_validate_warp<float><<<grid, 128, 0, st>>>(t->view, n, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt);
-		else k_validate_warp<double><<<grid, 128, 0, st>>>(t->view, n, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt);
+		GBP_DISPATCH(t->view, k_validate_warp, (grid, 128), st, t->view, n, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt);
 	} else {
 		// persistent-style geometry: a multiple of the SM count; each warp owns a contiguous range
 		const int threads = RF_WARPS * 32, warps_per_block = RF_WARPS;
@@ -344,8 +359,7 @@ int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states
 			return fail(GBP_E_INVALID, "states/actions/direction must be 16-byte aligned (TMA bulk copies)");
 		int64_t warps = (n + per_warp - 1) / per_warp;
 		unsigned grid = (unsigned) ((warps + warps_per_block - 1) / warps_per_block);
-		if (f32) k_validate_refill<float><<<grid, threads, 0, st>>>(t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
-		else k_validate_refill<double><<<grid, threads, 0, st>>>(t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
+		GBP_DISPATCH(t->view, k_validate_refill, (grid, threads), st, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
 	}
 	CU(cudaGetLastError());
 	return GBP_OK;
@@ -449,8 +463,7 @@ int gbp_sample_actions(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n,
 }
 static int sample_states_launch(const gbp_terrain *t, uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, int dir, double thr,
 								int speed, const double *d_from, const double *d_to, double *d_out, cudaStream_t st) {
-	if (t->view.cell_f32) k_sample_states<float><<<blocks_for(n, 256), 256, 0, st>>>(t->view, seed, stream, idx0, n, dir, thr, speed, d_from, d_to, d_out);
-	else k_sample_states<double><<<blocks_for(n, 256), 256, 0, st>>>(t->view, seed, stream, idx0, n, dir, thr, speed, d_from, d_to, d_out);
+	GBP_DISPATCH(t->view, k_sample_states, (blocks_for(n, 256), 256), st, t->view, seed, stream, idx0, n, dir, thr, speed, d_from, d_to, d_out);
 	CU(cudaGetLastError());
 	return GBP_OK;
 }
@@ -633,8 +646,7 @@ int gbp_extend(gbp_tree *T, const gbp_terrain *t, const double *target, int dire
 	cudaStream_t st = lib_stream();
 	CU(cudaMemcpyAsync(T->d_target, target, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
 	k_nearest<<<1, 256, 0, st>>>(T->view, 1, T->d_target, T->S.near_idx, T->S.near_dist);
-	if (t->view.cell_f32) k_extend_candidates<float><<<blocks_for(K, 128), 128, 0, st>>>(t->view, T->view, T->d_target, direction, K, adaptive, seed, stream, idx0, T->S);
-	else k_extend_candidates<double><<<blocks_for(K, 128), 128, 0, st>>>(t->view, T->view, T->d_target, direction, K, adaptive, seed, stream, idx0, T->S);
+	GBP_DISPATCH(t->view, k_extend_candidates, (blocks_for(K, 128), 128), st, t->view, T->view, T->d_target, direction, K, adaptive, seed, stream, idx0, T->S);
 	k_extend_select<<<1, 256, 0, st>>>(t->view, T->view, T->d_target, K, best_of_k, seed, stream, idx0, T->S);
 	CU(cudaGetLastError());
 	int res[4] = {0, -1, 0, 0};
@@ -657,8 +669,7 @@ int gbp_attempt_connect(const gbp_terrain *t, int64_t n, const double *s_existin
 	CU(dsn.alloc(sizeof(double) * 8 * n));
 	CU(dan.alloc(sizeof(double) * 10 * n));
 	if (flags) CU(dfl.alloc(n));
-	if (t->view.cell_f32) k_attempt_connect<float><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, de.as<double>(), ds.as<double>(), dd.as<uint8_t>(), adaptive, dst.as<int>(), dsn.as<double>(), dan.as<double>(), dfl.as<uint8_t>());
-	else k_attempt_connect<double><<<blocks_for(n, 128), 128, 0, st>>>(t->view, n, de.as<double>(), ds.as<double>(), dd.as<uint8_t>(), adaptive, dst.as<int>(), dsn.as<double>(), dan.as<double>(), dfl.as<uint8_t>());
+	GBP_DISPATCH(t->view, k_attempt_connect, (blocks_for(n, 128), 128), st, t->view, n, de.as<double>(), ds.as<double>(), dd.as<uint8_t>(), adaptive, dst.as<int>(), dsn.as<double>(), dan.as<double>(), dfl.as<uint8_t>());
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(status, dst.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemcpyAsync(s_new, dsn.p, sizeof(double) * 8 * n, cudaMemcpyDeviceToHost, st));
@@ -672,8 +683,7 @@ int gbp_connect(gbp_tree *T, const gbp_terrain *t, const double *target, int dir
 	cudaStream_t st = lib_stream();
 	CU(cudaMemcpyAsync(T->d_target, target, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
 	k_nearest<<<1, 256, 0, st>>>(T->view, 1, T->d_target, T->S.near_idx, T->S.near_dist);
-	if (t->view.cell_f32) k_connect<float><<<1, 32, 0, st>>>(t->view, T->view, T->d_target, direction, adaptive, T->S);
-	else k_connect<double><<<1, 32, 0, st>>>(t->view, T->view, T->d_target, direction, adaptive, T->S);
+	GBP_DISPATCH(t->view, k_connect, (1, 32), st, t->view, T->view, T->d_target, direction, adaptive, T->S);
 	CU(cudaGetLastError());
 	int res[4] = {0, -1, 0, 0};
 	CU(cudaMemcpyAsync(res, T->S.result, sizeof res, cudaMemcpyDeviceToHost, st));

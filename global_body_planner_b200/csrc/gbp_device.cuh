@@ -29,7 +29,16 @@ struct TerrainView {
 	int cell_f32;
 	double x0, y0, x_last, y_last;  // axis end points (bounds test of isValidState, OOG test)
 	double inv_dx, inv_dy;          // O(1) cell guess: i ~ (v - x0) * inv_dx
+	int uniform;                    // both axes are x0 + i*step to within 1e-12 m: the fast path computes cell edges
+	double step_x, step_y;          // instead of loading them (a probe within 1e-11 m of a grid line is flagged NEAR)
 };
+
+// map traits: cell storage type x axis kind
+template <typename C, bool U> struct MapKind { using cell = C; static constexpr bool uniform = U; };
+using MapF32U = MapKind<float, true>;
+using MapF32N = MapKind<float, false>;
+using MapF64U = MapKind<double, true>;
+using MapF64N = MapKind<double, false>;
 
 struct Counters {  // work under the reference's early-exit semantics, per candidate
 	unsigned substates, lookups, nanprobes, flags;
@@ -137,9 +146,6 @@ __device__ __forceinline__ int find_cell(const double *__restrict__ ax, int n, d
 }
 
 template <typename CellT>
-struct Quad { double f11, f12, f21, f22; };
-
-template <typename CellT>
 __device__ __forceinline__ void load_quad(const CellT *__restrict__ layer, int ny, int ix, int iy, double &f11, double &f12,
 										  double &f21, double &f22) {
 	const CellT *p = layer + (size_t) ix * ny + iy;
@@ -155,28 +161,28 @@ __device__ __forceinline__ double bilinear(double f11, double f12, double f21, d
 		   (f11 * (x2 - x) * (y2 - y) + f21 * (x - x1) * (y2 - y) + f12 * (x2 - x) * (y - y1) + f22 * (x - x1) * (y - y1));
 }
 
-template <typename CellT>
+template <typename M>
 __device__ __forceinline__ double ground_height(const TerrainView &T, double x, double y, unsigned &flags) {  // :94-132
 	double x1, x2, y1, y2, f11, f12, f21, f22;
 	int ix = find_cell(T.x, T.nx, x, T.x0, T.x_last, T.inv_dx, flags, x1, x2);
 	int iy = find_cell(T.y, T.ny, y, T.y0, T.y_last, T.inv_dy, flags, y1, y2);
-	load_quad<CellT>((const CellT *) T.z, T.ny, ix, iy, f11, f12, f21, f22);
+	load_quad<typename M::cell>((const typename M::cell *) T.z, T.ny, ix, iy, f11, f12, f21, f22);
 	return bilinear(f11, f12, f21, f22, x1, x2, y1, y2, x, y);
 }
 // heightIsNan (:135-157) and getGroundHeight of the SAME point share one cell search and one quad
-template <typename CellT>
+template <typename M>
 __device__ __forceinline__ bool nan_and_height(const TerrainView &T, double x, double y, unsigned &flags, double &h) {
 	double x1, x2, y1, y2, f11, f12, f21, f22;
 	int ix = find_cell(T.x, T.nx, x, T.x0, T.x_last, T.inv_dx, flags, x1, x2);
 	int iy = find_cell(T.y, T.ny, y, T.y0, T.y_last, T.inv_dy, flags, y1, y2);
-	load_quad<CellT>((const CellT *) T.z, T.ny, ix, iy, f11, f12, f21, f22);
+	load_quad<typename M::cell>((const typename M::cell *) T.z, T.ny, ix, iy, f11, f12, f21, f22);
 	h = bilinear(f11, f12, f21, f22, x1, x2, y1, y2, x, y);
 	return (f11 != f11) || (f12 != f12) || (f21 != f21) || (f22 != f22);
 }
-template <typename CellT>
+template <typename M>
 __device__ __forceinline__ bool height_is_nan(const TerrainView &T, double x, double y, unsigned &flags) {
 	double h;
-	return nan_and_height<CellT>(T, x, y, flags, h);
+	return nan_and_height<M>(T, x, y, flags, h);
 }
 __device__ __forceinline__ void surface_normal(const TerrainView &T, double x, double y, double n[3], unsigned &flags) {  // :160-213
 	double x1, x2, y1, y2, f11, f12, f21, f22;
@@ -275,7 +281,9 @@ struct Probe {
 	double h;       // bilinear ground height
 	bool nan;       // any of the 4 cells NaN
 	bool oog;       // outside [x0,x_last) x [y0,y_last)
+	bool edge;      // (uniform axes only) within EDGE_MARGIN of a grid line: the cell choice is not certain
 };
+constexpr double EDGE_MARGIN = 1e-11;  // computed edges / probe positions are within ~1e-12 m of the reference's
 
 __device__ __forceinline__ int find_cell_fast(const double *__restrict__ ax, int n, double v, double a0, double alast, double inv,
 											  bool &oog, double &lo_v, double &hi_v) {
@@ -303,20 +311,47 @@ __device__ __forceinline__ int find_cell_fast(const double *__restrict__ ax, int
 	return i;
 }
 
-template <typename CellT>
+// Uniform axis: cell index and cell-relative coordinate without touching the axis array.
+// u = (v - a0)/step - i in [0,1); the edges are within ~1e-13 m of the stored axis values.
+__device__ __forceinline__ int cell_uniform(int n, double v, double a0, double alast, double inv, double step, bool &oog, bool &edge,
+											 double &u) {
+	oog = !(v >= a0) || !(v < alast);
+	const double g = oog ? 0.0 : (v - a0) * inv;
+	int i = min((int) g, n - 2);
+	const double fi = (double) i;
+	u = oog ? (v - a0) * inv : g - fi;  // out of grid: extrapolate from cell 0 (defined semantics)
+	const double d = fmin(u, 1.0 - u) * step;
+	edge = !oog && d < EDGE_MARGIN;
+	return oog ? 0 : i;
+}
+
+template <typename M>
 __device__ __forceinline__ Probe probe_fast(const TerrainView &T, double x, double y) {
 	Probe p;
 	bool ox, oy;
-	double x1, x2, y1, y2, f11, f12, f21, f22;
-	int ix = find_cell_fast(T.x, T.nx, x, T.x0, T.x_last, T.inv_dx, ox, x1, x2);
-	int iy = find_cell_fast(T.y, T.ny, y, T.y0, T.y_last, T.inv_dy, oy, y1, y2);
-	load_quad<CellT>((const CellT *) T.z, T.ny, ix, iy, f11, f12, f21, f22);
+	double f11, f12, f21, f22;
+	if (M::uniform) {
+		bool ex, ey;
+		double ux, uy;
+		const int ix = cell_uniform(T.nx, x, T.x0, T.x_last, T.inv_dx, T.step_x, ox, ex, ux);
+		const int iy = cell_uniform(T.ny, y, T.y0, T.y_last, T.inv_dy, T.step_y, oy, ey, uy);
+		load_quad<typename M::cell>((const typename M::cell *) T.z, T.ny, ix, iy, f11, f12, f21, f22);
+		p.edge = ex || ey;
+		const double lo = __fma_rn(f21 - f11, ux, f11), hi = __fma_rn(f22 - f12, ux, f12);
+		p.h = __fma_rn(hi - lo, uy, lo);
+	} else {
+		double x1, x2, y1, y2;
+		const int ix = find_cell_fast(T.x, T.nx, x, T.x0, T.x_last, T.inv_dx, ox, x1, x2);
+		const int iy = find_cell_fast(T.y, T.ny, y, T.y0, T.y_last, T.inv_dy, oy, y1, y2);
+		load_quad<typename M::cell>((const typename M::cell *) T.z, T.ny, ix, iy, f11, f12, f21, f22);
+		p.edge = false;
+		const double ax = x2 - x, bx = x - x1, ay = y2 - y, by = y - y1;
+		const double w = __drcp_rn((x2 - x1) * (y2 - y1));
+		const double lo = __fma_rn(f21, bx, f11 * ax), hi = __fma_rn(f22, bx, f12 * ax);
+		p.h = w * __fma_rn(hi, by, lo * ay);
+	}
 	p.oog = ox || oy;
 	p.nan = (f11 != f11) || (f12 != f12) || (f21 != f21) || (f22 != f22);
-	const double ax = x2 - x, bx = x - x1, ay = y2 - y, by = y - y1;
-	const double w = __drcp_rn((x2 - x1) * (y2 - y1));
-	const double lo = __fma_rn(f21, bx, f11 * ax), hi = __fma_rn(f22, bx, f12 * ax);
-	p.h = w * __fma_rn(hi, by, lo * ay);
 	return p;
 }
 
@@ -361,10 +396,10 @@ __device__ __forceinline__ void yaw_cs(double dx, double dy, double r, double &c
 	}
 }
 
-template <typename CellT>
+template <typename M>
 __device__ __forceinline__ bool is_valid_state_fast(const TerrainView &T, const Pose6 &s, int phase, Counters &c) {
 	// ---- stage A: everything the reference would compute, without early exits
-	const Probe pc = probe_fast<CellT>(T, s.x, s.y);
+	const Probe pc = probe_fast<M>(T, s.x, s.y);
 	const bool pre_bad = (s.x < T.x0) || (s.x > T.x_last) || (s.y < T.y0) || (s.y > T.y_last) || (fabs(s.pitch) >= P_MAX);
 	const double r = sqrt(s.dx * s.dx + s.dy * s.dy);  // exact: the speed test is a hard comparison (:572)
 	const bool speed_bad = r > V_MAX;
@@ -381,23 +416,25 @@ __device__ __forceinline__ bool is_valid_state_fast(const TerrainView &T, const 
 		const double xl = __fma_rn(R12, yb, __fma_rn(R11, xb, s.x)), yl = __fma_rn(R22, yb, __fma_rn(R21, xb, s.y));
 		zl[k] = __fma_rn(R31, xb, s.z);
 		zc[k] = __fma_rn(R33, zb, zl[k]);
-		pl[k] = probe_fast<CellT>(T, xl, yl);
-		pk[k] = probe_fast<CellT>(T, __fma_rn(R13, zb, xl), __fma_rn(R23, zb, yl));
+		pl[k] = probe_fast<M>(T, xl, yl);
+		pk[k] = probe_fast<M>(T, __fma_rn(R13, zb, xl), __fma_rn(R23, zb, yl));
 	}
-	const Probe pb = probe_fast<CellT>(T, __fma_rn(R13, zb, s.x), __fma_rn(R23, zb, s.y));
+	const Probe pb = probe_fast<M>(T, __fma_rn(R13, zb, s.x), __fma_rn(R23, zb, s.y));
 	// ---- stage B: the reference's check order (:564-634) replayed on the precomputed pieces, as
 	// straight-line predicate arithmetic (no branches: the compiler must not sink the probe loads
 	// behind early exits, and the warp must not diverge).
 	const bool stance = phase == GBP_STANCE;
-	unsigned flags = pc.oog ? GBP_FLAG_OOG : 0u, nanprobes = 1, lookups = 0;
+	unsigned flags = (pc.oog ? GBP_FLAG_OOG : 0u) | (pc.edge ? GBP_FLAG_NEAR : 0u), nanprobes = 1, lookups = 0;
 	bool alive = !(pc.nan || pre_bad || speed_bad);
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
 		nanprobes += alive ? 1u : 0u;
 		flags |= (alive && pl[k].oog) ? GBP_FLAG_OOG : 0u;
+		flags |= (alive && pl[k].edge) ? GBP_FLAG_NEAR : 0u;
 		const bool reached = alive && !pl[k].nan;
 		lookups += reached ? 2u : 0u;
 		flags |= (reached && pk[k].oog) ? GBP_FLAG_OOG : 0u;
+		flags |= (reached && pk[k].edge) ? GBP_FLAG_NEAR : 0u;
 		const double leg_h = zl[k] - pl[k].h, cor_h = zc[k] - pk[k].h;
 		const bool near = (fabs(cor_h - H_MIN) < NEAR_MARGIN) || (stance && fabs(leg_h - H_MAX) < NEAR_MARGIN);
 		flags |= (reached && near) ? GBP_FLAG_NEAR : 0u;
@@ -406,6 +443,7 @@ __device__ __forceinline__ bool is_valid_state_fast(const TerrainView &T, const 
 	}
 	lookups += alive ? 1u : 0u;
 	flags |= (alive && pb.oog) ? GBP_FLAG_OOG : 0u;
+	flags |= (alive && pb.edge) ? GBP_FLAG_NEAR : 0u;
 	const double h = __fma_rn(R33, zb, s.z) - pb.h;
 	flags |= (alive && fabs(h - H_MIN) < NEAR_MARGIN) ? GBP_FLAG_NEAR : 0u;
 	c.substates += 1;
@@ -533,7 +571,7 @@ __device__ __forceinline__ void sample_action(uint64_t seed, uint64_t stream, ui
 	a[9] = clampd(sd * z1, -ANG_ACC_MAX, ANG_ACC_MAX);
 }
 // PlannerClass::randomState (planner_class.cpp:38-76) / randomStateDirection (:82-148)
-template <typename CellT>
+template <typename M>
 __device__ __forceinline__ void sample_state(const TerrainView &T, uint64_t seed, uint64_t stream, uint64_t idx, bool dir_flag,
 											 double dir_thresh, bool speed_dir, const double *s_from, const double *s_to,
 											 double q[8]) {
@@ -558,7 +596,7 @@ __device__ __forceinline__ void sample_state(const TerrainView &T, uint64_t seed
 	unsigned fl = 0;
 	q[0] = (x_max - x_min) * u0 + x_min;
 	q[1] = (y_max - y_min) * u1 + y_min;
-	q[2] = clampd(mean + sd * z0, z_min_rel, z_max_rel) + ground_height<CellT>(T, q[0], q[1], fl);
+	q[2] = clampd(mean + sd * z0, z_min_rel, z_max_rel) + ground_height<M>(T, q[0], q[1], fl);
 	double cos_theta = 2.0 * u5 - 1.0, sin_theta = sqrt(1.0 - cos_theta * cos_theta), v = u6 * V_MAX;
 	if (directional && speed_dir) {
 		double ddx = s_to[0] - s_from[0], ddy = s_to[1] - s_from[1], nrm = sqrt(ddx * ddx + ddy * ddy);

@@ -37,17 +37,17 @@ __device__ __forceinline__ int tree_push(const TreeView &T, int parent, const do
 }
 
 // ------------------------------------------------------------------ small batched queries
-template <typename CellT>
+template <typename M>
 __global__ void k_terrain_query(TerrainView T, int64_t n, const double *__restrict__ x, const double *__restrict__ y, int what,
 								double *__restrict__ out, uint8_t *__restrict__ out8) {
 	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	unsigned fl = 0;
 	if (what == 0) {
-		out[i] = ground_height<CellT>(T, x[i], y[i], fl);
+		out[i] = ground_height<M>(T, x[i], y[i], fl);
 		if (out8) out8[i] = (uint8_t) fl;
 	} else if (what == 1) {
-		out8[i] = height_is_nan<CellT>(T, x[i], y[i], fl) ? 1 : 0;
+		out8[i] = height_is_nan<M>(T, x[i], y[i], fl) ? 1 : 0;
 	} else {
 		double nn[3];
 		surface_normal(T, x[i], y[i], nn, fl);
@@ -82,7 +82,7 @@ __global__ void k_valid_actions(int64_t n, const double *__restrict__ a, uint8_t
 	out[i] = is_valid_action(aa) ? 1 : 0;
 }
 
-template <typename CellT>
+template <typename M>
 __global__ void k_valid_states(TerrainView T, int64_t n, const double *__restrict__ s, const uint8_t *__restrict__ phase,
 							   uint8_t *__restrict__ out, uint8_t *__restrict__ flags) {
 	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
@@ -91,7 +91,7 @@ __global__ void k_valid_states(TerrainView T, int64_t n, const double *__restric
 #pragma unroll
 	for (int d = 0; d < 8; ++d) ss[d] = s[8 * i + d];
 	Counters c = {0, 0, 0, 0};
-	bool ok = is_valid_state_fast<CellT>(T, pose6(ss), phase[i], c);
+	bool ok = is_valid_state_fast<M>(T, pose6(ss), phase[i], c);
 	out[i] = ok ? 1 : 0;
 	if (flags) flags[i] = (uint8_t) (c.flags | (ok ? GBP_FLAG_VALID : 0));
 }
@@ -179,7 +179,7 @@ __device__ __forceinline__ void cursor_start(Cursor &q, int dir) {
 }
 // isValidState of the sub-state at the cursor, through the fast validity path (guard-band accuracy;
 // the exact propagation is only used for outputs, see cursor_advance)
-template <typename CellT>
+template <typename M>
 __device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q) {
 	Pose6 p;
 	double tmp[8];
@@ -191,7 +191,7 @@ __device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q) {
 	default: apply_flight(q.s, -q.a[7], tmp); p = stance_reverse_fast(tmp, q.a, q.f, q.phase == PH_REV_ST ? q.t : 0.0); break;
 	}
 	const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
-	return is_valid_state_fast<CellT>(T, p, ph, q.c);
+	return is_valid_state_fast<M>(T, p, ph, q.c);
 }
 // Advance after the verdict of the current sub-state.  Returns 0 = continue, 1 = finished invalid,
 // 2 = finished valid.  On finish, s_new / t_new hold the reference's outputs.
@@ -267,7 +267,7 @@ __device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, bool adapti
 
 // Sequential walk of one pair by one thread: the cursor machine below run to completion.  Same
 // semantics as planning_utils.cpp:651-753 (forward) and :774-876 (reverse).
-template <typename CellT>
+template <typename M>
 __device__ __forceinline__ bool validate_pair_seq(const TerrainView &T, const double s[8], const double a[10], int direction,
 												  bool adaptive, double s_new[8], double &t_new, Counters &c) {
 	Cursor q;
@@ -278,7 +278,7 @@ __device__ __forceinline__ bool validate_pair_seq(const TerrainView &T, const do
 	cursor_start(q, direction);
 	int r = 0;
 	while (true) {
-		const bool valid = cursor_check<CellT>(T, q);
+		const bool valid = cursor_check<M>(T, q);
 		r = cursor_advance(q, valid, adaptive, s_new);
 		if (r) break;
 	}
@@ -288,7 +288,7 @@ __device__ __forceinline__ bool validate_pair_seq(const TerrainView &T, const do
 }
 
 // attemptConnect (src/rrt_connect.cpp:20-91), recursion unrolled into a loop (see oracle/gbp_oracle.c)
-template <typename CellT>
+template <typename M>
 __device__ int attempt_connect(const TerrainView &T, const double s_existing[8], const double s_in[8], int direction,
 							   bool adaptive, double s_new[8], double a_new[10], Counters &c, unsigned &pair_checks) {
 	double target[8], ts = pose_distance(s_in, s_existing) / V_NOM;
@@ -301,7 +301,7 @@ __device__ int attempt_connect(const TerrainView &T, const double s_existing[8],
 		if (!is_valid_action(a_new)) return GBP_TRAPPED;
 		double out[8], tn;
 		++pair_checks;
-		bool ok = validate_pair_seq<CellT>(T, s_existing, a_new, direction, adaptive, out, tn, c);
+		bool ok = validate_pair_seq<M>(T, s_existing, a_new, direction, adaptive, out, tn, c);
 #pragma unroll
 		for (int i = 0; i < 8; ++i) { s_new[i] = out[i]; target[i] = out[i]; }
 		if (ok) return depth == 0 ? GBP_REACHED : GBP_ADVANCED;
@@ -311,7 +311,7 @@ __device__ int attempt_connect(const TerrainView &T, const double s_existing[8],
 
 // ------------------------------------------------------------------ validate_pairs, variant 1
 // One thread per action, sub-states walked sequentially in the reference's order.
-template <typename CellT>
+template <typename M>
 __global__ void __launch_bounds__(128) k_validate_thread(TerrainView T, int64_t n, const double *__restrict__ states,
 														  const double *__restrict__ actions, const uint8_t *__restrict__ dir,
 														  int adaptive, uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(128) k_validate_thread(TerrainView T, int64_t 
 		double s[8], a[10], sn[8], tn;
 		load_state(states + 8 * i, s);
 		load_action(actions + 10 * i, a);
-		ok = validate_pair_seq<CellT>(T, s, a, dir[i], adaptive != 0, sn, tn, c);
+		ok = validate_pair_seq<M>(T, s, a, dir[i], adaptive != 0, sn, tn, c);
 		verdict[i] = ok ? 1 : 0;
 		if (flags) flags[i] = (uint8_t) (c.flags | (ok ? GBP_FLAG_VALID : 0));
 		if (s_new) store_state(s_new + 8 * i, sn);
@@ -352,7 +352,7 @@ __device__ __forceinline__ void walk_step(int &ph, double &t, double ts, double 
 	}
 }
 // All 32 lanes call this with identical (warp-uniform) s, a, direction; outputs are uniform too.
-template <typename CellT>
+template <typename M>
 __device__ bool validate_pair_warp(const TerrainView &T, const double s[8], const double a[10], int direction, double s_new[8],
 								   double &t_new, Counters &c) {
 	const int lane = threadIdx.x & 31;
@@ -378,7 +378,7 @@ __device__ bool validate_pair_warp(const TerrainView &T, const double s[8], cons
 			q.phase = ph;
 			q.t = t;
 			q.c = {0, 0, 0, 0};
-			valid = cursor_check<CellT>(T, q);
+			valid = cursor_check<M>(T, q);
 			lc = q.c;
 		}
 		const unsigned bad = __ballot_sync(FULL, active && !valid);
@@ -420,7 +420,7 @@ __device__ bool validate_pair_warp(const TerrainView &T, const double s[8], cons
 		walk_step(bph, bt, ts, tf);
 	}
 }
-template <typename CellT>
+template <typename M>
 __global__ void __launch_bounds__(128) k_validate_warp(TerrainView T, int64_t n, const double *__restrict__ states,
 														const double *__restrict__ actions, const uint8_t *__restrict__ dir,
 														uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(128) k_validate_warp(TerrainView T, int64_t n,
 	load_state(states + 8 * i, s);
 	load_action(actions + 10 * i, a);
 	Counters c = {0, 0, 0, 0};
-	const bool ok = validate_pair_warp<CellT>(T, s, a, dir[i], sn, tn, c);
+	const bool ok = validate_pair_warp<M>(T, s, a, dir[i], sn, tn, c);
 	if ((threadIdx.x & 31) == 0) {
 		verdict[i] = ok ? 1 : 0;
 		if (flags) flags[i] = (uint8_t) (c.flags | (ok ? GBP_FLAG_VALID : 0));
@@ -477,7 +477,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 				 : "memory");
 }
 
-template <typename CellT>
+template <typename M>
 __global__ void __launch_bounds__(RF_WARPS * 32, 3) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
 																   const double *__restrict__ states, const double *__restrict__ actions,
 																   const uint8_t *__restrict__ dir, int adaptive,
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) k_validate_refill(TerrainVie
 		}
 		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) break;
 		bool valid = true;
-		if (q.phase != PH_IDLE) valid = cursor_check<CellT>(T, q);
+		if (q.phase != PH_IDLE) valid = cursor_check<M>(T, q);
 		if (q.phase != PH_IDLE) {
 			double sn[8];
 			int r = cursor_advance(q, valid, adaptive != 0, sn);
@@ -591,7 +591,7 @@ __global__ void k_sample_actions(uint64_t seed, uint64_t stream, uint64_t idx0, 
 #pragma unroll
 	for (int d = 0; d < 5; ++d) q[d] = make_double2(a[2 * d], a[2 * d + 1]);
 }
-template <typename CellT>
+template <typename M>
 __global__ void k_sample_states(TerrainView T, uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, int dir_flag,
 								double dir_thresh, int speed_dir, const double *__restrict__ s_from, const double *__restrict__ s_to,
 								double *__restrict__ out) {
@@ -602,7 +602,7 @@ __global__ void k_sample_states(TerrainView T, uint64_t seed, uint64_t stream, u
 #pragma unroll
 		for (int d = 0; d < 8; ++d) { sf[d] = s_from[d]; st[d] = s_to[d]; }
 	}
-	sample_state<CellT>(T, seed, stream, idx0 + (uint64_t) i, dir_flag != 0, dir_thresh, speed_dir != 0, sf, st, q);
+	sample_state<M>(T, seed, stream, idx0 + (uint64_t) i, dir_flag != 0, dir_thresh, speed_dir != 0, sf, st, q);
 	store_state(out + 8 * i, q);
 }
 
@@ -744,7 +744,7 @@ struct ExtendScratch {
 	double *s_test;      // [K][8]
 	int *result;         // [4] status, new id, first-valid index / checks, pad
 };
-template <typename CellT>
+template <typename M>
 __global__ void __launch_bounds__(128) k_extend_candidates(TerrainView T, TreeView tree, const double *__restrict__ target,
 															int direction, int K, int adaptive, uint64_t seed, uint64_t stream,
 															uint64_t idx0, ExtendScratch S) {
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(128) k_extend_candidates(TerrainView T, TreeVi
 	grf_rotation(nn, R);
 	sample_action(seed, stream, idx0 + (uint64_t) j, R, false, 0.0, nullptr, nullptr, a);
 	Counters c = {0, 0, 0, 0};
-	bool ok = validate_pair_seq<CellT>(T, s_near, a, direction, adaptive != 0, sn, tn, c);
+	bool ok = validate_pair_seq<M>(T, s_near, a, direction, adaptive != 0, sn, tn, c);
 	S.valid[j] = ok ? 1 : 0;
 	S.dist[j] = ok ? state_distance(sn, tg) : INFINITY;
 	store_state(S.s_test + 8 * (size_t) j, sn);
@@ -817,7 +817,7 @@ __global__ void __launch_bounds__(256) k_extend_select(TerrainView T, TreeView t
 }
 
 // ------------------------------------------------------------------ attemptConnect / connect
-template <typename CellT>
+template <typename M>
 __global__ void __launch_bounds__(128) k_attempt_connect(TerrainView T, int64_t n, const double *__restrict__ s_existing,
 														  const double *__restrict__ s, const uint8_t *__restrict__ dir, int adaptive,
 														  int *__restrict__ status, double *__restrict__ s_new,
@@ -833,14 +833,14 @@ __global__ void __launch_bounds__(128) k_attempt_connect(TerrainView T, int64_t 
 	for (int d = 0; d < 10; ++d) an[d] = 0;
 	Counters c = {0, 0, 0, 0};
 	unsigned checks = 0;
-	status[i] = attempt_connect<CellT>(T, se, sg, dir[i], adaptive != 0, sn, an, c, checks);
+	status[i] = attempt_connect<M>(T, se, sg, dir[i], adaptive != 0, sn, an, c, checks);
 	store_state(s_new + 8 * i, sn);
 #pragma unroll
 	for (int d = 0; d < 10; ++d) a_new[10 * i + d] = an[d];
 	if (flags) flags[i] = (uint8_t) c.flags;
 }
 // connect (rrt_connect.cpp:98-120) after k_nearest put the neighbour into S.near_idx
-template <typename CellT>
+template <typename M>
 __global__ void k_connect(TerrainView T, TreeView tree, const double *__restrict__ target, int direction, int adaptive,
 						  ExtendScratch S) {
 	if (threadIdx.x != 0) return;
@@ -850,7 +850,7 @@ __global__ void k_connect(TerrainView T, TreeView tree, const double *__restrict
 	tree_get(tree, near, s_near);
 	Counters c = {0, 0, 0, 0};
 	unsigned checks = 0;
-	int r = attempt_connect<CellT>(T, s_near, tg, direction, adaptive != 0, sn, an, c, checks);
+	int r = attempt_connect<M>(T, s_near, tg, direction, adaptive != 0, sn, an, c, checks);
 	int new_id = -1;
 	if (r != GBP_TRAPPED) {
 		if (*tree.n < tree.cap) new_id = tree_push(tree, near, sn, an);

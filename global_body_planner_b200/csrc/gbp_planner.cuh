@@ -41,7 +41,7 @@ __device__ __forceinline__ int warp_nearest(const TreeView &T, int nv, const dou
 }
 
 // extend (rrt.cpp:77-102) on tree T toward s; returns status, appends on success.
-template <typename CellT>
+template <typename M>
 __device__ int warp_extend(const TerrainView &Tv, TreeView &T, int &nv, const double s[8], int dir, uint64_t seed, uint64_t query,
 						   uint64_t cell, const gbp_plan_params &P, int lane, long long &pair_checks) {
 	const int near = warp_nearest(T, nv, s, lane);
@@ -62,7 +62,7 @@ __device__ int warp_extend(const TerrainView &Tv, TreeView &T, int &nv, const do
 		if (j < K) {
 			sample_action(seed, query, cell * (uint64_t) K + (uint64_t) j, R, false, 0.0, nullptr, nullptr, a);
 			Counters c = {0, 0, 0, 0};
-			ok = validate_pair_seq<CellT>(Tv, s_near, a, dir, P.adaptive != 0, sn, tn, c);
+			ok = validate_pair_seq<M>(Tv, s_near, a, dir, P.adaptive != 0, sn, tn, c);
 		}
 		if (ok) {
 			const double d = state_distance(sn, s);
@@ -108,7 +108,7 @@ __device__ int warp_extend(const TerrainView &Tv, TreeView &T, int &nv, const do
 }
 
 // connect (rrt_connect.cpp:98-120)
-template <typename CellT>
+template <typename M>
 __device__ int warp_connect(const TerrainView &Tv, TreeView &T, int &nv, const double s[8], int dir, const gbp_plan_params &P,
 							int lane, long long &pair_checks) {
 	const int near = warp_nearest(T, nv, s, lane);
@@ -116,7 +116,7 @@ __device__ int warp_connect(const TerrainView &Tv, TreeView &T, int &nv, const d
 	tree_get(T, near, s_near);
 	Counters c = {0, 0, 0, 0};
 	unsigned checks = 0;
-	const int r = attempt_connect<CellT>(Tv, s_near, s, dir, P.adaptive != 0, sn, an, c, checks);
+	const int r = attempt_connect<M>(Tv, s_near, s, dir, P.adaptive != 0, sn, an, c, checks);
 	pair_checks += checks;
 	if (r != GBP_TRAPPED) {
 		if (lane == 0) tree_push(T, near, sn, an);
@@ -126,7 +126,7 @@ __device__ int warp_connect(const TerrainView &Tv, TreeView &T, int &nv, const d
 	return r;
 }
 
-template <typename CellT>
+template <typename M>
 __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, const double *__restrict__ starts,
 													 const double *__restrict__ goals, uint64_t seed, uint64_t query0,
 													 gbp_plan_params P, PlanArena A, int *__restrict__ counts,
@@ -159,15 +159,15 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 				if (nx >= A.cap || ny >= A.cap) { full = true; break; }
 				const uint64_t cell = 2 * (uint64_t) it + (uint64_t) half;
 				double s_rand[8];
-				sample_state<CellT>(Tv, seed, query, cell, false, 0.0, false, nullptr, nullptr, s_rand);
+				sample_state<M>(Tv, seed, query, cell, false, 0.0, false, nullptr, nullptr, s_rand);
 				Counters c = {0, 0, 0, 0};
-				if (!is_valid_state_fast<CellT>(Tv, pose6(s_rand), GBP_STANCE, c)) continue;  // rrt_connect.cpp:254
+				if (!is_valid_state_fast<M>(Tv, pose6(s_rand), GBP_STANCE, c)) continue;  // rrt_connect.cpp:254
 				++nn_queries;
-				if (warp_extend<CellT>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, lane, pair_checks) == GBP_TRAPPED) continue;
+				if (warp_extend<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, lane, pair_checks) == GBP_TRAPPED) continue;
 				double s_new[8];
 				tree_get(Tx, nx - 1, s_new);
 				++nn_queries;
-				if (warp_connect<CellT>(Tv, Ty, ny, s_new, dir_con, P, lane, pair_checks) == GBP_REACHED) solved = true;
+				if (warp_connect<M>(Tv, Ty, ny, s_new, dir_con, P, lane, pair_checks) == GBP_REACHED) solved = true;
 			}
 		}
 		// statistics + path (rrt_connect.cpp:269-270, :381-401, :463-466)
@@ -238,8 +238,10 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	A.y = A.g + per;
 	A.parent = (int *) (A.y + per);
 	counts = A.parent + per;
-	if (Tv.cell_f32) k_plan_batch<float><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap);
-	else k_plan_batch<double><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap);
+#define GBP_PLAN_(M) k_plan_batch<M><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap)
+	if (Tv.cell_f32) { if (Tv.uniform) GBP_PLAN_(MapF32U); else GBP_PLAN_(MapF32N); }
+	else { if (Tv.uniform) GBP_PLAN_(MapF64U); else GBP_PLAN_(MapF64N); }
+#undef GBP_PLAN_
 	e = cudaGetLastError();
 	cudaFreeAsync(mem, st);
 	if (e != cudaSuccess) { err = std::string("k_plan_batch: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
