@@ -1,0 +1,73 @@
+"""Tier-2 parity: the device-resident batch planner (gbp_plan_batch, one warp per query) against the
+iteration-budgeted oracle planner on the same Philox stream — trees, statistics and paths."""
+import numpy as np
+import pytest
+
+import pyoracle as po
+from conftest import assert_bits_equal, load_terrain
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gbp():
+    import __graft_entry__ as entry
+    entry.build()
+    import global_body_planner_b200 as g
+    assert g.device_count() > 0
+    return g
+
+
+def queries(o, T, n, seed):
+    q = o.sample_states(seed, 1, 0, 40 * n)
+    q[:, 3:8] = 0; q[:, 3] = 0.5
+    v, _ = o.valid_states(q, po.STANCE)
+    q = q[v == 1]
+    s, g = [], []
+    for i in range(len(q)):
+        d = np.hypot(q[:, 0] - q[i, 0], q[:, 1] - q[i, 1])
+        j = np.nonzero((d > 1.0) & (d < 3.0))[0]
+        if len(j):
+            s.append(q[i]); g.append(q[j[0]])
+        if len(s) == n:
+            break
+    return np.array(s), np.array(g)
+
+
+@pytest.mark.parametrize("name,K,best", [("slope", 6, 0), ("rough_terrain", 6, 0), ("slope", 48, 1), ("synth_nan", 6, 0)])
+def test_plan_batch_matches_oracle(gbp, name, K, best):
+    T = load_terrain(name)
+    o = po.Oracle(T)
+    t = gbp.Terrain(T.x, T.y, T.z, T.dx, T.dy, T.dz)
+    s, g = queries(o, T, 24, 5)
+    assert len(s) >= 8
+    P = gbp.PlanParams(K, best, 400, 256, 0, 0, 0)
+    st, ps, pa = t.plan_batch(s, g, 9, 100, P, path_cap=128)
+    Po = po.PlanParams(K, best, 400, 256, 0, 0, 0)
+    nsolved = 0
+    for i in range(len(s)):
+        so, pso, pao = o.plan(s[i], g[i], 9, 100 + i, Po)
+        for key in ("solved", "iters", "nv_a", "nv_b", "path_states", "pair_checks", "nn_queries"):
+            assert st[key][i] == getattr(so, key), f"query {i}: {key}"
+        if so.solved:
+            nsolved += 1
+            n = so.path_states
+            assert_bits_equal(np.array([st["path_length"][i]]), np.array([so.path_length]), what="path length")
+            assert abs(st["path_yaw"][i] - so.path_yaw) < 1e-9
+            assert_bits_equal(np.array([st["path_duration"][i]]), np.array([so.path_duration]), what="path duration")
+            assert_bits_equal(ps[i, :n], pso, what="path states")
+            assert_bits_equal(pa[i, :n - 1], pao, what="path actions")
+    assert nsolved >= 1 or name == "rough_terrain"
+
+
+def test_plan_batch_capacity_and_budget(gbp):
+    T = load_terrain("slope"); o = po.Oracle(T)
+    t = gbp.Terrain(T.x, T.y, T.z, T.dx, T.dy, T.dz)
+    s, g = queries(o, T, 8, 6)
+    P = gbp.PlanParams(6, 0, 300, 4, 0, 0, 0)  # tiny trees: queries stop when a tree is full
+    st = t.plan_batch(s, g, 3, 0, P)
+    Po = po.PlanParams(6, 0, 300, 4, 0, 0, 0)
+    for i in range(len(s)):
+        so, _, _ = o.plan(s[i], g[i], 3, i, Po)
+        assert (st["solved"][i], st["iters"][i], st["nv_a"][i], st["nv_b"][i]) == (so.solved, so.iters, so.nv_a, so.nv_b)
+    assert (st["nv_a"] <= 4).all() and (st["nv_b"] <= 4).all()
