@@ -28,7 +28,24 @@ def build(force=False, verbose=False):
     return SO
 
 
+HOST_SO = os.path.join(HERE, "libglobal_body_planner_b200.so")
+HOST_SOURCES = [os.path.join(HERE, "host", f) for f in ("dropin.cpp", "planners.cpp")]
+INCLUDE = os.path.join(HERE, "..", "include")
+
+
+def build_host(force=False):
+    """The drop-in C++ classes (include/global_body_planner/*.h) over the C ABI."""
+    hdrs = [os.path.join(INCLUDE, "global_body_planner", f) for f in os.listdir(os.path.join(INCLUDE, "global_body_planner"))]
+    if not force and os.path.exists(HOST_SO) and all(os.path.getmtime(f) <= os.path.getmtime(HOST_SO) for f in HOST_SOURCES + hdrs + [SO]):
+        return HOST_SO
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++14", "-O2", "-fPIC", "-shared", "-Wall", "-I" + INCLUDE, "-o", HOST_SO] + HOST_SOURCES + \
+          ["-L" + HERE, "-lgbp_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return HOST_SO
+
+
 if __name__ == "__main__":
     import sys
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_host(force="--force" in sys.argv)
     print(SO)

@@ -657,25 +657,44 @@ int gbp_extend(gbp_tree *T, const gbp_terrain *t, const double *target, int dire
 	if (pair_checks) *pair_checks = res[2];
 	return GBP_OK;
 }
-int gbp_attempt_connect(const gbp_terrain *t, int64_t n, const double *s_existing, const double *s, const uint8_t *direction,
-						int adaptive, int *status, double *s_new, double *a_new, uint8_t *flags) {
+int gbp_attempt_connect_ts(const gbp_terrain *t, int64_t n, const double *s_existing, const double *s, const double *t_s,
+						   const uint8_t *direction, int adaptive, int *status, double *s_new, double *a_new, uint8_t *flags) {
 	if (!t || n < 0 || (n && (!s_existing || !s || !direction || !status || !s_new || !a_new))) return fail(GBP_E_INVALID, "bad arguments");
 	if (n == 0) return GBP_OK;
 	cudaStream_t st = lib_stream();
-	Dev de(st), ds(st), dd(st), dst(st), dsn(st), dan(st), dfl(st);
+	Dev de(st), ds(st), dts(st), dd(st), dst(st), dsn(st), dan(st), dfl(st);
 	int rc;
 	if ((rc = upload(de, s_existing, (size_t) 8 * n, st)) || (rc = upload(ds, s, (size_t) 8 * n, st)) || (rc = upload(dd, direction, (size_t) n, st))) return rc;
+	if (t_s && (rc = upload(dts, t_s, (size_t) n, st))) return rc;
 	CU(dst.alloc(sizeof(int) * n));
 	CU(dsn.alloc(sizeof(double) * 8 * n));
 	CU(dan.alloc(sizeof(double) * 10 * n));
 	if (flags) CU(dfl.alloc(n));
-	GBP_DISPATCH(t->view, k_attempt_connect, (blocks_for(n, 128), 128), st, t->view, n, de.as<double>(), ds.as<double>(), dd.as<uint8_t>(), adaptive, dst.as<int>(), dsn.as<double>(), dan.as<double>(), dfl.as<uint8_t>());
+	GBP_DISPATCH(t->view, k_attempt_connect, (blocks_for(n, 128), 128), st, t->view, n, de.as<double>(), ds.as<double>(),
+				 t_s ? dts.as<double>() : nullptr, dd.as<uint8_t>(), adaptive, dst.as<int>(), dsn.as<double>(), dan.as<double>(), dfl.as<uint8_t>());
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(status, dst.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemcpyAsync(s_new, dsn.p, sizeof(double) * 8 * n, cudaMemcpyDeviceToHost, st));
 	CU(cudaMemcpyAsync(a_new, dan.p, sizeof(double) * 10 * n, cudaMemcpyDeviceToHost, st));
 	if (flags) CU(cudaMemcpyAsync(flags, dfl.p, n, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_attempt_connect(const gbp_terrain *t, int64_t n, const double *s_existing, const double *s, const uint8_t *direction,
+						int adaptive, int *status, double *s_new, double *a_new, uint8_t *flags) {
+	return gbp_attempt_connect_ts(t, n, s_existing, s, nullptr, direction, adaptive, status, s_new, a_new, flags);
+}
+int gbp_new_config(const gbp_terrain *t, const double *target, const double *s_near, int direction, int K, int best_of_k, int adaptive,
+				   uint64_t seed, uint64_t stream, uint64_t idx0, int *found, double *s_new, double *a_new, int64_t *pair_checks) {
+	if (!t || !target || !s_near || !found || !s_new || !a_new) return fail(GBP_E_INVALID, "bad arguments");
+	static thread_local gbp_tree *scratch = nullptr;  // a one-vertex tree whose nearest neighbour is s_near
+	int rc;
+	if (!scratch && (rc = gbp_tree_create(2, &scratch))) return rc;
+	if ((rc = gbp_tree_init(scratch, s_near))) return rc;
+	int status = GBP_TRAPPED, id = -1;
+	if ((rc = gbp_extend(scratch, t, target, direction, K, best_of_k, adaptive, seed, stream, idx0, &status, &id, pair_checks))) return rc;
+	*found = status != GBP_TRAPPED;
+	if (*found) return gbp_tree_read(scratch, id, 1, s_new, a_new, nullptr, nullptr, nullptr);
 	return GBP_OK;
 }
 int gbp_connect(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int adaptive, int *status, int *new_id) {

@@ -290,8 +290,9 @@ __device__ __forceinline__ bool validate_pair_seq(const TerrainView &T, const do
 // attemptConnect (src/rrt_connect.cpp:20-91), recursion unrolled into a loop (see oracle/gbp_oracle.c)
 template <typename M>
 __device__ int attempt_connect(const TerrainView &T, const double s_existing[8], const double s_in[8], int direction,
-							   bool adaptive, double s_new[8], double a_new[10], Counters &c, unsigned &pair_checks) {
-	double target[8], ts = pose_distance(s_in, s_existing) / V_NOM;
+							   bool adaptive, double s_new[8], double a_new[10], Counters &c, unsigned &pair_checks,
+							   double ts0 = -1.0) {
+	double target[8], ts = ts0 >= 0.0 ? ts0 : pose_distance(s_in, s_existing) / V_NOM;  // :89
 #pragma unroll
 	for (int i = 0; i < 8; ++i) target[i] = s_in[i];
 	for (int depth = 0;; ++depth) {
@@ -819,7 +820,8 @@ __global__ void __launch_bounds__(256) k_extend_select(TerrainView T, TreeView t
 // ------------------------------------------------------------------ attemptConnect / connect
 template <typename M>
 __global__ void __launch_bounds__(128) k_attempt_connect(TerrainView T, int64_t n, const double *__restrict__ s_existing,
-														  const double *__restrict__ s, const uint8_t *__restrict__ dir, int adaptive,
+														  const double *__restrict__ s, const double *__restrict__ t_s,
+														  const uint8_t *__restrict__ dir, int adaptive,
 														  int *__restrict__ status, double *__restrict__ s_new,
 														  double *__restrict__ a_new, uint8_t *__restrict__ flags) {
 	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
@@ -833,7 +835,7 @@ __global__ void __launch_bounds__(128) k_attempt_connect(TerrainView T, int64_t 
 	for (int d = 0; d < 10; ++d) an[d] = 0;
 	Counters c = {0, 0, 0, 0};
 	unsigned checks = 0;
-	status[i] = attempt_connect<M>(T, se, sg, dir[i], adaptive != 0, sn, an, c, checks);
+	status[i] = attempt_connect<M>(T, se, sg, dir[i], adaptive != 0, sn, an, c, checks, t_s ? t_s[i] : -1.0);
 	store_state(s_new + 8 * i, sn);
 #pragma unroll
 	for (int d = 0; d < 10; ++d) a_new[10 * i + d] = an[d];

@@ -167,10 +167,20 @@ int gbp_near(const gbp_tree *T, const double *query, double radius, int *ids, in
 int gbp_extend(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int k_candidates,
                int best_of_k, int adaptive, uint64_t seed, uint64_t stream, uint64_t idx0, int *status,
                int *new_id, int64_t *pair_checks);
-/* RRTConnectClass::attemptConnect (rrt_connect.cpp:20-91), n independent (s_existing, s) pairs */
+/* RRTClass::newConfig (rrt.cpp:20-70) from an explicit s_near (no tree): K candidates, selection and the
+ * "closer than s_near" acceptance as in gbp_extend.  *found = 1 when s_new / a_new were written. */
+int gbp_new_config(const gbp_terrain *t, const double *target, const double *s_near, int direction, int k_candidates,
+                   int best_of_k, int adaptive, uint64_t seed, uint64_t stream, uint64_t idx0, int *found, double *s_new,
+                   double *a_new, int64_t *pair_checks);
+/* RRTConnectClass::attemptConnect (rrt_connect.cpp:20-91), n independent (s_existing, s) pairs.  t_s may be
+ * NULL (stance time = poseDistance / V_NOM, the 6-argument overload :85-91) or hold n explicit stance times
+ * (the 7-argument overload :20-84). */
 int gbp_attempt_connect(const gbp_terrain *t, int64_t n, const double *s_existing, const double *s,
                         const uint8_t *direction, int adaptive, int *status, double *s_new, double *a_new,
                         uint8_t *flags);
+int gbp_attempt_connect_ts(const gbp_terrain *t, int64_t n, const double *s_existing, const double *s, const double *t_s,
+                           const uint8_t *direction, int adaptive, int *status, double *s_new, double *a_new,
+                           uint8_t *flags);
 /* RRTConnectClass::connect (rrt_connect.cpp:98-120) */
 int gbp_connect(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int adaptive, int *status,
                 int *new_id);
