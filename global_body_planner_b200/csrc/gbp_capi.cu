@@ -4,6 +4,7 @@
 // GBP_E_CUDA.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -89,6 +90,8 @@ struct gbp_terrain {
 	void *d_z = nullptr;
 	void *d_n = nullptr;
 	unsigned long long *d_cnt = nullptr;  // 6 work counters of the last validate launch
+	size_t z_bytes = 0;                   // height grid bytes
+	float l2_hit_ratio = 0.f;             // share of the grid that fits the persisting L2 carve-out (0 = no window)
 	std::vector<double> hx, hy;
 	int cell_bytes = 8;
 };
@@ -180,6 +183,22 @@ int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const d
 	TRY(cudaMalloc(&t->d_cnt, 6 * sizeof(unsigned long long)));
 	TRY(cudaMemset(t->d_cnt, 0, 6 * sizeof(unsigned long long)));
 #undef TRY
+	{  // "hot map pinned in L2": reserve persisting L2 lines for the height grid (streaming inputs/outputs must not evict it)
+		t->z_bytes = cells * (size_t) t->cell_bytes;
+		int dev = 0, max_persist = 0, max_window = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+		cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+		if (max_persist > 0 && max_window > 0 && t->z_bytes > (1u << 20)) {
+			size_t want = t->z_bytes < (size_t) max_persist ? t->z_bytes : (size_t) max_persist;
+			if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+				size_t win = t->z_bytes < (size_t) max_window ? t->z_bytes : (size_t) max_window;
+				t->l2_hit_ratio = (float) ((double) want / (double) win);
+				if (t->l2_hit_ratio > 1.f) t->l2_hit_ratio = 1.f;
+			}
+		}
+		(void) cudaGetLastError();
+	}
 	v.x0 = x[0]; v.y0 = y[0]; v.x_last = x[nx - 1]; v.y_last = y[ny - 1];
 	v.inv_dx = (nx - 1) / (x[nx - 1] - x[0]);
 	v.inv_dy = (ny - 1) / (y[ny - 1] - y[0]);
@@ -335,7 +354,9 @@ int gbp_distance(int kind, int64_t n, const double *q1, const double *q2, double
 int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
 						   int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream) {
 	if (!t || n < 0 || (n && (!states || !actions || !direction || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
-	if (variant < 0 || variant > 3) return fail(GBP_E_INVALID, "variant must be 0..3");
+	if (variant < 0 || variant > 5 || variant == 4) return fail(GBP_E_INVALID, "variant must be 0..3 or 5");
+	const bool walk_only = variant == 5;
+	if (walk_only) variant = 3;
 	if (variant == 2 && adaptive) return fail(GBP_E_INVALID, "variant 2 (warp per action) supports the fixed step only");
 	cudaStream_t st = (cudaStream_t) stream;
 	CU(cudaMemsetAsync(t->d_cnt, 0, 6 * sizeof(unsigned long long), st));
@@ -359,12 +380,40 @@ int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states
 			return fail(GBP_E_INVALID, "states/actions/direction must be 16-byte aligned (TMA bulk copies)");
 		int64_t warps = (n + per_warp - 1) / per_warp;
 		unsigned grid = (unsigned) ((warps + warps_per_block - 1) / warps_per_block);
-		GBP_DISPATCH(t->view, k_validate_refill, (grid, threads), st, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+		cudaLaunchAttribute attr[1];
+		cfg.attrs = attr; cfg.numAttrs = 0;
+		if (t->l2_hit_ratio > 0.f && !getenv("GBP_NO_L2_WINDOW")) {
+			attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+			attr[0].val.accessPolicyWindow.base_ptr = t->d_z;
+			size_t win = t->z_bytes;
+			int dev = 0, max_window = 0;
+			cudaGetDevice(&dev); cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+			if (win > (size_t) max_window) win = (size_t) max_window;
+			attr[0].val.accessPolicyWindow.num_bytes = win;
+			attr[0].val.accessPolicyWindow.hitRatio = t->l2_hit_ratio;
+			attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+			attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+			cfg.numAttrs = 1;
+		}
+#define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt))
+		if (t->view.cell_f32) { if (t->view.uniform) GBP_WALK_(MapF32U); else GBP_WALK_(MapF32N); }
+		else { if (t->view.uniform) GBP_WALK_(MapF64U); else GBP_WALK_(MapF64N); }
+#undef GBP_WALK_
+		if (s_new && !walk_only) k_pair_outputs<<<blocks_for(n, 256), 256, 0, st>>>(n, states, actions, s_new);
 	}
 	CU(cudaGetLastError());
 	return GBP_OK;
 }
 
+int gbp_pair_outputs_dev(int64_t n, const double *states, const double *actions, double *s_new, void *stream) {
+	if (n < 0 || (n && (!states || !actions || !s_new))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	k_pair_outputs<<<blocks_for(n, 256), 256, 0, (cudaStream_t) stream>>>(n, states, actions, s_new);
+	CU(cudaGetLastError());
+	return GBP_OK;
+}
 int gbp_validate_counters(const gbp_terrain *t, int64_t counters6[6]) {
 	if (!t || !counters6) return fail(GBP_E_INVALID, "bad arguments");
 	CU(cudaDeviceSynchronize());

@@ -193,15 +193,36 @@ __device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q) {
 	const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
 	return is_valid_state_fast<M>(T, p, ph, q.c);
 }
+// How the reference's s_new output is obtained once a pair check has finished.  The (cheap) decision is
+// taken where the walk ends; the (expensive, exact, division-heavy) evaluation is done once per
+// candidate by finish_output(), convergently, instead of inside the divergent walk.
+enum : int { OUT_SAME = 0, OUT_STANCE = 1, OUT_LAND = 2, OUT_REV = 3 };
+struct OutRecipe {
+	int kind;    // OUT_SAME: s_new = s (defined value where the reference leaves it unwritten)
+	double tau;  // OUT_STANCE: applyStance(s, a, tau); OUT_LAND: applyFlight(applyStance(s, a), t_f);
+};               // OUT_REV: applyStanceReverse(applyFlight(s, -t_f), a, tau)
+__device__ __forceinline__ void finish_output(const double s[8], const double a[10], int kind, double tau, double s_new[8]) {
+	double tmp[8];
+	switch (kind) {
+	case OUT_STANCE: apply_stance(s, a, tau, s_new); break;
+	case OUT_LAND: apply_stance(s, a, a[6], tmp); apply_flight(tmp, a[7], s_new); break;  // exact s_land (:743-749)
+	case OUT_REV: apply_flight(s, -a[7], tmp); apply_stance_reverse(tmp, a, tau, s_new); break;  // (:866-872)
+	default:
+#pragma unroll
+		for (int i = 0; i < 8; ++i) s_new[i] = s[i];
+		break;
+	}
+}
+
 // Advance after the verdict of the current sub-state.  Returns 0 = continue, 1 = finished invalid,
-// 2 = finished valid.  On finish, s_new / t_new hold the reference's outputs.
-__device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, bool adaptive, double s_new[8]) {
+// 2 = finished valid.  On finish, `out` says how to compute s_new and q.t_new holds t_new.
+__device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, bool adaptive, OutRecipe &out) {
 	const double ts = q.a[6], tf = q.a[7];
 	switch (q.phase) {
 	case PH_FWD_ST:
 		if (!valid) {
 			if (!adaptive || (KINEMATICS_RES - 0.01 <= q.step && q.step <= KINEMATICS_RES + 0.01)) {
-				apply_stance(q.s, q.a, (1.0 - BACKUP_RATIO) * q.t, s_new);
+				out.kind = OUT_STANCE; out.tau = (1.0 - BACKUP_RATIO) * q.t;  // :725 / :668
 				return 1;
 			}
 			q.step = KINEMATICS_RES;
@@ -214,26 +235,18 @@ __device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, bool adapti
 		if (!(q.t <= ts)) { q.t = 0; q.step = KINEMATICS_RES; q.phase = (0 < tf) ? PH_FWD_FL : PH_FWD_LAND; }
 		return 0;
 	case PH_FWD_FL:
-		if (!valid) {
-			if (q.have_ls) apply_stance(q.s, q.a, q.t_ls, s_new);
-			else { for (int i = 0; i < 8; ++i) s_new[i] = q.s[i]; }
-			return 1;
-		}
+		if (!valid) { out.kind = q.have_ls ? OUT_STANCE : OUT_SAME; out.tau = q.t_ls; return 1; }  // s_new keeps the last stance sample
 		if (adaptive) q.step += KINEMATICS_RES;
 		q.t += q.step;
 		if (!(q.t < tf)) q.phase = PH_FWD_LAND;
 		return 0;
 	case PH_FWD_LAND:
-		if (!valid) {
-			if (q.have_ls) apply_stance(q.s, q.a, q.t_ls, s_new);
-			else { for (int i = 0; i < 8; ++i) s_new[i] = q.s[i]; }
-			return 1;
-		}
-		{ double tmp[8]; apply_stance(q.s, q.a, ts, tmp); apply_flight(tmp, tf, s_new); }  // exact s_land (:743-749)
+		if (!valid) { out.kind = q.have_ls ? OUT_STANCE : OUT_SAME; out.tau = q.t_ls; return 1; }
+		out.kind = OUT_LAND; out.tau = 0;
 		q.t_new = ts + tf;
 		return 2;
 	case PH_REV_FL:
-		if (!valid) { for (int i = 0; i < 8; ++i) s_new[i] = q.s[i]; return 1; }
+		if (!valid) { out.kind = OUT_SAME; out.tau = 0; return 1; }
 		if (adaptive) q.step += KINEMATICS_RES;
 		q.t += q.step;
 		if (!(q.t < tf)) { q.t = ts; q.step = KINEMATICS_RES; q.phase = (ts >= 0) ? PH_REV_ST : PH_REV_START; }
@@ -241,7 +254,7 @@ __device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, bool adapti
 	case PH_REV_ST:
 		if (!valid) {
 			if (!adaptive || (KINEMATICS_RES - 0.01 <= q.step && q.step <= KINEMATICS_RES + 0.01)) {
-				apply_stance(q.s, q.a, q.t + BACKUP_RATIO * (ts - q.t), s_new);
+				out.kind = OUT_STANCE; out.tau = q.t + BACKUP_RATIO * (ts - q.t);  // sic (:862): forward stance from the END state
 				return 1;
 			}
 			q.step = KINEMATICS_RES;
@@ -254,12 +267,8 @@ __device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, bool adapti
 		if (!(q.t >= 0)) q.phase = PH_REV_START;
 		return 0;
 	default:  // PH_REV_START
-		if (!valid) {
-			if (q.have_ls) { double tmp[8]; apply_flight(q.s, -tf, tmp); apply_stance_reverse(tmp, q.a, q.t_ls, s_new); }
-			else { for (int i = 0; i < 8; ++i) s_new[i] = q.s[i]; }
-			return 1;
-		}
-		{ double tmp[8]; apply_flight(q.s, -tf, tmp); apply_stance_reverse(tmp, q.a, 0, s_new); }  // exact s_start (:866-872)
+		if (!valid) { out.kind = q.have_ls ? OUT_REV : OUT_SAME; out.tau = q.t_ls; return 1; }
+		out.kind = OUT_REV; out.tau = 0;
 		q.t_new = ts;
 		return 2;
 	}
@@ -277,11 +286,13 @@ __device__ __forceinline__ bool validate_pair_seq(const TerrainView &T, const do
 	for (int i = 0; i < 10; ++i) q.a[i] = a[i];
 	cursor_start(q, direction);
 	int r = 0;
+	OutRecipe out;
 	while (true) {
 		const bool valid = cursor_check<M>(T, q);
-		r = cursor_advance(q, valid, adaptive, s_new);
+		r = cursor_advance(q, valid, adaptive, out);
 		if (r) break;
 	}
+	finish_output(s, a, out.kind, out.tau, s_new);
 	t_new = q.t_new;
 	c.substates += q.c.substates; c.lookups += q.c.lookups; c.nanprobes += q.c.nanprobes; c.flags |= q.c.flags;
 	return r == 2;
@@ -554,17 +565,14 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) k_validate_refill(TerrainVie
 		bool valid = true;
 		if (q.phase != PH_IDLE) valid = cursor_check<M>(T, q);
 		if (q.phase != PH_IDLE) {
-			double sn[8];
-			int r = cursor_advance(q, valid, adaptive != 0, sn);
+			OutRecipe out;
+			int r = cursor_advance(q, valid, adaptive != 0, out);
 			if (r) {
 				const bool ok = r == 2;
 				verdict[mine] = ok ? 1 : 0;
 				if (flags) flags[mine] = (uint8_t) (q.c.flags | (ok ? GBP_FLAG_VALID : 0));
-				if (s_new) {
-					double2 *o = reinterpret_cast<double2 *>(s_new + 8 * mine);
-#pragma unroll
-					for (int d = 0; d < 4; ++d) __stcs(o + d, make_double2(sn[2 * d], sn[2 * d + 1]));
-				}
+				// s_new is finished by k_pair_outputs (convergent, exact); its slot carries the recipe meanwhile
+				if (s_new) *reinterpret_cast<double2 *>(s_new + 8 * mine) = make_double2(out.tau, (double) out.kind);
 				if (t_new) __stcs(t_new + mine, q.t_new);
 				k += q.c.substates; L += q.c.lookups; np += q.c.nanprobes;
 				oog += (q.c.flags & GBP_FLAG_OOG) ? 1 : 0; near += (q.c.flags & GBP_FLAG_NEAR) ? 1 : 0; nvalid += ok ? 1 : 0;
@@ -573,6 +581,24 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) k_validate_refill(TerrainVie
 		}
 	}
 	flush_counters(cnt, k, L, np, oog, near, nvalid);
+}
+
+// Second pass of the refill variant: s_new[i] = finish_output(recipe left in s_new[i][0..1]).  One thread
+// per candidate, no divergence beyond the 4 recipe kinds; streaming stores.  (An in-kernel shared-memory
+// output queue was measured too: it either shrinks the L1 that the terrain gathers live on or stalls on
+// re-reading the inputs — 12.5-22.6 ms against 10.7 ms for this two-pass form.)
+__global__ void __launch_bounds__(256) k_pair_outputs(int64_t n, const double *__restrict__ states, const double *__restrict__ actions,
+													   double *__restrict__ s_new) {
+	const int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double2 rc = *reinterpret_cast<const double2 *>(s_new + 8 * i);
+	double s[8], a[10], sn[8];
+	load_state(states + 8 * i, s);
+	load_action(actions + 10 * i, a);
+	finish_output(s, a, (int) rc.y, rc.x, sn);
+	double2 *o = reinterpret_cast<double2 *>(s_new + 8 * i);
+#pragma unroll
+	for (int d = 0; d < 4; ++d) __stcs(o + d, make_double2(sn[2 * d], sn[2 * d + 1]));
 }
 
 // ------------------------------------------------------------------ samplers

@@ -104,13 +104,17 @@ int gbp_distance(int kind, int64_t n, const double *q1, const double *q2, double
  * defined: s_new starts as the input state, t_new as 0.  flags / s_new / t_new may be NULL.
  * `variant` selects the kernel: 0 = default (currently the refill kernel), 1 = one thread per
  * action, 2 = one warp per action / one lane per sub-state (fixed step only), 3 = lane-per-action
- * with warp-level refill.  All variants return identical results. */
+ * with warp-level refill (two launches: the walk, then k_pair_outputs which turns the walk's output recipes
+ * into exact s_new values).  Variant 5 runs the walk of variant 3 alone and leaves the recipes {tau, kind}
+ * in s_new[i][0..1]; gbp_pair_outputs_dev finishes them (bench.py times the two kernels separately this
+ * way).  All variants return identical results. */
 int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, const double *actions,
                        const uint8_t *direction, int adaptive, int variant, uint8_t *verdict, uint8_t *flags,
                        double *s_new, double *t_new);
 int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states, const double *actions,
                            const uint8_t *direction, int adaptive, int variant, uint8_t *verdict, uint8_t *flags,
                            double *s_new, double *t_new, void *stream);
+int gbp_pair_outputs_dev(int64_t n, const double *states, const double *actions, double *s_new, void *stream);
 /* per-launch work counters of the last gbp_validate_pairs[_dev] call on this terrain handle, summed
  * over candidates under the REFERENCE's early-exit semantics: {sub-states k, getGroundHeight calls L,
  * heightIsNan calls, candidates flagged OOG, candidates flagged NEAR, valid}.  Synchronises. */
