@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libgbp_b200.so")
+SO = os.environ.get("GBP_B200_SO", os.path.join(HERE, "libgbp_b200.so"))
 
 FORWARD, REVERSE = 0, 1
 FLIGHT, STANCE = 0, 1

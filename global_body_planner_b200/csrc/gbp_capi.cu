@@ -372,7 +372,7 @@ int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states
 	} else {
 		// persistent-style geometry: a multiple of the SM count; each warp owns a contiguous range
 		const int threads = RF_WARPS * 32, warps_per_block = RF_WARPS;
-		int64_t max_warps = (int64_t) sm_count() * 12;  // 16 resident warps per SM at this register budget
+		int64_t max_warps = (int64_t) sm_count() * RF_WARPS * RF_MINBLOCKS;  // one wave of resident warps  // 16 resident warps per SM at this register budget
 		int64_t per_warp = (n + max_warps - 1) / max_warps;
 		if (per_warp < 64) per_warp = 64;
 		per_warp = (per_warp + RF_CHUNK - 1) / RF_CHUNK * RF_CHUNK;  // chunks of the TMA ring are 32-aligned

@@ -320,8 +320,13 @@ __device__ __forceinline__ int cell_uniform(int n, double v, double a0, double a
 	int i = min((int) g, n - 2);
 	const double fi = (double) i;
 	u = oog ? (v - a0) * inv : g - fi;  // out of grid: extrapolate from cell 0 (defined semantics)
+#ifdef GBP_EDGE_FMIN
 	const double d = fmin(u, 1.0 - u) * step;
 	edge = !oog && d < EDGE_MARGIN;
+#else
+	const double eps = EDGE_MARGIN * inv;  // guard band in cell units
+	edge = !oog && (u < eps || u > 1.0 - eps);
+#endif
 	return oog ? 0 : i;
 }
 
@@ -396,10 +401,46 @@ __device__ __forceinline__ void yaw_cs(double dx, double dy, double r, double &c
 	}
 }
 
+// Verdict bookkeeping shared by the fp64 and the mixed-precision evaluators: replays the reference's check order
+// (:564-634) on precomputed per-probe results as straight-line predicate arithmetic (no branches: the compiler
+// must not sink the probe loads behind early exits, and the warp must not diverge).
+// Probe order: 0 centre, 1+2k leg k, 2+2k corner k (k = 0..3 in the reference's loop order), 9 belly.
+struct ProbeBits {
+	unsigned nan, oog, edge;  // bit p = probe p
+};
+__device__ __forceinline__ bool replay_checks(const ProbeBits &pb, bool pre_bad, bool speed_bad, bool stance, const double leg_m[4],
+											  const double cor_m[4], double belly_m, double near_margin, Counters &c) {
+	// leg_m = leg_height - H_MAX, cor_m = corner_height - H_MIN, belly_m = height - H_MIN
+	unsigned flags = ((pb.oog & 1u) ? GBP_FLAG_OOG : 0u) | ((pb.edge & 1u) ? GBP_FLAG_NEAR : 0u), nanprobes = 1, lookups = 0;
+	bool alive = !((pb.nan & 1u) || pre_bad || speed_bad);
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const unsigned lb = 1u << (1 + 2 * k), cb = 1u << (2 + 2 * k);
+		nanprobes += alive ? 1u : 0u;
+		flags |= (alive && (pb.oog & lb)) ? GBP_FLAG_OOG : 0u;
+		flags |= (alive && (pb.edge & lb)) ? GBP_FLAG_NEAR : 0u;
+		const bool reached = alive && !(pb.nan & lb);
+		lookups += reached ? 2u : 0u;
+		flags |= (reached && (pb.oog & cb)) ? GBP_FLAG_OOG : 0u;
+		flags |= (reached && (pb.edge & cb)) ? GBP_FLAG_NEAR : 0u;
+		const bool near = (fabs(cor_m[k]) < near_margin) || (stance && fabs(leg_m[k]) < near_margin);
+		flags |= (reached && near) ? GBP_FLAG_NEAR : 0u;
+		const bool bad = (cor_m[k] < 0.0) || (stance && leg_m[k] > 0.0);
+		alive = reached && !bad;
+	}
+	lookups += alive ? 1u : 0u;
+	flags |= (alive && (pb.oog & (1u << 9))) ? GBP_FLAG_OOG : 0u;
+	flags |= (alive && (pb.edge & (1u << 9))) ? GBP_FLAG_NEAR : 0u;
+	flags |= (alive && fabs(belly_m) < near_margin) ? GBP_FLAG_NEAR : 0u;
+	c.substates += 1;
+	c.nanprobes += nanprobes;
+	c.lookups += lookups;
+	c.flags |= flags;
+	return alive && !(belly_m < 0.0);
+}
+
 template <typename M>
 __device__ __forceinline__ bool is_valid_state_fast(const TerrainView &T, const Pose6 &s, int phase, Counters &c) {
-	// ---- stage A: everything the reference would compute, without early exits
-	const Probe pc = probe_fast<M>(T, s.x, s.y);
 	const bool pre_bad = (s.x < T.x0) || (s.x > T.x_last) || (s.y < T.y0) || (s.y > T.y_last) || (fabs(s.pitch) >= P_MAX);
 	const double r = sqrt(s.dx * s.dx + s.dy * s.dy);  // exact: the speed test is a hard comparison (:572)
 	const bool speed_bad = r > V_MAX;
@@ -408,49 +449,65 @@ __device__ __forceinline__ bool is_valid_state_fast(const TerrainView &T, const 
 	sincos_small(pre_bad ? 0.0 : s.pitch, sp, cp);
 	const double R11 = cy * cp, R12 = -sy, R13 = cy * sp, R21 = sy * cp, R22 = cy, R23 = sy * sp, R31 = -sp, R33 = cp;
 	const double zb = -ROBOT_H;
-	Probe pl[4], pk[4];
-	double zl[4], zc[4];
+	// ---- stage A: the 10 probe points
+	double px[10], py[10], zl[4], zc[4];
+	px[0] = s.x; py[0] = s.y;
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
 		const double xb = (k & 2) ? 0.5 * ROBOT_L : -0.5 * ROBOT_L, yb = (k & 1) ? 0.5 * ROBOT_W : -0.5 * ROBOT_W;
-		const double xl = __fma_rn(R12, yb, __fma_rn(R11, xb, s.x)), yl = __fma_rn(R22, yb, __fma_rn(R21, xb, s.y));
+		px[1 + 2 * k] = __fma_rn(R12, yb, __fma_rn(R11, xb, s.x));
+		py[1 + 2 * k] = __fma_rn(R22, yb, __fma_rn(R21, xb, s.y));
+		px[2 + 2 * k] = __fma_rn(R13, zb, px[1 + 2 * k]);
+		py[2 + 2 * k] = __fma_rn(R23, zb, py[1 + 2 * k]);
 		zl[k] = __fma_rn(R31, xb, s.z);
 		zc[k] = __fma_rn(R33, zb, zl[k]);
-		pl[k] = probe_fast<M>(T, xl, yl);
-		pk[k] = probe_fast<M>(T, __fma_rn(R13, zb, xl), __fma_rn(R23, zb, yl));
 	}
-	const Probe pb = probe_fast<M>(T, __fma_rn(R13, zb, s.x), __fma_rn(R23, zb, s.y));
-	// ---- stage B: the reference's check order (:564-634) replayed on the precomputed pieces, as
-	// straight-line predicate arithmetic (no branches: the compiler must not sink the probe loads
-	// behind early exits, and the warp must not diverge).
-	const bool stance = phase == GBP_STANCE;
-	unsigned flags = (pc.oog ? GBP_FLAG_OOG : 0u) | (pc.edge ? GBP_FLAG_NEAR : 0u), nanprobes = 1, lookups = 0;
-	bool alive = !(pc.nan || pre_bad || speed_bad);
+	px[9] = __fma_rn(R13, zb, s.x); py[9] = __fma_rn(R23, zb, s.y);
+	// ---- stage B/C/D: cells, loads, heights
+	ProbeBits pb = {0u, 0u, 0u};
+	double h[10];
+	if (M::uniform) {
+		int cell[10];
+		double ux[10], uy[10];
+#pragma unroll
+		for (int p = 0; p < 10; ++p) {
+			bool ox, oy, ex, ey;
+			const int ix = cell_uniform(T.nx, px[p], T.x0, T.x_last, T.inv_dx, T.step_x, ox, ex, ux[p]);
+			const int iy = cell_uniform(T.ny, py[p], T.y0, T.y_last, T.inv_dy, T.step_y, oy, ey, uy[p]);
+			cell[p] = ix * T.ny + iy;
+			pb.oog |= (ox || oy) ? (1u << p) : 0u;
+			pb.edge |= (ex || ey) ? (1u << p) : 0u;
+		}
+		typename M::cell f[10][4];
+#pragma unroll
+		for (int p = 0; p < 10; ++p) {  // all 40 loads are issued before any is consumed
+			const typename M::cell *q = (const typename M::cell *) T.z + cell[p];
+			f[p][0] = __ldg(q); f[p][1] = __ldg(q + 1); f[p][2] = __ldg(q + T.ny); f[p][3] = __ldg(q + T.ny + 1);
+		}
+#pragma unroll
+		for (int p = 0; p < 10; ++p) {
+			const double f11 = (double) f[p][0], f12 = (double) f[p][1], f21 = (double) f[p][2], f22 = (double) f[p][3];
+			pb.nan |= ((f11 != f11) || (f12 != f12) || (f21 != f21) || (f22 != f22)) ? (1u << p) : 0u;
+			const double lo = __fma_rn(f21 - f11, ux[p], f11), hi = __fma_rn(f22 - f12, ux[p], f12);
+			h[p] = __fma_rn(hi - lo, uy[p], lo);
+		}
+	} else {
+#pragma unroll
+		for (int p = 0; p < 10; ++p) {
+			const Probe q = probe_fast<M>(T, px[p], py[p]);
+			h[p] = q.h;
+			pb.nan |= q.nan ? (1u << p) : 0u;
+			pb.oog |= q.oog ? (1u << p) : 0u;
+		}
+	}
+	double leg_m[4], cor_m[4];
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
-		nanprobes += alive ? 1u : 0u;
-		flags |= (alive && pl[k].oog) ? GBP_FLAG_OOG : 0u;
-		flags |= (alive && pl[k].edge) ? GBP_FLAG_NEAR : 0u;
-		const bool reached = alive && !pl[k].nan;
-		lookups += reached ? 2u : 0u;
-		flags |= (reached && pk[k].oog) ? GBP_FLAG_OOG : 0u;
-		flags |= (reached && pk[k].edge) ? GBP_FLAG_NEAR : 0u;
-		const double leg_h = zl[k] - pl[k].h, cor_h = zc[k] - pk[k].h;
-		const bool near = (fabs(cor_h - H_MIN) < NEAR_MARGIN) || (stance && fabs(leg_h - H_MAX) < NEAR_MARGIN);
-		flags |= (reached && near) ? GBP_FLAG_NEAR : 0u;
-		const bool bad = (cor_h < H_MIN) || (stance && leg_h > H_MAX);
-		alive = reached && !bad;
+		leg_m[k] = (zl[k] - h[1 + 2 * k]) - H_MAX;
+		cor_m[k] = (zc[k] - h[2 + 2 * k]) - H_MIN;
 	}
-	lookups += alive ? 1u : 0u;
-	flags |= (alive && pb.oog) ? GBP_FLAG_OOG : 0u;
-	flags |= (alive && pb.edge) ? GBP_FLAG_NEAR : 0u;
-	const double h = __fma_rn(R33, zb, s.z) - pb.h;
-	flags |= (alive && fabs(h - H_MIN) < NEAR_MARGIN) ? GBP_FLAG_NEAR : 0u;
-	c.substates += 1;
-	c.nanprobes += nanprobes;
-	c.lookups += lookups;
-	c.flags |= flags;
-	return alive && !(h < H_MIN);
+	const double belly_m = (__fma_rn(R33, zb, s.z) - h[9]) - H_MIN;
+	return replay_checks(pb, pre_bad, speed_bad, phase == GBP_STANCE, leg_m, cor_m, belly_m, NEAR_MARGIN, c);
 }
 __device__ __forceinline__ Pose6 pose6(const double s[8]) {
 	Pose6 p;

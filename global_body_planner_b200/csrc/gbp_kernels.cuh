@@ -489,8 +489,11 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 				 : "memory");
 }
 
+#ifndef RF_MINBLOCKS
+#define RF_MINBLOCKS 2
+#endif
 template <typename M>
-__global__ void __launch_bounds__(RF_WARPS * 32, 3) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
+__global__ void __launch_bounds__(RF_WARPS * 32, RF_MINBLOCKS) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
 																   const double *__restrict__ states, const double *__restrict__ actions,
 																   const uint8_t *__restrict__ dir, int adaptive,
 																   uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
