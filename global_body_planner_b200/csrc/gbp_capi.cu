@@ -208,6 +208,7 @@ int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const d
 	v.uniform = 1;
 	for (int i = 0; i < nx && v.uniform; ++i) if (fabs(x[i] - (x[0] + i * v.step_x)) > 1e-12) v.uniform = 0;
 	for (int i = 0; i < ny && v.uniform; ++i) if (fabs(y[i] - (y[0] + i * v.step_y)) > 1e-12) v.uniform = 0;
+	v.mixed_ok = (v.uniform && v.cell_f32 && v.step_x >= 0.01 && v.step_y >= 0.01 && !getenv("GBP_NO_MIXED")) ? 1 : 0;
 	*out = t;
 	return GBP_OK;
 }

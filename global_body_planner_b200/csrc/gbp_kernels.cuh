@@ -91,7 +91,7 @@ __global__ void k_valid_states(TerrainView T, int64_t n, const double *__restric
 #pragma unroll
 	for (int d = 0; d < 8; ++d) ss[d] = s[8 * i + d];
 	Counters c = {0, 0, 0, 0};
-	bool ok = is_valid_state_fast<M>(T, pose6(ss), phase[i], c);
+	bool ok = is_valid_state_auto<M>(T, pose6(ss), phase[i], c);
 	out[i] = ok ? 1 : 0;
 	if (flags) flags[i] = (uint8_t) (c.flags | (ok ? GBP_FLAG_VALID : 0));
 }
@@ -191,7 +191,7 @@ __device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q) {
 	default: apply_flight(q.s, -q.a[7], tmp); p = stance_reverse_fast(tmp, q.a, q.f, q.phase == PH_REV_ST ? q.t : 0.0); break;
 	}
 	const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
-	return is_valid_state_fast<M>(T, p, ph, q.c);
+	return is_valid_state_auto<M>(T, p, ph, q.c);
 }
 // How the reference's s_new output is obtained once a pair check has finished.  The (cheap) decision is
 // taken where the walk ends; the (expensive, exact, division-heavy) evaluation is done once per

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 				double s_rand[8];
 				sample_state<M>(Tv, seed, query, cell, false, 0.0, false, nullptr, nullptr, s_rand);
 				Counters c = {0, 0, 0, 0};
-				if (!is_valid_state_fast<M>(Tv, pose6(s_rand), GBP_STANCE, c)) continue;  // rrt_connect.cpp:254
+				if (!is_valid_state_auto<M>(Tv, pose6(s_rand), GBP_STANCE, c)) continue;  // rrt_connect.cpp:254
 				++nn_queries;
 				if (warp_extend<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, lane, pair_checks) == GBP_TRAPPED) continue;
 				double s_new[8];
