@@ -208,7 +208,13 @@ int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const d
 	v.uniform = 1;
 	for (int i = 0; i < nx && v.uniform; ++i) if (fabs(x[i] - (x[0] + i * v.step_x)) > 1e-12) v.uniform = 0;
 	for (int i = 0; i < ny && v.uniform; ++i) if (fabs(y[i] - (y[0] + i * v.step_y)) > 1e-12) v.uniform = 0;
-	v.mixed_ok = (v.uniform && v.cell_f32 && v.step_x >= 0.01 && v.step_y >= 0.01 && !getenv("GBP_NO_MIXED")) ? 1 : 0;
+	bool has_nan = false;
+	for (size_t i = 0; i < cells && !has_nan; ++i) has_nan = z[i] != z[i];
+	v.mixed_ok = (v.uniform && v.cell_f32 && !has_nan && v.step_x >= 0.01 && v.step_y >= 0.01 && !getenv("GBP_NO_MIXED")) ? 1 : 0;
+	{  // farthest a leg / corner / belly probe can be from the centre: sqrt(0.15^2 + 0.15^2) + 0.05 < 0.27 m
+		const double step = v.step_x < v.step_y ? v.step_x : v.step_y;
+		v.border = (int) std::ceil(0.27 / step) + 1;
+	}
 	*out = t;
 	return GBP_OK;
 }

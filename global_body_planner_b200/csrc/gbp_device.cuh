@@ -29,7 +29,8 @@ struct TerrainView {
 	int cell_f32;
 	double x0, y0, x_last, y_last;  // axis end points (bounds test of isValidState, OOG test)
 	double inv_dx, inv_dy;          // O(1) cell guess: i ~ (v - x0) * inv_dx
-	int mixed_ok;                   // fp32 cells, uniform axes, cell pitch >= 1 cm: the mixed-precision evaluator applies
+	int mixed_ok;                   // fp32 cells without NaN, uniform axes, cell pitch >= 1 cm: the mixed-precision evaluator applies
+	int border;                     // cells a body probe can lie from the centre's cell (0.23 m / pitch, rounded up, + 1)
 	int uniform;                    // both axes are x0 + i*step to within 1e-12 m: the fast path computes cell edges
 	double step_x, step_y;          // instead of loading them (a probe within 1e-11 m of a grid line is flagged NEAR)
 };
@@ -537,22 +538,23 @@ __device__ __forceinline__ void sincosf_small(float x, float &sn, float &cs) {  
 }
 
 // Returns true when the sub-state was decided (verdict in `valid`, counters updated); false = needs the fp64 path.
+// Preconditions checked here: the centre lies at least T.border cells inside the grid (so no probe can leave it:
+// no OOG flags, no index clamping) and the map holds no NaN (so heightIsNan never fires; T.mixed_ok).
 template <typename M>
 __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const Pose6 &s, int phase, Counters &c, bool &valid) {
-	const bool pre_bad = (s.x < T.x0) || (s.x > T.x_last) || (s.y < T.y0) || (s.y > T.y_last) || (fabs(s.pitch) >= P_MAX);
+	const bool pitch_bad = fabs(s.pitch) >= P_MAX;
 	// sqrt(r2) > V_MAX  <=>  r2 > nextafter(V_MAX^2): the largest double whose correctly rounded root is still 2.0
 	const double r2 = s.dx * s.dx + s.dy * s.dy;
 	const bool speed_bad = r2 > __longlong_as_double(0x4010000000000001ll);
 	static_assert(V_MAX == 2.0, "speed threshold constant is derived for V_MAX = 2");
 	// centre cell in fp64, in-cell fraction handed to fp32
-	const bool oog_c = !(s.x >= T.x0) || !(s.x < T.x_last) || !(s.y >= T.y0) || !(s.y < T.y_last);
 	const double gx = (s.x - T.x0) * T.inv_dx, gy = (s.y - T.y0) * T.inv_dy;
-	const int ixc = max(0, min((int) gx, T.nx - 2)), iyc = max(0, min((int) gy, T.ny - 2));
+	const int ixc = (int) gx, iyc = (int) gy;
+	bool ok = (gx >= (double) T.border) && (gy >= (double) T.border) && (ixc <= T.nx - 2 - T.border) && (iyc <= T.ny - 2 - T.border);
 	const float fux = (float) (gx - (double) ixc), fuy = (float) (gy - (double) iyc);
 	// body orientation in fp32
 	const float fdx = (float) s.dx, fdy = (float) s.dy, fr2 = fdx * fdx + fdy * fdy;
 	float cy, sy;
-	bool ok = !oog_c;
 	if (r2 == 0.0) {  // atan2(+-0, +0) = +-0, atan2(+-0, -0) = +-pi
 		cy = __double_as_longlong(s.dx) < 0 ? -1.0f : 1.0f;
 		sy = 0.0f;
@@ -563,62 +565,64 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 		sy = fdy * rinv;
 	}
 	float sp, cp;
-	sincosf_small(pre_bad ? 0.0f : (float) s.pitch, sp, cp);
+	sincosf_small(pitch_bad ? 0.0f : (float) s.pitch, sp, cp);
 	const float R11 = cy * cp, R12 = -sy, R13 = cy * sp, R21 = sy * cp, R22 = cy, R23 = sy * sp, R31 = -sp, R33 = cp;
 	const float kx = (float) T.inv_dx, ky = (float) T.inv_dy, zb = -(float) ROBOT_H;
-	// offsets of the 9 non-centre probes from the centre: cell units in x/y, metres in z
-	float ox[10], oy[10], oz[10];
-	ox[0] = oy[0] = oz[0] = 0.0f;
+	// offsets of the 9 probes from the centre: cell units in x/y, metres in z.  p = 2k leg k, 2k+1 corner k, 8 belly
+	float ox[9], oy[9], oz[9];
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
 		const float xb = (k & 2) ? 0.5f * (float) ROBOT_L : -0.5f * (float) ROBOT_L, yb = (k & 1) ? 0.5f * (float) ROBOT_W : -0.5f * (float) ROBOT_W;
 		const float lx = fmaf(R12, yb, R11 * xb), ly = fmaf(R22, yb, R21 * xb), lz = R31 * xb;
-		ox[1 + 2 * k] = lx * kx; oy[1 + 2 * k] = ly * ky; oz[1 + 2 * k] = lz;
-		ox[2 + 2 * k] = fmaf(R13, zb, lx) * kx; oy[2 + 2 * k] = fmaf(R23, zb, ly) * ky; oz[2 + 2 * k] = fmaf(R33, zb, lz);
+		ox[2 * k] = lx * kx; oy[2 * k] = ly * ky; oz[2 * k] = lz;
+		ox[2 * k + 1] = fmaf(R13, zb, lx) * kx; oy[2 * k + 1] = fmaf(R23, zb, ly) * ky; oz[2 * k + 1] = fmaf(R33, zb, lz);
 	}
-	ox[9] = R13 * zb * kx; oy[9] = R23 * zb * ky; oz[9] = R33 * zb;
-	// cells
-	int cell[10];
-	float ux[10], uy[10];
-	bool unsure = false;
+	ox[8] = R13 * zb * kx; oy[8] = R23 * zb * ky; oz[8] = R33 * zb;
+	// cells (no clamping needed: |offset| < T.border cells) and the distance of every probe to its nearest grid line
+	const int base = ixc * T.ny + iyc;
+	int cell[9];
+	float ux[9], uy[9], emin = 1.0f;
 #pragma unroll
-	for (int p = 0; p < 10; ++p) {
+	for (int p = 0; p < 9; ++p) {
 		const float pxf = fux + ox[p], pyf = fuy + oy[p], flx = floorf(pxf), fly = floorf(pyf);
 		ux[p] = pxf - flx; uy[p] = pyf - fly;
-		const int ix = ixc + (int) flx, iy = iyc + (int) fly;
-		unsure = unsure || (ix < 0) || (ix > T.nx - 2) || (iy < 0) || (iy > T.ny - 2) || (ux[p] < MIXED_EDGE) || (ux[p] > 1.0f - MIXED_EDGE) ||
-				 (uy[p] < MIXED_EDGE) || (uy[p] > 1.0f - MIXED_EDGE);
-		cell[p] = max(0, min(ix, T.nx - 2)) * T.ny + max(0, min(iy, T.ny - 2));
+		emin = fminf(emin, fminf(fminf(ux[p], 1.0f - ux[p]), fminf(uy[p], 1.0f - uy[p])));
+		cell[p] = ok ? base + (int) flx * T.ny + (int) fly : 0;
 	}
-	// all 40 loads, then the heights as increments over the first corner
-	float f[10][4];
+	// all 36 loads, then the heights as increments over the first corner
+	float f[9][4];
 #pragma unroll
-	for (int p = 0; p < 10; ++p) {
+	for (int p = 0; p < 9; ++p) {
 		const float *q = (const float *) T.z + cell[p];
 		f[p][0] = __ldg(q); f[p][1] = __ldg(q + 1); f[p][2] = __ldg(q + T.ny); f[p][3] = __ldg(q + T.ny + 1);
 	}
-	ProbeBits pb = {0u, 0u, 0u};
-	double m[10];
+	double m[9];
 #pragma unroll
-	for (int p = 0; p < 10; ++p) {
+	for (int p = 0; p < 9; ++p) {
 		const float f11 = f[p][0], f12 = f[p][1], f21 = f[p][2], f22 = f[p][3];
-		pb.nan |= ((f11 != f11) || (f12 != f12) || (f21 != f21) || (f22 != f22)) ? (1u << p) : 0u;
 		const float lo = (f21 - f11) * ux[p], hi = fmaf(f22 - f12, ux[p], f12 - f11);
 		const float inc = fmaf(hi - lo, uy[p], lo);  // ground(p) - f11
-		m[p] = (s.z - (double) f11) + (double) (oz[p] - inc);  // height of the probe point above the ground
+		const double H = (p & 1) ? H_MIN : (p == 8 ? H_MIN : H_MAX);
+		m[p] = ((s.z - (double) f11) - H) + (double) (oz[p] - inc);  // clearance margin: leg - H_MAX, corner / belly - H_MIN
 	}
-	double leg_m[4], cor_m[4];
+	// the reference's check order (:564-634), with no NaN and no out-of-grid probe possible here
+	const bool stance = phase == GBP_STANCE;
+	bool near = false;
+	unsigned bad = 0;
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
-		leg_m[k] = m[1 + 2 * k] - H_MAX;
-		cor_m[k] = m[2 + 2 * k] - H_MIN;
+		near = near || (fabs(m[2 * k + 1]) < MIXED_MARGIN) || (stance && fabs(m[2 * k]) < MIXED_MARGIN);
+		bad |= ((m[2 * k + 1] < 0.0) || (stance && m[2 * k] > 0.0)) ? (1u << k) : 0u;
 	}
-	Counters tmp = {0, 0, 0, 0};
-	valid = replay_checks(pb, pre_bad, speed_bad, phase == GBP_STANCE, leg_m, cor_m, m[9] - H_MIN, MIXED_MARGIN, tmp);
-	// the sub-state is decided here only if nothing on the reference's path was uncertain.  Probes past the first
-	// failing check are ignored by the replay; `unsure` (edges / out-of-grid) is conservative over all probes.
-	if (!ok || unsure || (tmp.flags & GBP_FLAG_NEAR)) return false;
-	c.substates += tmp.substates; c.nanprobes += tmp.nanprobes; c.lookups += tmp.lookups; c.flags |= tmp.flags;
+	near = near || (fabs(m[8]) < MIXED_MARGIN);
+	if (!ok || near || emin < MIXED_EDGE) return false;
+	const bool alive0 = !(pitch_bad || speed_bad);
+	const int corners = alive0 ? min(__ffs(bad | 16u), 4) : 0;  // corners the reference evaluates before it returns
+	const bool all_ok = alive0 && bad == 0;
+	c.substates += 1;
+	c.nanprobes += 1 + corners;
+	c.lookups += 2 * corners + (all_ok ? 1 : 0);
+	valid = all_ok && !(m[8] < 0.0);
 	return true;
 }
 
