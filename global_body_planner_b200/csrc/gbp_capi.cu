@@ -214,6 +214,7 @@ int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const d
 	{  // farthest a leg / corner / belly probe can be from the centre: sqrt(0.15^2 + 0.15^2) + 0.05 < 0.27 m
 		const double step = v.step_x < v.step_y ? v.step_x : v.step_y;
 		v.border = (int) std::ceil(0.27 / step) + 1;
+		if (nx < 16 * v.border || ny < 16 * v.border) v.mixed_ok = 0;  // border zone too large a share: fp64 walk throughout
 	}
 	*out = t;
 	return GBP_OK;
@@ -379,7 +380,7 @@ int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states
 	} else {
 		// persistent-style geometry: a multiple of the SM count; each warp owns a contiguous range
 		const int threads = RF_WARPS * 32, warps_per_block = RF_WARPS;
-		int64_t max_warps = (int64_t) sm_count() * RF_WARPS * RF_MINBLOCKS;  // one wave of resident warps  // 16 resident warps per SM at this register budget
+		int64_t max_warps = (int64_t) sm_count() * RF_WARPS * (t->view.mixed_ok ? 3 : 2);  // one wave of resident warps  // 16 resident warps per SM at this register budget
 		int64_t per_warp = (n + max_warps - 1) / max_warps;
 		if (per_warp < 64) per_warp = 64;
 		per_warp = (per_warp + RF_CHUNK - 1) / RF_CHUNK * RF_CHUNK;  // chunks of the TMA ring are 32-aligned
@@ -404,10 +405,24 @@ int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states
 			attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
 			cfg.numAttrs = 1;
 		}
-#define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt))
-		if (t->view.cell_f32) { if (t->view.uniform) GBP_WALK_(MapF32U); else GBP_WALK_(MapF32N); }
-		else { if (t->view.uniform) GBP_WALK_(MapF64U); else GBP_WALK_(MapF64N); }
+		if (t->view.mixed_ok) {
+			// mixed-precision walk (3 CTAs / SM) + fp64 redo pass over the candidates it could not decide
+			int64_t *redo = nullptr;
+			CU(cudaMallocAsync((void **) &redo, (size_t) n * sizeof(int64_t) + 16, st));
+			unsigned long long *redo_count = (unsigned long long *) (redo + n);
+			CU(cudaMemsetAsync(redo_count, 0, sizeof(unsigned long long), st));
+			CU(cudaLaunchKernelEx(&cfg, k_validate_refill<MapF32U, true>, t->view, n, per_warp, states, actions, direction, adaptive, verdict,
+								  flags, s_new, t_new, t->d_cnt, redo, redo_count));
+			if (!getenv("GBP_SKIP_REDO"))
+				k_validate_redo<MapF32U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
+																	   flags, s_new, t_new, t->d_cnt);
+			CU(cudaFreeAsync(redo, st));
+		} else {
+#define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M, false>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt, (int64_t *) nullptr, (unsigned long long *) nullptr))
+			if (t->view.cell_f32) { if (t->view.uniform) GBP_WALK_(MapF32U); else GBP_WALK_(MapF32N); }
+			else { if (t->view.uniform) GBP_WALK_(MapF64U); else GBP_WALK_(MapF64N); }
 #undef GBP_WALK_
+		}
 		if (s_new && !walk_only) k_pair_outputs<<<blocks_for(n, 256), 256, 0, st>>>(n, states, actions, s_new);
 	}
 	CU(cudaGetLastError());

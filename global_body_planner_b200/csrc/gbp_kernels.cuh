@@ -179,8 +179,8 @@ __device__ __forceinline__ void cursor_start(Cursor &q, int dir) {
 }
 // isValidState of the sub-state at the cursor, through the fast validity path (guard-band accuracy;
 // the exact propagation is only used for outputs, see cursor_advance)
-template <typename M>
-__device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q) {
+template <typename M, bool MIXED_ONLY = false>
+__device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q, bool *undecided = nullptr) {
 	Pose6 p;
 	double tmp[8];
 	switch (q.phase) {
@@ -191,6 +191,11 @@ __device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q) {
 	default: apply_flight(q.s, -q.a[7], tmp); p = stance_reverse_fast(tmp, q.a, q.f, q.phase == PH_REV_ST ? q.t : 0.0); break;
 	}
 	const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
+	if (MIXED_ONLY) {
+		bool valid = false;
+		*undecided = !is_valid_state_mixed<M>(T, p, ph, q.c, valid);
+		return valid;
+	}
 	return is_valid_state_auto<M>(T, p, ph, q.c);
 }
 // How the reference's s_new output is obtained once a pair check has finished.  The (cheap) decision is
@@ -489,16 +494,17 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 				 : "memory");
 }
 
-#ifndef RF_MINBLOCKS
-#define RF_MINBLOCKS 2
-#endif
-template <typename M>
-__global__ void __launch_bounds__(RF_WARPS * 32, RF_MINBLOCKS) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
+// MIXED_ONLY = true: the walk uses the mixed-precision evaluator alone (fewer registers: 3 CTAs / SM); a
+// candidate that reaches a sub-state the evaluator cannot decide is dropped from this pass — its index goes to
+// the redo list and k_validate_redo walks it again with the fp64 evaluator.
+template <typename M, bool MIXED_ONLY>
+__global__ void __launch_bounds__(RF_WARPS * 32, MIXED_ONLY ? 3 : 2) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
 																   const double *__restrict__ states, const double *__restrict__ actions,
 																   const uint8_t *__restrict__ dir, int adaptive,
 																   uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
 																   double *__restrict__ s_new, double *__restrict__ t_new,
-																   unsigned long long *__restrict__ cnt) {
+																   unsigned long long *__restrict__ cnt, int64_t *__restrict__ redo_idx,
+																   unsigned long long *__restrict__ redo_count) {
 	__shared__ __align__(128) unsigned char ring[RF_WARPS][RF_NBUF][RF_SLOT_BYTES + 112];  // slots padded to 128 B multiples
 	__shared__ __align__(8) uint64_t bars[RF_WARPS][RF_NBUF];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -565,8 +571,12 @@ __global__ void __launch_bounds__(RF_WARPS * 32, RF_MINBLOCKS) k_validate_refill
 			issued = __shfl_sync(FULL, issued, 0);
 		}
 		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) break;
-		bool valid = true;
-		if (q.phase != PH_IDLE) valid = cursor_check<M>(T, q);
+		bool valid = true, undecided = false;
+		if (q.phase != PH_IDLE) valid = cursor_check<M, MIXED_ONLY>(T, q, &undecided);
+		if (MIXED_ONLY && undecided) {  // hand the whole candidate to the fp64 pass
+			redo_idx[atomicAdd(redo_count, 1ull)] = mine;
+			q.phase = PH_IDLE;
+		}
 		if (q.phase != PH_IDLE) {
 			OutRecipe out;
 			int r = cursor_advance(q, valid, adaptive != 0, out);
@@ -582,6 +592,47 @@ __global__ void __launch_bounds__(RF_WARPS * 32, RF_MINBLOCKS) k_validate_refill
 				q.phase = PH_IDLE;
 			}
 		}
+	}
+	flush_counters(cnt, k, L, np, oog, near, nvalid);
+}
+
+// fp64 pass over the candidates the mixed-precision walk could not decide (about 1 %)
+template <typename M>
+__global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int64_t *__restrict__ redo_idx,
+														const unsigned long long *__restrict__ redo_count, const double *__restrict__ states,
+														const double *__restrict__ actions, const uint8_t *__restrict__ dir, int adaptive,
+														uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags, double *__restrict__ s_new,
+														double *__restrict__ t_new, unsigned long long *__restrict__ cnt) {
+	const unsigned long long m = *redo_count;
+	unsigned long long k = 0, L = 0, np = 0, oog = 0, near = 0, nvalid = 0;
+	for (unsigned long long j = blockIdx.x * (unsigned long long) blockDim.x + threadIdx.x; j < m; j += (unsigned long long) gridDim.x * blockDim.x) {
+		const int64_t i = redo_idx[j];
+		Cursor q;
+		load_state(states + 8 * i, q.s);
+		load_action(actions + 10 * i, q.a);
+		cursor_start(q, dir[i]);
+		OutRecipe out;
+		int r = 0;
+		while (!r) {
+			Pose6 p;
+			double tmp[8];
+			switch (q.phase) {
+			case PH_FWD_ST: p = stance_fast(q.s, q.a, q.f, q.t); break;
+			case PH_FWD_FL:
+			case PH_FWD_LAND: stance_fast8(q.s, q.a, q.f, q.a[6], tmp); p = flight_fast(tmp, q.phase == PH_FWD_FL ? q.t : q.a[7]); break;
+			case PH_REV_FL: p = flight_fast(q.s, -q.t); break;
+			default: apply_flight(q.s, -q.a[7], tmp); p = stance_reverse_fast(tmp, q.a, q.f, q.phase == PH_REV_ST ? q.t : 0.0); break;
+			}
+			const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
+			r = cursor_advance(q, is_valid_state_fast<M>(T, p, ph, q.c), adaptive != 0, out);
+		}
+		const bool ok = r == 2;
+		verdict[i] = ok ? 1 : 0;
+		if (flags) flags[i] = (uint8_t) (q.c.flags | (ok ? GBP_FLAG_VALID : 0));
+		if (s_new) *reinterpret_cast<double2 *>(s_new + 8 * i) = make_double2(out.tau, (double) out.kind);
+		if (t_new) t_new[i] = q.t_new;
+		k += q.c.substates; L += q.c.lookups; np += q.c.nanprobes;
+		oog += (q.c.flags & GBP_FLAG_OOG) ? 1 : 0; near += (q.c.flags & GBP_FLAG_NEAR) ? 1 : 0; nvalid += ok ? 1 : 0;
 	}
 	flush_counters(cnt, k, L, np, oog, near, nvalid);
 }
