@@ -90,6 +90,8 @@ struct gbp_terrain {
 	void *d_z = nullptr;
 	void *d_n = nullptr;
 	unsigned long long *d_cnt = nullptr;  // 6 work counters of the last validate launch
+	int *d_redo = nullptr;                // redo list of the mixed-precision walk: [redo_cap] indices + an 8-byte counter
+	size_t redo_cap = 0;
 	size_t z_bytes = 0;                   // height grid bytes
 	float l2_hit_ratio = 0.f;             // share of the grid that fits the persisting L2 carve-out (0 = no window)
 	std::vector<double> hx, hy;
@@ -241,7 +243,7 @@ int gbp_terrain_create_gridmap(int nx, int ny, double res, double cx, double cy,
 
 void gbp_terrain_destroy(gbp_terrain *t) {
 	if (!t) return;
-	cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z); cudaFree(t->d_n); cudaFree(t->d_cnt);
+	cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z); cudaFree(t->d_n); cudaFree(t->d_cnt); cudaFree(t->d_redo);
 	delete t;
 }
 int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes) {
@@ -407,18 +409,26 @@ int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states
 		}
 		if (t->view.mixed_ok) {
 			// mixed-precision walk (3 CTAs / SM) + fp64 redo pass over the candidates it could not decide
-			int64_t *redo = nullptr;
-			CU(cudaMallocAsync((void **) &redo, (size_t) n * sizeof(int64_t) + 16, st));
-			unsigned long long *redo_count = (unsigned long long *) (redo + n);
+			if (n > 0x7fffffff) return fail(GBP_E_INVALID, "at most 2^31-1 candidates per call");
+			gbp_terrain *tm = const_cast<gbp_terrain *>(t);  // grow-only scratch owned by the handle (handles are not thread-safe)
+			if (tm->redo_cap < (size_t) n) {
+				CU(cudaStreamSynchronize(st));
+				cudaFree(tm->d_redo);
+				tm->d_redo = nullptr; tm->redo_cap = 0;
+				const size_t cap = ((size_t) n + 1023) / 1024 * 1024;
+				CU(cudaMalloc((void **) &tm->d_redo, cap * sizeof(int) + 16));
+				tm->redo_cap = cap;
+			}
+			int *redo = tm->d_redo;
+			unsigned long long *redo_count = (unsigned long long *) (redo + tm->redo_cap);
 			CU(cudaMemsetAsync(redo_count, 0, sizeof(unsigned long long), st));
 			CU(cudaLaunchKernelEx(&cfg, k_validate_refill<MapF32U, true>, t->view, n, per_warp, states, actions, direction, adaptive, verdict,
 								  flags, s_new, t_new, t->d_cnt, redo, redo_count));
 			if (!getenv("GBP_SKIP_REDO"))
 				k_validate_redo<MapF32U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
 																	   flags, s_new, t_new, t->d_cnt);
-			CU(cudaFreeAsync(redo, st));
 		} else {
-#define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M, false>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt, (int64_t *) nullptr, (unsigned long long *) nullptr))
+#define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M, false>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt, (int *) nullptr, (unsigned long long *) nullptr))
 			if (t->view.cell_f32) { if (t->view.uniform) GBP_WALK_(MapF32U); else GBP_WALK_(MapF32N); }
 			else { if (t->view.uniform) GBP_WALK_(MapF64U); else GBP_WALK_(MapF64N); }
 #undef GBP_WALK_
@@ -453,7 +463,7 @@ int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, co
 	if (n == 0) return GBP_OK;
 	constexpr int NBUF = 3;
 	const int64_t chunk = n < (1 << 20) ? n : (1 << 20);
-	struct Set { cudaStream_t st = nullptr; char *in = nullptr, *out = nullptr; unsigned long long *cnt = nullptr; } sets[NBUF];
+	struct Set { cudaStream_t st = nullptr; char *in = nullptr, *out = nullptr; unsigned long long *cnt = nullptr; int *redo = nullptr; } sets[NBUF];
 	const size_t in_bytes = (size_t) chunk * (64 + 80 + 1), out_bytes = (size_t) chunk * (64 + 8 + 1 + 1);
 	const int nsets = (int) ((n + chunk - 1) / chunk < NBUF ? (n + chunk - 1) / chunk : NBUF);
 	int rc = GBP_OK;
@@ -463,7 +473,7 @@ int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, co
 	auto cleanup = [&]() {
 		for (int k = 0; k < NBUF; ++k) {
 			if (sets[k].st) cudaStreamSynchronize(sets[k].st);
-			cudaFree(sets[k].in); cudaFree(sets[k].out); cudaFree(sets[k].cnt);
+			cudaFree(sets[k].in); cudaFree(sets[k].out); cudaFree(sets[k].cnt); cudaFree(sets[k].redo);
 			if (sets[k].st) cudaStreamDestroy(sets[k].st);
 		}
 	};
@@ -473,6 +483,7 @@ int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, co
 		TRYC(cudaMalloc(&sets[k].in, in_bytes));
 		TRYC(cudaMalloc(&sets[k].out, out_bytes));
 		TRYC(cudaMalloc(&sets[k].cnt, 6 * sizeof(unsigned long long)));
+		TRYC(cudaMalloc((void **) &sets[k].redo, ((size_t) chunk + 1023) / 1024 * 1024 * sizeof(int) + 16));
 	}
 	int64_t ci = 0;
 	for (int64_t off = 0; off < n; off += chunk, ++ci) {
@@ -486,6 +497,8 @@ int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, co
 		TRYC(cudaMemcpyAsync(d_a, actions + 10 * off, (size_t) m * 80, cudaMemcpyHostToDevice, S.st));
 		TRYC(cudaMemcpyAsync(d_d, direction + off, (size_t) m, cudaMemcpyHostToDevice, S.st));
 		shadow.d_cnt = S.cnt;
+		shadow.d_redo = S.redo;
+		shadow.redo_cap = ((size_t) chunk + 1023) / 1024 * 1024;
 		rc = gbp_validate_pairs_dev(&shadow, m, d_s, d_a, d_d, adaptive, variant, d_v, flags ? d_f : nullptr, s_new ? d_sn : nullptr,
 									t_new ? d_tn : nullptr, S.st);
 		if (rc) { cleanup(); return rc; }

@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MIXED_ONLY ? 3 : 2) k_validate_
 																   const uint8_t *__restrict__ dir, int adaptive,
 																   uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
 																   double *__restrict__ s_new, double *__restrict__ t_new,
-																   unsigned long long *__restrict__ cnt, int64_t *__restrict__ redo_idx,
+																   unsigned long long *__restrict__ cnt, int *__restrict__ redo_idx,
 																   unsigned long long *__restrict__ redo_count) {
 	__shared__ __align__(128) unsigned char ring[RF_WARPS][RF_NBUF][RF_SLOT_BYTES + 112];  // slots padded to 128 B multiples
 	__shared__ __align__(8) uint64_t bars[RF_WARPS][RF_NBUF];
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MIXED_ONLY ? 3 : 2) k_validate_
 		bool valid = true, undecided = false;
 		if (q.phase != PH_IDLE) valid = cursor_check<M, MIXED_ONLY>(T, q, &undecided);
 		if (MIXED_ONLY && undecided) {  // hand the whole candidate to the fp64 pass
-			redo_idx[atomicAdd(redo_count, 1ull)] = mine;
+			redo_idx[atomicAdd(redo_count, 1ull)] = (int) mine;
 			q.phase = PH_IDLE;
 		}
 		if (q.phase != PH_IDLE) {
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MIXED_ONLY ? 3 : 2) k_validate_
 
 // fp64 pass over the candidates the mixed-precision walk could not decide (about 1 %)
 template <typename M>
-__global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int64_t *__restrict__ redo_idx,
+__global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int *__restrict__ redo_idx,
 														const unsigned long long *__restrict__ redo_count, const double *__restrict__ states,
 														const double *__restrict__ actions, const uint8_t *__restrict__ dir, int adaptive,
 														uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags, double *__restrict__ s_new,
