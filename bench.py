@@ -318,7 +318,7 @@ def main():
         assert int(hv.sum().item()) == n_valid and torch.equal(hv, verdict.cpu()), "e2e verdicts differ from the resident run"
         e2e = {"value": world * n * args.e2e_steps / float(te.item()), "unit": "validated actions/s",
                "h2d_bytes_per_step": n * (64 + 80 + 1), "d2h_bytes_per_step": n * (1 + 1 + 64 + 8), "steps": args.e2e_steps,
-               "api": "gbp_validate_pairs (host pointers, pinned), 3-deep chunked H2D/kernel/D2H pipeline"}
+               "api": "gbp_validate_pairs (host pointers, pinned): 3 streams, 512K-candidate chunks, H2D / kernels / D2H overlapped"}
         del hs, ha, hd, hv, hf, hsn, htn
 
     # ---- secondary metric: solved plans/s (BASELINE configs[4], scaled to a short run)

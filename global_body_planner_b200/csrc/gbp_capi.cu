@@ -84,8 +84,19 @@ inline unsigned blocks_for(int64_t n, int threads) { return (unsigned) ((n + thr
 
 }  // namespace
 
+// Staging pipeline of the HOST-pointer pair check: ring of device buffer sets, one stream each, kept by the
+// terrain handle between calls (grow-only) so that a call costs copies + kernels, not allocations.
+struct HostPipe {
+	static constexpr int NBUF = 3;
+	cudaStream_t st[NBUF] = {nullptr, nullptr, nullptr};
+	char *in[NBUF] = {nullptr, nullptr, nullptr}, *out[NBUF] = {nullptr, nullptr, nullptr};
+	int *redo[NBUF] = {nullptr, nullptr, nullptr};
+	int64_t chunk = 0;  // candidates per buffer set
+};
+
 struct gbp_terrain {
 	TerrainView view;
+	HostPipe pipe;
 	double *d_x = nullptr, *d_y = nullptr;
 	void *d_z = nullptr;
 	void *d_n = nullptr;
@@ -244,6 +255,10 @@ int gbp_terrain_create_gridmap(int nx, int ny, double res, double cx, double cy,
 void gbp_terrain_destroy(gbp_terrain *t) {
 	if (!t) return;
 	cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z); cudaFree(t->d_n); cudaFree(t->d_cnt); cudaFree(t->d_redo);
+	for (int k = 0; k < HostPipe::NBUF; ++k) {
+		cudaFree(t->pipe.in[k]); cudaFree(t->pipe.out[k]); cudaFree(t->pipe.redo[k]);
+		if (t->pipe.st[k]) cudaStreamDestroy(t->pipe.st[k]);
+	}
 	delete t;
 }
 int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes) {
@@ -361,15 +376,23 @@ int gbp_distance(int kind, int64_t n, const double *q1, const double *q2, double
 }
 
 // ------------------------------------------------------------------------------ validate_pairs
+static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
+							 int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream,
+							 bool zero_counters);
 int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
 						   int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream) {
+	return validate_dev_impl(t, n, states, actions, direction, adaptive, variant, verdict, flags, s_new, t_new, stream, true);
+}
+static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
+							 int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream,
+							 bool zero_counters) {
 	if (!t || n < 0 || (n && (!states || !actions || !direction || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
 	if (variant < 0 || variant > 5 || variant == 4) return fail(GBP_E_INVALID, "variant must be 0..3 or 5");
 	const bool walk_only = variant == 5;
 	if (walk_only) variant = 3;
 	if (variant == 2 && adaptive) return fail(GBP_E_INVALID, "variant 2 (warp per action) supports the fixed step only");
 	cudaStream_t st = (cudaStream_t) stream;
-	CU(cudaMemsetAsync(t->d_cnt, 0, 6 * sizeof(unsigned long long), st));
+	if (zero_counters) CU(cudaMemsetAsync(t->d_cnt, 0, 6 * sizeof(unsigned long long), st));
 	if (n == 0) return GBP_OK;
 	if (variant == 0) variant = 3;
 	const bool f32 = t->view.cell_f32 != 0;
@@ -455,65 +478,62 @@ int gbp_validate_counters(const gbp_terrain *t, int64_t counters6[6]) {
 	return GBP_OK;
 }
 
-// HOST buffers: chunks of candidates flow through NBUF device buffer sets, each on its own stream, so
-// the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap.
+// HOST buffers: chunks of candidates flow through the handle's ring of device buffer sets, each on its own
+// stream, so the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap (PCIe is
+// full duplex).  Nothing in the loop blocks the host; work counters accumulate on the device.
 int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
 					   int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new) {
 	if (!t || n < 0 || (n && (!states || !actions || !direction || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
 	if (n == 0) return GBP_OK;
-	constexpr int NBUF = 3;
-	const int64_t chunk = n < (1 << 20) ? n : (1 << 20);
-	struct Set { cudaStream_t st = nullptr; char *in = nullptr, *out = nullptr; unsigned long long *cnt = nullptr; int *redo = nullptr; } sets[NBUF];
-	const size_t in_bytes = (size_t) chunk * (64 + 80 + 1), out_bytes = (size_t) chunk * (64 + 8 + 1 + 1);
-	const int nsets = (int) ((n + chunk - 1) / chunk < NBUF ? (n + chunk - 1) / chunk : NBUF);
-	int rc = GBP_OK;
-	unsigned long long total[6] = {0, 0, 0, 0, 0, 0};
-	std::vector<unsigned long long> hcnt((size_t) 6 * ((n + chunk - 1) / chunk));
-	gbp_terrain shadow = *t;  // per-set counter buffers, same view
-	auto cleanup = [&]() {
+	constexpr int NBUF = HostPipe::NBUF;
+	HostPipe &P = const_cast<gbp_terrain *>(t)->pipe;  // scratch owned by the handle (handles are not thread-safe)
+	const int64_t want = n < (1 << 19) ? (n + 1023) / 1024 * 1024 : (1 << 19);
+	if (P.chunk < want) {
 		for (int k = 0; k < NBUF; ++k) {
-			if (sets[k].st) cudaStreamSynchronize(sets[k].st);
-			cudaFree(sets[k].in); cudaFree(sets[k].out); cudaFree(sets[k].cnt); cudaFree(sets[k].redo);
-			if (sets[k].st) cudaStreamDestroy(sets[k].st);
+			if (P.st[k]) CU(cudaStreamSynchronize(P.st[k]));
+			cudaFree(P.in[k]); cudaFree(P.out[k]); cudaFree(P.redo[k]);
+			P.in[k] = P.out[k] = nullptr; P.redo[k] = nullptr;
 		}
-	};
-#define TRYC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(GBP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
-	for (int k = 0; k < nsets; ++k) {
-		TRYC(cudaStreamCreateWithFlags(&sets[k].st, cudaStreamNonBlocking));
-		TRYC(cudaMalloc(&sets[k].in, in_bytes));
-		TRYC(cudaMalloc(&sets[k].out, out_bytes));
-		TRYC(cudaMalloc(&sets[k].cnt, 6 * sizeof(unsigned long long)));
-		TRYC(cudaMalloc((void **) &sets[k].redo, ((size_t) chunk + 1023) / 1024 * 1024 * sizeof(int) + 16));
+		P.chunk = 0;
+		for (int k = 0; k < NBUF; ++k) {
+			if (!P.st[k]) CU(cudaStreamCreateWithFlags(&P.st[k], cudaStreamNonBlocking));
+			CU(cudaMalloc(&P.in[k], (size_t) want * (64 + 80 + 1)));
+			CU(cudaMalloc(&P.out[k], (size_t) want * (64 + 8 + 1 + 1)));
+			CU(cudaMalloc((void **) &P.redo[k], (size_t) want * sizeof(int) + 16));
+		}
+		P.chunk = want;
 	}
+	const int64_t chunk = P.chunk;
+	CU(cudaMemset(t->d_cnt, 0, 6 * sizeof(unsigned long long)));
+	gbp_terrain shadow = *t;  // same view and counters, per-set redo scratch
 	int64_t ci = 0;
-	for (int64_t off = 0; off < n; off += chunk, ++ci) {
-		Set &S = sets[ci % nsets];
+	int rc = GBP_OK;
+	for (int64_t off = 0; off < n && rc == GBP_OK; off += chunk, ++ci) {
+		const int k = (int) (ci % NBUF);
+		cudaStream_t st = P.st[k];
 		const int64_t m = n - off < chunk ? n - off : chunk;
-		double *d_s = (double *) S.in, *d_a = (double *) (S.in + (size_t) chunk * 64);
-		uint8_t *d_d = (uint8_t *) (S.in + (size_t) chunk * 144);
-		double *d_sn = (double *) S.out, *d_tn = (double *) (S.out + (size_t) chunk * 64);
-		uint8_t *d_v = (uint8_t *) (S.out + (size_t) chunk * 72), *d_f = d_v + chunk;
-		TRYC(cudaMemcpyAsync(d_s, states + 8 * off, (size_t) m * 64, cudaMemcpyHostToDevice, S.st));
-		TRYC(cudaMemcpyAsync(d_a, actions + 10 * off, (size_t) m * 80, cudaMemcpyHostToDevice, S.st));
-		TRYC(cudaMemcpyAsync(d_d, direction + off, (size_t) m, cudaMemcpyHostToDevice, S.st));
-		shadow.d_cnt = S.cnt;
-		shadow.d_redo = S.redo;
-		shadow.redo_cap = ((size_t) chunk + 1023) / 1024 * 1024;
-		rc = gbp_validate_pairs_dev(&shadow, m, d_s, d_a, d_d, adaptive, variant, d_v, flags ? d_f : nullptr, s_new ? d_sn : nullptr,
-									t_new ? d_tn : nullptr, S.st);
-		if (rc) { cleanup(); return rc; }
-		TRYC(cudaMemcpyAsync(verdict + off, d_v, (size_t) m, cudaMemcpyDeviceToHost, S.st));
-		if (flags) TRYC(cudaMemcpyAsync(flags + off, d_f, (size_t) m, cudaMemcpyDeviceToHost, S.st));
-		if (s_new) TRYC(cudaMemcpyAsync(s_new + 8 * off, d_sn, (size_t) m * 64, cudaMemcpyDeviceToHost, S.st));
-		if (t_new) TRYC(cudaMemcpyAsync(t_new + off, d_tn, (size_t) m * 8, cudaMemcpyDeviceToHost, S.st));
-		TRYC(cudaMemcpyAsync(hcnt.data() + 6 * ci, S.cnt, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, S.st));
+		double *d_s = (double *) P.in[k], *d_a = (double *) (P.in[k] + (size_t) chunk * 64);
+		uint8_t *d_d = (uint8_t *) (P.in[k] + (size_t) chunk * 144);
+		double *d_sn = (double *) P.out[k], *d_tn = (double *) (P.out[k] + (size_t) chunk * 64);
+		uint8_t *d_v = (uint8_t *) (P.out[k] + (size_t) chunk * 72), *d_f = d_v + chunk;
+		CU(cudaMemcpyAsync(d_s, states + 8 * off, (size_t) m * 64, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(d_a, actions + 10 * off, (size_t) m * 80, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(d_d, direction + off, (size_t) m, cudaMemcpyHostToDevice, st));
+		shadow.d_redo = P.redo[k];
+		shadow.redo_cap = (size_t) chunk;
+		rc = validate_dev_impl(&shadow, m, d_s, d_a, d_d, adaptive, variant, d_v, flags ? d_f : nullptr, s_new ? d_sn : nullptr,
+							   t_new ? d_tn : nullptr, st, false);
+		if (rc) break;
+		CU(cudaMemcpyAsync(verdict + off, d_v, (size_t) m, cudaMemcpyDeviceToHost, st));
+		if (flags) CU(cudaMemcpyAsync(flags + off, d_f, (size_t) m, cudaMemcpyDeviceToHost, st));
+		if (s_new) CU(cudaMemcpyAsync(s_new + 8 * off, d_sn, (size_t) m * 64, cudaMemcpyDeviceToHost, st));
+		if (t_new) CU(cudaMemcpyAsync(t_new + off, d_tn, (size_t) m * 8, cudaMemcpyDeviceToHost, st));
 	}
-	for (int k = 0; k < nsets; ++k) TRYC(cudaStreamSynchronize(sets[k].st));
-	for (int64_t c = 0; c < ci; ++c) for (int i = 0; i < 6; ++i) total[i] += hcnt[6 * c + i];
-	TRYC(cudaMemcpy(t->d_cnt, total, sizeof total, cudaMemcpyHostToDevice));
-#undef TRYC
-	cleanup();
-	return GBP_OK;
+	for (int k = 0; k < NBUF; ++k) {
+		cudaError_t e = cudaStreamSynchronize(P.st[k]);
+		if (e != cudaSuccess && rc == GBP_OK) rc = fail(GBP_E_CUDA, std::string("validate pipeline: ") + cudaGetErrorString(e));
+	}
+	return rc;
 }
 
 // ------------------------------------------------------------------------------------ samplers
