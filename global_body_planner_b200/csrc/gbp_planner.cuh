@@ -1,10 +1,14 @@
 // Device-resident batch planner: one WARP per planning query runs the whole bidirectional loop
-// (runRRTConnect, rrt_connect.cpp:230-314) with an iteration budget instead of the wall clock.
-// Queries are independent, so there is no inter-warp or inter-GPU traffic.
+// (runRRTConnect, rrt_connect.cpp:230-314; RRT*-Connect main loop, rrt_star_connect.cpp:130-165) with an
+// iteration budget instead of the wall clock.  Queries are independent: no inter-warp or
+// inter-GPU traffic.
 //   nearest neighbour : lanes stride over the query's SoA tree, warp-shuffle argmin
-//   newConfig         : lane j validates candidate j (ACTION cell (2*iter+half)*K + j), ballot /
-//                       argmin selection (first valid in stream order, or closest valid)
+//   newConfig         : lane j validates candidate j (ACTION cell (2*iter+half)*K + j), ballot / argmin
+//                       selection (first valid in stream order, or closest valid)
 //   connect           : closed-form action + pair check, evaluated warp-uniformly
+//   RRT* extend       : lane per near vertex runs both attemptConnect probes (geometry only), then lane 0
+//                       replays parent choice and rewiring in ascending id order (rrt_star_connect.cpp:12-75)
+//   postProcessPath   : lane per later path state probes attemptConnect, farthest REACHED wins
 // Tree arenas live in HBM, one slot per resident warp, reused across the queries a warp processes.
 #pragma once
 #include <string>
@@ -14,22 +18,70 @@
 namespace gbp {
 
 struct PlanArena {
-	double *v, *act, *g, *y;  // per slot: 2 trees x cap x {8, 10, 1, 1} doubles
-	int *parent;              // per slot: 2 trees x cap
 	int cap;
+	double *v, *act, *g, *y;         // per slot: 2 trees x cap x {8, 10, 1, 1} doubles
+	int *parent, *child, *sibling;   // per slot: 2 trees x cap (child / sibling lists replace GraphClass::successors)
+	// scratch per slot: RRT* near set (cap entries) and the stitched path (2*cap entries)
+	int *near_id, *near_in, *near_out;   // [cap]: vertex id, attemptConnect status near->new and new->near
+	double *near_ain, *near_aout;        // [cap][10]: the two connect actions
+	double *pstate, *paction;            // [2*cap][8], [2*cap][10]
 };
 
-__device__ __forceinline__ TreeView arena_tree(const PlanArena &A, int slot, int which, int *n_ptr) {
-	TreeView T;
+struct PlanTree {
+	TreeView t;
+	int *child, *sibling;
+};
+
+__device__ __forceinline__ PlanTree arena_tree(const PlanArena &A, int slot, int which, int *n_ptr) {
+	PlanTree T;
 	const size_t t = (size_t) slot * 2 + which;
-	T.cap = A.cap;
-	T.n = n_ptr;
-	T.v = A.v + t * 8 * A.cap;
-	T.act = A.act + t * 10 * A.cap;
-	T.parent = A.parent + t * A.cap;
-	T.g = A.g + t * A.cap;
-	T.y = A.y + t * A.cap;
+	T.t.cap = A.cap;
+	T.t.n = n_ptr;
+	T.t.v = A.v + t * 8 * A.cap;
+	T.t.act = A.act + t * 10 * A.cap;
+	T.t.parent = A.parent + t * A.cap;
+	T.t.g = A.g + t * A.cap;
+	T.t.y = A.y + t * A.cap;
+	T.child = A.child + t * A.cap;
+	T.sibling = A.sibling + t * A.cap;
 	return T;
+}
+__device__ __forceinline__ void plan_tree_init(PlanTree &T, const double root[8]) {  // GraphClass::init (graph_class.cpp:140-152)
+	*T.t.n = 1;
+	for (int d = 0; d < 8; ++d) T.t.v[(size_t) d * T.t.cap] = root[d];
+	for (int d = 0; d < 10; ++d) T.t.act[(size_t) d * T.t.cap] = 0;
+	T.t.parent[0] = -1; T.child[0] = -1; T.sibling[0] = -1; T.t.g[0] = 0; T.t.y[0] = 0;
+}
+__device__ __forceinline__ void plan_link(PlanTree &T, int p, int c) { T.t.parent[c] = p; T.sibling[c] = T.child[p]; T.child[p] = c; }
+__device__ __forceinline__ void plan_unlink(PlanTree &T, int p, int c) {  // graph_class.cpp:44-59
+	int *it = &T.child[p];
+	while (*it != -1 && *it != c) it = &T.sibling[*it];
+	if (*it == c) *it = T.sibling[c];
+	T.sibling[c] = -1;
+}
+__device__ __forceinline__ int plan_push(PlanTree &T, int parent, const double s[8], const double a[10]) {
+	const int i = tree_push(T.t, parent, s, a);
+	T.child[i] = -1; T.sibling[i] = -1;
+	plan_link(T, parent, i);
+	return i;
+}
+// updateGYValue (graph_class.cpp:131-138): set (g, y) of `root` and refresh its subtree, stack-free pre-order walk
+__device__ void plan_update_gy(PlanTree &T, int root, double g, double y) {
+	T.t.g[root] = g;
+	T.t.y[root] = y;
+	int i = T.child[root];
+	while (i != -1) {
+		const int p = T.t.parent[i];
+		double a[8], b[8];
+		tree_get(T.t, p, a);
+		tree_get(T.t, i, b);
+		T.t.g[i] = T.t.g[p] + pose_distance(a, b);
+		T.t.y[i] = T.t.y[p] + yaw_distance(a, b);
+		if (T.child[i] != -1) { i = T.child[i]; continue; }
+		while (i != root && T.sibling[i] == -1) i = T.t.parent[i];
+		if (i == root) break;
+		i = T.sibling[i];
+	}
 }
 
 __device__ __forceinline__ int warp_nearest(const TreeView &T, int nv, const double q[8], int lane) {
@@ -40,21 +92,18 @@ __device__ __forceinline__ int warp_nearest(const TreeView &T, int nv, const dou
 	return bi == 0x7fffffff ? 0 : bi;
 }
 
-// extend (rrt.cpp:77-102) on tree T toward s; returns status, appends on success.
+// newConfig (rrt.cpp:20-70) generalised to K candidates; uniform outputs.  Returns found.
 template <typename M>
-__device__ int warp_extend(const TerrainView &Tv, TreeView &T, int &nv, const double s[8], int dir, uint64_t seed, uint64_t query,
-						   uint64_t cell, const gbp_plan_params &P, int lane, long long &pair_checks) {
-	const int near = warp_nearest(T, nv, s, lane);
-	double s_near[8], nn[3], R[9];
-	tree_get(T, near, s_near);
+__device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const double s_near[8], int dir, uint64_t seed, uint64_t query,
+								uint64_t cell, const gbp_plan_params &P, int lane, long long &pair_checks, double s_new[8], double a_new[10]) {
+	double nn[3], R[9];
 	const double best0 = state_distance(s_near, s);
 	unsigned fl = 0;
-	surface_normal(Tv, s[0], s[1], nn, fl);  // rrt.cpp:25
+	surface_normal(Tv, s[0], s[1], nn, fl);  // rrt.cpp:25 — at the TARGET sample
 	grf_rotation(nn, R);
 	const int K = P.k_candidates;
 	double my_d = INFINITY, my_sn[8], my_a[10];
-	int my_j = 0x7fffffff;
-	int first = 0x7fffffff;
+	int my_j = 0x7fffffff, first = 0x7fffffff;
 	for (int base = 0; base < K; base += 32) {
 		const int j = base + lane;
 		bool ok = false;
@@ -86,47 +135,203 @@ __device__ int warp_extend(const TerrainView &Tv, TreeView &T, int &nv, const do
 		double bd = my_d;
 		int bj = my_j;
 		warp_argmin(bd, bj);
-		if (bj == 0x7fffffff) return GBP_TRAPPED;
+		if (bj == 0x7fffffff) return false;
 		src_lane = bj & 31;
 		d_sel = bd;
 	} else {
 		pair_checks += (first == 0x7fffffff) ? K : first + 1;
-		if (first == 0x7fffffff) return GBP_TRAPPED;
+		if (first == 0x7fffffff) return false;
 		src_lane = first & 31;
 		d_sel = __shfl_sync(FULL, my_d, src_lane);
 	}
-	if (!(d_sel < best0)) return GBP_TRAPPED;  // rrt.cpp:55-66
-	double sn[8], a[10];
+	if (!(d_sel < best0)) return false;  // rrt.cpp:55-66
 #pragma unroll
-	for (int i = 0; i < 8; ++i) sn[i] = __shfl_sync(FULL, my_sn[i], src_lane);
+	for (int i = 0; i < 8; ++i) s_new[i] = __shfl_sync(FULL, my_sn[i], src_lane);
 #pragma unroll
-	for (int i = 0; i < 10; ++i) a[i] = __shfl_sync(FULL, my_a[i], src_lane);
-	if (lane == 0) tree_push(T, near, sn, a);
+	for (int i = 0; i < 10; ++i) a_new[i] = __shfl_sync(FULL, my_a[i], src_lane);
+	return true;
+}
+
+// RRTClass::extend (rrt.cpp:77-102)
+template <typename M>
+__device__ int warp_extend(const TerrainView &Tv, PlanTree &T, int &nv, const double s[8], int dir, uint64_t seed, uint64_t query,
+						   uint64_t cell, const gbp_plan_params &P, int lane, long long &pair_checks) {
+	const int near = warp_nearest(T.t, nv, s, lane);
+	double s_near[8], sn[8], a[10];
+	tree_get(T.t, near, s_near);
+	if (!warp_new_config<M>(Tv, s, s_near, dir, seed, query, cell, P, lane, pair_checks, sn, a)) return GBP_TRAPPED;
+	if (lane == 0) plan_push(T, near, sn, a);
 	__syncwarp();
 	nv += 1;
 	return state_distance(sn, s) <= GOAL_BOUNDS ? GBP_REACHED : GBP_ADVANCED;
 }
 
+// RRTStarConnectClass::extend (rrt_star_connect.cpp:12-75)
+template <typename M>
+__device__ int warp_extend_star(const TerrainView &Tv, PlanTree &T, int &nv, const double s[8], int dir, uint64_t seed, uint64_t query,
+								uint64_t cell, const gbp_plan_params &P, const PlanArena &A, int slot, int lane, long long &pair_checks) {
+	const int nearest = warp_nearest(T.t, nv, s, lane);
+	double s_nearest[8], s_new[8], a_new[10];
+	tree_get(T.t, nearest, s_nearest);
+	if (!warp_new_config<M>(Tv, s, s_nearest, dir, seed, query, cell, P, lane, pair_checks, s_new, a_new)) return GBP_TRAPPED;
+	const int id = nv;
+	if (lane == 0) {  // addVertex (:22)
+		*T.t.n = id + 1;
+		for (int d = 0; d < 8; ++d) T.t.v[(size_t) d * T.t.cap + id] = s_new[d];
+		T.t.parent[id] = -1; T.child[id] = -1; T.sibling[id] = -1;
+	}
+	__syncwarp();
+	nv += 1;
+	// near set in ascending id (neighborhoodDist, planner_class.cpp:173-182); probe near -> new for every member
+	int *nid = A.near_id + (size_t) slot * A.cap, *nin = A.near_in + (size_t) slot * A.cap, *nout = A.near_out + (size_t) slot * A.cap;
+	double *ain = A.near_ain + (size_t) slot * A.cap * 10, *aout = A.near_aout + (size_t) slot * A.cap * 10;
+	int count = 0;
+	unsigned checks = 0;
+	for (int j0 = 0; j0 < nv; j0 += 32) {
+		const int j = j0 + lane;
+		bool in = false;
+		double sj[8];
+		if (j < nv) {
+			tree_get(T.t, j, sj);
+			const double d = state_distance(s_new, sj);
+			in = (d <= RRT_STAR_DELTA) && (d > 0);
+		}
+		const unsigned m = __ballot_sync(FULL, in);
+		if (in) {
+			const int pos = count + __popc(m & ((1u << lane) - 1));
+			double dummy[8], ac[10];
+			Counters c = {0, 0, 0, 0};
+			nid[pos] = j;
+			nin[pos] = attempt_connect<M>(Tv, sj, s_new, dir, P.adaptive != 0, dummy, ac, c, checks);
+			for (int d = 0; d < 10; ++d) ain[(size_t) pos * 10 + d] = ac[d];
+		}
+		count += __popc(m);
+	}
+	__syncwarp();
+	int parent = nearest;
+	if (lane == 0) {  // choose parent (:30-44), link the new vertex
+		double g_new = T.t.g[nearest] + pose_distance(s_new, s_nearest), y_new = T.t.y[nearest] + yaw_distance(s_new, s_nearest);
+		for (int i = 0; i < count; ++i) {
+			if (nin[i] != GBP_REACHED) continue;
+			double sj[8];
+			tree_get(T.t, nid[i], sj);
+			const double g = T.t.g[nid[i]] + pose_distance(sj, s_new);
+			if (g < g_new) {
+				for (int d = 0; d < 10; ++d) a_new[d] = ain[(size_t) i * 10 + d];
+				parent = nid[i];
+				g_new = g;
+				y_new = T.t.y[nid[i]] + yaw_distance(sj, s_new);
+			}
+		}
+		plan_link(T, parent, id);
+		plan_update_gy(T, id, g_new, y_new);
+		for (int d = 0; d < 10; ++d) T.t.act[(size_t) d * T.t.cap + id] = a_new[d];
+	}
+	parent = __shfl_sync(FULL, parent, 0);
+	// probe new -> near for every member but the parent (:51-53), then rewire in id order
+	for (int i0 = 0; i0 < count; i0 += 32) {
+		const int i = i0 + lane;
+		if (i < count && nid[i] != parent) {
+			double sj[8], dummy[8], ac[10];
+			Counters c = {0, 0, 0, 0};
+			tree_get(T.t, nid[i], sj);
+			nout[i] = attempt_connect<M>(Tv, s_new, sj, dir, P.adaptive != 0, dummy, ac, c, checks);
+			for (int d = 0; d < 10; ++d) aout[(size_t) i * 10 + d] = ac[d];
+		}
+	}
+	pair_checks += __reduce_add_sync(FULL, checks);
+	__syncwarp();
+	if (lane == 0) {
+		for (int i = 0; i < count; ++i) {  // rewire (:50-64)
+			const int k = nid[i];
+			if (k == parent || nout[i] != GBP_REACHED) continue;
+			double sj[8];
+			tree_get(T.t, k, sj);
+			const double through = T.t.g[id] + pose_distance(sj, s_new);
+			if (T.t.g[k] > through) {
+				plan_unlink(T, T.t.parent[k], k);
+				plan_link(T, id, k);
+				plan_update_gy(T, k, through, T.t.y[id] + yaw_distance(sj, s_new));
+				for (int d = 0; d < 10; ++d) T.t.act[(size_t) d * T.t.cap + k] = aout[(size_t) i * 10 + d];
+			}
+		}
+	}
+	__syncwarp();
+	return state_distance(s_new, s) <= GOAL_BOUNDS ? GBP_REACHED : GBP_ADVANCED;
+}
+
 // connect (rrt_connect.cpp:98-120)
 template <typename M>
-__device__ int warp_connect(const TerrainView &Tv, TreeView &T, int &nv, const double s[8], int dir, const gbp_plan_params &P,
-							int lane, long long &pair_checks) {
-	const int near = warp_nearest(T, nv, s, lane);
+__device__ int warp_connect(const TerrainView &Tv, PlanTree &T, int &nv, const double s[8], int dir, const gbp_plan_params &P, int lane,
+							long long &pair_checks) {
+	const int near = warp_nearest(T.t, nv, s, lane);
 	double s_near[8], sn[8], an[10];
-	tree_get(T, near, s_near);
+	tree_get(T.t, near, s_near);
 	Counters c = {0, 0, 0, 0};
 	unsigned checks = 0;
 	const int r = attempt_connect<M>(Tv, s_near, s, dir, P.adaptive != 0, sn, an, c, checks);
 	pair_checks += checks;
 	if (r != GBP_TRAPPED) {
-		if (lane == 0) tree_push(T, near, sn, an);
+		if (lane == 0) plan_push(T, near, sn, an);
 		__syncwarp();
 		nv += 1;
 	}
 	return r;
 }
 
+// postProcessPath (rrt_connect.cpp:139-227) on a stitched path in scratch, in place.  The reference probes
+// attemptConnect(s, s_next) from the last state backwards and takes the first REACHED; lanes probe 32 later states
+// at a time from the far end, the farthest REACHED one wins — the same choice.  Quirk kept: the fallback branch adds to
+// path_cost only.  Returns the new number of states; stats3 = {length, yaw, cost}.
 template <typename M>
+__device__ int warp_post_process(const TerrainView &Tv, double *ps, double *pa, int ns, bool adaptive, int lane, double stats3[3]) {
+	int m = 1, cur = 0;
+	double len = 0, yaw = 0, cost = 0;
+	while (cur < ns - 1) {
+		double sc[8];
+		for (int d = 0; d < 8; ++d) sc[d] = ps[8 * (size_t) cur + d];
+		int pick = -1;
+		double a_pick[10];
+		for (int hi = ns - 1; hi > cur && pick < 0; hi -= 32) {
+			const int j = hi - lane;
+			int st = GBP_TRAPPED;
+			double an[10];
+			if (j > cur) {
+				double sj[8], dummy[8];
+				for (int d = 0; d < 8; ++d) sj[d] = ps[8 * (size_t) j + d];
+				Counters c = {0, 0, 0, 0};
+				unsigned checks = 0;
+				st = attempt_connect<M>(Tv, sc, sj, GBP_FORWARD, adaptive, dummy, an, c, checks);
+			}
+			const unsigned reached = __ballot_sync(FULL, st == GBP_REACHED);
+			if (reached) {
+				const int src = __ffs(reached) - 1;  // lowest lane = farthest state
+				pick = hi - src;
+#pragma unroll
+				for (int d = 0; d < 10; ++d) a_pick[d] = __shfl_sync(FULL, an[d], src);
+			}
+		}
+		const int nxt = pick >= 0 ? pick : cur + 1;
+		double sn[8];
+		for (int d = 0; d < 8; ++d) sn[d] = ps[8 * (size_t) nxt + d];
+		const double dl = pose_distance(sc, sn);
+		if (pick >= 0) { len += dl; yaw += yaw_distance(sc, sn); }
+		else { for (int d = 0; d < 10; ++d) a_pick[d] = pa[10 * (size_t) cur + d]; }  // the original action into state cur+1
+		cost += dl;
+		__syncwarp();
+		if (lane == 0) {
+			for (int d = 0; d < 8; ++d) ps[8 * (size_t) m + d] = sn[d];
+			for (int d = 0; d < 10; ++d) pa[10 * (size_t) (m - 1) + d] = a_pick[d];
+		}
+		__syncwarp();
+		++m;
+		cur = nxt;
+	}
+	stats3[0] = len; stats3[1] = yaw; stats3[2] = cost;
+	return m;
+}
+
+template <typename M, bool STAR>
 __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, const double *__restrict__ starts,
 													 const double *__restrict__ goals, uint64_t seed, uint64_t query0,
 													 gbp_plan_params P, PlanArena A, int *__restrict__ counts,
@@ -136,16 +341,11 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 	const int64_t slot = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
 	const int64_t nslots = ((int64_t) gridDim.x * blockDim.x) >> 5;
 	for (int64_t qi = slot; qi < nq; qi += nslots) {
-		TreeView Ta = arena_tree(A, (int) slot, 0, counts + 2 * slot), Tb = arena_tree(A, (int) slot, 1, counts + 2 * slot + 1);
+		PlanTree Ta = arena_tree(A, (int) slot, 0, counts + 2 * slot), Tb = arena_tree(A, (int) slot, 1, counts + 2 * slot + 1);
 		double start[8], goal[8];
 #pragma unroll
 		for (int d = 0; d < 8; ++d) { start[d] = starts[8 * qi + d]; goal[d] = goals[8 * qi + d]; }
-		if (lane == 0) {  // GraphClass::init (graph_class.cpp:140-152)
-			*Ta.n = 1; *Tb.n = 1;
-			for (int d = 0; d < 8; ++d) { Ta.v[(size_t) d * Ta.cap] = start[d]; Tb.v[(size_t) d * Tb.cap] = goal[d]; }
-			for (int d = 0; d < 10; ++d) { Ta.act[(size_t) d * Ta.cap] = 0; Tb.act[(size_t) d * Tb.cap] = 0; }
-			Ta.parent[0] = -1; Tb.parent[0] = -1; Ta.g[0] = 0; Tb.g[0] = 0; Ta.y[0] = 0; Tb.y[0] = 0;
-		}
+		if (lane == 0) { plan_tree_init(Ta, start); plan_tree_init(Tb, goal); }
 		__syncwarp();
 		int na = 1, nb = 1, it = 0;
 		bool solved = false, full = false;
@@ -153,7 +353,7 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 		const uint64_t query = query0 + (uint64_t) qi;
 		for (; it < P.max_iters && !solved && !full; ++it) {
 			for (int half = 0; half < 2 && !solved; ++half) {
-				TreeView &Tx = half == 0 ? Ta : Tb, &Ty = half == 0 ? Tb : Ta;
+				PlanTree &Tx = half == 0 ? Ta : Tb, &Ty = half == 0 ? Tb : Ta;
 				int &nx = half == 0 ? na : nb, &ny = half == 0 ? nb : na;
 				const int dir_ext = half == 0 ? GBP_FORWARD : GBP_REVERSE, dir_con = half == 0 ? GBP_REVERSE : GBP_FORWARD;
 				if (nx >= A.cap || ny >= A.cap) { full = true; break; }
@@ -163,51 +363,58 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 				Counters c = {0, 0, 0, 0};
 				if (!is_valid_state_auto<M>(Tv, pose6(s_rand), GBP_STANCE, c)) continue;  // rrt_connect.cpp:254
 				++nn_queries;
-				if (warp_extend<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, lane, pair_checks) == GBP_TRAPPED) continue;
+				const int r = STAR ? warp_extend_star<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, A, (int) slot, lane, pair_checks)
+								   : warp_extend<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, lane, pair_checks);
+				if (r == GBP_TRAPPED) continue;
 				double s_new[8];
-				tree_get(Tx, nx - 1, s_new);
+				tree_get(Tx.t, nx - 1, s_new);
 				++nn_queries;
 				if (warp_connect<M>(Tv, Ty, ny, s_new, dir_con, P, lane, pair_checks) == GBP_REACHED) solved = true;
 			}
 		}
 		// statistics + path (rrt_connect.cpp:269-270, :381-401, :463-466)
-		if (lane == 0) {
-			gbp_plan_stats st;
-			st.solved = solved ? 1 : 0; st.iters = it; st.nv_a = na; st.nv_b = nb; st.path_states = 0; st.pad = 0;
-			st.path_length = 0; st.path_yaw = 0; st.path_duration = 0; st.pair_checks = pair_checks; st.nn_queries = nn_queries;
-			if (solved) {
-				st.path_length = Ta.g[na - 1] + Tb.g[nb - 1];
-				st.path_yaw = Ta.y[na - 1] + Tb.y[nb - 1];
-				int la = 0, lb = 0;
-				for (int i = na - 1; i != -1; i = Ta.parent[i]) ++la;
-				for (int i = nb - 1; i != -1; i = Tb.parent[i]) ++lb;
-				const int total = la + lb - 1;
-				st.path_states = total;
-				double dur = 0;
-				double *ps = path_states ? path_states + (size_t) qi * path_cap * 8 : nullptr;
-				double *pa = path_actions ? path_actions + (size_t) qi * path_cap * 10 : nullptr;
-				// the duration sum follows the path order (a_0 .. a_{total-2}) so the fp64 sum matches the reference's
+		gbp_plan_stats st;
+		st.solved = solved ? 1 : 0; st.iters = it; st.nv_a = na; st.nv_b = nb; st.path_states = 0; st.pad = 0;
+		st.path_length = 0; st.path_yaw = 0; st.path_duration = 0; st.pair_checks = pair_checks; st.nn_queries = nn_queries;
+		if (solved) {
+			double *ps = A.pstate + (size_t) slot * 2 * A.cap * 8, *pa = A.paction + (size_t) slot * 2 * A.cap * 10;
+			int la = 0, lb = 0;
+			for (int i = na - 1; i != -1; i = Ta.t.parent[i]) ++la;
+			for (int i = nb - 1; i != -1; i = Tb.t.parent[i]) ++lb;
+			int total = la + lb - 1;
+			if (lane == 0) {  // stitch: start .. shared state (tree A), then tree B back to the goal
 				int k = la - 1;
-				for (int i = na - 1; i != -1; i = Ta.parent[i], --k) {
-					if (ps && k < path_cap) for (int d = 0; d < 8; ++d) ps[8 * k + d] = Ta.v[(size_t) d * Ta.cap + i];
-					if (pa && k > 0 && k - 1 < path_cap) for (int d = 0; d < 10; ++d) pa[10 * (k - 1) + d] = Ta.act[(size_t) d * Ta.cap + i];
+				for (int i = na - 1; i != -1; i = Ta.t.parent[i], --k) {
+					for (int d = 0; d < 8; ++d) ps[8 * (size_t) k + d] = Ta.t.v[(size_t) d * Ta.t.cap + i];
+					if (k > 0) for (int d = 0; d < 10; ++d) pa[10 * (size_t) (k - 1) + d] = Ta.t.act[(size_t) d * Ta.t.cap + i];
 				}
-				// tree A actions in path order: walk again from the root side using the stored parents
-				for (int step = 1; step < la; ++step) {
-					int i = na - 1;
-					for (int up = 0; up < la - 1 - step; ++up) i = Ta.parent[i];
-					dur += Ta.act[(size_t) 6 * Ta.cap + i] + Ta.act[(size_t) 7 * Ta.cap + i];
+				k = la - 1;  // Tb.last duplicates the shared state: its ACTION is kept, its STATE is dropped (:388-395)
+				for (int i = nb - 1; Tb.t.parent[i] != -1; i = Tb.t.parent[i], ++k) {
+					for (int d = 0; d < 10; ++d) pa[10 * (size_t) k + d] = Tb.t.act[(size_t) d * Tb.t.cap + i];
+					for (int d = 0; d < 8; ++d) ps[8 * (size_t) (k + 1) + d] = Tb.t.v[(size_t) d * Tb.t.cap + Tb.t.parent[i]];
 				}
-				k = la - 1;
-				for (int i = nb - 1; Tb.parent[i] != -1; i = Tb.parent[i], ++k) {
-					dur += Tb.act[(size_t) 6 * Tb.cap + i] + Tb.act[(size_t) 7 * Tb.cap + i];
-					if (pa && k < path_cap) for (int d = 0; d < 10; ++d) pa[10 * k + d] = Tb.act[(size_t) d * Tb.cap + i];
-					if (ps && k + 1 < path_cap) for (int d = 0; d < 8; ++d) ps[8 * (k + 1) + d] = Tb.v[(size_t) d * Tb.cap + Tb.parent[i]];
-				}
-				st.path_duration = dur;
 			}
-			stats[qi] = st;
+			__syncwarp();
+			st.path_length = Ta.t.g[na - 1] + Tb.t.g[nb - 1];
+			st.path_yaw = Ta.t.y[na - 1] + Tb.t.y[nb - 1];
+			if (P.post_process) {
+				double s3[3];
+				total = warp_post_process<M>(Tv, ps, pa, total, P.adaptive != 0, lane, s3);
+				st.path_length = s3[0];
+				st.path_yaw = s3[1];
+			}
+			st.path_states = total;
+			double dur = 0;
+			for (int i = 0; i + 1 < total; ++i) dur += pa[10 * (size_t) i + 6] + pa[10 * (size_t) i + 7];
+			st.path_duration = dur;
+			if (path_states && path_actions) {
+				for (int i = lane; i < total && i < path_cap; i += 32)
+					for (int d = 0; d < 8; ++d) path_states[((size_t) qi * path_cap + i) * 8 + d] = ps[8 * (size_t) i + d];
+				for (int i = lane; i + 1 < total && i < path_cap; i += 32)
+					for (int d = 0; d < 10; ++d) path_actions[((size_t) qi * path_cap + i) * 10 + d] = pa[10 * (size_t) i + d];
+			}
 		}
+		if (lane == 0) stats[qi] = st;
 		__syncwarp();
 	}
 }
@@ -216,7 +423,6 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *starts, const double *goals, uint64_t seed,
 							 uint64_t query0, const gbp_plan_params &P, gbp_plan_stats *stats, double *path_states, double *path_actions,
 							 int path_cap, cudaStream_t st, std::string &err) {
-	if (P.rrt_star || P.post_process) { err = "rrt_star / post_process are not implemented in the device planner yet"; return GBP_E_INVALID; }
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -226,19 +432,34 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	const unsigned grid = (unsigned) (slots / warps_per_block);
 	PlanArena A;
 	A.cap = P.max_vertices;
-	const size_t per = (size_t) slots * 2 * A.cap;
+	const size_t cap = (size_t) A.cap, per = (size_t) slots * 2 * cap;
+	const size_t n_doubles = per * (8 + 10 + 1 + 1) + (size_t) slots * cap * 20 + (size_t) slots * 2 * cap * 18;
+	const size_t n_ints = per * 3 + (size_t) slots * cap * 3 + (size_t) slots * 2;
 	void *mem = nullptr;
-	int *counts = nullptr;
 	cudaError_t e;
-	const size_t bytes = per * (8 + 10 + 1 + 1) * sizeof(double) + per * sizeof(int) + (size_t) slots * 2 * sizeof(int);
-	if ((e = cudaMallocAsync(&mem, bytes, st)) != cudaSuccess) { err = std::string("plan arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
-	A.v = (double *) mem;
-	A.act = A.v + per * 8;
-	A.g = A.act + per * 10;
-	A.y = A.g + per;
-	A.parent = (int *) (A.y + per);
-	counts = A.parent + per;
-#define GBP_PLAN_(M) k_plan_batch<M><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap)
+	if ((e = cudaMallocAsync(&mem, n_doubles * sizeof(double) + n_ints * sizeof(int), st)) != cudaSuccess) {
+		err = std::string("plan arena: ") + cudaGetErrorString(e);
+		return GBP_E_CUDA;
+	}
+	double *dp = (double *) mem;
+	A.v = dp; dp += per * 8;
+	A.act = dp; dp += per * 10;
+	A.g = dp; dp += per;
+	A.y = dp; dp += per;
+	A.near_ain = dp; dp += (size_t) slots * cap * 10;
+	A.near_aout = dp; dp += (size_t) slots * cap * 10;
+	A.pstate = dp; dp += (size_t) slots * 2 * cap * 8;
+	A.paction = dp; dp += (size_t) slots * 2 * cap * 10;
+	int *ip = (int *) dp;
+	A.parent = ip; ip += per;
+	A.child = ip; ip += per;
+	A.sibling = ip; ip += per;
+	A.near_id = ip; ip += (size_t) slots * cap;
+	A.near_in = ip; ip += (size_t) slots * cap;
+	A.near_out = ip; ip += (size_t) slots * cap;
+	int *counts = ip;
+#define GBP_PLAN_(M) do { if (P.rrt_star) k_plan_batch<M, true><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); \
+						  else k_plan_batch<M, false><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); } while (0)
 	if (Tv.cell_f32) { if (Tv.uniform) GBP_PLAN_(MapF32U); else GBP_PLAN_(MapF32N); }
 	else { if (Tv.uniform) GBP_PLAN_(MapF64U); else GBP_PLAN_(MapF64N); }
 #undef GBP_PLAN_

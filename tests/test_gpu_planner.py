@@ -34,16 +34,20 @@ def queries(o, T, n, seed):
     return np.array(s), np.array(g)
 
 
-@pytest.mark.parametrize("name,K,best", [("slope", 6, 0), ("rough_terrain", 6, 0), ("slope", 48, 1), ("synth_nan", 6, 0)])
-def test_plan_batch_matches_oracle(gbp, name, K, best):
+@pytest.mark.parametrize("name,K,best,star,post", [("slope", 6, 0, 0, 0), ("rough_terrain", 6, 0, 0, 0), ("slope", 48, 1, 0, 0),
+                                                  ("synth_nan", 6, 0, 0, 0), ("slope", 6, 0, 0, 1), ("synth_nan", 24, 1, 0, 1),
+                                                  ("slope", 32, 1, 1, 0), ("synth_nan", 32, 1, 1, 1), ("rough_terrain", 32, 1, 1, 0)])
+def test_plan_batch_matches_oracle(gbp, name, K, best, star, post):
+    """RRT-Connect, RRT*-Connect (choose parent + rewire) and postProcessPath, all resident on the device."""
     T = load_terrain(name)
     o = po.Oracle(T)
     t = gbp.Terrain(T.x, T.y, T.z, T.dx, T.dy, T.dz)
     s, g = queries(o, T, 24, 5)
     assert len(s) >= 8
-    P = gbp.PlanParams(K, best, 400, 256, 0, 0, 0)
+    iters = 250 if star else 400
+    P = gbp.PlanParams(K, best, iters, 256, 0, star, post)
     st, ps, pa = t.plan_batch(s, g, 9, 100, P, path_cap=128)
-    Po = po.PlanParams(K, best, 400, 256, 0, 0, 0)
+    Po = po.PlanParams(K, best, iters, 256, 0, star, post)
     nsolved = 0
     for i in range(len(s)):
         so, pso, pao = o.plan(s[i], g[i], 9, 100 + i, Po)
@@ -53,7 +57,7 @@ def test_plan_batch_matches_oracle(gbp, name, K, best):
             nsolved += 1
             n = so.path_states
             assert_bits_equal(np.array([st["path_length"][i]]), np.array([so.path_length]), what="path length")
-            assert abs(st["path_yaw"][i] - so.path_yaw) < 1e-9
+            assert abs(st["path_yaw"][i] - so.path_yaw) < 1e-9  # yaw sums go through atan2 (libm): tolerance, not bits
             assert_bits_equal(np.array([st["path_duration"][i]]), np.array([so.path_duration]), what="path duration")
             assert_bits_equal(ps[i, :n], pso, what="path states")
             assert_bits_equal(pa[i, :n - 1], pao, what="path actions")

@@ -78,3 +78,31 @@ def test_gridmap_ingest_matches_loaddata():
     r2 = po.Ref(T)
     px = rng.uniform(x[0], x[-1] - 1e-9, 500); py = rng.uniform(y[0], y[-1] - 1e-9, 500)
     assert_bits_equal(r.ground_height(px, py), r2.ground_height(px, py), what="gridmap vs loadData")
+
+
+def test_post_process_path(pair):
+    """postProcessPath (rrt_connect.cpp:139-227): oracle restatement vs the reference on paths the oracle planner found."""
+    o, r, T = pair
+    q = o.sample_states(5, 1, 0, 2000)
+    q[:, 3:8] = 0; q[:, 3] = 0.5
+    v, _ = o.valid_states(q, po.STANCE)
+    q = q[v == 1]
+    P = po.PlanParams(32, 1, 300, 256, 0, 0, 0)
+    compared = 0
+    for i in range(min(len(q) - 1, 40)):
+        d = np.hypot(q[:, 0] - q[i, 0], q[:, 1] - q[i, 1])
+        j = np.nonzero((d > 1.0) & (d < 3.0))[0]
+        if not len(j):
+            continue
+        st, ps, pa = o.plan(q[i], q[j[0]], 9, 100 + i, P)
+        if not st.solved or st.path_states < 3:
+            continue
+        so, ao, s3 = o.post_process_path(ps, pa)
+        sr, ar, r3 = r.post_process_path(ps, pa)
+        assert so.shape == sr.shape
+        assert_bits_equal(so, sr, what="post-processed states")
+        assert_bits_equal(ao, ar, what="post-processed actions")
+        assert_bits_equal(s3[[0, 2]], r3[[0, 2]], what="path length / cost")
+        assert abs(s3[1] - r3[1]) < 1e-12
+        compared += 1
+    assert compared >= 1 or T.nx < 60
