@@ -47,6 +47,33 @@ def make_queries(valid_states_fn, sample_states_fn, nq, seed, stream):
     return np.array(starts[:nq]), np.array(goals[:nq])
 
 
+def run_rough_k4096(gbp, torch, dev, nq=512, iters=100):
+    """BASELINE configs[1]: RRT-Connect on the reference's data/rough_terrain (committed as
+    tests/golden/terrain_rough_terrain.npz), 4096 candidate actions per extend (closest valid), start (0,0) ->
+    goal (8,0) at body height 0.375 m; nq independent searches (distinct Philox streams)."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "terrain_rough_terrain.npz"))
+    t = gbp.Terrain(d["x"], d["y"], d["z"], d["dx"], d["dy"], d["dz"])
+    h, _ = t.ground_height([0.0, 8.0], [0.0, 0.0])
+    start = np.array([0, 0, h[0] + 0.375, 1, 0, 0, 0, 0.0]); goal = np.array([8, 0, h[1] + 0.375, 1, 0, 0, 0, 0.0])
+    s = torch.from_numpy(np.repeat(start[None], nq, 0)).to(dev); g = torch.from_numpy(np.repeat(goal[None], nq, 0)).to(dev)
+    P = gbp.PlanParams(4096, 1, iters, 256, 0, 0, 0)
+    dstats = torch.zeros(nq * 64, dtype=torch.uint8, device=dev)
+    cur = torch.cuda.current_stream().cuda_stream
+    t.plan_batch_dev(8, s.data_ptr(), g.data_ptr(), 1, 0, P, dstats.data_ptr(), cur)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t.plan_batch_dev(nq, s.data_ptr(), g.data_ptr(), 1, 0, P, dstats.data_ptr(), cur)
+    e1.record()
+    torch.cuda.synchronize()
+    secs = e0.elapsed_time(e1) * 1e-3
+    st = dstats.cpu().numpy().view(gbp.PLAN_STATS_DTYPE)
+    return {"workload": f"{nq} searches on data/rough_terrain, (0,0)->(8,0), K=4096 closest-valid candidates per extend, {iters} iterations",
+            "validated_actions_per_s": float(st["pair_checks"].sum() / secs), "extends_per_s": float(st["nn_queries"].sum() / 2 / secs),
+            "solved": int(st["solved"].sum()), "solved_plans_per_s": float(st["solved"].sum() / secs), "seconds": secs,
+            "note": "the unmodified CPU reference completes 0 plans in 120 s on this query (BASELINE.md row 9)"}
+
+
 def run(gbp, torch, dist, dev, rank, world, q_per_gpu=Q_PER_GPU, cpu_seconds=8.0, want_cpu=True):
     x, y, z = rough_terrain()
     t = gbp.Terrain(x, y, z)
@@ -94,6 +121,7 @@ def run(gbp, torch, dist, dev, rank, world, q_per_gpu=Q_PER_GPU, cpu_seconds=8.0
            "nn_queries_per_s": float(st["nn_queries"].sum() / secs), "seconds": secs,
            "mean_path_length_m": float(st["path_length"][st["solved"] == 1].mean()) if st["solved"].any() else None,
            "mean_iters": float(st["iters"].mean()), "stats_gather_bytes": int(allstats.nbytes)}
+    out["rough_k4096"] = run_rough_k4096(gbp, torch, dev) if world == 1 or rank == 0 else None
     if want_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import pyoracle as po
