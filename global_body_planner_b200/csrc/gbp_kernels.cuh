@@ -221,62 +221,56 @@ __device__ __forceinline__ void finish_output(const double s[8], const double a[
 
 // Advance after the verdict of the current sub-state.  Returns 0 = continue, 1 = finished invalid,
 // 2 = finished valid.  On finish, `out` says how to compute s_new and q.t_new holds t_new.
+// Written as one predicated flow (not a switch over the six phases): the lanes of a warp are in different
+// phases almost every trip, and a switch would execute all its arms one after the other.
 __device__ __forceinline__ int cursor_advance(Cursor &q, bool valid, bool adaptive, OutRecipe &out) {
 	const double ts = q.a[6], tf = q.a[7];
-	switch (q.phase) {
-	case PH_FWD_ST:
-		if (!valid) {
-			if (!adaptive || (KINEMATICS_RES - 0.01 <= q.step && q.step <= KINEMATICS_RES + 0.01)) {
-				out.kind = OUT_STANCE; out.tau = (1.0 - BACKUP_RATIO) * q.t;  // :725 / :668
-				return 1;
+	const int ph = q.phase;
+	const bool fwd = ph <= PH_FWD_LAND;
+	const bool stance_seg = ph == PH_FWD_ST || ph == PH_REV_ST;   // the sampled stance loop (:718-730, :850-868)
+	const bool terminal = ph == PH_FWD_LAND || ph == PH_REV_START;  // landing / exact start state
+	if (!valid) {
+		if (stance_seg) {
+			if (adaptive && !(KINEMATICS_RES - 0.01 <= q.step && q.step <= KINEMATICS_RES + 0.01)) {
+				q.step = KINEMATICS_RES;  // adaptive step: rewind to the last success (:672-675, :812-815)
+				q.t = fwd ? q.t_ok + q.step : q.t_ok - q.step;
+				if (fwd ? !(q.t <= ts) : !(q.t >= 0)) {
+					q.t = 0; q.phase = fwd ? ((0 < tf) ? PH_FWD_FL : PH_FWD_LAND) : PH_REV_START;
+				}
+				return 0;
 			}
-			q.step = KINEMATICS_RES;
-			q.t = q.t_ok;
+			out.kind = OUT_STANCE;  // back up half of the failed step; REVERSE applies the FORWARD stance to the END state (sic, :862)
+			out.tau = fwd ? (1.0 - BACKUP_RATIO) * q.t : q.t + BACKUP_RATIO * (ts - q.t);
 		} else {
-			q.t_new = q.t; q.t_ls = q.t; q.have_ls = 1;
-			if (adaptive) { q.step += KINEMATICS_RES; q.t_ok = q.t; }
+			// flight / landing failure keeps the last valid stance sample; REVERSE flight failure leaves s_new untouched
+			const bool keep = q.have_ls != 0 && ph != PH_REV_FL;
+			out.kind = keep ? (ph == PH_REV_START ? OUT_REV : OUT_STANCE) : OUT_SAME;
+			out.tau = q.t_ls;
 		}
-		q.t += q.step;
-		if (!(q.t <= ts)) { q.t = 0; q.step = KINEMATICS_RES; q.phase = (0 < tf) ? PH_FWD_FL : PH_FWD_LAND; }
-		return 0;
-	case PH_FWD_FL:
-		if (!valid) { out.kind = q.have_ls ? OUT_STANCE : OUT_SAME; out.tau = q.t_ls; return 1; }  // s_new keeps the last stance sample
-		if (adaptive) q.step += KINEMATICS_RES;
-		q.t += q.step;
-		if (!(q.t < tf)) q.phase = PH_FWD_LAND;
-		return 0;
-	case PH_FWD_LAND:
-		if (!valid) { out.kind = q.have_ls ? OUT_STANCE : OUT_SAME; out.tau = q.t_ls; return 1; }
-		out.kind = OUT_LAND; out.tau = 0;
-		q.t_new = ts + tf;
-		return 2;
-	case PH_REV_FL:
-		if (!valid) { out.kind = OUT_SAME; out.tau = 0; return 1; }
-		if (adaptive) q.step += KINEMATICS_RES;
-		q.t += q.step;
-		if (!(q.t < tf)) { q.t = ts; q.step = KINEMATICS_RES; q.phase = (ts >= 0) ? PH_REV_ST : PH_REV_START; }
-		return 0;
-	case PH_REV_ST:
-		if (!valid) {
-			if (!adaptive || (KINEMATICS_RES - 0.01 <= q.step && q.step <= KINEMATICS_RES + 0.01)) {
-				out.kind = OUT_STANCE; out.tau = q.t + BACKUP_RATIO * (ts - q.t);  // sic (:862): forward stance from the END state
-				return 1;
-			}
-			q.step = KINEMATICS_RES;
-			q.t = q.t_ok;
-		} else {
-			q.t_new = ts - q.t; q.t_ls = q.t; q.have_ls = 1;
-			if (adaptive) { q.step += KINEMATICS_RES; q.t_ok = q.t; }
-		}
-		q.t -= q.step;
-		if (!(q.t >= 0)) q.phase = PH_REV_START;
-		return 0;
-	default:  // PH_REV_START
-		if (!valid) { out.kind = q.have_ls ? OUT_REV : OUT_SAME; out.tau = q.t_ls; return 1; }
-		out.kind = OUT_REV; out.tau = 0;
-		q.t_new = ts;
+		return 1;
+	}
+	if (terminal) {
+		out.kind = fwd ? OUT_LAND : OUT_REV;
+		out.tau = 0;
+		q.t_new = fwd ? ts + tf : ts;
 		return 2;
 	}
+	if (stance_seg) {
+		q.t_ls = q.t; q.have_ls = 1;
+		q.t_new = fwd ? q.t : ts - q.t;
+		if (adaptive) q.t_ok = q.t;
+	}
+	if (adaptive) q.step += KINEMATICS_RES;
+	q.t = ph == PH_REV_ST ? q.t - q.step : q.t + q.step;
+	const bool done = ph == PH_FWD_ST ? !(q.t <= ts) : (ph == PH_REV_ST ? !(q.t >= 0) : !(q.t < tf));
+	if (done) {
+		q.step = KINEMATICS_RES;
+		if (ph == PH_FWD_ST) { q.t = 0; q.phase = (0 < tf) ? PH_FWD_FL : PH_FWD_LAND; }
+		else if (ph == PH_FWD_FL) q.phase = PH_FWD_LAND;
+		else if (ph == PH_REV_FL) { q.t = ts; q.phase = (ts >= 0) ? PH_REV_ST : PH_REV_START; }
+		else q.phase = PH_REV_START;
+	}
+	return 0;
 }
 
 // Sequential walk of one pair by one thread: the cursor machine below run to completion.  Same
