@@ -92,6 +92,50 @@ __device__ __forceinline__ int warp_nearest(const TreeView &T, int nv, const dou
 	return bi == 0x7fffffff ? 0 : bi;
 }
 
+// Only the VERDICT of a candidate matters to newConfig (s_new / t_new of rejected actions are never used), so the
+// fixed-step pair check can be speculated across sub-states: the 32 lanes are split into groups of S = 32 / K lanes
+// (K = 6 -> 5 lanes per candidate, 30 of 32 lanes busy); lane r of a group evaluates sub-state r of the group's
+// candidate (the reference's fp64-accumulated sample times, by walking r steps from the group's cursor), a ballot
+// finds each group's first failing lane, groups whose S sub-states all passed move on by S sub-states.
+// Returns, per group, whether its candidate is fully valid; exact s_test comes from finish_output afterwards.
+template <typename M>
+__device__ __forceinline__ bool group_validate(const TerrainView &Tv, const double s_near[8], const double a[10], int dir, int S, int r,
+											   unsigned gmask, int gshift, bool has_candidate) {
+	Cursor q;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) q.s[i] = s_near[i];
+#pragma unroll
+	for (int i = 0; i < 10; ++i) q.a[i] = a[i];
+	cursor_start(q, dir);
+	const double ts = a[6], tf = a[7];
+	int bph = q.phase;
+	double bt = q.t;
+	int state = has_candidate ? 0 : 1;  // 0 running, 1 invalid / no candidate, 2 valid
+	while (__ballot_sync(FULL, state == 0)) {
+		int ph = bph;
+		double t = bt;
+		for (int i = 0; i < r && ph != PH_DONE; ++i) walk_step(ph, t, ts, tf);
+		const bool active = state == 0 && ph != PH_DONE;
+		bool valid = true;
+		if (active) {
+			q.phase = ph;
+			q.t = t;
+			valid = cursor_check<M>(Tv, q);
+		}
+		const unsigned bad = (__ballot_sync(FULL, active && !valid) >> gshift) & gmask;
+		const unsigned term = (__ballot_sync(FULL, active && (ph == PH_FWD_LAND || ph == PH_REV_START)) >> gshift) & gmask;
+		// the cursor of the group's last lane, one step further, is the next round's base
+		int lph = __shfl_sync(FULL, ph, gshift + S - 1);
+		double lt = __shfl_sync(FULL, t, gshift + S - 1);
+		if (state == 0) {
+			if (bad) state = 1;            // some sub-state on the reference's path failed (earlier ones all passed or are moot)
+			else if (term) state = 2;      // landing / exact start state reached with every sub-state valid
+			else { walk_step(lph, lt, ts, tf); bph = lph; bt = lt; }
+		}
+	}
+	return state == 2;
+}
+
 // newConfig (rrt.cpp:20-70) generalised to K candidates; uniform outputs.  Returns found.
 template <typename M>
 __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const double s_near[8], int dir, uint64_t seed, uint64_t query,
@@ -104,28 +148,58 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 	const int K = P.k_candidates;
 	double my_d = INFINITY, my_sn[8], my_a[10];
 	int my_j = 0x7fffffff, first = 0x7fffffff;
-	for (int base = 0; base < K; base += 32) {
-		const int j = base + lane;
-		bool ok = false;
-		double a[10], sn[8], tn;
-		if (j < K) {
-			sample_action(seed, query, cell * (uint64_t) K + (uint64_t) j, R, false, 0.0, nullptr, nullptr, a);
-			Counters c = {0, 0, 0, 0};
-			ok = validate_pair_seq<M>(Tv, s_near, a, dir, P.adaptive != 0, sn, tn, c);
-		}
-		if (ok) {
-			const double d = state_distance(sn, s);
-			if (P.best_of_k ? (d < my_d) : (my_j == 0x7fffffff)) {
-				my_d = d; my_j = j;
+	if (!P.adaptive) {
+		// speculative form: G candidates per pass, S lanes each
+		const int S = K >= 32 ? 1 : 32 / K, G = 32 / S;
+		const int g = lane / S, r = lane - g * S, gshift = g * S;
+		const unsigned gmask = S == 32 ? FULL : ((1u << S) - 1u);
+		for (int base = 0; base < K; base += G) {
+			const int j = base + g;
+			const bool has = g < G && j < K;
+			double a[10];
+			sample_action(seed, query, cell * (uint64_t) K + (uint64_t) (has ? j : 0), R, false, 0.0, nullptr, nullptr, a);
+			const bool ok = group_validate<M>(Tv, s_near, a, dir, S, r, gmask, has ? gshift : 0, has);
+			if (ok && r == 0) {  // one lane per candidate keeps the result
+				double sn[8];
+				finish_output(s_near, a, dir == GBP_FORWARD ? OUT_LAND : OUT_REV, 0.0, sn);
+				const double d = state_distance(sn, s);
+				if (P.best_of_k ? (d < my_d) : (my_j == 0x7fffffff)) {
+					my_d = d; my_j = j;
 #pragma unroll
-				for (int i = 0; i < 8; ++i) my_sn[i] = sn[i];
+					for (int i = 0; i < 8; ++i) my_sn[i] = sn[i];
 #pragma unroll
-				for (int i = 0; i < 10; ++i) my_a[i] = a[i];
+					for (int i = 0; i < 10; ++i) my_a[i] = a[i];
+				}
+			}
+			if (!P.best_of_k) {
+				const unsigned m = __ballot_sync(FULL, ok && r == 0);
+				if (m) { first = base + (__ffs(m) - 1) / S; break; }  // first valid action decides (rrt.cpp:44-47)
 			}
 		}
-		if (!P.best_of_k) {
-			const unsigned m = __ballot_sync(FULL, ok);
-			if (m) { first = base + __ffs(m) - 1; break; }  // first valid action decides (rrt.cpp:44-47)
+	} else {
+		for (int base = 0; base < K; base += 32) {
+			const int j = base + lane;
+			bool ok = false;
+			double a[10], sn[8], tn;
+			if (j < K) {
+				sample_action(seed, query, cell * (uint64_t) K + (uint64_t) j, R, false, 0.0, nullptr, nullptr, a);
+				Counters c = {0, 0, 0, 0};
+				ok = validate_pair_seq<M>(Tv, s_near, a, dir, true, sn, tn, c);
+			}
+			if (ok) {
+				const double d = state_distance(sn, s);
+				if (P.best_of_k ? (d < my_d) : (my_j == 0x7fffffff)) {
+					my_d = d; my_j = j;
+#pragma unroll
+					for (int i = 0; i < 8; ++i) my_sn[i] = sn[i];
+#pragma unroll
+					for (int i = 0; i < 10; ++i) my_a[i] = a[i];
+				}
+			}
+			if (!P.best_of_k) {
+				const unsigned m = __ballot_sync(FULL, ok);
+				if (m) { first = base + __ffs(m) - 1; break; }
+			}
 		}
 	}
 	int src_lane;
@@ -134,14 +208,23 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 		pair_checks += K;
 		double bd = my_d;
 		int bj = my_j;
-		warp_argmin(bd, bj);
+		// argmin over (distance, candidate index); remember which lane holds the winner
+		int bl = lane;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			const double od = __shfl_xor_sync(FULL, bd, o);
+			const int oj = __shfl_xor_sync(FULL, bj, o), ol = __shfl_xor_sync(FULL, bl, o);
+			if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; bl = ol; }
+		}
 		if (bj == 0x7fffffff) return false;
-		src_lane = bj & 31;
+		src_lane = bl;
 		d_sel = bd;
 	} else {
 		pair_checks += (first == 0x7fffffff) ? K : first + 1;
 		if (first == 0x7fffffff) return false;
-		src_lane = first & 31;
+		// the lane that kept candidate `first`
+		const unsigned holder = __ballot_sync(FULL, my_j == first);
+		src_lane = __ffs(holder) - 1;
 		d_sel = __shfl_sync(FULL, my_d, src_lane);
 	}
 	if (!(d_sel < best0)) return false;  // rrt.cpp:55-66
