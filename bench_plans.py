@@ -59,7 +59,7 @@ def run_rough_k4096(gbp, torch, dev, nq=512, iters=100):
     P = gbp.PlanParams(4096, 1, iters, 256, 0, 0, 0)
     dstats = torch.zeros(nq * 64, dtype=torch.uint8, device=dev)
     cur = torch.cuda.current_stream().cuda_stream
-    t.plan_batch_dev(8, s.data_ptr(), g.data_ptr(), 1, 0, P, dstats.data_ptr(), cur)
+    t.plan_batch_dev(nq, s.data_ptr(), g.data_ptr(), 1, 0, P, dstats.data_ptr(), cur)  # warm-up (also sizes the tree arena)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -92,7 +92,7 @@ def run(gbp, torch, dist, dev, rank, world, q_per_gpu=Q_PER_GPU, cpu_seconds=8.0
     dstats = torch.zeros(nq * 64, dtype=torch.uint8, device=dev)
     cur = torch.cuda.current_stream().cuda_stream
     query0 = rank * q_per_gpu
-    t.plan_batch_dev(min(nq, 256), ds.data_ptr(), dg.data_ptr(), seed, query0, P, dstats.data_ptr(), cur)  # warm-up
+    t.plan_batch_dev(nq, ds.data_ptr(), dg.data_ptr(), seed, query0, P, dstats.data_ptr(), cur)  # warm-up (also sizes the tree arena)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -103,6 +103,8 @@ struct gbp_terrain {
 	unsigned long long *d_cnt = nullptr;  // 6 work counters of the last validate launch
 	int *d_redo = nullptr;                // redo list of the mixed-precision walk: [redo_cap] indices + an 8-byte counter
 	size_t redo_cap = 0;
+	void *d_plan_arena = nullptr;         // tree arena of the batch planner (grow-only)
+	size_t plan_arena_bytes = 0;
 	size_t z_bytes = 0;                   // height grid bytes
 	float l2_hit_ratio = 0.f;             // share of the grid that fits the persisting L2 carve-out (0 = no window)
 	std::vector<double> hx, hy;
@@ -254,7 +256,7 @@ int gbp_terrain_create_gridmap(int nx, int ny, double res, double cx, double cy,
 
 void gbp_terrain_destroy(gbp_terrain *t) {
 	if (!t) return;
-	cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z); cudaFree(t->d_n); cudaFree(t->d_cnt); cudaFree(t->d_redo);
+	cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z); cudaFree(t->d_n); cudaFree(t->d_cnt); cudaFree(t->d_redo); cudaFree(t->d_plan_arena);
 	for (int k = 0; k < HostPipe::NBUF; ++k) {
 		cudaFree(t->pipe.in[k]); cudaFree(t->pipe.out[k]); cudaFree(t->pipe.redo[k]);
 		if (t->pipe.st[k]) cudaStreamDestroy(t->pipe.st[k]);
@@ -824,7 +826,9 @@ int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, c
 	if (p->k_candidates < 1 || p->max_iters < 0 || p->max_vertices < 2) return fail(GBP_E_INVALID, "bad plan parameters");
 	if (nq == 0) return GBP_OK;
 	std::string err;
-	int rc = plan_batch_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, (cudaStream_t) stream, err);
+	gbp_terrain *tm = const_cast<gbp_terrain *>(t);  // scratch owned by the handle (handles are not thread-safe)
+	int rc = plan_batch_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, (cudaStream_t) stream,
+							   &tm->d_plan_arena, &tm->plan_arena_bytes, err);
 	if (rc) return fail(rc, err);
 	return GBP_OK;
 }

@@ -503,9 +503,10 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 }
 
 // host-side launcher: sizes the grid to the SM count, allocates the tree arena for the resident warps
+// `arena` / `arena_bytes`: grow-only device scratch owned by the caller's terrain handle
 inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *starts, const double *goals, uint64_t seed,
 							 uint64_t query0, const gbp_plan_params &P, gbp_plan_stats *stats, double *path_states, double *path_actions,
-							 int path_cap, cudaStream_t st, std::string &err) {
+							 int path_cap, cudaStream_t st, void **arena, size_t *arena_bytes, std::string &err) {
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -518,12 +519,16 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	const size_t cap = (size_t) A.cap, per = (size_t) slots * 2 * cap;
 	const size_t n_doubles = per * (8 + 10 + 1 + 1) + (size_t) slots * cap * 20 + (size_t) slots * 2 * cap * 18;
 	const size_t n_ints = per * 3 + (size_t) slots * cap * 3 + (size_t) slots * 2;
-	void *mem = nullptr;
 	cudaError_t e;
-	if ((e = cudaMallocAsync(&mem, n_doubles * sizeof(double) + n_ints * sizeof(int), st)) != cudaSuccess) {
-		err = std::string("plan arena: ") + cudaGetErrorString(e);
-		return GBP_E_CUDA;
+	const size_t need = n_doubles * sizeof(double) + n_ints * sizeof(int);
+	if (*arena_bytes < need) {
+		cudaStreamSynchronize(st);
+		cudaFree(*arena);
+		*arena = nullptr; *arena_bytes = 0;
+		if ((e = cudaMalloc(arena, need)) != cudaSuccess) { err = std::string("plan arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
+		*arena_bytes = need;
 	}
+	void *mem = *arena;
 	double *dp = (double *) mem;
 	A.v = dp; dp += per * 8;
 	A.act = dp; dp += per * 10;
@@ -547,7 +552,6 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	else { if (Tv.uniform) GBP_PLAN_(MapF64U); else GBP_PLAN_(MapF64N); }
 #undef GBP_PLAN_
 	e = cudaGetLastError();
-	cudaFreeAsync(mem, st);
 	if (e != cudaSuccess) { err = std::string("k_plan_batch: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
 	return GBP_OK;
 }
