@@ -422,8 +422,13 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 													 double *__restrict__ path_actions, int path_cap) {
 	const int lane = threadIdx.x & 31;
 	const int64_t slot = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
-	const int64_t nslots = ((int64_t) gridDim.x * blockDim.x) >> 5;
-	for (int64_t qi = slot; qi < nq; qi += nslots) {
+	unsigned long long *next_query = (unsigned long long *) (counts + 2 * (((int64_t) gridDim.x * blockDim.x) >> 5));
+	while (true) {
+		// queries differ widely in iterations: warps pull the next query from a device counter (no static round-robin tail)
+		unsigned long long grabbed = 0;
+		if (lane == 0) grabbed = atomicAdd(next_query, 1ull);
+		const int64_t qi = (int64_t) __shfl_sync(FULL, grabbed, 0);
+		if (qi >= nq) break;
 		PlanTree Ta = arena_tree(A, (int) slot, 0, counts + 2 * slot), Tb = arena_tree(A, (int) slot, 1, counts + 2 * slot + 1);
 		double start[8], goal[8];
 #pragma unroll
@@ -518,7 +523,7 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	A.cap = P.max_vertices;
 	const size_t cap = (size_t) A.cap, per = (size_t) slots * 2 * cap;
 	const size_t n_doubles = per * (8 + 10 + 1 + 1) + (size_t) slots * cap * 20 + (size_t) slots * 2 * cap * 18;
-	const size_t n_ints = per * 3 + (size_t) slots * cap * 3 + (size_t) slots * 2;
+	const size_t n_ints = per * 3 + (size_t) slots * cap * 3 + (size_t) slots * 2 + 4;  // + the 8-byte work counter
 	cudaError_t e;
 	const size_t need = n_doubles * sizeof(double) + n_ints * sizeof(int);
 	if (*arena_bytes < need) {
@@ -546,6 +551,10 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	A.near_in = ip; ip += (size_t) slots * cap;
 	A.near_out = ip; ip += (size_t) slots * cap;
 	int *counts = ip;
+	{  // 8-byte aligned work counter right after the per-slot vertex counts
+		unsigned long long *next_query = (unsigned long long *) (counts + 2 * slots);
+		if ((e = cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st)) != cudaSuccess) { err = cudaGetErrorString(e); return GBP_E_CUDA; }
+	}
 #define GBP_PLAN_(M) do { if (P.rrt_star) k_plan_batch<M, true><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); \
 						  else k_plan_batch<M, false><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); } while (0)
 	if (Tv.cell_f32) { if (Tv.uniform) GBP_PLAN_(MapF32U); else GBP_PLAN_(MapF32N); }
