@@ -260,7 +260,8 @@ def main():
     per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     # the dominant kernel alone (the walk, k_validate_refill): variant 5 = variant 3 without k_pair_outputs
     walk_variant = 5 if args.variant in (0, 3) else args.variant
-    kernels_per_step = 2 if args.variant in (0, 3) else 1
+    # variant 0/3: the walk (k_validate_refill), the fp64 redo pass when the mixed-precision walk is in use, k_pair_outputs
+    kernels_per_step = (3 if t.flags()["mixed_precision"] else 2) if args.variant in (0, 3) else 1
     evk = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evk[0].record()
     for i in range(args.steps):
@@ -353,7 +354,7 @@ def main():
                 "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                 "bytes_per_candidate": alg_bytes / n, "k_mean": k_tot / n, "L_mean": L_tot / n,
                 "step_ms": float(np.mean(per_step_ms)), "kernels_per_step": kernels_per_step,
-                "note": "fp64-issue/latency-bound gather pipeline; see DESIGN.md for the fp64 ceiling"}
+                "note": "latency/issue-bound terrain-gather pipeline, not HBM-bound (DESIGN.md section 5); launch_ms = walk + redo kernels (variant 5), step_ms adds k_pair_outputs"}
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         roofline["traffic"] = prof.get("dram_bytes_per_launch")

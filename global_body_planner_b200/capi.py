@@ -146,6 +146,11 @@ class Terrain:
         _check(lib().gbp_terrain_dims(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return c.value
 
+    def flags(self):
+        u, m = C.c_int(), C.c_int()
+        _check(lib().gbp_terrain_flags(self.h, C.byref(u), C.byref(m)))
+        return dict(uniform_axes=bool(u.value), mixed_precision=bool(m.value))
+
     def axes(self):
         x, y = np.zeros(self.nx), np.zeros(self.ny)
         _check(lib().gbp_terrain_axes(self.h, _p(x), _p(y)))

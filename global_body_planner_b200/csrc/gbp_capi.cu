@@ -270,6 +270,12 @@ int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes) {
 	if (cell_bytes) *cell_bytes = t->cell_bytes;
 	return GBP_OK;
 }
+int gbp_terrain_flags(const gbp_terrain *t, int *uniform_axes, int *mixed_precision) {
+	if (!t) return fail(GBP_E_INVALID, "terrain is NULL");
+	if (uniform_axes) *uniform_axes = t->view.uniform;
+	if (mixed_precision) *mixed_precision = t->view.mixed_ok;
+	return GBP_OK;
+}
 int gbp_terrain_axes(const gbp_terrain *t, double *x, double *y) {
 	if (!t) return fail(GBP_E_INVALID, "terrain is NULL");
 	if (x) memcpy(x, t->hx.data(), t->hx.size() * sizeof(double));

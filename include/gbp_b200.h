@@ -76,6 +76,9 @@ int gbp_terrain_create_gridmap(int nx, int ny, double resolution, double centre_
                                gbp_terrain **out);
 void gbp_terrain_destroy(gbp_terrain *t);
 int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes);
+/* which evaluator serves this terrain: uniform_axes = cell edges are computed, not loaded; mixed_precision = the
+ * fp32-around-fp64 evaluator applies (fp32 cells, no NaN, uniform axes, pitch >= 1 cm, interior >> border) */
+int gbp_terrain_flags(const gbp_terrain *t, int *uniform_axes, int *mixed_precision);
 /* FastTerrainMap::getXData / getYData (fast_terrain_map.cpp:216-223) */
 int gbp_terrain_axes(const gbp_terrain *t, double *x, double *y);
 /* getGroundHeight (:94-132), heightIsNan (:135-157), getSurfaceNormal (:160-213, not renormalised) */
