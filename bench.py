@@ -149,7 +149,25 @@ def run_cpu(seed, stream, target_seconds, cores, want="reference"):
 
 
 # ------------------------------------------------------------------ main
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route fd 1 to stderr while libraries initialise (NCCL prints its version banner to stdout); the JSON line
+    is written to the saved descriptor by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -189,7 +207,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
                 "e2e": {"value": v, "unit": "validated actions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -380,7 +398,7 @@ def main():
             "valid_fraction": float(all_stats[:, 0].sum() / all_stats[:, 5].sum()),
             "flagged": {"out_of_grid": int(all_stats[:, 3].sum()), "libm_guard_band": int(all_stats[:, 4].sum())},
             "per_rank_valid": [int(v) for v in all_stats[:, 0]], "plans": plans}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
