@@ -100,6 +100,8 @@ struct gbp_terrain {
 	double *d_x = nullptr, *d_y = nullptr;
 	void *d_z = nullptr;
 	void *d_n = nullptr;
+	cudaArray_t z_arr = nullptr;          // block-linear copy of the fp32 height grid behind view.ztex (texture gathers of the walk)
+	cudaTextureObject_t z_tex = 0;
 	unsigned long long *d_cnt = nullptr;  // 6 work counters of the last validate launch
 	int *d_redo = nullptr;                // redo list of the mixed-precision walk: [redo_cap] indices + an 8-byte counter
 	size_t redo_cap = 0;
@@ -231,6 +233,28 @@ int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const d
 		v.border = (int) std::ceil(0.27 / step) + 1;
 		if (nx < 16 * v.border || ny < 16 * v.border) v.mixed_ok = 0;  // border zone too large a share: fp64 walk throughout
 	}
+	if (v.mixed_ok && nx <= 32768 && ny <= 32768 && !getenv("GBP_NO_TEX")) {
+		// the mixed-precision walk fetches each probe's 2x2 cells with one texture gather: needs a CUDA array created
+		// with the gather flag (array x = iy, array y = ix).  Optional: on failure the walk keeps the 4-load form.
+		cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+		cudaResourceDesc rd;
+		cudaTextureDesc td;
+		memset(&rd, 0, sizeof rd);
+		memset(&td, 0, sizeof td);
+		if (cudaMallocArray(&t->z_arr, &fd, (size_t) ny, (size_t) nx, cudaArrayTextureGather) == cudaSuccess &&
+			cudaMemcpy2DToArray(t->z_arr, 0, 0, t->d_z, (size_t) ny * sizeof(float), (size_t) ny * sizeof(float), (size_t) nx,
+								cudaMemcpyDeviceToDevice) == cudaSuccess) {
+			rd.resType = cudaResourceTypeArray;
+			rd.res.array.array = t->z_arr;
+			td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+			td.filterMode = cudaFilterModePoint;
+			td.readMode = cudaReadModeElementType;
+			td.normalizedCoords = 0;
+			if (cudaCreateTextureObject(&t->z_tex, &rd, &td, nullptr) == cudaSuccess) v.ztex = (unsigned long long) t->z_tex;
+		}
+		if (!v.ztex && t->z_arr) { cudaFreeArray(t->z_arr); t->z_arr = nullptr; }
+		(void) cudaGetLastError();
+	}
 	*out = t;
 	return GBP_OK;
 }
@@ -256,6 +280,8 @@ int gbp_terrain_create_gridmap(int nx, int ny, double res, double cx, double cy,
 
 void gbp_terrain_destroy(gbp_terrain *t) {
 	if (!t) return;
+	if (t->z_tex) cudaDestroyTextureObject(t->z_tex);
+	if (t->z_arr) cudaFreeArray(t->z_arr);
 	cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z); cudaFree(t->d_n); cudaFree(t->d_cnt); cudaFree(t->d_redo); cudaFree(t->d_plan_arena);
 	for (int k = 0; k < HostPipe::NBUF; ++k) {
 		cudaFree(t->pipe.in[k]); cudaFree(t->pipe.out[k]); cudaFree(t->pipe.redo[k]);
@@ -453,8 +479,12 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 			int *redo = tm->d_redo;
 			unsigned long long *redo_count = (unsigned long long *) (redo + tm->redo_cap);
 			CU(cudaMemsetAsync(redo_count, 0, sizeof(unsigned long long), st));
-			CU(cudaLaunchKernelEx(&cfg, k_validate_refill<MapF32U, true>, t->view, n, per_warp, states, actions, direction, adaptive, verdict,
-								  flags, s_new, t_new, t->d_cnt, redo, redo_count));
+			if (t->view.ztex)
+				CU(cudaLaunchKernelEx(&cfg, k_validate_refill<MapF32U, true, true>, t->view, n, per_warp, states, actions, direction, adaptive,
+									  verdict, flags, s_new, t_new, t->d_cnt, redo, redo_count));
+			else
+				CU(cudaLaunchKernelEx(&cfg, k_validate_refill<MapF32U, true, false>, t->view, n, per_warp, states, actions, direction, adaptive,
+									  verdict, flags, s_new, t_new, t->d_cnt, redo, redo_count));
 			if (!getenv("GBP_SKIP_REDO"))
 				k_validate_redo<MapF32U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
 																	   flags, s_new, t_new, t->d_cnt);

@@ -33,6 +33,8 @@ struct TerrainView {
 	int border;                     // cells a body probe can lie from the centre's cell (0.23 m / pitch, rounded up, + 1)
 	int uniform;                    // both axes are x0 + i*step to within 1e-12 m: the fast path computes cell edges
 	double step_x, step_y;          // instead of loading them (a probe within 1e-11 m of a grid line is flagged NEAR)
+	unsigned long long ztex;        // cudaTextureObject_t over a block-linear copy of the fp32 height grid (0 = none): the mixed
+	                                // evaluator fetches the 2x2 cells of a probe with ONE tex2Dgather (SASS TLD4) instead of 4 LDGs
 };
 
 // map traits: cell storage type x axis kind
@@ -540,7 +542,10 @@ __device__ __forceinline__ void sincosf_small(float x, float &sn, float &cs) {  
 // Returns true when the sub-state was decided (verdict in `valid`, counters updated); false = needs the fp64 path.
 // Preconditions checked here: the centre lies at least T.border cells inside the grid (so no probe can leave it:
 // no OOG flags, no index clamping) and the map holds no NaN (so heightIsNan never fires; T.mixed_ok).
-template <typename M>
+// TEX = true: the 4 cells of a probe come from one texture gather on T.ztex (array x = iy, array y = ix; sampling at the
+// centre of the 2x2 footprint, (iy + 1, ix + 1), is exact in the unit's fixed-point coordinates; components w, z, x, y
+// = cells (ix,iy), (ix,iy+1), (ix+1,iy), (ix+1,iy+1) — raw fp32 values, so every result is identical to the LDG form).
+template <typename M, bool TEX = false>
 __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const Pose6 &s, int phase, Counters &c, bool &valid) {
 	const bool pitch_bad = fabs(s.pitch) >= P_MAX;
 	// sqrt(r2) > V_MAX  <=>  r2 > nextafter(V_MAX^2): the largest double whose correctly rounded root is still 2.0
@@ -580,21 +585,29 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 	ox[8] = R13 * zb * kx; oy[8] = R23 * zb * ky; oz[8] = R33 * zb;
 	// cells (no clamping needed: |offset| < T.border cells) and the distance of every probe to its nearest grid line
 	const int base = ixc * T.ny + iyc;
+	const float tbx = (float) (iyc + 1), tby = (float) (ixc + 1);  // texel-footprint centre of the centre cell (exact: < 2^24)
 	int cell[9];
+	float tx[9], ty[9];
 	float ux[9], uy[9], emin = 1.0f;
 #pragma unroll
 	for (int p = 0; p < 9; ++p) {
 		const float pxf = fux + ox[p], pyf = fuy + oy[p], flx = floorf(pxf), fly = floorf(pyf);
 		ux[p] = pxf - flx; uy[p] = pyf - fly;
 		emin = fminf(emin, fminf(fminf(ux[p], 1.0f - ux[p]), fminf(uy[p], 1.0f - uy[p])));
-		cell[p] = ok ? base + (int) flx * T.ny + (int) fly : 0;
+		if (TEX) { tx[p] = ok ? tbx + fly : 1.0f; ty[p] = ok ? tby + flx : 1.0f; }
+		else cell[p] = ok ? base + (int) flx * T.ny + (int) fly : 0;
 	}
-	// all 36 loads, then the heights as increments over the first corner
+	// all 36 cells (36 loads or 9 gathers), then the heights as increments over the first corner
 	float f[9][4];
 #pragma unroll
 	for (int p = 0; p < 9; ++p) {
-		const float *q = (const float *) T.z + cell[p];
-		f[p][0] = __ldg(q); f[p][1] = __ldg(q + 1); f[p][2] = __ldg(q + T.ny); f[p][3] = __ldg(q + T.ny + 1);
+		if (TEX) {
+			const float4 g = tex2Dgather<float4>((cudaTextureObject_t) T.ztex, tx[p], ty[p], 0);
+			f[p][0] = g.w; f[p][1] = g.z; f[p][2] = g.x; f[p][3] = g.y;
+		} else {
+			const float *q = (const float *) T.z + cell[p];
+			f[p][0] = __ldg(q); f[p][1] = __ldg(q + 1); f[p][2] = __ldg(q + T.ny); f[p][3] = __ldg(q + T.ny + 1);
+		}
 	}
 	double m[9];
 #pragma unroll

@@ -179,7 +179,7 @@ __device__ __forceinline__ void cursor_start(Cursor &q, int dir) {
 }
 // isValidState of the sub-state at the cursor, through the fast validity path (guard-band accuracy;
 // the exact propagation is only used for outputs, see cursor_advance)
-template <typename M, bool MIXED_ONLY = false>
+template <typename M, bool MIXED_ONLY = false, bool TEX = false>
 __device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q, bool *undecided = nullptr) {
 	Pose6 p;
 	double tmp[8];
@@ -193,7 +193,7 @@ __device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q, bo
 	const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
 	if (MIXED_ONLY) {
 		bool valid = false;
-		*undecided = !is_valid_state_mixed<M>(T, p, ph, q.c, valid);
+		*undecided = !is_valid_state_mixed<M, TEX>(T, p, ph, q.c, valid);
 		return valid;
 	}
 	return is_valid_state_auto<M>(T, p, ph, q.c);
@@ -491,7 +491,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 // MIXED_ONLY = true: the walk uses the mixed-precision evaluator alone (fewer registers: 3 CTAs / SM); a
 // candidate that reaches a sub-state the evaluator cannot decide is dropped from this pass — its index goes to
 // the redo list and k_validate_redo walks it again with the fp64 evaluator.
-template <typename M, bool MIXED_ONLY>
+template <typename M, bool MIXED_ONLY, bool TEX = false>
 __global__ void __launch_bounds__(RF_WARPS * 32, MIXED_ONLY ? 3 : 2) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
 																   const double *__restrict__ states, const double *__restrict__ actions,
 																   const uint8_t *__restrict__ dir, int adaptive,
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MIXED_ONLY ? 3 : 2) k_validate_
 		}
 		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) break;
 		bool valid = true, undecided = false;
-		if (q.phase != PH_IDLE) valid = cursor_check<M, MIXED_ONLY>(T, q, &undecided);
+		if (q.phase != PH_IDLE) valid = cursor_check<M, MIXED_ONLY, TEX>(T, q, &undecided);
 		if (MIXED_ONLY && undecided) {  // hand the whole candidate to the fp64 pass
 			redo_idx[atomicAdd(redo_count, 1ull)] = (int) mine;
 			q.phase = PH_IDLE;
