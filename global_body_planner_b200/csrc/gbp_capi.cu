@@ -11,6 +11,7 @@
 
 #include "gbp_kernels.cuh"
 #include "gbp_planner.cuh"
+#include "gbp_walk.cuh"
 
 using namespace gbp;
 
@@ -81,7 +82,6 @@ int upload(Dev &d, const T *host, size_t n, cudaStream_t st) {
 	} while (0)
 
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned) ((n + threads - 1) / threads); }
-
 }  // namespace
 
 // Staging pipeline of the HOST-pointer pair check: ring of device buffer sets, one stream each, kept by the
@@ -439,12 +439,12 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 	} else {
 		// persistent-style geometry: a multiple of the SM count; each warp owns a contiguous range
 		const int threads = RF_WARPS * 32, warps_per_block = RF_WARPS;
-		int64_t max_warps = (int64_t) sm_count() * RF_WARPS * (t->view.mixed_ok ? 3 : 2);  // one wave of resident warps  // 16 resident warps per SM at this register budget
+		int64_t max_warps = (int64_t) sm_count() * RF_WARPS * (t->view.mixed_ok ? GBP_WALK_CTAS : 2);  // one wave of resident warps  // 16 resident warps per SM at this register budget
 		int64_t per_warp = (n + max_warps - 1) / max_warps;
 		if (per_warp < 64) per_warp = 64;
 		per_warp = (per_warp + RF_CHUNK - 1) / RF_CHUNK * RF_CHUNK;  // chunks of the TMA ring are 32-aligned
-		if ((((uintptr_t) states) | ((uintptr_t) actions) | ((uintptr_t) direction)) & 15)
-			return fail(GBP_E_INVALID, "states/actions/direction must be 16-byte aligned (TMA bulk copies)");
+		if ((((uintptr_t) states) | ((uintptr_t) actions) | ((uintptr_t) direction) | ((uintptr_t) s_new)) & 15)
+			return fail(GBP_E_INVALID, "states/actions/direction/s_new must be 16-byte aligned (TMA bulk copies)");
 		int64_t warps = (n + per_warp - 1) / per_warp;
 		unsigned grid = (unsigned) ((warps + warps_per_block - 1) / warps_per_block);
 		cudaLaunchConfig_t cfg = {};
@@ -479,17 +479,15 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 			int *redo = tm->d_redo;
 			unsigned long long *redo_count = (unsigned long long *) (redo + tm->redo_cap);
 			CU(cudaMemsetAsync(redo_count, 0, sizeof(unsigned long long), st));
-			if (t->view.ztex)
-				CU(cudaLaunchKernelEx(&cfg, k_validate_refill<MapF32U, true, true>, t->view, n, per_warp, states, actions, direction, adaptive,
-									  verdict, flags, s_new, t_new, t->d_cnt, redo, redo_count));
-			else
-				CU(cudaLaunchKernelEx(&cfg, k_validate_refill<MapF32U, true, false>, t->view, n, per_warp, states, actions, direction, adaptive,
-									  verdict, flags, s_new, t_new, t->d_cnt, redo, redo_count));
+#define GBP_WALK_(TEX, AD) CU(cudaLaunchKernelEx(&cfg, k_walk_mixed<TEX, AD>, t->view, (int) n, (int) per_warp, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt, redo, redo_count))
+			if (t->view.ztex) { if (adaptive) GBP_WALK_(true, true); else GBP_WALK_(true, false); }
+			else { if (adaptive) GBP_WALK_(false, true); else GBP_WALK_(false, false); }
+#undef GBP_WALK_
 			if (!getenv("GBP_SKIP_REDO"))
 				k_validate_redo<MapF32U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
 																	   flags, s_new, t_new, t->d_cnt);
 		} else {
-#define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M, false>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt, (int *) nullptr, (unsigned long long *) nullptr))
+#define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt))
 			if (t->view.cell_f32) { if (t->view.uniform) GBP_WALK_(MapF32U); else GBP_WALK_(MapF32N); }
 			else { if (t->view.uniform) GBP_WALK_(MapF64U); else GBP_WALK_(MapF64N); }
 #undef GBP_WALK_
@@ -503,6 +501,8 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 int gbp_pair_outputs_dev(int64_t n, const double *states, const double *actions, double *s_new, void *stream) {
 	if (n < 0 || (n && (!states || !actions || !s_new))) return fail(GBP_E_INVALID, "bad arguments");
 	if (n == 0) return GBP_OK;
+	if ((((uintptr_t) states) | ((uintptr_t) actions) | ((uintptr_t) s_new)) & 15)
+		return fail(GBP_E_INVALID, "states/actions/s_new must be 16-byte aligned (TMA bulk copies)");
 	k_pair_outputs<<<blocks_for(n, 256), 256, 0, (cudaStream_t) stream>>>(n, states, actions, s_new);
 	CU(cudaGetLastError());
 	return GBP_OK;

@@ -588,13 +588,13 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 	const float tbx = (float) (iyc + 1), tby = (float) (ixc + 1);  // texel-footprint centre of the centre cell (exact: < 2^24)
 	int cell[9];
 	float tx[9], ty[9];
-	float ux[9], uy[9], emin = 1.0f;
+	float ux[9], uy[9], emax = 0.0f;  // emax: largest |u - 0.5| over all probes; u within MIXED_EDGE of a grid line <=> emax > 0.5 - MIXED_EDGE
 #pragma unroll
 	for (int p = 0; p < 9; ++p) {
 		const float pxf = fux + ox[p], pyf = fuy + oy[p], flx = floorf(pxf), fly = floorf(pyf);
 		ux[p] = pxf - flx; uy[p] = pyf - fly;
-		emin = fminf(emin, fminf(fminf(ux[p], 1.0f - ux[p]), fminf(uy[p], 1.0f - uy[p])));
-		if (TEX) { tx[p] = ok ? tbx + fly : 1.0f; ty[p] = ok ? tby + flx : 1.0f; }
+		emax = fmaxf(emax, fmaxf(fabsf(ux[p] - 0.5f), fabsf(uy[p] - 0.5f)));
+		if (TEX) { tx[p] = tbx + fly; ty[p] = tby + flx; }  // clamp addressing: a lane that is not `ok` reads some cell and is discarded below
 		else cell[p] = ok ? base + (int) flx * T.ny + (int) fly : 0;
 	}
 	// all 36 cells (36 loads or 9 gathers), then the heights as increments over the first corner
@@ -602,6 +602,11 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 #pragma unroll
 	for (int p = 0; p < 9; ++p) {
 		if (TEX) {
+#ifndef GBP_NO_FLIGHT_SKIP
+			// the 4 leg probes (p = 0, 2, 4, 6) only feed the STANCE reach test (:614-617): a lane checking a FLIGHT sub-state
+			// does not fetch them (no NaN cell and no out-of-grid probe exists on this path, so nothing else depends on them)
+			if (p < 8 && (p & 1) == 0 && phase != GBP_STANCE) { f[p][0] = f[p][1] = f[p][2] = f[p][3] = 0.0f; continue; }
+#endif
 			const float4 g = tex2Dgather<float4>((cudaTextureObject_t) T.ztex, tx[p], ty[p], 0);
 			f[p][0] = g.w; f[p][1] = g.z; f[p][2] = g.x; f[p][3] = g.y;
 		} else {
@@ -628,7 +633,7 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 		bad |= ((m[2 * k + 1] < 0.0) || (stance && m[2 * k] > 0.0)) ? (1u << k) : 0u;
 	}
 	near = near || (fabs(m[8]) < MIXED_MARGIN);
-	if (!ok || near || emin < MIXED_EDGE) return false;
+	if (!ok || near || !(emax <= 0.5f - MIXED_EDGE)) return false;
 	const bool alive0 = !(pitch_bad || speed_bad);
 	const int corners = alive0 ? min(__ffs(bad | 16u), 4) : 0;  // corners the reference evaluates before it returns
 	const bool all_ok = alive0 && bad == 0;

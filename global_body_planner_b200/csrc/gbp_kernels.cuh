@@ -179,8 +179,8 @@ __device__ __forceinline__ void cursor_start(Cursor &q, int dir) {
 }
 // isValidState of the sub-state at the cursor, through the fast validity path (guard-band accuracy;
 // the exact propagation is only used for outputs, see cursor_advance)
-template <typename M, bool MIXED_ONLY = false, bool TEX = false>
-__device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q, bool *undecided = nullptr) {
+template <typename M>
+__device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q) {
 	Pose6 p;
 	double tmp[8];
 	switch (q.phase) {
@@ -191,11 +191,6 @@ __device__ __forceinline__ bool cursor_check(const TerrainView &T, Cursor &q, bo
 	default: apply_flight(q.s, -q.a[7], tmp); p = stance_reverse_fast(tmp, q.a, q.f, q.phase == PH_REV_ST ? q.t : 0.0); break;
 	}
 	const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
-	if (MIXED_ONLY) {
-		bool valid = false;
-		*undecided = !is_valid_state_mixed<M, TEX>(T, p, ph, q.c, valid);
-		return valid;
-	}
 	return is_valid_state_auto<M>(T, p, ph, q.c);
 }
 // How the reference's s_new output is obtained once a pair check has finished.  The (cheap) decision is
@@ -487,18 +482,29 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 				 "l"(src), "r"(bytes), "r"(smem_u32(bar))
 				 : "memory");
 }
+// candidate streams are read exactly once: evict-first in L2, so that they do not displace the height grid
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *dst, const void *src, unsigned bytes, uint64_t *bar, uint64_t policy) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+					 smem_u32(dst)),
+				 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+				 : "memory");
+}
 
-// MIXED_ONLY = true: the walk uses the mixed-precision evaluator alone (fewer registers: 3 CTAs / SM); a
-// candidate that reaches a sub-state the evaluator cannot decide is dropped from this pass — its index goes to
-// the redo list and k_validate_redo walks it again with the fp64 evaluator.
-template <typename M, bool MIXED_ONLY, bool TEX = false>
-__global__ void __launch_bounds__(RF_WARPS * 32, MIXED_ONLY ? 3 : 2) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
+
+// General form (any map kind: fp64 cells, non-uniform axes, NaN cells, small maps), evaluator is_valid_state_auto.
+// fp32 maps on uniform axes without NaN take k_walk_mixed (gbp_walk.cuh) instead.
+template <typename M>
+__global__ void __launch_bounds__(RF_WARPS * 32, 2) k_validate_refill(TerrainView T, int64_t n, int64_t per_warp,
 																   const double *__restrict__ states, const double *__restrict__ actions,
 																   const uint8_t *__restrict__ dir, int adaptive,
 																   uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
 																   double *__restrict__ s_new, double *__restrict__ t_new,
-																   unsigned long long *__restrict__ cnt, int *__restrict__ redo_idx,
-																   unsigned long long *__restrict__ redo_count) {
+																   unsigned long long *__restrict__ cnt) {
 	__shared__ __align__(128) unsigned char ring[RF_WARPS][RF_NBUF][RF_SLOT_BYTES + 112];  // slots padded to 128 B multiples
 	__shared__ __align__(8) uint64_t bars[RF_WARPS][RF_NBUF];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -513,6 +519,12 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MIXED_ONLY ? 3 : 2) k_validate_
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncwarp();
+#ifndef GBP_NO_L2_HINTS
+	const uint64_t pol = l2_evict_first_policy();
+#define GBP_TMA_LOAD(d, s, b, m) tma_load_1d_hint(d, s, b, m, pol)
+#else
+#define GBP_TMA_LOAD(d, s, b, m) tma_load_1d(d, s, b, m)
+#endif
 	auto issue = [&](int c) {  // lane 0 only: chunk c -> ring slot c % RF_NBUF
 		const int slot = c % RF_NBUF;
 		const int64_t c0 = wbase + (int64_t) c * RF_CHUNK;
@@ -521,10 +533,11 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MIXED_ONLY ? 3 : 2) k_validate_
 		const unsigned dbytes = (m == RF_CHUNK) ? RF_CHUNK : 0;  // a partial (tail) chunk reads its directions from global memory
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of this slot precede the async write
 		mbar_expect_tx(&bars[wib][slot], (unsigned) m * (64 + 80) + dbytes);
-		tma_load_1d(dst, states + 8 * c0, (unsigned) m * 64, &bars[wib][slot]);
-		tma_load_1d(dst + RF_CHUNK * 64, actions + 10 * c0, (unsigned) m * 80, &bars[wib][slot]);
-		if (dbytes) tma_load_1d(dst + RF_CHUNK * 144, dir + c0, dbytes, &bars[wib][slot]);
+		GBP_TMA_LOAD(dst, states + 8 * c0, (unsigned) m * 64, &bars[wib][slot]);
+		GBP_TMA_LOAD(dst + RF_CHUNK * 64, actions + 10 * c0, (unsigned) m * 80, &bars[wib][slot]);
+		if (dbytes) GBP_TMA_LOAD(dst + RF_CHUNK * 144, dir + c0, dbytes, &bars[wib][slot]);
 	};
+#undef GBP_TMA_LOAD
 	if (lane == 0) {
 		for (; issued < nchunks && issued < RF_NBUF; ++issued) issue(issued);
 	}
@@ -565,21 +578,23 @@ __global__ void __launch_bounds__(RF_WARPS * 32, MIXED_ONLY ? 3 : 2) k_validate_
 			issued = __shfl_sync(FULL, issued, 0);
 		}
 		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) break;
-		bool valid = true, undecided = false;
-		if (q.phase != PH_IDLE) valid = cursor_check<M, MIXED_ONLY, TEX>(T, q, &undecided);
-		if (MIXED_ONLY && undecided) {  // hand the whole candidate to the fp64 pass
-			redo_idx[atomicAdd(redo_count, 1ull)] = (int) mine;
-			q.phase = PH_IDLE;
-		}
+		bool valid = true;
+		if (q.phase != PH_IDLE) valid = cursor_check<M>(T, q);
 		if (q.phase != PH_IDLE) {
 			OutRecipe out;
 			int r = cursor_advance(q, valid, adaptive != 0, out);
 			if (r) {
 				const bool ok = r == 2;
+#ifndef GBP_NO_L2_HINTS
+				__stcs(verdict + mine, (uint8_t) (ok ? 1 : 0));
+				if (flags) __stcs(flags + mine, (uint8_t) (q.c.flags | (ok ? GBP_FLAG_VALID : 0)));
+				// s_new is finished by k_pair_outputs (convergent, exact); its slot carries the recipe meanwhile
+				if (s_new) __stcs(reinterpret_cast<double2 *>(s_new + 8 * mine), make_double2(out.tau, (double) out.kind));
+#else
 				verdict[mine] = ok ? 1 : 0;
 				if (flags) flags[mine] = (uint8_t) (q.c.flags | (ok ? GBP_FLAG_VALID : 0));
-				// s_new is finished by k_pair_outputs (convergent, exact); its slot carries the recipe meanwhile
 				if (s_new) *reinterpret_cast<double2 *>(s_new + 8 * mine) = make_double2(out.tau, (double) out.kind);
+#endif
 				if (t_new) __stcs(t_new + mine, q.t_new);
 				k += q.c.substates; L += q.c.lookups; np += q.c.nanprobes;
 				oog += (q.c.flags & GBP_FLAG_OOG) ? 1 : 0; near += (q.c.flags & GBP_FLAG_NEAR) ? 1 : 0; nvalid += ok ? 1 : 0;
@@ -631,10 +646,13 @@ __global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int 
 	flush_counters(cnt, k, L, np, oog, near, nvalid);
 }
 
-// Second pass of the refill variant: s_new[i] = finish_output(recipe left in s_new[i][0..1]).  One thread
-// per candidate, no divergence beyond the 4 recipe kinds; streaming stores.  (An in-kernel shared-memory
-// output queue was measured too: it either shrinks the L1 that the terrain gathers live on or stalls on
-// re-reading the inputs — 12.5-22.6 ms against 10.7 ms for this two-pass form.)
+// Second pass of the refill variant: s_new[i] = finish_output(recipe left in s_new[i][0..1]).  One thread per candidate,
+// no divergence beyond the 4 recipe kinds; streaming loads / stores.  Latency-bound on the exact fp64 divisions of
+// applyStance (8 per candidate).  Measured and rejected: staging the rows through shared memory with cp.async.bulk
+// (per-CTA tiles 1.11 ms; persistent CTAs with a 2-stage ring and recipes prefetched one tile ahead 1.27 ms), 128-thread
+// CTAs capped at 64 registers with streaming (ld.cs) input loads (1.35 ms), against 1.05 ms for this form — the
+// block-wide barriers per tile cost more than the row-strided accesses they remove; and an in-kernel shared-memory output queue inside the walk
+// (12.5-22.6 ms against 10.7 ms at the time: it shrinks the L1 the terrain gathers live on).
 __global__ void __launch_bounds__(256) k_pair_outputs(int64_t n, const double *__restrict__ states, const double *__restrict__ actions,
 													   double *__restrict__ s_new) {
 	const int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
