@@ -149,7 +149,9 @@ class Terrain:
     def flags(self):
         u, m = C.c_int(), C.c_int()
         _check(lib().gbp_terrain_flags(self.h, C.byref(u), C.byref(m)))
-        return dict(uniform_axes=bool(u.value), mixed_precision=bool(m.value))
+        g = C.c_int()
+        _check(lib().gbp_terrain_fetch_path(self.h, C.byref(g)))
+        return dict(uniform_axes=bool(u.value), mixed_precision=bool(m.value), texture_gather=bool(g.value))
 
     def axes(self):
         x, y = np.zeros(self.nx), np.zeros(self.ny)

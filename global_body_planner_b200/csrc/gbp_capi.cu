@@ -302,6 +302,11 @@ int gbp_terrain_flags(const gbp_terrain *t, int *uniform_axes, int *mixed_precis
 	if (mixed_precision) *mixed_precision = t->view.mixed_ok;
 	return GBP_OK;
 }
+int gbp_terrain_fetch_path(const gbp_terrain *t, int *texture_gather) {
+	if (!t) return fail(GBP_E_INVALID, "terrain is NULL");
+	if (texture_gather) *texture_gather = t->view.ztex ? 1 : 0;
+	return GBP_OK;
+}
 int gbp_terrain_axes(const gbp_terrain *t, double *x, double *y) {
 	if (!t) return fail(GBP_E_INVALID, "terrain is NULL");
 	if (x) memcpy(x, t->hx.data(), t->hx.size() * sizeof(double));
@@ -429,7 +434,6 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 	if (zero_counters) CU(cudaMemsetAsync(t->d_cnt, 0, 6 * sizeof(unsigned long long), st));
 	if (n == 0) return GBP_OK;
 	if (variant == 0) variant = 3;
-	const bool f32 = t->view.cell_f32 != 0;
 	if (variant == 1) {
 		GBP_DISPATCH(t->view, k_validate_thread, (blocks_for(n, 128), 128), st, t->view, n, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
 	} else if (variant == 2) {

@@ -79,6 +79,10 @@ int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes);
 /* which evaluator serves this terrain: uniform_axes = cell edges are computed, not loaded; mixed_precision = the
  * fp32-around-fp64 evaluator applies (fp32 cells, no NaN, uniform axes, pitch >= 1 cm, interior >> border) */
 int gbp_terrain_flags(const gbp_terrain *t, int *uniform_axes, int *mixed_precision);
+/* texture_gather = 1 when the mixed-precision walk fetches each probe's 2x2 cells with one texture gather from a
+ * block-linear copy of the height grid (the default for such terrains; GBP_NO_TEX=1 in the environment at creation
+ * time keeps the 4-load form, results are identical) */
+int gbp_terrain_fetch_path(const gbp_terrain *t, int *texture_gather);
 /* FastTerrainMap::getXData / getYData (fast_terrain_map.cpp:216-223) */
 int gbp_terrain_axes(const gbp_terrain *t, double *x, double *y);
 /* getGroundHeight (:94-132), heightIsNan (:135-157), getSurfaceNormal (:160-213, not renormalised) */

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import pyoracle as po  # noqa: E402  (test infrastructure)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-TERRAINS = ("rough_terrain", "slope", "synth_nan")
+TERRAINS = ("rough_terrain", "slope", "synth_nan", "synth_mixed")
 
 
 def pytest_configure(config):

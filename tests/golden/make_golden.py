@@ -34,6 +34,19 @@ def synth_nan_terrain():
     return po.Terrain(ax, ax.copy(), z, dx, dy, dz)
 
 
+def synth_mixed_terrain():
+    """384x384 @ 0.05 m, rolling ground + seeded fp32 noise, no NaN, uniform axes: the terrain class served by the
+    mixed-precision walk kernel (k_walk_mixed + fp64 redo pass) and its texture-gather fetch path."""
+    rng = np.random.default_rng(17)
+    n, pitch = 384, 0.05
+    ax = np.arange(n) * pitch - 2.0
+    z = 0.06 * np.sin(0.9 * ax)[:, None] * np.cos(0.6 * ax)[None, :] + rng.normal(0, 0.008, (n, n))
+    z = z.astype(np.float32).astype(np.float64)
+    dz = np.ones_like(z)
+    dx = rng.normal(0, 0.05, (n, n)); dy = rng.normal(0, 0.05, (n, n))
+    return po.Terrain(ax, ax.copy(), z, dx, dy, dz)
+
+
 def mint(name, T, seed):
     o, r = po.Oracle(T), po.Ref(T)
     out = {}
@@ -53,7 +66,7 @@ def mint(name, T, seed):
     big = o.sample_states(seed, 5, 0, 40000)
     v, _ = o.valid_states(big, po.STANCE)
     s = big[v == 1][:N_PAIRS]
-    normal = r.surface_normal(s[:1, 0], s[:1, 1])[0] if name != "synth_nan" else np.array([0.03, -0.02, 0.99])
+    normal = r.surface_normal(s[:1, 0], s[:1, 1])[0] if not name.startswith("synth") else np.array([0.03, -0.02, 0.99])
     a = o.sample_actions(seed, 9, 0, len(s), normal)
     a[: len(s) // 8, 7] = 0.0  # some pure-stance primitives
     g0 = 2 * len(s) // 3       # last third: gentle primitives so that the fully-valid branch is well covered
@@ -117,3 +130,8 @@ if __name__ == "__main__":
                         dx=T.dx.astype(np.float32), dy=T.dy.astype(np.float32), dz=T.dz.astype(np.float32))
     T = po.Terrain.from_npz(os.path.join(HERE, "terrain_synth_nan.npz"))  # exactly what the tests will load
     mint("synth_nan", T, seed=13)
+    T = synth_mixed_terrain()
+    np.savez_compressed(os.path.join(HERE, "terrain_synth_mixed.npz"), x=T.x, y=T.y, z=T.z.astype(np.float32),
+                        dx=T.dx.astype(np.float32), dy=T.dy.astype(np.float32), dz=T.dz.astype(np.float32))
+    T = po.Terrain.from_npz(os.path.join(HERE, "terrain_synth_mixed.npz"))
+    mint("synth_mixed", T, seed=14)

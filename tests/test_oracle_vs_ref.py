@@ -10,7 +10,7 @@ from conftest import assert_bits_equal, load_terrain
 pytestmark = pytest.mark.skipif(not po.Ref.available(), reason="oracle/_ref not built (no /root/reference)")
 
 
-@pytest.fixture(scope="module", params=["rough_terrain", "slope", "synth_nan"])
+@pytest.fixture(scope="module", params=["rough_terrain", "slope", "synth_nan", "synth_mixed"])
 def pair(request):
     T = load_terrain(request.param)
     return po.Oracle(T), po.Ref(T), T
