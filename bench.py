@@ -354,7 +354,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_validate_refill): algorithmic bytes / launch duration
+    # ---- roofline of the dominant kernel (k_walk_mixed): algorithmic bytes / launch duration
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -366,13 +366,14 @@ def main():
     alg_bytes = n * B_IO + 4 * cell_bytes * (L_tot + k_tot)
     launch_ms = float(np.mean(per_launch_ms))
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_validate_refill<MapF32U>" if args.variant in (0, 3) else f"variant {args.variant}",
+    fetch = "TEX" if t.flags().get("texture_gather") else "LDG"
+    roofline = {"bound": "hbm", "kernel": f"k_walk_mixed<{fetch}>" if args.variant in (0, 3) else f"variant {args.variant}",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                 "bytes_per_candidate": alg_bytes / n, "k_mean": k_tot / n, "L_mean": L_tot / n,
                 "step_ms": float(np.mean(per_step_ms)), "kernels_per_step": kernels_per_step,
-                "note": "latency/issue-bound terrain-gather pipeline, not HBM-bound (DESIGN.md section 5); launch_ms = walk + redo kernels (variant 5), step_ms adds k_pair_outputs"}
+                "note": "issue / texture-gather-bound pipeline, not HBM-bound (DESIGN.md section 5: 58 % issue slots, 48 % texture data pipe); launch_ms = walk + redo kernels (variant 5), step_ms adds k_pair_outputs"}
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         roofline["traffic"] = prof.get("dram_bytes_per_launch")

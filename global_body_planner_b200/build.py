@@ -29,18 +29,25 @@ def build(force=False, verbose=False):
 
 
 HOST_SO = os.path.join(HERE, "libglobal_body_planner_b200.so")
-HOST_SOURCES = [os.path.join(HERE, "host", f) for f in ("dropin.cpp", "planners.cpp")]
+HOST_SOURCES = [os.path.join(HERE, "host", f) for f in ("dropin.cpp", "planners.cpp", "global_body_planner.cpp")]
+CLI = os.path.join(HERE, "gbp_plan")
+CLI_SOURCE = os.path.join(HERE, "host", "gbp_plan_main.cpp")
 INCLUDE = os.path.join(HERE, "..", "include")
 
 
 def build_host(force=False):
     """The drop-in C++ classes (include/global_body_planner/*.h) over the C ABI."""
     hdrs = [os.path.join(INCLUDE, "global_body_planner", f) for f in os.listdir(os.path.join(INCLUDE, "global_body_planner"))]
-    if not force and os.path.exists(HOST_SO) and all(os.path.getmtime(f) <= os.path.getmtime(HOST_SO) for f in HOST_SOURCES + hdrs + [SO]):
+    if not force and os.path.exists(HOST_SO) and os.path.exists(CLI) and \
+            all(os.path.getmtime(f) <= min(os.path.getmtime(HOST_SO), os.path.getmtime(CLI)) for f in HOST_SOURCES + hdrs + [SO, CLI_SOURCE]):
         return HOST_SO
-    cmd = [os.environ.get("CXX", "g++"), "-std=c++14", "-O2", "-fPIC", "-shared", "-Wall", "-I" + INCLUDE, "-o", HOST_SO] + HOST_SOURCES + \
+    cxx = os.environ.get("CXX", "g++")
+    cmd = [cxx, "-std=c++14", "-O2", "-fPIC", "-shared", "-Wall", "-I" + INCLUDE, "-o", HOST_SO] + HOST_SOURCES + \
           ["-L" + HERE, "-lgbp_b200", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True)
+    # gbp_plan: the ROS-free callPlanner driver as a command-line tool
+    subprocess.run([cxx, "-std=c++14", "-O2", "-Wall", "-I" + INCLUDE, "-o", CLI, CLI_SOURCE, "-L" + HERE, "-lglobal_body_planner_b200",
+                    "-lgbp_b200", "-Wl,-rpath,$ORIGIN"], check=True)
     return HOST_SO
 
 

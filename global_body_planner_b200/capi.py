@@ -101,6 +101,27 @@ def distance(kind, q1, q2):
     return out
 
 
+def interp_path(states, actions, dt=0.05, cap=None):
+    """getInterpPath (planning_utils.cpp:175-192) -> interpolated states [m, 8], times [m], phases [m - 1]."""
+    s, a = _f64(states, (-1, 8)), _f64(actions, (-1, 10))
+    if len(s) != len(a) + 1:
+        raise GbpError("interp_path needs len(states) == len(actions) + 1")
+    if cap is None:
+        cap = int(sum(np.ceil(max(x, 0.0) / dt) + 2 for x in np.concatenate([a[:, 6], a[:, 7]]))) + 2
+    os_, ot, op = np.zeros((cap, 8)), np.zeros(cap), np.zeros(cap, np.int32)
+    m = C.c_int64()
+    _check(lib().gbp_interp_path(len(a), _p(s), _p(a), C.c_double(dt), C.c_int64(cap), _p(os_), _p(ot), _p(op), C.byref(m)))
+    n = min(m.value, cap)
+    return os_[:n].copy(), ot[:n].copy(), op[:max(n - 1, 0)].copy()
+
+
+def max_curvature(states):
+    """calculateMaxCurvature (planning_utils.cpp:900-909)."""
+    s = _f64(states, (-1, 8)); out = C.c_double()
+    _check(lib().gbp_max_curvature(C.c_int64(len(s)), _p(s), C.byref(out)))
+    return out.value
+
+
 def sample_actions(seed, stream, idx0, n, normal=(0.0, 0.0, 1.0), s_from=None, s_to=None, thresh=0.0):
     """getRandomAction / getRandomActionDirection on the Philox stream."""
     a = np.zeros((n, 10)); nrm = _f64(normal)
@@ -131,6 +152,18 @@ class Terrain:
         _check(lib().gbp_terrain_create_gridmap(nx, ny, C.c_double(res), C.c_double(cx), C.c_double(cy), _p(e), _p(a), _p(b),
                                                 _p(c), C.byref(h)))
         self.h, self.nx, self.ny = h, nx, ny
+        return self
+
+    @classmethod
+    def from_csv(cls, directory, via_gridmap=False):
+        """<directory>/{x,y,z,dx,dy,dz}data.csv in the reference's format (terrain_map_publisher.cpp:289-370)."""
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _check(lib().gbp_terrain_create_csv(os.fsencode(directory), int(bool(via_gridmap)), C.byref(h)))
+        self.h = h
+        a, b = C.c_int(), C.c_int()
+        _check(lib().gbp_terrain_dims(h, C.byref(a), C.byref(b), None))
+        self.nx, self.ny = a.value, b.value
         return self
 
     def close(self):

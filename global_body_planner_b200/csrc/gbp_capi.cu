@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -278,6 +280,64 @@ int gbp_terrain_create_gridmap(int nx, int ny, double res, double cx, double cy,
 							  normals ? c.data() : nullptr, out);
 }
 
+// TerrainMapPublisher::loadCSV (terrain_map_publisher.cpp:289-327): '#' lines skipped, fields split on ',', std::stod
+static bool load_csv(const std::string &path, std::vector<std::vector<double>> &data, std::string &err) {
+	std::ifstream in(path);
+	if (!in) { err = "cannot open " + path; return false; }
+	std::string line;
+	while (std::getline(in, line)) {
+		if (!line.empty() && line[0] == '#') continue;
+		std::vector<double> rec;
+		std::istringstream ss(line);
+		std::string num;
+		while (std::getline(ss, num, ',')) {
+			try { rec.push_back(std::stod(num)); } catch (const std::exception &) { /* the reference drops unparsable fields */ }
+		}
+		data.push_back(rec);
+	}
+	while (!data.empty() && data.back().empty()) data.pop_back();  // trailing blank lines
+	return true;
+}
+
+int gbp_terrain_create_csv(const char *directory, int via_gridmap, gbp_terrain **out) {
+	if (!out) return fail(GBP_E_INVALID, "out is NULL");
+	*out = nullptr;
+	if (!directory) return fail(GBP_E_INVALID, "directory is NULL");
+	const char *names[6] = {"x", "y", "z", "dx", "dy", "dz"};
+	std::vector<std::vector<double>> L[6];
+	std::string err;
+	for (int k = 0; k < 6; ++k)
+		if (!load_csv(std::string(directory) + "/" + names[k] + "data.csv", L[k], err)) return fail(GBP_E_INVALID, err);
+	const size_t ny = L[2].size(), nx = ny ? L[2][0].size() : 0;  // rows = y, columns = x (:343-344)
+	if (nx < 2 || ny < 2) return fail(GBP_E_INVALID, "zdata.csv needs at least 2 x 2 values");
+	for (int k = 0; k < 6; ++k) {
+		if (L[k].size() != ny) return fail(GBP_E_INVALID, std::string(names[k]) + "data.csv: row count differs from zdata.csv");
+		for (const auto &row : L[k]) if (row.size() != nx) return fail(GBP_E_INVALID, std::string(names[k]) + "data.csv: ragged rows");
+	}
+	if (!via_gridmap) {
+		std::vector<double> x(nx), y(ny), lay[4];
+		for (size_t i = 0; i < nx; ++i) x[i] = L[0][0][i];
+		for (size_t j = 0; j < ny; ++j) y[j] = L[1][j][0];
+		for (int k = 0; k < 4; ++k) {
+			lay[k].resize(nx * ny);
+			for (size_t i = 0; i < nx; ++i) for (size_t j = 0; j < ny; ++j) lay[k][i * ny + j] = L[2 + k][j][i];
+		}
+		return gbp_terrain_create((int) nx, (int) ny, x.data(), y.data(), lay[0].data(), lay[1].data(), lay[2].data(), lay[3].data(), out);
+	}
+	// the ROS path (:345-369): float resolution, map centred so that cell centres sit on the data points, float layers
+	const float x_res = (float) (L[0][0][1] - L[0][0][0]), y_res = (float) (L[1][1][0] - L[1][0][0]);
+	if (x_res != y_res) return fail(GBP_E_INVALID, "Map did not have square elements, make sure x and y resolution are equal.");
+	const double x_length = L[0][0].back() - L[0][0].front() + x_res, y_length = L[1].back()[0] - L[1].front()[0] + y_res;
+	const double cx = L[0][0].front() - 0.5 * x_res + 0.5 * x_length, cy = L[1].front()[0] - 0.5 * y_res + 0.5 * y_length;
+	std::vector<float> lay[4];
+	for (int k = 0; k < 4; ++k) {
+		lay[k].resize(nx * ny);
+		for (size_t i = 0; i < nx; ++i)
+			for (size_t j = 0; j < ny; ++j) lay[k][i * ny + j] = (float) L[2 + k][(ny - 1) - j][(nx - 1) - i];  // grid_map index (i, j), :363-367
+	}
+	return gbp_terrain_create_gridmap((int) nx, (int) ny, (double) x_res, cx, cy, lay[0].data(), lay[1].data(), lay[2].data(), lay[3].data(), out);
+}
+
 void gbp_terrain_destroy(gbp_terrain *t) {
 	if (!t) return;
 	if (t->z_tex) cudaDestroyTextureObject(t->z_tex);
@@ -411,6 +471,65 @@ int gbp_distance(int kind, int64_t n, const double *q1, const double *q2, double
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(out, o.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+
+// ---------------------------------------------------------------------------------- plan output
+int gbp_interp_path(int n_actions, const double *states, const double *actions, double dt, int64_t cap, double *interp_states,
+					double *interp_t, int *interp_phase, int64_t *count) {
+	if (n_actions < 0 || !states || (n_actions && !actions) || !(dt > 0) || cap < 0 || !count || (cap && (!interp_states || !interp_t || !interp_phase)))
+		return fail(GBP_E_INVALID, "bad arguments (dt must be positive)");
+	// the sample grid, exactly as the reference's loops lay it out (planning_utils.cpp:142-193)
+	std::vector<int> prim;
+	std::vector<uint8_t> kind;
+	std::vector<double> tloc, tabs;
+	std::vector<int> phase;
+	double t0 = 0;
+	for (int i = 0; i < n_actions; ++i) {
+		const double t_s = actions[10 * (size_t) i + 6], t_f = actions[10 * (size_t) i + 7];
+		if (!(t_s < 1e6) || !(t_f < 1e6)) return fail(GBP_E_INVALID, "primitive duration out of range");
+		for (double t = 0; t < t_s; t += dt) { prim.push_back(i); kind.push_back(0); tloc.push_back(t); tabs.push_back(t + t0); phase.push_back(t_f == 0 ? 2 : GBP_STANCE); }
+		for (double t = 0; t < t_f; t += dt) { prim.push_back(i); kind.push_back(1); tloc.push_back(t); tabs.push_back(t_s + t + t0); phase.push_back(GBP_FLIGHT); }
+		if (t_f > 0) { prim.push_back(i); kind.push_back(1); tloc.push_back(t_f); tabs.push_back(t0 + t_s + t_f); phase.push_back(GBP_STANCE); }
+		t0 += (t_s + t_f);
+	}
+	prim.push_back(n_actions); kind.push_back(2); tloc.push_back(0.0); tabs.push_back(t0);
+	const int64_t m = (int64_t) prim.size();
+	*count = m;
+	const int64_t w = m < cap ? m : cap;
+	if (w == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev dp(st), dk(st), dt_(st), ds(st), da(st), dout(st);
+	int rc;
+	if ((rc = upload(dp, prim.data(), (size_t) w, st)) || (rc = upload(dk, kind.data(), (size_t) w, st)) || (rc = upload(dt_, tloc.data(), (size_t) w, st)) ||
+		(rc = upload(ds, states, 8 * ((size_t) n_actions + 1), st)) || (rc = upload(da, actions, 10 * (size_t) n_actions, st)))
+		return rc;
+	CU(dout.alloc((size_t) w * 8 * sizeof(double)));
+	k_interp_samples<<<blocks_for(w, 128), 128, 0, st>>>(w, dp.as<int>(), dk.as<uint8_t>(), dt_.as<double>(), ds.as<double>(), da.as<double>(), dout.as<double>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(interp_states, dout.p, (size_t) w * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	memcpy(interp_t, tabs.data(), (size_t) w * sizeof(double));
+	const int64_t np = (int64_t) phase.size() < w ? (int64_t) phase.size() : w;
+	if (np) memcpy(interp_phase, phase.data(), (size_t) np * sizeof(int));
+	return GBP_OK;
+}
+int gbp_max_curvature(int64_t n, const double *states, double *max_curvature) {
+	if (n < 0 || (n && !states) || !max_curvature) return fail(GBP_E_INVALID, "bad arguments");
+	*max_curvature = 0.0;
+	if (n < 3) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev ds(st), dm(st);
+	int rc;
+	if ((rc = upload(ds, states, 8 * (size_t) n, st))) return rc;
+	CU(dm.alloc(sizeof(unsigned long long)));
+	CU(cudaMemsetAsync(dm.p, 0, sizeof(unsigned long long), st));
+	k_max_curvature<<<blocks_for(n - 2, 128), 128, 0, st>>>(n, ds.as<double>(), dm.as<unsigned long long>());
+	CU(cudaGetLastError());
+	unsigned long long bits = 0;
+	CU(cudaMemcpyAsync(&bits, dm.p, sizeof bits, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	memcpy(max_curvature, &bits, sizeof bits);
 	return GBP_OK;
 }
 

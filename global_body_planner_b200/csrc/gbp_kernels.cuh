@@ -667,6 +667,52 @@ __global__ void __launch_bounds__(256) k_pair_outputs(int64_t n, const double *_
 	for (int d = 0; d < 4; ++d) __stcs(o + d, make_double2(sn[2 * d], sn[2 * d + 1]));
 }
 
+// ------------------------------------------------------------------ plan output
+// getInterpPath / interpStateActionPair (planning_utils.cpp:142-193).  The sample grid (which primitive, which phase,
+// local time: the reference's fp64-accumulated t += dt loops) is laid out by the host; one thread per sample evaluates
+// the state with the exact primitives.  kind 0: applyStance(s, a, t); 1: applyFlight(applyStance(s, a), t) (the
+// landing sample is kind 1 at t = t_f); 2: the state itself (the closing sample of the path).
+__global__ void k_interp_samples(int64_t m, const int *__restrict__ prim, const uint8_t *__restrict__ kind, const double *__restrict__ tloc,
+								 const double *__restrict__ states, const double *__restrict__ actions, double *__restrict__ out) {
+	const int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	double s[8], a[10], o[8], tmp[8];
+	const int p = prim[i], k = kind[i];
+#pragma unroll
+	for (int d = 0; d < 8; ++d) s[d] = states[8 * (size_t) p + d];
+	if (k != 2) {
+#pragma unroll
+		for (int d = 0; d < 10; ++d) a[d] = actions[10 * (size_t) p + d];
+	}
+	if (k == 0) apply_stance(s, a, tloc[i], o);
+	else if (k == 1) { apply_stance(s, a, a[6], tmp); apply_flight(tmp, tloc[i], o); }
+	else {
+#pragma unroll
+		for (int d = 0; d < 8; ++d) o[d] = s[d];
+	}
+	store_state(out + 8 * i, o);
+}
+// calculateMaxCurvature (planning_utils.cpp:884-909): three-point curvature of consecutive plan states, maximum over the
+// plan.  std::max(max, c) never takes a NaN c, curvatures are >= 0: the maximum is an atomicMax on the fp64 bit pattern.
+__global__ void k_max_curvature(int64_t n, const double *__restrict__ states, unsigned long long *__restrict__ max_bits) {
+	const int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i + 2 >= n) return;
+	const double x1 = states[8 * i], y1 = states[8 * i + 1], x2 = states[8 * (i + 1)], y2 = states[8 * (i + 1) + 1],
+				 x3 = states[8 * (i + 2)], y3 = states[8 * (i + 2) + 1];
+	double c = 0.0;
+	if (!((x1 == x2 && x2 == x3) || (y1 == y2 && y2 == y3))) {
+		const double dis12 = sqrt((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
+		const double dis13 = sqrt((x1 - x3) * (x1 - x3) + (y1 - y3) * (y1 - y3));
+		const double dis23 = sqrt((x2 - x3) * (x2 - x3) + (y2 - y3) * (y2 - y3));
+		const double dis = dis12 * dis12 + dis23 * dis23 - dis13 * dis13;
+		const double cosA = dis / (2 * dis12 * dis23);
+		const double sinA = sqrt(1 - cosA * cosA);
+		c = 0.5 * dis13 / sinA;
+		c = 1 / c;
+	}
+	if (c > 0.0) atomicMax(max_bits, (unsigned long long) __double_as_longlong(c));
+}
+
 // ------------------------------------------------------------------ samplers
 __global__ void k_sample_actions(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, double n0, double n1, double n2,
 								 int dir_flag, double dir_thresh, const double *__restrict__ s_from, const double *__restrict__ s_to,

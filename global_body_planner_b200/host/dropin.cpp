@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <iomanip>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -36,6 +37,16 @@ void FastTerrainMap::loadData(int x_size, int y_size, std::vector<double> x_data
 	dev_.reset(t, gbp_terrain_destroy);
 	x_data_.assign(x_data.begin(), x_data.begin() + x_size);
 	y_data_.assign(y_data.begin(), y_data.begin() + y_size);
+}
+void FastTerrainMap::loadDataFromCSV(const std::string &directory, bool via_gridmap) {
+	gbp_terrain *t = nullptr;
+	check(gbp_terrain_create_csv(directory.c_str(), via_gridmap ? 1 : 0, &t), "FastTerrainMap::loadDataFromCSV");
+	dev_.reset(t, gbp_terrain_destroy);
+	int nx = 0, ny = 0;
+	check(gbp_terrain_dims(t, &nx, &ny, nullptr), "FastTerrainMap::loadDataFromCSV");
+	x_data_.resize(nx);
+	y_data_.resize(ny);
+	check(gbp_terrain_axes(t, x_data_.data(), y_data_.data()), "FastTerrainMap::loadDataFromCSV");
 }
 const gbp_terrain *FastTerrainMap::handle() const {
 	if (!dev_) throw std::runtime_error("FastTerrainMap: no terrain loaded");
@@ -182,47 +193,85 @@ std::vector<unsigned char> isValidStateActionPair(const std::vector<State> &s, c
 	return v;
 }
 
-// Output interpolation (planning_utils.cpp:142-193).  The sample-time grid is built on the host exactly as the
-// reference's loops do (t += dt); the states on it are propagated in one batched launch per primitive phase.
+// Output interpolation (planning_utils.cpp:142-193): the sample grid is laid out exactly as the reference's loops do
+// (t += dt) and every state on it is evaluated in one launch (gbp_interp_path).
+namespace {
+void interp_append(const State *states, const Action *actions, int n_actions, bool closing_state, double t0, double dt,
+				   std::vector<State> &interp_path, std::vector<double> &interp_t, std::vector<int> &interp_phase) {
+	std::int64_t count = 0;
+	std::vector<State> out(1);
+	std::vector<double> tt(1);
+	std::vector<int> ph(1);
+	check(gbp_interp_path(n_actions, states[0].data(), n_actions ? actions[0].data() : nullptr, dt, 0, nullptr, nullptr, nullptr, &count), "getInterpPath");
+	out.resize((size_t) count); tt.resize((size_t) count); ph.resize((size_t) count);
+	check(gbp_interp_path(n_actions, states[0].data(), n_actions ? actions[0].data() : nullptr, dt, count, out[0].data(), tt.data(), ph.data(), &count),
+		  "getInterpPath");
+	const size_t keep = closing_state ? (size_t) count : (size_t) count - 1;  // a single pair has no closing sample
+	for (size_t i = 0; i < keep; ++i) { interp_path.push_back(out[i]); interp_t.push_back(tt[i] + t0); }
+	for (size_t i = 0; i + 1 < (size_t) count; ++i) interp_phase.push_back(ph[i]);
+}
+}  // namespace
 void interpStateActionPair(State s, Action a, double t0, double dt, std::vector<State> &interp_path, std::vector<double> &interp_t,
 						   std::vector<int> &interp_phase) {
+	State two[2] = {s, s};
+	// t0 is added on the host AFTER the device call, which would round differently from the reference's `t + t0`;
+	// with a non-zero t0 the times are therefore rebuilt with the reference's own expressions below
+	const size_t first = interp_t.size();
+	interp_append(two, &a, 1, false, 0.0, dt, interp_path, interp_t, interp_phase);
 	const double t_s = a[6], t_f = a[7];
-	std::vector<double> ts;
-	for (double t = 0; t < t_s; t += dt) ts.push_back(t);
-	if (!ts.empty()) {
-		std::vector<State> ss(ts.size(), s), out(ts.size());
-		std::vector<Action> aa(ts.size(), a);
-		check(gbp_propagate(0, (int64_t) ts.size(), ss[0].data(), aa[0].data(), ts.data(), out[0].data()), "interp stance");
-		for (size_t i = 0; i < ts.size(); ++i) {
-			interp_t.push_back(ts[i] + t0);
-			interp_path.push_back(out[i]);
-			interp_phase.push_back(t_f == 0 ? CONNECT_STANCE : STANCE);
-		}
-	}
-	State s_takeoff = applyStance(s, a);
-	std::vector<double> tf;
-	for (double t = 0; t < t_f; t += dt) tf.push_back(t);
-	if (t_f > 0) tf.push_back(t_f);  // the exact landing state (:170-174)
-	if (!tf.empty()) {
-		std::vector<State> ss(tf.size(), s_takeoff), out(tf.size());
-		check(gbp_propagate(1, (int64_t) tf.size(), ss[0].data(), nullptr, tf.data(), out[0].data()), "interp flight");
-		for (size_t i = 0; i < tf.size(); ++i) {
-			const bool landing = t_f > 0 && i + 1 == tf.size();
-			interp_t.push_back(landing ? t0 + t_s + t_f : t_s + tf[i] + t0);
-			interp_path.push_back(out[i]);
-			interp_phase.push_back(landing ? STANCE : FLIGHT);
-		}
-	}
+	size_t k = first;
+	for (double t = 0; t < t_s; t += dt) interp_t[k++] = t + t0;
+	for (double t = 0; t < t_f; t += dt) interp_t[k++] = t_s + t + t0;
+	if (t_f > 0) interp_t[k++] = t0 + t_s + t_f;
 }
 void getInterpPath(std::vector<State> state_sequence, std::vector<Action> action_sequence, double dt, std::vector<State> &interp_path,
 				   std::vector<double> &interp_t, std::vector<int> &interp_phase) {
-	double t0 = 0;
-	for (size_t i = 0; i < action_sequence.size(); ++i) {
-		interpStateActionPair(state_sequence[i], action_sequence[i], t0, dt, interp_path, interp_t, interp_phase);
-		t0 += action_sequence[i][6] + action_sequence[i][7];
+	if (state_sequence.empty()) return;
+	if (state_sequence.size() != action_sequence.size() + 1) throw std::runtime_error("getInterpPath: need one more state than actions");
+	interp_append(state_sequence.data(), action_sequence.data(), (int) action_sequence.size(), true, 0.0, dt, interp_path, interp_t, interp_phase);
+}
+
+double calculateMaxCurvature(std::vector<State> &body_plan) {  // :900-909
+	double c = 0;
+	check(gbp_max_curvature((std::int64_t) body_plan.size(), body_plan.empty() ? nullptr : body_plan[0].data(), &c), "calculateMaxCurvature");
+	return c;
+}
+
+// ---- printing: same text as the reference emits (:16-104)
+void printState(State vec) {
+	std::cout << "{";
+	for (size_t i = 0; i < vec.size(); i++) std::cout << vec[i] << ", ";
+	std::cout << "\b\b}";
+}
+void printStateNewline(State vec) { printState(vec); std::cout << std::endl; }
+void printAction(Action a) {
+	std::cout << "{";
+	for (size_t i = 0; i < a.size(); i++) std::cout << a[i] << ", ";
+	std::cout << "\b\b}";
+}
+void printActionNewline(Action a) { printAction(a); std::cout << std::endl; }
+void printStateSequence(std::vector<State> state_sequence) { for (const State &s : state_sequence) printStateNewline(s); }
+void printActionSequence(std::vector<Action> action_sequence) { for (const Action &a : action_sequence) printActionNewline(a); }
+static void printStateXYZPYaw(const State &s) {
+	std::cout << "x: " << std::setw(7) << std::setprecision(3) << s[0] << " | y: " << std::setw(7) << std::setprecision(3) << s[1]
+			  << " | z: " << std::setw(7) << std::setprecision(3) << s[2] << " | p: " << std::setw(7) << std::setprecision(4) << s[6]
+			  << " | yaw: " << std::setw(6) << std::setprecision(3) << std::atan2(s[4], s[3]) << " |" << std::endl;
+}
+void printStateSequenceXYZPYaw(const std::vector<State> &state_sequence) {
+	std::cout << "---------- discrete state sequence ----------" << std::endl;
+	if (state_sequence.empty()) return;
+	double path_length = 0, path_yaw = 0;
+	for (size_t i = 0; i + 1 < state_sequence.size(); ++i) {
+		printStateXYZPYaw(state_sequence[i]);
+		const double dl = poseDistance(state_sequence[i], state_sequence[i + 1]), dy = stateYawDistance(state_sequence[i], state_sequence[i + 1]);
+		std::cout << "           |            |            |            |            "
+				  << " | length: " << std::setw(6) << std::setprecision(3) << dl << " | yaw: " << std::setw(6) << std::setprecision(3) << dy << std::endl;
+		path_length += dl;
+		path_yaw += dy;
 	}
-	interp_t.push_back(t0);
-	interp_path.push_back(state_sequence.back());
+	printStateXYZPYaw(state_sequence.back());
+	std::cout << "path length: " << std::setw(6) << std::setprecision(3) << path_length << std::endl;
+	std::cout << "path yaw:    " << std::setw(6) << std::setprecision(3) << path_yaw << std::endl;
 }
 
 }  // namespace planning_utils

@@ -74,6 +74,12 @@ int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const d
 int gbp_terrain_create_gridmap(int nx, int ny, double resolution, double centre_x, double centre_y,
                                const float *elevation, const float *dx, const float *dy, const float *dz,
                                gbp_terrain **out);
+/* The reference's on-disk terrain format: <directory>/{x,y,z,dx,dy,dz}data.csv, rows = y, columns = x, '#' comment
+ * lines skipped (TerrainMapPublisher::loadCSV / loadMapFromCSV, terrain_map_publisher.cpp:289-370).
+ * via_gridmap = 0: the values go to FastTerrainMap::loadData as fp64 (x = first row of xdata, y = first column of
+ * ydata) — what the oracle harness does.  via_gridmap = 1: the ROS path — layers and the resolution are rounded to
+ * float and indexed like the GridMap the publisher fills (:345-369), then FastTerrainMap::loadDataFromGridMap. */
+int gbp_terrain_create_csv(const char *directory, int via_gridmap, gbp_terrain **out);
 void gbp_terrain_destroy(gbp_terrain *t);
 int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes);
 /* which evaluator serves this terrain: uniform_axes = cell edges are computed, not loaded; mixed_precision = the
@@ -126,6 +132,18 @@ int gbp_pair_outputs_dev(int64_t n, const double *states, const double *actions,
  * over candidates under the REFERENCE's early-exit semantics: {sub-states k, getGroundHeight calls L,
  * heightIsNan calls, candidates flagged OOG, candidates flagged NEAR, valid}.  Synchronises. */
 int gbp_validate_counters(const gbp_terrain *t, int64_t counters6[6]);
+
+/* ---------------------------------------------------------------------------------- plan output */
+/* getInterpPath / interpStateActionPair (planning_utils.cpp:142-193): n_actions primitives, n_actions + 1 states.
+ * Per primitive: stance samples for (t = 0; t < t_s; t += dt) (phase 1 STANCE, or 2 CONNECT_STANCE when t_f == 0),
+ * flight samples for (t = 0; t < t_f; t += dt) (phase 0 FLIGHT) from the exact take-off state, the exact landing
+ * state when t_f > 0 (phase 1), and after the last primitive the final state of the sequence.  *count receives the
+ * number of interpolated states (it may exceed cap: only cap entries are written then).  As in the reference the
+ * closing state has no phase entry: interp_phase holds *count - 1 values. */
+int gbp_interp_path(int n_actions, const double *states, const double *actions, double dt, int64_t cap,
+                    double *interp_states, double *interp_t, int *interp_phase, int64_t *count);
+/* calculateMaxCurvature (planning_utils.cpp:884-909) over n plan states */
+int gbp_max_curvature(int64_t n, const double *states, double *max_curvature);
 
 /* ------------------------------------------------------------------------------------ samplers */
 /* Philox4x32-10 stream spec (shared with the CPU harness, oracle/gbp_oracle.c):

@@ -31,6 +31,10 @@ public:
 	// reference: fast_terrain_map.cpp:31-91 (index flip, float layers "elevation", "dx", "dy", "dz")
 	void loadDataFromGridMap(grid_map::GridMap map);
 #endif
+	// B200 addition: the reference's CSV terrain directory (data/<name>/{x,y,z,dx,dy,dz}data.csv, rows = y, columns = x,
+	// TerrainMapPublisher::loadMapFromCSV, terrain_map_publisher.cpp:330-370).  via_gridmap = false: fp64 values through
+	// loadData; true: float layers / float resolution through the GridMap index flip, as the ROS pipeline delivers them.
+	void loadDataFromCSV(const std::string &directory, bool via_gridmap = false);
 	double getGroundHeight(const double x, const double y);              // :94-132
 	bool heightIsNan(const double x, const double y);                    // :135-157
 	std::array<double, 3> getSurfaceNormal(const double x, const double y);  // :160-213

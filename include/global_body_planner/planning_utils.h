@@ -35,6 +35,17 @@ void interpStateActionPair(State s, Action a, double t0, double dt, std::vector<
 void getInterpPath(std::vector<State> state_sequence, std::vector<Action> action_sequence, double dt,
 				   std::vector<State> &interp_path, std::vector<double> &interp_t, std::vector<int> &interp_phase);
 
+double calculateMaxCurvature(std::vector<State> &body_plan);  // :884-909 (three-point curvature, maximum over the plan)
+
+// ---- printing (:16-104)
+void printState(State vec);
+void printStateNewline(State vec);
+void printAction(Action a);
+void printActionNewline(Action a);
+void printStateSequence(std::vector<State> state_sequence);
+void printActionSequence(std::vector<Action> action_sequence);
+void printStateSequenceXYZPYaw(const std::vector<State> &state_sequence);
+
 // ---- distances (:106-132, header :133-155)
 double poseDistance(const State &q1, const State &q2);
 double stateDistance(const State &q1, const State &q2);

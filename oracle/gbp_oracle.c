@@ -781,3 +781,54 @@ void orc_plan_batch(const orc_terrain *t, long long nq, const double *starts, co
 	free(jobs);
 	free(th);
 }
+
+/* ---- plan output: getInterpPath / interpStateActionPair (src/planning_utils.cpp:142-193).  Returns the number of
+ * interpolated states; writes at most cap of them.  phase has one entry fewer than states (the closing state of the
+ * sequence gets none, :189-191). */
+long long orc_interp_path(int n_actions, const double *states, const double *actions, double dt, long long cap,
+						  double *out_s, double *out_t, int *out_phase) {
+	long long m = 0;
+	double t0 = 0;
+	for (int i = 0; i < n_actions; ++i) {
+		const double *s = states + 8 * (size_t) i, *a = actions + 10 * (size_t) i;
+		const double t_s = a[6], t_f = a[7];
+		double takeoff[8];
+		for (double t = 0; t < t_s; t += dt) {                                 /* :148-155 */
+			if (m < cap) { out_t[m] = t + t0; orc_apply_stance(s, a, t, out_s + 8 * m); out_phase[m] = (t_f == 0) ? 2 : 1; }
+			++m;
+		}
+		orc_apply_stance(s, a, t_s, takeoff);                                  /* :158 */
+		for (double t = 0; t < t_f; t += dt) {                                 /* :161-165 */
+			if (m < cap) { out_t[m] = t_s + t + t0; orc_apply_flight(takeoff, t, out_s + 8 * m); out_phase[m] = 0; }
+			++m;
+		}
+		if (t_f > 0) {                                                         /* :168-172 */
+			if (m < cap) { out_t[m] = t0 + t_s + t_f; orc_apply_flight(takeoff, t_f, out_s + 8 * m); out_phase[m] = 1; }
+			++m;
+		}
+		t0 += (t_s + t_f);                                                     /* :186 */
+	}
+	if (m < cap) { out_t[m] = t0; memcpy(out_s + 8 * m, states + 8 * (size_t) n_actions, 64); }
+	return m + 1;
+}
+
+/* calculateCurvature / calculateMaxCurvature (src/planning_utils.cpp:884-909) */
+static double curvature3(double x1, double y1, double x2, double y2, double x3, double y3) {
+	if ((x1 == x2 && x2 == x3) || (y1 == y2 && y2 == y3)) return 0;
+	double dis12 = sqrt((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
+	double dis13 = sqrt((x1 - x3) * (x1 - x3) + (y1 - y3) * (y1 - y3));
+	double dis23 = sqrt((x2 - x3) * (x2 - x3) + (y2 - y3) * (y2 - y3));
+	double dis = dis12 * dis12 + dis23 * dis23 - dis13 * dis13;
+	double cosA = dis / (2 * dis12 * dis23);
+	double sinA = sqrt(1 - cosA * cosA);
+	double curvature = 0.5 * dis13 / sinA;
+	return 1 / curvature;
+}
+double orc_max_curvature(long long n, const double *states) {
+	double mx = 0;
+	for (long long i = 0; i + 2 < n; ++i) {
+		double c = curvature3(states[8 * i], states[8 * i + 1], states[8 * (i + 1)], states[8 * (i + 1) + 1], states[8 * (i + 2)], states[8 * (i + 2) + 1]);
+		mx = (mx < c) ? c : mx;  /* std::max(mx, c): a NaN c is never taken */
+	}
+	return mx;
+}

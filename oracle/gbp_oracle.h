@@ -145,6 +145,9 @@ int orc_plan(const orc_terrain *t, const double start[8], const double goal[8], 
 			 const orc_plan_params *p, orc_plan_stats *st, double *path_states, double *path_actions, int path_cap);
 void orc_plan_batch(const orc_terrain *t, long long nq, const double *starts, const double *goals, uint64_t seed,
 					uint64_t query0, const orc_plan_params *p, orc_plan_stats *st, int nthreads);
+long long orc_interp_path(int n_actions, const double *states, const double *actions, double dt, long long cap,
+						  double *out_s, double *out_t, int *out_phase);
+double orc_max_curvature(long long n, const double *states);
 int orc_post_process_path(const orc_terrain *t, int ns, double *states, double *actions, int adaptive, double stats3[3]);
 
 #ifdef __cplusplus

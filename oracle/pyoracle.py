@@ -286,6 +286,18 @@ class Oracle:
                               C.byref(params), _p(st), int(nthreads))
         return st
 
+    def interp_path(self, states, actions, dt=0.05, cap=1 << 16):
+        s, a = _f64(states, (-1, 8)), _f64(actions, (-1, 10))
+        os_, ot, op = np.zeros((cap, 8)), np.zeros(cap), np.zeros(cap, np.int32)
+        self.L.orc_interp_path.restype = C.c_longlong
+        m = self.L.orc_interp_path(len(a), _p(s), _p(a), C.c_double(dt), C.c_longlong(cap), _p(os_), _p(ot), _p(op))
+        return os_[:m].copy(), ot[:m].copy(), op[:m - 1].copy()
+
+    def max_curvature(self, states):
+        s = _f64(states, (-1, 8))
+        self.L.orc_max_curvature.restype = C.c_double
+        return self.L.orc_max_curvature(C.c_longlong(len(s)), _p(s))
+
     def post_process_path(self, states, actions, adaptive=False):
         s, a = _f64(states, (-1, 8)).copy(), _f64(actions, (-1, 10)).copy()
         a = np.concatenate([a, np.zeros((1, 10))])
@@ -411,6 +423,18 @@ class Ref:
         st = np.zeros(n, np.int32); sn = np.zeros((n, 8)); an = np.zeros((n, 10))
         self.L.ref_attempt_connect(self.h, C.c_longlong(n), _p(se), _p(s), _p(d), int(adaptive), _p(st), _p(sn), _p(an))
         return st, sn, an
+
+    def interp_path(self, states, actions, dt=0.05, cap=1 << 16):
+        s, a = _f64(states, (-1, 8)), _f64(actions, (-1, 10))
+        os_, ot, op = np.zeros((cap, 8)), np.zeros(cap), np.zeros(cap, np.int32)
+        self.L.ref_interp_path.restype = C.c_longlong
+        m = self.L.ref_interp_path(len(a), _p(s), _p(a), C.c_double(dt), C.c_longlong(cap), _p(os_), _p(ot), _p(op))
+        return os_[:m].copy(), ot[:m].copy(), op[:m - 1].copy()
+
+    def max_curvature(self, states):
+        s = _f64(states, (-1, 8))
+        self.L.ref_max_curvature.restype = C.c_double
+        return self.L.ref_max_curvature(C.c_longlong(len(s)), _p(s))
 
     def post_process_path(self, states, actions):
         s = _f64(states, (-1, 8)).copy(); a = np.concatenate([_f64(actions, (-1, 10)), np.zeros((1, 10))])

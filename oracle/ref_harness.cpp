@@ -255,6 +255,23 @@ int ref_post_process_path(void *h, int ns, double *states, double *actions, int 
 	return m;
 }
 
+// getInterpPath (planning_utils.cpp:175-192) and calculateMaxCurvature (:900-909), unmodified
+long long ref_interp_path(int n_actions, const double *states, const double *actions, double dt, long long cap, double *out_s,
+						  double *out_t, int *out_phase) {
+	std::vector<State> ss, path; std::vector<Action> aa; std::vector<double> tt; std::vector<int> ph;
+	for (int i = 0; i <= n_actions; ++i) ss.push_back(to_state(states + 8 * i));
+	for (int i = 0; i < n_actions; ++i) aa.push_back(to_action(actions + 10 * i));
+	getInterpPath(ss, aa, dt, path, tt, ph);
+	for (long long i = 0; i < (long long) path.size() && i < cap; ++i) { from_state(path[i], out_s + 8 * i); out_t[i] = tt[i]; }
+	for (long long i = 0; i < (long long) ph.size() && i < cap; ++i) out_phase[i] = ph[i];
+	return (long long) path.size();
+}
+double ref_max_curvature(long long n, const double *states) {
+	std::vector<State> plan;
+	for (long long i = 0; i < n; ++i) plan.push_back(to_state(states + 8 * i));
+	return calculateMaxCurvature(plan);
+}
+
 // Unmodified buildRRTConnect / buildRRTStarConnect called the way callPlanner does
 // (global_body_planner.cpp:113-124).  algorithm 0 = rrt-connect, 1 = rrt-star-connect.
 // out: [plan_time, success, vertices, time_to_first, path_length(last cost), path_duration, n_states]

@@ -112,6 +112,12 @@ def mint(name, T, seed):
     out.update(gy_parent=parent, gy_g=g, gy_y=y)
     f3 = rng.normal(0, 100, (200, 3)); n3 = rng.normal(0, 0.2, (200, 3)) + np.array([0, 0, 1.0]); n3[:5] = [0, 0, 1]
     out.update(grf_n=n3, grf_f=f3, grf_out=r.rotate_grf(n3, f3))
+    # plan output: getInterpPath + calculateMaxCurvature over a 40-primitive sequence (half of them pure stance)
+    i0 = len(s) // 8 - 20
+    ps, pa = s[i0:i0 + 41], a[i0:i0 + 40]
+    ips, ipt, ipp = r.interp_path(ps, pa, 0.05)
+    out.update(interp_in_states=ps, interp_in_actions=pa, interp_states=ips, interp_t=ipt, interp_phase=ipp,
+               interp_max_curvature=np.array(r.max_curvature(ips)))
     np.savez_compressed(os.path.join(HERE, f"golden_{name}.npz"), **out)
     r.close()
     print(name, {k2: getattr(v2, "shape", None) for k2, v2 in list(out.items())[:4]}, "valid pairs:",

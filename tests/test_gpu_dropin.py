@@ -108,3 +108,50 @@ def test_dropin_api_against_oracle(exe, tmp_path, name):
         p = R["plan"][0]
         assert p[0] >= 2 and p[1] == 1 and p[2] < 1e-9 and p[3] < 1e-9, f"buildRRTConnect path is not a valid chain: {p}"
         assert p[9] > p[0]
+
+
+def write_csv_dir(T, directory):
+    """the reference's data/<name>/ layout: rows = y, columns = x"""
+    os.makedirs(directory, exist_ok=True)
+    X, Y = np.meshgrid(T.x, T.y)
+    for k, v in {"x": X, "y": Y, "z": T.z.T, "dx": T.dx.T, "dy": T.dy.T, "dz": T.dz.T}.items():
+        with open(os.path.join(directory, f"{k}data.csv"), "w") as f:
+            for row in v:
+                f.write(",".join(repr(float(c)) for c in row) + "\n")
+
+
+def test_call_planner_driver(tmp_path):
+    """gbp_plan = GlobalBodyPlanner::callPlanner without ROS (global_body_planner.cpp:60-168) on BASELINE configs[0]:
+    data/slope from its CSV files, (0,0) -> (8,0), body 0.30 m above ground (the fork's 0.375 m start pose is
+    invalid on this map), the reference's statistics protocol; the discrete plan is re-validated primitive by primitive
+    by the oracle and the published body plan must be the oracle's interpolation of it."""
+    import __graft_entry__ as entry
+    entry.build()
+    T = load_terrain("slope")
+    o = po.Oracle(T)
+    d = str(tmp_path / "slope")
+    write_csv_dir(T, d)
+    exe = os.path.join(ROOT, "global_body_planner_b200", "gbp_plan")
+    plan, disc = str(tmp_path / "plan.csv"), str(tmp_path / "disc.csv")
+    r = subprocess.run([exe, d, "--height", "0.30", "--num-calls", "2", "--replan-time-limit", "0.3", "--max-time-solve", "40",
+                        "--attempts", "2048", "1500", "512", "--plan-out", plan, "--discrete-out", disc],
+                       capture_output=True, text=True, timeout=170)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    assert "----- plan times: 2 / 2 -----" in out and "---------- Average ----------" in out and "Average path length:" in out
+    summ = dict(zip(out.split("SUMMARY")[1].split()[0::2], out.split("SUMMARY")[1].split()[1::2]))
+    assert int(summ["calls"]) == 2
+    rows = np.loadtxt(disc, delimiter=",", ndmin=2)
+    assert len(rows) >= 2, "the planner found no plan for the slope query within 40 s"
+    ss, aa = rows[:, :8], rows[:-1, 8:]
+    h0 = o.ground_height(np.array([0.0, 8.0]), np.array([0.0, 0.0]))[0]
+    assert np.allclose(ss[0], [0, 0, 0.30 + h0[0], 1, 0, 0, 0, 0]) and np.allclose(ss[-1], [8, 0, 0.30 + h0[1], 1, 0, 0, 0, 0])
+    v, fl, sn, tn, _ = o.validate_pairs(ss[:-1], aa, np.zeros(len(aa), np.uint8))
+    assert v.all(), "a primitive of the returned plan is invalid under the oracle"
+    assert np.abs(sn - ss[1:]).max() < 1e-9
+    body = np.loadtxt(plan, delimiter=",", ndmin=2)
+    ips, ipt, ipp = o.interp_path(ss, aa, 0.05)
+    assert len(body) == len(ips)
+    assert_bits_equal(body[:, 1:9], ips, what="body plan states")
+    assert np.array_equal(body[:, 0], ipt) and np.array_equal(body[:-1, 9].astype(int), ipp) and body[-1, 9] == -1
+    assert float(summ["avg_path_length"]) >= 8.0 - 1e-9  # no path is shorter than the straight line

@@ -252,3 +252,66 @@ def test_empty_and_ragged_inputs(gbp, dev):
             v, fl, sn, tn = t.validate_pairs(G["pair_states"][:n], G["pair_actions"][:n], G["pair_dir"][:n], variant=variant)
             assert (v[(fl & 2) == 0] == G["pair_verdict_0"][:n][(fl & 2) == 0]).all()
     assert len(t.ground_height([], [])[0]) == 0
+
+
+def test_interp_path_and_curvature_golden(gbp, dev):
+    """getInterpPath / calculateMaxCurvature through the C ABI: bit-equal to the reference's vectors and the oracle"""
+    t, o, T, G, _ = dev
+    s, tt, ph = gbp.interp_path(G["interp_in_states"], G["interp_in_actions"], 0.05)
+    assert len(s) == len(G["interp_states"]) and len(ph) == len(s) - 1
+    assert_bits_equal(s, G["interp_states"], what="interp states")
+    assert_bits_equal(tt, G["interp_t"], what="interp times")
+    assert (ph == G["interp_phase"]).all()
+    assert gbp.max_curvature(s) == float(G["interp_max_curvature"])
+    for dt in (0.03, 0.011, 1.0):
+        so, to, po_ = o.interp_path(G["interp_in_states"], G["interp_in_actions"], dt)
+        sg, tg, pg = gbp.interp_path(G["interp_in_states"], G["interp_in_actions"], dt)
+        assert_bits_equal(sg, so, what=f"interp states dt={dt}")
+        assert np.array_equal(tg, to) and np.array_equal(pg, po_)
+        assert gbp.max_curvature(sg) == o.max_curvature(so)
+    # capacity smaller than the path, empty action list, degenerate plans
+    sg, tg, pg = gbp.interp_path(G["interp_in_states"], G["interp_in_actions"], 0.05, cap=7)
+    assert len(sg) == 7 and (sg == G["interp_states"][:7]).all()
+    s1, t1, p1 = gbp.interp_path(G["interp_in_states"][:1], np.zeros((0, 10)), 0.05)
+    assert len(s1) == 1 and (s1[0] == G["interp_in_states"][0]).all() and t1[0] == 0.0 and len(p1) == 0
+    assert gbp.max_curvature(G["interp_in_states"][:2]) == 0.0
+    with pytest.raises(gbp.GbpError):
+        gbp.interp_path(G["interp_in_states"], G["interp_in_actions"], 0.0)
+
+
+def test_csv_ingest(gbp, dev, tmp_path):
+    """The reference's on-disk terrain format (data/<name>/*.csv, rows = y, columns = x): the loadData route equals
+    the arrays handed over directly, the GridMap route equals gbp_terrain_create_gridmap on the float-rounded layers."""
+    t, o, T, G, name = dev
+    X, Y = np.meshgrid(T.x, T.y)  # [ny, nx]
+    lay = {"x": X, "y": Y, "z": T.z.T, "dx": T.dx.T, "dy": T.dy.T, "dz": T.dz.T}
+    for k, v in lay.items():
+        with open(tmp_path / f"{k}data.csv", "w") as f:
+            if k == "z":
+                f.write("# elevation, rows = y\n")
+            for row in v:
+                f.write(",".join("nan" if np.isnan(c) else repr(float(c)) for c in row) + "\n")
+    tc = gbp.Terrain.from_csv(str(tmp_path))
+    assert (tc.nx, tc.ny) == (len(T.x), len(T.y)) and tc.cell_bytes == t.cell_bytes
+    xa, ya = tc.axes()
+    assert (xa == T.x).all() and (ya == T.y).all()
+    px, py = G["probe_x"], G["probe_y"]
+    assert_bits_equal(tc.ground_height(px, py)[0], G["probe_h"], what="height via CSV")
+    assert_bits_equal(tc.surface_normal(px, py), G["probe_normal"], what="normal via CSV")
+    assert (tc.height_is_nan(px, py) == G["probe_nan"]).all()
+    # ROS route: uniform square cells only (the reference throws otherwise)
+    res = np.float32(T.x[1] - T.x[0])
+    if np.float32(T.y[1] - T.y[0]) == res:
+        tg = gbp.Terrain.from_csv(str(tmp_path), via_gridmap=True)
+        nx, ny = len(T.x), len(T.y)
+        xl = T.x[-1] - T.x[0] + res; yl = T.y[-1] - T.y[0] + res
+        cx = T.x[0] - 0.5 * res + 0.5 * xl; cy = T.y[0] - 0.5 * res + 0.5 * yl
+        flip = lambda a: np.ascontiguousarray(a[::-1, ::-1].astype(np.float32))
+        tr = gbp.Terrain.from_gridmap(nx, ny, float(res), float(cx), float(cy), flip(T.z), flip(T.dx), flip(T.dy), flip(T.dz))
+        x2, y2 = tg.axes(); x3, y3 = tr.axes()
+        assert (x2 == x3).all() and (y2 == y3).all() and np.allclose(x2, T.x, atol=1e-6)
+        inside = (px > x2[0]) & (px < x2[-1] - 1e-6) & (py > y2[0]) & (py < y2[-1] - 1e-6)
+        h2, h3 = tg.ground_height(px[inside], py[inside])[0], tr.ground_height(px[inside], py[inside])[0]
+        assert_bits_equal(h2, h3, what="height via CSV -> GridMap")
+    with pytest.raises(gbp.GbpError):
+        gbp.Terrain.from_csv(str(tmp_path / "missing"))

@@ -123,3 +123,18 @@ def test_tree_queries(golden):
     v = G["nn_verts"]
     for kind, key in ((0, "dist_pose"), (1, "dist_state"), (2, "dist_yaw")):
         assert_bits_equal(o.distance(v[:500], v[500:1000], kind), G[key], what=key)
+
+
+def test_interp_path_and_curvature(golden):
+    """getInterpPath / calculateMaxCurvature (planning_utils.cpp:142-193, :884-909) against the reference's vectors"""
+    name, T, G = golden
+    o = po.Oracle(T)
+    s, t, ph = o.interp_path(G["interp_in_states"], G["interp_in_actions"], 0.05)
+    assert len(s) == len(G["interp_states"]) and len(ph) == len(s) - 1
+    assert_bits_equal(s, G["interp_states"], what="interp states")
+    assert_bits_equal(t, G["interp_t"], what="interp times")
+    assert (ph == G["interp_phase"]).all() and set(np.unique(ph)) == {0, 1, 2}
+    assert o.max_curvature(s) == float(G["interp_max_curvature"])
+    # capacity: the count is still the full length, only `cap` entries are written
+    s2, t2, _ = o.interp_path(G["interp_in_states"], G["interp_in_actions"], 0.05, cap=10)
+    assert len(s2) == len(s) or len(s2) == 10

@@ -106,3 +106,19 @@ def test_post_process_path(pair):
         assert abs(s3[1] - r3[1]) < 1e-12
         compared += 1
     assert compared >= 1 or T.nx < 60
+
+
+def test_interp_path_other_resolutions(pair):
+    """dt values that do / do not divide the stance time, straight and degenerate curvature triples"""
+    import os
+    o, r, T = pair
+    name = [n for n in ("rough_terrain", "slope", "synth_nan", "synth_mixed") if np.array_equal(load_terrain(n).z, T.z, equal_nan=True)][0]
+    G = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", f"golden_{name}.npz")))
+    for dt in (0.05, 0.03, 0.011, 0.3, 1.0):
+        so, to, po_ = o.interp_path(G["interp_in_states"], G["interp_in_actions"], dt)
+        sr, tr, pr = r.interp_path(G["interp_in_states"], G["interp_in_actions"], dt)
+        assert np.array_equal(so.view(np.uint64), sr.view(np.uint64)) and np.array_equal(to, tr) and np.array_equal(po_, pr)
+        assert o.max_curvature(so) == r.max_curvature(sr)
+    line = np.zeros((5, 8)); line[:, 0] = np.arange(5)
+    assert o.max_curvature(line) == r.max_curvature(line) == 0.0
+    assert o.max_curvature(line[:2]) == r.max_curvature(line[:2]) == 0.0
