@@ -106,10 +106,11 @@ def interp_path(states, actions, dt=0.05, cap=None):
     s, a = _f64(states, (-1, 8)), _f64(actions, (-1, 10))
     if len(s) != len(a) + 1:
         raise GbpError("interp_path needs len(states) == len(actions) + 1")
-    if cap is None:
-        cap = int(sum(np.ceil(max(x, 0.0) / dt) + 2 for x in np.concatenate([a[:, 6], a[:, 7]]))) + 2
-    os_, ot, op = np.zeros((cap, 8)), np.zeros(cap), np.zeros(cap, np.int32)
     m = C.c_int64()
+    if cap is None:  # size query: cap = 0 writes nothing and returns the count
+        _check(lib().gbp_interp_path(len(a), _p(s), _p(a), C.c_double(dt), C.c_int64(0), None, None, None, C.byref(m)))
+        cap = m.value
+    os_, ot, op = np.zeros((cap, 8)), np.zeros(cap), np.zeros(cap, np.int32)
     _check(lib().gbp_interp_path(len(a), _p(s), _p(a), C.c_double(dt), C.c_int64(cap), _p(os_), _p(ot), _p(op), C.byref(m)))
     n = min(m.value, cap)
     return os_[:n].copy(), ot[:n].copy(), op[:max(n - 1, 0)].copy()
