@@ -21,7 +21,7 @@ class GbpError(RuntimeError):
 
 class PlanParams(C.Structure):
     _fields_ = [("k_candidates", C.c_int), ("best_of_k", C.c_int), ("max_iters", C.c_int), ("max_vertices", C.c_int),
-                ("adaptive", C.c_int), ("rrt_star", C.c_int), ("post_process", C.c_int)]
+                ("adaptive", C.c_int), ("rrt_star", C.c_int), ("post_process", C.c_int), ("stop_after_solved", C.c_int)]
 
 
 PLAN_STATS_DTYPE = np.dtype([("solved", "i4"), ("iters", "i4"), ("nv_a", "i4"), ("nv_b", "i4"), ("path_states", "i4"),

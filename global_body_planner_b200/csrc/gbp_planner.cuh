@@ -423,12 +423,17 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 	const int lane = threadIdx.x & 31;
 	const int64_t slot = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
 	unsigned long long *next_query = (unsigned long long *) (counts + 2 * (((int64_t) gridDim.x * blockDim.x) >> 5));
+	volatile int *solved_count = (volatile int *) (next_query + 1);  // anytime use: queries solved so far in this launch
 	while (true) {
 		// queries differ widely in iterations: warps pull the next query from a device counter (no static round-robin tail)
 		unsigned long long grabbed = 0;
 		if (lane == 0) grabbed = atomicAdd(next_query, 1ull);
 		const int64_t qi = (int64_t) __shfl_sync(FULL, grabbed, 0);
 		if (qi >= nq) break;
+		if (P.stop_after_solved > 0 && __shfl_sync(FULL, *solved_count, 0) >= P.stop_after_solved) {  // enough solved: skip the rest
+			if (lane == 0) { gbp_plan_stats z = {}; stats[qi] = z; }
+			continue;
+		}
 		PlanTree Ta = arena_tree(A, (int) slot, 0, counts + 2 * slot), Tb = arena_tree(A, (int) slot, 1, counts + 2 * slot + 1);
 		double start[8], goal[8];
 #pragma unroll
@@ -440,6 +445,7 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 		long long pair_checks = 0, nn_queries = 0;
 		const uint64_t query = query0 + (uint64_t) qi;
 		for (; it < P.max_iters && !solved && !full; ++it) {
+			if (P.stop_after_solved > 0 && __shfl_sync(FULL, *solved_count, 0) >= P.stop_after_solved) break;
 			for (int half = 0; half < 2 && !solved; ++half) {
 				PlanTree &Tx = half == 0 ? Ta : Tb, &Ty = half == 0 ? Tb : Ta;
 				int &nx = half == 0 ? na : nb, &ny = half == 0 ? nb : na;
@@ -502,7 +508,10 @@ __global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, 
 					for (int d = 0; d < 10; ++d) path_actions[((size_t) qi * path_cap + i) * 10 + d] = pa[10 * (size_t) i + d];
 			}
 		}
-		if (lane == 0) stats[qi] = st;
+		if (lane == 0) {
+			stats[qi] = st;
+			if (solved && P.stop_after_solved > 0) atomicAdd((int *) solved_count, 1);
+		}
 		__syncwarp();
 	}
 }
@@ -523,7 +532,7 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	A.cap = P.max_vertices;
 	const size_t cap = (size_t) A.cap, per = (size_t) slots * 2 * cap;
 	const size_t n_doubles = per * (8 + 10 + 1 + 1) + (size_t) slots * cap * 20 + (size_t) slots * 2 * cap * 18;
-	const size_t n_ints = per * 3 + (size_t) slots * cap * 3 + (size_t) slots * 2 + 4;  // + the 8-byte work counter
+	const size_t n_ints = per * 3 + (size_t) slots * cap * 3 + (size_t) slots * 2 + 4;  // + the 8-byte work counter and the solved count
 	cudaError_t e;
 	const size_t need = n_doubles * sizeof(double) + n_ints * sizeof(int);
 	if (*arena_bytes < need) {
@@ -553,7 +562,7 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	int *counts = ip;
 	{  // 8-byte aligned work counter right after the per-slot vertex counts
 		unsigned long long *next_query = (unsigned long long *) (counts + 2 * slots);
-		if ((e = cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st)) != cudaSuccess) { err = cudaGetErrorString(e); return GBP_E_CUDA; }
+		if ((e = cudaMemsetAsync(next_query, 0, sizeof(unsigned long long) + 2 * sizeof(int), st)) != cudaSuccess) { err = cudaGetErrorString(e); return GBP_E_CUDA; }
 	}
 #define GBP_PLAN_(M) do { if (P.rrt_star) k_plan_batch<M, true><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); \
 						  else k_plan_batch<M, false><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); } while (0)

@@ -295,8 +295,10 @@ void RRTConnectClass::buildRRTConnect(FastTerrainMap &terrain, State s_start, St
 	anytime_horizon = poseDistance(s_start, s_goal) / planning_rate_estimate;
 	double cost_so_far = INFTY;
 	const int R = parallel_attempts_, cap = 256;
+	// anytime use of the batch planner: all attempts work on the same query, the round ends once 8 of them have solved
+	// (the 8 shortest raw paths are shortcut below)
 	gbp_plan_params P = {k_candidates_, best_of_k_ ? 1 : 0, iterations_per_attempt_, vertices_per_tree_,
-						 state_action_pair_check_adaptive_step_size_flag_ ? 1 : 0, 0, 0};
+						 state_action_pair_check_adaptive_step_size_flag_ ? 1 : 0, 0, 0, 8};
 	std::vector<State> starts(R, s_start), goals(R, s_goal);
 	std::vector<gbp_plan_stats> stats(R);
 	std::vector<double> ps((size_t) R * cap * 8), pa((size_t) R * cap * 10);
@@ -304,6 +306,7 @@ void RRTConnectClass::buildRRTConnect(FastTerrainMap &terrain, State s_start, St
 	std::vector<Action> best_actions;
 	bool first = true;
 	for (std::uint64_t round = 0;; ++round) {
+		P.stop_after_solved = goal_found ? 8 : 1;  // until a first solution exists the round ends with the first attempt that solves
 		check(gbp_plan_batch(terrain.handle(), R, starts[0].data(), goals[0].data(), seed_, (stream_ << 20) + round * (std::uint64_t) R, &P,
 							 stats.data(), ps.data(), pa.data(), cap), "buildRRTConnect");
 		std::vector<int> solved;

@@ -227,6 +227,9 @@ typedef struct {
 	int adaptive;
 	int rrt_star;     /* RRTStarConnectClass::extend (rrt_star_connect.cpp:12-75), delta = 3.0 */
 	int post_process; /* postProcessPath (rrt_connect.cpp:139-227) on solved queries */
+	int stop_after_solved; /* > 0: anytime use (many attempts at ONE query): once this many queries of the batch have
+	                          solved, the others stop at their next iteration and report solved = 0 with the work done
+	                          so far (which ones depends on timing).  0: every query runs to its own budget (reproducible) */
 } gbp_plan_params;
 
 typedef struct {

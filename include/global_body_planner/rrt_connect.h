@@ -32,7 +32,7 @@ protected:
 	double anytime_horizon_init = 0;
 	double horizon_expansion_factor = 1.2;
 	const int max_time_solve = 4000;
-	int parallel_attempts_ = 2048, iterations_per_attempt_ = 2000, vertices_per_tree_ = 512;
+	int parallel_attempts_ = 2368, iterations_per_attempt_ = 8000, vertices_per_tree_ = 2048;  // one wave of warps on 148 SMs; trees as large as the reference's solves (1-2 k vertices)
 	double max_time_solve_ = 4000;
 };
 

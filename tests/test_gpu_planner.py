@@ -75,3 +75,23 @@ def test_plan_batch_capacity_and_budget(gbp):
         so, _, _ = o.plan(s[i], g[i], 3, i, Po)
         assert (st["solved"][i], st["iters"][i], st["nv_a"][i], st["nv_b"][i]) == (so.solved, so.iters, so.nv_a, so.nv_b)
     assert (st["nv_a"] <= 4).all() and (st["nv_b"] <= 4).all()
+
+
+def test_stop_after_solved(gbp):
+    """anytime use (many attempts at one query): the launch ends once `stop_after_solved` attempts have solved; attempts
+    that did solve are unaffected (their own search is deterministic), the others report the work done so far."""
+    T = load_terrain("slope"); o = po.Oracle(T)
+    t = gbp.Terrain(T.x, T.y, T.z, T.dx, T.dy, T.dz)
+    s, g = queries(o, T, 24, 5)
+    Po = po.PlanParams(6, 0, 400, 256, 0, 0, 0)
+    i = next(k for k in range(len(s)) if o.plan(s[k], g[k], 1, 1 << 20, Po)[0].solved)
+    n = 4096
+    S, G = np.repeat(s[i][None], n, 0), np.repeat(g[i][None], n, 0)
+    full = t.plan_batch(S, G, 1, 1 << 20, gbp.PlanParams(6, 0, 400, 256, 0, 0, 0, 0))
+    early = t.plan_batch(S, G, 1, 1 << 20, gbp.PlanParams(6, 0, 400, 256, 0, 0, 0, 4))
+    assert full["solved"][0] == 1 and full["solved"].sum() >= 4
+    assert 4 <= early["solved"].sum() <= full["solved"].sum()
+    hit = early["solved"] == 1
+    for key in ("iters", "nv_a", "nv_b", "path_states", "pair_checks", "nn_queries", "path_length"):
+        assert (early[key][hit] == full[key][hit]).all(), key
+    assert (early["iters"] <= full["iters"]).all() and early["iters"].sum() < full["iters"].sum()
