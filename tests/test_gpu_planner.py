@@ -36,7 +36,9 @@ def queries(o, T, n, seed):
 
 @pytest.mark.parametrize("name,K,best,star,post", [("slope", 6, 0, 0, 0), ("rough_terrain", 6, 0, 0, 0), ("slope", 48, 1, 0, 0),
                                                   ("synth_nan", 6, 0, 0, 0), ("slope", 6, 0, 0, 1), ("synth_nan", 24, 1, 0, 1),
-                                                  ("slope", 32, 1, 1, 0), ("synth_nan", 32, 1, 1, 1), ("rough_terrain", 32, 1, 1, 0)])
+                                                  ("slope", 32, 1, 1, 0), ("synth_nan", 32, 1, 1, 1), ("rough_terrain", 32, 1, 1, 0),
+                                                  # fp32 NaN-free map on uniform axes: the mixed-precision / texture-gather evaluator
+                                                  ("synth_mixed", 6, 0, 0, 0), ("synth_mixed", 24, 1, 0, 1), ("synth_mixed", 32, 1, 1, 1)])
 def test_plan_batch_matches_oracle(gbp, name, K, best, star, post):
     """RRT-Connect, RRT*-Connect (choose parent + rewire) and postProcessPath, all resident on the device."""
     T = load_terrain(name)
