@@ -47,10 +47,11 @@ def make_queries(valid_states_fn, sample_states_fn, nq, seed, stream):
     return np.array(starts[:nq]), np.array(goals[:nq])
 
 
-def run_rough_k4096(gbp, torch, dev, nq=512, iters=100):
+def run_rough_k4096(gbp, torch, dev, nq=4736, iters=40):
     """BASELINE configs[1]: RRT-Connect on the reference's data/rough_terrain (committed as
     tests/golden/terrain_rough_terrain.npz), 4096 candidate actions per extend (closest valid), start (0,0) ->
-    goal (8,0) at body height 0.375 m; nq independent searches (distinct Philox streams)."""
+    goal (8,0) at body height 0.375 m; nq independent searches (distinct Philox streams; 4736 = two
+    waves of the planner's 16 resident warps per SM on 148 SMs)."""
     d = np.load(os.path.join(ROOT, "tests", "golden", "terrain_rough_terrain.npz"))
     t = gbp.Terrain(d["x"], d["y"], d["z"], d["dx"], d["dy"], d["dz"])
     h, _ = t.ground_height([0.0, 8.0], [0.0, 0.0])
@@ -122,6 +123,28 @@ def run(gbp, torch, dist, dev, rank, world, q_per_gpu=Q_PER_GPU, cpu_seconds=8.0
            "mean_path_length_m": float(st["path_length"][st["solved"] == 1].mean()) if st["solved"].any() else None,
            "mean_iters": float(st["iters"].mean()), "stats_gather_bytes": int(allstats.nbytes)}
     out["rough_k4096"] = run_rough_k4096(gbp, torch, dev) if world == 1 or rank == 0 else None
+    # BASELINE configs[2]: RRT*-Connect (choose parent + near-set rewiring, delta = 3 m, rrt_star_connect.cpp:12-75) with
+    # postProcessPath, on the first queries of the same set; iteration budget instead of the wall-clock budget
+    ns, star_iters = min(nq, 2048), 400
+    Ps = gbp.PlanParams(K_CAND, 0, star_iters, MAX_VERTS, 0, 1, 1)
+    Pc2 = gbp.PlanParams(K_CAND, 0, star_iters, MAX_VERTS, 0, 0, 1)
+    res = {}
+    for name, PP in (("rrt_star_connect", Ps), ("rrt_connect_same_budget", Pc2)):
+        t.plan_batch_dev(ns, ds.data_ptr(), dg.data_ptr(), seed, query0, PP, dstats.data_ptr(), cur)
+        torch.cuda.synchronize()
+        e0.record()
+        t.plan_batch_dev(ns, ds.data_ptr(), dg.data_ptr(), seed, query0, PP, dstats.data_ptr(), cur)
+        e1.record()
+        torch.cuda.synchronize()
+        ss = dstats.cpu().numpy().view(gbp.PLAN_STATS_DTYPE)[:ns]
+        sec = e0.elapsed_time(e1) * 1e-3
+        ok = ss["solved"] == 1
+        res[name] = {"solved": int(ok.sum()), "solved_plans_per_s": float(ok.sum() / sec), "seconds": sec,
+                     "mean_path_length_m": float(ss["path_length"][ok].mean()) if ok.any() else None,
+                     "validated_actions_per_s": float(ss["pair_checks"].sum() / sec), "mean_vertices": float((ss["nv_a"] + ss["nv_b"]).mean())}
+    res["workload"] = (f"{ns} queries of the same set, {star_iters} iterations, post-processed paths; RRT*-Connect (delta = 3 m rewiring) against "
+                       "RRT-Connect at the same budget")
+    out["rrt_star"] = res
     if want_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import pyoracle as po
