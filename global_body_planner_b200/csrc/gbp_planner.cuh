@@ -415,7 +415,14 @@ __device__ int warp_post_process(const TerrainView &Tv, double *ps, double *pa, 
 }
 
 template <typename M, bool STAR>
-__global__ void __launch_bounds__(128) k_plan_batch(TerrainView Tv, int64_t nq, const double *__restrict__ starts,
+// Occupancy over registers: the kernel is 21 k SASS instructions and its warps sit at unrelated program counters, so
+// at 255 registers (8 warps / SM) ncu shows 8.3 of the 12.2 cycles between two issues of a warp waiting for
+// instruction fetch (profiles/r1b_planner_ncu_summary.csv).  Capping the registers at 80 (24 warps / SM, ~2.7 KB of
+// spills per thread, L1-resident) hides that latency: 9.2 k -> 15.8 k plans/s (4 CTAs / SM: 12.3 k, 8: 16.2 k).
+#ifndef GBP_PLAN_MINBLOCKS
+#define GBP_PLAN_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainView Tv, int64_t nq, const double *__restrict__ starts,
 													 const double *__restrict__ goals, uint64_t seed, uint64_t query0,
 													 gbp_plan_params P, PlanArena A, int *__restrict__ counts,
 													 gbp_plan_stats *__restrict__ stats, double *__restrict__ path_states,
@@ -525,7 +532,7 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	const int threads = 128, warps_per_block = threads / 32;
-	int64_t slots = (int64_t) sms * 16;  // resident warps
+	int64_t slots = (int64_t) sms * 4 * GBP_PLAN_MINBLOCKS;  // resident warps (register-limited)
 	if (slots > nq) slots = ((nq + warps_per_block - 1) / warps_per_block) * warps_per_block;
 	const unsigned grid = (unsigned) (slots / warps_per_block);
 	PlanArena A;

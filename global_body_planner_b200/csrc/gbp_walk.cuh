@@ -71,14 +71,17 @@ __device__ __forceinline__ void walk_take_off(WalkCursor &q) {
 // stance from its start state (applyStanceReverse at t = 0, :324-367).  st = this thread's column of the parked
 // accelerations {a_td x,y,z,pitch, a_to x,y,z,pitch}, stride RF_WARPS * 32 doubles.
 __device__ __forceinline__ void walk_reverse_stance(WalkCursor &q, const double *st) {
-	const double ts = q.ts, mtf = -q.tf, inv6ts = __drcp_rn(6.0 * ts), ts2 = ts * ts, ts3 = ts2 * ts;
+	const double ts = q.ts, mtf = -q.tf, inv6ts = __drcp_rn(6.0 * ts);
 #pragma unroll
 	for (int d = 0; d < 4; ++d) {
-		const double tp = cubic(q.c[d], mtf), tv = cubic_d(q.c[d], mtf);
+		// the segment being left is a flight: c3 = 0 and c2 is the constant -g/2 (z) or 0
+		const double tp = d == 2 ? __fma_rn(__fma_rn(q.c[d][2], mtf, q.c[d][1]), mtf, q.c[d][0]) : __fma_rn(q.c[d][1], mtf, q.c[d][0]);
+		const double tv = d == 2 ? __fma_rn(q.c[d][2] + q.c[d][2], mtf, q.c[d][1]) : q.c[d][1];
 		const double atd = st[d * (RF_WARPS * 32)], j = st[(4 + d) * (RF_WARPS * 32)] - atd;
-		const double cc = tv - atd * ts - 0.5 * j * ts;
-		q.c[d][0] = tp - cc * ts - 0.5 * atd * ts2 - j * ts3 * inv6ts;
-		q.c[d][1] = cc; q.c[d][2] = 0.5 * atd; q.c[d][3] = j * inv6ts;
+		const double c2 = 0.5 * atd, c3 = j * inv6ts;
+		const double cc = __fma_rn(-ts, __fma_rn(0.5, j, atd), tv);                      // tv - a_td ts - j ts / 2
+		q.c[d][0] = __fma_rn(-ts, __fma_rn(ts, __fma_rn(c3, ts, c2), cc), tp);           // tp - cc ts - a_td ts^2 / 2 - j ts^3 / (6 ts)
+		q.c[d][1] = cc; q.c[d][2] = c2; q.c[d][3] = c3;
 	}
 }
 
