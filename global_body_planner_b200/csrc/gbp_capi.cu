@@ -562,7 +562,7 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 	} else {
 		// persistent-style geometry: a multiple of the SM count; each warp owns a contiguous range
 		const int threads = RF_WARPS * 32, warps_per_block = RF_WARPS;
-		int64_t max_warps = (int64_t) sm_count() * RF_WARPS * (t->view.mixed_ok ? GBP_WALK_CTAS : 2);  // one wave of resident warps  // 16 resident warps per SM at this register budget
+		int64_t max_warps = (int64_t) sm_count() * RF_WARPS * (t->view.mixed_ok ? GBP_WALK_CTAS : 2);  // one wave of resident warps
 		int64_t per_warp = (n + max_warps - 1) / max_warps;
 		if (per_warp < 64) per_warp = 64;
 		per_warp = (per_warp + RF_CHUNK - 1) / RF_CHUNK * RF_CHUNK;  // chunks of the TMA ring are 32-aligned
@@ -588,7 +588,7 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 			cfg.numAttrs = 1;
 		}
 		if (t->view.mixed_ok) {
-			// mixed-precision walk (3 CTAs / SM) + fp64 redo pass over the candidates it could not decide
+			// mixed-precision walk (k_walk_mixed, gbp_walk.cuh) + fp64 redo pass over the candidates it could not decide
 			if (n > 0x7fffffff) return fail(GBP_E_INVALID, "at most 2^31-1 candidates per call");
 			gbp_terrain *tm = const_cast<gbp_terrain *>(t);  // grow-only scratch owned by the handle (handles are not thread-safe)
 			if (tm->redo_cap < (size_t) n) {
@@ -606,9 +606,8 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 			if (t->view.ztex) { if (adaptive) GBP_WALK_(true, true); else GBP_WALK_(true, false); }
 			else { if (adaptive) GBP_WALK_(false, true); else GBP_WALK_(false, false); }
 #undef GBP_WALK_
-			if (!getenv("GBP_SKIP_REDO"))
-				k_validate_redo<MapF32U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
-																	   flags, s_new, t_new, t->d_cnt);
+			k_validate_redo<MapF32U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
+																   flags, s_new, t_new, t->d_cnt);
 		} else {
 #define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt))
 			if (t->view.cell_f32) { if (t->view.uniform) GBP_WALK_(MapF32U); else GBP_WALK_(MapF32N); }

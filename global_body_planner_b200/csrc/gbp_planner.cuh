@@ -417,7 +417,7 @@ __device__ int warp_post_process(const TerrainView &Tv, double *ps, double *pa, 
 template <typename M, bool STAR>
 // Occupancy over registers: the kernel is 21 k SASS instructions and its warps sit at unrelated program counters, so
 // at 255 registers (8 warps / SM) ncu shows 8.3 of the 12.2 cycles between two issues of a warp waiting for
-// instruction fetch (profiles/r1b_planner_ncu_summary.csv).  Capping the registers at 80 (24 warps / SM, ~2.7 KB of
+// instruction fetch (profiles/r1b_planner_2ctas_ncu_summary.csv).  Capping the registers at 80 (24 warps / SM, ~2.7 KB of
 // spills per thread, L1-resident) hides that latency: 9.2 k -> 15.8 k plans/s (4 CTAs / SM: 12.3 k, 8: 16.2 k).
 #ifndef GBP_PLAN_MINBLOCKS
 #define GBP_PLAN_MINBLOCKS 6

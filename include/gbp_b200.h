@@ -85,6 +85,9 @@ int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes);
 /* which evaluator serves this terrain: uniform_axes = cell edges are computed, not loaded; mixed_precision = the
  * fp32-around-fp64 evaluator applies (fp32 cells, no NaN, uniform axes, pitch >= 1 cm, interior >> border) */
 int gbp_terrain_flags(const gbp_terrain *t, int *uniform_axes, int *mixed_precision);
+/* Environment switches read at terrain creation / launch, for A/B measurements only (results are identical):
+ * GBP_NO_MIXED=1 keeps the fp64 evaluator on every terrain, GBP_NO_TEX=1 the 4-load fetch, GBP_NO_L2_WINDOW=1 drops the
+ * persisting-L2 access window of the height grid. */
 /* texture_gather = 1 when the mixed-precision walk fetches each probe's 2x2 cells with one texture gather from a
  * block-linear copy of the height grid (the default for such terrains; GBP_NO_TEX=1 in the environment at creation
  * time keeps the 4-load form, results are identical) */
