@@ -449,6 +449,8 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 		__syncwarp();
 		int na = 1, nb = 1, it = 0;
 		bool solved = false, full = false;
+		double rs[8];          // this lane's random state of the current batch of 32 STATE cells
+		unsigned rs_valid = 0;  // isValidState(STANCE) of the 32 states
 		long long pair_checks = 0, nn_queries = 0;
 		const uint64_t query = query0 + (uint64_t) qi;
 		for (; it < P.max_iters && !solved && !full; ++it) {
@@ -459,10 +461,19 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 				const int dir_ext = half == 0 ? GBP_FORWARD : GBP_REVERSE, dir_con = half == 0 ? GBP_REVERSE : GBP_FORWARD;
 				if (nx >= A.cap || ny >= A.cap) { full = true; break; }
 				const uint64_t cell = 2 * (uint64_t) it + (uint64_t) half;
+				// Random states come from a counter-based stream (STATE cell = 2 * iter + half) and their validity does not
+				// depend on the trees: the warp draws and checks the next 32 cells at once, lane L holding cell base + L,
+				// instead of all 32 lanes redundantly producing one (that was ~75 % of the kernel's instructions).
+				if ((cell & 31ull) == 0) {
+					sample_state<M>(Tv, seed, query, cell + (uint64_t) lane, false, 0.0, false, nullptr, nullptr, rs);
+					Counters c = {0, 0, 0, 0};
+					rs_valid = __ballot_sync(FULL, is_valid_state_auto<M>(Tv, pose6(rs), GBP_STANCE, c));
+				}
+				const int src = (int) (cell & 31ull);
+				if (!((rs_valid >> src) & 1u)) continue;  // rrt_connect.cpp:254
 				double s_rand[8];
-				sample_state<M>(Tv, seed, query, cell, false, 0.0, false, nullptr, nullptr, s_rand);
-				Counters c = {0, 0, 0, 0};
-				if (!is_valid_state_auto<M>(Tv, pose6(s_rand), GBP_STANCE, c)) continue;  // rrt_connect.cpp:254
+#pragma unroll
+				for (int d = 0; d < 8; ++d) s_rand[d] = __shfl_sync(FULL, rs[d], src);
 				++nn_queries;
 				const int r = STAR ? warp_extend_star<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, A, (int) slot, lane, pair_checks)
 								   : warp_extend<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, lane, pair_checks);
