@@ -276,9 +276,9 @@ def main():
     torch.cuda.synchronize()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    # the dominant kernel alone (the walk, k_validate_refill): variant 5 = variant 3 without k_pair_outputs
+    # the dominant kernel alone (the walk, k_walk_mixed on this map): variant 5 = variant 3 without k_pair_outputs
     walk_variant = 5 if args.variant in (0, 3) else args.variant
-    # variant 0/3: the walk (k_validate_refill), the fp64 redo pass when the mixed-precision walk is in use, k_pair_outputs
+    # variant 0/3: the walk (k_walk_mixed), the fp64 redo pass when the mixed-precision walk is in use, k_pair_outputs
     kernels_per_step = (3 if t.flags()["mixed_precision"] else 2) if args.variant in (0, 3) else 1
     evk = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     evk[0].record()

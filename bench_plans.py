@@ -47,11 +47,11 @@ def make_queries(valid_states_fn, sample_states_fn, nq, seed, stream):
     return np.array(starts[:nq]), np.array(goals[:nq])
 
 
-def run_rough_k4096(gbp, torch, dev, nq=4736, iters=40):
+def run_rough_k4096(gbp, torch, dev, nq=7104, iters=40):
     """BASELINE configs[1]: RRT-Connect on the reference's data/rough_terrain (committed as
     tests/golden/terrain_rough_terrain.npz), 4096 candidate actions per extend (closest valid), start (0,0) ->
-    goal (8,0) at body height 0.375 m; nq independent searches (distinct Philox streams; 4736 = two
-    waves of the planner's 16 resident warps per SM on 148 SMs)."""
+    goal (8,0) at body height 0.375 m; nq independent searches (distinct Philox streams; 7104 = two
+    waves of the planner's 24 resident warps per SM on 148 SMs)."""
     d = np.load(os.path.join(ROOT, "tests", "golden", "terrain_rough_terrain.npz"))
     t = gbp.Terrain(d["x"], d["y"], d["z"], d["dx"], d["dy"], d["dz"])
     h, _ = t.ground_height([0.0, 8.0], [0.0, 0.0])

@@ -1,7 +1,8 @@
 // k_walk_mixed — the pair-check walk for fp32 maps on uniform axes (the kernel bench.py's headline number runs).
-// Same contract as k_validate_refill<M, MIXED_ONLY = true> (lane per action, warp-level refill, TMA-staged candidate
-// ring, mixed-precision isValidState, undecided candidates handed to the fp64 redo pass) with the per-lane cursor
-// rebuilt around what the walk's ncu profile showed (profiles/r1b_*): half of the 940 warp instructions per trip were
+// Same contract as k_validate_refill<M> (gbp_kernels.cuh: lane per action, warp-level refill, TMA-staged candidate
+// ring) with the mixed-precision isValidState alone — a candidate that reaches a sub-state it cannot decide is handed to
+// the fp64 redo pass (k_validate_redo) — and the per-lane cursor rebuilt around what the walk's ncu profile showed
+// (profiles/r1b_step1_*): half of the 940 warp instructions per trip were
 // divergent bookkeeping, led by the per-phase propagation switch (stance / flight-after-stance / reverse flight /
 // reverse stance executed one after the other, 177 instructions at 5-14 active lanes).
 //
