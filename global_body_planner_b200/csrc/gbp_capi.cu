@@ -854,8 +854,13 @@ int gbp_tree_read(const gbp_tree *T, int first, int n, double *states, double *a
 int gbp_nearest_dev(const gbp_tree *T, int64_t m, const double *queries, int *idx, double *dist, void *stream) {
 	if (!T || m < 0 || (m && (!queries || !idx))) return fail(GBP_E_INVALID, "bad arguments");
 	if (m == 0) return GBP_OK;
-	unsigned grid = (unsigned) (m < 65535 ? m : 65535);
-	k_nearest<<<grid, 256, 0, (cudaStream_t) stream>>>(T->view, m, queries, idx, dist);
+	if (m >= 4 * (int64_t) sm_count()) {  // enough queries to fill the GPU with 4-query tiles
+		const int64_t tiles = (m + 3) / 4;
+		k_nearest_tiled<4><<<(unsigned) (tiles < 65535 ? tiles : 65535), 256, 0, (cudaStream_t) stream>>>(T->view, m, queries, idx, dist);
+	} else {
+		unsigned grid = (unsigned) (m < 65535 ? m : 65535);
+		k_nearest<<<grid, 256, 0, (cudaStream_t) stream>>>(T->view, m, queries, idx, dist);
+	}
 	CU(cudaGetLastError());
 	return GBP_OK;
 }

@@ -795,6 +795,59 @@ __global__ void __launch_bounds__(256) k_nearest(TreeView T, int64_t m, const do
 		__syncthreads();
 	}
 }
+// Many queries against one tree: QT queries per CTA pass, so a vertex is loaded once for QT distance evaluations
+// (the one-query form moves 64 B per 24 flop and sits at 41 % of the fp64 issue rate; profiles/r1b_measured_nn.json).
+// Same arithmetic per (query, vertex) pair, same (distance, id) argmin: results are bit-identical to k_nearest.
+template <int QT>
+__global__ void __launch_bounds__(256) k_nearest_tiled(TreeView T, int64_t m, const double *__restrict__ queries, int *__restrict__ idx,
+														double *__restrict__ dist) {
+	__shared__ double sd[QT][8];
+	__shared__ int si[QT][8];
+	const int nv = *T.n;
+	for (int64_t q0 = (int64_t) blockIdx.x * QT; q0 < m; q0 += (int64_t) gridDim.x * QT) {
+		double q[QT][8], bd[QT];
+		int bi[QT];
+#pragma unroll
+		for (int t = 0; t < QT; ++t) {
+			const int64_t qi = min(q0 + t, m - 1);  // a partial tile repeats its last query (results of the repeats are not written)
+#pragma unroll
+			for (int d = 0; d < 8; ++d) q[t][d] = queries[8 * qi + d];
+			bd[t] = INFINITY;
+			bi[t] = 0x7fffffff;
+		}
+		for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+			double v[8];
+#pragma unroll
+			for (int d = 0; d < 8; ++d) v[d] = T.v[(size_t) d * T.cap + j];
+#pragma unroll
+			for (int t = 0; t < QT; ++t) {
+				double sum = 0;
+#pragma unroll
+				for (int d = 0; d < 8; ++d) sum = sum + 1.0 * (v[d] - q[t][d]) * (v[d] - q[t][d]);
+				argmin_combine(bd[t], bi[t], sqrt(sum), j);
+			}
+		}
+#pragma unroll
+		for (int t = 0; t < QT; ++t) {
+			warp_argmin(bd[t], bi[t]);
+			if ((threadIdx.x & 31) == 0) { sd[t][threadIdx.x >> 5] = bd[t]; si[t][threadIdx.x >> 5] = bi[t]; }
+		}
+		__syncthreads();
+		if (threadIdx.x < 32) {
+#pragma unroll
+			for (int t = 0; t < QT; ++t) {
+				double d = threadIdx.x < (blockDim.x >> 5) ? sd[t][threadIdx.x] : INFINITY;
+				int i = threadIdx.x < (blockDim.x >> 5) ? si[t][threadIdx.x] : 0x7fffffff;
+				warp_argmin(d, i);
+				if (threadIdx.x == 0 && q0 + t < m) {
+					idx[q0 + t] = i == 0x7fffffff ? 0 : i;  // reference default index 0 (planner_class.cpp:186)
+					if (dist) dist[q0 + t] = d;
+				}
+			}
+		}
+		__syncthreads();
+	}
+}
 // neighborhoodDist (planner_class.cpp:173-182): one warp, ballot/popc compaction keeps ascending ids
 __global__ void k_near(TreeView T, const double *__restrict__ query, double radius, int *__restrict__ ids, int cap,
 					   int *__restrict__ count) {

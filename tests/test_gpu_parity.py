@@ -315,3 +315,23 @@ def test_csv_ingest(gbp, dev, tmp_path):
         assert_bits_equal(h2, h3, what="height via CSV -> GridMap")
     with pytest.raises(gbp.GbpError):
         gbp.Terrain.from_csv(str(tmp_path / "missing"))
+
+
+def test_nearest_many_queries_tiled(gbp, dev):
+    """enough queries to take the 4-queries-per-pass kernel (k_nearest_tiled), with a ragged last tile and exact ties"""
+    t, o, T, G, _ = dev
+    verts = G["nn_verts"].copy()
+    verts[700] = verts[3]; verts[1200] = verts[3]          # duplicated states: the lowest id must win (Appendix B-4)
+    rng = np.random.default_rng(1)
+    q = np.concatenate([G["vs_states"][:1001], verts[[3, 700, 9]]])   # 1004 queries + exact hits
+    q = q[: 1003]                                           # not a multiple of 4
+    tree = gbp.Tree(2048)
+    tree.load(verts)
+    gi, gd = tree.nearest(q)
+    oi, od, uniq = o.nearest(verts, q)
+    assert_bits_equal(gd, od, what="nearest distance")
+    assert (gi[uniq == 1] == oi[uniq == 1]).all()
+    d_all = np.sqrt(((verts[None, :, :] - q[:, None, :]) ** 2).sum(-1))
+    assert (gi == d_all.argmin(1)).all() or (gd == d_all.min(1)).all()   # ties resolved to the lowest id
+    hit = np.nonzero((q == verts[3]).all(1))[0]
+    assert len(hit) >= 1 and (gi[hit] == 3).all()
