@@ -163,3 +163,29 @@ def test_device_pointer_call_and_alignment(gbp, env):
     assert_bits_equal(dtn.cpu().numpy(), tno, what="t_new (device call)")
     with pytest.raises(gbp.GbpError, match="aligned"):
         t.validate_pairs_dev(n - 1, ds.data_ptr() + 8, da.data_ptr(), dd.data_ptr(), 0, 0, dv.data_ptr(), df.data_ptr(), dsn.data_ptr(), dtn.data_ptr(), 0)
+
+
+@pytest.mark.parametrize("n", [1, 17, 1000, 33333])
+def test_no_write_outside_the_outputs(gbp, env, n):
+    """guard bands around every output buffer of the device-pointer call stay untouched (compute-sanitizer is not
+    available on the GPU pool: this is the bounds check the kernels get)"""
+    import torch
+    t, o, T = env
+    s, a, d = candidates(o, n, seed=37)
+    dev = torch.device("cuda:0")
+    pad = 4096  # bytes, keeps the 16-byte alignment the TMA copies need
+    def guarded(nbytes):
+        buf = torch.full((pad + nbytes + pad,), 0xA5, dtype=torch.uint8, device=dev)
+        return buf, buf.data_ptr() + pad
+    ds, da, dd = torch.from_numpy(s).to(dev), torch.from_numpy(a).to(dev), torch.from_numpy(d).to(dev)
+    bufs = {k: guarded(sz) for k, sz in (("v", n), ("f", n), ("sn", 64 * n), ("tn", 8 * n))}
+    for adaptive in (0, 1):
+        t.validate_pairs_dev(n, ds.data_ptr(), da.data_ptr(), dd.data_ptr(), adaptive, 0, bufs["v"][1], bufs["f"][1], bufs["sn"][1], bufs["tn"][1], 0)
+        torch.cuda.synchronize()
+        for k, (buf, _) in bufs.items():
+            h = buf.cpu().numpy()
+            assert (h[:pad] == 0xA5).all() and (h[-pad:] == 0xA5).all(), f"{k}: guard band overwritten"
+        vo, fo, sno, tno, _ = o.validate_pairs(s, a, d, adaptive=bool(adaptive))
+        assert (bufs["v"][0].cpu().numpy()[pad:pad + n] == vo).all()
+        sn = bufs["sn"][0].cpu().numpy()[pad:pad + 64 * n].view(np.float64).reshape(n, 8)
+        assert_bits_equal(sn, sno, what="s_new")
