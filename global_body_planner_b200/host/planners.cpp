@@ -287,6 +287,12 @@ void RRTConnectClass::runRRTConnect(PlannerClass &Ta, PlannerClass &Tb, FastTerr
 // post-processed path so far is kept.  Same termination rule and statistics as the reference.
 void RRTConnectClass::buildRRTConnect(FastTerrainMap &terrain, State s_start, State s_goal, std::vector<State> &state_sequence,
 									  std::vector<Action> &action_sequence, double max_time_opt) {
+	buildAnytime(terrain, s_start, s_goal, state_sequence, action_sequence, max_time_opt, false);
+}
+// star = true: every attempt is an RRT*-Connect search (choose parent + near-set rewiring on the device,
+// rrt_star_connect.cpp:12-75); otherwise RRT-Connect.
+void RRTConnectClass::buildAnytime(FastTerrainMap &terrain, State s_start, State s_goal, std::vector<State> &state_sequence,
+								   std::vector<Action> &action_sequence, double max_time_opt, bool star) {
 	const auto t0 = Clock::now();
 	success_ = 0;
 	length_vector_.clear(); yaw_vector_.clear(); cost_vector_.clear(); cost_vector_times_.clear();
@@ -298,7 +304,7 @@ void RRTConnectClass::buildRRTConnect(FastTerrainMap &terrain, State s_start, St
 	// anytime use of the batch planner: all attempts work on the same query, the round ends once 8 of them have solved
 	// (the 8 shortest raw paths are shortcut below)
 	gbp_plan_params P = {k_candidates_, best_of_k_ ? 1 : 0, iterations_per_attempt_, vertices_per_tree_,
-						 state_action_pair_check_adaptive_step_size_flag_ ? 1 : 0, 0, 0, 8};
+						 state_action_pair_check_adaptive_step_size_flag_ ? 1 : 0, star ? 1 : 0, 0, 8};
 	std::vector<State> starts(R, s_start), goals(R, s_goal);
 	std::vector<gbp_plan_stats> stats(R);
 	std::vector<double> ps((size_t) R * cap * 8), pa((size_t) R * cap * 10);
@@ -308,7 +314,7 @@ void RRTConnectClass::buildRRTConnect(FastTerrainMap &terrain, State s_start, St
 	for (std::uint64_t round = 0;; ++round) {
 		P.stop_after_solved = goal_found ? 8 : 1;  // until a first solution exists the round ends with the first attempt that solves
 		check(gbp_plan_batch(terrain.handle(), R, starts[0].data(), goals[0].data(), seed_, (stream_ << 20) + round * (std::uint64_t) R, &P,
-							 stats.data(), ps.data(), pa.data(), cap), "buildRRTConnect");
+							 stats.data(), ps.data(), pa.data(), cap), star ? "buildRRTStarConnect" : "buildRRTConnect");
 		std::vector<int> solved;
 		for (int i = 0; i < R; ++i) {
 			num_vertices += stats[i].nv_a + stats[i].nv_b;
@@ -424,55 +430,13 @@ void RRTStarConnectClass::getStateAndActionSequences(PlannerClass &Ta, PlannerCl
 	action_sequence.insert(action_sequence.end(), actions_b.begin(), actions_b.end());
 }
 
-// rrt_star_connect.cpp:100-226 (host-driven loop; the reference never exits before a goal is found — here
-// max_time_solve bounds it as in buildRRTConnect).
+// rrt_star_connect.cpp:100-226.  Like buildRRTConnect, re-designed for the GPU: every round runs `parallel_attempts_`
+// independent RRT*-Connect searches resident on the device (gbp_plan_batch with rrt_star = 1: choose parent and
+// near-set rewiring inside the kernel) and the cheapest post-processed path so far is kept; the reference's loop never
+// exits before a goal is found, here max_time_solve bounds it.  (The single-tree loop driven call by call from the
+// host — extend() above is still available to callers — manages ~1 k iterations/s and does not solve the shipped maps.)
 void RRTStarConnectClass::buildRRTStarConnect(FastTerrainMap &terrain, State s_start, State s_goal, std::vector<State> &state_sequence,
 											  std::vector<Action> &action_sequence, double max_time) {
-	const auto t0 = Clock::now();
-	success_ = 0;
-	length_vector_.clear(); yaw_vector_.clear(); cost_vector_.clear(); cost_vector_times_.clear();
-	PlannerClass Ta, Tb;
-	Ta.init(s_start, cost_add_yaw_flag_, cost_add_yaw_length_weight_, cost_add_yaw_yaw_weight_);
-	Tb.init(s_goal, cost_add_yaw_flag_, cost_add_yaw_length_weight_, cost_add_yaw_yaw_weight_);
-	int shared_a_idx = -1, shared_b_idx = -1;
-	std::vector<int> shared_a, shared_b;
-	goal_found = false;
-	double cost_so_far = INFTY;
-	while (true) {
-		for (int half = 0; half < 2; ++half) {
-			PlannerClass &Tx = half == 0 ? Ta : Tb, &Ty = half == 0 ? Tb : Ta;
-			State s_rand = Tx.randomState(terrain);
-			if (!isValidState(s_rand, terrain, STANCE)) continue;
-			if (extend(Tx, s_rand, terrain, half == 0 ? FORWARD : REVERSE) == TRAPPED) continue;
-			State s_new = Tx.getVertex(Tx.getNumVertices() - 1);
-			if (connect(Ty, s_new, terrain, half == 0 ? REVERSE : FORWARD) == REACHED) {
-				if (!goal_found) elapsed_to_first = Clock::now() - t0;
-				goal_found = true;
-				shared_a.push_back(Ta.getNumVertices() - 1);
-				shared_b.push_back(Tb.getNumVertices() - 1);
-			}
-		}
-		for (size_t i = 0; i < shared_a.size(); ++i) {  // cheapest junction so far (:175-197)
-			const double cost = Ta.getGValue(shared_a[i]) + Tb.getGValue(shared_b[i]);
-			if (cost < cost_so_far) {
-				cost_so_far = cost;
-				shared_a_idx = shared_a[i];
-				shared_b_idx = shared_b[i];
-				length_vector_.push_back(cost);
-				yaw_vector_.push_back(Ta.getYValue(shared_a[i]) + Tb.getYValue(shared_b[i]));
-				cost_vector_.push_back(cost);
-				cost_vector_times_.push_back(seconds_since(t0));
-			}
-		}
-		const double elapsed = seconds_since(t0);
-		if ((goal_found && elapsed >= max_time) || elapsed >= max_time_solve_) break;
-	}
-	num_vertices = Ta.getNumVertices() + Tb.getNumVertices();
-	elapsed_total = Clock::now() - t0;
-	if (!goal_found) { std::cout << "Path not found" << std::endl; return; }
-	getStateAndActionSequences(Ta, Tb, shared_a_idx, shared_b_idx, state_sequence, action_sequence);
-	postProcessPath(state_sequence, action_sequence, terrain);
-	if (elapsed_total.count() <= 5.0) success_ = 1;
-	path_duration_ = 0.0;
-	for (const Action &a : action_sequence) path_duration_ += a[6] + a[7];
+	buildAnytime(terrain, s_start, s_goal, state_sequence, action_sequence, max_time, true);
+	if (!goal_found) std::cout << "Path not found" << std::endl;
 }

@@ -27,6 +27,9 @@ public:
 	void set_max_time_solve(double seconds);  // hard stop (the reference's constant max_time_solve, :119-120)
 
 protected:
+	// shared by buildRRTConnect and RRTStarConnectClass::buildRRTStarConnect
+	void buildAnytime(FastTerrainMap &terrain, State s_start, State s_goal, std::vector<State> &state_sequence,
+					  std::vector<Action> &action_sequence, double max_time, bool star);
 	double anytime_horizon = 0;
 	const double planning_rate_estimate = 16.0;
 	double anytime_horizon_init = 0;

@@ -162,3 +162,28 @@ def test_call_planner_driver(tmp_path):
     # geometric length of the discrete plan cannot be below the straight line
     assert float(summ["avg_path_length"]) > 0
     assert o.distance(ss[:-1], ss[1:], 0).sum() >= 8.0 - 1e-9
+
+
+def test_call_planner_driver_rrt_star(tmp_path):
+    """the same driver with algorithm = rrt-star-connect (device-resident RRT*-Connect attempts, rrt_star_connect.cpp)"""
+    import __graft_entry__ as entry
+    entry.build()
+    T = load_terrain("slope")
+    o = po.Oracle(T)
+    d = str(tmp_path / "slope")
+    write_csv_dir(T, d)
+    exe = os.path.join(ROOT, "global_body_planner_b200", "gbp_plan")
+    disc = str(tmp_path / "disc.csv")
+    r = subprocess.run([exe, d, "--height", "0.30", "--algorithm", "rrt-star-connect", "--num-calls", "1", "--replan-time-limit", "0.2",
+                        "--max-time-solve", "40", "--discrete-out", disc, "--quiet"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    rows = np.loadtxt(disc, delimiter=",", ndmin=2)
+    assert len(rows) >= 2, "no RRT*-Connect plan for the slope query within 40 s"
+    ss, aa = rows[:, :8], rows[:-1, 8:]
+    end = o.apply_flight(o.apply_stance(ss[:-1], aa, aa[:, 6]), aa[:, 7])
+    assert np.abs(end - ss[1:]).max() < 1e-9
+    vf = o.validate_pairs(ss[:-1], aa, np.zeros(len(aa), np.uint8))[0]
+    vr = o.validate_pairs(ss[1:], aa, np.ones(len(aa), np.uint8))[0]
+    assert ((vf == 1) | (vr == 1)).all()
+    bad = subprocess.run([exe, d, "--algorithm", "a-star"], capture_output=True, text=True, timeout=60)
+    assert bad.returncode == 1 and "Invalid algorithm specified" in bad.stderr
