@@ -136,10 +136,24 @@ __device__ __forceinline__ bool group_validate(const TerrainView &Tv, const doub
 	return state == 2;
 }
 
+// How the 32 lanes split over the K candidates of an extend (fixed for a launch, computed once per kernel: the runtime
+// integer divisions are out-of-line subroutines, and far jumps are what this kernel stalls on).
+struct GroupMap { int S, G, g, r, gshift; unsigned gmask; };
+__device__ __forceinline__ GroupMap make_group_map(int K, int lane) {
+	GroupMap m;
+	m.S = K >= 32 ? 1 : 32 / K;
+	m.G = 32 / m.S;
+	m.g = lane / m.S;
+	m.r = lane - m.g * m.S;
+	m.gshift = m.g * m.S;
+	m.gmask = m.S == 32 ? FULL : ((1u << m.S) - 1u);
+	return m;
+}
+
 // newConfig (rrt.cpp:20-70) generalised to K candidates; uniform outputs.  Returns found.
 template <typename M>
 __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const double s_near[8], int dir, uint64_t seed, uint64_t query,
-								uint64_t cell, const gbp_plan_params &P, int lane, long long &pair_checks, double s_new[8], double a_new[10]) {
+								uint64_t cell, const gbp_plan_params &P, const GroupMap &gm, int lane, long long &pair_checks, double s_new[8], double a_new[10]) {
 	double nn[3], R[9];
 	const double best0 = state_distance(s_near, s);
 	unsigned fl = 0;
@@ -150,9 +164,8 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 	int my_j = 0x7fffffff, first = 0x7fffffff;
 	if (!P.adaptive) {
 		// speculative form: G candidates per pass, S lanes each
-		const int S = K >= 32 ? 1 : 32 / K, G = 32 / S;
-		const int g = lane / S, r = lane - g * S, gshift = g * S;
-		const unsigned gmask = S == 32 ? FULL : ((1u << S) - 1u);
+		const int S = gm.S, G = gm.G, g = gm.g, r = gm.r, gshift = gm.gshift;
+		const unsigned gmask = gm.gmask;
 		for (int base = 0; base < K; base += G) {
 			const int j = base + g;
 			const bool has = g < G && j < K;
@@ -173,7 +186,7 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 			}
 			if (!P.best_of_k) {
 				const unsigned m = __ballot_sync(FULL, ok && r == 0);
-				if (m) { first = base + (__ffs(m) - 1) / S; break; }  // first valid action decides (rrt.cpp:44-47)
+				if (m) { first = base + __shfl_sync(FULL, g, __ffs(m) - 1); break; }  // first valid action decides (rrt.cpp:44-47): the group of the lowest set lane
 			}
 		}
 	} else {
@@ -238,11 +251,11 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 // RRTClass::extend (rrt.cpp:77-102)
 template <typename M>
 __device__ int warp_extend(const TerrainView &Tv, PlanTree &T, int &nv, const double s[8], int dir, uint64_t seed, uint64_t query,
-						   uint64_t cell, const gbp_plan_params &P, int lane, long long &pair_checks) {
+						   uint64_t cell, const gbp_plan_params &P, const GroupMap &gm, int lane, long long &pair_checks) {
 	const int near = warp_nearest(T.t, nv, s, lane);
 	double s_near[8], sn[8], a[10];
 	tree_get(T.t, near, s_near);
-	if (!warp_new_config<M>(Tv, s, s_near, dir, seed, query, cell, P, lane, pair_checks, sn, a)) return GBP_TRAPPED;
+	if (!warp_new_config<M>(Tv, s, s_near, dir, seed, query, cell, P, gm, lane, pair_checks, sn, a)) return GBP_TRAPPED;
 	if (lane == 0) plan_push(T, near, sn, a);
 	__syncwarp();
 	nv += 1;
@@ -252,11 +265,11 @@ __device__ int warp_extend(const TerrainView &Tv, PlanTree &T, int &nv, const do
 // RRTStarConnectClass::extend (rrt_star_connect.cpp:12-75)
 template <typename M>
 __device__ int warp_extend_star(const TerrainView &Tv, PlanTree &T, int &nv, const double s[8], int dir, uint64_t seed, uint64_t query,
-								uint64_t cell, const gbp_plan_params &P, const PlanArena &A, int slot, int lane, long long &pair_checks) {
+								uint64_t cell, const gbp_plan_params &P, const GroupMap &gm, const PlanArena &A, int slot, int lane, long long &pair_checks) {
 	const int nearest = warp_nearest(T.t, nv, s, lane);
 	double s_nearest[8], s_new[8], a_new[10];
 	tree_get(T.t, nearest, s_nearest);
-	if (!warp_new_config<M>(Tv, s, s_nearest, dir, seed, query, cell, P, lane, pair_checks, s_new, a_new)) return GBP_TRAPPED;
+	if (!warp_new_config<M>(Tv, s, s_nearest, dir, seed, query, cell, P, gm, lane, pair_checks, s_new, a_new)) return GBP_TRAPPED;
 	const int id = nv;
 	if (lane == 0) {  // addVertex (:22)
 		*T.t.n = id + 1;
@@ -431,6 +444,7 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 	const int64_t slot = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
 	unsigned long long *next_query = (unsigned long long *) (counts + 2 * (((int64_t) gridDim.x * blockDim.x) >> 5));
 	volatile int *solved_count = (volatile int *) (next_query + 1);  // anytime use: queries solved so far in this launch
+	const GroupMap gm = make_group_map(P.k_candidates, lane);
 	while (true) {
 		// queries differ widely in iterations: warps pull the next query from a device counter (no static round-robin tail)
 		unsigned long long grabbed = 0;
@@ -475,8 +489,8 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 #pragma unroll
 				for (int d = 0; d < 8; ++d) s_rand[d] = __shfl_sync(FULL, rs[d], src);
 				++nn_queries;
-				const int r = STAR ? warp_extend_star<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, A, (int) slot, lane, pair_checks)
-								   : warp_extend<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, lane, pair_checks);
+				const int r = STAR ? warp_extend_star<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, gm, A, (int) slot, lane, pair_checks)
+								   : warp_extend<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, gm, lane, pair_checks);
 				if (r == GBP_TRAPPED) continue;
 				double s_new[8];
 				tree_get(Tx.t, nx - 1, s_new);

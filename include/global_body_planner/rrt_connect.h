@@ -35,7 +35,7 @@ protected:
 	double anytime_horizon_init = 0;
 	double horizon_expansion_factor = 1.2;
 	const int max_time_solve = 4000;
-	int parallel_attempts_ = 2368, iterations_per_attempt_ = 8000, vertices_per_tree_ = 2048;  // one wave of warps on 148 SMs; trees as large as the reference's solves (1-2 k vertices)
+	int parallel_attempts_ = 3552, iterations_per_attempt_ = 8000, vertices_per_tree_ = 2048;  // one wave of warps on 148 SMs (24 per SM); trees as large as the reference's solves (1-2 k vertices)
 	double max_time_solve_ = 4000;
 };
 
