@@ -228,24 +228,36 @@ int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const d
 	for (int i = 0; i < nx && v.uniform; ++i) if (fabs(x[i] - (x[0] + i * v.step_x)) > 1e-12) v.uniform = 0;
 	for (int i = 0; i < ny && v.uniform; ++i) if (fabs(y[i] - (y[0] + i * v.step_y)) > 1e-12) v.uniform = 0;
 	bool has_nan = false;
-	for (size_t i = 0; i < cells && !has_nan; ++i) has_nan = z[i] != z[i];
-	v.mixed_ok = (v.uniform && v.cell_f32 && !has_nan && v.step_x >= 0.01 && v.step_y >= 0.01 && !getenv("GBP_NO_MIXED")) ? 1 : 0;
+	double zmax = 0.0;
+	for (size_t i = 0; i < cells; ++i) {
+		if (z[i] != z[i]) { has_nan = true; break; }
+		if (fabs(z[i]) > zmax) zmax = fabs(z[i]);
+	}
+	bool mixed = v.uniform && !has_nan && v.step_x >= 0.01 && v.step_y >= 0.01 && !getenv("GBP_NO_MIXED");
 	{  // farthest a leg / corner / belly probe can be from the centre: sqrt(0.15^2 + 0.15^2) + 0.05 < 0.27 m
 		const double step = v.step_x < v.step_y ? v.step_x : v.step_y;
 		v.border = (int) std::ceil(0.27 / step) + 1;
-		if (nx < 16 * v.border || ny < 16 * v.border) v.mixed_ok = 0;  // border zone too large a share: fp64 walk throughout
+		if (nx < 4 * v.border + 2 || ny < 4 * v.border + 2) mixed = false;  // hardly any interior: fp64 walk throughout
 	}
-	if (v.mixed_ok && nx <= 32768 && ny <= 32768 && !getenv("GBP_NO_TEX")) {
+	// The mixed evaluator decides only sub-states whose margins exceed 1e-5 m, so it may read heights ROUNDED to fp32 as
+	// long as the rounding stays inside its error budget: |z| <= 4 m keeps it below 2.4e-7 m per cell.  fp64 maps (the
+	// shipped CSV maps: 0.1 m steps are not fp32 numbers) therefore get the mixed walk too — through the texture copy
+	// only; everything exact (lookups, fp64 evaluator, outputs) keeps reading the fp64 grid.
+	const bool rounded_copy = !v.cell_f32 && mixed && zmax <= 4.0;
+	v.mixed_ok = (mixed && v.cell_f32) ? 1 : 0;
+	if ((v.mixed_ok || rounded_copy) && nx <= 32768 && ny <= 32768 && !getenv("GBP_NO_TEX")) {
 		// the mixed-precision walk fetches each probe's 2x2 cells with one texture gather: needs a CUDA array created
-		// with the gather flag (array x = iy, array y = ix).  Optional: on failure the walk keeps the 4-load form.
+		// with the gather flag (array x = iy, array y = ix).  Optional for fp32 maps: on failure the walk keeps the 4-load form.
 		cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
 		cudaResourceDesc rd;
 		cudaTextureDesc td;
 		memset(&rd, 0, sizeof rd);
 		memset(&td, 0, sizeof td);
+		std::vector<float> zr;
+		if (rounded_copy) { zr.resize(cells); for (size_t i = 0; i < cells; ++i) zr[i] = (float) z[i]; }
 		if (cudaMallocArray(&t->z_arr, &fd, (size_t) ny, (size_t) nx, cudaArrayTextureGather) == cudaSuccess &&
-			cudaMemcpy2DToArray(t->z_arr, 0, 0, t->d_z, (size_t) ny * sizeof(float), (size_t) ny * sizeof(float), (size_t) nx,
-								cudaMemcpyDeviceToDevice) == cudaSuccess) {
+			cudaMemcpy2DToArray(t->z_arr, 0, 0, rounded_copy ? (const void *) zr.data() : (const void *) t->d_z, (size_t) ny * sizeof(float),
+								(size_t) ny * sizeof(float), (size_t) nx, rounded_copy ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice) == cudaSuccess) {
 			rd.resType = cudaResourceTypeArray;
 			rd.res.array.array = t->z_arr;
 			td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
@@ -256,6 +268,7 @@ int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const d
 		}
 		if (!v.ztex && t->z_arr) { cudaFreeArray(t->z_arr); t->z_arr = nullptr; }
 		(void) cudaGetLastError();
+		if (rounded_copy && v.ztex) v.mixed_ok = 1;
 	}
 	*out = t;
 	return GBP_OK;
@@ -606,8 +619,12 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 			if (t->view.ztex) { if (adaptive) GBP_WALK_(true, true); else GBP_WALK_(true, false); }
 			else { if (adaptive) GBP_WALK_(false, true); else GBP_WALK_(false, false); }
 #undef GBP_WALK_
-			k_validate_redo<MapF32U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
-																   flags, s_new, t_new, t->d_cnt);
+			if (t->view.cell_f32)
+				k_validate_redo<MapF32U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
+																	   flags, s_new, t_new, t->d_cnt);
+			else
+				k_validate_redo<MapF64U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
+																	   flags, s_new, t_new, t->d_cnt);
 		} else {
 #define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt))
 			if (t->view.cell_f32) { if (t->view.uniform) GBP_WALK_(MapF32U); else GBP_WALK_(MapF32N); }

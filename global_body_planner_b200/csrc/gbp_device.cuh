@@ -29,7 +29,7 @@ struct TerrainView {
 	int cell_f32;
 	double x0, y0, x_last, y_last;  // axis end points (bounds test of isValidState, OOG test)
 	double inv_dx, inv_dy;          // O(1) cell guess: i ~ (v - x0) * inv_dx
-	int mixed_ok;                   // fp32 cells without NaN, uniform axes, cell pitch >= 1 cm: the mixed-precision evaluator applies
+	int mixed_ok;                   // no NaN, uniform axes, cell pitch >= 1 cm, fp32 cells or an fp32-rounded texture copy (|z| <= 4 m): the mixed-precision evaluator applies
 	int border;                     // cells a body probe can lie from the centre's cell (0.23 m / pitch, rounded up, + 1)
 	int uniform;                    // both axes are x0 + i*step to within 1e-12 m: the fast path computes cell edges
 	double step_x, step_y;          // instead of loading them (a probe within 1e-11 m of a grid line is flagged NEAR)
@@ -514,7 +514,8 @@ __device__ __forceinline__ bool is_valid_state_fast(const TerrainView &T, const 
 	return replay_checks(pb, pre_bad, speed_bad, phase == GBP_STANCE, leg_m, cor_m, belly_m, NEAR_MARGIN, c);
 }
 // =====================================================================================================
-// Mixed-precision evaluator (fp32 cells on uniform axes).  Same contract as is_valid_state_fast, one more
+// Mixed-precision evaluator (uniform axes; fp32 cells, or fp64 cells read through their fp32-rounded texture copy: that
+// rounding, <= 2.4e-7 m for |z| <= 4 m, is part of the error budget below).  Same contract as is_valid_state_fast, one more
 // level of the same idea: the centre cell and its in-cell fraction are found in fp64, everything that is a
 // SMALL offset from it (body rotation, the 9 leg / corner / belly offsets in cell units, the bilinear
 // increment over the cell's first corner) is fp32 on the full-rate FMA pipe, and each clearance margin is
@@ -647,11 +648,12 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 // the evaluator every kernel calls
 template <typename M>
 __device__ __forceinline__ bool is_valid_state_auto(const TerrainView &T, const Pose6 &s, int phase, Counters &c) {
-	if (M::uniform && sizeof(typename M::cell) == 4) {
+	if (M::uniform) {
 		bool valid;
-		// texture-gather fetch when the handle carries the block-linear copy (ztex implies mixed_ok): +13 % plans/s in k_plan_batch
+		// texture-gather fetch when the handle carries the block-linear fp32 copy (ztex implies mixed_ok; for fp64 maps it is
+		// the only mixed form: the copy holds the heights rounded to fp32): +13 % plans/s in k_plan_batch
 		if (T.ztex) { if (is_valid_state_mixed<M, true>(T, s, phase, c, valid)) return valid; }
-		else if (T.mixed_ok && is_valid_state_mixed<M>(T, s, phase, c, valid)) return valid;
+		else if (sizeof(typename M::cell) == 4 && T.mixed_ok && is_valid_state_mixed<M>(T, s, phase, c, valid)) return valid;
 	}
 	return is_valid_state_fast<M>(T, s, phase, c);
 }

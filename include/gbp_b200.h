@@ -83,7 +83,9 @@ int gbp_terrain_create_csv(const char *directory, int via_gridmap, gbp_terrain *
 void gbp_terrain_destroy(gbp_terrain *t);
 int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes);
 /* which evaluator serves this terrain: uniform_axes = cell edges are computed, not loaded; mixed_precision = the
- * fp32-around-fp64 evaluator applies (fp32 cells, no NaN, uniform axes, pitch >= 1 cm, interior >> border) */
+ * fp32-around-fp64 evaluator applies (no NaN, uniform axes, pitch >= 1 cm, an interior beyond the border zone, and either
+ * fp32 cells or — for fp64 maps with |z| <= 4 m — an fp32-rounded texture copy whose rounding is inside the evaluator's
+ * guard band; sub-states it cannot decide are re-evaluated in fp64 on the exact grid) */
 int gbp_terrain_flags(const gbp_terrain *t, int *uniform_axes, int *mixed_precision);
 /* Environment switches read at terrain creation / launch, for A/B measurements only (results are identical):
  * GBP_NO_MIXED=1 keeps the fp64 evaluator on every terrain, GBP_NO_TEX=1 the 4-load fetch, GBP_NO_L2_WINDOW=1 drops the
