@@ -189,3 +189,32 @@ def test_no_write_outside_the_outputs(gbp, env, n):
         assert (bufs["v"][0].cpu().numpy()[pad:pad + n] == vo).all()
         sn = bufs["sn"][0].cpu().numpy()[pad:pad + 64 * n].view(np.float64).reshape(n, 8)
         assert_bits_equal(sn, sno, what="s_new")
+
+
+def test_fp64_map_through_rounded_texture_copy(gbp):
+    """fp64 heights that are not fp32 numbers (the shipped CSV maps' class), lifted to 3.9 m where the fp32 rounding of
+    the texture copy is largest (2.4e-7 m): the mixed walk applies and every result still equals the oracle's; above
+    4 m the rounded copy is not used at all."""
+    T0 = load_terrain("synth_mixed")
+    rng = np.random.default_rng(3)
+    z = T0.z + 3.83 + rng.uniform(0, 1e-6, T0.z.shape)       # no longer fp32-representable
+    assert (z.astype(np.float32).astype(np.float64) != z).mean() > 0.9 and np.abs(z).max() < 4.0
+    T = po.Terrain(T0.x, T0.y, z, T0.dx, T0.dy, T0.dz)
+    t = gbp.Terrain(T.x, T.y, T.z, T.dx, T.dy, T.dz)
+    assert t.cell_bytes == 8 and t.flags()["mixed_precision"] and t.flags()["texture_gather"]
+    o = po.Oracle(T)
+    s, a, d = candidates(o, 30000, seed=41)
+    for adaptive in (False, True):
+        check(gbp, t, o, s, a, d, adaptive=adaptive)
+    # near-threshold poses: body heights swept in 1e-7 m steps across the belly-clearance and leg-reach limits
+    q = s[:2000].copy()
+    h = o.ground_height(q[:, 0], q[:, 1])[0]
+    q[:, 3:] = 0; q[:, 3] = 0.3
+    q[:1000, 2] = h[:1000] + 0.125 + np.arange(-500, 500) * 1e-7
+    q[1000:, 2] = h[1000:] + 0.45 + np.arange(-500, 500) * 1e-7
+    for phase in (gbp.STANCE, gbp.FLIGHT):
+        vg, fg = t.valid_states(q, phase)
+        vo, fo = o.valid_states(q, phase)
+        assert (vg == vo).all()
+    t2 = gbp.Terrain(T.x, T.y, T.z + 1.0)
+    assert not t2.flags()["mixed_precision"] and not t2.flags()["texture_gather"]
