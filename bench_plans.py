@@ -75,6 +75,42 @@ def run_rough_k4096(gbp, torch, dev, nq=7104, iters=40):
             "note": "the unmodified CPU reference completes 0 plans in 120 s on this query (BASELINE.md row 9)"}
 
 
+def run_slope_config0(gbp, rounds=8):
+    """BASELINE configs[0]: RRT-Connect on the reference's data/slope (tests/golden/terrain_slope.npz), (0,0) -> (8,0) at body
+    height 0.30 m (the fork's 0.375 m start pose is invalid on this map), default parameters.
+    Time to a first solution through the host-pointer C ABI: one gbp_plan_batch launch of 3552 attempts at the same query
+    (distinct Philox streams, 8000 iterations / 2048 vertices per tree) that stops when the first attempt has solved —
+    what RRTConnectClass::buildRRTConnect of the drop-in does in its first anytime round."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "terrain_slope.npz"))
+    t = gbp.Terrain(d["x"], d["y"], d["z"], d["dx"], d["dy"], d["dz"])
+    h, _ = t.ground_height([0.0, 8.0], [0.0, 0.0])
+    start = np.array([0, 0, h[0] + 0.30, 1, 0, 0, 0, 0.0]); goal = np.array([8, 0, h[1] + 0.30, 1, 0, 0, 0, 0.0])
+    nq = 3552
+    S, G = np.repeat(start[None], nq, 0), np.repeat(goal[None], nq, 0)
+    P = gbp.PlanParams(6, 0, 8000, 2048, 0, 0, 0, 1)
+    t.plan_batch(S[:64], G[:64], 1, 0, gbp.PlanParams(6, 0, 10, 2048, 0, 0, 0, 0))  # warm-up: sizes the tree arena
+    t.plan_batch(S, G, 1, 1 << 40, gbp.PlanParams(6, 0, 10, 2048, 0, 0, 0, 0))
+    times, solved, lengths, launches, q0 = [], 0, [], 0, nq
+    for r in range(rounds):
+        t0 = time.perf_counter()
+        for attempt_round in range(60):  # anytime rounds of one call: fresh Philox streams until an attempt solves
+            st = t.plan_batch(S, G, 1, q0, P)
+            q0 += nq
+            launches += 1
+            ok = st["solved"] == 1
+            if ok.any():
+                solved += 1
+                lengths.append(float(st["path_length"][ok].min()))
+                break
+        times.append(time.perf_counter() - t0)
+    return {"workload": f"data/slope, (0,0)->(8,0), body 0.30 m, K=6 first-valid; {rounds} independent calls; a call launches rounds of {nq} "
+                        "device-resident attempts (each round ends with its first solution) until one solves (host-pointer C ABI, wall clock)",
+            "calls": rounds, "calls_solved": solved, "rounds_launched": launches,
+            "first_solution_s": {"mean": float(np.mean(times)), "min": float(np.min(times)), "max": float(np.max(times))},
+            "raw_path_length_m_mean": float(np.mean(lengths)) if lengths else None,
+            "reference_note": "unmodified reference, 1 core (BASELINE.md row 8): first solutions after 4.6 s and 6.7 s, 2 plans in 93 s"}
+
+
 def run(gbp, torch, dist, dev, rank, world, q_per_gpu=Q_PER_GPU, cpu_seconds=8.0, want_cpu=True):
     x, y, z = rough_terrain()
     t = gbp.Terrain(x, y, z)
@@ -123,6 +159,7 @@ def run(gbp, torch, dist, dev, rank, world, q_per_gpu=Q_PER_GPU, cpu_seconds=8.0
            "mean_path_length_m": float(st["path_length"][st["solved"] == 1].mean()) if st["solved"].any() else None,
            "mean_iters": float(st["iters"].mean()), "stats_gather_bytes": int(allstats.nbytes)}
     out["rough_k4096"] = run_rough_k4096(gbp, torch, dev) if world == 1 or rank == 0 else None
+    out["slope_config0"] = run_slope_config0(gbp)
     # BASELINE configs[2]: RRT*-Connect (choose parent + near-set rewiring, delta = 3 m, rrt_star_connect.cpp:12-75) with
     # postProcessPath, on the first queries of the same set; iteration budget instead of the wall-clock budget
     ns, star_iters = min(nq, 2048), 400
