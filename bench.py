@@ -50,6 +50,8 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
         self.th = None
+        self.ready = threading.Event()   # NVML is initialised and the loop is running
+        self.recording = False           # samples count only while the timed region is open
 
     def _run(self):
         try:
@@ -59,23 +61,35 @@ class ClockSampler:
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                      0x80: "hw_power_brake", 0x2: "applications_clocks", 0x10: "sync_boost"}
+            self.ready.set()
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.01)
+                if self.recording:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(0.002)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
+            self.ready.set()
 
-    def __enter__(self):
+    def start(self):
+        """spin the sampling thread up BEFORE the timed region (NVML initialisation takes longer than a short run)"""
         self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
+        self.ready.wait(timeout=10)
+        return self
+
+    def __enter__(self):
+        if self.th is None:
+            self.start()
+        self.recording = True
         return self
 
     def __exit__(self, *a):
+        self.recording = False
         self.stop_flag = True
         self.th.join(timeout=2)
 
@@ -258,6 +272,7 @@ def main():
         t.validate_pairs_dev(n, states.data_ptr(), actions.data_ptr(), direction.data_ptr(), 0, args.variant, verdict.data_ptr(),
                              flags.data_ptr(), s_new.data_ptr(), t_new.data_ptr(), torch.cuda.current_stream().cuda_stream)
 
+    sampler = ClockSampler(local_rank).start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -265,7 +280,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    with ClockSampler(local_rank) as clk:
+    with sampler as clk:
         ev[0].record()
         for i in range(args.steps):
             step()
