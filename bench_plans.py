@@ -69,7 +69,24 @@ def run_rough_k4096(gbp, torch, dev, nq=7104, iters=40):
     torch.cuda.synchronize()
     secs = e0.elapsed_time(e1) * 1e-3
     st = dstats.cpu().numpy().view(gbp.PLAN_STATS_DTYPE)
+    # ONE search driven extend by extend through the host-pointer call (gbp_extend: nearest neighbour, 4096 candidates
+    # sampled and validated in-kernel, selection and append on the device; 64 B in, 16 B out per call)
+    tree = gbp.Tree(8192, start)
+    targets = t.sample_states(5, 77, 0, 4000)
+    targets = targets[t.valid_states(targets, gbp.STANCE)[0] == 1][:600]
+    for i in range(20):
+        tree.extend(t, targets[i], gbp.FORWARD, 4096, 1, 5, 78, i * 4096)
+    t0 = time.perf_counter()
+    added = 0
+    for i in range(20, len(targets)):
+        stt, nid, chk = tree.extend(t, targets[i], gbp.FORWARD, 4096, 1, 5, 78, i * 4096)
+        added += int(stt != gbp.TRAPPED)
+    dt_single = time.perf_counter() - t0
+    n_ext = len(targets) - 20
+    single = {"extends_per_s": n_ext / dt_single, "validated_actions_per_s": n_ext * 4096 / dt_single, "us_per_extend": dt_single / n_ext * 1e6,
+              "extends": n_ext, "vertices_added": added, "api": "gbp_extend (host pointers, one synchronous call per extend)"}
     return {"workload": f"{nq} searches on data/rough_terrain, (0,0)->(8,0), K=4096 closest-valid candidates per extend, {iters} iterations",
+            "single_search": single,
             "validated_actions_per_s": float(st["pair_checks"].sum() / secs), "extends_per_s": float(st["nn_queries"].sum() / 2 / secs),
             "solved": int(st["solved"].sum()), "solved_plans_per_s": float(st["solved"].sum() / secs), "seconds": secs,
             "note": "the unmodified CPU reference completes 0 plans in 120 s on this query (BASELINE.md row 9)"}
