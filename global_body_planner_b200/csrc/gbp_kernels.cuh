@@ -650,7 +650,8 @@ __global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int 
 // no divergence beyond the 4 recipe kinds; streaming loads / stores.  Latency-bound on the exact fp64 divisions of
 // applyStance (8 per candidate).  Measured and rejected: staging the rows through shared memory with cp.async.bulk
 // (per-CTA tiles 1.11 ms; persistent CTAs with a 2-stage ring and recipes prefetched one tile ahead 1.27 ms), 128-thread
-// CTAs capped at 64 registers with streaming (ld.cs) input loads (1.35 ms), against 1.05 ms for this form — the
+// CTAs capped at 64 registers with streaming (ld.cs) input loads (1.35 ms), persistent warps each with a private 2-stage
+// TMA ring and no block barrier at all (1.41 ms), against 1.05 ms for this form — the
 // block-wide barriers per tile cost more than the row-strided accesses they remove; and an in-kernel shared-memory output queue inside the walk
 // (12.5-22.6 ms against 10.7 ms at the time: it shrinks the L1 the terrain gathers live on).
 __global__ void __launch_bounds__(256) k_pair_outputs(int64_t n, const double *__restrict__ states, const double *__restrict__ actions,

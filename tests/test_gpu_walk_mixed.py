@@ -218,3 +218,25 @@ def test_fp64_map_through_rounded_texture_copy(gbp):
         assert (vg == vo).all()
     t2 = gbp.Terrain(T.x, T.y, T.z + 1.0)
     assert not t2.flags()["mixed_precision"] and not t2.flags()["texture_gather"]
+
+
+def test_large_ragged_batch_device_call(gbp, env):
+    """150 001 candidates (ragged for every tile size in use) through the device-pointer call: guard bands around s_new,
+    results bit-equal to the oracle"""
+    import torch
+    t, o, T = env
+    n = 150001
+    s, a, d = candidates(o, n, seed=43)
+    dev = torch.device("cuda:0")
+    ds, da, dd = torch.from_numpy(s).to(dev), torch.from_numpy(a).to(dev), torch.from_numpy(d).to(dev)
+    pad = 4096
+    buf = torch.full((pad + 64 * n + pad,), 0xA5, dtype=torch.uint8, device=dev)
+    dv = torch.zeros(n, dtype=torch.uint8, device=dev); df = torch.zeros_like(dv); dtn = torch.zeros(n, dtype=torch.float64, device=dev)
+    t.validate_pairs_dev(n, ds.data_ptr(), da.data_ptr(), dd.data_ptr(), 0, 0, dv.data_ptr(), df.data_ptr(), buf.data_ptr() + pad, dtn.data_ptr(), 0)
+    torch.cuda.synchronize()
+    h = buf.cpu().numpy()
+    assert (h[:pad] == 0xA5).all() and (h[-pad:] == 0xA5).all(), "guard band overwritten"
+    vo, fo, sno, tno, _ = o.validate_pairs(s, a, d, nthreads=8)
+    assert (dv.cpu().numpy() == vo).all()
+    assert_bits_equal(h[pad:pad + 64 * n].view(np.float64).reshape(n, 8), sno, what="s_new vs oracle")
+    assert_bits_equal(dtn.cpu().numpy(), tno, what="t_new vs oracle")
