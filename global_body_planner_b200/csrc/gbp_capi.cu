@@ -600,6 +600,7 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 			attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
 			cfg.numAttrs = 1;
 		}
+		double2 *recipe = nullptr;
 		if (t->view.mixed_ok) {
 			// mixed-precision walk (k_walk_mixed, gbp_walk.cuh) + fp64 redo pass over the candidates it could not decide
 			if (n > 0x7fffffff) return fail(GBP_E_INVALID, "at most 2^31-1 candidates per call");
@@ -609,29 +610,32 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 				cudaFree(tm->d_redo);
 				tm->d_redo = nullptr; tm->redo_cap = 0;
 				const size_t cap = ((size_t) n + 1023) / 1024 * 1024;
-				CU(cudaMalloc((void **) &tm->d_redo, cap * sizeof(int) + 16));
+				CU(cudaMalloc((void **) &tm->d_redo, cap * sizeof(int) + 16 + cap * sizeof(double2)));  // + the compact recipe array
 				tm->redo_cap = cap;
 			}
 			int *redo = tm->d_redo;
 			unsigned long long *redo_count = (unsigned long long *) (redo + tm->redo_cap);
+			// {tau, kind} per candidate between the walk and k_pair_outputs: compact side array, except when the caller
+			// finishes the outputs itself (variant 5: the recipes stay in s_new[i][0..1])
+			recipe = (s_new && !walk_only) ? (double2 *) ((char *) redo + tm->redo_cap * sizeof(int) + 16) : nullptr;
 			CU(cudaMemsetAsync(redo_count, 0, sizeof(unsigned long long), st));
-#define GBP_WALK_(TEX, AD) CU(cudaLaunchKernelEx(&cfg, k_walk_mixed<TEX, AD>, t->view, (int) n, (int) per_warp, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt, redo, redo_count))
+#define GBP_WALK_(TEX, AD) CU(cudaLaunchKernelEx(&cfg, k_walk_mixed<TEX, AD>, t->view, (int) n, (int) per_warp, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt, redo, redo_count, recipe))
 			if (t->view.ztex) { if (adaptive) GBP_WALK_(true, true); else GBP_WALK_(true, false); }
 			else { if (adaptive) GBP_WALK_(false, true); else GBP_WALK_(false, false); }
 #undef GBP_WALK_
 			if (t->view.cell_f32)
 				k_validate_redo<MapF32U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
-																	   flags, s_new, t_new, t->d_cnt);
+																	   flags, s_new, t_new, t->d_cnt, recipe);
 			else
 				k_validate_redo<MapF64U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
-																	   flags, s_new, t_new, t->d_cnt);
+																	   flags, s_new, t_new, t->d_cnt, recipe);
 		} else {
 #define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt))
 			if (t->view.cell_f32) { if (t->view.uniform) GBP_WALK_(MapF32U); else GBP_WALK_(MapF32N); }
 			else { if (t->view.uniform) GBP_WALK_(MapF64U); else GBP_WALK_(MapF64N); }
 #undef GBP_WALK_
 		}
-		if (s_new && !walk_only) k_pair_outputs<<<blocks_for(n, 256), 256, 0, st>>>(n, states, actions, s_new);
+		if (s_new && !walk_only) k_pair_outputs<<<blocks_for(n, 256), 256, 0, st>>>(n, states, actions, s_new, recipe);
 	}
 	CU(cudaGetLastError());
 	return GBP_OK;
@@ -642,7 +646,7 @@ int gbp_pair_outputs_dev(int64_t n, const double *states, const double *actions,
 	if (n == 0) return GBP_OK;
 	if ((((uintptr_t) states) | ((uintptr_t) actions) | ((uintptr_t) s_new)) & 15)
 		return fail(GBP_E_INVALID, "states/actions/s_new must be 16-byte aligned (TMA bulk copies)");
-	k_pair_outputs<<<blocks_for(n, 256), 256, 0, (cudaStream_t) stream>>>(n, states, actions, s_new);
+	k_pair_outputs<<<blocks_for(n, 256), 256, 0, (cudaStream_t) stream>>>(n, states, actions, s_new, (const double2 *) nullptr);
 	CU(cudaGetLastError());
 	return GBP_OK;
 }
@@ -676,7 +680,7 @@ int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, co
 			if (!P.st[k]) CU(cudaStreamCreateWithFlags(&P.st[k], cudaStreamNonBlocking));
 			CU(cudaMalloc(&P.in[k], (size_t) want * (64 + 80 + 1)));
 			CU(cudaMalloc(&P.out[k], (size_t) want * (64 + 8 + 1 + 1)));
-			CU(cudaMalloc((void **) &P.redo[k], (size_t) want * sizeof(int) + 16));
+			CU(cudaMalloc((void **) &P.redo[k], (size_t) want * sizeof(int) + 16 + (size_t) want * sizeof(double2)));
 		}
 		P.chunk = want;
 	}

@@ -611,7 +611,8 @@ __global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int 
 														const unsigned long long *__restrict__ redo_count, const double *__restrict__ states,
 														const double *__restrict__ actions, const uint8_t *__restrict__ dir, int adaptive,
 														uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags, double *__restrict__ s_new,
-														double *__restrict__ t_new, unsigned long long *__restrict__ cnt) {
+														double *__restrict__ t_new, unsigned long long *__restrict__ cnt,
+														double2 *__restrict__ recipe) {
 	const unsigned long long m = *redo_count;
 	unsigned long long k = 0, L = 0, np = 0, oog = 0, near = 0, nvalid = 0;
 	for (unsigned long long j = blockIdx.x * (unsigned long long) blockDim.x + threadIdx.x; j < m; j += (unsigned long long) gridDim.x * blockDim.x) {
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int 
 		const bool ok = r == 2;
 		verdict[i] = ok ? 1 : 0;
 		if (flags) flags[i] = (uint8_t) (q.c.flags | (ok ? GBP_FLAG_VALID : 0));
-		if (s_new) *reinterpret_cast<double2 *>(s_new + 8 * i) = make_double2(out.tau, (double) out.kind);
+		if (s_new) *(recipe ? recipe + i : reinterpret_cast<double2 *>(s_new + 8 * i)) = make_double2(out.tau, (double) out.kind);
 		if (t_new) t_new[i] = q.t_new;
 		k += q.c.substates; L += q.c.lookups; np += q.c.nanprobes;
 		oog += (q.c.flags & GBP_FLAG_OOG) ? 1 : 0; near += (q.c.flags & GBP_FLAG_NEAR) ? 1 : 0; nvalid += ok ? 1 : 0;
@@ -655,10 +656,10 @@ __global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int 
 // block-wide barriers per tile cost more than the row-strided accesses they remove; and an in-kernel shared-memory output queue inside the walk
 // (12.5-22.6 ms against 10.7 ms at the time: it shrinks the L1 the terrain gathers live on).
 __global__ void __launch_bounds__(256) k_pair_outputs(int64_t n, const double *__restrict__ states, const double *__restrict__ actions,
-													   double *__restrict__ s_new) {
+													   double *__restrict__ s_new, const double2 *__restrict__ recipe) {
 	const int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	const double2 rc = *reinterpret_cast<const double2 *>(s_new + 8 * i);
+	const double2 rc = recipe ? __ldcs(recipe + i) : *reinterpret_cast<const double2 *>(s_new + 8 * i);
 	double s[8], a[10], sn[8];
 	load_state(states + 8 * i, s);
 	load_action(actions + 10 * i, a);

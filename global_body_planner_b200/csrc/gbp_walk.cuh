@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_mixed(Ter
 																			   uint8_t *__restrict__ verdict, uint8_t *__restrict__ flags,
 																			   double *__restrict__ s_new, double *__restrict__ t_new,
 																			   unsigned long long *__restrict__ cnt, int *__restrict__ redo_idx,
-																			   unsigned long long *__restrict__ redo_count) {
+																			   unsigned long long *__restrict__ redo_count, double2 *__restrict__ recipe) {
 	__shared__ __align__(128) unsigned char ring[RF_WARPS][WK_NBUF][WK_SLOT_BYTES];
 	__shared__ __align__(16) double stash[8][RF_WARPS * 32];
 	__shared__ __align__(8) uint64_t bars[RF_WARPS][WK_NBUF];
@@ -281,8 +281,10 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_mixed(Ter
 				const bool ok = r == 2;
 				__stcs(verdict + mine, (uint8_t) (ok ? 1 : 0));
 				if (flags) __stcs(flags + mine, (uint8_t) (ok ? GBP_FLAG_VALID : 0));  // no OOG / NEAR flag can arise on this path
-				// s_new is finished by k_pair_outputs (convergent, exact); its slot carries the recipe meanwhile
-				if (s_new) __stcs(reinterpret_cast<double2 *>(s_new + 8 * (int64_t) mine), make_double2(out.tau, (double) out.kind));
+				// s_new is finished by k_pair_outputs (convergent, exact) from the recipe: kept in a compact side array when the
+				// caller runs both kernels (a 16-byte write into a 64-byte s_new row costs k_pair_outputs a read of the whole row),
+				// else in the row itself (variant 5 / gbp_pair_outputs_dev contract)
+				if (s_new) __stcs(recipe ? recipe + mine : reinterpret_cast<double2 *>(s_new + 8 * (int64_t) mine), make_double2(out.tau, (double) out.kind));
 				if (t_new) {
 					const double tn = ok ? (fwd ? q.ts + q.tf : q.ts) : (q.have_ls ? (fwd ? q.t_ls : q.ts - q.t_ls) : 0.0);
 					__stcs(t_new + mine, tn);
