@@ -132,6 +132,15 @@ def sample_actions(seed, stream, idx0, n, normal=(0.0, 0.0, 1.0), s_from=None, s
     return a
 
 
+def own_map_layer(seed, x_size=221, y_size=161, x_start=-0.5, y_start=-4.0, res=0.05, rects=None):
+    """The float elevation layer createOwnMap fills (grid_map index order) and (resolution, centre x, centre y)."""
+    r = None if rects is None else _f64(rects, (-1, 6))
+    elev = np.zeros((x_size, y_size), np.float32); geom = np.zeros(3)
+    _check(lib().gbp_own_map_layer(C.c_uint64(seed), x_size, y_size, C.c_double(x_start), C.c_double(y_start), C.c_double(res),
+                                   0 if r is None else len(r), _p(r), _p(elev), _p(geom)))
+    return elev, geom
+
+
 class Terrain:
     """Device-resident FastTerrainMap (fast_terrain_map.h).  x-major [nx, ny] layers."""
 
@@ -165,6 +174,27 @@ class Terrain:
         a, b = C.c_int(), C.c_int()
         _check(lib().gbp_terrain_dims(h, C.byref(a), C.byref(b), None))
         self.nx, self.ny = a.value, b.value
+        return self
+
+    @classmethod
+    def own_map(cls, seed, x_size=221, y_size=161, x_start=-0.5, y_start=-4.0, res=0.05, rects=None):
+        """TerrainMapPublisher::createOwnMap (terrain_map_publisher.cpp:34-231) on the Philox stream; rects [n][6] =
+        x1 y1 x2 y2 mu delta, None = the reference's table."""
+        r = None if rects is None else _f64(rects, (-1, 6))
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _check(lib().gbp_terrain_create_own_map(C.c_uint64(seed), x_size, y_size, C.c_double(x_start), C.c_double(y_start),
+                                                C.c_double(res), 0 if r is None else len(r), _p(r), C.byref(h)))
+        self.h, self.nx, self.ny = h, x_size, y_size
+        return self
+
+    @classmethod
+    def default_map(cls):
+        """TerrainMapPublisher::createMap (terrain_map_publisher.cpp:253-286)."""
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        _check(lib().gbp_terrain_create_default_map(C.byref(h)))
+        self.h, self.nx, self.ny = h, 60, 25
         return self
 
     def close(self):

@@ -2,6 +2,7 @@
 // HOST buffers through a chunked copy/compute pipeline, kernel selection and launch geometry.
 // No torch types, no CPU fallback: without a CUDA device every compute entry point fails with
 // GBP_E_CUDA.
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -349,6 +350,96 @@ int gbp_terrain_create_csv(const char *directory, int via_gridmap, gbp_terrain *
 			for (size_t j = 0; j < ny; ++j) lay[k][i * ny + j] = (float) L[2 + k][(ny - 1) - j][(nx - 1) - i];  // grid_map index (i, j), :363-367
 	}
 	return gbp_terrain_create_gridmap((int) nx, (int) ny, (double) x_res, cx, cy, lay[0].data(), lay[1].data(), lay[2].data(), lay[3].data(), out);
+}
+
+// TerrainMapPublisher::findXYIndex (terrain_map_publisher.cpp:178-231): rectangle [x1, x2] x [y1, y2] -> node index
+// range [lo, hi) on one axis.  v == last node leaves the reference's lower index uninitialised; defined as the last node.
+static int own_index_lo(const std::vector<double> &ax, double v) {
+	if (v <= ax.front()) return 0;
+	for (size_t i = 0; i + 1 < ax.size(); ++i)
+		if (ax[i] <= v && v < ax[i + 1]) return (int) i;
+	return (int) ax.size() - 1;
+}
+static int own_index_hi(const std::vector<double> &ax, double v) {
+	if (v >= ax.back()) return (int) ax.size();
+	for (size_t i = ax.size() - 1; i > 0; --i)
+		if (ax[i - 1] <= v && v < ax[i]) return (int) i;
+	return 0;
+}
+static const double k_own_map_rects[13][6] = {  // changeOwnMapZData (:107-127): global 1 cm noise, then 12 boxes
+	{-DBL_MAX, -DBL_MAX, DBL_MAX, DBL_MAX, 0, 0.01},
+	{8.13, -4, 8.42, 4, 0.158, 0.01}, {8.42, -4, 8.71, 4, 0.316, 0.01}, {8.71, -4, 10.5, 4, 0.474, 0.01},
+	{0.75, -3.15, 2.05, -2.35, 0.6, 0.1}, {4.25, -2.4, 5.4, -1.75, 0.5, 0.05}, {2.9, -0.6, 3.25, 1.15, 0.158, 0.01},
+	{4.9, -0.5, 5.3, 0.35, -0.3, 0.01}, {6.5, 0.45, 7.2, 1.05, 0.7, 0.07}, {0.65, 2.95, 1.15, 3.75, 0.3, 0.08},
+	{4.4, 2.8, 5.7, 3.55, 0.65, 0.04}, {7.5, -2.6, 9.45, -1.15, 0.68, 0.06}, {6.2, 1.1, 9.2, 2.3, -0.2, 0.06}};
+
+int gbp_own_map_layer(uint64_t seed, int x_size, int y_size, double x_start, double y_start, double res, int n_rect,
+					  const double *rects, float *elevation, double *geometry3) {
+	if (x_size < 2 || y_size < 2 || (int64_t) x_size * y_size > (1ll << 30) || !(res > 0) || !elevation || !geometry3 || n_rect < 0 ||
+		(n_rect && !rects))
+		return fail(GBP_E_INVALID, "bad own-map arguments");
+	if (!rects) { rects = &k_own_map_rects[0][0]; n_rect = 13; }
+	// axes (:46-60): centimetre-rounded accumulation
+	std::vector<double> xa(x_size), ya(y_size);
+	double v = x_start;
+	for (int i = 0; i < x_size; ++i) { xa[i] = std::round(v * 100) / 100; v = std::round((v + res) * 100) / 100; }
+	v = y_start;
+	for (int i = 0; i < y_size; ++i) { ya[i] = std::round(v * 100) / 100; v = std::round((v + res) * 100) / 100; }
+	std::vector<OwnMapRect> rr(n_rect ? n_rect : 1);
+	for (int r = 0; r < n_rect; ++r) {
+		const double x1 = rects[6 * r], y1 = rects[6 * r + 1], x2 = rects[6 * r + 2], y2 = rects[6 * r + 3];
+		OwnMapRect q = {0, 0, 0, 0, rects[6 * r + 4], rects[6 * r + 5]};
+		if (!(x1 > xa.back() || x2 < xa.front() || y1 > ya.back() || y2 < ya.front() || x1 >= x2 || y1 >= y2)) {  // :153-156
+			q.x1 = own_index_lo(xa, x1); q.y1 = own_index_lo(ya, y1);
+			q.x2 = own_index_hi(xa, x2); q.y2 = own_index_hi(ya, y2);
+		}
+		rr[r] = q;
+	}
+	cudaStream_t st = lib_stream();
+	Dev dr(st), de(st);
+	int rc;
+	if ((rc = upload(dr, rr.data(), rr.size(), st))) return rc;
+	const size_t cells = (size_t) x_size * y_size;
+	CU(de.alloc(cells * sizeof(float)));
+	k_own_map<<<blocks_for((int64_t) cells, 256), 256, 0, st>>>(seed, x_size, y_size, n_rect, dr.as<OwnMapRect>(), de.as<float>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(elevation, de.p, cells * sizeof(float), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	const double x_end = x_start + res * (x_size - 1), y_end = y_start + res * (y_size - 1);  // :41-44
+	const double x_length = x_end - x_start + res, y_length = y_end - y_start + res;
+	geometry3[0] = res;
+	geometry3[1] = xa.front() - 0.5 * res + 0.5 * x_length;  // :76-78
+	geometry3[2] = ya.front() - 0.5 * res + 0.5 * y_length;
+	return GBP_OK;
+}
+
+int gbp_terrain_create_own_map(uint64_t seed, int x_size, int y_size, double x_start, double y_start, double res, int n_rect,
+							   const double *rects, gbp_terrain **out) {
+	if (!out) return fail(GBP_E_INVALID, "out is NULL");
+	*out = nullptr;
+	if (x_size < 2 || y_size < 2 || (int64_t) x_size * y_size > (1ll << 30)) return fail(GBP_E_INVALID, "bad own-map arguments");
+	std::vector<float> elev((size_t) x_size * y_size);
+	double g[3];
+	int rc = gbp_own_map_layer(seed, x_size, y_size, x_start, y_start, res, n_rect, rects, elev.data(), g);
+	if (rc) return rc;
+	// createOwnMap erases the dx / dy / dz layers (:83-85): loadDataFromGridMap then fills (0, 0, 1) (fast_terrain_map.cpp:68-72)
+	return gbp_terrain_create_gridmap(x_size, y_size, g[0], g[1], g[2], elev.data(), nullptr, nullptr, nullptr, out);
+}
+
+// TerrainMapPublisher::createMap (terrain_map_publisher.cpp:253-286), the publisher's default source
+int gbp_terrain_create_default_map(gbp_terrain **out) {
+	if (!out) return fail(GBP_E_INVALID, "out is NULL");
+	*out = nullptr;
+	const int nx = 60, ny = 25;  // Length (12, 5) at 0.2 m
+	const double res = 0.2, cx = 4.0, cy = 0.0;
+	std::vector<float> elev((size_t) nx * ny), zero(elev.size(), 0.0f), one(elev.size(), 1.0f);
+	for (int i = 0; i < nx; ++i)
+		for (int j = 0; j < ny; ++j) {
+			const double px = cx + (0.5 * (nx - 1) - i) * res, py = cy + (0.5 * (ny - 1) - j) * res;
+			const double xd = px - 2, yd = py - 0;
+			elev[(size_t) i * ny + j] = (xd * xd + yd * yd <= 0.5 * 0.5) ? 0.1f : 0.0f;
+		}
+	return gbp_terrain_create_gridmap(nx, ny, res, cx, cy, elev.data(), zero.data(), zero.data(), one.data(), out);
 }
 
 void gbp_terrain_destroy(gbp_terrain *t) {

@@ -715,6 +715,40 @@ __global__ void k_max_curvature(int64_t n, const double *__restrict__ states, un
 	if (c > 0.0) atomicMax(max_bits, (unsigned long long) __double_as_longlong(c));
 }
 
+// ------------------------------------------------------------------ terrain generator of the publisher node
+// TerrainMapPublisher::createOwnMap / changeOwnMapZDataRectangle[Random] (terrain_map_publisher.cpp:34-176): a flat
+// 221 x 161 map at 5 cm on which a list of rectangles is filled, in order, with truncated-Gaussian heights.  The
+// reference draws them from a time(0)-seeded engine; here every (rectangle, cell) owns a TERRAIN cell of the Philox
+// stream (purpose 3, idx = iy * x_size + ix, stream = rectangle number), so a cell only evaluates the LAST rectangle that
+// covers it.  One thread per cell; the float layer is written in grid_map index order (:88-93).
+struct OwnMapRect { int x1, y1, x2, y2; double mu, delta; };
+__global__ void k_own_map(uint64_t seed, int x_size, int y_size, int n_rect, const OwnMapRect *__restrict__ rects,
+						  float *__restrict__ elevation) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= x_size * y_size) return;
+	const int iy = c / x_size, ix = c - iy * x_size;
+	double val = 0.0;  // z_data starts as zeros (:63)
+	for (int r = n_rect - 1; r >= 0; --r) {
+		const OwnMapRect q = rects[r];
+		if (ix < q.x1 || ix >= q.x2 || iy < q.y1 || iy >= q.y2) continue;
+		val = q.mu;
+		if (q.delta > 0.0 && q.mu == q.mu) {  // rejection loop of :171-173, two attempts per Box-Muller pair
+			const double lo = q.mu - q.delta, hi = q.mu + q.delta;
+			bool done = false;
+			for (int b = 0; b < 16 && !done; ++b) {
+				double ua, ub, z0, z1;
+				uniform_pair(seed, (uint64_t) r, (uint64_t) c, 3, b, ua, ub);
+				box_muller(ua, ub, z0, z1);
+				const double v0 = z0 * q.delta + q.mu, v1 = z1 * q.delta + q.mu;
+				if (!(v0 < lo || v0 > hi)) { val = v0; done = true; }
+				else if (!(v1 < lo || v1 > hi)) { val = v1; done = true; }
+			}
+		}
+		break;
+	}
+	elevation[(size_t) ((x_size - 1) - ix) * y_size + ((y_size - 1) - iy)] = (float) val;
+}
+
 // ------------------------------------------------------------------ samplers
 __global__ void k_sample_actions(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, double n0, double n1, double n2,
 								 int dir_flag, double dir_thresh, const double *__restrict__ s_from, const double *__restrict__ s_to,

@@ -41,12 +41,25 @@ void FastTerrainMap::loadData(int x_size, int y_size, std::vector<double> x_data
 void FastTerrainMap::loadDataFromCSV(const std::string &directory, bool via_gridmap) {
 	gbp_terrain *t = nullptr;
 	check(gbp_terrain_create_csv(directory.c_str(), via_gridmap ? 1 : 0, &t), "FastTerrainMap::loadDataFromCSV");
+	adopt(t, "FastTerrainMap::loadDataFromCSV");
+}
+void FastTerrainMap::adopt(gbp_terrain *t, const char *what) {
 	dev_.reset(t, gbp_terrain_destroy);
 	int nx = 0, ny = 0;
-	check(gbp_terrain_dims(t, &nx, &ny, nullptr), "FastTerrainMap::loadDataFromCSV");
+	check(gbp_terrain_dims(t, &nx, &ny, nullptr), what);
 	x_data_.resize(nx);
 	y_data_.resize(ny);
-	check(gbp_terrain_axes(t, x_data_.data(), y_data_.data()), "FastTerrainMap::loadDataFromCSV");
+	check(gbp_terrain_axes(t, x_data_.data(), y_data_.data()), what);
+}
+void FastTerrainMap::createOwnMap(uint64_t seed) {
+	gbp_terrain *t = nullptr;
+	check(gbp_terrain_create_own_map(seed, 221, 161, -0.5, -4.0, 0.05, 0, nullptr, &t), "FastTerrainMap::createOwnMap");  // :36-38
+	adopt(t, "FastTerrainMap::createOwnMap");
+}
+void FastTerrainMap::createMap() {
+	gbp_terrain *t = nullptr;
+	check(gbp_terrain_create_default_map(&t), "FastTerrainMap::createMap");
+	adopt(t, "FastTerrainMap::createMap");
 }
 const gbp_terrain *FastTerrainMap::handle() const {
 	if (!dev_) throw std::runtime_error("FastTerrainMap: no terrain loaded");

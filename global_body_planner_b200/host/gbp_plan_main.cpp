@@ -1,7 +1,7 @@
 // gbp_plan — command-line front end of the ROS-free GlobalBodyPlanner driver: the reference's benchmarking protocol
 // ("num_calls planner calls, print every statistic, then the averages", global_body_planner.cpp:60-168) on a terrain in
 // the reference's CSV format.
-//   gbp_plan <csv-dir> [--algorithm rrt-connect|rrt-star-connect] [--num-calls N] [--replan-time-limit S]
+//   gbp_plan <csv-dir | create:SEED | default> [--algorithm rrt-connect|rrt-star-connect] [--num-calls N] [--replan-time-limit S]
 //            [--start X Y YAW] [--goal X Y YAW] [--height H] [--seed S] [--gridmap] [--attempts A ITERS VERTS]
 //            [--max-time-solve S] [--adaptive] [--plan-out FILE] [--discrete-out FILE] [--quiet]
 #include <cstdio>
@@ -41,7 +41,15 @@ int main(int argc, char **argv) {
 	}
 	try {
 		GlobalBodyPlanner planner(p);
-		planner.loadTerrainFromCSV(argv[1], gridmap);
+		if (!std::strncmp(argv[1], "create:", 7)) {  // the publisher's "create" source on Philox seed N
+			FastTerrainMap m;
+			m.createOwnMap(std::strtoull(argv[1] + 7, nullptr, 10));
+			planner.setTerrain(m);
+		} else if (!std::strcmp(argv[1], "default")) {  // the publisher's default source (createMap)
+			FastTerrainMap m;
+			m.createMap();
+			planner.setTerrain(m);
+		} else planner.loadTerrainFromCSV(argv[1], gridmap);
 		planner.callPlanner();
 		if (plan_out) {  // the BodyPlan wire content: t, 8 state components, phase (the closing state carries -1)
 			std::ofstream f(plan_out);

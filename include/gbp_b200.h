@@ -80,6 +80,23 @@ int gbp_terrain_create_gridmap(int nx, int ny, double resolution, double centre_
  * ydata) — what the oracle harness does.  via_gridmap = 1: the ROS path — layers and the resolution are rounded to
  * float and indexed like the GridMap the publisher fills (:345-369), then FastTerrainMap::loadDataFromGridMap. */
 int gbp_terrain_create_csv(const char *directory, int via_gridmap, gbp_terrain **out);
+/* The publisher's procedural terrains.  TerrainMapPublisher::createOwnMap (terrain_map_publisher.cpp:34-96, "create"
+ * source): a flat x_size x y_size map (reference: 221 x 161 at 0.05 m from (-0.5, -4.0), :36-38) whose axes are the
+ * centimetre-rounded accumulation of :46-60, on which n_rect rectangles {x1, y1, x2, y2, mu, delta} are filled in order
+ * (changeOwnMapZDataRectangleRandom :148-176 with findXYIndex :178-231; delta <= 0 or NaN mu = the constant fill of
+ * changeOwnMapZDataRectangle :129-146); rects = NULL takes the reference's table (:107-127).  The reference draws the
+ * truncated Gaussians from a time(0)-seeded engine; here they come from the Philox stream (TERRAIN cell: purpose 3,
+ * idx = iy * x_size + ix, stream = rectangle number, Box-Muller pair b = attempts 2b, 2b+1 of the rejection loop,
+ * val = z * delta + mu kept iff mu - delta <= val <= mu + delta, mu after 32 rejections), generated on the device.
+ * gbp_own_map_layer returns the float elevation layer in grid_map index order and {resolution, centre x, centre y};
+ * gbp_terrain_create_own_map feeds it to the GridMap ingest (no dx / dy / dz layers: normals (0, 0, 1)). */
+int gbp_own_map_layer(uint64_t seed, int x_size, int y_size, double x_start, double y_start, double resolution, int n_rect,
+                      const double *rects, float *elevation, double *geometry3);
+int gbp_terrain_create_own_map(uint64_t seed, int x_size, int y_size, double x_start, double y_start, double resolution,
+                               int n_rect, const double *rects, gbp_terrain **out);
+/* TerrainMapPublisher::createMap (terrain_map_publisher.cpp:253-286, the default source): 12 x 5 m at 0.2 m centred on
+ * (4, 0), a 0.1 m disc of radius 0.5 m around (2, 0), normals (0, 0, 1). */
+int gbp_terrain_create_default_map(gbp_terrain **out);
 void gbp_terrain_destroy(gbp_terrain *t);
 int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes);
 /* which evaluator serves this terrain: uniform_axes = cell edges are computed, not loaded; mixed_precision = the

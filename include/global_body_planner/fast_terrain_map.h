@@ -35,6 +35,12 @@ public:
 	// TerrainMapPublisher::loadMapFromCSV, terrain_map_publisher.cpp:330-370).  via_gridmap = false: fp64 values through
 	// loadData; true: float layers / float resolution through the GridMap index flip, as the ROS pipeline delivers them.
 	void loadDataFromCSV(const std::string &directory, bool via_gridmap = false);
+	// B200 addition: the publisher's procedural sources.  createOwnMap: the "create" source (TerrainMapPublisher::createOwnMap,
+	// terrain_map_publisher.cpp:34-231: 221 x 161 box world at 5 cm, the reference's rectangle table, heights from the Philox
+	// stream `seed` instead of the reference's time(0)-seeded engine); createMap: the default source (:253-286, 12 x 5 m with a
+	// 0.1 m disc).  Both go through the GridMap ingest like the ROS pipeline.
+	void createOwnMap(uint64_t seed);
+	void createMap();
 	double getGroundHeight(const double x, const double y);              // :94-132
 	bool heightIsNan(const double x, const double y);                    // :135-157
 	std::array<double, 3> getSurfaceNormal(const double x, const double y);  // :160-213
@@ -48,6 +54,7 @@ public:
 	const gbp_terrain *handle() const;
 
 private:
+	void adopt(gbp_terrain *t, const char *what);
 	std::shared_ptr<gbp_terrain> dev_;  // copies of a FastTerrainMap share the device terrain (it is immutable)
 	std::vector<double> x_data_, y_data_;
 };

@@ -832,3 +832,98 @@ double orc_max_curvature(long long n, const double *states) {
 	}
 	return mx;
 }
+
+/* ====================================================================== terrain generators of the publisher node
+ * TerrainMapPublisher::createOwnMap / changeOwnMapZData* / findXYIndex (terrain_map_publisher.cpp:34-231) and
+ * createMap (:253-286).  PARITY UNPINNED against compiled reference code: that TU needs ROS, grid_map_ros and OpenCV;
+ * the restatement follows the source line by line instead.  The reference draws the box heights from a
+ * std::default_random_engine seeded with time(0) (:165), i.e. irreproducibly; here they come from the Philox stream:
+ * TERRAIN cell (purpose 3), idx = iy * x_size + ix, stream = rectangle number, Box-Muller pair b = (u_2b, u_2b+1) gives
+ * attempts 2b and 2b+1 of the rejection loop (:171-173): val = z * delta + mu, accepted iff mu - delta <= val <= mu + delta;
+ * after 32 rejected attempts (p = 1e-16) the cell takes mu.  A rectangle with delta <= 0 or a NaN mu is the constant fill
+ * of changeOwnMapZDataRectangle (:129-146). */
+static int own_index_lo(const double *ax, int n, double v) { /* findXYIndex :188-197 */
+	if (v <= ax[0]) return 0;
+	for (int i = 0; i < n - 1; ++i)
+		if (ax[i] <= v && v < ax[i + 1]) return i;
+	return n - 1; /* v == ax[n-1]: the reference leaves the index uninitialised; defined as the last node */
+}
+static int own_index_hi(const double *ax, int n, double v) { /* :198-207 */
+	if (v >= ax[n - 1]) return n;
+	for (int i = n - 1; i > 0; --i)
+		if (ax[i - 1] <= v && v < ax[i]) return i;
+	return 0; /* unreachable: v < ax[0] returns before the search (:153-156) */
+}
+const double orc_own_map_default_rects[13][6] = { /* changeOwnMapZData :107-127 */
+	{-1.7976931348623157e308, -1.7976931348623157e308, 1.7976931348623157e308, 1.7976931348623157e308, 0, 0.01},
+	{8.13, -4, 8.42, 4, 0.158, 0.01}, {8.42, -4, 8.71, 4, 0.316, 0.01}, {8.71, -4, 10.5, 4, 0.474, 0.01},
+	{0.75, -3.15, 2.05, -2.35, 0.6, 0.1}, {4.25, -2.4, 5.4, -1.75, 0.5, 0.05}, {2.9, -0.6, 3.25, 1.15, 0.158, 0.01},
+	{4.9, -0.5, 5.3, 0.35, -0.3, 0.01}, {6.5, 0.45, 7.2, 1.05, 0.7, 0.07}, {0.65, 2.95, 1.15, 3.75, 0.3, 0.08},
+	{4.4, 2.8, 5.7, 3.55, 0.65, 0.04}, {7.5, -2.6, 9.45, -1.15, 0.68, 0.06}, {6.2, 1.1, 9.2, 2.3, -0.2, 0.06}};
+void orc_own_map_axes(int n, double start, double res, double *ax) { /* :46-60: centimetre-rounded accumulation */
+	double v = start;
+	for (int i = 0; i < n; ++i) {
+		ax[i] = round(v * 100) / 100;
+		v = round((v + res) * 100) / 100;
+	}
+}
+/* rectangle r -> [ix1, ix2) x [iy1, iy2) or an empty range when the reference returns early (:153-156) */
+void orc_own_map_range(const double *xa, int nx, const double *ya, int ny, const double rect[6], int range[4]) {
+	double x1 = rect[0], y1 = rect[1], x2 = rect[2], y2 = rect[3];
+	range[0] = range[1] = range[2] = range[3] = 0;
+	if (x1 > xa[nx - 1] || x2 < xa[0] || y1 > ya[ny - 1] || y2 < ya[0] || x1 >= x2 || y1 >= y2) return;
+	range[0] = own_index_lo(xa, nx, x1); range[1] = own_index_lo(ya, ny, y1);
+	range[2] = own_index_hi(xa, nx, x2); range[3] = own_index_hi(ya, ny, y2);
+}
+double orc_own_map_draw(uint64_t seed, int rect_no, uint64_t cell, double mu, double delta) {
+	if (!(delta > 0.0) || mu != mu) return mu;
+	double lo = mu - delta, hi = mu + delta;
+	for (int b = 0; b < 16; ++b) {
+		double u[2], z[2];
+		orc_uniforms(seed, (uint64_t) rect_no, cell, 3, 2 * b, 2, u);
+		box_muller(u[0], u[1], &z[0], &z[1]);
+		for (int k = 0; k < 2; ++k) {
+			double val = z[k] * delta + mu;
+			if (!(val < lo || val > hi)) return val;
+		}
+	}
+	return mu;
+}
+/* elevation: float layer in grid_map index order [i * y_size + j] (:88-93); geom = {resolution, centre x, centre y} (:76-78) */
+void orc_own_map(uint64_t seed, int x_size, int y_size, double x_start, double y_start, double res, int n_rect,
+				 const double *rects, float *elevation, double geom[3]) {
+	double *xa = malloc(sizeof(double) * x_size), *ya = malloc(sizeof(double) * y_size);
+	double *z = calloc((size_t) x_size * y_size, sizeof(double)); /* z_data[iy][ix], zeros (:63) */
+	orc_own_map_axes(x_size, x_start, res, xa);
+	orc_own_map_axes(y_size, y_start, res, ya);
+	if (!rects) { rects = &orc_own_map_default_rects[0][0]; n_rect = 13; }
+	for (int r = 0; r < n_rect; ++r) {
+		int g[4];
+		orc_own_map_range(xa, x_size, ya, y_size, rects + 6 * r, g);
+		for (int i = g[1]; i < g[3]; ++i)
+			for (int j = g[0]; j < g[2]; ++j)
+				z[(size_t) i * x_size + j] = orc_own_map_draw(seed, r, (uint64_t) i * x_size + j, rects[6 * r + 4], rects[6 * r + 5]);
+	}
+	double x_end = x_start + res * (x_size - 1), y_end = y_start + res * (y_size - 1); /* :41-44 */
+	double x_length = x_end - x_start + res, y_length = y_end - y_start + res;
+	geom[0] = res;
+	geom[1] = xa[0] - 0.5 * res + 0.5 * x_length;
+	geom[2] = ya[0] - 0.5 * res + 0.5 * y_length;
+	for (int i = 0; i < x_size; ++i)
+		for (int j = 0; j < y_size; ++j)
+			elevation[(size_t) i * y_size + j] = (float) z[(size_t) ((y_size - 1) - j) * x_size + ((x_size - 1) - i)];
+	free(xa); free(ya); free(z);
+}
+/* createMap (:253-286): 12 x 5 m at 0.2 m centred on (4, 0) -> 60 x 25 cells; a disc of radius 0.5 m around (2, 0)
+ * is 0.1 m high, everything else 0; normals (0, 0, 1).  Cell positions as in the grid_map stand-in of oracle/shim. */
+void orc_default_map(float *elevation /* [60 * 25] */, double geom[3]) {
+	const int nx = 60, ny = 25;
+	const double res = 0.2, cx = 4.0, cy = 0.0;
+	for (int i = 0; i < nx; ++i)
+		for (int j = 0; j < ny; ++j) {
+			double px = cx + (0.5 * (nx - 1) - i) * res, py = cy + (0.5 * (ny - 1) - j) * res;
+			double xd = px - 2, yd = py - 0;
+			elevation[i * ny + j] = (xd * xd + yd * yd <= 0.5 * 0.5) ? 0.1f : 0.0f;
+		}
+	geom[0] = res; geom[1] = cx; geom[2] = cy;
+}

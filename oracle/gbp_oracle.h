@@ -149,6 +149,14 @@ long long orc_interp_path(int n_actions, const double *states, const double *act
 						  double *out_s, double *out_t, int *out_phase);
 double orc_max_curvature(long long n, const double *states);
 int orc_post_process_path(const orc_terrain *t, int ns, double *states, double *actions, int adaptive, double stats3[3]);
+/* terrain generators of the publisher node (terrain_map_publisher.cpp:34-231, :253-286); see gbp_oracle.c */
+extern const double orc_own_map_default_rects[13][6];
+void orc_own_map_axes(int n, double start, double res, double *ax);
+void orc_own_map_range(const double *xa, int nx, const double *ya, int ny, const double rect[6], int range[4]);
+double orc_own_map_draw(uint64_t seed, int rect_no, uint64_t cell, double mu, double delta);
+void orc_own_map(uint64_t seed, int x_size, int y_size, double x_start, double y_start, double res, int n_rect,
+				 const double *rects, float *elevation, double geom[3]);
+void orc_default_map(float *elevation, double geom[3]);
 
 #ifdef __cplusplus
 }

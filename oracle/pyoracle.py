@@ -109,6 +109,45 @@ PLAN_STATS_DTYPE = np.dtype([("solved", "i4"), ("iters", "i4"), ("nv_a", "i4"), 
                              ("pair_checks", "i8"), ("nn_queries", "i8")])
 
 
+def _orc():
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    return C.CDLL(ORACLE_SO)
+
+
+OWN_MAP_DEFAULT = dict(x_size=221, y_size=161, x_start=-0.5, y_start=-4.0, res=0.05)  # terrain_map_publisher.cpp:36-38
+
+
+def own_map(seed, x_size=221, y_size=161, x_start=-0.5, y_start=-4.0, res=0.05, rects=None):
+    """createOwnMap restated (terrain_map_publisher.cpp:34-231): float elevation layer in grid_map index order and
+    (resolution, centre x, centre y); rects [n][6] = x1 y1 x2 y2 mu delta, None = the reference's table."""
+    L = _orc()
+    elev = np.zeros((x_size, y_size), np.float32); geom = np.zeros(3)
+    r = None if rects is None else _f64(rects, (-1, 6))
+    L.orc_own_map(C.c_uint64(seed), x_size, y_size, C.c_double(x_start), C.c_double(y_start), C.c_double(res),
+                  0 if r is None else len(r), _p(r), _p(elev), _p(geom))
+    return elev, geom
+
+
+def own_map_axes(n, start, res):
+    L = _orc(); ax = np.zeros(n)
+    L.orc_own_map_axes(n, C.c_double(start), C.c_double(res), _p(ax))
+    return ax
+
+
+def own_map_range(xa, ya, rect):
+    L = _orc(); xa, ya, rect = _f64(xa), _f64(ya), _f64(rect); g = np.zeros(4, np.int32)
+    L.orc_own_map_range(_p(xa), len(xa), _p(ya), len(ya), _p(rect), _p(g))
+    return g
+
+
+def default_map():
+    """createMap restated (terrain_map_publisher.cpp:253-286)"""
+    L = _orc(); elev = np.zeros((60, 25), np.float32); geom = np.zeros(3)
+    L.orc_default_map(_p(elev), _p(geom))
+    return elev, geom
+
+
 class Oracle:
     """The plain-C restatement."""
 
