@@ -43,6 +43,34 @@ def synthetic_map(n=MAP_N, pitch=MAP_PITCH):
     return ax, ax.copy(), z.astype(np.float32).astype(np.float64)
 
 
+def device_batch(torch, capi, t, x, y, n, seed, stream_id, dev):
+    """The candidate batch of BASELINE configs[3], generated on the device with the Philox samplers: start states from the
+    randomState recipe filtered to valid STANCE poses >= 0.5 m inside the border, actions from the getRandomAction recipe
+    with normal (0, 0, 1), alternating FORWARD / REVERSE.  Shared with tests/test_gpu_full_size.py."""
+    cur = torch.cuda.current_stream().cuda_stream
+    states = torch.empty((n, 8), dtype=torch.float64, device=dev)
+    have, idx0 = 0, 0
+    chunk = min(max(n, 1 << 16) * 2, 1 << 25)
+    buf = torch.empty((chunk, 8), dtype=torch.float64, device=dev)
+    ph = torch.ones(chunk, dtype=torch.uint8, device=dev)
+    ver = torch.empty(chunk, dtype=torch.uint8, device=dev)
+    while have < n:
+        t.sample_states_dev(seed, stream_id, idx0, chunk, buf.data_ptr(), cur)
+        t.valid_states_dev(chunk, buf.data_ptr(), ph.data_ptr(), ver.data_ptr(), 0, cur)
+        keep = (ver == 1) & (buf[:, 0] >= x[0] + 0.5) & (buf[:, 0] <= x[-1] - 0.5) & (buf[:, 1] >= y[0] + 0.5) & (buf[:, 1] <= y[-1] - 0.5)
+        sel = buf[keep]
+        m = min(len(sel), n - have)
+        states[have:have + m] = sel[:m]
+        have += m
+        idx0 += chunk
+    del buf, ph, ver, keep, sel
+    actions = torch.empty((n, 10), dtype=torch.float64, device=dev)
+    capi.sample_actions_dev(seed, stream_id + 1, 0, n, actions.data_ptr(), (0.0, 0.0, 1.0), cur)
+    direction = (torch.arange(n, device=dev) % 2).to(torch.uint8)
+    torch.cuda.synchronize()
+    return states, actions, direction
+
+
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
     """Samples SM clock and throttle reasons during the timed region (pynvml, else nvidia-smi)."""
@@ -242,26 +270,7 @@ def main():
     t = gbp.Terrain(x, y, z)
     n = args.candidates
     stream_id = 100 + 2 * rank  # disjoint Philox streams per rank
-    cur = torch.cuda.current_stream().cuda_stream
-    states = torch.empty((n, 8), dtype=torch.float64, device=dev)
-    have, idx0 = 0, 0
-    chunk = min(max(n, 1 << 16) * 2, 1 << 25)
-    buf = torch.empty((chunk, 8), dtype=torch.float64, device=dev)
-    ph = torch.ones(chunk, dtype=torch.uint8, device=dev)
-    ver = torch.empty(chunk, dtype=torch.uint8, device=dev)
-    while have < n:
-        t.sample_states_dev(seed, stream_id, idx0, chunk, buf.data_ptr(), cur)
-        t.valid_states_dev(chunk, buf.data_ptr(), ph.data_ptr(), ver.data_ptr(), 0, cur)
-        keep = (ver == 1) & (buf[:, 0] >= x[0] + 0.5) & (buf[:, 0] <= x[-1] - 0.5) & (buf[:, 1] >= y[0] + 0.5) & (buf[:, 1] <= y[-1] - 0.5)
-        sel = buf[keep]
-        m = min(len(sel), n - have)
-        states[have:have + m] = sel[:m]
-        have += m
-        idx0 += chunk
-    del buf, ph, ver, keep, sel
-    actions = torch.empty((n, 10), dtype=torch.float64, device=dev)
-    capi.sample_actions_dev(seed, stream_id + 1, 0, n, actions.data_ptr(), (0.0, 0.0, 1.0), cur)
-    direction = (torch.arange(n, device=dev) % 2).to(torch.uint8)
+    states, actions, direction = device_batch(torch, capi, t, x, y, n, seed, stream_id, dev)
     verdict = torch.empty(n, dtype=torch.uint8, device=dev)
     flags = torch.empty(n, dtype=torch.uint8, device=dev)
     s_new = torch.empty((n, 8), dtype=torch.float64, device=dev)
