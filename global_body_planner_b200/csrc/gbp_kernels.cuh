@@ -653,7 +653,11 @@ __global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int 
 // (per-CTA tiles 1.11 ms; persistent CTAs with a 2-stage ring and recipes prefetched one tile ahead 1.27 ms), 128-thread
 // CTAs capped at 64 registers with streaming (ld.cs) input loads (1.35 ms), persistent warps each with a private 2-stage
 // TMA ring and no block barrier at all (1.41 ms), against 1.05 ms for this form — the
-// block-wide barriers per tile cost more than the row-strided accesses they remove; and an in-kernel shared-memory output queue inside the walk
+// block-wide barriers per tile cost more than the row-strided accesses they remove; a non-persistent warp-private tile with plain
+// coalesced 512-byte LDG / STG requests and __syncwarp only (13 full-line wavefronts per warp instead of ~230 single-sector
+// ones): 0.927 against 0.937 ms, i.e. the access pattern is NOT what limits this pass (a warp lives ~11 k cycles for 281
+// instructions, 44 % of them waiting on its one batch of loads; 24 warps / SM at 66 registers) — not kept;
+// and an in-kernel shared-memory output queue inside the walk
 // (12.5-22.6 ms against 10.7 ms at the time: it shrinks the L1 the terrain gathers live on).
 __global__ void __launch_bounds__(256) k_pair_outputs(int64_t n, const double *__restrict__ states, const double *__restrict__ actions,
 													   double *__restrict__ s_new, const double2 *__restrict__ recipe) {
