@@ -656,7 +656,11 @@ __global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int 
 // block-wide barriers per tile cost more than the row-strided accesses they remove; a non-persistent warp-private tile with plain
 // coalesced 512-byte LDG / STG requests and __syncwarp only (13 full-line wavefronts per warp instead of ~230 single-sector
 // ones): 0.927 against 0.937 ms, i.e. the access pattern is NOT what limits this pass (a warp lives ~11 k cycles for 281
-// instructions, 44 % of them waiting on its one batch of loads; 24 warps / SM at 66 registers) — not kept;
+// instructions, 44 % of them waiting on its one batch of loads; 24 warps / SM at 66 registers) — not kept; the same tile
+// software-pipelined (persistent warps, cp.async double buffer: the loads of tile t+1 in flight while tile t is computed
+// and stored, 92 registers, 2 / 3 / 4 CTAs of 4 warps per SM): 0.914 / 0.918 / 0.960 against 0.926 ms in the same run.
+// Five structurally different forms land within 4 % of each other at ~4.1 TB/s of DRAM traffic (2.70 GB read in three
+// streams + 1.06 GB written): the pass sits at what the memory system delivers for this mix, not at a kernel-side limit;
 // and an in-kernel shared-memory output queue inside the walk
 // (12.5-22.6 ms against 10.7 ms at the time: it shrinks the L1 the terrain gathers live on).
 __global__ void __launch_bounds__(256) k_pair_outputs(int64_t n, const double *__restrict__ states, const double *__restrict__ actions,
