@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libgbp_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "gbp_capi.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("gbp_device.cuh", "gbp_kernels.cuh", "gbp_planner.cuh")] + \
+HEADERS = [os.path.join(HERE, "csrc", f) for f in ("gbp_device.cuh", "gbp_kernels.cuh", "gbp_planner.cuh", "gbp_walk.cuh")] + \
           [os.path.join(HERE, "..", "include", "gbp_b200.h")]
 # -fmad=false: fp64 results must match the reference's x86-64 (no FMA) arithmetic bit for bit.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-lineinfo", "-std=c++17",

@@ -125,6 +125,8 @@ struct gbp_tree {
 	ExtendScratch S;
 	int k_cap = 0;
 	double *d_target = nullptr;
+	unsigned *d_done = nullptr;  // CTA counter of k_extend_fused
+	int *h_result = nullptr;     // pinned, mapped: the result words of an extend without a copy
 };
 
 extern "C" {
@@ -869,7 +871,8 @@ void gbp_tree_destroy(gbp_tree *T) {
 	if (!T) return;
 	cudaFree(T->d_n); cudaFree(T->d_v); cudaFree(T->d_act); cudaFree(T->d_g); cudaFree(T->d_y); cudaFree(T->d_parent);
 	cudaFree(T->S.near_idx); cudaFree(T->S.near_dist); cudaFree(T->S.valid); cudaFree(T->S.dist); cudaFree(T->S.s_test); cudaFree(T->S.result);
-	cudaFree(T->d_target);
+	cudaFree(T->d_target); cudaFree(T->d_done);
+	if (T->h_result) cudaFreeHost(T->h_result);
 	delete T;
 }
 int gbp_tree_create(int capacity, gbp_tree **out) {
@@ -890,6 +893,9 @@ int gbp_tree_create(int capacity, gbp_tree **out) {
 	TRY(cudaMalloc(&T->S.near_dist, sizeof(double)));
 	TRY(cudaMalloc(&T->S.result, 4 * sizeof(int)));
 	TRY(cudaMalloc(&T->d_target, 18 * sizeof(double)));
+	TRY(cudaMalloc(&T->d_done, sizeof(unsigned)));
+	TRY(cudaMemset(T->d_done, 0, sizeof(unsigned)));
+	TRY(cudaHostAlloc((void **) &T->h_result, 4 * sizeof(int), cudaHostAllocMapped));
 #undef TRY
 	T->view.cap = capacity; T->view.n = T->d_n; T->view.v = T->d_v; T->view.act = T->d_act; T->view.parent = T->d_parent;
 	T->view.g = T->d_g; T->view.y = T->d_y;
@@ -1025,14 +1031,24 @@ int gbp_extend(gbp_tree *T, const gbp_terrain *t, const double *target, int dire
 	int rc;
 	if ((rc = ensure_k(T, K))) return rc;
 	cudaStream_t st = lib_stream();
-	CU(cudaMemcpyAsync(T->d_target, target, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
-	k_nearest<<<1, 256, 0, st>>>(T->view, 1, T->d_target, T->S.near_idx, T->S.near_dist);
-	GBP_DISPATCH(t->view, k_extend_candidates, (blocks_for(K, 128), 128), st, t->view, T->view, T->d_target, direction, K, adaptive, seed, stream, idx0, T->S);
-	k_extend_select<<<1, 256, 0, st>>>(t->view, T->view, T->d_target, K, best_of_k, seed, stream, idx0, T->S);
+	Target8 tg;
+	memcpy(tg.v, target, sizeof tg.v);
+	int *dres = nullptr;
+	CU(cudaHostGetDevicePointer((void **) &dres, T->h_result, 0));
+	if (adaptive) {
+		GBP_DISPATCH(t->view, k_extend_fused_adaptive, (blocks_for(K, 128), 128), st, t->view, T->view, tg, direction, K, best_of_k, 1, seed, stream, idx0,
+					 T->S, T->d_done, dres);
+	} else {
+		// lanes per candidate: as many as keep the launch inside one wave of resident CTAs (2 x 128 threads per SM at ~250 registers)
+		int S = 32;
+		while (S > 1 && (int64_t) K * S > (int64_t) sm_count() * 2 * 128) S >>= 1;
+		const int per_block = 4 * (32 / S);
+		GBP_DISPATCH(t->view, k_extend_fused, (blocks_for(K, per_block), 128), st, t->view, T->view, tg, direction, K, best_of_k, S, seed, stream, idx0,
+					 T->S, T->d_done, dres);
+	}
 	CU(cudaGetLastError());
-	int res[4] = {0, -1, 0, 0};
-	CU(cudaMemcpyAsync(res, T->S.result, sizeof res, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	const int res[3] = {T->h_result[0], T->h_result[1], T->h_result[2]};
 	if (status) *status = res[0];
 	if (new_id) *new_id = res[1];
 	if (pair_checks) *pair_checks = res[2];

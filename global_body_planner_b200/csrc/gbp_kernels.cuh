@@ -971,7 +971,6 @@ __global__ void k_tree_read(TreeView T, int first, int n, double *__restrict__ s
 }
 
 // ------------------------------------------------------------------ extend (rrt.cpp:20-102)
-// Stage 2 of gbp_extend: candidate j = ACTION cell idx0 + j from s_near; one thread per candidate.
 struct ExtendScratch {
 	int *near_idx;       // [1] result of k_nearest
 	double *near_dist;   // [1]
@@ -980,77 +979,7 @@ struct ExtendScratch {
 	double *s_test;      // [K][8]
 	int *result;         // [4] status, new id, first-valid index / checks, pad
 };
-template <typename M>
-__global__ void __launch_bounds__(128) k_extend_candidates(TerrainView T, TreeView tree, const double *__restrict__ target,
-															int direction, int K, int adaptive, uint64_t seed, uint64_t stream,
-															uint64_t idx0, ExtendScratch S) {
-	int j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= K) return;
-	double tg[8], s_near[8], nn[3], R[9], a[10], sn[8], tn;
-#pragma unroll
-	for (int d = 0; d < 8; ++d) tg[d] = target[d];
-	tree_get(tree, *S.near_idx, s_near);
-	unsigned fl = 0;
-	surface_normal(T, tg[0], tg[1], nn, fl);  // rrt.cpp:25 — normal at the TARGET sample
-	grf_rotation(nn, R);
-	sample_action(seed, stream, idx0 + (uint64_t) j, R, false, 0.0, nullptr, nullptr, a);
-	Counters c = {0, 0, 0, 0};
-	bool ok = validate_pair_seq<M>(T, s_near, a, direction, adaptive != 0, sn, tn, c);
-	S.valid[j] = ok ? 1 : 0;
-	S.dist[j] = ok ? state_distance(sn, tg) : INFINITY;
-	store_state(S.s_test + 8 * (size_t) j, sn);
-}
-// Stage 3: selection + acceptance + append + status (single CTA)
-__global__ void __launch_bounds__(256) k_extend_select(TerrainView T, TreeView tree, const double *__restrict__ target, int K,
-														int best_of_k, uint64_t seed, uint64_t stream, uint64_t idx0, ExtendScratch S) {
-	__shared__ double sd[8];
-	__shared__ int si[8];
-	// best_of_k: argmin of dist (ties: lowest j); first-valid: lowest valid j
-	double bd = INFINITY;
-	int bi = 0x7fffffff;
-	for (int j = threadIdx.x; j < K; j += blockDim.x) {
-		if (!S.valid[j]) continue;
-		if (best_of_k) argmin_combine(bd, bi, S.dist[j], j);
-		else if (j < bi) { bi = j; bd = S.dist[j]; }
-	}
-	if (!best_of_k) {  // reduce on index only
-		for (int o = 16; o > 0; o >>= 1) {
-			double od = __shfl_xor_sync(FULL, bd, o);
-			int oi = __shfl_xor_sync(FULL, bi, o);
-			if (oi < bi) { bi = oi; bd = od; }
-		}
-	} else {
-		warp_argmin(bd, bi);
-	}
-	if ((threadIdx.x & 31) == 0) { sd[threadIdx.x >> 5] = bd; si[threadIdx.x >> 5] = bi; }
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		for (int w = 1; w < (blockDim.x >> 5); ++w) {
-			if (best_of_k) argmin_combine(bd, bi, sd[w], si[w]);
-			else if (si[w] < bi) { bi = si[w]; bd = sd[w]; }
-		}
-		int status = GBP_TRAPPED, new_id = -1;
-		int checks = best_of_k ? K : (bi == 0x7fffffff ? K : bi + 1);
-		if (bi != 0x7fffffff && *tree.n < tree.cap) {
-			double tg[8], s_near[8], sn[8];
-			for (int d = 0; d < 8; ++d) { tg[d] = target[d]; sn[d] = S.s_test[8 * (size_t) bi + d]; }
-			int near = *S.near_idx;
-			tree_get(tree, near, s_near);
-			if (bd < state_distance(s_near, tg)) {  // rrt.cpp:55-66
-				double nn[3], R[9], a[10];
-				unsigned fl = 0;
-				surface_normal(T, tg[0], tg[1], nn, fl);
-				grf_rotation(nn, R);
-				sample_action(seed, stream, idx0 + (uint64_t) bi, R, false, 0.0, nullptr, nullptr, a);
-				new_id = tree_push(tree, near, sn, a);
-				status = state_distance(sn, tg) <= GOAL_BOUNDS ? GBP_REACHED : GBP_ADVANCED;  // rrt.cpp:96-99
-			}
-		}
-		S.result[0] = status;
-		S.result[1] = new_id;
-		S.result[2] = checks;
-	}
-}
+// (gbp_extend's kernel, k_extend_fused, lives in gbp_planner.cuh next to group_validate)
 
 // ------------------------------------------------------------------ attemptConnect / connect
 template <typename M>

@@ -606,4 +606,138 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	return GBP_OK;
 }
 
+// ------------------------------------------------------------------ extend through the host call (rrt.cpp:20-102)
+// gbp_extend in ONE launch (measured before: k_nearest 4.3 us + k_extend_candidates 12-23 us + k_extend_select 9.7 us and
+// three launch gaps, 56 us per host call).  Every CTA finds the nearest neighbour itself (the same arithmetic and
+// (distance, id) argmin as k_nearest: trees are a few hundred vertices, 64 B each, out of L2), then one thread per
+// candidate j = ACTION cell idx0 + j from s_near (S lanes per candidate on the fixed step); the last CTA to finish (device counter) does selection + acceptance +
+// append + status and writes the result words to device memory and to the caller's mapped host buffer.  The target
+// travels as a kernel argument.
+struct Target8 { double v[8]; };
+template <typename M, bool GROUP>
+__device__ __forceinline__ void extend_fused_body(const TerrainView &T, const TreeView &tree, const Target8 &tgt, int direction, int K, int best_of_k,
+												  int S, uint64_t seed, uint64_t stream, uint64_t idx0, const ExtendScratch &S_,
+												  unsigned *__restrict__ done, int *__restrict__ host_result) {
+	__shared__ double sd[4];
+	__shared__ int si[4];
+	__shared__ int s_near_idx, s_last;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	double tg[8];
+#pragma unroll
+	for (int d = 0; d < 8; ++d) tg[d] = tgt.v[d];
+	// ---- getNearestNeighbor (planner_class.cpp:185-200)
+	{
+		const int nv = *tree.n;
+		double bd = INFINITY;
+		int bi = 0x7fffffff;
+		for (int j = threadIdx.x; j < nv; j += blockDim.x) argmin_combine(bd, bi, vertex_distance(tree, j, tg), j);
+		warp_argmin(bd, bi);
+		if (lane == 0) { sd[wib] = bd; si[wib] = bi; }
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			bd = threadIdx.x < 4 ? sd[threadIdx.x] : INFINITY;
+			bi = threadIdx.x < 4 ? si[threadIdx.x] : 0x7fffffff;
+			warp_argmin(bd, bi);
+			if (threadIdx.x == 0) {
+				s_near_idx = bi == 0x7fffffff ? 0 : bi;  // reference default index 0 (planner_class.cpp:186)
+				if (blockIdx.x == 0) { *S_.near_idx = s_near_idx; *S_.near_dist = bd; }
+			}
+		}
+		__syncthreads();
+	}
+	const int near = s_near_idx;
+	double s_near[8], nn[3], R[9];
+	tree_get(tree, near, s_near);
+	unsigned fl = 0;
+	surface_normal(T, tg[0], tg[1], nn, fl);  // rrt.cpp:25 — normal at the TARGET sample
+	grf_rotation(nn, R);
+	// ---- candidates (newConfig, rrt.cpp:20-70, generalised to K)
+	if (GROUP) {
+		// fixed step: S lanes per candidate speculate its sub-states S at a time (group_validate: only the verdict of a
+		// candidate matters here, the exact end state of a valid one comes from finish_output) — ceil(19 / S) evaluator
+		// passes of latency instead of up to 19
+		const int G = 32 / S, g = lane / S, r = lane - g * S;
+		const int j = (blockIdx.x * 4 + wib) * G + g;
+		const bool has = g < G && j < K;
+		const unsigned gmask = S == 32 ? FULL : ((1u << S) - 1u);
+		double a[10];
+		sample_action(seed, stream, idx0 + (uint64_t) (has ? j : 0), R, false, 0.0, nullptr, nullptr, a);
+		const bool ok = group_validate<M>(T, s_near, a, direction, S, r, gmask, has ? g * S : 0, has);
+		if (has && r == 0) {
+			double sn[8];
+			if (ok) finish_output(s_near, a, direction == GBP_FORWARD ? OUT_LAND : OUT_REV, 0.0, sn);
+			S_.valid[j] = ok ? 1 : 0;
+			S_.dist[j] = ok ? state_distance(sn, tg) : INFINITY;
+			if (ok) store_state(S_.s_test + 8 * (size_t) j, sn);
+		}
+	} else {     // adaptive step: a thread per candidate walks its sub-states in sequence
+		const int j = blockIdx.x * blockDim.x + threadIdx.x;
+		if (j < K) {
+			double a[10], sn[8], tn;
+			sample_action(seed, stream, idx0 + (uint64_t) j, R, false, 0.0, nullptr, nullptr, a);
+			Counters c = {0, 0, 0, 0};
+			const bool ok = validate_pair_seq<M>(T, s_near, a, direction, true, sn, tn, c);
+			S_.valid[j] = ok ? 1 : 0;
+			S_.dist[j] = ok ? state_distance(sn, tg) : INFINITY;
+			store_state(S_.s_test + 8 * (size_t) j, sn);
+		}
+	}
+	// ---- the last CTA selects
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1 ? 1 : 0;
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	// best_of_k: argmin of dist (ties: lowest j); first-valid: lowest valid j
+	double bd = INFINITY;
+	int bi = 0x7fffffff;
+	for (int c = threadIdx.x; c < K; c += blockDim.x) {
+		if (!__ldcg(S_.valid + c)) continue;
+		if (best_of_k) argmin_combine(bd, bi, __ldcg(S_.dist + c), c);
+		else if (c < bi) { bi = c; bd = __ldcg(S_.dist + c); }
+	}
+	if (!best_of_k) {  // reduce on index only
+		for (int o = 16; o > 0; o >>= 1) {
+			const double od = __shfl_xor_sync(FULL, bd, o);
+			const int oi = __shfl_xor_sync(FULL, bi, o);
+			if (oi < bi) { bi = oi; bd = od; }
+		}
+	} else {
+		warp_argmin(bd, bi);
+	}
+	if (lane == 0) { sd[wib] = bd; si[wib] = bi; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < 4; ++w) {
+			if (best_of_k) argmin_combine(bd, bi, sd[w], si[w]);
+			else if (si[w] < bi) { bi = si[w]; bd = sd[w]; }
+		}
+		int status = GBP_TRAPPED, new_id = -1;
+		const int checks = best_of_k ? K : (bi == 0x7fffffff ? K : bi + 1);
+		if (bi != 0x7fffffff && *tree.n < tree.cap && bd < state_distance(s_near, tg)) {  // rrt.cpp:55-66
+			double sn[8], a[10];
+			for (int d = 0; d < 8; ++d) sn[d] = __ldcg(S_.s_test + 8 * (size_t) bi + d);
+			sample_action(seed, stream, idx0 + (uint64_t) bi, R, false, 0.0, nullptr, nullptr, a);
+			new_id = tree_push(tree, near, sn, a);
+			status = state_distance(sn, tg) <= GOAL_BOUNDS ? GBP_REACHED : GBP_ADVANCED;  // rrt.cpp:96-99
+		}
+		S_.result[0] = status; S_.result[1] = new_id; S_.result[2] = checks;
+		host_result[0] = status; host_result[1] = new_id; host_result[2] = checks;
+		*done = 0;  // ready for the next call on this tree
+	}
+}
+template <typename M>
+__global__ void __launch_bounds__(128) k_extend_fused(TerrainView T, TreeView tree, Target8 tgt, int direction, int K, int best_of_k,
+													   int lanes_per_candidate, uint64_t seed, uint64_t stream, uint64_t idx0, ExtendScratch S,
+													   unsigned *__restrict__ done, int *__restrict__ host_result) {
+	extend_fused_body<M, true>(T, tree, tgt, direction, K, best_of_k, lanes_per_candidate, seed, stream, idx0, S, done, host_result);
+}
+template <typename M>
+__global__ void __launch_bounds__(128) k_extend_fused_adaptive(TerrainView T, TreeView tree, Target8 tgt, int direction, int K, int best_of_k,
+																int unused, uint64_t seed, uint64_t stream, uint64_t idx0, ExtendScratch S,
+																unsigned *__restrict__ done, int *__restrict__ host_result) {
+	extend_fused_body<M, false>(T, tree, tgt, direction, K, best_of_k, 1, seed, stream, idx0, S, done, host_result);
+}
+
 }  // namespace gbp
