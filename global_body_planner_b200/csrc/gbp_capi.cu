@@ -1097,13 +1097,14 @@ int gbp_new_config(const gbp_terrain *t, const double *target, const double *s_n
 int gbp_connect(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int adaptive, int *status, int *new_id) {
 	if (!T || !t || !target || (direction != GBP_FORWARD && direction != GBP_REVERSE)) return fail(GBP_E_INVALID, "bad arguments");
 	cudaStream_t st = lib_stream();
-	CU(cudaMemcpyAsync(T->d_target, target, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
-	k_nearest<<<1, 256, 0, st>>>(T->view, 1, T->d_target, T->S.near_idx, T->S.near_dist);
-	GBP_DISPATCH(t->view, k_connect, (1, 32), st, t->view, T->view, T->d_target, direction, adaptive, T->S);
+	Target8 tg;
+	memcpy(tg.v, target, sizeof tg.v);
+	int *dres = nullptr;
+	CU(cudaHostGetDevicePointer((void **) &dres, T->h_result, 0));
+	GBP_DISPATCH(t->view, k_connect, (1, 32), st, t->view, T->view, tg, direction, adaptive, T->S, dres);
 	CU(cudaGetLastError());
-	int res[4] = {0, -1, 0, 0};
-	CU(cudaMemcpyAsync(res, T->S.result, sizeof res, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	const int res[3] = {T->h_result[0], T->h_result[1], T->h_result[2]};
 	if (status) *status = res[0];
 	if (new_id) *new_id = res[1];
 	return GBP_OK;

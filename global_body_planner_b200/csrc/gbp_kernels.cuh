@@ -1005,26 +1005,60 @@ __global__ void __launch_bounds__(128) k_attempt_connect(TerrainView T, int64_t 
 	for (int d = 0; d < 10; ++d) a_new[10 * i + d] = an[d];
 	if (flags) flags[i] = (uint8_t) c.flags;
 }
-// connect (rrt_connect.cpp:98-120) after k_nearest put the neighbour into S.near_idx
+// attemptConnect with the pair check spread over the warp (validate_pair_warp: a lane per sub-state, identical outputs);
+// connect primitives are long (t_s = distance / 0.75: a 4 m connection is 107 sub-states).  Fixed step only; all lanes
+// call with uniform arguments and get uniform results.
 template <typename M>
-__global__ void k_connect(TerrainView T, TreeView tree, const double *__restrict__ target, int direction, int adaptive,
-						  ExtendScratch S) {
-	if (threadIdx.x != 0) return;
+__device__ int attempt_connect_warp(const TerrainView &T, const double s_existing[8], const double s_in[8], int direction, double s_new[8],
+									double a_new[10], Counters &c, unsigned &pair_checks) {
+	double target[8], ts = pose_distance(s_in, s_existing) / V_NOM;  // rrt_connect.cpp:29
+#pragma unroll
+	for (int i = 0; i < 8; ++i) target[i] = s_in[i];
+	for (int depth = 0;; ++depth) {
+		if (ts <= KINEMATICS_RES) return GBP_TRAPPED;
+		if (direction == GBP_FORWARD) connect_action(s_existing, target, ts, a_new);
+		else connect_action(target, s_existing, ts, a_new);
+		if (!is_valid_action(a_new)) return GBP_TRAPPED;
+		double out[8], tn;
+		++pair_checks;
+		const bool ok = validate_pair_warp<M>(T, s_existing, a_new, direction, out, tn, c);
+#pragma unroll
+		for (int i = 0; i < 8; ++i) { s_new[i] = out[i]; target[i] = out[i]; }
+		if (ok) return depth == 0 ? GBP_REACHED : GBP_ADVANCED;
+		ts = tn;
+	}
+}
+// gbp_connect in one launch of one warp (rrt_connect.cpp:98-120): nearest neighbour by the warp (same arithmetic and
+// (distance, id) argmin as k_nearest), attemptConnect, append; the target travels as a kernel argument and the result
+// words also go to the caller's mapped host buffer.
+struct Target8 { double v[8]; };
+template <typename M>
+__global__ void __launch_bounds__(32) k_connect(TerrainView T, TreeView tree, Target8 tgt, int direction, int adaptive, ExtendScratch S,
+												  int *__restrict__ host_result) {
+	const int lane = threadIdx.x;
 	double tg[8], s_near[8], sn[8], an[10];
-	for (int d = 0; d < 8; ++d) tg[d] = target[d];
-	int near = *S.near_idx;
+#pragma unroll
+	for (int d = 0; d < 8; ++d) tg[d] = tgt.v[d];
+	const int nv = *tree.n;
+	double bd = INFINITY;
+	int bi = 0x7fffffff;
+	for (int j = lane; j < nv; j += 32) argmin_combine(bd, bi, vertex_distance(tree, j, tg), j);
+	warp_argmin(bd, bi);
+	const int near = bi == 0x7fffffff ? 0 : bi;  // reference default index 0 (planner_class.cpp:186)
 	tree_get(tree, near, s_near);
 	Counters c = {0, 0, 0, 0};
 	unsigned checks = 0;
-	int r = attempt_connect<M>(T, s_near, tg, direction, adaptive != 0, sn, an, c, checks);
+	int r = adaptive ? attempt_connect<M>(T, s_near, tg, direction, true, sn, an, c, checks)
+					 : attempt_connect_warp<M>(T, s_near, tg, direction, sn, an, c, checks);
+	if (lane != 0) return;
+	*S.near_idx = near; *S.near_dist = bd;
 	int new_id = -1;
 	if (r != GBP_TRAPPED) {
-		if (*tree.n < tree.cap) new_id = tree_push(tree, near, sn, an);
+		if (nv < tree.cap) new_id = tree_push(tree, near, sn, an);
 		else r = GBP_TRAPPED;
 	}
-	S.result[0] = r;
-	S.result[1] = new_id;
-	S.result[2] = (int) checks;
+	S.result[0] = r; S.result[1] = new_id; S.result[2] = (int) checks;
+	host_result[0] = r; host_result[1] = new_id; host_result[2] = (int) checks;
 }
 
 }  // namespace gbp

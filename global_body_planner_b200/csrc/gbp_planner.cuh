@@ -613,7 +613,6 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 // candidate j = ACTION cell idx0 + j from s_near (S lanes per candidate on the fixed step); the last CTA to finish (device counter) does selection + acceptance +
 // append + status and writes the result words to device memory and to the caller's mapped host buffer.  The target
 // travels as a kernel argument.
-struct Target8 { double v[8]; };
 template <typename M, bool GROUP>
 __device__ __forceinline__ void extend_fused_body(const TerrainView &T, const TreeView &tree, const Target8 &tgt, int direction, int K, int best_of_k,
 												  int S, uint64_t seed, uint64_t stream, uint64_t idx0, const ExtendScratch &S_,

@@ -30,3 +30,13 @@ for i in range(20, len(targets)):
 dt = time.perf_counter() - t0
 n = len(targets) - 20
 print(f"K={K}: {dt / n * 1e6:.1f} us per extend, {n * K / dt / 1e6:.1f} M validated actions/s, {added} of {n} extends added a vertex")
+# gbp_connect against the grown tree (rrt_connect.cpp:98-120): nearest neighbour + attemptConnect + append per call
+ctargets = targets[: min(300, len(targets))]
+n0 = tree.size() if hasattr(tree, "size") else None
+for tg in ctargets[:10]:
+    tree.connect(t, tg, gbp.FORWARD)
+t0 = time.perf_counter()
+res = [tree.connect(t, tg, gbp.FORWARD)[0] for tg in ctargets]
+dt = time.perf_counter() - t0
+print(f"connect: {dt / len(ctargets) * 1e6:.1f} us per call, statuses trapped/advanced/reached = "
+      f"{res.count(gbp.TRAPPED)}/{res.count(gbp.ADVANCED)}/{res.count(gbp.REACHED)}")
