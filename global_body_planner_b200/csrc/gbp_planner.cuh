@@ -365,7 +365,9 @@ __device__ int warp_connect(const TerrainView &Tv, PlanTree &T, int &nv, const d
 	tree_get(T.t, near, s_near);
 	Counters c = {0, 0, 0, 0};
 	unsigned checks = 0;
-	const int r = attempt_connect<M>(Tv, s_near, s, dir, P.adaptive != 0, sn, an, c, checks);
+	// fixed step: the connect primitive's sub-states 32 at a time over the lanes instead of one after the other on all of them
+	const int r = P.adaptive ? attempt_connect<M>(Tv, s_near, s, dir, true, sn, an, c, checks)
+							 : attempt_connect_warp<M>(Tv, s_near, s, dir, sn, an, c, checks);
 	pair_checks += checks;
 	if (r != GBP_TRAPPED) {
 		if (lane == 0) plan_push(T, near, sn, an);
