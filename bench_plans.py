@@ -12,7 +12,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-Q_PER_GPU = 65536  # BASELINE configs[4]'s batch on every GPU (weak scaling); 8192 per launch measured 28.5 k plans/s, 65536 30.7 k (fewer partial waves)
+Q_PER_GPU = 65536  # BASELINE configs[4]'s batch on every GPU (weak scaling); 8192 per launch measured 30.8 k plans/s, 65536 33.8 k (fewer partial waves)
 MAP_N, PITCH, BLOCK, STEP_H = 1024, 0.05, 8, 0.1
 MAX_ITERS, MAX_VERTS, K_CAND = 2000, 512, 6
 
