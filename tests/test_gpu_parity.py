@@ -173,17 +173,20 @@ def test_extend_matches_oracle(gbp, dev):
     """gbp_extend (NN + K candidates + selection + append) against the oracle's newConfig."""
     t, o, T, G, name = dev
     s = G["pair_states"]
-    for K, best in ((6, 0), (256, 1), (256, 0)):
+    # K x lanes per candidate of k_extend_fused on a 148-SM part: 6 / 256 -> 32, 2000 -> 16, 4096 -> 8, 40000 -> 1; the
+    # adaptive step takes the thread-per-candidate kernel
+    for K, best, adaptive in ((6, 0, False), (256, 1, False), (256, 0, False), (2000, 0, False), (4096, 1, False), (40000, 1, False),
+                              (6, 0, True), (300, 1, True)):
         tree = gbp.Tree(512)
         tree.load(s[:200])
-        for trial in range(12):
+        for trial in range(12 if K <= 256 else 4):
             target = s[300 + trial]
             near, _, _ = o.nearest(s[:200], target[None])
             s_near = s[int(near[0])]
             normal = o.surface_normal(target[:1], target[1:2])[0]
             a = o.sample_actions(9, 4, trial * K, K, normal)
             direction = trial % 2
-            vo, _, sno, _, _ = o.validate_pairs(np.repeat(s_near[None], K, 0), a, direction)
+            vo, _, sno, _, _ = o.validate_pairs(np.repeat(s_near[None], K, 0), a, direction, adaptive=adaptive, nthreads=8)
             d = o.distance(sno, np.repeat(target[None], K, 0), 1)
             base = o.distance(s_near[None], target[None], 1)[0]
             exp = None
@@ -192,7 +195,7 @@ def test_extend_matches_oracle(gbp, dev):
                 if d[j] < base:
                     exp = j
             before = tree.size()
-            st, nid, chk = tree.extend(t, target, direction, K, best, 9, 4, trial * K)
+            st, nid, chk = tree.extend(t, target, direction, K, best, 9, 4, trial * K, adaptive=adaptive)
             if exp is None:
                 assert st == gbp.TRAPPED and tree.size() == before
             else:
