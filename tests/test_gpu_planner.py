@@ -38,7 +38,9 @@ def queries(o, T, n, seed):
                                                   ("synth_nan", 6, 0, 0, 0), ("slope", 6, 0, 0, 1), ("synth_nan", 24, 1, 0, 1),
                                                   ("slope", 32, 1, 1, 0), ("synth_nan", 32, 1, 1, 1), ("rough_terrain", 32, 1, 1, 0),
                                                   # fp32 NaN-free map on uniform axes: the mixed-precision / texture-gather evaluator
-                                                  ("synth_mixed", 6, 0, 0, 0), ("synth_mixed", 24, 1, 0, 1), ("synth_mixed", 32, 1, 1, 1)])
+                                                  ("synth_mixed", 6, 0, 0, 0), ("synth_mixed", 24, 1, 0, 1), ("synth_mixed", 32, 1, 1, 1),
+                                                  # closest-valid over more than a warp of candidates (several batches of 32 per newConfig)
+                                                  ("rough_terrain", 200, 1, 0, 0), ("synth_mixed", 100, 1, 0, 1), ("slope", 70, 1, 1, 0)])
 def test_plan_batch_matches_oracle(gbp, name, K, best, star, post):
     """RRT-Connect, RRT*-Connect (choose parent + rewire) and postProcessPath, all resident on the device."""
     T = load_terrain(name)
