@@ -151,7 +151,7 @@ __device__ __forceinline__ GroupMap make_group_map(int K, int lane) {
 }
 
 // newConfig (rrt.cpp:20-70) generalised to K candidates; uniform outputs.  Returns found.
-template <typename M>
+template <typename M, bool WIDE = false>
 __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const double s_near[8], int dir, uint64_t seed, uint64_t query,
 								uint64_t cell, const gbp_plan_params &P, const GroupMap &gm, int lane, long long &pair_checks, double s_new[8], double a_new[10]) {
 	double nn[3], R[9];
@@ -162,7 +162,54 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 	const int K = P.k_candidates;
 	double my_d = INFINITY, my_sn[8], my_a[10];
 	int my_j = 0x7fffffff, first = 0x7fffffff;
-	if (!P.adaptive) {
+	if (WIDE) {
+		// Closest valid of MANY candidates at the fixed step (configs[1]: K = 4096; the launcher picks this instantiation
+		// for best_of_k, K > 32, no adaptive step): lane per candidate with warp-level REFILL, as in the walk kernels — a
+		// lane whose candidate has failed (k = 2-4 sub-states on average) or landed takes the next candidate index instead
+		// of idling until the slowest lane of a batch of 32 (up to 19 sub-states) is through.  Idle lanes are refilled once
+		// a quarter of the warp is idle, so that sampling stays mostly convergent.  Every candidate is evaluated exactly as
+		// in the batched form, and the (distance, index) argmin below does not depend on which lane evaluated which
+		// candidate: results are identical.  A separate instantiation because inlined next to the K = 6 path it cost that
+		// path 6.5 % (instruction fetch) and out of line 40 % (stack).
+		Cursor q;
+#pragma unroll
+		for (int i = 0; i < 8; ++i) q.s[i] = s_near[i];
+		int next = 0, j = -1;
+		bool running = false;
+		while (true) {
+			const unsigned idle = __ballot_sync(FULL, !running);
+			if (next < K && (__popc(idle) >= 8 || idle == FULL)) {
+				if (!running) {
+					const int rel = next + __popc(idle & ((1u << lane) - 1u));
+					if (rel < K) {
+						j = rel;
+						sample_action(seed, query, cell * (uint64_t) K + (uint64_t) j, R, false, 0.0, nullptr, nullptr, q.a);
+						cursor_start(q, dir);
+						running = true;
+					}
+				}
+				next = min(K, next + __popc(idle));
+			}
+			if (__ballot_sync(FULL, running) == 0) break;
+			if (running) {
+				const bool valid = cursor_check<M>(Tv, q);
+				if (!valid) running = false;
+				else if (q.phase == PH_FWD_LAND || q.phase == PH_REV_START) {  // every sub-state valid: exact end state, distance to the target
+					double sn[8];
+					finish_output(s_near, q.a, dir == GBP_FORWARD ? OUT_LAND : OUT_REV, 0.0, sn);
+					const double d = state_distance(sn, s);
+					if (d < my_d) {
+						my_d = d; my_j = j;
+#pragma unroll
+						for (int i = 0; i < 8; ++i) my_sn[i] = sn[i];
+#pragma unroll
+						for (int i = 0; i < 10; ++i) my_a[i] = q.a[i];
+					}
+					running = false;
+				} else walk_step(q.phase, q.t, q.a[6], q.a[7]);
+			}
+		}
+	} else if (!P.adaptive) {
 		// speculative form: G candidates per pass, S lanes each
 		const int S = gm.S, G = gm.G, g = gm.g, r = gm.r, gshift = gm.gshift;
 		const unsigned gmask = gm.gmask;
@@ -249,13 +296,13 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 }
 
 // RRTClass::extend (rrt.cpp:77-102)
-template <typename M>
+template <typename M, bool WIDE = false>
 __device__ int warp_extend(const TerrainView &Tv, PlanTree &T, int &nv, const double s[8], int dir, uint64_t seed, uint64_t query,
 						   uint64_t cell, const gbp_plan_params &P, const GroupMap &gm, int lane, long long &pair_checks) {
 	const int near = warp_nearest(T.t, nv, s, lane);
 	double s_near[8], sn[8], a[10];
 	tree_get(T.t, near, s_near);
-	if (!warp_new_config<M>(Tv, s, s_near, dir, seed, query, cell, P, gm, lane, pair_checks, sn, a)) return GBP_TRAPPED;
+	if (!warp_new_config<M, WIDE>(Tv, s, s_near, dir, seed, query, cell, P, gm, lane, pair_checks, sn, a)) return GBP_TRAPPED;
 	if (lane == 0) plan_push(T, near, sn, a);
 	__syncwarp();
 	nv += 1;
@@ -429,7 +476,7 @@ __device__ int warp_post_process(const TerrainView &Tv, double *ps, double *pa, 
 	return m;
 }
 
-template <typename M, bool STAR>
+template <typename M, bool STAR, bool WIDE = false>
 // Occupancy over registers: the kernel is 21 k SASS instructions and its warps sit at unrelated program counters, so
 // at 255 registers (8 warps / SM) ncu shows 8.3 of the 12.2 cycles between two issues of a warp waiting for
 // instruction fetch (profiles/r1b_planner_2ctas_ncu_summary.csv).  Capping the registers at 80 (24 warps / SM, ~2.7 KB of
@@ -492,7 +539,7 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 				for (int d = 0; d < 8; ++d) s_rand[d] = __shfl_sync(FULL, rs[d], src);
 				++nn_queries;
 				const int r = STAR ? warp_extend_star<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, gm, A, (int) slot, lane, pair_checks)
-								   : warp_extend<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, gm, lane, pair_checks);
+								   : warp_extend<M, WIDE>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, gm, lane, pair_checks);
 				if (r == GBP_TRAPPED) continue;
 				double s_new[8];
 				tree_get(Tx.t, nx - 1, s_new);
@@ -598,7 +645,9 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 		unsigned long long *next_query = (unsigned long long *) (counts + 2 * slots);
 		if ((e = cudaMemsetAsync(next_query, 0, sizeof(unsigned long long) + 2 * sizeof(int), st)) != cudaSuccess) { err = cudaGetErrorString(e); return GBP_E_CUDA; }
 	}
+	const bool wide = !P.rrt_star && !P.adaptive && P.best_of_k && P.k_candidates > 32;  // the refill form of newConfig
 #define GBP_PLAN_(M) do { if (P.rrt_star) k_plan_batch<M, true><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); \
+						  else if (wide) k_plan_batch<M, false, true><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); \
 						  else k_plan_batch<M, false><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); } while (0)
 	if (Tv.cell_f32) { if (Tv.uniform) GBP_PLAN_(MapF32U); else GBP_PLAN_(MapF32N); }
 	else { if (Tv.uniform) GBP_PLAN_(MapF64U); else GBP_PLAN_(MapF64N); }
