@@ -4,27 +4,48 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libgbp_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", "gbp_capi.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("gbp_device.cuh", "gbp_kernels.cuh", "gbp_planner.cuh", "gbp_walk.cuh")] + \
-          [os.path.join(HERE, "..", "include", "gbp_b200.h")]
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")  # git-ignored and gpurun-ignored: only the linked .so travels
+PUBLIC_H = os.path.join(HERE, "..", "include", "gbp_b200.h")
+_COMMON = ["gbp_device.cuh", "gbp_kernels.cuh", "gbp_host.h"]
+# translation unit -> private headers it includes (the three units compile in parallel)
+UNITS = {"gbp_capi.cu": _COMMON,
+         "gbp_capi_validate.cu": _COMMON + ["gbp_walk.cuh", "gbp_sv.cuh"],
+         "gbp_capi_plan.cu": _COMMON + ["gbp_planner.cuh"]}
+SOURCES = [os.path.join(CSRC, u) for u in UNITS]
+HEADERS = sorted({os.path.join(CSRC, h) for hs in UNITS.values() for h in hs}) + [PUBLIC_H]
 # -fmad=false: fp64 results must match the reference's x86-64 (no FMA) arithmetic bit for bit.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(f) > t for f in deps)
 
 
 def stale():
-    if not os.path.exists(SO):
-        return True
-    t = os.path.getmtime(SO)
-    return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS)
+    return _newer(SO, SOURCES + HEADERS)
 
 
 def build(force=False, verbose=False):
     if not force and not stale():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
-    subprocess.run(cmd, check=True)
+    os.makedirs(OBJ, exist_ok=True)
+    jobs, objs = [], []
+    for unit, hdrs in UNITS.items():
+        src, obj = os.path.join(CSRC, unit), os.path.join(OBJ, unit[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [src, PUBLIC_H] + [os.path.join(CSRC, h) for h in hdrs]):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+            jobs.append((unit, subprocess.Popen(cmd)))
+    failed = [unit for unit, p in jobs if p.wait() != 0]
+    if failed:
+        raise subprocess.CalledProcessError(1, "nvcc " + " ".join(failed))
+    subprocess.run([nvcc, "-shared", "-o", SO] + objs, check=True)
     return SO
 
 

@@ -24,6 +24,29 @@ class PlanParams(C.Structure):
                 ("adaptive", C.c_int), ("rrt_star", C.c_int), ("post_process", C.c_int), ("stop_after_solved", C.c_int)]
 
 
+class SvParams(C.Structure):
+    """gbp_sv_params (include/gbp_b200.h): the per-call part of a sample + validate batch."""
+    _fields_ = [("seed", C.c_uint64), ("stream", C.c_uint64), ("idx0", C.c_uint64), ("normal", C.c_double * 3),
+                ("adaptive", C.c_int), ("direction0", C.c_int), ("action_direction_sampling", C.c_int),
+                ("action_direction_threshold", C.c_double), ("target", C.c_double * 8), ("row0", C.c_int64)]
+
+
+class SvResult(C.Structure):
+    _fields_ = [("n_valid", C.c_int64), ("substates", C.c_int64), ("lookups", C.c_int64), ("nanprobes", C.c_int64),
+                ("oog", C.c_int64), ("near", C.c_int64), ("reserved", C.c_int64 * 2)]
+
+
+def sv_params(seed, stream, idx0, normal=(0.0, 0.0, 1.0), adaptive=False, direction0=0, target=None, thresh=0.0, row0=0):
+    p = SvParams()
+    p.seed, p.stream, p.idx0 = seed, stream, idx0
+    p.normal[:] = [float(v) for v in normal]
+    p.adaptive, p.direction0, p.row0 = int(adaptive), int(direction0), int(row0)
+    p.action_direction_sampling = 0 if target is None else 1
+    p.action_direction_threshold = float(thresh)
+    p.target[:] = [0.0] * 8 if target is None else [float(v) for v in target]
+    return p
+
+
 PLAN_STATS_DTYPE = np.dtype([("solved", "i4"), ("iters", "i4"), ("nv_a", "i4"), ("nv_b", "i4"), ("path_states", "i4"),
                              ("pad", "i4"), ("path_length", "f8"), ("path_yaw", "f8"), ("path_duration", "f8"),
                              ("pair_checks", "i8"), ("nn_queries", "i8")])
@@ -139,6 +162,28 @@ def own_map_layer(seed, x_size=221, y_size=161, x_start=-0.5, y_start=-4.0, res=
     _check(lib().gbp_own_map_layer(C.c_uint64(seed), x_size, y_size, C.c_double(x_start), C.c_double(y_start), C.c_double(res),
                                    0 if r is None else len(r), _p(r), _p(elev), _p(geom)))
     return elev, geom
+
+
+class States:
+    """Device-resident table of start states (gbp_states): the vertices sample + validate candidates start from."""
+
+    def __init__(self, states):
+        s = _f64(states, (-1, 8))
+        h = C.c_void_p()
+        _check(lib().gbp_states_create(C.c_int64(len(s)), _p(s), C.byref(h)))
+        self.h, self.rows = h, len(s)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().gbp_states_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def unpack_bits(bits, n):
+    """verdict words -> one 0/1 byte per candidate"""
+    return np.unpackbits(np.ascontiguousarray(bits, dtype="<u4").view(np.uint8), bitorder="little")[:n]
 
 
 class Terrain:
@@ -260,6 +305,36 @@ class Terrain:
         vp = lambda p: C.c_void_p(p) if p else None
         _check(lib().gbp_validate_pairs_dev(self.h, C.c_int64(n), vp(states_ptr), vp(actions_ptr), vp(dir_ptr), int(adaptive),
                                             int(variant), vp(verdict_ptr), vp(flags_ptr), vp(snew_ptr), vp(tnew_ptr), vp(stream)))
+
+    def sample_validate(self, table, n, params, state_idx=None, direction=None, valid_cap=None, want_flags=True, rows=True):
+        """newConfig's unit of work (rrt.cpp:34-50) on HOST arrays through the narrow wire format: -> dict with the
+        verdict words, the unpacked verdicts, optional flags, the compact rows of the valid candidates and the result."""
+        idx = None if state_idx is None else np.ascontiguousarray(state_idx, dtype=np.int32)
+        d = None if direction is None else _u8(direction, n)
+        cap = n if valid_cap is None else int(valid_cap)
+        bits = np.zeros((n + 31) // 32, np.uint32)
+        fl = np.zeros(n, np.uint8) if want_flags else None
+        vi = np.zeros(cap, np.int32)
+        sn = np.zeros((cap, 8)) if rows else None
+        tn = np.zeros(cap) if rows else None
+        ac = np.zeros((cap, 10)) if rows else None
+        res = SvResult()
+        _check(lib().gbp_sample_validate(self.h, table.h, C.c_int64(n), _p(idx), _p(d), C.byref(params), _p(bits), _p(fl), C.c_int64(cap),
+                                         _p(vi), _p(sn), _p(tn), _p(ac), C.byref(res)))
+        m = min(res.n_valid, cap)
+        out = dict(bits=bits, verdict=unpack_bits(bits, n), flags=fl, index=vi[:m], n_valid=res.n_valid,
+                   counters=dict(substates=res.substates, lookups=res.lookups, nanprobes=res.nanprobes, oog=res.oog, near=res.near))
+        if rows:
+            out.update(s_new=sn[:m], t_new=tn[:m], action=ac[:m])
+        return out
+
+    def sample_validate_dev(self, states_ptr, n, params, idx_ptr, dir_ptr, bits_ptr, flags_ptr, valid_cap, index_ptr, snew_ptr, tnew_ptr,
+                            action_ptr, result_ptr, stream=0):
+        """Device pointers (ints) in, enqueue only."""
+        vp = lambda q: C.c_void_p(q) if q else None
+        _check(lib().gbp_sample_validate_dev(self.h, vp(states_ptr), C.c_int64(n), vp(idx_ptr), vp(dir_ptr), C.byref(params), vp(bits_ptr),
+                                             vp(flags_ptr), C.c_int64(valid_cap), vp(index_ptr), vp(snew_ptr), vp(tnew_ptr), vp(action_ptr),
+                                             vp(result_ptr), vp(stream)))
 
     def validate_counters(self):
         c = np.zeros(6, np.int64)

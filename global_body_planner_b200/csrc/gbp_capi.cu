@@ -2,136 +2,20 @@
 // HOST buffers through a chunked copy/compute pipeline, kernel selection and launch geometry.
 // No torch types, no CPU fallback: without a CUDA device every compute entry point fails with
 // GBP_E_CUDA.
-#include <cfloat>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
 #include <fstream>
 #include <sstream>
-#include <string>
-#include <vector>
 
-#include "gbp_kernels.cuh"
-#include "gbp_planner.cuh"
-#include "gbp_walk.cuh"
+#include "gbp_host.h"
 
-using namespace gbp;
-
-namespace {
-
-thread_local std::string g_err;
-int fail(int code, const std::string &msg) { g_err = msg; return code; }
-
-#define CU(call)                                                                                          \
-	do {                                                                                                  \
-		cudaError_t e_ = (call);                                                                          \
-		if (e_ != cudaSuccess) return fail(GBP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
-	} while (0)
-
-int sm_count() {
-	static int sms = 0;
-	if (!sms) {
-		int dev = 0;
-		if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-			sms = 148;
-	}
-	return sms;
+std::string &gbp_err() {
+	static thread_local std::string e;
+	return e;
 }
-
-// stream-ordered device scratch; the pool keeps freed blocks, so repeated calls do not hit the driver
-struct Dev {
-	void *p = nullptr;
-	cudaStream_t st;
-	explicit Dev(cudaStream_t s) : st(s) {}
-	cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
-	~Dev() { if (p) cudaFreeAsync(p, st); }
-	template <class T> T *as() { return (T *) p; }
-};
-
-cudaStream_t lib_stream() {
-	static thread_local cudaStream_t s = nullptr;
-	if (!s) {
-		if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
-		int dev = 0;
-		cudaMemPool_t pool;
-		if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-			unsigned long long keep = ~0ull;
-			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-		}
-	}
-	return s;
-}
-
-template <class T>
-int upload(Dev &d, const T *host, size_t n, cudaStream_t st) {
-	CU(d.alloc(n * sizeof(T)));
-	if (n) CU(cudaMemcpyAsync(d.p, host, n * sizeof(T), cudaMemcpyHostToDevice, st));
-	return GBP_OK;
-}
-
-// kernel instantiation by map kind: fp32 / fp64 cells x uniform / general axes
-#define GBP_LAUNCH_(K, M, CFG, ST, ...) K<M><<<GBP_UNPACK CFG, 0, ST>>>(__VA_ARGS__)
-#define GBP_UNPACK(...) __VA_ARGS__
-#define GBP_DISPATCH(VIEW, K, CFG, ST, ...)                                                  \
-	do {                                                                                     \
-		if ((VIEW).cell_f32) {                                                               \
-			if ((VIEW).uniform) GBP_LAUNCH_(K, MapF32U, CFG, ST, __VA_ARGS__);               \
-			else GBP_LAUNCH_(K, MapF32N, CFG, ST, __VA_ARGS__);                              \
-		} else {                                                                             \
-			if ((VIEW).uniform) GBP_LAUNCH_(K, MapF64U, CFG, ST, __VA_ARGS__);               \
-			else GBP_LAUNCH_(K, MapF64N, CFG, ST, __VA_ARGS__);                              \
-		}                                                                                    \
-	} while (0)
-
-inline unsigned blocks_for(int64_t n, int threads) { return (unsigned) ((n + threads - 1) / threads); }
-}  // namespace
-
-// Staging pipeline of the HOST-pointer pair check: ring of device buffer sets, one stream each, kept by the
-// terrain handle between calls (grow-only) so that a call costs copies + kernels, not allocations.
-struct HostPipe {
-	static constexpr int NBUF = 3;
-	cudaStream_t st[NBUF] = {nullptr, nullptr, nullptr};
-	char *in[NBUF] = {nullptr, nullptr, nullptr}, *out[NBUF] = {nullptr, nullptr, nullptr};
-	int *redo[NBUF] = {nullptr, nullptr, nullptr};
-	int64_t chunk = 0;  // candidates per buffer set
-};
-
-struct gbp_terrain {
-	TerrainView view;
-	HostPipe pipe;
-	double *d_x = nullptr, *d_y = nullptr;
-	void *d_z = nullptr;
-	void *d_n = nullptr;
-	cudaArray_t z_arr = nullptr;          // block-linear copy of the fp32 height grid behind view.ztex (texture gathers of the walk)
-	cudaTextureObject_t z_tex = 0;
-	unsigned long long *d_cnt = nullptr;  // 6 work counters of the last validate launch
-	int *d_redo = nullptr;                // redo list of the mixed-precision walk: [redo_cap] indices + an 8-byte counter
-	size_t redo_cap = 0;
-	void *d_plan_arena = nullptr;         // tree arena of the batch planner (grow-only)
-	size_t plan_arena_bytes = 0;
-	size_t z_bytes = 0;                   // height grid bytes
-	float l2_hit_ratio = 0.f;             // share of the grid that fits the persisting L2 carve-out (0 = no window)
-	std::vector<double> hx, hy;
-	int cell_bytes = 8;
-};
-
-struct gbp_tree {
-	TreeView view;
-	int *d_n = nullptr;
-	double *d_v = nullptr, *d_act = nullptr, *d_g = nullptr, *d_y = nullptr;
-	int *d_parent = nullptr;
-	// scratch of extend/connect
-	ExtendScratch S;
-	int k_cap = 0;
-	double *d_target = nullptr;
-	unsigned *d_done = nullptr;  // CTA counter of k_extend_fused
-	int *h_result = nullptr;     // pinned, mapped: the result words of an extend without a copy
-};
 
 extern "C" {
 
-const char *gbp_last_error(void) { return g_err.c_str(); }
+
+const char *gbp_last_error(void) { return gbp_err().c_str(); }
 const char *gbp_version(void) { return "gbp_b200 0.1 (sm_100a, fp64 exact path)"; }
 int gbp_device_count(int *count) {
 	int n = 0;
@@ -639,177 +523,6 @@ int gbp_max_curvature(int64_t n, const double *states, double *max_curvature) {
 	return GBP_OK;
 }
 
-// ------------------------------------------------------------------------------ validate_pairs
-static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
-							 int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream,
-							 bool zero_counters);
-int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
-						   int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream) {
-	return validate_dev_impl(t, n, states, actions, direction, adaptive, variant, verdict, flags, s_new, t_new, stream, true);
-}
-static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
-							 int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream,
-							 bool zero_counters) {
-	if (!t || n < 0 || (n && (!states || !actions || !direction || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
-	if (variant < 0 || variant > 5 || variant == 4) return fail(GBP_E_INVALID, "variant must be 0..3 or 5");
-	const bool walk_only = variant == 5;
-	if (walk_only) variant = 3;
-	if (variant == 2 && adaptive) return fail(GBP_E_INVALID, "variant 2 (warp per action) supports the fixed step only");
-	cudaStream_t st = (cudaStream_t) stream;
-	if (zero_counters) CU(cudaMemsetAsync(t->d_cnt, 0, 6 * sizeof(unsigned long long), st));
-	if (n == 0) return GBP_OK;
-	if (variant == 0) variant = 3;
-	if (variant == 1) {
-		GBP_DISPATCH(t->view, k_validate_thread, (blocks_for(n, 128), 128), st, t->view, n, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt);
-	} else if (variant == 2) {
-		const int64_t warps_per_block = 4;
-		unsigned grid = (unsigned) ((n + warps_per_block - 1) / warps_per_block);
-		GBP_DISPATCH(t->view, k_validate_warp, (grid, 128), st, t->view, n, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt);
-	} else {
-		// persistent-style geometry: a multiple of the SM count; each warp owns a contiguous range
-		const int threads = RF_WARPS * 32, warps_per_block = RF_WARPS;
-		int64_t max_warps = (int64_t) sm_count() * RF_WARPS * (t->view.mixed_ok ? GBP_WALK_CTAS : 2);  // one wave of resident warps
-		int64_t per_warp = (n + max_warps - 1) / max_warps;
-		if (per_warp < 64) per_warp = 64;
-		per_warp = (per_warp + RF_CHUNK - 1) / RF_CHUNK * RF_CHUNK;  // chunks of the TMA ring are 32-aligned
-		if ((((uintptr_t) states) | ((uintptr_t) actions) | ((uintptr_t) direction) | ((uintptr_t) s_new)) & 15)
-			return fail(GBP_E_INVALID, "states/actions/direction/s_new must be 16-byte aligned (TMA bulk copies)");
-		int64_t warps = (n + per_warp - 1) / per_warp;
-		unsigned grid = (unsigned) ((warps + warps_per_block - 1) / warps_per_block);
-		cudaLaunchConfig_t cfg = {};
-		cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-		cudaLaunchAttribute attr[1];
-		cfg.attrs = attr; cfg.numAttrs = 0;
-		if (t->l2_hit_ratio > 0.f && !getenv("GBP_NO_L2_WINDOW")) {
-			attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-			attr[0].val.accessPolicyWindow.base_ptr = t->d_z;
-			size_t win = t->z_bytes;
-			int dev = 0, max_window = 0;
-			cudaGetDevice(&dev); cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-			if (win > (size_t) max_window) win = (size_t) max_window;
-			attr[0].val.accessPolicyWindow.num_bytes = win;
-			attr[0].val.accessPolicyWindow.hitRatio = t->l2_hit_ratio;
-			attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-			attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-			cfg.numAttrs = 1;
-		}
-		double2 *recipe = nullptr;
-		if (t->view.mixed_ok) {
-			// mixed-precision walk (k_walk_mixed, gbp_walk.cuh) + fp64 redo pass over the candidates it could not decide
-			if (n > 0x7fffffff) return fail(GBP_E_INVALID, "at most 2^31-1 candidates per call");
-			gbp_terrain *tm = const_cast<gbp_terrain *>(t);  // grow-only scratch owned by the handle (handles are not thread-safe)
-			if (tm->redo_cap < (size_t) n) {
-				CU(cudaStreamSynchronize(st));
-				cudaFree(tm->d_redo);
-				tm->d_redo = nullptr; tm->redo_cap = 0;
-				const size_t cap = ((size_t) n + 1023) / 1024 * 1024;
-				CU(cudaMalloc((void **) &tm->d_redo, cap * sizeof(int) + 16 + cap * sizeof(double2)));  // + the compact recipe array
-				tm->redo_cap = cap;
-			}
-			int *redo = tm->d_redo;
-			unsigned long long *redo_count = (unsigned long long *) (redo + tm->redo_cap);
-			// {tau, kind} per candidate between the walk and k_pair_outputs: compact side array, except when the caller
-			// finishes the outputs itself (variant 5: the recipes stay in s_new[i][0..1])
-			recipe = (s_new && !walk_only) ? (double2 *) ((char *) redo + tm->redo_cap * sizeof(int) + 16) : nullptr;
-			CU(cudaMemsetAsync(redo_count, 0, sizeof(unsigned long long), st));
-#define GBP_WALK_(TEX, AD) CU(cudaLaunchKernelEx(&cfg, k_walk_mixed<TEX, AD>, t->view, (int) n, (int) per_warp, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt, redo, redo_count, recipe))
-			if (t->view.ztex) { if (adaptive) GBP_WALK_(true, true); else GBP_WALK_(true, false); }
-			else { if (adaptive) GBP_WALK_(false, true); else GBP_WALK_(false, false); }
-#undef GBP_WALK_
-			if (t->view.cell_f32)
-				k_validate_redo<MapF32U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
-																	   flags, s_new, t_new, t->d_cnt, recipe);
-			else
-				k_validate_redo<MapF64U><<<sm_count() * 4, 128, 0, st>>>(t->view, redo, redo_count, states, actions, direction, adaptive, verdict,
-																	   flags, s_new, t_new, t->d_cnt, recipe);
-		} else {
-#define GBP_WALK_(M) CU(cudaLaunchKernelEx(&cfg, k_validate_refill<M>, t->view, n, per_warp, states, actions, direction, adaptive, verdict, flags, s_new, t_new, t->d_cnt))
-			if (t->view.cell_f32) { if (t->view.uniform) GBP_WALK_(MapF32U); else GBP_WALK_(MapF32N); }
-			else { if (t->view.uniform) GBP_WALK_(MapF64U); else GBP_WALK_(MapF64N); }
-#undef GBP_WALK_
-		}
-		if (s_new && !walk_only) k_pair_outputs<<<blocks_for(n, 256), 256, 0, st>>>(n, states, actions, s_new, recipe);
-	}
-	CU(cudaGetLastError());
-	return GBP_OK;
-}
-
-int gbp_pair_outputs_dev(int64_t n, const double *states, const double *actions, double *s_new, void *stream) {
-	if (n < 0 || (n && (!states || !actions || !s_new))) return fail(GBP_E_INVALID, "bad arguments");
-	if (n == 0) return GBP_OK;
-	if ((((uintptr_t) states) | ((uintptr_t) actions) | ((uintptr_t) s_new)) & 15)
-		return fail(GBP_E_INVALID, "states/actions/s_new must be 16-byte aligned (TMA bulk copies)");
-	k_pair_outputs<<<blocks_for(n, 256), 256, 0, (cudaStream_t) stream>>>(n, states, actions, s_new, (const double2 *) nullptr);
-	CU(cudaGetLastError());
-	return GBP_OK;
-}
-int gbp_validate_counters(const gbp_terrain *t, int64_t counters6[6]) {
-	if (!t || !counters6) return fail(GBP_E_INVALID, "bad arguments");
-	CU(cudaDeviceSynchronize());
-	unsigned long long h[6];
-	CU(cudaMemcpy(h, t->d_cnt, sizeof h, cudaMemcpyDeviceToHost));
-	for (int i = 0; i < 6; ++i) counters6[i] = (int64_t) h[i];
-	return GBP_OK;
-}
-
-// HOST buffers: chunks of candidates flow through the handle's ring of device buffer sets, each on its own
-// stream, so the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap (PCIe is
-// full duplex).  Nothing in the loop blocks the host; work counters accumulate on the device.
-int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
-					   int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new) {
-	if (!t || n < 0 || (n && (!states || !actions || !direction || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
-	if (n == 0) return GBP_OK;
-	constexpr int NBUF = HostPipe::NBUF;
-	HostPipe &P = const_cast<gbp_terrain *>(t)->pipe;  // scratch owned by the handle (handles are not thread-safe)
-	const int64_t want = n < (1 << 19) ? (n + 1023) / 1024 * 1024 : (1 << 19);
-	if (P.chunk < want) {
-		for (int k = 0; k < NBUF; ++k) {
-			if (P.st[k]) CU(cudaStreamSynchronize(P.st[k]));
-			cudaFree(P.in[k]); cudaFree(P.out[k]); cudaFree(P.redo[k]);
-			P.in[k] = P.out[k] = nullptr; P.redo[k] = nullptr;
-		}
-		P.chunk = 0;
-		for (int k = 0; k < NBUF; ++k) {
-			if (!P.st[k]) CU(cudaStreamCreateWithFlags(&P.st[k], cudaStreamNonBlocking));
-			CU(cudaMalloc(&P.in[k], (size_t) want * (64 + 80 + 1)));
-			CU(cudaMalloc(&P.out[k], (size_t) want * (64 + 8 + 1 + 1)));
-			CU(cudaMalloc((void **) &P.redo[k], (size_t) want * sizeof(int) + 16 + (size_t) want * sizeof(double2)));
-		}
-		P.chunk = want;
-	}
-	const int64_t chunk = P.chunk;
-	CU(cudaMemset(t->d_cnt, 0, 6 * sizeof(unsigned long long)));
-	gbp_terrain shadow = *t;  // same view and counters, per-set redo scratch
-	int64_t ci = 0;
-	int rc = GBP_OK;
-	for (int64_t off = 0; off < n && rc == GBP_OK; off += chunk, ++ci) {
-		const int k = (int) (ci % NBUF);
-		cudaStream_t st = P.st[k];
-		const int64_t m = n - off < chunk ? n - off : chunk;
-		double *d_s = (double *) P.in[k], *d_a = (double *) (P.in[k] + (size_t) chunk * 64);
-		uint8_t *d_d = (uint8_t *) (P.in[k] + (size_t) chunk * 144);
-		double *d_sn = (double *) P.out[k], *d_tn = (double *) (P.out[k] + (size_t) chunk * 64);
-		uint8_t *d_v = (uint8_t *) (P.out[k] + (size_t) chunk * 72), *d_f = d_v + chunk;
-		CU(cudaMemcpyAsync(d_s, states + 8 * off, (size_t) m * 64, cudaMemcpyHostToDevice, st));
-		CU(cudaMemcpyAsync(d_a, actions + 10 * off, (size_t) m * 80, cudaMemcpyHostToDevice, st));
-		CU(cudaMemcpyAsync(d_d, direction + off, (size_t) m, cudaMemcpyHostToDevice, st));
-		shadow.d_redo = P.redo[k];
-		shadow.redo_cap = (size_t) chunk;
-		rc = validate_dev_impl(&shadow, m, d_s, d_a, d_d, adaptive, variant, d_v, flags ? d_f : nullptr, s_new ? d_sn : nullptr,
-							   t_new ? d_tn : nullptr, st, false);
-		if (rc) break;
-		CU(cudaMemcpyAsync(verdict + off, d_v, (size_t) m, cudaMemcpyDeviceToHost, st));
-		if (flags) CU(cudaMemcpyAsync(flags + off, d_f, (size_t) m, cudaMemcpyDeviceToHost, st));
-		if (s_new) CU(cudaMemcpyAsync(s_new + 8 * off, d_sn, (size_t) m * 64, cudaMemcpyDeviceToHost, st));
-		if (t_new) CU(cudaMemcpyAsync(t_new + off, d_tn, (size_t) m * 8, cudaMemcpyDeviceToHost, st));
-	}
-	for (int k = 0; k < NBUF; ++k) {
-		cudaError_t e = cudaStreamSynchronize(P.st[k]);
-		if (e != cudaSuccess && rc == GBP_OK) rc = fail(GBP_E_CUDA, std::string("validate pipeline: ") + cudaGetErrorString(e));
-	}
-	return rc;
-}
-
 // ------------------------------------------------------------------------------------ samplers
 int gbp_sample_actions_dev(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, const double *normal3_host, double *actions,
 						   void *cuda_stream) {
@@ -1011,142 +724,6 @@ int gbp_near(const gbp_tree *T, const double *query, double radius, int *ids, in
 	CU(cudaStreamSynchronize(st));
 	int m = *count < cap ? *count : cap;
 	if (m > 0) CU(cudaMemcpy(ids, di.p, sizeof(int) * m, cudaMemcpyDeviceToHost));
-	return GBP_OK;
-}
-
-// -------------------------------------------------------------------------- extend / connect
-static int ensure_k(gbp_tree *T, int K) {
-	if (K <= T->k_cap) return GBP_OK;
-	cudaFree(T->S.valid); cudaFree(T->S.dist); cudaFree(T->S.s_test);
-	T->S.valid = nullptr; T->S.dist = nullptr; T->S.s_test = nullptr; T->k_cap = 0;
-	CU(cudaMalloc(&T->S.valid, K));
-	CU(cudaMalloc(&T->S.dist, sizeof(double) * K));
-	CU(cudaMalloc(&T->S.s_test, sizeof(double) * 8 * K));
-	T->k_cap = K;
-	return GBP_OK;
-}
-int gbp_extend(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int K, int best_of_k, int adaptive,
-			   uint64_t seed, uint64_t stream, uint64_t idx0, int *status, int *new_id, int64_t *pair_checks) {
-	if (!T || !t || !target || K < 1 || (direction != GBP_FORWARD && direction != GBP_REVERSE)) return fail(GBP_E_INVALID, "bad arguments");
-	int rc;
-	if ((rc = ensure_k(T, K))) return rc;
-	cudaStream_t st = lib_stream();
-	Target8 tg;
-	memcpy(tg.v, target, sizeof tg.v);
-	int *dres = nullptr;
-	CU(cudaHostGetDevicePointer((void **) &dres, T->h_result, 0));
-	if (adaptive) {
-		GBP_DISPATCH(t->view, k_extend_fused_adaptive, (blocks_for(K, 128), 128), st, t->view, T->view, tg, direction, K, best_of_k, 1, seed, stream, idx0,
-					 T->S, T->d_done, dres);
-	} else {
-		// lanes per candidate: as many as keep the launch inside one wave of resident CTAs (2 x 128 threads per SM at ~250 registers)
-		int S = 32;
-		while (S > 1 && (int64_t) K * S > (int64_t) sm_count() * 2 * 128) S >>= 1;
-		const int per_block = 4 * (32 / S);
-		GBP_DISPATCH(t->view, k_extend_fused, (blocks_for(K, per_block), 128), st, t->view, T->view, tg, direction, K, best_of_k, S, seed, stream, idx0,
-					 T->S, T->d_done, dres);
-	}
-	CU(cudaGetLastError());
-	CU(cudaStreamSynchronize(st));
-	const int res[3] = {T->h_result[0], T->h_result[1], T->h_result[2]};
-	if (status) *status = res[0];
-	if (new_id) *new_id = res[1];
-	if (pair_checks) *pair_checks = res[2];
-	return GBP_OK;
-}
-int gbp_attempt_connect_ts(const gbp_terrain *t, int64_t n, const double *s_existing, const double *s, const double *t_s,
-						   const uint8_t *direction, int adaptive, int *status, double *s_new, double *a_new, uint8_t *flags) {
-	if (!t || n < 0 || (n && (!s_existing || !s || !direction || !status || !s_new || !a_new))) return fail(GBP_E_INVALID, "bad arguments");
-	if (n == 0) return GBP_OK;
-	cudaStream_t st = lib_stream();
-	Dev de(st), ds(st), dts(st), dd(st), dst(st), dsn(st), dan(st), dfl(st);
-	int rc;
-	if ((rc = upload(de, s_existing, (size_t) 8 * n, st)) || (rc = upload(ds, s, (size_t) 8 * n, st)) || (rc = upload(dd, direction, (size_t) n, st))) return rc;
-	if (t_s && (rc = upload(dts, t_s, (size_t) n, st))) return rc;
-	CU(dst.alloc(sizeof(int) * n));
-	CU(dsn.alloc(sizeof(double) * 8 * n));
-	CU(dan.alloc(sizeof(double) * 10 * n));
-	if (flags) CU(dfl.alloc(n));
-	GBP_DISPATCH(t->view, k_attempt_connect, (blocks_for(n, 128), 128), st, t->view, n, de.as<double>(), ds.as<double>(),
-				 t_s ? dts.as<double>() : nullptr, dd.as<uint8_t>(), adaptive, dst.as<int>(), dsn.as<double>(), dan.as<double>(), dfl.as<uint8_t>());
-	CU(cudaGetLastError());
-	CU(cudaMemcpyAsync(status, dst.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-	CU(cudaMemcpyAsync(s_new, dsn.p, sizeof(double) * 8 * n, cudaMemcpyDeviceToHost, st));
-	CU(cudaMemcpyAsync(a_new, dan.p, sizeof(double) * 10 * n, cudaMemcpyDeviceToHost, st));
-	if (flags) CU(cudaMemcpyAsync(flags, dfl.p, n, cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
-	return GBP_OK;
-}
-int gbp_attempt_connect(const gbp_terrain *t, int64_t n, const double *s_existing, const double *s, const uint8_t *direction,
-						int adaptive, int *status, double *s_new, double *a_new, uint8_t *flags) {
-	return gbp_attempt_connect_ts(t, n, s_existing, s, nullptr, direction, adaptive, status, s_new, a_new, flags);
-}
-int gbp_new_config(const gbp_terrain *t, const double *target, const double *s_near, int direction, int K, int best_of_k, int adaptive,
-				   uint64_t seed, uint64_t stream, uint64_t idx0, int *found, double *s_new, double *a_new, int64_t *pair_checks) {
-	if (!t || !target || !s_near || !found || !s_new || !a_new) return fail(GBP_E_INVALID, "bad arguments");
-	static thread_local gbp_tree *scratch = nullptr;  // a one-vertex tree whose nearest neighbour is s_near
-	int rc;
-	if (!scratch && (rc = gbp_tree_create(2, &scratch))) return rc;
-	if ((rc = gbp_tree_init(scratch, s_near))) return rc;
-	int status = GBP_TRAPPED, id = -1;
-	if ((rc = gbp_extend(scratch, t, target, direction, K, best_of_k, adaptive, seed, stream, idx0, &status, &id, pair_checks))) return rc;
-	*found = status != GBP_TRAPPED;
-	if (*found) return gbp_tree_read(scratch, id, 1, s_new, a_new, nullptr, nullptr, nullptr);
-	return GBP_OK;
-}
-int gbp_connect(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int adaptive, int *status, int *new_id) {
-	if (!T || !t || !target || (direction != GBP_FORWARD && direction != GBP_REVERSE)) return fail(GBP_E_INVALID, "bad arguments");
-	cudaStream_t st = lib_stream();
-	Target8 tg;
-	memcpy(tg.v, target, sizeof tg.v);
-	int *dres = nullptr;
-	CU(cudaHostGetDevicePointer((void **) &dres, T->h_result, 0));
-	GBP_DISPATCH(t->view, k_connect, (1, 32), st, t->view, T->view, tg, direction, adaptive, T->S, dres);
-	CU(cudaGetLastError());
-	CU(cudaStreamSynchronize(st));
-	const int res[3] = {T->h_result[0], T->h_result[1], T->h_result[2]};
-	if (status) *status = res[0];
-	if (new_id) *new_id = res[1];
-	return GBP_OK;
-}
-
-// ------------------------------------------------------------------------------ batch planner
-int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
-					   const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap,
-					   void *stream) {
-	if (!t || nq < 0 || !p || (nq && (!starts || !goals || !stats))) return fail(GBP_E_INVALID, "bad arguments");
-	if (p->k_candidates < 1 || p->max_iters < 0 || p->max_vertices < 2) return fail(GBP_E_INVALID, "bad plan parameters");
-	if (nq == 0) return GBP_OK;
-	std::string err;
-	gbp_terrain *tm = const_cast<gbp_terrain *>(t);  // scratch owned by the handle (handles are not thread-safe)
-	int rc = plan_batch_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, (cudaStream_t) stream,
-							   &tm->d_plan_arena, &tm->plan_arena_bytes, err);
-	if (rc) return fail(rc, err);
-	return GBP_OK;
-}
-int gbp_plan_batch(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
-				   const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap) {
-	if (!t || nq < 0 || !p || (nq && (!starts || !goals || !stats))) return fail(GBP_E_INVALID, "bad arguments");
-	if (nq == 0) return GBP_OK;
-	cudaStream_t st = lib_stream();
-	Dev ds(st), dg(st), dst(st), dps(st), dpa(st);
-	int rc;
-	if ((rc = upload(ds, starts, (size_t) 8 * nq, st)) || (rc = upload(dg, goals, (size_t) 8 * nq, st))) return rc;
-	CU(dst.alloc(sizeof(gbp_plan_stats) * nq));
-	const bool want_paths = path_states && path_actions && path_cap > 0;
-	if (want_paths) {
-		CU(dps.alloc(sizeof(double) * 8 * (size_t) path_cap * nq));
-		CU(dpa.alloc(sizeof(double) * 10 * (size_t) path_cap * nq));
-	}
-	if ((rc = gbp_plan_batch_dev(t, nq, ds.as<double>(), dg.as<double>(), seed, query0, p, dst.as<gbp_plan_stats>(),
-								 want_paths ? dps.as<double>() : nullptr, want_paths ? dpa.as<double>() : nullptr, path_cap, st)))
-		return rc;
-	CU(cudaMemcpyAsync(stats, dst.p, sizeof(gbp_plan_stats) * nq, cudaMemcpyDeviceToHost, st));
-	if (want_paths) {
-		CU(cudaMemcpyAsync(path_states, dps.p, sizeof(double) * 8 * (size_t) path_cap * nq, cudaMemcpyDeviceToHost, st));
-		CU(cudaMemcpyAsync(path_actions, dpa.p, sizeof(double) * 10 * (size_t) path_cap * nq, cudaMemcpyDeviceToHost, st));
-	}
-	CU(cudaStreamSynchronize(st));
 	return GBP_OK;
 }
 

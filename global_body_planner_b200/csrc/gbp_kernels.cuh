@@ -55,7 +55,7 @@ __global__ void k_terrain_query(TerrainView T, int64_t n, const double *__restri
 	}
 }
 
-__global__ void k_propagate(int kind, int64_t n, const double *__restrict__ s, const double *__restrict__ a,
+static __global__ void k_propagate(int kind, int64_t n, const double *__restrict__ s, const double *__restrict__ a,
 							const double *__restrict__ t, double *__restrict__ out) {
 	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -73,7 +73,7 @@ __global__ void k_propagate(int kind, int64_t n, const double *__restrict__ s, c
 	for (int d = 0; d < 8; ++d) out[8 * i + d] = o[d];
 }
 
-__global__ void k_valid_actions(int64_t n, const double *__restrict__ a, uint8_t *__restrict__ out) {
+static __global__ void k_valid_actions(int64_t n, const double *__restrict__ a, uint8_t *__restrict__ out) {
 	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	double aa[10];
@@ -96,7 +96,7 @@ __global__ void k_valid_states(TerrainView T, int64_t n, const double *__restric
 	if (flags) flags[i] = (uint8_t) (c.flags | (ok ? GBP_FLAG_VALID : 0));
 }
 
-__global__ void k_distance(int kind, int64_t n, const double *__restrict__ q1, const double *__restrict__ q2,
+static __global__ void k_distance(int kind, int64_t n, const double *__restrict__ q1, const double *__restrict__ q2,
 						   double *__restrict__ out) {
 	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(128) k_validate_redo(TerrainView T, const int 
 // streams + 1.06 GB written): the pass sits at what the memory system delivers for this mix, not at a kernel-side limit;
 // and an in-kernel shared-memory output queue inside the walk
 // (12.5-22.6 ms against 10.7 ms at the time: it shrinks the L1 the terrain gathers live on).
-__global__ void __launch_bounds__(256) k_pair_outputs(int64_t n, const double *__restrict__ states, const double *__restrict__ actions,
+static __global__ void __launch_bounds__(256) k_pair_outputs(int64_t n, const double *__restrict__ states, const double *__restrict__ actions,
 													   double *__restrict__ s_new, const double2 *__restrict__ recipe) {
 	const int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(256) k_pair_outputs(int64_t n, const double *_
 // local time: the reference's fp64-accumulated t += dt loops) is laid out by the host; one thread per sample evaluates
 // the state with the exact primitives.  kind 0: applyStance(s, a, t); 1: applyFlight(applyStance(s, a), t) (the
 // landing sample is kind 1 at t = t_f); 2: the state itself (the closing sample of the path).
-__global__ void k_interp_samples(int64_t m, const int *__restrict__ prim, const uint8_t *__restrict__ kind, const double *__restrict__ tloc,
+static __global__ void k_interp_samples(int64_t m, const int *__restrict__ prim, const uint8_t *__restrict__ kind, const double *__restrict__ tloc,
 								 const double *__restrict__ states, const double *__restrict__ actions, double *__restrict__ out) {
 	const int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
 	if (i >= m) return;
@@ -704,7 +704,7 @@ __global__ void k_interp_samples(int64_t m, const int *__restrict__ prim, const 
 }
 // calculateMaxCurvature (planning_utils.cpp:884-909): three-point curvature of consecutive plan states, maximum over the
 // plan.  std::max(max, c) never takes a NaN c, curvatures are >= 0: the maximum is an atomicMax on the fp64 bit pattern.
-__global__ void k_max_curvature(int64_t n, const double *__restrict__ states, unsigned long long *__restrict__ max_bits) {
+static __global__ void k_max_curvature(int64_t n, const double *__restrict__ states, unsigned long long *__restrict__ max_bits) {
 	const int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
 	if (i + 2 >= n) return;
 	const double x1 = states[8 * i], y1 = states[8 * i + 1], x2 = states[8 * (i + 1)], y2 = states[8 * (i + 1) + 1],
@@ -730,7 +730,7 @@ __global__ void k_max_curvature(int64_t n, const double *__restrict__ states, un
 // stream (purpose 3, idx = iy * x_size + ix, stream = rectangle number), so a cell only evaluates the LAST rectangle that
 // covers it.  One thread per cell; the float layer is written in grid_map index order (:88-93).
 struct OwnMapRect { int x1, y1, x2, y2; double mu, delta; };
-__global__ void k_own_map(uint64_t seed, int x_size, int y_size, int n_rect, const OwnMapRect *__restrict__ rects,
+static __global__ void k_own_map(uint64_t seed, int x_size, int y_size, int n_rect, const OwnMapRect *__restrict__ rects,
 						  float *__restrict__ elevation) {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= x_size * y_size) return;
@@ -758,7 +758,7 @@ __global__ void k_own_map(uint64_t seed, int x_size, int y_size, int n_rect, con
 }
 
 // ------------------------------------------------------------------ samplers
-__global__ void k_sample_actions(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, double n0, double n1, double n2,
+static __global__ void k_sample_actions(uint64_t seed, uint64_t stream, uint64_t idx0, int64_t n, double n0, double n1, double n2,
 								 int dir_flag, double dir_thresh, const double *__restrict__ s_from, const double *__restrict__ s_to,
 								 double *__restrict__ out) {
 	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
@@ -812,7 +812,7 @@ __device__ __forceinline__ void warp_argmin(double &d, int &i) {
 		argmin_combine(d, i, od, oi);
 	}
 }
-__global__ void __launch_bounds__(256) k_nearest(TreeView T, int64_t m, const double *__restrict__ queries, int *__restrict__ idx,
+static __global__ void __launch_bounds__(256) k_nearest(TreeView T, int64_t m, const double *__restrict__ queries, int *__restrict__ idx,
 												  double *__restrict__ dist) {
 	__shared__ double sd[8];
 	__shared__ int si[8];
@@ -893,7 +893,7 @@ __global__ void __launch_bounds__(256) k_nearest_tiled(TreeView T, int64_t m, co
 	}
 }
 // neighborhoodDist (planner_class.cpp:173-182): one warp, ballot/popc compaction keeps ascending ids
-__global__ void k_near(TreeView T, const double *__restrict__ query, double radius, int *__restrict__ ids, int cap,
+static __global__ void k_near(TreeView T, const double *__restrict__ query, double radius, int *__restrict__ ids, int cap,
 					   int *__restrict__ count) {
 	const int nv = *T.n, lane = threadIdx.x;
 	double q[8];
@@ -915,7 +915,7 @@ __global__ void k_near(TreeView T, const double *__restrict__ query, double radi
 	if (lane == 0) *count = base;
 }
 
-__global__ void k_tree_init(TreeView T, const double *__restrict__ root) {
+static __global__ void k_tree_init(TreeView T, const double *__restrict__ root) {
 	if (threadIdx.x == 0) {
 		*T.n = 1;
 		for (int d = 0; d < 8; ++d) T.v[(size_t) d * T.cap] = root[d];
@@ -925,7 +925,7 @@ __global__ void k_tree_init(TreeView T, const double *__restrict__ root) {
 		T.y[0] = 0;
 	}
 }
-__global__ void k_tree_append(TreeView T, int parent, const double *__restrict__ s, const double *__restrict__ a, int *__restrict__ out) {
+static __global__ void k_tree_append(TreeView T, int parent, const double *__restrict__ s, const double *__restrict__ a, int *__restrict__ out) {
 	if (threadIdx.x == 0) {
 		double ss[8], aa[10];
 		for (int d = 0; d < 8; ++d) ss[d] = s[d];
@@ -936,14 +936,14 @@ __global__ void k_tree_append(TreeView T, int parent, const double *__restrict__
 	}
 }
 // bulk load: AoS host layout -> SoA, g / yaw rebuilt in id order (parents precede children)
-__global__ void k_tree_load(TreeView T, int n, const double *__restrict__ s, const double *__restrict__ a, const int *__restrict__ parent) {
+static __global__ void k_tree_load(TreeView T, int n, const double *__restrict__ s, const double *__restrict__ a, const int *__restrict__ parent) {
 	for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < n; i += blockDim.x * gridDim.x) {
 		for (int d = 0; d < 8; ++d) T.v[(size_t) d * T.cap + i] = s[8 * (size_t) i + d];
 		for (int d = 0; d < 10; ++d) T.act[(size_t) d * T.cap + i] = a ? a[10 * (size_t) i + d] : 0.0;
 		T.parent[i] = i == 0 ? -1 : parent[i];
 	}
 }
-__global__ void k_tree_gy(TreeView T, int n) {
+static __global__ void k_tree_gy(TreeView T, int n) {
 	if (threadIdx.x == 0 && blockIdx.x == 0) {
 		*T.n = n;
 		T.g[0] = 0;
@@ -958,7 +958,7 @@ __global__ void k_tree_gy(TreeView T, int n) {
 		}
 	}
 }
-__global__ void k_tree_read(TreeView T, int first, int n, double *__restrict__ s, double *__restrict__ a, int *__restrict__ parent,
+static __global__ void k_tree_read(TreeView T, int first, int n, double *__restrict__ s, double *__restrict__ a, int *__restrict__ parent,
 							double *__restrict__ g, double *__restrict__ y) {
 	for (int k = threadIdx.x + blockIdx.x * blockDim.x; k < n; k += blockDim.x * gridDim.x) {
 		int i = first + k;

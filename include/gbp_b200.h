@@ -155,6 +155,58 @@ int gbp_pair_outputs_dev(int64_t n, const double *states, const double *actions,
  * heightIsNan calls, candidates flagged OOG, candidates flagged NEAR, valid}.  Synchronises. */
 int gbp_validate_counters(const gbp_terrain *t, int64_t counters6[6]);
 
+/* ------------------------------------------------------------------- sample + validate (narrow wire) */
+/* The unit of work of RRTClass::newConfig (rrt.cpp:34-50): getRandomAction(surf_norm, ...) followed by
+ * isValidStateActionPair[Reverse](s_near, a_test, ...), for n candidates per call, with a wire format that carries
+ * only what newConfig exchanges with its caller:
+ *   in   the start state of candidate i is a ROW of a device-resident state table (the tree vertices candidates start
+ *        from, uploaded once with gbp_states_create): state_idx[i] (4 bytes; NULL = row row0 + i), and direction[i]
+ *        (1 byte; NULL = direction0 for all).  Its action is ACTION cell idx0 + i of the Philox stream (seed, stream)
+ *        — the same cells gbp_sample_actions(seed, stream, idx0, n, normal, ...) returns — sampled inside the kernel.
+ *   out  verdict_bits: bit (i & 31) of word i >> 5 (ceil(n / 32) words; every bit is written) and, for the VALID
+ *        candidates only, in ascending candidate order, row j of valid_index / valid_s_new / valid_t_new /
+ *        valid_action: the candidate number, the s_new and t_new the pair check returns for it (the landing state and
+ *        t_s + t_f, or in REVERSE the exact start state and t_s) and its sampled action — everything rrt.cpp:44-62
+ *        reads (s_test of an invalid pair check is never used there).  At most valid_cap rows are written;
+ *        result->n_valid is the total.  Any of the valid_* arrays and flags (n bytes, GBP_FLAG_* per candidate) may
+ *        be NULL.
+ * Verdicts, rows and work counters equal those of gbp_validate_pairs on the same (state, action, direction) triples.
+ * Against its 145 B in + 74 B out per candidate this call moves 5 B in + 1 bit out (+ 156 B per valid candidate).
+ * All scratch is allocated per call on the call's stream: concurrent calls on one terrain handle are safe. */
+typedef struct gbp_states gbp_states; /* device-resident table of start states, rows of 8 doubles */
+int gbp_states_create(int64_t rows, const double *states, gbp_states **out);
+void gbp_states_destroy(gbp_states *s);
+int gbp_states_rows(const gbp_states *s, int64_t *rows);
+
+typedef struct {
+	uint64_t seed, stream, idx0;       /* candidate i samples ACTION cell idx0 + i of (seed, stream) */
+	double normal[3];                  /* terrain.getSurfaceNormal at the target sample (rrt.cpp:25) */
+	int adaptive;                      /* state_action_pair_check_adaptive_step_size_flag_ (rrt.h:186-188) */
+	int direction0;                    /* direction of every candidate when `direction` is NULL */
+	int action_direction_sampling;     /* getRandomAction(surf_norm, direction, flag, threshold, s, s_near) */
+	double action_direction_threshold; /*   (planning_utils.cpp:379-391): s_near = the candidate's start state, */
+	double target[8];                  /*   s = target (read only when the flag is set) */
+	int64_t row0;                      /* state_idx == NULL: candidate i starts from table row row0 + i */
+} gbp_sv_params;
+
+typedef struct {
+	int64_t n_valid;                             /* valid candidates of the call (may exceed valid_cap) */
+	int64_t substates, lookups, nanprobes;       /* work under the reference's early-exit semantics (k, L, heightIsNan calls) */
+	int64_t oog, near;                           /* candidates flagged GBP_FLAG_OOG / GBP_FLAG_NEAR */
+	int64_t reserved[2];
+} gbp_sv_result; /* 64 bytes */
+
+int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n, const int32_t *state_idx,
+                        const uint8_t *direction, const gbp_sv_params *params, uint32_t *verdict_bits, uint8_t *flags,
+                        int64_t valid_cap, int32_t *valid_index, double *valid_s_new, double *valid_t_new,
+                        double *valid_action, gbp_sv_result *result);
+/* device pointers throughout (states_dev = the table rows, [rows][8], 16-byte aligned; result_dev = 8 int64 words laid
+ * out as gbp_sv_result); enqueues on `stream` and returns */
+int gbp_sample_validate_dev(const gbp_terrain *t, const double *states_dev, int64_t n, const int32_t *state_idx_dev,
+                            const uint8_t *direction_dev, const gbp_sv_params *params, uint32_t *verdict_bits_dev,
+                            uint8_t *flags_dev, int64_t valid_cap, int32_t *valid_index_dev, double *valid_s_new_dev,
+                            double *valid_t_new_dev, double *valid_action_dev, int64_t *result_dev, void *stream);
+
 /* ---------------------------------------------------------------------------------- plan output */
 /* getInterpPath / interpStateActionPair (planning_utils.cpp:142-193): n_actions primitives, n_actions + 1 states.
  * Per primitive: stance samples for (t = 0; t < t_s; t += dt) (phase 1 STANCE, or 2 CONNECT_STANCE when t_f == 0),
