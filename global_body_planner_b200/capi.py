@@ -328,13 +328,18 @@ class Terrain:
             out.update(s_new=sn[:m], t_new=tn[:m], action=ac[:m])
         return out
 
-    def sample_validate_dev(self, states_ptr, n, params, idx_ptr, dir_ptr, bits_ptr, flags_ptr, valid_cap, index_ptr, snew_ptr, tnew_ptr,
+    def sample_validate_dev(self, states_ptr, table_rows, n, params, idx_ptr, dir_ptr, bits_ptr, flags_ptr, valid_cap, index_ptr, snew_ptr, tnew_ptr,
                             action_ptr, result_ptr, stream=0):
         """Device pointers (ints) in, enqueue only."""
         vp = lambda q: C.c_void_p(q) if q else None
-        _check(lib().gbp_sample_validate_dev(self.h, vp(states_ptr), C.c_int64(n), vp(idx_ptr), vp(dir_ptr), C.byref(params), vp(bits_ptr),
+        _check(lib().gbp_sample_validate_dev(self.h, vp(states_ptr), C.c_int64(table_rows), C.c_int64(n), vp(idx_ptr), vp(dir_ptr), C.byref(params), vp(bits_ptr),
                                              vp(flags_ptr), C.c_int64(valid_cap), vp(index_ptr), vp(snew_ptr), vp(tnew_ptr), vp(action_ptr),
                                              vp(result_ptr), vp(stream)))
+
+    def sample_validate_walk_dev(self, states_ptr, table_rows, n, params, idx_ptr, dir_ptr, bits_ptr, counters_ptr, stream=0):
+        vp = lambda q: C.c_void_p(q) if q else None
+        _check(lib().gbp_sample_validate_walk_dev(self.h, vp(states_ptr), C.c_int64(table_rows), C.c_int64(n), vp(idx_ptr), vp(dir_ptr),
+                                                  C.byref(params), vp(bits_ptr), vp(counters_ptr), vp(stream)))
 
     def validate_counters(self):
         c = np.zeros(6, np.int64)

@@ -207,9 +207,10 @@ int gbp_states_rows(const gbp_states *s, int64_t *rows) {
 	return GBP_OK;
 }
 
-static SvParams sv_device_params(const gbp_sv_params &p, const double *table, const int *idx, const uint8_t *dir, int64_t off) {
+static SvParams sv_device_params(const gbp_sv_params &p, const double *table, int64_t rows, const int *idx, const uint8_t *dir, int64_t off) {
 	SvParams P;
 	P.table = table;
+	P.rows = (long long) rows;
 	P.state_idx = idx ? idx + off : nullptr;
 	P.dir = dir ? dir + off : nullptr;
 	P.row0 = (long long) (p.row0 + off);
@@ -223,10 +224,10 @@ static SvParams sv_device_params(const gbp_sv_params &p, const double *table, co
 }
 // the walk (+ fp64 redo pass) or, on terrains without the mixed-precision evaluator, the general fp64 kernel, over
 // candidates [off, off + m) of a call; `bits`, `flags` are the call's arrays (off is a multiple of 32), `redo` = m ints
-static int sv_launch_range(const gbp_terrain *t, const gbp_sv_params &p, const double *table, const int *idx, const uint8_t *dir, int64_t off,
+static int sv_launch_range(const gbp_terrain *t, const gbp_sv_params &p, const double *table, int64_t rows, const int *idx, const uint8_t *dir, int64_t off,
 						   int64_t m, unsigned *bits, uint8_t *flags, unsigned long long *cnt, int *redo, unsigned long long *redo_count,
 						   cudaStream_t st) {
-	const SvParams P = sv_device_params(p, table, idx, dir, off);
+	const SvParams P = sv_device_params(p, table, rows, idx, dir, off);
 	unsigned *b = bits + off / 32;
 	uint8_t *f = flags ? flags + off : nullptr;
 	if (t->view.mixed_ok) {
@@ -285,29 +286,50 @@ static int sv_check(const gbp_terrain *t, int64_t n, const gbp_sv_params *p, con
 	return GBP_OK;
 }
 
-int gbp_sample_validate_dev(const gbp_terrain *t, const double *states_dev, int64_t n, const int32_t *state_idx_dev, const uint8_t *direction_dev,
+int gbp_sample_validate_dev(const gbp_terrain *t, const double *states_dev, int64_t table_rows, int64_t n, const int32_t *state_idx_dev, const uint8_t *direction_dev,
 							const gbp_sv_params *p, uint32_t *bits, uint8_t *flags, int64_t valid_cap, int32_t *valid_index, double *valid_s_new,
 							double *valid_t_new, double *valid_action, int64_t *result_dev, void *stream) {
 	int rc;
 	if ((rc = sv_check(t, n, p, bits, valid_cap))) return rc;
-	if (!states_dev || !result_dev) return fail(GBP_E_INVALID, "states_dev and result_dev are required");
+	if (!states_dev || !result_dev || table_rows < 1) return fail(GBP_E_INVALID, "states_dev (table_rows >= 1) and result_dev are required");
 	if (((uintptr_t) states_dev) & 15) return fail(GBP_E_INVALID, "the state table must be 16-byte aligned");
 	if ((valid_s_new || valid_t_new || valid_action) && !valid_index) return fail(GBP_E_INVALID, "valid rows need valid_index");
 	cudaStream_t st = (cudaStream_t) stream;
 	const int64_t nwords = (n + 31) / 32;
-	Dev scratch(st);  // [cnt 6 | redo_count 1 | sums 1024] u64, then the redo list
-	CU(scratch.alloc((6 + 1 + 1024) * sizeof(unsigned long long) + (size_t) (n ? n : 1) * sizeof(int)));
-	unsigned long long *cnt = scratch.as<unsigned long long>(), *redo_count = cnt + 6, *sums = cnt + 7;
+	Dev scratch(st);  // [cnt 7 | redo_count 1 | sums 1024] u64, then the redo list
+	CU(scratch.alloc((8 + 1024) * sizeof(unsigned long long) + (size_t) (n ? n : 1) * sizeof(int)));
+	unsigned long long *cnt = scratch.as<unsigned long long>(), *redo_count = cnt + 7, *sums = cnt + 8;
 	int *redo = (int *) (sums + 1024);
-	CU(cudaMemsetAsync(cnt, 0, 7 * sizeof(unsigned long long), st));
+	CU(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), st));
 	if (nwords) CU(cudaMemsetAsync(bits, 0, (size_t) nwords * 4, st));
-	if (n && (rc = sv_launch_range(t, *p, states_dev, state_idx_dev, direction_dev, 0, n, bits, flags, cnt, redo, redo_count, st))) return rc;
+	if (n && (rc = sv_launch_range(t, *p, states_dev, table_rows, state_idx_dev, direction_dev, 0, n, bits, flags, cnt, redo, redo_count, st))) return rc;
 	if ((rc = sv_compact(n, bits, sums, valid_index ? valid_cap : 0, valid_index, cnt, (long long *) result_dev, st))) return rc;
 	if (valid_index && valid_cap > 0 && (valid_s_new || valid_t_new || valid_action)) {
-		const SvParams P = sv_device_params(*p, states_dev, state_idx_dev, direction_dev, 0);
+		const SvParams P = sv_device_params(*p, states_dev, table_rows, state_idx_dev, direction_dev, 0);
 		k_sv_outputs<<<sm_count() * 2, 128, 0, st>>>(P, (const long long *) result_dev, valid_cap, valid_index, valid_s_new, valid_t_new, valid_action);
 		CU(cudaGetLastError());
 	}
+	return GBP_OK;
+}
+
+// the walk alone (k_walk_sv + the fp64 redo pass, or the general fp64 kernel): verdict bits and the 8 counter words
+// {k, L, NaN probes, OOG, NEAR, valid, rows out of range, 0}.  For measurements: bench.py times the dominant kernel this way.
+int gbp_sample_validate_walk_dev(const gbp_terrain *t, const double *states_dev, int64_t table_rows, int64_t n, const int32_t *state_idx_dev,
+								 const uint8_t *direction_dev, const gbp_sv_params *p, uint32_t *bits, int64_t *counters8_dev, void *stream) {
+	int rc;
+	if ((rc = sv_check(t, n, p, bits, 0))) return rc;
+	if (!states_dev || !counters8_dev || table_rows < 1) return fail(GBP_E_INVALID, "states_dev (table_rows >= 1) and counters8_dev are required");
+	if (((uintptr_t) states_dev) & 15) return fail(GBP_E_INVALID, "the state table must be 16-byte aligned");
+	cudaStream_t st = (cudaStream_t) stream;
+	Dev scratch(st);
+	CU(scratch.alloc(sizeof(unsigned long long) + (size_t) (n ? n : 1) * sizeof(int)));
+	unsigned long long *redo_count = scratch.as<unsigned long long>();
+	CU(cudaMemsetAsync(redo_count, 0, sizeof(unsigned long long), st));
+	CU(cudaMemsetAsync(counters8_dev, 0, 8 * sizeof(long long), st));
+	if (n) CU(cudaMemsetAsync(bits, 0, (size_t) ((n + 31) / 32) * 4, st));
+	if (n && (rc = sv_launch_range(t, *p, states_dev, table_rows, state_idx_dev, direction_dev, 0, n, bits, nullptr, (unsigned long long *) counters8_dev,
+								   (int *) (redo_count + 1), redo_count, st)))
+		return rc;
 	return GBP_OK;
 }
 
@@ -324,10 +346,6 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 	memset(result, 0, sizeof *result);
 	if (n == 0) return GBP_OK;
 	if (!state_idx && (p->row0 < 0 || p->row0 + n > table->rows)) return fail(GBP_E_INVALID, "row0 + n exceeds the state table");
-	if (state_idx) {  // rows are dereferenced on the device: reject anything outside the table here
-		for (int64_t i = 0; i < n; ++i)
-			if (state_idx[i] < 0 || state_idx[i] >= table->rows) return fail(GBP_E_INVALID, "state_idx entry outside the state table");
-	}
 	cudaStream_t st = lib_stream();
 	static thread_local cudaStream_t cs = nullptr;
 	static thread_local cudaEvent_t ev = nullptr;
@@ -338,8 +356,8 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 	const int64_t nwords = (n + 31) / 32, CH = 1 << 21, nch = (n + CH - 1) / CH;
 	const int64_t cap = !valid_index ? 0 : (valid_cap < n ? valid_cap : n);
 	Dev scratch(st), d_idx(st), d_dir(st), d_bits(st), d_flags(st), d_index(st), d_res(st), d_sn(st), d_tn(st), d_act(st);
-	CU(scratch.alloc((6 + 1024 + (size_t) nch) * sizeof(unsigned long long) + (size_t) n * sizeof(int)));
-	unsigned long long *cnt = scratch.as<unsigned long long>(), *sums = cnt + 6, *redo_counts = sums + 1024;
+	CU(scratch.alloc((8 + 1024 + (size_t) nch) * sizeof(unsigned long long) + (size_t) n * sizeof(int)));
+	unsigned long long *cnt = scratch.as<unsigned long long>(), *sums = cnt + 8, *redo_counts = sums + 1024;
 	int *redo = (int *) (redo_counts + nch);
 	if (state_idx) CU(d_idx.alloc((size_t) n * 4));
 	if (direction) CU(d_dir.alloc((size_t) n));
@@ -347,7 +365,7 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 	if (flags) CU(d_flags.alloc((size_t) n));
 	if (cap) CU(d_index.alloc((size_t) cap * 4));
 	CU(d_res.alloc(8 * sizeof(long long)));
-	CU(cudaMemsetAsync(cnt, 0, (6 + 1024 + (size_t) nch) * sizeof(unsigned long long), st));
+	CU(cudaMemsetAsync(cnt, 0, (8 + 1024 + (size_t) nch) * sizeof(unsigned long long), st));
 	CU(cudaMemsetAsync(d_bits.p, 0, (size_t) nwords * 4, st));
 	CU(cudaEventRecord(ev, st));
 	CU(cudaStreamWaitEvent(cs, ev, 0));  // the copy stream may touch the buffers once they exist in stream order
@@ -360,7 +378,7 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 		if (e == cudaSuccess) e = cudaEventRecord(ev, cs);
 		if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
 		if (e != cudaSuccess) { rc = fail(GBP_E_CUDA, std::string("sample_validate copy: ") + cudaGetErrorString(e)); break; }
-		rc = sv_launch_range(t, *p, table->d, state_idx ? d_idx.as<int>() : nullptr, direction ? d_dir.as<uint8_t>() : nullptr, off, m,
+		rc = sv_launch_range(t, *p, table->d, table->rows, state_idx ? d_idx.as<int>() : nullptr, direction ? d_dir.as<uint8_t>() : nullptr, off, m,
 							 d_bits.as<unsigned>(), flags ? d_flags.as<uint8_t>() : nullptr, cnt, redo + off, redo_counts + c, st);
 	}
 	if (rc == GBP_OK) rc = sv_compact(n, d_bits.as<unsigned>(), sums, cap, cap ? d_index.as<int>() : nullptr, cnt, d_res.as<long long>(), st);
@@ -375,6 +393,9 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 	if (e != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
 		return fail(GBP_E_CUDA, std::string("sample_validate: ") + cudaGetErrorString(e != cudaSuccess ? e : (e2 != cudaSuccess ? e2 : e3)));
 	memcpy(result, h_result, sizeof *result);
+	// row numbers are checked where they are read (a host-side scan of 16 M indices costs more than the whole call): a row
+	// outside the table was read as row 0 and counted; the call's results are void then
+	if (result->reserved[0] > 0) return fail(GBP_E_INVALID, "state_idx entry outside the state table");
 	const int64_t rows = result->n_valid < cap ? result->n_valid : cap;
 	if (rows > 0) {
 		CU(cudaMemcpyAsync(valid_index, d_index.p, (size_t) rows * 4, cudaMemcpyDeviceToHost, st));
@@ -382,7 +403,7 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 			if (valid_s_new) CU(d_sn.alloc((size_t) rows * 64));
 			if (valid_t_new) CU(d_tn.alloc((size_t) rows * 8));
 			if (valid_action) CU(d_act.alloc((size_t) rows * 80));
-			const SvParams P = sv_device_params(*p, table->d, state_idx ? d_idx.as<int>() : nullptr, direction ? d_dir.as<uint8_t>() : nullptr, 0);
+			const SvParams P = sv_device_params(*p, table->d, table->rows, state_idx ? d_idx.as<int>() : nullptr, direction ? d_dir.as<uint8_t>() : nullptr, 0);
 			k_sv_outputs<<<(unsigned) std::min<int64_t>((rows + 127) / 128, (int64_t) sm_count() * 2), 128, 0, st>>>(
 				P, d_res.as<long long>(), rows, d_index.as<int>(), d_sn.as<double>(), d_tn.as<double>(), d_act.as<double>());
 			CU(cudaGetLastError());

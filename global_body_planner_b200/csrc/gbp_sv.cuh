@@ -29,6 +29,7 @@ struct SvParams {
 	const int *state_idx;    // [n] row numbers or null: candidate i starts from row row0 + i
 	const uint8_t *dir;      // [n] directions or null: every candidate uses dir0
 	long long row0;
+	long long rows;          // table size: a row number outside [0, rows) is counted in cnt[6] and read as row 0
 	int dir0;
 	uint64_t seed, stream, idx0;
 	double normal[3];        // rrt.cpp:25: one surface normal per newConfig
@@ -102,7 +103,8 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_sv(Terrai
 				if (r < total) {
 					const int e = r % SV_CAP;
 					const int i = wbase + r;
-					const long long row = P.state_idx ? (long long) __ldcs(P.state_idx + i) : P.row0 + i;
+					long long row = P.state_idx ? (long long) __ldcs(P.state_idx + i) : P.row0 + i;
+					if ((unsigned long long) row >= (unsigned long long) P.rows) { row = 0; atomicAdd(cnt + 6, 1ull); }
 					const double *src = P.table + 8 * row;
 #pragma unroll
 					for (int d = 0; d < 4; ++d) cp_async16_hint(&ringS[wib][e][2 * d], src + 2 * d, pol);
@@ -160,7 +162,8 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_sv(Terrai
 
 // the candidate's inputs, rebuilt from its index (redo pass, general path, output pass)
 __device__ __forceinline__ void sv_candidate(const SvParams &P, const double *R, int64_t i, double s[8], double a[10], int &dir) {
-	const long long row = P.state_idx ? (long long) P.state_idx[i] : P.row0 + i;
+	long long row = P.state_idx ? (long long) P.state_idx[i] : P.row0 + i;
+	if ((unsigned long long) row >= (unsigned long long) P.rows) row = 0;  // counted by the pass that decides the candidate
 	load_state(P.table + 8 * row, s);
 	dir = P.dir ? (int) P.dir[i] : P.dir0;
 	sv_sample(P.seed, P.stream, P.idx0 + (uint64_t) i, R, P.dir_sampling, P.dir_thresh, P.target[3], P.target[4], dir, s[3], s[4], a);
@@ -208,6 +211,10 @@ __global__ void __launch_bounds__(128) k_sv_fp64(TerrainView T, SvParams P, int6
 		const int64_t i = list ? (int64_t) list[j] : (int64_t) j;
 		double s[8], a[10];
 		int dir;
+		if (!list) {  // the walk has counted the listed ones
+			const long long row = P.state_idx ? (long long) P.state_idx[i] : P.row0 + i;
+			if ((unsigned long long) row >= (unsigned long long) P.rows) atomicAdd(cnt + 6, 1ull);
+		}
 		sv_candidate(P, sR, i, s, a, dir);
 		Counters c = {0, 0, 0, 0};
 		const bool ok = sv_walk_fp64<M>(T, s, a, dir, adaptive != 0, c);
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(256) k_sv_count(const unsigned *__restrict__ b
 	}
 }
 // pass 2: block b starts at the sum of the blocks before it and lists its set bits in ascending order; block 0 also
-// publishes the call's result words {n_valid, sub-states k, lookups L, NaN probes, OOG, NEAR, 0, 0}
+// publishes the call's result words {n_valid, sub-states k, lookups L, NaN probes, OOG, NEAR, rows out of range, 0}
 __global__ void __launch_bounds__(256) k_sv_list(const unsigned *__restrict__ bits, int64_t nwords, int64_t span, const unsigned long long *__restrict__ sums,
 												  int64_t cap, int *__restrict__ index, const unsigned long long *__restrict__ cnt, long long *__restrict__ result) {
 	__shared__ unsigned long long part[8];
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(256) k_sv_list(const unsigned *__restrict__ bi
 		if (blockIdx.x == 0) {
 			result[0] = (long long) s;
 			for (int j = 0; j < 5; ++j) result[1 + j] = (long long) cnt[j];
-			result[6] = 0; result[7] = 0;
+			result[6] = (long long) cnt[6]; result[7] = 0;
 			s = 0;
 		}
 		s_base = s;

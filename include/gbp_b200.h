@@ -193,19 +193,26 @@ typedef struct {
 	int64_t n_valid;                             /* valid candidates of the call (may exceed valid_cap) */
 	int64_t substates, lookups, nanprobes;       /* work under the reference's early-exit semantics (k, L, heightIsNan calls) */
 	int64_t oog, near;                           /* candidates flagged GBP_FLAG_OOG / GBP_FLAG_NEAR */
-	int64_t reserved[2];
+	int64_t reserved[2];                         /* [0]: row numbers outside the table (results are void when > 0) */
 } gbp_sv_result; /* 64 bytes */
 
 int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n, const int32_t *state_idx,
                         const uint8_t *direction, const gbp_sv_params *params, uint32_t *verdict_bits, uint8_t *flags,
                         int64_t valid_cap, int32_t *valid_index, double *valid_s_new, double *valid_t_new,
                         double *valid_action, gbp_sv_result *result);
-/* device pointers throughout (states_dev = the table rows, [rows][8], 16-byte aligned; result_dev = 8 int64 words laid
- * out as gbp_sv_result); enqueues on `stream` and returns */
-int gbp_sample_validate_dev(const gbp_terrain *t, const double *states_dev, int64_t n, const int32_t *state_idx_dev,
+/* device pointers throughout (states_dev = the table, [table_rows][8], 16-byte aligned; result_dev = 8 int64 words laid
+ * out as gbp_sv_result); enqueues on `stream` and returns.  Row numbers are checked where they are read: one outside
+ * [0, table_rows) is read as row 0 and counted in reserved[0] (the host-pointer call returns GBP_E_INVALID then). */
+int gbp_sample_validate_dev(const gbp_terrain *t, const double *states_dev, int64_t table_rows, int64_t n, const int32_t *state_idx_dev,
                             const uint8_t *direction_dev, const gbp_sv_params *params, uint32_t *verdict_bits_dev,
                             uint8_t *flags_dev, int64_t valid_cap, int32_t *valid_index_dev, double *valid_s_new_dev,
                             double *valid_t_new_dev, double *valid_action_dev, int64_t *result_dev, void *stream);
+
+/* measurement aid: the walk kernels of the call above alone (no compaction, no rows): verdict bits and 8 counter words
+ * {sub-states k, lookups L, NaN probes, OOG, NEAR, valid, rows out of range, 0} — bench.py times the dominant kernel so */
+int gbp_sample_validate_walk_dev(const gbp_terrain *t, const double *states_dev, int64_t table_rows, int64_t n,
+                                 const int32_t *state_idx_dev, const uint8_t *direction_dev, const gbp_sv_params *params,
+                                 uint32_t *verdict_bits_dev, int64_t *counters8_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------- plan output */
 /* getInterpPath / interpStateActionPair (planning_utils.cpp:142-193): n_actions primitives, n_actions + 1 states.

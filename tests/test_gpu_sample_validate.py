@@ -177,7 +177,7 @@ def test_device_pointer_entry(gbp, env):
         res = torch.zeros(8, dtype=torch.int64, device=dev)
         p = gbp.sv_params(21, 22, 7)
         for _ in range(2):  # twice on the same buffers: no state leaks from one call into the next
-            t.sample_validate_dev(dt.data_ptr(), n, p, di.data_ptr(), dd.data_ptr(), bits.data_ptr(), fl.data_ptr(), cap, vi.data_ptr(),
+            t.sample_validate_dev(dt.data_ptr(), n, n, p, di.data_ptr(), dd.data_ptr(), bits.data_ptr(), fl.data_ptr(), cap, vi.data_ptr(),
                                   sn.data_ptr(), tn.data_ptr(), ac.data_ptr(), res.data_ptr(), st.cuda_stream)
     st.synchronize()
     s = table[idx]
