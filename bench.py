@@ -301,7 +301,11 @@ def main():
         t.sample_validate_dev(states.data_ptr(), n, n, sv, idx.data_ptr(), direction.data_ptr(), bits.data_ptr(), 0, cap, vi.data_ptr(),
                               vsn.data_ptr(), vtn.data_ptr(), vac.data_ptr(), res.data_ptr(), cur)
 
-    sampler = ClockSampler(local_rank).start()
+    sampler = ClockSampler(local_rank)
+    if not os.environ.get("GBP_BENCH_NO_CLOCKS"):  # diagnostic switch: the sampler thread polls NVML every 2 ms
+        sampler.start()
+    else:
+        sampler.th = threading.Thread(target=lambda: None); sampler.th.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -505,7 +509,8 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                 "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                 "bytes_per_candidate": alg_bytes / n, "k_mean": k_tot / n, "L_mean": L_tot / n,
-                "step_ms": float(np.mean(per_step_ms)), "kernels_per_step": kernels_per_step, "ceilings": ceil,
+                "step_ms": float(np.mean(per_step_ms)), "step_ms_min_max": [float(np.min(per_step_ms)), float(np.max(per_step_ms))],
+                "kernels_per_step": kernels_per_step, "ceilings": ceil,
                 "note": "bound 'hbm' is the contract's vocabulary; the kernel is bound by issue slots and the texture-gather pipe (ceilings), "
                         "with terrain probes served from L2; launch_ms = k_walk_sv + fp64 redo (gbp_sample_validate_walk_dev), step_ms adds "
                         "the compaction kernels and the valid-row pass.  north_star's 'tiles staged in shared memory via TMA' is replaced by "

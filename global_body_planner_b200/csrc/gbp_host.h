@@ -35,12 +35,26 @@ inline int sm_count() {
 	return sms;
 }
 
+// The default memory pool of a device gives freed blocks back to the driver at the next synchronisation unless told
+// otherwise; every call would then pay a driver allocation (measured: 5-45 ms spikes on the first call after a sync).
+inline void keep_pool(void) {
+	static thread_local int done_for = -1;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+		unsigned long long keep = ~0ull;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+	}
+	done_for = dev;
+}
+
 // stream-ordered device scratch; the pool keeps freed blocks, so repeated calls do not hit the driver
 struct Dev {
 	void *p = nullptr;
 	cudaStream_t st;
 	explicit Dev(cudaStream_t s) : st(s) {}
-	cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
+	cudaError_t alloc(size_t bytes) { keep_pool(); return cudaMallocAsync(&p, bytes ? bytes : 1, st); }
 	~Dev() { if (p) cudaFreeAsync(p, st); }
 	template <class T> T *as() { return (T *) p; }
 };
@@ -49,12 +63,7 @@ inline cudaStream_t lib_stream() {
 	static thread_local cudaStream_t s = nullptr;
 	if (!s) {
 		if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
-		int dev = 0;
-		cudaMemPool_t pool;
-		if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-			unsigned long long keep = ~0ull;
-			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-		}
+		keep_pool();
 	}
 	return s;
 }

@@ -588,7 +588,10 @@ static int new_config(plan_ctx *C, uint64_t cell, const double s[8], const doubl
 	int K = C->p->k_candidates, found = 0;
 	for (int j = 0; j < K; ++j) {
 		double a[10], st[8], tn;
-		orc_sample_action(C->seed, C->query, cell * (uint64_t) K + (uint64_t) j, normal, 0, 0.0, 0, 0, a);
+		/* getRandomAction(surf_norm, direction, flag, threshold, s, s_near): FORWARD samples from s_near towards s,
+		 * REVERSE from s towards s_near (planning_utils.cpp:385-388) */
+		orc_sample_action(C->seed, C->query, cell * (uint64_t) K + (uint64_t) j, normal, C->p->action_direction_sampling,
+						  C->p->action_direction_threshold, dir == ORC_FORWARD ? s_near : s, dir == ORC_FORWARD ? s : s_near, a);
 		if (!checked_pair(C, s_near, a, dir, st, &tn)) continue;
 		double d = orc_state_distance(st, s);
 		if (d < best) { best = d; memcpy(s_new, st, 64); memcpy(a_new, a, 80); found = 1; }
@@ -656,6 +659,10 @@ static int connect_tree(plan_ctx *C, orc_tree *T, const double s[8], int dir) { 
 /* postProcessPath, rrt_connect.cpp:139-227 (FORWARD shortcutting; quirk kept: the fallback branch
  * adds to path_cost_ only, not to path_length_/path_yaw_). */
 int orc_post_process_path(const orc_terrain *t, int ns, double *states, double *actions, int adaptive, double stats3[3]) {
+	return orc_post_process_path_w(t, ns, states, actions, adaptive, 0, 1.0, 1.0, stats3);
+}
+int orc_post_process_path_w(const orc_terrain *t, int ns, double *states, double *actions, int adaptive, int cost_add_yaw,
+							double w_length, double w_yaw, double stats3[3]) {
 	double *ns_states = (double *) malloc(sizeof(double) * 8 * (size_t) (ns + 1)), *ns_actions = (double *) malloc(sizeof(double) * 10 * (size_t) (ns + 1));
 	int m = 1;
 	double cur[8], goal[8], len = 0, yaw = 0, cost = 0;
@@ -676,12 +683,14 @@ int orc_post_process_path(const orc_terrain *t, int ns, double *states, double *
 			nxt = states + 8 * j;
 			memcpy(ns_actions + 10 * (m - 1), a_new, 80);
 			double dl = orc_pose_distance(cur, nxt), dy = orc_yaw_distance(cur, nxt);
-			len += dl; yaw += dy; cost += dl;
+			len += dl; yaw += dy;
+			if (cost_add_yaw) cost += dl * w_length + dy * w_yaw; else cost += dl;
 		} else {
 			if (!have_old) break; /* cannot happen for a well-formed path */
 			nxt = states + 8 * jold;
 			memcpy(ns_actions + 10 * (m - 1), actions + 10 * (jold - 1), 80);
-			cost += orc_pose_distance(cur, nxt);
+			double dl = orc_pose_distance(cur, nxt), dy = orc_yaw_distance(cur, nxt);
+			if (cost_add_yaw) cost += dl * w_length + dy * w_yaw; else cost += dl;
 		}
 		memcpy(ns_states + 8 * m, nxt, 64);
 		memcpy(cur, nxt, 64);
@@ -698,8 +707,24 @@ int orc_post_process_path(const orc_terrain *t, int ns, double *states, double *
 /* runRRTConnect (rrt_connect.cpp:230-314) with an iteration budget; the RRT* main loop
  * (rrt_star_connect.cpp:130-165) has the same body, so rrt_star only swaps the extend.
  * Philox cells: STATE cell idx = 2*iter + half; ACTION cells idx = (2*iter + half)*K + j; stream = query. */
+static void tree_dump(const orc_tree *T, orc_tree_dump *d) {
+	if (!d) return;
+	d->n = T->n;
+	for (int i = 0; i < T->n && i < d->cap; ++i) {
+		memcpy(d->states + 8 * i, T->v + 8 * i, 64);
+		if (i == 0) memset(d->actions, 0, 80); else memcpy(d->actions + 10 * i, T->act + 10 * i, 80);
+		d->parent[i] = T->parent[i];
+		d->g[i] = T->g[i];
+		d->y[i] = T->y[i];
+	}
+}
 int orc_plan(const orc_terrain *t, const double start[8], const double goal[8], uint64_t seed, uint64_t query,
 			 const orc_plan_params *p, orc_plan_stats *st, double *path_states, double *path_actions, int path_cap) {
+	return orc_plan_ex(t, start, goal, seed, query, p, st, path_states, path_actions, path_cap, 0, 0);
+}
+int orc_plan_ex(const orc_terrain *t, const double start[8], const double goal[8], uint64_t seed, uint64_t query,
+				const orc_plan_params *p, orc_plan_stats *st, double *path_states, double *path_actions, int path_cap,
+				orc_tree_dump *dump_a, orc_tree_dump *dump_b) {
 	memset(st, 0, sizeof *st);
 	plan_ctx C = {t, p, seed, query, st};
 	orc_tree Ta, Tb;
@@ -716,7 +741,11 @@ int orc_plan(const orc_terrain *t, const double start[8], const double goal[8], 
 			if (Tx->n >= Tx->cap || Ty->n >= Ty->cap) { full = 1; break; }
 			uint64_t cell = 2 * (uint64_t) it + (uint64_t) half;
 			double s_rand[8];
-			orc_sample_state(t, seed, query, cell, 0, 0.0, 0, 0, 0, s_rand);
+			/* directional state sampling between the growing tree's newest vertex and the other tree's root
+			 * (rrt_connect.cpp:246-251, :281-286): s_from on the start side, s_to on the goal side */
+			const double *s_from = half == 0 ? Ta.v + 8 * (Ta.n - 1) : Ta.v, *s_to = half == 0 ? Tb.v : Tb.v + 8 * (Tb.n - 1);
+			orc_sample_state(t, seed, query, cell, p->state_direction_sampling, p->state_direction_threshold, p->state_direction_speed,
+							 s_from, s_to, s_rand);
 			if (!orc_is_valid_state(t, s_rand, ORC_STANCE, 0)) continue;
 			int r = p->rrt_star ? extend_star(&C, Tx, cell, s_rand, dir_ext) : extend_plain(&C, Tx, cell, s_rand, dir_ext);
 			if (r == ORC_TRAPPED) continue;
@@ -727,6 +756,7 @@ int orc_plan(const orc_terrain *t, const double start[8], const double goal[8], 
 	if (solved) {
 		st->path_length = Ta.g[Ta.n - 1] + Tb.g[Tb.n - 1]; /* rrt_connect.cpp:269-270 */
 		st->path_yaw = Ta.y[Ta.n - 1] + Tb.y[Tb.n - 1];
+		st->path_cost = p->cost_add_yaw ? st->path_length * p->cost_length_weight + st->path_yaw * p->cost_yaw_weight : st->path_length; /* :270-274 */
 		/* stitch: rrt_connect.cpp:381-401 */
 		int na = 0, nb = 0;
 		for (int i = Ta.n - 1; i != -1; i = Ta.parent[i]) ++na;
@@ -746,8 +776,8 @@ int orc_plan(const orc_terrain *t, const double start[8], const double goal[8], 
 		int nstates = total;
 		if (p->post_process) {
 			double s3[3];
-			nstates = orc_post_process_path(t, total, ps, pa, p->adaptive, s3);
-			st->path_length = s3[0]; st->path_yaw = s3[1];
+			nstates = orc_post_process_path_w(t, total, ps, pa, p->adaptive, p->cost_add_yaw, p->cost_length_weight, p->cost_yaw_weight, s3);
+			st->path_length = s3[0]; st->path_yaw = s3[1]; st->path_cost = s3[2];
 		}
 		st->path_states = nstates;
 		for (int i = 0; i + 1 < nstates; ++i) st->path_duration += pa[10 * i + 6] + pa[10 * i + 7];
@@ -756,6 +786,8 @@ int orc_plan(const orc_terrain *t, const double start[8], const double goal[8], 
 		free(ps);
 		free(pa);
 	}
+	tree_dump(&Ta, dump_a);
+	tree_dump(&Tb, dump_b);
 	tree_free(&Ta);
 	tree_free(&Tb);
 	return solved;

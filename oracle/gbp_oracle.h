@@ -126,6 +126,13 @@ typedef struct {
 	int adaptive;      /* state_action_pair_check_adaptive_step_size_flag */
 	int rrt_star;      /* 1 = RRTStarConnectClass::extend (choose parent + rewire, delta = 3.0) */
 	int post_process;  /* 1 = run postProcessPath on the stitched path (rrt_connect.cpp:139-227) */
+	/* the fork's options (rrt.h:186-199, set by RRTClass::set_*; all off in config/params.yaml:16-27) */
+	int state_direction_sampling;       /* randomState(terrain, flag, threshold, speed flag, s_from, s_to), rrt_connect.cpp:246-251, :281-286 */
+	int state_direction_speed;          /* state_direction_sampling_speed_direction_flag_ */
+	int action_direction_sampling;      /* getRandomAction(surf_norm, direction, flag, threshold, s, s_near), rrt.cpp:34, :49 */
+	int cost_add_yaw;                   /* path_cost_ = length * w_l + yaw * w_y (rrt_connect.cpp:270-274, :196, :212) */
+	double state_direction_threshold, action_direction_threshold;
+	double cost_length_weight, cost_yaw_weight;
 } orc_plan_params;
 
 typedef struct {
@@ -139,16 +146,34 @@ typedef struct {
 	double path_duration; /* sum of t_s+t_f over the path's actions (rrt_connect.cpp:463-466) */
 	long long pair_checks; /* isValidStateActionPair[Reverse] evaluations ("validated actions") */
 	long long nn_queries;
-} orc_plan_stats;
+	double path_cost;   /* path_cost_ as the reference leaves it: rrt_connect.cpp:270-274, or postProcessPath's sum (:196, :212) */
+	long long reserved;
+} orc_plan_stats; /* 80 bytes, same layout as gbp_plan_stats */
+
+/* dump of one tree after a run (AoS, ids in insertion order): what the pin against the reference's own loops compares */
+typedef struct {
+	int cap, n;
+	double *states;   /* [cap][8] */
+	double *actions;  /* [cap][10]: the action stored with vertex i (GraphClass::actions[i]) */
+	int *parent;      /* [cap], -1 for the root */
+	double *g, *y;    /* [cap] */
+} orc_tree_dump;
 
 int orc_plan(const orc_terrain *t, const double start[8], const double goal[8], uint64_t seed, uint64_t query,
 			 const orc_plan_params *p, orc_plan_stats *st, double *path_states, double *path_actions, int path_cap);
+/* orc_plan that also copies the two trees out (ta / tb may be NULL) */
+int orc_plan_ex(const orc_terrain *t, const double start[8], const double goal[8], uint64_t seed, uint64_t query,
+				const orc_plan_params *p, orc_plan_stats *st, double *path_states, double *path_actions, int path_cap,
+				orc_tree_dump *ta, orc_tree_dump *tb);
 void orc_plan_batch(const orc_terrain *t, long long nq, const double *starts, const double *goals, uint64_t seed,
 					uint64_t query0, const orc_plan_params *p, orc_plan_stats *st, int nthreads);
 long long orc_interp_path(int n_actions, const double *states, const double *actions, double dt, long long cap,
 						  double *out_s, double *out_t, int *out_phase);
 double orc_max_curvature(long long n, const double *states);
 int orc_post_process_path(const orc_terrain *t, int ns, double *states, double *actions, int adaptive, double stats3[3]);
+/* with the yaw-aware cost of the fork: stats3[2] = sum of dl * w_l + dyaw * w_y when cost_add_yaw (rrt_connect.cpp:196, :212) */
+int orc_post_process_path_w(const orc_terrain *t, int ns, double *states, double *actions, int adaptive, int cost_add_yaw,
+							double w_length, double w_yaw, double stats3[3]);
 /* terrain generators of the publisher node (terrain_map_publisher.cpp:34-231, :253-286); see gbp_oracle.c */
 extern const double orc_own_map_default_rects[13][6];
 void orc_own_map_axes(int n, double start, double res, double *ax);

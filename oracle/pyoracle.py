@@ -2,6 +2,8 @@
 
 * ``Oracle``  -> oracle/libgbp_oracle.so  (plain-C restatement, oracle/gbp_oracle.c)
 * ``Ref``     -> oracle/_ref/libgbp_ref.so (the UNMODIFIED reference core, oracle/ref_harness.cpp)
+* ``RefPin``  -> oracle/_ref/libgbp_ref_pin.so (the same objects with the samplers served from the Philox stream:
+                 the reference's own planner loops, oracle/ref_pin_harness.cpp)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
 module.  The product package (global_body_planner_b200/) never does.
@@ -15,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libgbp_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libgbp_ref.so")
+REF_PIN_SO = os.path.join(HERE, "_ref", "libgbp_ref_pin.so")
 REFERENCE_ROOT = "/root/reference"
 
 FORWARD, REVERSE = 0, 1
@@ -95,18 +98,36 @@ class Counters(C.Structure):
 
 class PlanParams(C.Structure):
     _fields_ = [("k_candidates", C.c_int), ("best_of_k", C.c_int), ("max_iters", C.c_int), ("max_vertices", C.c_int),
-                ("adaptive", C.c_int), ("rrt_star", C.c_int), ("post_process", C.c_int)]
+                ("adaptive", C.c_int), ("rrt_star", C.c_int), ("post_process", C.c_int),
+                ("state_direction_sampling", C.c_int), ("state_direction_speed", C.c_int), ("action_direction_sampling", C.c_int),
+                ("cost_add_yaw", C.c_int), ("state_direction_threshold", C.c_double), ("action_direction_threshold", C.c_double),
+                ("cost_length_weight", C.c_double), ("cost_yaw_weight", C.c_double)]
+
+
+class TreeDump(C.Structure):
+    _fields_ = [("cap", C.c_int), ("n", C.c_int), ("states", C.c_void_p), ("actions", C.c_void_p), ("parent", C.c_void_p),
+                ("g", C.c_void_p), ("y", C.c_void_p)]
+
+
+def _tree_buffers(cap):
+    b = dict(states=np.zeros((cap, 8)), actions=np.zeros((cap, 10)), parent=np.zeros(cap, np.int32), g=np.zeros(cap), yaw=np.zeros(cap))
+    d = TreeDump(cap, 0, b["states"].ctypes.data, b["actions"].ctypes.data, b["parent"].ctypes.data, b["g"].ctypes.data, b["yaw"].ctypes.data)
+    return b, d
+
+
+def _tree_result(b, d):
+    return {k: v[:d.n].copy() for k, v in b.items()}
 
 
 class PlanStats(C.Structure):
     _fields_ = [("solved", C.c_int), ("iters", C.c_int), ("nv_a", C.c_int), ("nv_b", C.c_int), ("path_states", C.c_int),
                 ("pad", C.c_int), ("path_length", C.c_double), ("path_yaw", C.c_double), ("path_duration", C.c_double),
-                ("pair_checks", C.c_longlong), ("nn_queries", C.c_longlong)]
+                ("pair_checks", C.c_longlong), ("nn_queries", C.c_longlong), ("path_cost", C.c_double), ("reserved", C.c_longlong)]
 
 
 PLAN_STATS_DTYPE = np.dtype([("solved", "i4"), ("iters", "i4"), ("nv_a", "i4"), ("nv_b", "i4"), ("path_states", "i4"),
                              ("pad", "i4"), ("path_length", "f8"), ("path_yaw", "f8"), ("path_duration", "f8"),
-                             ("pair_checks", "i8"), ("nn_queries", "i8")])
+                             ("pair_checks", "i8"), ("nn_queries", "i8"), ("path_cost", "f8"), ("reserved", "i8")])
 
 
 def _orc():
@@ -318,6 +339,16 @@ class Oracle:
         n = st.path_states
         return st, ps[:n].copy(), pa[:max(n - 1, 0)].copy()
 
+    def plan_ex(self, start, goal, seed, query, params, path_cap=4096):
+        """orc_plan with both trees copied out -> stats, path states, path actions, tree A, tree B"""
+        st = PlanStats(); ps = np.zeros((path_cap, 8)); pa = np.zeros((path_cap, 10))
+        s, g = _f64(start), _f64(goal)
+        ba, da = _tree_buffers(params.max_vertices); bb, db = _tree_buffers(params.max_vertices)
+        self.L.orc_plan_ex(C.byref(self.t), _p(s), _p(g), C.c_uint64(seed), C.c_uint64(query), C.byref(params), C.byref(st),
+                           _p(ps), _p(pa), path_cap, C.byref(da), C.byref(db))
+        n = st.path_states
+        return st, ps[:n].copy(), pa[:max(n - 1, 0)].copy(), _tree_result(ba, da), _tree_result(bb, db)
+
     def plan_batch(self, starts, goals, seed, query0, params, nthreads=1):
         s, g = _f64(starts, (-1, 8)), _f64(goals, (-1, 8)); nq = len(s)
         st = np.zeros(nq, PLAN_STATS_DTYPE)
@@ -343,6 +374,60 @@ class Oracle:
         st3 = np.zeros(3)
         m = self.L.orc_post_process_path(C.byref(self.t), len(s), _p(s), _p(a), int(adaptive), _p(st3))
         return s[:m].copy(), a[:m - 1].copy(), st3
+
+
+class PinParams(C.Structure):
+    _fields_ = [("star", C.c_int), ("max_iters", C.c_int), ("adaptive", C.c_int), ("sort_near", C.c_int),
+                ("state_direction_sampling", C.c_int), ("state_direction_speed", C.c_int), ("action_direction_sampling", C.c_int),
+                ("cost_add_yaw", C.c_int), ("state_direction_threshold", C.c_double), ("action_direction_threshold", C.c_double),
+                ("cost_length_weight", C.c_double), ("cost_yaw_weight", C.c_double)]
+
+
+class PinResult(C.Structure):
+    _fields_ = [("solved", C.c_int), ("cells_used", C.c_int), ("nv_a", C.c_int), ("nv_b", C.c_int), ("path_states", C.c_int),
+                ("budget_hit", C.c_int), ("path_length", C.c_double), ("path_yaw", C.c_double), ("path_cost", C.c_double),
+                ("oog_height", C.c_longlong), ("oog_nan", C.c_longlong), ("near_sets", C.c_longlong), ("near_reordered", C.c_longlong)]
+
+
+class RefPin:
+    """The unmodified reference's planner loops (runRRTConnect, extend, newConfig, connect, RRT* extend) on the shared Philox
+    stream: oracle/ref_pin_harness.cpp.  What the Tier-2 oracle planner (Oracle.plan_ex) is pinned against."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_PIN_SO)
+
+    def __init__(self, terrain):
+        self.L = C.CDLL(REF_PIN_SO)
+        self.L.pin_terrain_create.restype = C.c_void_p
+        self.terrain = t = terrain
+        self.h = C.c_void_p(self.L.pin_terrain_create(t.nx, t.ny, _p(t.x), _p(t.y), _p(t.z), _p(t.dx), _p(t.dy), _p(t.dz)))
+        self.L.pin_terrain_set(t.nx, t.ny, _p(t.x), _p(t.y), _p(t.z), _p(t.dx), _p(t.dy), _p(t.dz))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pin_terrain_clear()
+            self.L.pin_terrain_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def run(self, start, goal, seed, query, params, cap=4096, path_cap=4096):
+        """-> PinResult, tree A, tree B, path states, path actions (the stitched path before postProcessPath)"""
+        t = self.terrain
+        self.L.pin_terrain_set(t.nx, t.ny, _p(t.x), _p(t.y), _p(t.z), _p(t.dx), _p(t.dy), _p(t.dz))  # one terrain is current at a time
+        s, g = _f64(start), _f64(goal)
+        ba, _ = _tree_buffers(cap); bb, _ = _tree_buffers(cap)
+        ps = np.zeros((path_cap, 8)); pa = np.zeros((path_cap, 10))
+        out = PinResult()
+        self.L.pin_run(self.h, _p(s), _p(g), C.c_uint64(seed), C.c_uint64(query), C.byref(params), C.byref(out), cap,
+                       _p(ba["states"]), _p(ba["actions"]), _p(ba["parent"]), _p(ba["g"]), _p(ba["yaw"]),
+                       _p(bb["states"]), _p(bb["actions"]), _p(bb["parent"]), _p(bb["g"]), _p(bb["yaw"]), path_cap, _p(ps), _p(pa))
+        if out.nv_a > cap or out.nv_b > cap:
+            raise RuntimeError("tree capacity of the dump exceeded")
+        n = out.path_states
+        return (out, {k: v[:out.nv_a].copy() for k, v in ba.items()}, {k: v[:out.nv_b].copy() for k, v in bb.items()},
+                ps[:n].copy(), pa[:max(n - 1, 0)].copy())
 
 
 class Ref:

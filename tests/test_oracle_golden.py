@@ -138,3 +138,29 @@ def test_interp_path_and_curvature(golden):
     # capacity: the count is still the full length, only `cap` entries are written
     s2, t2, _ = o.interp_path(G["interp_in_states"], G["interp_in_actions"], 0.05, cap=10)
     assert len(s2) == len(s) or len(s2) == 10
+
+
+# ---- planner level: the oracle planner against results minted from the UNMODIFIED reference's own loops
+# (tests/golden/golden_planner.npz, tests/golden/make_golden_planner.py).  Runs everywhere, /root/reference not needed.
+import os  # noqa: E402
+
+import planner_cases as pc  # noqa: E402
+from conftest import load_terrain  # noqa: E402
+
+
+def _planner_golden():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_planner", os.path.join(os.path.dirname(__file__), "golden", "make_golden_planner.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.load()
+
+
+@pytest.mark.parametrize("case", pc.CASES, ids=[c[0] for c in pc.CASES])
+def test_planner_matches_reference_loops_golden(case):
+    start, goal, want = _planner_golden()[case[0]]
+    T = load_terrain(case[1])
+    o = po.Oracle(T)
+    s, g = pc.start_goal(case[1], T, o)
+    assert pc.bits_equal(s, start) and pc.bits_equal(g, goal)
+    pc.compare_run(case[0], pc.oracle_run(o, case, s, g), want)

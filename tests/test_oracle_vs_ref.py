@@ -122,3 +122,49 @@ def test_interp_path_other_resolutions(pair):
     line = np.zeros((5, 8)); line[:, 0] = np.arange(5)
     assert o.max_curvature(line) == r.max_curvature(line) == 0.0
     assert o.max_curvature(line[:2]) == r.max_curvature(line[:2]) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Tier 2: the oracle PLANNER (orc_plan: extend / newConfig / connect / runRRTConnect / RRT* extend restated) against the
+# unmodified reference's own loops.  oracle/_ref/libgbp_ref_pin.so links the reference objects with the samplers served
+# from the Philox stream (ld --wrap on getRandomAction / randomState), out-of-grid terrain lookups given the defined
+# semantics, and neighborhoodDist returned in ascending id: see oracle/ref_pin_harness.cpp.
+import planner_cases as pc
+
+pin_available = pytest.mark.skipif(not po.RefPin.available(), reason="oracle/_ref/libgbp_ref_pin.so not built (no /root/reference)")
+
+
+@pin_available
+@pytest.mark.parametrize("case", pc.CASES, ids=[c[0] for c in pc.CASES])
+def test_planner_loops_match_reference(case):
+    """RRTClass::extend + newConfig (rrt.cpp:20-102), RRTConnectClass::connect + runRRTConnect (rrt_connect.cpp:98-120,
+    :230-314), RRTStarConnectClass::extend (rrt_star_connect.cpp:12-75), with and without the fork's options: both trees
+    (states, actions, parents, g, yaw sums), the stitched path (rrt_connect.cpp:381-401) and path length / yaw / cost,
+    bit for bit, after the same number of iterations."""
+    T = load_terrain(case[1])
+    o, pin = po.Oracle(T), po.RefPin(T)
+    s, g = pc.start_goal(case[1], T, o)
+    want = pc.reference_run(pin, case, s, g)
+    got = pc.oracle_run(o, case, s, g)
+    pc.compare_run(case[0], got, want)
+    assert want["oog_lookups"] > 0          # the runs do reach the reference's undefined out-of-grid lookups: the wrapper mattered
+    if case[2]:
+        assert want["near_sets"] > 0        # RRT* runs exercised choose-parent / rewire
+    if case[0].endswith("_solve") or case[0].startswith(("nan_", "mixed_")):
+        assert want["solved"] and len(want["path_states"]) >= 3
+    pin.close()
+
+
+@pin_available
+def test_near_set_order_is_the_only_interposed_semantic():
+    """Plain RRT-Connect never calls neighborhoodDist, so its runs cannot depend on the near-set order the pin library
+    defines; RRT* runs may (the reference's order is std::unordered_map's) — the raw order is
+    reported, not asserted."""
+    case = [c for c in pc.CASES if c[0] == "rough_short"][0]
+    T = load_terrain(case[1])
+    o, pin = po.Oracle(T), po.RefPin(T)
+    s, g = pc.start_goal(case[1], T, o)
+    a, b = pc.reference_run(pin, case, s, g, sort_near=1), pc.reference_run(pin, case, s, g, sort_near=0)
+    pc.compare_run("sorted vs raw near sets", a, b)
+    assert a["near_sets"] == 0
+    pin.close()
