@@ -2,7 +2,7 @@
 
 Q independent RRT-Connect queries per GPU on a seeded synthetic rough terrain, resident on the device
 (gbp_plan_batch_dev: one warp per query), contiguous query ranges per rank, no inter-GPU traffic
-except the final NCCL gather of the 64-byte per-query statistics records.  Reference-faithful
+except the final NCCL gather of the 80-byte per-query statistics records.  Reference-faithful
 extend (K = 6 candidates, first valid decides), iteration budget instead of the wall clock.
 """
 import os
@@ -58,7 +58,7 @@ def run_rough_k4096(gbp, torch, dev, nq=7104, iters=40):
     start = np.array([0, 0, h[0] + 0.375, 1, 0, 0, 0, 0.0]); goal = np.array([8, 0, h[1] + 0.375, 1, 0, 0, 0, 0.0])
     s = torch.from_numpy(np.repeat(start[None], nq, 0)).to(dev); g = torch.from_numpy(np.repeat(goal[None], nq, 0)).to(dev)
     P = gbp.PlanParams(4096, 1, iters, 256, 0, 0, 0)
-    dstats = torch.zeros(nq * 64, dtype=torch.uint8, device=dev)
+    dstats = torch.zeros(nq * 80, dtype=torch.uint8, device=dev)
     cur = torch.cuda.current_stream().cuda_stream
     t.plan_batch_dev(nq, s.data_ptr(), g.data_ptr(), 1, 0, P, dstats.data_ptr(), cur)  # warm-up (also sizes the tree arena)
     torch.cuda.synchronize()
@@ -143,7 +143,7 @@ def run(gbp, torch, dist, dev, rank, world, q_per_gpu=Q_PER_GPU, cpu_seconds=8.0
     nq = len(s)
     P = gbp.PlanParams(K_CAND, 0, MAX_ITERS, MAX_VERTS, 0, 0, 0)
     ds = torch.from_numpy(s).to(dev); dg = torch.from_numpy(g).to(dev)
-    dstats = torch.zeros(nq * 64, dtype=torch.uint8, device=dev)
+    dstats = torch.zeros(nq * 80, dtype=torch.uint8, device=dev)
     cur = torch.cuda.current_stream().cuda_stream
     query0 = rank * q_per_gpu
     t.plan_batch_dev(nq, ds.data_ptr(), dg.data_ptr(), seed, query0, P, dstats.data_ptr(), cur)  # warm-up (also sizes the tree arena)
@@ -159,7 +159,7 @@ def run(gbp, torch, dist, dev, rank, world, q_per_gpu=Q_PER_GPU, cpu_seconds=8.0
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         gathered = [torch.empty_like(dstats) for _ in range(world)] if rank == 0 else None
-        dist.gather(dstats, gathered, dst=0)  # the final NCCL gather of plan statistics (64 B per query)
+        dist.gather(dstats, gathered, dst=0)  # the final NCCL gather of plan statistics (80 B per query)
         allstats = torch.cat(gathered).cpu().numpy() if rank == 0 else None
     else:
         allstats = dstats.cpu().numpy()

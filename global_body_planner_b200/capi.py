@@ -21,7 +21,10 @@ class GbpError(RuntimeError):
 
 class PlanParams(C.Structure):
     _fields_ = [("k_candidates", C.c_int), ("best_of_k", C.c_int), ("max_iters", C.c_int), ("max_vertices", C.c_int),
-                ("adaptive", C.c_int), ("rrt_star", C.c_int), ("post_process", C.c_int), ("stop_after_solved", C.c_int)]
+                ("adaptive", C.c_int), ("rrt_star", C.c_int), ("post_process", C.c_int), ("stop_after_solved", C.c_int),
+                ("state_direction_sampling", C.c_int), ("state_direction_speed", C.c_int), ("action_direction_sampling", C.c_int),
+                ("cost_add_yaw", C.c_int), ("state_direction_threshold", C.c_double), ("action_direction_threshold", C.c_double),
+                ("cost_length_weight", C.c_double), ("cost_yaw_weight", C.c_double)]
 
 
 class SvParams(C.Structure):
@@ -49,7 +52,7 @@ def sv_params(seed, stream, idx0, normal=(0.0, 0.0, 1.0), adaptive=False, direct
 
 PLAN_STATS_DTYPE = np.dtype([("solved", "i4"), ("iters", "i4"), ("nv_a", "i4"), ("nv_b", "i4"), ("path_states", "i4"),
                              ("pad", "i4"), ("path_length", "f8"), ("path_yaw", "f8"), ("path_duration", "f8"),
-                             ("pair_checks", "i8"), ("nn_queries", "i8")])
+                             ("pair_checks", "i8"), ("nn_queries", "i8"), ("path_cost", "f8"), ("reserved", "i8")])
 
 _lib = None
 
@@ -372,6 +375,25 @@ class Terrain:
                                     _p(st), _p(ps), _p(pa), int(path_cap)))
         return (st, ps, pa) if path_cap else st
 
+    def plan_batch_trees(self, starts, goals, seed, query0, params, path_cap, tree_cap):
+        """gbp_plan_batch_trees -> stats, path states, path actions, list of (tree A, tree B) dicts per query"""
+        s, g = _f64(starts, (-1, 8)), _f64(goals, (-1, 8)); nq = len(s)
+        st = np.zeros(nq, PLAN_STATS_DTYPE)
+        ps, pa = np.zeros((nq, path_cap, 8)), np.zeros((nq, path_cap, 10))
+        ts, ta = np.zeros((nq, 2, tree_cap, 8)), np.zeros((nq, 2, tree_cap, 10))
+        tp = np.zeros((nq, 2, tree_cap), np.int32); tg, ty = np.zeros((nq, 2, tree_cap)), np.zeros((nq, 2, tree_cap))
+        _check(lib().gbp_plan_batch_trees(self.h, C.c_int64(nq), _p(s), _p(g), C.c_uint64(seed), C.c_uint64(query0), C.byref(params),
+                                          _p(st), _p(ps), _p(pa), int(path_cap), int(tree_cap), _p(ts), _p(ta), _p(tp), _p(tg), _p(ty)))
+        trees = []
+        for q in range(nq):
+            pair = []
+            for w, n in ((0, int(st["nv_a"][q])), (1, int(st["nv_b"][q]))):
+                n = min(n, tree_cap)
+                pair.append(dict(states=ts[q, w, :n].copy(), actions=ta[q, w, :n].copy(), parent=tp[q, w, :n].copy(), g=tg[q, w, :n].copy(),
+                                 yaw=ty[q, w, :n].copy()))
+            trees.append(tuple(pair))
+        return st, ps, pa, trees
+
     def plan_batch_dev(self, nq, starts_ptr, goals_ptr, seed, query0, params, stats_ptr, stream=0):
         _check(lib().gbp_plan_batch_dev(self.h, C.c_int64(nq), C.c_void_p(starts_ptr), C.c_void_p(goals_ptr), C.c_uint64(seed),
                                         C.c_uint64(query0), C.byref(params), C.c_void_p(stats_ptr), None, None, 0,
@@ -438,10 +460,10 @@ class Tree:
         _check(lib().gbp_near(self.h, _p(_f64(query)), C.c_double(radius), _p(ids), int(cap), C.byref(cnt)))
         return ids[:min(cnt.value, cap)].copy(), cnt.value
 
-    def extend(self, terrain, target, direction, k, best_of_k, seed, stream, idx0, adaptive=False):
+    def extend(self, terrain, target, direction, k, best_of_k, seed, stream, idx0, adaptive=False, dir_thresh=-1.0):
         st, nid, chk = C.c_int(), C.c_int(), C.c_int64()
         _check(lib().gbp_extend(self.h, terrain.h, _p(_f64(target)), int(direction), int(k), int(best_of_k), int(adaptive),
-                                C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(idx0), C.byref(st), C.byref(nid), C.byref(chk)))
+                                C.c_double(dir_thresh), C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(idx0), C.byref(st), C.byref(nid), C.byref(chk)))
         return st.value, nid.value, chk.value
 
     def connect(self, terrain, target, direction, adaptive=False):

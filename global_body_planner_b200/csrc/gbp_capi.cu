@@ -332,11 +332,12 @@ void gbp_terrain_destroy(gbp_terrain *t) {
 	if (!t) return;
 	if (t->z_tex) cudaDestroyTextureObject(t->z_tex);
 	if (t->z_arr) cudaFreeArray(t->z_arr);
-	cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z); cudaFree(t->d_n); cudaFree(t->d_cnt); cudaFree(t->d_redo); cudaFree(t->d_plan_arena);
+	cudaFree(t->d_x); cudaFree(t->d_y); cudaFree(t->d_z); cudaFree(t->d_n); cudaFree(t->d_cnt);
 	for (int k = 0; k < HostPipe::NBUF; ++k) {
 		cudaFree(t->pipe.in[k]); cudaFree(t->pipe.out[k]); cudaFree(t->pipe.redo[k]);
 		if (t->pipe.st[k]) cudaStreamDestroy(t->pipe.st[k]);
 	}
+	if (t->pipe.ready) cudaEventDestroy(t->pipe.ready);
 	delete t;
 }
 int gbp_terrain_dims(const gbp_terrain *t, int *nx, int *ny, int *cell_bytes) {

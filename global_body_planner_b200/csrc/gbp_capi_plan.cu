@@ -16,7 +16,7 @@ static int ensure_k(gbp_tree *T, int K) {
 	return GBP_OK;
 }
 int gbp_extend(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int K, int best_of_k, int adaptive,
-			   uint64_t seed, uint64_t stream, uint64_t idx0, int *status, int *new_id, int64_t *pair_checks) {
+			   double dir_thresh, uint64_t seed, uint64_t stream, uint64_t idx0, int *status, int *new_id, int64_t *pair_checks) {
 	if (!T || !t || !target || K < 1 || (direction != GBP_FORWARD && direction != GBP_REVERSE)) return fail(GBP_E_INVALID, "bad arguments");
 	int rc;
 	if ((rc = ensure_k(T, K))) return rc;
@@ -27,21 +27,22 @@ int gbp_extend(gbp_tree *T, const gbp_terrain *t, const double *target, int dire
 	CU(cudaHostGetDevicePointer((void **) &dres, T->h_result, 0));
 	if (adaptive) {
 		GBP_DISPATCH(t->view, k_extend_fused_adaptive, (blocks_for(K, 128), 128), st, t->view, T->view, tg, direction, K, best_of_k, 1, seed, stream, idx0,
-					 T->S, T->d_done, dres);
+					 dir_thresh, T->S, T->d_done, dres);
 	} else {
 		// lanes per candidate: as many as keep the launch inside one wave of resident CTAs (2 x 128 threads per SM at ~250 registers)
 		int S = 32;
 		while (S > 1 && (int64_t) K * S > (int64_t) sm_count() * 2 * 128) S >>= 1;
 		const int per_block = 4 * (32 / S);
 		GBP_DISPATCH(t->view, k_extend_fused, (blocks_for(K, per_block), 128), st, t->view, T->view, tg, direction, K, best_of_k, S, seed, stream, idx0,
-					 T->S, T->d_done, dres);
+					 dir_thresh, T->S, T->d_done, dres);
 	}
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(st));
 	const int res[3] = {T->h_result[0], T->h_result[1], T->h_result[2]};
+	if (pair_checks) *pair_checks = res[2];
+	if (res[0] < 0) return fail(GBP_E_CAPACITY, "tree full: the accepted vertex was not appended");
 	if (status) *status = res[0];
 	if (new_id) *new_id = res[1];
-	if (pair_checks) *pair_checks = res[2];
 	return GBP_OK;
 }
 int gbp_attempt_connect_ts(const gbp_terrain *t, int64_t n, const double *s_existing, const double *s, const double *t_s,
@@ -72,14 +73,14 @@ int gbp_attempt_connect(const gbp_terrain *t, int64_t n, const double *s_existin
 	return gbp_attempt_connect_ts(t, n, s_existing, s, nullptr, direction, adaptive, status, s_new, a_new, flags);
 }
 int gbp_new_config(const gbp_terrain *t, const double *target, const double *s_near, int direction, int K, int best_of_k, int adaptive,
-				   uint64_t seed, uint64_t stream, uint64_t idx0, int *found, double *s_new, double *a_new, int64_t *pair_checks) {
+				   double dir_thresh, uint64_t seed, uint64_t stream, uint64_t idx0, int *found, double *s_new, double *a_new, int64_t *pair_checks) {
 	if (!t || !target || !s_near || !found || !s_new || !a_new) return fail(GBP_E_INVALID, "bad arguments");
 	static thread_local gbp_tree *scratch = nullptr;  // a one-vertex tree whose nearest neighbour is s_near
 	int rc;
 	if (!scratch && (rc = gbp_tree_create(2, &scratch))) return rc;
 	if ((rc = gbp_tree_init(scratch, s_near))) return rc;
 	int status = GBP_TRAPPED, id = -1;
-	if ((rc = gbp_extend(scratch, t, target, direction, K, best_of_k, adaptive, seed, stream, idx0, &status, &id, pair_checks))) return rc;
+	if ((rc = gbp_extend(scratch, t, target, direction, K, best_of_k, adaptive, dir_thresh, seed, stream, idx0, &status, &id, pair_checks))) return rc;
 	*found = status != GBP_TRAPPED;
 	if (*found) return gbp_tree_read(scratch, id, 1, s_new, a_new, nullptr, nullptr, nullptr);
 	return GBP_OK;
@@ -95,32 +96,46 @@ int gbp_connect(gbp_tree *T, const gbp_terrain *t, const double *target, int dir
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(st));
 	const int res[3] = {T->h_result[0], T->h_result[1], T->h_result[2]};
+	if (res[0] < 0) return fail(GBP_E_CAPACITY, "tree full: the connect vertex was not appended");
 	if (status) *status = res[0];
 	if (new_id) *new_id = res[1];
 	return GBP_OK;
 }
 
 // ------------------------------------------------------------------------------ batch planner
-int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
-					   const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap,
-					   void *stream) {
+static int plan_check(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, const gbp_plan_params *p, const gbp_plan_stats *stats) {
 	if (!t || nq < 0 || !p || (nq && (!starts || !goals || !stats))) return fail(GBP_E_INVALID, "bad arguments");
 	if (p->k_candidates < 1 || p->max_iters < 0 || p->max_vertices < 2) return fail(GBP_E_INVALID, "bad plan parameters");
-	if (nq == 0) return GBP_OK;
+	return GBP_OK;
+}
+static int plan_dev(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+					const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap,
+					const PlanTreeDump &dump, cudaStream_t st) {
+	keep_pool();
 	std::string err;
-	gbp_terrain *tm = const_cast<gbp_terrain *>(t);  // scratch owned by the handle (handles are not thread-safe)
-	int rc = plan_batch_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, (cudaStream_t) stream,
-							   &tm->d_plan_arena, &tm->plan_arena_bytes, err);
+	const int rc = plan_batch_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, st, dump, err);
 	if (rc) return fail(rc, err);
 	return GBP_OK;
 }
-int gbp_plan_batch(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
-				   const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap) {
-	if (!t || nq < 0 || !p || (nq && (!starts || !goals || !stats))) return fail(GBP_E_INVALID, "bad arguments");
-	if (nq == 0) return GBP_OK;
-	cudaStream_t st = lib_stream();
-	Dev ds(st), dg(st), dst(st), dps(st), dpa(st);
+int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+					   const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap,
+					   void *stream) {
 	int rc;
+	if ((rc = plan_check(t, nq, starts, goals, p, stats))) return rc;
+	if (nq == 0) return GBP_OK;
+	const PlanTreeDump none = {0, nullptr, nullptr, nullptr, nullptr, nullptr};
+	return plan_dev(t, nq, starts, goals, seed, query0, p, stats, path_states, path_actions, path_cap, none, (cudaStream_t) stream);
+}
+int gbp_plan_batch_trees(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+						 const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap, int tree_cap,
+						 double *tree_states, double *tree_actions, int *tree_parent, double *tree_g, double *tree_yaw) {
+	int rc;
+	if ((rc = plan_check(t, nq, starts, goals, p, stats))) return rc;
+	if (nq == 0) return GBP_OK;
+	const bool want_trees = tree_cap > 0 && tree_states && tree_actions && tree_parent && tree_g && tree_yaw;
+	if (tree_cap > 0 && !want_trees) return fail(GBP_E_INVALID, "tree_cap > 0 needs all five tree arrays");
+	cudaStream_t st = lib_stream();
+	Dev ds(st), dg(st), dst(st), dps(st), dpa(st), dts(st), dta(st), dtp(st), dtg(st), dty(st);
 	if ((rc = upload(ds, starts, (size_t) 8 * nq, st)) || (rc = upload(dg, goals, (size_t) 8 * nq, st))) return rc;
 	CU(dst.alloc(sizeof(gbp_plan_stats) * nq));
 	const bool want_paths = path_states && path_actions && path_cap > 0;
@@ -128,16 +143,35 @@ int gbp_plan_batch(const gbp_terrain *t, int64_t nq, const double *starts, const
 		CU(dps.alloc(sizeof(double) * 8 * (size_t) path_cap * nq));
 		CU(dpa.alloc(sizeof(double) * 10 * (size_t) path_cap * nq));
 	}
-	if ((rc = gbp_plan_batch_dev(t, nq, ds.as<double>(), dg.as<double>(), seed, query0, p, dst.as<gbp_plan_stats>(),
-								 want_paths ? dps.as<double>() : nullptr, want_paths ? dpa.as<double>() : nullptr, path_cap, st)))
+	PlanTreeDump dump = {0, nullptr, nullptr, nullptr, nullptr, nullptr};
+	const size_t rows = want_trees ? (size_t) nq * 2 * tree_cap : 0;
+	if (want_trees) {
+		CU(dts.alloc(rows * 64)); CU(dta.alloc(rows * 80)); CU(dtp.alloc(rows * 4)); CU(dtg.alloc(rows * 8)); CU(dty.alloc(rows * 8));
+		dump.cap = tree_cap; dump.states = dts.as<double>(); dump.actions = dta.as<double>(); dump.parent = dtp.as<int>();
+		dump.g = dtg.as<double>(); dump.y = dty.as<double>();
+	}
+	if ((rc = plan_dev(t, nq, ds.as<double>(), dg.as<double>(), seed, query0, p, dst.as<gbp_plan_stats>(), want_paths ? dps.as<double>() : nullptr,
+					   want_paths ? dpa.as<double>() : nullptr, path_cap, dump, st)))
 		return rc;
 	CU(cudaMemcpyAsync(stats, dst.p, sizeof(gbp_plan_stats) * nq, cudaMemcpyDeviceToHost, st));
 	if (want_paths) {
 		CU(cudaMemcpyAsync(path_states, dps.p, sizeof(double) * 8 * (size_t) path_cap * nq, cudaMemcpyDeviceToHost, st));
 		CU(cudaMemcpyAsync(path_actions, dpa.p, sizeof(double) * 10 * (size_t) path_cap * nq, cudaMemcpyDeviceToHost, st));
 	}
+	if (want_trees) {
+		CU(cudaMemcpyAsync(tree_states, dts.p, rows * 64, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(tree_actions, dta.p, rows * 80, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(tree_parent, dtp.p, rows * 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(tree_g, dtg.p, rows * 8, cudaMemcpyDeviceToHost, st));
+		CU(cudaMemcpyAsync(tree_yaw, dty.p, rows * 8, cudaMemcpyDeviceToHost, st));
+	}
 	CU(cudaStreamSynchronize(st));
 	return GBP_OK;
+}
+int gbp_plan_batch(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+				   const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap) {
+	return gbp_plan_batch_trees(t, nq, starts, goals, seed, query0, p, stats, path_states, path_actions, path_cap, 0, nullptr, nullptr, nullptr,
+								nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -6,22 +6,26 @@
 extern "C" {
 
 // ------------------------------------------------------------------------------ validate_pairs
+// `scratch` / `scratch_cap`: redo list + recipe array of the mixed-precision walk ([cap] ints, an 8-byte counter at a 16-byte
+// offset, [cap] double2) owned by the caller (the host pipeline keeps one per buffer set), or null: allocated for this call
+// on its stream and released in stream order — concurrent calls on one terrain handle do not share scratch.
 static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
 							 int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream,
-							 bool zero_counters);
+							 bool zero_counters, int *scratch, size_t scratch_cap);
 int gbp_validate_pairs_dev(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
 						   int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream) {
-	return validate_dev_impl(t, n, states, actions, direction, adaptive, variant, verdict, flags, s_new, t_new, stream, true);
+	return validate_dev_impl(t, n, states, actions, direction, adaptive, variant, verdict, flags, s_new, t_new, stream, true, nullptr, 0);
 }
 static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *states, const double *actions, const uint8_t *direction,
 							 int adaptive, int variant, uint8_t *verdict, uint8_t *flags, double *s_new, double *t_new, void *stream,
-							 bool zero_counters) {
+							 bool zero_counters, int *scratch, size_t scratch_cap) {
 	if (!t || n < 0 || (n && (!states || !actions || !direction || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
 	if (variant < 0 || variant > 5 || variant == 4) return fail(GBP_E_INVALID, "variant must be 0..3 or 5");
 	const bool walk_only = variant == 5;
 	if (walk_only) variant = 3;
 	if (variant == 2 && adaptive) return fail(GBP_E_INVALID, "variant 2 (warp per action) supports the fixed step only");
 	cudaStream_t st = (cudaStream_t) stream;
+	Dev own(st);  // per-call scratch: released (in stream order) when the function returns, i.e. after k_pair_outputs is enqueued
 	if (zero_counters) CU(cudaMemsetAsync(t->d_cnt, 0, 6 * sizeof(unsigned long long), st));
 	if (n == 0) return GBP_OK;
 	if (variant == 0) variant = 3;
@@ -63,20 +67,17 @@ static int validate_dev_impl(const gbp_terrain *t, int64_t n, const double *stat
 		if (t->view.mixed_ok) {
 			// mixed-precision walk (k_walk_mixed, gbp_walk.cuh) + fp64 redo pass over the candidates it could not decide
 			if (n > 0x7fffffff) return fail(GBP_E_INVALID, "at most 2^31-1 candidates per call");
-			gbp_terrain *tm = const_cast<gbp_terrain *>(t);  // grow-only scratch owned by the handle (handles are not thread-safe)
-			if (tm->redo_cap < (size_t) n) {
-				CU(cudaStreamSynchronize(st));
-				cudaFree(tm->d_redo);
-				tm->d_redo = nullptr; tm->redo_cap = 0;
-				const size_t cap = ((size_t) n + 1023) / 1024 * 1024;
-				CU(cudaMalloc((void **) &tm->d_redo, cap * sizeof(int) + 16 + cap * sizeof(double2)));  // + the compact recipe array
-				tm->redo_cap = cap;
+			size_t cap = scratch_cap;
+			int *redo = scratch;
+			if (!redo || cap < (size_t) n) {
+				cap = ((size_t) n + 1023) / 1024 * 1024;
+				CU(own.alloc(cap * sizeof(int) + 16 + cap * sizeof(double2)));  // freed in stream order when `own` goes out of scope
+				redo = own.as<int>();
 			}
-			int *redo = tm->d_redo;
-			unsigned long long *redo_count = (unsigned long long *) (redo + tm->redo_cap);
+			unsigned long long *redo_count = (unsigned long long *) (redo + cap);
 			// {tau, kind} per candidate between the walk and k_pair_outputs: compact side array, except when the caller
 			// finishes the outputs itself (variant 5: the recipes stay in s_new[i][0..1])
-			recipe = (s_new && !walk_only) ? (double2 *) ((char *) redo + tm->redo_cap * sizeof(int) + 16) : nullptr;
+			recipe = (s_new && !walk_only) ? (double2 *) ((char *) redo + cap * sizeof(int) + 16) : nullptr;
 			CU(cudaMemsetAsync(redo_count, 0, sizeof(unsigned long long), st));
 #define GBP_WALK_(TEX, AD) CU(cudaLaunchKernelEx(&cfg, k_walk_mixed<TEX, AD>, t->view, (int) n, (int) per_warp, states, actions, direction, verdict, flags, s_new, t_new, t->d_cnt, redo, redo_count, recipe))
 			if (t->view.ztex) { if (adaptive) GBP_WALK_(true, true); else GBP_WALK_(true, false); }
@@ -126,7 +127,9 @@ int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, co
 	if (!t || n < 0 || (n && (!states || !actions || !direction || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
 	if (n == 0) return GBP_OK;
 	constexpr int NBUF = HostPipe::NBUF;
-	HostPipe &P = const_cast<gbp_terrain *>(t)->pipe;  // scratch owned by the handle (handles are not thread-safe)
+	gbp_terrain *tm = const_cast<gbp_terrain *>(t);
+	std::lock_guard<std::mutex> lock(tm->pipe_mutex);  // the staging ring and the work counters belong to the handle: one host-pointer call at a time
+	HostPipe &P = tm->pipe;
 	const int64_t want = n < (1 << 19) ? (n + 1023) / 1024 * 1024 : (1 << 19);
 	if (P.chunk < want) {
 		for (int k = 0; k < NBUF; ++k) {
@@ -141,14 +144,18 @@ int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, co
 			CU(cudaMalloc(&P.out[k], (size_t) want * (64 + 8 + 1 + 1)));
 			CU(cudaMalloc((void **) &P.redo[k], (size_t) want * sizeof(int) + 16 + (size_t) want * sizeof(double2)));
 		}
+		if (!P.ready) CU(cudaEventCreateWithFlags(&P.ready, cudaEventDisableTiming));
 		P.chunk = want;
 	}
 	const int64_t chunk = P.chunk;
-	CU(cudaMemset(t->d_cnt, 0, 6 * sizeof(unsigned long long)));
-	gbp_terrain shadow = *t;  // same view and counters, per-set redo scratch
+	// the counters are zeroed on the first pipeline stream; the other streams (non-blocking: nothing else orders them) wait for it
+	CU(cudaMemsetAsync(t->d_cnt, 0, 6 * sizeof(unsigned long long), P.st[0]));
+	CU(cudaEventRecord(P.ready, P.st[0]));
+	for (int k = 1; k < NBUF; ++k) CU(cudaStreamWaitEvent(P.st[k], P.ready, 0));
 	int64_t ci = 0;
 	int rc = GBP_OK;
-	for (int64_t off = 0; off < n && rc == GBP_OK; off += chunk, ++ci) {
+	cudaError_t e = cudaSuccess;
+	for (int64_t off = 0; off < n && rc == GBP_OK && e == cudaSuccess; off += chunk, ++ci) {
 		const int k = (int) (ci % NBUF);
 		cudaStream_t st = P.st[k];
 		const int64_t m = n - off < chunk ? n - off : chunk;
@@ -156,23 +163,24 @@ int gbp_validate_pairs(const gbp_terrain *t, int64_t n, const double *states, co
 		uint8_t *d_d = (uint8_t *) (P.in[k] + (size_t) chunk * 144);
 		double *d_sn = (double *) P.out[k], *d_tn = (double *) (P.out[k] + (size_t) chunk * 64);
 		uint8_t *d_v = (uint8_t *) (P.out[k] + (size_t) chunk * 72), *d_f = d_v + chunk;
-		CU(cudaMemcpyAsync(d_s, states + 8 * off, (size_t) m * 64, cudaMemcpyHostToDevice, st));
-		CU(cudaMemcpyAsync(d_a, actions + 10 * off, (size_t) m * 80, cudaMemcpyHostToDevice, st));
-		CU(cudaMemcpyAsync(d_d, direction + off, (size_t) m, cudaMemcpyHostToDevice, st));
-		shadow.d_redo = P.redo[k];
-		shadow.redo_cap = (size_t) chunk;
-		rc = validate_dev_impl(&shadow, m, d_s, d_a, d_d, adaptive, variant, d_v, flags ? d_f : nullptr, s_new ? d_sn : nullptr,
-							   t_new ? d_tn : nullptr, st, false);
+		e = cudaMemcpyAsync(d_s, states + 8 * off, (size_t) m * 64, cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(d_a, actions + 10 * off, (size_t) m * 80, cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, direction + off, (size_t) m, cudaMemcpyHostToDevice, st);
+		if (e != cudaSuccess) break;
+		rc = validate_dev_impl(t, m, d_s, d_a, d_d, adaptive, variant, d_v, flags ? d_f : nullptr, s_new ? d_sn : nullptr, t_new ? d_tn : nullptr, st,
+							   false, P.redo[k], (size_t) chunk);
 		if (rc) break;
-		CU(cudaMemcpyAsync(verdict + off, d_v, (size_t) m, cudaMemcpyDeviceToHost, st));
-		if (flags) CU(cudaMemcpyAsync(flags + off, d_f, (size_t) m, cudaMemcpyDeviceToHost, st));
-		if (s_new) CU(cudaMemcpyAsync(s_new + 8 * off, d_sn, (size_t) m * 64, cudaMemcpyDeviceToHost, st));
-		if (t_new) CU(cudaMemcpyAsync(t_new + off, d_tn, (size_t) m * 8, cudaMemcpyDeviceToHost, st));
+		e = cudaMemcpyAsync(verdict + off, d_v, (size_t) m, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess && flags) e = cudaMemcpyAsync(flags + off, d_f, (size_t) m, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess && s_new) e = cudaMemcpyAsync(s_new + 8 * off, d_sn, (size_t) m * 64, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess && t_new) e = cudaMemcpyAsync(t_new + off, d_tn, (size_t) m * 8, cudaMemcpyDeviceToHost, st);
 	}
+	// common epilogue, also after a failure: no copy into the caller's buffers stays in flight
 	for (int k = 0; k < NBUF; ++k) {
-		cudaError_t e = cudaStreamSynchronize(P.st[k]);
-		if (e != cudaSuccess && rc == GBP_OK) rc = fail(GBP_E_CUDA, std::string("validate pipeline: ") + cudaGetErrorString(e));
+		const cudaError_t es = cudaStreamSynchronize(P.st[k]);
+		if (es != cudaSuccess && e == cudaSuccess) e = es;
 	}
+	if (rc == GBP_OK && e != cudaSuccess) rc = fail(GBP_E_CUDA, std::string("validate pipeline: ") + cudaGetErrorString(e));
 	return rc;
 }
 

@@ -99,21 +99,19 @@ struct HostPipe {
 	char *in[NBUF] = {nullptr, nullptr, nullptr}, *out[NBUF] = {nullptr, nullptr, nullptr};
 	int *redo[NBUF] = {nullptr, nullptr, nullptr};
 	int64_t chunk = 0;  // candidates per buffer set
+	cudaEvent_t ready = nullptr;
 };
 
 struct gbp_terrain {
 	TerrainView view;
 	HostPipe pipe;
+	std::mutex pipe_mutex;                // serialises the host-pointer pair checks on this handle (they share `pipe` and d_cnt)
 	double *d_x = nullptr, *d_y = nullptr;
 	void *d_z = nullptr;
 	void *d_n = nullptr;
 	cudaArray_t z_arr = nullptr;          // block-linear copy of the fp32 height grid behind view.ztex (texture gathers of the walk)
 	cudaTextureObject_t z_tex = 0;
 	unsigned long long *d_cnt = nullptr;  // 6 work counters of the last validate launch
-	int *d_redo = nullptr;                // redo list of the mixed-precision walk: [redo_cap] indices + an 8-byte counter
-	size_t redo_cap = 0;
-	void *d_plan_arena = nullptr;         // tree arena of the batch planner (grow-only)
-	size_t plan_arena_bytes = 0;
 	size_t z_bytes = 0;                   // height grid bytes
 	float l2_hit_ratio = 0.f;             // share of the grid that fits the persisting L2 carve-out (0 = no window)
 	std::vector<double> hx, hy;

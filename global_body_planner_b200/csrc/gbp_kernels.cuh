@@ -1055,7 +1055,7 @@ __global__ void __launch_bounds__(32) k_connect(TerrainView T, TreeView tree, Ta
 	int new_id = -1;
 	if (r != GBP_TRAPPED) {
 		if (nv < tree.cap) new_id = tree_push(tree, near, sn, an);
-		else r = GBP_TRAPPED;
+		else r = -1;  // tree full: reported as GBP_E_CAPACITY, not as TRAPPED
 	}
 	S.result[0] = r; S.result[1] = new_id; S.result[2] = (int) checks;
 	host_result[0] = r; host_result[1] = new_id; host_result[2] = (int) checks;

@@ -31,6 +31,14 @@ struct PlanTree {
 	TreeView t;
 	int *child, *sibling;
 };
+// optional copy of every query's two trees (inspection / parity tests): AoS rows per (query, tree, vertex)
+struct PlanTreeDump {
+	int cap;           // vertices per tree in the dump
+	double *states;    // [nq][2][cap][8]
+	double *actions;   // [nq][2][cap][10]
+	int *parent;       // [nq][2][cap]
+	double *g, *y;     // [nq][2][cap]
+};
 
 __device__ __forceinline__ PlanTree arena_tree(const PlanArena &A, int slot, int which, int *n_ptr) {
 	PlanTree T;
@@ -160,6 +168,10 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 	surface_normal(Tv, s[0], s[1], nn, fl);  // rrt.cpp:25 — at the TARGET sample
 	grf_rotation(nn, R);
 	const int K = P.k_candidates;
+	// getRandomAction(surf_norm, direction, flag, threshold, s, s_near) (rrt.cpp:34, :49): FORWARD samples from s_near
+	// towards s, REVERSE from s towards s_near (planning_utils.cpp:385-388)
+	const bool dirs = P.action_direction_sampling != 0;
+	const double *a_from = dir == GBP_FORWARD ? s_near : s, *a_to = dir == GBP_FORWARD ? s : s_near;
 	double my_d = INFINITY, my_sn[8], my_a[10];
 	int my_j = 0x7fffffff, first = 0x7fffffff;
 	if (WIDE) {
@@ -183,7 +195,7 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 					const int rel = next + __popc(idle & ((1u << lane) - 1u));
 					if (rel < K) {
 						j = rel;
-						sample_action(seed, query, cell * (uint64_t) K + (uint64_t) j, R, false, 0.0, nullptr, nullptr, q.a);
+						sample_action(seed, query, cell * (uint64_t) K + (uint64_t) j, R, dirs, P.action_direction_threshold, a_from, a_to, q.a);
 						cursor_start(q, dir);
 						running = true;
 					}
@@ -217,7 +229,7 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 			const int j = base + g;
 			const bool has = g < G && j < K;
 			double a[10];
-			sample_action(seed, query, cell * (uint64_t) K + (uint64_t) (has ? j : 0), R, false, 0.0, nullptr, nullptr, a);
+			sample_action(seed, query, cell * (uint64_t) K + (uint64_t) (has ? j : 0), R, dirs, P.action_direction_threshold, a_from, a_to, a);
 			const bool ok = group_validate<M>(Tv, s_near, a, dir, S, r, gmask, has ? gshift : 0, has);
 			if (ok && r == 0) {  // one lane per candidate keeps the result
 				double sn[8];
@@ -242,7 +254,7 @@ __device__ bool warp_new_config(const TerrainView &Tv, const double s[8], const 
 			bool ok = false;
 			double a[10], sn[8], tn;
 			if (j < K) {
-				sample_action(seed, query, cell * (uint64_t) K + (uint64_t) j, R, false, 0.0, nullptr, nullptr, a);
+				sample_action(seed, query, cell * (uint64_t) K + (uint64_t) j, R, dirs, P.action_direction_threshold, a_from, a_to, a);
 				Counters c = {0, 0, 0, 0};
 				ok = validate_pair_seq<M>(Tv, s_near, a, dir, true, sn, tn, c);
 			}
@@ -429,7 +441,7 @@ __device__ int warp_connect(const TerrainView &Tv, PlanTree &T, int &nv, const d
 // at a time from the far end, the farthest REACHED one wins — the same choice.  Quirk kept: the fallback branch adds to
 // path_cost only.  Returns the new number of states; stats3 = {length, yaw, cost}.
 template <typename M>
-__device__ int warp_post_process(const TerrainView &Tv, double *ps, double *pa, int ns, bool adaptive, int lane, double stats3[3]) {
+__device__ int warp_post_process(const TerrainView &Tv, double *ps, double *pa, int ns, bool adaptive, int lane, const gbp_plan_params &P, double stats3[3]) {
 	int m = 1, cur = 0;
 	double len = 0, yaw = 0, cost = 0;
 	while (cur < ns - 1) {
@@ -459,10 +471,10 @@ __device__ int warp_post_process(const TerrainView &Tv, double *ps, double *pa, 
 		const int nxt = pick >= 0 ? pick : cur + 1;
 		double sn[8];
 		for (int d = 0; d < 8; ++d) sn[d] = ps[8 * (size_t) nxt + d];
-		const double dl = pose_distance(sc, sn);
-		if (pick >= 0) { len += dl; yaw += yaw_distance(sc, sn); }
+		const double dl = pose_distance(sc, sn), dy = yaw_distance(sc, sn);
+		if (pick >= 0) { len += dl; yaw += dy; }
 		else { for (int d = 0; d < 10; ++d) a_pick[d] = pa[10 * (size_t) cur + d]; }  // the original action into state cur+1
-		cost += dl;
+		if (P.cost_add_yaw) cost += dl * P.cost_length_weight + dy * P.cost_yaw_weight; else cost += dl;  // rrt_connect.cpp:196, :212
 		__syncwarp();
 		if (lane == 0) {
 			for (int d = 0; d < 8; ++d) ps[8 * (size_t) m + d] = sn[d];
@@ -488,7 +500,7 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 													 const double *__restrict__ goals, uint64_t seed, uint64_t query0,
 													 gbp_plan_params P, PlanArena A, int *__restrict__ counts,
 													 gbp_plan_stats *__restrict__ stats, double *__restrict__ path_states,
-													 double *__restrict__ path_actions, int path_cap) {
+													 double *__restrict__ path_actions, int path_cap, PlanTreeDump dump) {
 	const int lane = threadIdx.x & 31;
 	const int64_t slot = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
 	unsigned long long *next_query = (unsigned long long *) (counts + 2 * (((int64_t) gridDim.x * blockDim.x) >> 5));
@@ -527,16 +539,28 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 				// Random states come from a counter-based stream (STATE cell = 2 * iter + half) and their validity does not
 				// depend on the trees: the warp draws and checks the next 32 cells at once, lane L holding cell base + L,
 				// instead of all 32 lanes redundantly producing one (that was ~75 % of the kernel's instructions).
-				if ((cell & 31ull) == 0) {
-					sample_state<M>(Tv, seed, query, cell + (uint64_t) lane, false, 0.0, false, nullptr, nullptr, rs);
-					Counters c = {0, 0, 0, 0};
-					rs_valid = __ballot_sync(FULL, is_valid_state_auto<M>(Tv, pose6(rs), GBP_STANCE, c));
-				}
-				const int src = (int) (cell & 31ull);
-				if (!((rs_valid >> src) & 1u)) continue;  // rrt_connect.cpp:254
 				double s_rand[8];
+				if (P.state_direction_sampling) {
+					// randomState(terrain, flag, threshold, speed flag, s_from, s_to) between the start-side tree's newest vertex /
+					// root and the goal-side tree's root / newest vertex (rrt_connect.cpp:246-251, :281-286): the sample depends on
+					// the trees, so it is drawn when it is needed (every lane draws the same cell)
+					double s_from[8], s_to[8];
+					tree_get(Ta.t, half == 0 ? na - 1 : 0, s_from);
+					tree_get(Tb.t, half == 0 ? 0 : nb - 1, s_to);
+					sample_state<M>(Tv, seed, query, cell, true, P.state_direction_threshold, P.state_direction_speed != 0, s_from, s_to, s_rand);
+					Counters c = {0, 0, 0, 0};
+					if (!is_valid_state_auto<M>(Tv, pose6(s_rand), GBP_STANCE, c)) continue;  // rrt_connect.cpp:254
+				} else {
+					if ((cell & 31ull) == 0) {
+						sample_state<M>(Tv, seed, query, cell + (uint64_t) lane, false, 0.0, false, nullptr, nullptr, rs);
+						Counters c = {0, 0, 0, 0};
+						rs_valid = __ballot_sync(FULL, is_valid_state_auto<M>(Tv, pose6(rs), GBP_STANCE, c));
+					}
+					const int src = (int) (cell & 31ull);
+					if (!((rs_valid >> src) & 1u)) continue;  // rrt_connect.cpp:254
 #pragma unroll
-				for (int d = 0; d < 8; ++d) s_rand[d] = __shfl_sync(FULL, rs[d], src);
+					for (int d = 0; d < 8; ++d) s_rand[d] = __shfl_sync(FULL, rs[d], src);
+				}
 				++nn_queries;
 				const int r = STAR ? warp_extend_star<M>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, gm, A, (int) slot, lane, pair_checks)
 								   : warp_extend<M, WIDE>(Tv, Tx, nx, s_rand, dir_ext, seed, query, cell, P, gm, lane, pair_checks);
@@ -551,6 +575,7 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 		gbp_plan_stats st;
 		st.solved = solved ? 1 : 0; st.iters = it; st.nv_a = na; st.nv_b = nb; st.path_states = 0; st.pad = 0;
 		st.path_length = 0; st.path_yaw = 0; st.path_duration = 0; st.pair_checks = pair_checks; st.nn_queries = nn_queries;
+		st.path_cost = 0; st.reserved = 0;
 		if (solved) {
 			double *ps = A.pstate + (size_t) slot * 2 * A.cap * 8, *pa = A.paction + (size_t) slot * 2 * A.cap * 10;
 			int la = 0, lb = 0;
@@ -572,11 +597,13 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 			__syncwarp();
 			st.path_length = Ta.t.g[na - 1] + Tb.t.g[nb - 1];
 			st.path_yaw = Ta.t.y[na - 1] + Tb.t.y[nb - 1];
+			st.path_cost = P.cost_add_yaw ? st.path_length * P.cost_length_weight + st.path_yaw * P.cost_yaw_weight : st.path_length;  // :270-274
 			if (P.post_process) {
 				double s3[3];
-				total = warp_post_process<M>(Tv, ps, pa, total, P.adaptive != 0, lane, s3);
+				total = warp_post_process<M>(Tv, ps, pa, total, P.adaptive != 0, lane, P, s3);
 				st.path_length = s3[0];
 				st.path_yaw = s3[1];
+				st.path_cost = s3[2];
 			}
 			st.path_states = total;
 			double dur = 0;
@@ -589,6 +616,20 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 					for (int d = 0; d < 10; ++d) path_actions[((size_t) qi * path_cap + i) * 10 + d] = pa[10 * (size_t) i + d];
 			}
 		}
+		if (dump.states) {  // both trees, vertex by vertex
+			for (int w = 0; w < 2; ++w) {
+				const PlanTree &Tw = w == 0 ? Ta : Tb;
+				const int nw = w == 0 ? na : nb;
+				const size_t base = ((size_t) qi * 2 + w) * dump.cap;
+				for (int i = lane; i < nw && i < dump.cap; i += 32) {
+					for (int d = 0; d < 8; ++d) dump.states[(base + i) * 8 + d] = Tw.t.v[(size_t) d * Tw.t.cap + i];
+					for (int d = 0; d < 10; ++d) dump.actions[(base + i) * 10 + d] = Tw.t.act[(size_t) d * Tw.t.cap + i];
+					dump.parent[base + i] = Tw.t.parent[i];
+					dump.g[base + i] = Tw.t.g[i];
+					dump.y[base + i] = Tw.t.y[i];
+				}
+			}
+		}
 		if (lane == 0) {
 			stats[qi] = st;
 			if (solved && P.stop_after_solved > 0) atomicAdd((int *) solved_count, 1);
@@ -599,9 +640,11 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 
 // host-side launcher: sizes the grid to the SM count, allocates the tree arena for the resident warps
 // `arena` / `arena_bytes`: grow-only device scratch owned by the caller's terrain handle
+// the tree arena is stream-ordered scratch of the call (cudaMallocAsync / cudaFreeAsync on `st`): concurrent calls on one
+// terrain handle from different streams or threads do not share it
 inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *starts, const double *goals, uint64_t seed,
 							 uint64_t query0, const gbp_plan_params &P, gbp_plan_stats *stats, double *path_states, double *path_actions,
-							 int path_cap, cudaStream_t st, void **arena, size_t *arena_bytes, std::string &err) {
+							 int path_cap, cudaStream_t st, const PlanTreeDump &dump, std::string &err) {
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -616,14 +659,8 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	const size_t n_ints = per * 3 + (size_t) slots * cap * 3 + (size_t) slots * 2 + 4;  // + the 8-byte work counter and the solved count
 	cudaError_t e;
 	const size_t need = n_doubles * sizeof(double) + n_ints * sizeof(int);
-	if (*arena_bytes < need) {
-		cudaStreamSynchronize(st);
-		cudaFree(*arena);
-		*arena = nullptr; *arena_bytes = 0;
-		if ((e = cudaMalloc(arena, need)) != cudaSuccess) { err = std::string("plan arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
-		*arena_bytes = need;
-	}
-	void *mem = *arena;
+	void *mem = nullptr;
+	if ((e = cudaMallocAsync(&mem, need, st)) != cudaSuccess) { err = std::string("plan arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
 	double *dp = (double *) mem;
 	A.v = dp; dp += per * 8;
 	A.act = dp; dp += per * 10;
@@ -643,16 +680,17 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	int *counts = ip;
 	{  // 8-byte aligned work counter right after the per-slot vertex counts
 		unsigned long long *next_query = (unsigned long long *) (counts + 2 * slots);
-		if ((e = cudaMemsetAsync(next_query, 0, sizeof(unsigned long long) + 2 * sizeof(int), st)) != cudaSuccess) { err = cudaGetErrorString(e); return GBP_E_CUDA; }
+		if ((e = cudaMemsetAsync(next_query, 0, sizeof(unsigned long long) + 2 * sizeof(int), st)) != cudaSuccess) { err = cudaGetErrorString(e); cudaFreeAsync(mem, st); return GBP_E_CUDA; }
 	}
 	const bool wide = !P.rrt_star && !P.adaptive && P.best_of_k && P.k_candidates > 32;  // the refill form of newConfig
-#define GBP_PLAN_(M) do { if (P.rrt_star) k_plan_batch<M, true><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); \
-						  else if (wide) k_plan_batch<M, false, true><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); \
-						  else k_plan_batch<M, false><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap); } while (0)
+#define GBP_PLAN_(M) do { if (P.rrt_star) k_plan_batch<M, true><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap, dump); \
+						  else if (wide) k_plan_batch<M, false, true><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap, dump); \
+						  else k_plan_batch<M, false><<<grid, threads, 0, st>>>(Tv, nq, starts, goals, seed, query0, P, A, counts, stats, path_states, path_actions, path_cap, dump); } while (0)
 	if (Tv.cell_f32) { if (Tv.uniform) GBP_PLAN_(MapF32U); else GBP_PLAN_(MapF32N); }
 	else { if (Tv.uniform) GBP_PLAN_(MapF64U); else GBP_PLAN_(MapF64N); }
 #undef GBP_PLAN_
 	e = cudaGetLastError();
+	cudaFreeAsync(mem, st);  // stream-ordered: released after the kernel
 	if (e != cudaSuccess) { err = std::string("k_plan_batch: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
 	return GBP_OK;
 }
@@ -666,7 +704,7 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 // travels as a kernel argument.
 template <typename M, bool GROUP>
 __device__ __forceinline__ void extend_fused_body(const TerrainView &T, const TreeView &tree, const Target8 &tgt, int direction, int K, int best_of_k,
-												  int S, uint64_t seed, uint64_t stream, uint64_t idx0, const ExtendScratch &S_,
+												  int S, uint64_t seed, uint64_t stream, uint64_t idx0, double dir_thresh, const ExtendScratch &S_,
 												  unsigned *__restrict__ done, int *__restrict__ host_result) {
 	__shared__ double sd[4];
 	__shared__ int si[4];
@@ -701,6 +739,9 @@ __device__ __forceinline__ void extend_fused_body(const TerrainView &T, const Tr
 	unsigned fl = 0;
 	surface_normal(T, tg[0], tg[1], nn, fl);  // rrt.cpp:25 — normal at the TARGET sample
 	grf_rotation(nn, R);
+	// directional action sampling (planning_utils.cpp:379-391): a negative threshold switches it off (flag && p <= thr)
+	const bool dirs = dir_thresh >= 0.0;
+	const double *a_from = direction == GBP_FORWARD ? s_near : tg, *a_to = direction == GBP_FORWARD ? tg : s_near;
 	// ---- candidates (newConfig, rrt.cpp:20-70, generalised to K)
 	if (GROUP) {
 		// fixed step: S lanes per candidate speculate its sub-states S at a time (group_validate: only the verdict of a
@@ -711,7 +752,7 @@ __device__ __forceinline__ void extend_fused_body(const TerrainView &T, const Tr
 		const bool has = g < G && j < K;
 		const unsigned gmask = S == 32 ? FULL : ((1u << S) - 1u);
 		double a[10];
-		sample_action(seed, stream, idx0 + (uint64_t) (has ? j : 0), R, false, 0.0, nullptr, nullptr, a);
+		sample_action(seed, stream, idx0 + (uint64_t) (has ? j : 0), R, dirs, dir_thresh, a_from, a_to, a);
 		const bool ok = group_validate<M>(T, s_near, a, direction, S, r, gmask, has ? g * S : 0, has);
 		if (has && r == 0) {
 			double sn[8];
@@ -724,7 +765,7 @@ __device__ __forceinline__ void extend_fused_body(const TerrainView &T, const Tr
 		const int j = blockIdx.x * blockDim.x + threadIdx.x;
 		if (j < K) {
 			double a[10], sn[8], tn;
-			sample_action(seed, stream, idx0 + (uint64_t) j, R, false, 0.0, nullptr, nullptr, a);
+			sample_action(seed, stream, idx0 + (uint64_t) j, R, dirs, dir_thresh, a_from, a_to, a);
 			Counters c = {0, 0, 0, 0};
 			const bool ok = validate_pair_seq<M>(T, s_near, a, direction, true, sn, tn, c);
 			S_.valid[j] = ok ? 1 : 0;
@@ -765,10 +806,12 @@ __device__ __forceinline__ void extend_fused_body(const TerrainView &T, const Tr
 		}
 		int status = GBP_TRAPPED, new_id = -1;
 		const int checks = best_of_k ? K : (bi == 0x7fffffff ? K : bi + 1);
-		if (bi != 0x7fffffff && *tree.n < tree.cap && bd < state_distance(s_near, tg)) {  // rrt.cpp:55-66
+		const bool accept = bi != 0x7fffffff && bd < state_distance(s_near, tg);  // rrt.cpp:55-66
+		if (accept && !(*tree.n < tree.cap)) status = -1;  // tree full: reported as GBP_E_CAPACITY, not as TRAPPED
+		else if (accept) {
 			double sn[8], a[10];
 			for (int d = 0; d < 8; ++d) sn[d] = __ldcg(S_.s_test + 8 * (size_t) bi + d);
-			sample_action(seed, stream, idx0 + (uint64_t) bi, R, false, 0.0, nullptr, nullptr, a);
+			sample_action(seed, stream, idx0 + (uint64_t) bi, R, dirs, dir_thresh, a_from, a_to, a);
 			new_id = tree_push(tree, near, sn, a);
 			status = state_distance(sn, tg) <= GOAL_BOUNDS ? GBP_REACHED : GBP_ADVANCED;  // rrt.cpp:96-99
 		}
@@ -779,15 +822,15 @@ __device__ __forceinline__ void extend_fused_body(const TerrainView &T, const Tr
 }
 template <typename M>
 __global__ void __launch_bounds__(128) k_extend_fused(TerrainView T, TreeView tree, Target8 tgt, int direction, int K, int best_of_k,
-													   int lanes_per_candidate, uint64_t seed, uint64_t stream, uint64_t idx0, ExtendScratch S,
+													   int lanes_per_candidate, uint64_t seed, uint64_t stream, uint64_t idx0, double dir_thresh, ExtendScratch S,
 													   unsigned *__restrict__ done, int *__restrict__ host_result) {
-	extend_fused_body<M, true>(T, tree, tgt, direction, K, best_of_k, lanes_per_candidate, seed, stream, idx0, S, done, host_result);
+	extend_fused_body<M, true>(T, tree, tgt, direction, K, best_of_k, lanes_per_candidate, seed, stream, idx0, dir_thresh, S, done, host_result);
 }
 template <typename M>
 __global__ void __launch_bounds__(128) k_extend_fused_adaptive(TerrainView T, TreeView tree, Target8 tgt, int direction, int K, int best_of_k,
-																int unused, uint64_t seed, uint64_t stream, uint64_t idx0, ExtendScratch S,
+																int unused, uint64_t seed, uint64_t stream, uint64_t idx0, double dir_thresh, ExtendScratch S,
 																unsigned *__restrict__ done, int *__restrict__ host_result) {
-	extend_fused_body<M, false>(T, tree, tgt, direction, K, best_of_k, 1, seed, stream, idx0, S, done, host_result);
+	extend_fused_body<M, false>(T, tree, tgt, direction, K, best_of_k, 1, seed, stream, idx0, dir_thresh, S, done, host_result);
 }
 
 }  // namespace gbp

@@ -20,31 +20,17 @@ RRTClass::~RRTClass() {}
 void RRTClass::set_candidates_per_extend(int k, bool best_of_k) { k_candidates_ = std::max(1, k); best_of_k_ = best_of_k; }
 void RRTClass::set_random_stream(std::uint64_t seed, std::uint64_t stream) { seed_ = seed; stream_ = stream; cell_ = 0; }
 
-// rrt.cpp:20-70.  Without directional action sampling the K candidates are sampled, validated and selected in
-// one device pass (gbp_new_config); with it, candidates are drawn one at a time as the reference does.
+// rrt.cpp:20-70: the K candidates are sampled (with the directional option when set: planning_utils.cpp:379-391),
+// validated and selected in one device pass
 bool RRTClass::newConfig(State s, State s_near, State &s_new, Action &a_new, FastTerrainMap &terrain, int direction) {
-	if (!action_direction_sampling_flag_) {
-		int found = 0;
-		const std::uint64_t idx0 = (cell_++) * (std::uint64_t) k_candidates_;
-		check(gbp_new_config(terrain.handle(), s.data(), s_near.data(), direction, k_candidates_, best_of_k_ ? 1 : 0,
-							 state_action_pair_check_adaptive_step_size_flag_ ? 1 : 0, seed_, stream_, idx0, &found, s_new.data(), a_new.data(), nullptr),
-			  "newConfig");
-		return found != 0;
-	}
-	const double best_so_far = stateDistance(s_near, s);
-	std::array<double, 3> surf_norm = terrain.getSurfaceNormal(s[0], s[1]);
-	for (int j = 0; j < k_candidates_; ++j) {
-		Action a_test = getRandomAction(surf_norm, direction, true, action_direction_sampling_probability_threshold_, s, s_near);
-		State s_test;
-		double t_new;
-		const bool ok = direction == FORWARD
-			? isValidStateActionPair(s_near, a_test, terrain, s_test, t_new, state_action_pair_check_adaptive_step_size_flag_)
-			: isValidStateActionPairReverse(s_near, a_test, terrain, s_test, t_new, state_action_pair_check_adaptive_step_size_flag_);
-		if (!ok) continue;
-		if (stateDistance(s_test, s) < best_so_far) { s_new = s_test; a_new = a_test; return true; }
-		return false;  // the first valid action decides
-	}
-	return false;
+	int found = 0;
+	const std::uint64_t idx0 = (cell_++) * (std::uint64_t) k_candidates_;
+	const double dir_thresh = action_direction_sampling_flag_ ? action_direction_sampling_probability_threshold_ : -1.0;
+	check(gbp_new_config(terrain.handle(), s.data(), s_near.data(), direction, k_candidates_, best_of_k_ ? 1 : 0,
+						 state_action_pair_check_adaptive_step_size_flag_ ? 1 : 0, dir_thresh, seed_, stream_, idx0, &found, s_new.data(), a_new.data(),
+						 nullptr),
+		  "newConfig");
+	return found != 0;
 }
 
 int RRTClass::extend(PlannerClass &T, State s, FastTerrainMap &terrain, int direction) {  // rrt.cpp:77-102
@@ -303,8 +289,13 @@ void RRTConnectClass::buildAnytime(FastTerrainMap &terrain, State s_start, State
 	const int R = parallel_attempts_, cap = 256;
 	// anytime use of the batch planner: all attempts work on the same query, the round ends once 8 of them have solved
 	// (the 8 shortest raw paths are shortcut below)
+	// the fork's options travel with the batch: directional state / action sampling and the yaw-aware cost run inside the
+	// device planner exactly as the setters configured them (rrt_connect.cpp:246-251, rrt.cpp:34, rrt_connect.cpp:270-274)
 	gbp_plan_params P = {k_candidates_, best_of_k_ ? 1 : 0, iterations_per_attempt_, vertices_per_tree_,
-						 state_action_pair_check_adaptive_step_size_flag_ ? 1 : 0, star ? 1 : 0, 0, 8};
+						 state_action_pair_check_adaptive_step_size_flag_ ? 1 : 0, star ? 1 : 0, 0, 8,
+						 state_direction_sampling_flag_ ? 1 : 0, state_direction_sampling_speed_direction_flag_ ? 1 : 0,
+						 action_direction_sampling_flag_ ? 1 : 0, cost_add_yaw_flag_ ? 1 : 0, state_direction_sampling_probability_threshold_,
+						 action_direction_sampling_probability_threshold_, cost_add_yaw_length_weight_, cost_add_yaw_yaw_weight_};
 	std::vector<State> starts(R, s_start), goals(R, s_goal);
 	std::vector<gbp_plan_stats> stats(R);
 	std::vector<double> ps((size_t) R * cap * 8), pa((size_t) R * cap * 10);

@@ -273,15 +273,18 @@ int gbp_near(const gbp_tree *T, const double *query, double radius, int *ids, in
  * nearest neighbour, K actions from ACTION cells idx0..idx0+K-1 of (seed, stream), pair checks from
  * s_near in `direction`, selection (best_of_k 0: first valid in stream order decides, the reference's
  * behaviour with K = 6; 1: closest valid), acceptance iff closer to `target` than s_near, append.
- * One launch; everything stays on the device.  *status, *new_id, checks may be NULL. */
+ * action_direction_threshold: getRandomAction(surf_norm, direction, flag, threshold, s, s_near) (rrt.cpp:34,
+ * planning_utils.cpp:379-391) with s = target; a NEGATIVE value is flag = false (the draw p in [0, 1) is never <= it).
+ * One launch; everything stays on the device.  *status, *new_id, checks may be NULL.  A tree that is full when the
+ * accepted vertex is to be appended returns GBP_E_CAPACITY (the tree is unchanged), as gbp_connect does. */
 int gbp_extend(gbp_tree *T, const gbp_terrain *t, const double *target, int direction, int k_candidates,
-               int best_of_k, int adaptive, uint64_t seed, uint64_t stream, uint64_t idx0, int *status,
-               int *new_id, int64_t *pair_checks);
+               int best_of_k, int adaptive, double action_direction_threshold, uint64_t seed, uint64_t stream,
+               uint64_t idx0, int *status, int *new_id, int64_t *pair_checks);
 /* RRTClass::newConfig (rrt.cpp:20-70) from an explicit s_near (no tree): K candidates, selection and the
  * "closer than s_near" acceptance as in gbp_extend.  *found = 1 when s_new / a_new were written. */
 int gbp_new_config(const gbp_terrain *t, const double *target, const double *s_near, int direction, int k_candidates,
-                   int best_of_k, int adaptive, uint64_t seed, uint64_t stream, uint64_t idx0, int *found, double *s_new,
-                   double *a_new, int64_t *pair_checks);
+                   int best_of_k, int adaptive, double action_direction_threshold, uint64_t seed, uint64_t stream,
+                   uint64_t idx0, int *found, double *s_new, double *a_new, int64_t *pair_checks);
 /* RRTConnectClass::attemptConnect (rrt_connect.cpp:20-91), n independent (s_existing, s) pairs.  t_s may be
  * NULL (stance time = poseDistance / V_NOM, the 6-argument overload :85-91) or hold n explicit stance times
  * (the 7-argument overload :20-84). */
@@ -311,13 +314,22 @@ typedef struct {
 	int stop_after_solved; /* > 0: anytime use (many attempts at ONE query): once this many queries of the batch have
 	                          solved, the others stop at their next iteration and report solved = 0 with the work done
 	                          so far (which ones depends on timing).  0: every query runs to its own budget (reproducible) */
-} gbp_plan_params;
+	/* the fork's options, as RRTClass::set_* stores them (rrt.h:124-139, :186-199; all off in config/params.yaml:16-27) */
+	int state_direction_sampling;  /* randomState(terrain, flag, threshold, speed flag, s_from, s_to): rrt_connect.cpp:246-251, :281-286 */
+	int state_direction_speed;     /* state_direction_sampling_speed_direction_flag_ */
+	int action_direction_sampling; /* getRandomAction(surf_norm, direction, flag, threshold, s, s_near): rrt.cpp:34, :49 */
+	int cost_add_yaw;              /* path_cost = length * w_length + yaw * w_yaw (rrt_connect.cpp:270-274, :196, :212) */
+	double state_direction_threshold, action_direction_threshold;
+	double cost_length_weight, cost_yaw_weight;
+} gbp_plan_params; /* 80 bytes */
 
 typedef struct {
 	int solved, iters, nv_a, nv_b, path_states, pad;
 	double path_length, path_yaw, path_duration;
 	int64_t pair_checks, nn_queries;
-} gbp_plan_stats; /* 64 bytes; what the final NCCL gather carries per query */
+	double path_cost; /* path_cost_ as the reference leaves it (rrt_connect.cpp:270-274, or postProcessPath's sum :196, :212) */
+	int64_t reserved;
+} gbp_plan_stats; /* 80 bytes; what the final NCCL gather carries per query */
 
 int gbp_plan_batch(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed,
                    uint64_t query0, const gbp_plan_params *params, gbp_plan_stats *stats, double *path_states,
@@ -325,6 +337,14 @@ int gbp_plan_batch(const gbp_terrain *t, int64_t nq, const double *starts, const
 int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed,
                        uint64_t query0, const gbp_plan_params *params, gbp_plan_stats *stats, double *path_states,
                        double *path_actions, int path_cap, void *stream);
+/* gbp_plan_batch that also returns every query's two trees as they stand when its search ends (inspection and parity
+ * tests: the trees are compared vertex by vertex with the reference's): row ((q * 2 + w) * tree_cap + i) of tree_states
+ * [8], tree_actions [10], tree_parent, tree_g, tree_yaw holds vertex i of tree w (0 start side, 1 goal side) of query q;
+ * stats[q].nv_a / nv_b give the vertex counts.  HOST pointers. */
+int gbp_plan_batch_trees(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed,
+                         uint64_t query0, const gbp_plan_params *params, gbp_plan_stats *stats, double *path_states,
+                         double *path_actions, int path_cap, int tree_cap, double *tree_states, double *tree_actions,
+                         int *tree_parent, double *tree_g, double *tree_yaw);
 
 #ifdef __cplusplus
 }

@@ -19,9 +19,9 @@ struct GlobalBodyPlannerParams {  // rosparam names: global_body_planner/* and s
 	bool cost_add_yaw_flag = false;          // :181-183
 	double cost_add_yaw_length_weight = 1.0, cost_add_yaw_yaw_weight = 1.0;
 	bool action_direction_sampling_flag = false;  // :189-190
-	double action_direction_sampling_probability_threshold = 0.15;
+	double action_direction_sampling_probability_threshold = 0.1;   // config/params.yaml:27 (the node's fallback without a rosparam is 0.15, :201)
 	bool state_direction_sampling_flag = false;   // :196-198
-	double state_direction_sampling_probability_threshold = 0.15;
+	double state_direction_sampling_probability_threshold = 0.05;   // config/params.yaml:23 (fallback 0.15, :203)
 	bool state_direction_sampling_speed_direction_flag = false;
 	double start_position_x = 0, start_position_y = 0, start_yaw = 0;  // :214-218
 	double goal_position_x = 0, goal_position_y = 0, goal_yaw = 0;     // :219-223

@@ -34,8 +34,9 @@ def test_exports_every_declared_symbol(L):
 
 def test_struct_layout_matches_header():
     import global_body_planner_b200 as gbp
-    assert gbp.PLAN_STATS_DTYPE.itemsize == 64
-    assert ctypes.sizeof(gbp.PlanParams) == 32
+    assert gbp.PLAN_STATS_DTYPE.itemsize == 80
+    assert ctypes.sizeof(gbp.PlanParams) == 80
+    assert ctypes.sizeof(gbp.SvParams) == 144 and ctypes.sizeof(gbp.SvResult) == 64
 
 
 def test_argument_validation_without_device(L):

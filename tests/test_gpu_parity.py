@@ -338,3 +338,35 @@ def test_nearest_many_queries_tiled(gbp, dev):
     assert (gi == d_all.argmin(1)).all() or (gd == d_all.min(1)).all()   # ties resolved to the lowest id
     hit = np.nonzero((q == verts[3]).all(1))[0]
     assert len(hit) >= 1 and (gi[hit] == 3).all()
+
+
+def test_full_tree_is_a_capacity_error_not_trapped(gbp, dev):
+    """gbp_extend / gbp_connect on a tree without room for the accepted vertex return GBP_E_CAPACITY and leave the tree
+    untouched (TRAPPED means the reference's newConfig / attemptConnect rejected, rrt.cpp:55-66, rrt_connect.cpp:107)"""
+    t, o, T, G, name = dev
+    s = G["nn_verts"]
+    v, _ = o.valid_states(s, po.STANCE)
+    s = s[v == 1]
+    hit = None
+    for i in range(min(len(s) - 1, 40)):  # a (root, target) pair whose extend succeeds on a roomy tree
+        roomy = gbp.Tree(4, s[i])
+        for j in range(i + 1, min(len(s), i + 20)):
+            st, nid, _ = roomy.extend(t, s[j], gbp.FORWARD, 2048, 1, 9, 4, 0)
+            if st != gbp.TRAPPED:
+                hit = (i, j)
+                break
+        if hit:
+            break
+    if hit is None:
+        pytest.skip("no successful extend among the sampled pairs on this map")
+    full = gbp.Tree(1, s[hit[0]])
+    with pytest.raises(gbp.GbpError, match="-3"):
+        full.extend(t, s[hit[1]], gbp.FORWARD, 2048, 1, 9, 4, 0)
+    assert full.size() == 1
+    # connect: a target right next to the root always connects
+    near = s[hit[0]].copy(); near[0] += 0.1
+    st, _ = gbp.Tree(4, s[hit[0]]).connect(t, near, gbp.FORWARD)
+    if st != gbp.TRAPPED:
+        with pytest.raises(gbp.GbpError, match="-3"):
+            full.connect(t, near, gbp.FORWARD)
+        assert full.size() == 1
