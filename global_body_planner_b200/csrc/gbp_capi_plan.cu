@@ -113,7 +113,9 @@ static int plan_dev(const gbp_terrain *t, int64_t nq, const double *starts, cons
 					const PlanTreeDump &dump, cudaStream_t st) {
 	keep_pool();
 	std::string err;
-	const int rc = plan_batch_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, st, dump, err);
+	const int rc = plan_step_applies(*p, nq)
+		? plan_step_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, st, dump, err)
+		: plan_batch_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, st, dump, err);
 	if (rc) return fail(rc, err);
 	return GBP_OK;
 }

@@ -11,6 +11,8 @@
 //   postProcessPath   : lane per later path state probes attemptConnect, farthest REACHED wins
 // Tree arenas live in HBM, one slot per resident warp, reused across the queries a warp processes.
 #pragma once
+#include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "gbp_kernels.cuh"
@@ -488,6 +490,74 @@ __device__ int warp_post_process(const TerrainView &Tv, double *ps, double *pa, 
 	return m;
 }
 
+// End of a query: statistics (rrt_connect.cpp:269-270, :463-466), the stitched path (:381-401), postProcessPath, and the
+// optional copies of the path and of both trees.  Shared by the megakernel and the stepped planner; all lanes call it.
+template <typename M>
+__device__ __forceinline__ void plan_finish(const TerrainView &Tv, const gbp_plan_params &P, const PlanArena &A, int64_t scratch_slot, const PlanTree &Ta,
+											 const PlanTree &Tb, int na, int nb, bool solved, int it, long long pair_checks, long long nn_queries, int64_t qi,
+											 gbp_plan_stats *__restrict__ stats, double *__restrict__ path_states, double *__restrict__ path_actions,
+											 int path_cap, const PlanTreeDump &dump, int lane) {
+		gbp_plan_stats st;
+	st.solved = solved ? 1 : 0; st.iters = it; st.nv_a = na; st.nv_b = nb; st.path_states = 0; st.pad = 0;
+	st.path_length = 0; st.path_yaw = 0; st.path_duration = 0; st.pair_checks = pair_checks; st.nn_queries = nn_queries;
+	st.path_cost = 0; st.reserved = 0;
+	if (solved) {
+		double *ps = A.pstate + (size_t) scratch_slot * 2 * A.cap * 8, *pa = A.paction + (size_t) scratch_slot * 2 * A.cap * 10;
+		int la = 0, lb = 0;
+		for (int i = na - 1; i != -1; i = Ta.t.parent[i]) ++la;
+		for (int i = nb - 1; i != -1; i = Tb.t.parent[i]) ++lb;
+		int total = la + lb - 1;
+		if (lane == 0) {  // stitch: start .. shared state (tree A), then tree B back to the goal
+			int k = la - 1;
+			for (int i = na - 1; i != -1; i = Ta.t.parent[i], --k) {
+				for (int d = 0; d < 8; ++d) ps[8 * (size_t) k + d] = Ta.t.v[(size_t) d * Ta.t.cap + i];
+				if (k > 0) for (int d = 0; d < 10; ++d) pa[10 * (size_t) (k - 1) + d] = Ta.t.act[(size_t) d * Ta.t.cap + i];
+			}
+			k = la - 1;  // Tb.last duplicates the shared state: its ACTION is kept, its STATE is dropped (:388-395)
+			for (int i = nb - 1; Tb.t.parent[i] != -1; i = Tb.t.parent[i], ++k) {
+				for (int d = 0; d < 10; ++d) pa[10 * (size_t) k + d] = Tb.t.act[(size_t) d * Tb.t.cap + i];
+				for (int d = 0; d < 8; ++d) ps[8 * (size_t) (k + 1) + d] = Tb.t.v[(size_t) d * Tb.t.cap + Tb.t.parent[i]];
+			}
+		}
+		__syncwarp();
+		st.path_length = Ta.t.g[na - 1] + Tb.t.g[nb - 1];
+		st.path_yaw = Ta.t.y[na - 1] + Tb.t.y[nb - 1];
+		st.path_cost = P.cost_add_yaw ? st.path_length * P.cost_length_weight + st.path_yaw * P.cost_yaw_weight : st.path_length;  // :270-274
+		if (P.post_process) {
+			double s3[3];
+			total = warp_post_process<M>(Tv, ps, pa, total, P.adaptive != 0, lane, P, s3);
+			st.path_length = s3[0];
+			st.path_yaw = s3[1];
+			st.path_cost = s3[2];
+		}
+		st.path_states = total;
+		double dur = 0;
+		for (int i = 0; i + 1 < total; ++i) dur += pa[10 * (size_t) i + 6] + pa[10 * (size_t) i + 7];
+		st.path_duration = dur;
+		if (path_states && path_actions) {
+			for (int i = lane; i < total && i < path_cap; i += 32)
+				for (int d = 0; d < 8; ++d) path_states[((size_t) qi * path_cap + i) * 8 + d] = ps[8 * (size_t) i + d];
+			for (int i = lane; i + 1 < total && i < path_cap; i += 32)
+				for (int d = 0; d < 10; ++d) path_actions[((size_t) qi * path_cap + i) * 10 + d] = pa[10 * (size_t) i + d];
+		}
+	}
+	if (dump.states) {  // both trees, vertex by vertex
+		for (int w = 0; w < 2; ++w) {
+			const PlanTree &Tw = w == 0 ? Ta : Tb;
+			const int nw = w == 0 ? na : nb;
+			const size_t base = ((size_t) qi * 2 + w) * dump.cap;
+			for (int i = lane; i < nw && i < dump.cap; i += 32) {
+				for (int d = 0; d < 8; ++d) dump.states[(base + i) * 8 + d] = Tw.t.v[(size_t) d * Tw.t.cap + i];
+				for (int d = 0; d < 10; ++d) dump.actions[(base + i) * 10 + d] = Tw.t.act[(size_t) d * Tw.t.cap + i];
+				dump.parent[base + i] = Tw.t.parent[i];
+				dump.g[base + i] = Tw.t.g[i];
+				dump.y[base + i] = Tw.t.y[i];
+			}
+		}
+	}
+	if (lane == 0) stats[qi] = st;
+}
+
 template <typename M, bool STAR, bool WIDE = false>
 // Occupancy over registers: the kernel is 21 k SASS instructions and its warps sit at unrelated program counters, so
 // at 255 registers (8 warps / SM) ncu shows 8.3 of the 12.2 cycles between two issues of a warp waiting for
@@ -571,69 +641,8 @@ __global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_plan_batch(TerrainV
 				if (warp_connect<M>(Tv, Ty, ny, s_new, dir_con, P, lane, pair_checks) == GBP_REACHED) solved = true;
 			}
 		}
-		// statistics + path (rrt_connect.cpp:269-270, :381-401, :463-466)
-		gbp_plan_stats st;
-		st.solved = solved ? 1 : 0; st.iters = it; st.nv_a = na; st.nv_b = nb; st.path_states = 0; st.pad = 0;
-		st.path_length = 0; st.path_yaw = 0; st.path_duration = 0; st.pair_checks = pair_checks; st.nn_queries = nn_queries;
-		st.path_cost = 0; st.reserved = 0;
-		if (solved) {
-			double *ps = A.pstate + (size_t) slot * 2 * A.cap * 8, *pa = A.paction + (size_t) slot * 2 * A.cap * 10;
-			int la = 0, lb = 0;
-			for (int i = na - 1; i != -1; i = Ta.t.parent[i]) ++la;
-			for (int i = nb - 1; i != -1; i = Tb.t.parent[i]) ++lb;
-			int total = la + lb - 1;
-			if (lane == 0) {  // stitch: start .. shared state (tree A), then tree B back to the goal
-				int k = la - 1;
-				for (int i = na - 1; i != -1; i = Ta.t.parent[i], --k) {
-					for (int d = 0; d < 8; ++d) ps[8 * (size_t) k + d] = Ta.t.v[(size_t) d * Ta.t.cap + i];
-					if (k > 0) for (int d = 0; d < 10; ++d) pa[10 * (size_t) (k - 1) + d] = Ta.t.act[(size_t) d * Ta.t.cap + i];
-				}
-				k = la - 1;  // Tb.last duplicates the shared state: its ACTION is kept, its STATE is dropped (:388-395)
-				for (int i = nb - 1; Tb.t.parent[i] != -1; i = Tb.t.parent[i], ++k) {
-					for (int d = 0; d < 10; ++d) pa[10 * (size_t) k + d] = Tb.t.act[(size_t) d * Tb.t.cap + i];
-					for (int d = 0; d < 8; ++d) ps[8 * (size_t) (k + 1) + d] = Tb.t.v[(size_t) d * Tb.t.cap + Tb.t.parent[i]];
-				}
-			}
-			__syncwarp();
-			st.path_length = Ta.t.g[na - 1] + Tb.t.g[nb - 1];
-			st.path_yaw = Ta.t.y[na - 1] + Tb.t.y[nb - 1];
-			st.path_cost = P.cost_add_yaw ? st.path_length * P.cost_length_weight + st.path_yaw * P.cost_yaw_weight : st.path_length;  // :270-274
-			if (P.post_process) {
-				double s3[3];
-				total = warp_post_process<M>(Tv, ps, pa, total, P.adaptive != 0, lane, P, s3);
-				st.path_length = s3[0];
-				st.path_yaw = s3[1];
-				st.path_cost = s3[2];
-			}
-			st.path_states = total;
-			double dur = 0;
-			for (int i = 0; i + 1 < total; ++i) dur += pa[10 * (size_t) i + 6] + pa[10 * (size_t) i + 7];
-			st.path_duration = dur;
-			if (path_states && path_actions) {
-				for (int i = lane; i < total && i < path_cap; i += 32)
-					for (int d = 0; d < 8; ++d) path_states[((size_t) qi * path_cap + i) * 8 + d] = ps[8 * (size_t) i + d];
-				for (int i = lane; i + 1 < total && i < path_cap; i += 32)
-					for (int d = 0; d < 10; ++d) path_actions[((size_t) qi * path_cap + i) * 10 + d] = pa[10 * (size_t) i + d];
-			}
-		}
-		if (dump.states) {  // both trees, vertex by vertex
-			for (int w = 0; w < 2; ++w) {
-				const PlanTree &Tw = w == 0 ? Ta : Tb;
-				const int nw = w == 0 ? na : nb;
-				const size_t base = ((size_t) qi * 2 + w) * dump.cap;
-				for (int i = lane; i < nw && i < dump.cap; i += 32) {
-					for (int d = 0; d < 8; ++d) dump.states[(base + i) * 8 + d] = Tw.t.v[(size_t) d * Tw.t.cap + i];
-					for (int d = 0; d < 10; ++d) dump.actions[(base + i) * 10 + d] = Tw.t.act[(size_t) d * Tw.t.cap + i];
-					dump.parent[base + i] = Tw.t.parent[i];
-					dump.g[base + i] = Tw.t.g[i];
-					dump.y[base + i] = Tw.t.y[i];
-				}
-			}
-		}
-		if (lane == 0) {
-			stats[qi] = st;
-			if (solved && P.stop_after_solved > 0) atomicAdd((int *) solved_count, 1);
-		}
+		plan_finish<M>(Tv, P, A, slot, Ta, Tb, na, nb, solved, it, pair_checks, nn_queries, qi, stats, path_states, path_actions, path_cap, dump, lane);
+		if (lane == 0 && solved && P.stop_after_solved > 0) atomicAdd((int *) solved_count, 1);
 		__syncwarp();
 	}
 }
@@ -693,6 +702,190 @@ inline int plan_batch_launch(const TerrainView &Tv, int64_t nq, const double *st
 	cudaFreeAsync(mem, st);  // stream-ordered: released after the kernel
 	if (e != cudaSuccess) { err = std::string("k_plan_batch: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
 	return GBP_OK;
+}
+
+// ------------------------------------------------------------------ the stepped planner
+// The same searches, split by role instead of run as one megakernel: ONE launch per half-iteration of runRRTConnect
+// (rrt_connect.cpp:246-279 / :281-312) advances every query of the batch by that half — extend towards the query's random
+// state and, when the tree grew, connect from the other tree — with the trees and a few words of per-query state in HBM
+// between launches, and one launch per 16 iterations draws and validity-checks the next 32 STATE cells of every query.
+// Why: k_plan_batch is a 21 k-instruction kernel whose warps sit at unrelated program counters (7.3 of 15 stall cycles per
+// issue are instruction fetch, profiles/r1c_planner_ncu_summary.csv) and whose 80-register cap spills 2.7 KB per thread
+// (23.5 GB of DRAM writes per 98 ms launch).  Here every resident warp of the chip runs the same ~3 k instructions at
+// the same time and each kernel gets the registers it needs.  Arithmetic, Philox cells and the order of tree updates
+// per query are the megakernel's, so trees, statistics and paths are bit-identical (tests/test_gpu_planner.py runs both).
+// Used for large batches of plain RRT-Connect queries at the fixed step (the launcher decides); everything else — RRT*,
+// adaptive step, directional state sampling, K > 32, anytime rounds — stays on the megakernel.
+struct StepState {
+	int *na, *nb;              // [Q] vertex counts (the trees' `n` words)
+	int *status;               // [Q] 0 running, 1 solved, 2 a tree is full
+	int *iters;                // [Q] started iterations when the query stopped (max_iters while running)
+	long long *pair_checks, *nn_queries;  // [Q]
+	double *rs;                // [Q][32][8] the 32 random states of the current batch of STATE cells
+	unsigned *rs_valid;        // [Q] isValidState(STANCE) of those 32 states
+};
+
+template <typename M>
+__global__ void __launch_bounds__(128) k_step_init(StepState S, PlanArena A, int64_t Q, const double *__restrict__ starts,
+													const double *__restrict__ goals, int max_iters) {
+	const int64_t q = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (q >= Q) return;
+	PlanTree Ta = arena_tree(A, (int) q, 0, S.na + q), Tb = arena_tree(A, (int) q, 1, S.nb + q);
+	double s[8], g[8];
+#pragma unroll
+	for (int d = 0; d < 8; ++d) { s[d] = starts[8 * q + d]; g[d] = goals[8 * q + d]; }
+	plan_tree_init(Ta, s);
+	plan_tree_init(Tb, g);
+	S.status[q] = 0; S.iters[q] = max_iters; S.pair_checks[q] = 0; S.nn_queries[q] = 0; S.rs_valid[q] = 0;
+}
+
+// STATE cells base .. base + 31 of every running query: lane L draws cell base + L and checks it (their validity does not
+// depend on the trees)
+template <typename M>
+__global__ void __launch_bounds__(128) k_step_sample(TerrainView Tv, StepState S, int64_t Q, uint64_t seed, uint64_t query0, uint64_t cell_base) {
+	const int lane = threadIdx.x & 31;
+	const int64_t q = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+	if (q >= Q || S.status[q] != 0) return;
+	double rs[8];
+	sample_state<M>(Tv, seed, query0 + (uint64_t) q, cell_base + (uint64_t) lane, false, 0.0, false, nullptr, nullptr, rs);
+	Counters c = {0, 0, 0, 0};
+	const unsigned valid = __ballot_sync(FULL, is_valid_state_auto<M>(Tv, pose6(rs), GBP_STANCE, c));
+	double2 *o = reinterpret_cast<double2 *>(S.rs + ((size_t) q * 32 + lane) * 8);
+#pragma unroll
+	for (int d = 0; d < 4; ++d) o[d] = make_double2(rs[2 * d], rs[2 * d + 1]);
+	if (lane == 0) S.rs_valid[q] = valid;
+}
+
+// one half-iteration of every running query: warp per query
+template <typename M>
+__global__ void __launch_bounds__(128) k_step_half(TerrainView Tv, StepState S, PlanArena A, int64_t Q, uint64_t seed, uint64_t query0,
+													gbp_plan_params P, int it, int half) {
+	const int lane = threadIdx.x & 31;
+	const int64_t q = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+	if (q >= Q || S.status[q] != 0) return;
+	int na = S.na[q], nb = S.nb[q];
+	int &nx = half == 0 ? na : nb, &ny = half == 0 ? nb : na;
+	if (nx >= A.cap || ny >= A.cap) {  // a tree is full at the start of a half: the query stops unsolved (as the megakernel)
+		if (lane == 0) { S.status[q] = 2; S.iters[q] = it + 1; }
+		return;
+	}
+	const uint64_t cell = 2 * (uint64_t) it + (uint64_t) half;
+	const int src = (int) (cell & 31ull);
+	if (!((S.rs_valid[q] >> src) & 1u)) return;  // rrt_connect.cpp:254
+	double s_rand[8];
+	{
+		const double2 *r = reinterpret_cast<const double2 *>(S.rs + ((size_t) q * 32 + src) * 8);
+#pragma unroll
+		for (int d = 0; d < 4; ++d) { const double2 v = r[d]; s_rand[2 * d] = v.x; s_rand[2 * d + 1] = v.y; }
+	}
+	PlanTree Ta = arena_tree(A, (int) q, 0, S.na + q), Tb = arena_tree(A, (int) q, 1, S.nb + q);
+	PlanTree &Tx = half == 0 ? Ta : Tb, &Ty = half == 0 ? Tb : Ta;
+	const int dir_ext = half == 0 ? GBP_FORWARD : GBP_REVERSE, dir_con = half == 0 ? GBP_REVERSE : GBP_FORWARD;
+	const GroupMap gm = make_group_map(P.k_candidates, lane);
+	long long pair_checks = 0, nn_queries = 1;
+	bool solved = false;
+	if (warp_extend<M, false>(Tv, Tx, nx, s_rand, dir_ext, seed, query0 + (uint64_t) q, cell, P, gm, lane, pair_checks) != GBP_TRAPPED) {
+		double s_new[8];
+		tree_get(Tx.t, nx - 1, s_new);
+		++nn_queries;
+		solved = warp_connect<M>(Tv, Ty, ny, s_new, dir_con, P, lane, pair_checks) == GBP_REACHED;
+	}
+	if (lane == 0) {
+		S.pair_checks[q] += pair_checks;
+		S.nn_queries[q] += nn_queries;
+		if (solved) { S.status[q] = 1; S.iters[q] = it + 1; }
+	}
+}
+
+// statistics, stitched paths, postProcessPath: warps pull queries from a counter (path scratch per resident warp)
+template <typename M>
+__global__ void __launch_bounds__(128) k_step_finish(TerrainView Tv, StepState S, PlanArena A, PlanArena scratch, int64_t Q, gbp_plan_params P,
+													  unsigned long long *__restrict__ next_query, gbp_plan_stats *__restrict__ stats,
+													  double *__restrict__ path_states, double *__restrict__ path_actions, int path_cap, PlanTreeDump dump) {
+	const int lane = threadIdx.x & 31;
+	const int64_t slot = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+	while (true) {
+		unsigned long long grabbed = 0;
+		if (lane == 0) grabbed = atomicAdd(next_query, 1ull);
+		const int64_t q = (int64_t) __shfl_sync(FULL, grabbed, 0);
+		if (q >= Q) break;
+		PlanTree Ta = arena_tree(A, (int) q, 0, S.na + q), Tb = arena_tree(A, (int) q, 1, S.nb + q);
+		plan_finish<M>(Tv, P, scratch, slot, Ta, Tb, S.na[q], S.nb[q], S.status[q] == 1, S.iters[q], S.pair_checks[q], S.nn_queries[q], q, stats,
+					   path_states, path_actions, path_cap, dump, lane);
+		__syncwarp();
+	}
+}
+
+inline bool plan_step_applies(const gbp_plan_params &P, int64_t nq) {
+	const char *mode = getenv("GBP_PLAN_MODE");  // "mega" / "step": force one form (A/B measurements, tests); results are identical
+	if (P.rrt_star || P.adaptive || P.state_direction_sampling || P.stop_after_solved > 0 || P.k_candidates > 32) return false;
+	if (mode && !strcmp(mode, "mega")) return false;
+	if (mode && !strcmp(mode, "step")) return true;
+	return nq >= 16384;
+}
+
+template <typename M>
+inline int plan_step_launch_kind(const TerrainView &Tv, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+								 const gbp_plan_params &P, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap,
+								 cudaStream_t st, const PlanTreeDump &dump, std::string &err) {
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const size_t cap = (size_t) P.max_vertices, Q = (size_t) nq, per = Q * 2 * cap;
+	const int64_t fin_slots = (int64_t) sms * 4 * 4;
+	const size_t n_doubles = per * (8 + 10 + 1 + 1) + Q * 32 * 8 + (size_t) fin_slots * 2 * cap * 18;
+	const size_t n_ll = Q * 2 + 1;
+	const size_t n_ints = per * 3 + Q * 5;
+	const size_t need = n_doubles * 8 + n_ll * 8 + n_ints * 4;
+	void *mem = nullptr;
+	cudaError_t e;
+	if ((e = cudaMallocAsync(&mem, need, st)) != cudaSuccess) { err = std::string("stepped planner arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
+	PlanArena A = {}, Sc = {};
+	StepState S;
+	A.cap = Sc.cap = P.max_vertices;
+	double *dp = (double *) mem;
+	A.v = dp; dp += per * 8;
+	A.act = dp; dp += per * 10;
+	A.g = dp; dp += per;
+	A.y = dp; dp += per;
+	S.rs = dp; dp += Q * 32 * 8;
+	Sc.pstate = dp; dp += (size_t) fin_slots * 2 * cap * 8;
+	Sc.paction = dp; dp += (size_t) fin_slots * 2 * cap * 10;
+	long long *lp = (long long *) dp;
+	S.pair_checks = lp; lp += Q;
+	S.nn_queries = lp; lp += Q;
+	unsigned long long *next_query = (unsigned long long *) lp; lp += 1;
+	int *ip = (int *) lp;
+	A.parent = ip; ip += per;
+	A.child = ip; ip += per;
+	A.sibling = ip; ip += per;
+	S.na = ip; ip += Q;
+	S.nb = ip; ip += Q;
+	S.status = ip; ip += Q;
+	S.iters = ip; ip += Q;
+	S.rs_valid = (unsigned *) ip; ip += Q;
+	const unsigned warp_blocks = (unsigned) ((Q + 3) / 4);
+	k_step_init<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(S, A, nq, starts, goals, P.max_iters);
+	for (int it = 0; it < P.max_iters; ++it) {
+		if ((it & 15) == 0) k_step_sample<M><<<warp_blocks, 128, 0, st>>>(Tv, S, nq, seed, query0, 2 * (uint64_t) it);
+		k_step_half<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, nq, seed, query0, P, it, 0);
+		k_step_half<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, nq, seed, query0, P, it, 1);
+	}
+	cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st);
+	const int64_t fin_warps = (int64_t) Q < fin_slots ? (int64_t) ((Q + 3) / 4 * 4) : fin_slots;
+	k_step_finish<M><<<(unsigned) (fin_warps / 4), 128, 0, st>>>(Tv, S, A, Sc, nq, P, next_query, stats, path_states, path_actions, path_cap, dump);
+	e = cudaGetLastError();
+	cudaFreeAsync(mem, st);
+	if (e != cudaSuccess) { err = std::string("stepped planner: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
+	return GBP_OK;
+}
+inline int plan_step_launch(const TerrainView &Tv, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+							const gbp_plan_params &P, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap,
+							cudaStream_t st, const PlanTreeDump &dump, std::string &err) {
+#define GBP_STEP_(M) return plan_step_launch_kind<M>(Tv, nq, starts, goals, seed, query0, P, stats, path_states, path_actions, path_cap, st, dump, err)
+	if (Tv.cell_f32) { if (Tv.uniform) GBP_STEP_(MapF32U); else GBP_STEP_(MapF32N); }
+	else { if (Tv.uniform) GBP_STEP_(MapF64U); else GBP_STEP_(MapF64N); }
+#undef GBP_STEP_
 }
 
 // ------------------------------------------------------------------ extend through the host call (rrt.cpp:20-102)
