@@ -285,7 +285,7 @@ def main():
     # the narrow wire format of gbp_sample_validate: row numbers into the resident state table + direction bytes in,
     # verdict bits + the rows of the valid candidates out; actions = ACTION cells 0..n-1 of (seed, stream_id + 1), i.e.
     # exactly the `actions` array above, sampled inside the kernel
-    sv = gbp.sv_params(seed, stream_id + 1, 0)
+    sv = gbp.sv_params(seed, stream_id + 1, 0, states_valid=True)  # the table rows ARE valid STANCE states (device_batch filtered them)
     idx = torch.arange(n, dtype=torch.int32, device=dev)
     bits = torch.empty(nw, dtype=torch.int32, device=dev)
     cap = max(n // 64, 1024)

@@ -31,7 +31,8 @@ class SvParams(C.Structure):
     """gbp_sv_params (include/gbp_b200.h): the per-call part of a sample + validate batch."""
     _fields_ = [("seed", C.c_uint64), ("stream", C.c_uint64), ("idx0", C.c_uint64), ("normal", C.c_double * 3),
                 ("adaptive", C.c_int), ("direction0", C.c_int), ("action_direction_sampling", C.c_int),
-                ("action_direction_threshold", C.c_double), ("target", C.c_double * 8), ("row0", C.c_int64)]
+                ("action_direction_threshold", C.c_double), ("target", C.c_double * 8), ("row0", C.c_int64),
+                ("start_states_valid", C.c_int), ("reserved", C.c_int)]
 
 
 class SvResult(C.Structure):
@@ -39,8 +40,9 @@ class SvResult(C.Structure):
                 ("oog", C.c_int64), ("near", C.c_int64), ("reserved", C.c_int64 * 2)]
 
 
-def sv_params(seed, stream, idx0, normal=(0.0, 0.0, 1.0), adaptive=False, direction0=0, target=None, thresh=0.0, row0=0):
+def sv_params(seed, stream, idx0, normal=(0.0, 0.0, 1.0), adaptive=False, direction0=0, target=None, thresh=0.0, row0=0, states_valid=False):
     p = SvParams()
+    p.start_states_valid = int(states_valid)
     p.seed, p.stream, p.idx0 = seed, stream, idx0
     p.normal[:] = [float(v) for v in normal]
     p.adaptive, p.direction0, p.row0 = int(adaptive), int(direction0), int(row0)
@@ -110,6 +112,20 @@ def propagate(kind, states, actions, t):
     s = _f64(states, (-1, 8)); n = len(s); t = _f64(np.broadcast_to(t, (n,))); out = np.zeros_like(s)
     a = None if actions is None else _f64(actions, (-1, 10))
     _check(lib().gbp_propagate(kind, C.c_int64(n), _p(s), _p(a), _p(t), _p(out)))
+    return out
+
+
+def rotate_grf(normals, forces):
+    """rotate_grf, planning_utils.cpp:198-231 (n triples)."""
+    nn, f = _f64(normals, (-1, 3)), _f64(forces, (-1, 3)); out = np.zeros_like(f)
+    _check(lib().gbp_rotate_grf(C.c_int64(len(f)), _p(nn), _p(f), _p(out)))
+    return out
+
+
+def curvature(points6):
+    """calculateCurvature, planning_utils.cpp:884-899 (n sextuples x1 y1 x2 y2 x3 y3)."""
+    p = _f64(points6, (-1, 6)); out = np.zeros(len(p))
+    _check(lib().gbp_curvature(C.c_int64(len(p)), _p(p), _p(out)))
     return out
 
 

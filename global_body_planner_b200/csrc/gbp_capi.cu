@@ -411,6 +411,34 @@ int gbp_propagate(int kind, int64_t n, const double *states, const double *actio
 	CU(cudaStreamSynchronize(st));
 	return GBP_OK;
 }
+int gbp_rotate_grf(int64_t n, const double *normal3, const double *force3, double *out3) {
+	if (n < 0 || (n && (!normal3 || !force3 || !out3))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev dn(st), df(st), dout(st);
+	int rc;
+	if ((rc = upload(dn, normal3, 3 * n, st)) || (rc = upload(df, force3, 3 * n, st))) return rc;
+	CU(dout.alloc(3 * n * sizeof(double)));
+	k_rotate_grf<<<blocks_for(n, 256), 256, 0, st>>>(n, dn.as<double>(), df.as<double>(), dout.as<double>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(out3, dout.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
+int gbp_curvature(int64_t n, const double *points6, double *curvature) {
+	if (n < 0 || (n && (!points6 || !curvature))) return fail(GBP_E_INVALID, "bad arguments");
+	if (n == 0) return GBP_OK;
+	cudaStream_t st = lib_stream();
+	Dev dp(st), dout(st);
+	int rc;
+	if ((rc = upload(dp, points6, 6 * n, st))) return rc;
+	CU(dout.alloc(n * sizeof(double)));
+	k_curvature<<<blocks_for(n, 256), 256, 0, st>>>(n, dp.as<double>(), dout.as<double>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(curvature, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return GBP_OK;
+}
 int gbp_valid_actions(int64_t n, const double *actions, uint8_t *verdict) {
 	if (n < 0 || (n && (!actions || !verdict))) return fail(GBP_E_INVALID, "bad arguments");
 	if (n == 0) return GBP_OK;

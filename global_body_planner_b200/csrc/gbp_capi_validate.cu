@@ -225,6 +225,7 @@ static SvParams sv_device_params(const gbp_sv_params &p, const double *table, in
 	P.dir0 = p.direction0;
 	P.seed = p.seed; P.stream = p.stream; P.idx0 = p.idx0 + (uint64_t) off;
 	for (int k = 0; k < 3; ++k) P.normal[k] = p.normal[k];
+	P.states_valid = p.start_states_valid;
 	P.dir_sampling = p.action_direction_sampling;
 	P.dir_thresh = p.action_direction_threshold;
 	for (int k = 0; k < 8; ++k) P.target[k] = p.target[k];

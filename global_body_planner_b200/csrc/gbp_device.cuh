@@ -51,7 +51,14 @@ struct Counters {  // work under the reference's early-exit semantics, per candi
 // ---- Philox4x32-10 stream spec (see include/gbp_b200.h)
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
 											  uint32_t w[4]) {
-#pragma unroll
+	// GBP_PHILOX_UNROLL = 1 keeps the ten rounds a LOOP: the samplers run once per extend, so their code is fetched, not
+	// reused — 5 unrolled blocks are ~500 instructions (8 KB) of the planner's instruction-cache footprint
+#ifndef GBP_PHILOX_UNROLL
+#define GBP_PHILOX_UNROLL 10
+#endif
+#define GBP_PRAGMA_(x) _Pragma(#x)
+#define GBP_UNROLL_(n) GBP_PRAGMA_(unroll n)
+	GBP_UNROLL_(GBP_PHILOX_UNROLL)
 	for (int r = 0; r < 10; ++r) {
 		uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
 		uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;

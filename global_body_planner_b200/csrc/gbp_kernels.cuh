@@ -73,6 +73,33 @@ static __global__ void k_propagate(int kind, int64_t n, const double *__restrict
 	for (int d = 0; d < 8; ++d) out[8 * i + d] = o[d];
 }
 
+// rotate_grf (planning_utils.cpp:198-231) and calculateCurvature (:884-899), one thread per element
+static __global__ void k_rotate_grf(int64_t n, const double *__restrict__ normal, const double *__restrict__ force, double *__restrict__ out) {
+	const int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double nn[3] = {normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]}, f[3] = {force[3 * i], force[3 * i + 1], force[3 * i + 2]};
+	double R[9], o[3];
+	grf_rotation(nn, R);
+	mat3_apply(R, f, o);
+	out[3 * i] = o[0]; out[3 * i + 1] = o[1]; out[3 * i + 2] = o[2];
+}
+__device__ __forceinline__ double curvature3(double x1, double y1, double x2, double y2, double x3, double y3) {
+	if ((x1 == x2 && x2 == x3) || (y1 == y2 && y2 == y3)) return 0.0;
+	const double dis12 = sqrt((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
+	const double dis13 = sqrt((x1 - x3) * (x1 - x3) + (y1 - y3) * (y1 - y3));
+	const double dis23 = sqrt((x2 - x3) * (x2 - x3) + (y2 - y3) * (y2 - y3));
+	const double dis = dis12 * dis12 + dis23 * dis23 - dis13 * dis13;
+	const double cosA = dis / (2 * dis12 * dis23);
+	const double sinA = sqrt(1 - cosA * cosA);
+	double c = 0.5 * dis13 / sinA;
+	c = 1 / c;
+	return c;
+}
+static __global__ void k_curvature(int64_t n, const double *__restrict__ p, double *__restrict__ out) {
+	const int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	out[i] = curvature3(p[6 * i], p[6 * i + 1], p[6 * i + 2], p[6 * i + 3], p[6 * i + 4], p[6 * i + 5]);
+}
 static __global__ void k_valid_actions(int64_t n, const double *__restrict__ a, uint8_t *__restrict__ out) {
 	int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -709,17 +736,7 @@ static __global__ void k_max_curvature(int64_t n, const double *__restrict__ sta
 	if (i + 2 >= n) return;
 	const double x1 = states[8 * i], y1 = states[8 * i + 1], x2 = states[8 * (i + 1)], y2 = states[8 * (i + 1) + 1],
 				 x3 = states[8 * (i + 2)], y3 = states[8 * (i + 2) + 1];
-	double c = 0.0;
-	if (!((x1 == x2 && x2 == x3) || (y1 == y2 && y2 == y3))) {
-		const double dis12 = sqrt((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
-		const double dis13 = sqrt((x1 - x3) * (x1 - x3) + (y1 - y3) * (y1 - y3));
-		const double dis23 = sqrt((x2 - x3) * (x2 - x3) + (y2 - y3) * (y2 - y3));
-		const double dis = dis12 * dis12 + dis23 * dis23 - dis13 * dis13;
-		const double cosA = dis / (2 * dis12 * dis23);
-		const double sinA = sqrt(1 - cosA * cosA);
-		c = 0.5 * dis13 / sinA;
-		c = 1 / c;
-	}
+	const double c = curvature3(x1, y1, x2, y2, x3, y3);
 	if (c > 0.0) atomicMax(max_bits, (unsigned long long) __double_as_longlong(c));
 }
 

@@ -757,8 +757,11 @@ __global__ void __launch_bounds__(128) k_step_sample(TerrainView Tv, StepState S
 }
 
 // one half-iteration of every running query: warp per query
+#ifndef GBP_STEP_MINBLOCKS
+#define GBP_STEP_MINBLOCKS 4
+#endif
 template <typename M>
-__global__ void __launch_bounds__(128) k_step_half(TerrainView Tv, StepState S, PlanArena A, int64_t Q, uint64_t seed, uint64_t query0,
+__global__ void __launch_bounds__(128, GBP_STEP_MINBLOCKS) k_step_half(TerrainView Tv, StepState S, PlanArena A, int64_t Q, uint64_t seed, uint64_t query0,
 													gbp_plan_params P, int it, int half) {
 	const int lane = threadIdx.x & 31;
 	const int64_t q = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;

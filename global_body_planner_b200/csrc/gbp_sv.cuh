@@ -33,6 +33,7 @@ struct SvParams {
 	int dir0;
 	uint64_t seed, stream, idx0;
 	double normal[3];        // rrt.cpp:25: one surface normal per newConfig
+	int states_valid;        // the caller's promise that every table row is a valid STANCE state (tree vertices are): see below
 	int dir_sampling;        // getRandomAction(..., flag, threshold, s, s_near) (planning_utils.cpp:379-391)
 	double dir_thresh;
 	double target[8];        // `s` of newConfig (directional sampling only)
@@ -131,6 +132,15 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_sv(Terrai
 					for (int d = 0; d < 5; ++d) { const double2 v = pa[d]; a[2 * d] = v.x; a[2 * d + 1] = v.y; }
 					mine = wbase + rel;
 					walk_start(q, s, a, (int) ringD[wib][e], st);
+					// The reference's first sub-state is the start state itself (FORWARD: the stance sample at t = 0, :718-730;
+					// REVERSE: the flight sample at t = 0, :842-848, and a STANCE-valid state is FLIGHT-valid: the flight check only
+					// drops the leg-reach test).  For a row promised valid it is counted as the reference counts it (1 sub-state,
+					// 5 NaN probes, 9 lookups) and not evaluated again: every candidate of a tree vertex repeats that same check.
+					if (P.states_valid && q.t == 0 && (q.phase == PH_FWD_ST || q.phase == PH_REV_FL)) {
+						OutRecipe dummy;
+						q.c_.substates = 1; q.c_.nanprobes = 5; q.c_.lookups = 9;
+						(void) walk_advance<ADAPTIVE>(q, true, dummy, st);
+					}
 				}
 			}
 			next = min(filled, next + nidle);

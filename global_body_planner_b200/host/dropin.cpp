@@ -265,7 +265,35 @@ void printAction(Action a) {
 void printActionNewline(Action a) { printAction(a); std::cout << std::endl; }
 void printStateSequence(std::vector<State> state_sequence) { for (const State &s : state_sequence) printStateNewline(s); }
 void printActionSequence(std::vector<Action> action_sequence) { for (const Action &a : action_sequence) printActionNewline(a); }
-static void printStateXYZPYaw(const State &s) {
+void vectorToArray(State vec, double *new_array) {  // :5-8
+	for (size_t i = 0; i < vec.size(); i++) new_array[i] = vec.at(i);
+}
+void printVectorInt(std::vector<int> vec) {
+	std::cout << "{";
+	for (size_t i = 0; i < vec.size(); i++) std::cout << vec[i] << ", ";
+	std::cout << "\b\b}";
+}
+void printVectorIntNewline(std::vector<int> vec) { printVectorInt(vec); std::cout << std::endl; }
+void printInterpStateSequence(std::vector<State> state_sequence, std::vector<double> interp_t) {
+	for (size_t i = 0; i < state_sequence.size(); i++) { std::cout << interp_t[i] << "\t"; printStateNewline(state_sequence[i]); }
+}
+State interp(State q1, State q2, double x) {  // :97-103
+	State q_out;
+	for (size_t dim = 0; dim < q1.size(); dim++) q_out[dim] = (q2[dim] - q1[dim]) * x + q1[dim];
+	return q_out;
+}
+std::array<double, 3> rotate_grf(std::array<double, 3> surface_norm, std::array<double, 3> grf) {  // :198-231
+	std::array<double, 3> out;
+	check(gbp_rotate_grf(1, surface_norm.data(), grf.data(), out.data()), "rotate_grf");
+	return out;
+}
+double calculateCurvature(double x1, double y1, double x2, double y2, double x3, double y3) {  // :884-899
+	const double p[6] = {x1, y1, x2, y2, x3, y3};
+	double c = 0;
+	check(gbp_curvature(1, p, &c), "calculateCurvature");
+	return c;
+}
+void printStateXYZPYaw(const State &s) {
 	std::cout << "x: " << std::setw(7) << std::setprecision(3) << s[0] << " | y: " << std::setw(7) << std::setprecision(3) << s[1]
 			  << " | z: " << std::setw(7) << std::setprecision(3) << s[2] << " | p: " << std::setw(7) << std::setprecision(4) << s[6]
 			  << " | yaw: " << std::setw(6) << std::setprecision(3) << std::atan2(s[4], s[3]) << " |" << std::endl;

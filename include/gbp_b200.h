@@ -122,6 +122,10 @@ int gbp_surface_normal(const gbp_terrain *t, int64_t n, const double *x, const d
 /* applyStance (planning_utils.cpp:237-277), applyFlight (:282-306), applyStanceReverse (:324-370);
  * t has n entries.  kind: 0 stance, 1 flight (actions ignored, may be NULL), 2 stance-reverse. */
 int gbp_propagate(int kind, int64_t n, const double *states, const double *actions, const double *t, double *out);
+/* rotate_grf (planning_utils.cpp:198-231): the Rodrigues rotation taking +z to normal[i], applied to force[i]; n triples */
+int gbp_rotate_grf(int64_t n, const double *normal3, const double *force3, double *out3);
+/* calculateCurvature (planning_utils.cpp:884-899): three-point curvature of n (x1,y1,x2,y2,x3,y3) sextuples */
+int gbp_curvature(int64_t n, const double *points6, double *curvature);
 /* isValidAction (planning_utils.cpp:519-556) */
 int gbp_valid_actions(int64_t n, const double *actions, uint8_t *verdict);
 /* isValidState (planning_utils.cpp:562-635); phase has n entries */
@@ -187,6 +191,13 @@ typedef struct {
 	double action_direction_threshold; /*   (planning_utils.cpp:379-391): s_near = the candidate's start state, */
 	double target[8];                  /*   s = target (read only when the flag is set) */
 	int64_t row0;                      /* state_idx == NULL: candidate i starts from table row row0 + i */
+	int start_states_valid;            /* 1 = the caller promises that every table row is a valid STANCE state, as tree vertices
+	                                      are by construction (only end states of fully valid pair checks are ever added,
+	                                      rrt.cpp:87, rrt_connect.cpp:110; a root is checked once with gbp_valid_states).  The
+	                                      reference re-checks the start state as the first sub-state of EVERY candidate
+	                                      (planning_utils.cpp:718-730, :842-848); with the promise that check is counted
+	                                      (work counters stay the reference's) but not repeated.  0 = evaluate it. */
+	int reserved;
 } gbp_sv_params;
 
 typedef struct {

@@ -35,9 +35,16 @@ void interpStateActionPair(State s, Action a, double t0, double dt, std::vector<
 void getInterpPath(std::vector<State> state_sequence, std::vector<Action> action_sequence, double dt,
 				   std::vector<State> &interp_path, std::vector<double> &interp_t, std::vector<int> &interp_phase);
 
-double calculateMaxCurvature(std::vector<State> &body_plan);  // :884-909 (three-point curvature, maximum over the plan)
+State interp(State q1, State q2, double x);                   // :97-103
+double calculateCurvature(double x1, double y1, double x2, double y2, double x3, double y3);  // :884-899 (three-point curvature)
+double calculateMaxCurvature(std::vector<State> &body_plan);  // :900-909 (maximum over the plan)
 
-// ---- printing (:16-104)
+// ---- printing and conversion helpers (:5-94)
+void vectorToArray(State vec, double *new_array);
+void printVectorInt(std::vector<int> vec);
+void printVectorIntNewline(std::vector<int> vec);
+void printInterpStateSequence(std::vector<State> state_sequence, std::vector<double> interp_t);
+void printStateXYZPYaw(const State &s);
 void printState(State vec);
 void printStateNewline(State vec);
 void printAction(Action a);
@@ -53,6 +60,8 @@ double stateYawDistance(const State &q1, const State &q2);
 double stateDistance(const State &q1, const State &q2, bool cost_add_yaw_flag, double cost_add_yaw_length_weight,
 					 double cost_add_yaw_yaw_weight);
 bool isWithinBounds(State s1, State s2);
+// rotates a ground reaction force by the Rodrigues rotation taking +z to the surface normal (:198-231)
+std::array<double, 3> rotate_grf(std::array<double, 3> surface_norm, std::array<double, 3> grf);
 
 // ---- primitives (:237-370)
 State applyStance(State s, Action a, double t);

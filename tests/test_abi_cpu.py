@@ -36,7 +36,7 @@ def test_struct_layout_matches_header():
     import global_body_planner_b200 as gbp
     assert gbp.PLAN_STATS_DTYPE.itemsize == 80
     assert ctypes.sizeof(gbp.PlanParams) == 80
-    assert ctypes.sizeof(gbp.SvParams) == 144 and ctypes.sizeof(gbp.SvResult) == 64
+    assert ctypes.sizeof(gbp.SvParams) == 152 and ctypes.sizeof(gbp.SvResult) == 64
 
 
 def test_argument_validation_without_device(L):

@@ -370,3 +370,19 @@ def test_full_tree_is_a_capacity_error_not_trapped(gbp, dev):
         with pytest.raises(gbp.GbpError, match="-3"):
             full.connect(t, near, gbp.FORWARD)
         assert full.size() == 1
+
+
+def test_rotate_grf_and_curvature_exports(gbp, dev):
+    """rotate_grf (planning_utils.cpp:198-231) bit-equal to the reference golden G["grf_out"]; calculateCurvature (:884-899)
+    bit-equal to calculateMaxCurvature's per-triple value (the oracle's, pinned against the reference's maximum)"""
+    t, o, T, G, name = dev
+    assert_bits_equal(gbp.rotate_grf(G["grf_n"], G["grf_f"]), G["grf_out"], what="rotate_grf")
+    s = G["interp_states"] if "interp_states" in G else G["pair_states"]
+    tri = np.concatenate([s[:-2, :2], s[1:-1, :2], s[2:, :2]], axis=1)[:400]
+    got = gbp.curvature(tri)
+    for i in (0, 7, len(tri) - 1):  # a three-state plan's maximum curvature IS the curvature of its only triple
+        three = np.zeros((3, 8)); three[:, :2] = tri[i].reshape(3, 2)
+        want = o.max_curvature(three)
+        assert got[i] == want or (np.isnan(got[i]) and want == 0.0)  # std::max never takes a NaN (collinear points)
+    deg = gbp.curvature(np.array([[0, 0, 1, 0, 2, 0.0], [1, 1, 1, 2, 1, 3.0], [0, 0, 0, 0, 0, 0.0]]))
+    assert (deg == 0).all()

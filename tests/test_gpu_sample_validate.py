@@ -48,9 +48,9 @@ def vertex_table(o, rows, seed):
 
 
 def check(gbp, t, o, table, n, seed=5, stream=9, idx0=0, state_idx=None, direction=None, direction0=0, row0=0, adaptive=False,
-          normal=(0.0, 0.0, 1.0), target=None, thresh=0.0, valid_cap=None):
+          normal=(0.0, 0.0, 1.0), target=None, thresh=0.0, valid_cap=None, states_valid=False):
     tab = gbp.States(table)
-    p = gbp.sv_params(seed, stream, idx0, normal, adaptive, direction0, target, thresh, row0)
+    p = gbp.sv_params(seed, stream, idx0, normal, adaptive, direction0, target, thresh, row0, states_valid)
     r = t.sample_validate(tab, n, p, state_idx, direction, valid_cap=valid_cap)
     # the same candidates, spelled out
     rows = np.asarray(state_idx, dtype=np.int64) if state_idx is not None else row0 + np.arange(n)
@@ -133,6 +133,19 @@ def test_action_direction_sampling(gbp, env):
     d = rng.integers(0, 2, 1500).astype(np.uint8)
     for thresh in (0.15, 1.0):
         check(gbp, t, o, table, 1500, direction=d, target=target, thresh=thresh)
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+def test_start_states_promised_valid(gbp, env, adaptive):
+    """start_states_valid = 1: the first sub-state of every candidate (the start state itself, valid by the caller's promise) is
+    counted, not re-evaluated — verdicts, rows and the k / L / NaN-probe counters stay exactly the reference's.  Stance and
+    flight times that skip whole phases included."""
+    name, t, o, T = env
+    table = vertex_table(o, 9000, seed=13)   # valid STANCE states: the promise holds
+    rng = np.random.default_rng(13)
+    d = rng.integers(0, 2, 9000).astype(np.uint8)
+    check(gbp, t, o, table, 9000, direction=d, adaptive=adaptive, states_valid=True)
+    check(gbp, t, o, table, 3000, direction0=1, adaptive=adaptive, states_valid=True, normal=(0.03, 0.01, 0.99))
 
 
 def test_capped_valid_list(gbp, env):

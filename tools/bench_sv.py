@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--no-idx", action="store_true", help="implicit rows (state_idx = NULL)")
     ap.add_argument("--skip-dense", action="store_true")
+    ap.add_argument("--no-promise", action="store_true", help="start_states_valid = 0")
     args = ap.parse_args()
     import torch
     import bench
@@ -46,7 +47,7 @@ def main():
     vi = torch.empty(cap, dtype=torch.int32, device=dev); sn = torch.empty((cap, 8), dtype=torch.float64, device=dev)
     tn = torch.empty(cap, dtype=torch.float64, device=dev); ac = torch.empty((cap, 10), dtype=torch.float64, device=dev)
     res = torch.zeros(8, dtype=torch.int64, device=dev)
-    p = gbp.sv_params(1, 101, 0)  # bench.device_batch samples the actions from (seed 1, stream 101, idx 0 ...)
+    p = gbp.sv_params(1, 101, 0, states_valid="--no-promise" not in sys.argv)  # bench.device_batch samples the actions from (seed 1, stream 101, idx 0 ...)
 
     def step():
         t.sample_validate_dev(states.data_ptr(), n, n, p, 0 if args.no_idx else idx.data_ptr(), direction.data_ptr(), bits.data_ptr(), 0, cap,
