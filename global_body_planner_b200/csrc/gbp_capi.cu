@@ -115,12 +115,16 @@ int gbp_terrain_create(int nx, int ny, const double *x, const double *y, const d
 	for (int i = 0; i < nx && v.uniform; ++i) if (fabs(x[i] - (x[0] + i * v.step_x)) > 1e-12) v.uniform = 0;
 	for (int i = 0; i < ny && v.uniform; ++i) if (fabs(y[i] - (y[0] + i * v.step_y)) > 1e-12) v.uniform = 0;
 	bool has_nan = false;
-	double zmax = 0.0;
+	double zmax = 0.0, dzmax = 0.0;  // largest |z| and largest height step between neighbouring cells (both directions)
 	for (size_t i = 0; i < cells; ++i) {
 		if (z[i] != z[i]) { has_nan = true; break; }
 		if (fabs(z[i]) > zmax) zmax = fabs(z[i]);
+		if ((i + 1) % (size_t) ny && fabs(z[i + 1] - z[i]) > dzmax) dzmax = fabs(z[i + 1] - z[i]);
+		if (i + (size_t) ny < cells && fabs(z[i + ny] - z[i]) > dzmax) dzmax = fabs(z[i + ny] - z[i]);
 	}
-	bool mixed = v.uniform && !has_nan && v.step_x >= 0.01 && v.step_y >= 0.01 && !getenv("GBP_NO_MIXED");
+	// the mixed evaluator's error budget (< 1e-6 m against its 1e-5 m guard) carries ~1e-7 x the height step inside a cell
+	// (fp32 bilinear increments): cliffs above 4 m per cell, like |z| above 4 m for the rounded copy, keep the fp64 walk
+	bool mixed = v.uniform && !has_nan && dzmax <= 4.0 && v.step_x >= 0.01 && v.step_y >= 0.01 && !getenv("GBP_NO_MIXED");
 	{  // farthest a leg / corner / belly probe can be from the centre: sqrt(0.15^2 + 0.15^2) + 0.05 < 0.27 m
 		const double step = v.step_x < v.step_y ? v.step_x : v.step_y;
 		v.border = (int) std::ceil(0.27 / step) + 1;

@@ -17,6 +17,7 @@ constexpr double M_CONST = 13.0, G_CONST = 9.81, F_MAX = 637.0, MU = 1.0, T_F_MI
 constexpr double KINEMATICS_RES = 0.05, BACKUP_RATIO = 0.5, GOAL_BOUNDS = 0.5, MY_PI = 3.14159;
 constexpr double RRT_STAR_DELTA = 3.0;  // rrt_star_connect.h:59
 constexpr double NEAR_MARGIN = 1e-9;    // GBP_FLAG_NEAR guard band, metres
+constexpr double HARD_MARGIN = 1e-12;   // guard band of the speed (m/s) and pitch (rad) comparisons of isValidState
 
 // ---- device-resident FastTerrainMap (fast_terrain_map.h:97-118) as SoA grids.
 // Height cells are CellT = float when the fp64 input converts losslessly, else double.
@@ -453,8 +454,12 @@ __device__ __forceinline__ bool replay_checks(const ProbeBits &pb, bool pre_bad,
 template <typename M>
 __device__ __forceinline__ bool is_valid_state_fast(const TerrainView &T, const Pose6 &s, int phase, Counters &c) {
 	const bool pre_bad = (s.x < T.x0) || (s.x > T.x_last) || (s.y < T.y0) || (s.y > T.y_last) || (fabs(s.pitch) >= P_MAX);
-	const double r = sqrt(s.dx * s.dx + s.dy * s.dy);  // exact: the speed test is a hard comparison (:572)
+	const double r = sqrt(s.dx * s.dx + s.dy * s.dy);  // the speed test is a hard comparison (:572)
 	const bool speed_bad = r > V_MAX;
+	// The poses checked here come from FMA forms of applyStance / applyFlight (rounding-level differences from the reference's
+	// expressions, ~1e-15): the two hard comparisons get the same guard-band treatment as the clearances — a speed or pitch
+	// within HARD_MARGIN of its threshold is flagged, not silently decided
+	c.flags |= (fabs(r - V_MAX) < HARD_MARGIN || fabs(fabs(s.pitch) - P_MAX) < HARD_MARGIN) ? GBP_FLAG_NEAR : 0u;
 	double cy, sy, sp, cp;
 	yaw_cs(s.dx, s.dy, r, cy, sy);
 	sincos_small(pre_bad ? 0.0 : s.pitch, sp, cp);
@@ -560,6 +565,9 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 	const double r2 = s.dx * s.dx + s.dy * s.dy;
 	const bool speed_bad = r2 > __longlong_as_double(0x4010000000000001ll);
 	static_assert(V_MAX == 2.0, "speed threshold constant is derived for V_MAX = 2");
+	// speed or pitch within 1e-9 of its threshold (poses here come from the polynomial cursor, ~1e-14 from the reference's
+	// expressions): not decided here, the fp64 evaluator flags it if it is closer than HARD_MARGIN
+	const bool hard_near = fabs(r2 - V_MAX * V_MAX) < 4e-9 || fabs(fabs(s.pitch) - P_MAX) < 1e-9;
 	// centre cell in fp64, in-cell fraction handed to fp32
 	const double gx = (s.x - T.x0) * T.inv_dx, gy = (s.y - T.y0) * T.inv_dy;
 	const int ixc = (int) gx, iyc = (int) gy;
@@ -641,7 +649,7 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 		bad |= ((m[2 * k + 1] < 0.0) || (stance && m[2 * k] > 0.0)) ? (1u << k) : 0u;
 	}
 	near = near || (fabs(m[8]) < MIXED_MARGIN);
-	if (!ok || near || !(emax <= 0.5f - MIXED_EDGE)) return false;
+	if (!ok || near || hard_near || !(emax <= 0.5f - MIXED_EDGE)) return false;
 	const bool alive0 = !(pitch_bad || speed_bad);
 	const int corners = alive0 ? min(__ffs(bad | 16u), 4) : 0;  // corners the reference evaluates before it returns
 	const bool all_ok = alive0 && bad == 0;

@@ -240,3 +240,30 @@ def test_large_ragged_batch_device_call(gbp, env):
     assert (dv.cpu().numpy() == vo).all()
     assert_bits_equal(h[pad:pad + 64 * n].view(np.float64).reshape(n, 8), sno, what="s_new vs oracle")
     assert_bits_equal(dtn.cpu().numpy(), tno, what="t_new vs oracle")
+
+
+def test_hard_thresholds_are_guarded_and_cliffs_disable_the_mixed_walk(gbp, env):
+    """isValidState's speed (> V_MAX) and pitch (>= P_MAX) tests are hard comparisons on poses that, inside a pair check, come
+    from FMA forms of the primitives: a value within 1e-12 of its threshold is flagged GBP_FLAG_NEAR (and never decided by the
+    mixed-precision evaluator); verdicts on exact inputs still equal the oracle's.  A map with cliffs above 4 m per cell is
+    outside the mixed evaluator's error budget and keeps the fp64 walk."""
+    t, o, T = env
+    q = candidates(o, 64, seed=77)[0]
+    q[:, 3:6] = 0.0
+    q[:32, 3] = 2.0 + np.linspace(-4e-13, 4e-13, 32)             # speed on both sides of V_MAX = 2
+    q[32:, 3] = 0.5; q[32:, 6] = 1.0 + np.linspace(-4e-13, 4e-13, 32)  # pitch on both sides of P_MAX = 1
+    for phase in (gbp.STANCE, gbp.FLIGHT):
+        vg, fg = t.valid_states(q, phase)
+        vo, fo = o.valid_states(q, phase)
+        assert (vg == vo).all()
+        assert ((fg & gbp.FLAG_NEAR) != 0).sum() >= 60
+    far = q.copy(); far[:, 3] = 1.0; far[:, 6] = 0.2
+    assert not (t.valid_states(far, gbp.STANCE)[1] & gbp.FLAG_NEAR).any()
+    z = T.z.copy()
+    z[T.nx // 2:, :] += 10.0                                          # a 10 m cliff across the map
+    t2 = gbp.Terrain(T.x, T.y, z, T.dx, T.dy, T.dz)
+    assert not t2.flags()["mixed_precision"]
+    s, a, d = candidates(po.Oracle(po.Terrain(T.x, T.y, z, T.dx, T.dy, T.dz)), 3000, seed=78)
+    vg = t2.validate_pairs(s, a, d)[0]
+    vo = po.Oracle(po.Terrain(T.x, T.y, z, T.dx, T.dy, T.dz)).validate_pairs(s, a, d)[0]
+    assert (vg == vo).all()
