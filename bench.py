@@ -537,7 +537,7 @@ def main():
 
     value = world * n * args.steps / (total_ms_max * 1e-3)
     flagged = {"out_of_grid": int(all_stats[:, 3].sum()), "libm_guard_band": int(all_stats[:, 4].sum())}
-    # GBP_FLAG_NEAR candidates (a decisive margin inside the 1e-9 m guard band: expected ~1e-9 of the candidates) are REPORTED: their
+    # GBP_FLAG_NEAR candidates (a decisive margin inside the 1e-11 m guard band: expected ~1e-11 of the candidates) are REPORTED: their
     # verdict is the device's 1e-12 m-accurate evaluation, not provably glibc's; every other verdict is provably the reference's
     summary = {"validated_actions_per_s": value, "e2e_validated_actions_per_s": e2e["value"] if e2e else None, "n_gpus": world}
     if plans and "solved_plans_per_s" in plans:

@@ -16,7 +16,8 @@ constexpr double ROBOT_L = 0.3, ROBOT_W = 0.3, ROBOT_H = 0.05;
 constexpr double M_CONST = 13.0, G_CONST = 9.81, F_MAX = 637.0, MU = 1.0, T_F_MIN = 0.0, T_F_MAX = 0.5;
 constexpr double KINEMATICS_RES = 0.05, BACKUP_RATIO = 0.5, GOAL_BOUNDS = 0.5, MY_PI = 3.14159;
 constexpr double RRT_STAR_DELTA = 3.0;  // rrt_star_connect.h:59
-constexpr double NEAR_MARGIN = 1e-9;    // GBP_FLAG_NEAR guard band, metres
+constexpr double NEAR_MARGIN = 1e-11;   // GBP_FLAG_NEAR guard band, metres: 10x the 1e-12 m error bound of the fp64 evaluator (coordinates up to
+                                        // 10 km, heights up to 1 km; measured error ~1e-13 m, the size of the reference's own rounding noise)
 constexpr double HARD_MARGIN = 1e-12;   // guard band of the speed (m/s) and pitch (rad) comparisons of isValidState
 
 // ---- device-resident FastTerrainMap (fast_terrain_map.h:97-118) as SoA grids.
@@ -279,7 +280,7 @@ __device__ __forceinline__ bool is_valid_action(const double a[10]) {  // :519-5
 // =====================================================================================================
 // Fast validity path.  Everything computed INSIDE isValidState only feeds threshold comparisons, so it
 // needs guard-band accuracy, not bit equality: each clearance / reach comparison records whether its
-// margin is below NEAR_MARGIN (1e-9 m, GBP_FLAG_NEAR), and the arithmetic below is accurate to
+// margin is below NEAR_MARGIN (1e-11 m, GBP_FLAG_NEAR), and the arithmetic below is accurate to
 // ~1e-12 m (fp64 with explicit FMAs, IEEE reciprocal, algebraic yaw, polynomial sin/cos on |pitch|<1).
 // A candidate that is not flagged NEAR therefore has the same verdict as the reference's libm-based
 // evaluation, by an error bound instead of by instruction order.  Exact (bit-identical) arithmetic is
@@ -533,7 +534,7 @@ __device__ __forceinline__ bool is_valid_state_fast(const TerrainView &T, const 
 // increment over the cell's first corner) is fp32 on the full-rate FMA pipe, and each clearance margin is
 // assembled in fp64 as (z - f11) - H + (offset - increment).  Error budget < 1e-6 m; any sub-state with a
 // margin below MIXED_MARGIN (1e-5 m), a probe within MIXED_EDGE (2e-5 cells) of a grid line, or a probe
-// outside the grid is NOT decided here: it is re-evaluated by is_valid_state_fast (fp64, 1e-9 m guard).
+// outside the grid is NOT decided here: it is re-evaluated by is_valid_state_fast (fp64, 1e-11 m guard).
 constexpr double MIXED_MARGIN = 1e-5;
 constexpr float MIXED_EDGE = 2e-5f;
 

@@ -819,12 +819,16 @@ __global__ void __launch_bounds__(128) k_step_finish(TerrainView Tv, StepState S
 	}
 }
 
+// Measured on configs[4] (65,536 queries, B200): 1.18-1.78 s against the megakernel's 0.90 s at 80 / 168 / 255 registers —
+// every launch streams ~60 KB of straight-line code through each warp ONCE, so the instruction-fetch stalls of the megakernel
+// (no_instruction 6.9 cycles per issue in profiles/r2_step_half_ncu_summary.csv, against 7.3) stay and the HBM round trips of
+// the per-query state are added.  Kept as an opt-in form (GBP_PLAN_MODE=step) because it is the one whose launches are short
+// and uniform (e.g. for interleaving with other work on the stream); results are bit-identical either way.
 inline bool plan_step_applies(const gbp_plan_params &P, int64_t nq) {
-	const char *mode = getenv("GBP_PLAN_MODE");  // "mega" / "step": force one form (A/B measurements, tests); results are identical
+	const char *mode = getenv("GBP_PLAN_MODE");  // "step": plain fixed-step RRT-Connect batches take the stepped form
+	(void) nq;
 	if (P.rrt_star || P.adaptive || P.state_direction_sampling || P.stop_after_solved > 0 || P.k_candidates > 32) return false;
-	if (mode && !strcmp(mode, "mega")) return false;
-	if (mode && !strcmp(mode, "step")) return true;
-	return nq >= 16384;
+	return mode && !strcmp(mode, "step");
 }
 
 template <typename M>

@@ -207,7 +207,7 @@ __device__ __forceinline__ bool sv_walk_fp64(const TerrainView &T, const double 
 }
 // Candidates listed in redo_idx (the ones the mixed-precision walk could not decide), or — list == null — every candidate
 // of [0, n): the general path for terrains without the mixed evaluator (fp64 cells beyond the rounding budget, NaN cells,
-// non-uniform axes).  One thread per candidate, fp64 evaluator (1e-9 m guard).
+// non-uniform axes).  One thread per candidate, fp64 evaluator (1e-11 m guard).
 template <typename M>
 __global__ void __launch_bounds__(128) k_sv_fp64(TerrainView T, SvParams P, int64_t n, const int *__restrict__ list,
 												  const unsigned long long *__restrict__ list_count, int adaptive, unsigned *__restrict__ bits,

@@ -48,7 +48,7 @@ extern "C" {
 #define GBP_FLAG_OOG 2u   /* a terrain probe reached under the reference's sequential semantics fell outside
                              [x_0,x_last) x [y_0,y_last); the reference has undefined behaviour there, this
                              library uses cell-(0,0)-anchored extrapolation */
-#define GBP_FLAG_NEAR 4u  /* guard band: a clearance/reach comparison was decided by a margin below 1e-9 m, or a
+#define GBP_FLAG_NEAR 4u  /* guard band: a clearance/reach comparison was decided by a margin below 1e-11 m, or a
                              terrain probe fell within 1e-11 m of a grid line.  isValidState is evaluated with
                              ~1e-12 m accuracy (not bit-identical to glibc's atan2/sin/cos), so these are the
                              only candidates whose verdict is not PROVABLY the reference's */

@@ -89,7 +89,7 @@ def test_validate_pairs_golden(gbp, dev, variant, adaptive):
     assert (v[ing] == G[f"pair_verdict_{adaptive}"][ing]).all(), "verdict bits differ from the reference"
     assert_bits_equal(sn, G[f"pair_snew_{adaptive}"], where=ing, what="s_new")
     assert_bits_equal(tn, G[f"pair_tnew_{adaptive}"], where=ing, what="t_new")
-    # guard band: candidates whose verdict hinges on a margin < 1e-9 m or a probe < 1e-11 m from a grid line are
+    # guard band: candidates whose verdict hinges on a margin < 1e-11 m or a probe < 1e-11 m from a grid line are
     # flagged, not silently decided; they must be vanishingly rare (and here still agree with the reference)
     assert (fl & gbp.FLAG_NEAR).mean() < 1e-3
     # work counters equal the oracle's count of the reference's early-exit work

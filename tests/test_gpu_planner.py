@@ -150,3 +150,24 @@ def test_stop_after_solved(gbp):
     for key in ("iters", "nv_a", "nv_b", "path_states", "pair_checks", "nn_queries", "path_length"):
         assert (early[key][hit] == full[key][hit]).all(), key
     assert (early["iters"] <= full["iters"]).all() and early["iters"].sum() < full["iters"].sum()
+
+
+def test_stepped_form_is_identical(gbp, monkeypatch):
+    """GBP_PLAN_MODE=step: one launch per half-iteration over the whole batch (k_step_half) instead of the megakernel — same
+    trees, statistics and paths, bit for bit"""
+    T = load_terrain("synth_mixed"); o = po.Oracle(T)
+    t = gbp.Terrain(T.x, T.y, T.z, T.dx, T.dy, T.dz)
+    s, g = queries(o, T, 24, 5)
+    S, G = np.tile(s, (20, 1)), np.tile(g, (20, 1))
+    P = gbp.PlanParams(6, 0, 300, 128, 0, 0, 1)
+    monkeypatch.delenv("GBP_PLAN_MODE", raising=False)
+    a, pa_s, pa_a, ta = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
+    monkeypatch.setenv("GBP_PLAN_MODE", "step")
+    b, pb_s, pb_a, tb = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
+    assert a["solved"].sum() >= 5
+    for k in a.dtype.names:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(pa_s, pb_s) and np.array_equal(pa_a, pb_a)
+    for (xa, xb), (ya, yb) in zip(ta, tb):
+        for k in xa:
+            assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), k
