@@ -2,6 +2,12 @@
 #include "gbp_host.h"
 #include "gbp_planner.cuh"
 
+// the pipelined form lives in gbp_capi_pipeline.cu
+bool gbp_plan_pipe_applies(const TerrainView &Tv, const gbp_plan_params &P, int64_t nq);
+int gbp_plan_pipe_launch(const TerrainView &Tv, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+						 const gbp_plan_params &P, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap, cudaStream_t st,
+						 const PlanTreeDump &dump, std::string &err);
+
 extern "C" {
 
 // -------------------------------------------------------------------------- extend / connect
@@ -113,7 +119,9 @@ static int plan_dev(const gbp_terrain *t, int64_t nq, const double *starts, cons
 					const PlanTreeDump &dump, cudaStream_t st) {
 	keep_pool();
 	std::string err;
-	const int rc = plan_step_applies(*p, nq)
+	const int rc = gbp_plan_pipe_applies(t->view, *p, nq)
+		? gbp_plan_pipe_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, st, dump, err)
+		: plan_step_applies(*p, nq)
 		? plan_step_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, st, dump, err)
 		: plan_batch_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, st, dump, err);
 	if (rc) return fail(rc, err);

@@ -1,0 +1,448 @@
+// The pipelined batch planner: runRRTConnect (rrt_connect.cpp:230-314) for a large batch of independent queries as a
+// sequence of ROUNDS, each advancing every running query by one extend attempt, with the three roles of an extend in three
+// kernels that all queries go through together:
+//
+//   k_pipe_prep    warp per query: skips the query's invalid random states (rrt_connect.cpp:254; STATE cells are drawn and
+//                  validity-checked 32 at a time), checks the budget and the tree capacity, finds the nearest neighbour
+//                  (rrt.cpp:78), the surface normal at the target (rrt.cpp:25) and its GRF rotation, and appends one SEGMENT
+//                  {s_near, R, s_rand, direction, Philox cell} to the round's dense list
+//   k_walk_seg     the candidates of all segments FLATTENED: candidate i = (segment i / K, action j = i % K).  This is
+//                  k_walk_sv (gbp_sv.cuh) with per-segment parameters: a warp produces 32 candidates convergently (state
+//                  row gathered with cp.async while the action is sampled), a lane walks one candidate's sub-states in the
+//                  reference's order through the mixed-precision evaluator, a finished lane takes the next candidate.  The
+//                  start state of a candidate is a tree vertex — valid by construction — so its own check (the reference's
+//                  first sub-state) is not repeated (roots are checked once by k_pipe_init).  Out: one VALID bit and one
+//                  UNDECIDED bit per candidate.
+//   k_pipe_select  warp per segment: resolves undecided candidates with the fp64 evaluator, takes the first valid action
+//                  in stream order (or the closest valid one), rebuilds its exact end state (finish_output), applies
+//                  newConfig's acceptance (rrt.cpp:55-66), appends the vertex (rrt.cpp:87-92) and runs connect from the
+//                  other tree (rrt_connect.cpp:98-120, the pair check spread over the lanes); then moves the query to its
+//                  next half-iteration or marks it solved.
+//
+// Why (profiles/r1c_planner_ncu_summary.csv, profiles/r2_step_half_ncu_summary.csv): in the megakernel a warp is one query,
+// its 6 candidates x 5 speculative sub-states fill 30 lanes, and every lane of a candidate's group samples the same action
+// — sampling alone is ~900 of the ~3800 warp instructions of an extend, the code of an extend is ~60 KB of straight line
+// that every warp streams through once per iteration (instruction fetch is 7 of the 15 stall cycles per issue), and the
+// 80-register cap spills 2.7 KB per thread.  Flattened, a lane samples ONE action for ONE candidate (28 warp instructions per
+// candidate instead of 150), the walk is the microbenchmark's 1.2 k-instruction loop (no fetch stalls, 128 registers, no
+// spills), and invalid random states cost nothing: ~1700 rounds instead of 4000 half-iterations.
+// Results are the megakernel's bit for bit (same Philox cells, same arithmetic, same order of tree updates per query):
+// tests/test_gpu_planner.py runs both forms against the oracle and the reference-loop golden.
+// Applies to plain RRT-Connect at the fixed step with K <= 32 on terrains with the mixed-precision evaluator; everything
+// else (RRT*, adaptive step, directional STATE sampling, anytime rounds, K > 32, other map kinds) stays on k_plan_batch.
+#pragma once
+#include "gbp_planner.cuh"
+#include "gbp_sv.cuh"
+
+namespace gbp {
+
+constexpr int PIPE_ROW = 26;  // doubles per segment row: s_near[8], R[9], s_rand[8], pad (rows stay 16-byte aligned)
+
+struct PipeState {  // per query
+	int *na, *nb;              // vertex counts (the trees' `n` words)
+	int *status;               // 0 running, 1 solved, 2 stopped (budget used up or a tree full)
+	int *it, *half;            // the half-iteration the query is at
+	int *iters;                // started iterations when it stopped
+	long long *pair_checks, *nn_queries;
+	double *rs;                // [Q][32][8] the current batch of 32 STATE cells
+	unsigned *rs_valid;        // isValidState(STANCE) of the batch
+	long long *rs_base;        // first cell of the batch (-1: none yet)
+	unsigned char *root_valid; // [Q][2] isValidState(root, STANCE) of the start-side / goal-side tree
+};
+struct PipeSegs {  // the round's dense segment list
+	double *rows;              // [Q][PIPE_ROW]
+	int *q, *near;             // query, id of s_near in the tree being extended
+	unsigned char *flags;      // bit 0: direction, bit 1: s_near is known valid
+	unsigned long long *idx0;  // ACTION cell of candidate 0: cell * K
+	int *count;                // segments of this round; followed by the valid / undecided bit words
+	unsigned *vbits, *ubits;
+};
+
+template <typename M>
+__global__ void __launch_bounds__(128) k_pipe_init(TerrainView Tv, PipeState S, PlanArena A, int64_t Q, const double *__restrict__ starts,
+													const double *__restrict__ goals, int max_iters) {
+	const int64_t q = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	if (q >= Q) return;
+	PlanTree Ta = arena_tree(A, (int) q, 0, S.na + q), Tb = arena_tree(A, (int) q, 1, S.nb + q);
+	double s[8], g[8];
+#pragma unroll
+	for (int d = 0; d < 8; ++d) { s[d] = starts[8 * q + d]; g[d] = goals[8 * q + d]; }
+	plan_tree_init(Ta, s);
+	plan_tree_init(Tb, g);
+	Counters c = {0, 0, 0, 0};
+	S.root_valid[2 * q] = is_valid_state_auto<M>(Tv, pose6(s), GBP_STANCE, c) ? 1 : 0;
+	S.root_valid[2 * q + 1] = is_valid_state_auto<M>(Tv, pose6(g), GBP_STANCE, c) ? 1 : 0;
+	S.status[q] = 0; S.it[q] = 0; S.half[q] = 0; S.iters[q] = max_iters; S.pair_checks[q] = 0; S.nn_queries[q] = 0;
+	S.rs_valid[q] = 0; S.rs_base[q] = -1;
+}
+
+template <typename M>
+__global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int64_t Q, uint64_t seed, uint64_t query0,
+													gbp_plan_params P) {
+	const int lane = threadIdx.x & 31;
+	const int64_t q = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+	if (q >= Q || S.status[q] != 0) return;
+	int it = S.it[q], half = S.half[q];
+	const int na = S.na[q], nb = S.nb[q];
+	while (true) {
+		if (it >= P.max_iters) {  // budget used up
+			if (lane == 0) { S.status[q] = 2; S.iters[q] = P.max_iters; }
+			return;
+		}
+		if (na >= A.cap || nb >= A.cap) {  // a tree is full at the start of a half: the query stops unsolved
+			if (lane == 0) { S.status[q] = 2; S.iters[q] = it + 1; }
+			return;
+		}
+		const long long cell = 2ll * it + half, base = cell & ~31ll;
+		if (S.rs_base[q] != base) {  // STATE cells base .. base + 31: lane L draws and checks cell base + L
+			double rs[8];
+			sample_state<M>(Tv, seed, query0 + (uint64_t) q, (uint64_t) base + (uint64_t) lane, false, 0.0, false, nullptr, nullptr, rs);
+			Counters c = {0, 0, 0, 0};
+			const unsigned valid = __ballot_sync(FULL, is_valid_state_auto<M>(Tv, pose6(rs), GBP_STANCE, c));
+			double2 *o = reinterpret_cast<double2 *>(S.rs + ((size_t) q * 32 + lane) * 8);
+#pragma unroll
+			for (int d = 0; d < 4; ++d) o[d] = make_double2(rs[2 * d], rs[2 * d + 1]);
+			if (lane == 0) { S.rs_valid[q] = valid; S.rs_base[q] = base; }
+			__syncwarp();
+		}
+		const unsigned mask = S.rs_valid[q] >> (unsigned) (cell & 31ll);
+		const long long next = mask ? cell + (__ffs(mask) - 1) : base + 32;  // invalid random states are skipped (rrt_connect.cpp:254)
+		it = (int) (next >> 1); half = (int) (next & 1);
+		if (mask) break;
+	}
+	if (it >= P.max_iters) {
+		if (lane == 0) { S.status[q] = 2; S.iters[q] = P.max_iters; }
+		return;
+	}
+	const long long cell = 2ll * it + half;
+	double s_rand[8];
+	{
+		const double2 *r = reinterpret_cast<const double2 *>(S.rs + ((size_t) q * 32 + (size_t) (cell & 31ll)) * 8);
+#pragma unroll
+		for (int d = 0; d < 4; ++d) { const double2 v = r[d]; s_rand[2 * d] = v.x; s_rand[2 * d + 1] = v.y; }
+	}
+	PlanTree Tx = arena_tree(A, (int) q, half, (half == 0 ? S.na : S.nb) + q);
+	const int nx = half == 0 ? na : nb;
+	const int near = warp_nearest(Tx.t, nx, s_rand, lane);  // rrt.cpp:78
+	double s_near[8], nn[3], R[9];
+	tree_get(Tx.t, near, s_near);
+	unsigned fl = 0;
+	surface_normal(Tv, s_rand[0], s_rand[1], nn, fl);  // rrt.cpp:25 — at the TARGET sample
+	grf_rotation(nn, R);
+	int seg = 0;
+	if (lane == 0) seg = atomicAdd(G.count, 1);
+	seg = __shfl_sync(FULL, seg, 0);
+	double *row = G.rows + (size_t) seg * PIPE_ROW;
+	if (lane < 8) row[lane] = s_near[lane];
+	else if (lane < 17) row[lane] = R[lane - 8];
+	else if (lane < 25) row[lane] = s_rand[lane - 17];
+	if (lane == 0) {
+		G.q[seg] = (int) q;
+		G.near[seg] = near;
+		// a tree vertex other than the root is the end state of a fully valid pair check: STANCE-valid by construction
+		const bool known_valid = near != 0 || S.root_valid[2 * q + half] != 0;
+		G.flags[seg] = (unsigned char) ((half == 0 ? GBP_FORWARD : GBP_REVERSE) | (known_valid ? 2 : 0));
+		G.idx0[seg] = (unsigned long long) cell * (unsigned long long) P.k_candidates;
+		S.it[q] = it; S.half[q] = half;
+	}
+}
+
+// k_walk_sv with per-segment parameters; see the file header.  `count` = segments of this round (device).
+template <bool TEX>
+__global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_seg(TerrainView T, PipeSegs G, int K, uint64_t seed, uint64_t query0, int dir_sampling,
+																		 double dir_thresh) {
+	__shared__ __align__(16) double ringS[RF_WARPS][SV_CAP][8];
+	__shared__ __align__(16) double ringA[RF_WARPS][SV_CAP][10];
+	__shared__ __align__(16) double stash[8][RF_WARPS * 32];
+	__shared__ uint8_t ringD[RF_WARPS][SV_CAP];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int n = *G.count * K;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	int per_warp = (n + warps - 1) / warps;
+	per_warp = max(32, (per_warp + 31) / 32 * 32);  // whole bit words per warp
+	const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+	const int wbase = (int) min(warp * (int64_t) per_warp, (int64_t) n);
+	const int total = min(n - wbase, per_warp);
+	double *const st = &stash[0][threadIdx.x];
+	const uint64_t pol = l2_evict_first_policy();
+	int next = 0, filled = 0;
+	WalkCursor q;
+	q.phase = PH_IDLE;
+	int mine = -1;
+	while (true) {
+		const unsigned need = __ballot_sync(FULL, q.phase == PH_IDLE);
+		if (need && next < total) {
+			const int nidle = __popc(need);
+			if (filled - next < nidle && filled < total && filled - next <= SV_CAP - 32) {
+				const int r = filled + lane;
+				if (r < total) {
+					const int e = r % SV_CAP;
+					const int i = wbase + r;
+					const int seg = i / K, j = i - seg * K;
+					const double *row = G.rows + (size_t) seg * PIPE_ROW;
+#pragma unroll
+					for (int d = 0; d < 4; ++d) cp_async16_hint(&ringS[wib][e][2 * d], row + 2 * d, pol);
+					const int f = (int) G.flags[seg];
+					ringD[wib][e] = (uint8_t) f;
+					double vx = 0, vy = 0, tvx = 0, tvy = 0;
+					if (dir_sampling) { vx = row[3]; vy = row[4]; tvx = row[17 + 3]; tvy = row[17 + 4]; }
+					sv_sample_to_ring(seed, query0 + (uint64_t) G.q[seg], G.idx0[seg] + (uint64_t) j, row + 8, dir_sampling, dir_thresh, tvx, tvy, f & 1, vx,
+									  vy, &ringA[wib][e][0]);
+				}
+				cp_async_wait_all();
+				__syncwarp();
+				filled = min(total, filled + 32);
+			}
+			if (q.phase == PH_IDLE) {
+				const int rel = next + __popc(need & ((1u << lane) - 1));
+				if (rel < filled) {
+					const int e = rel % SV_CAP;
+					const double2 *ps = reinterpret_cast<const double2 *>(&ringS[wib][e][0]);
+					const double2 *pa = reinterpret_cast<const double2 *>(&ringA[wib][e][0]);
+					double s[8], a[10];
+#pragma unroll
+					for (int d = 0; d < 4; ++d) { const double2 v = ps[d]; s[2 * d] = v.x; s[2 * d + 1] = v.y; }
+#pragma unroll
+					for (int d = 0; d < 5; ++d) { const double2 v = pa[d]; a[2 * d] = v.x; a[2 * d + 1] = v.y; }
+					mine = wbase + rel;
+					const int f = (int) ringD[wib][e];
+					walk_start(q, s, a, f & 1, st);
+					// the start state's own check (the reference's first sub-state) is not repeated for a vertex known valid
+					if ((f & 2) && q.t == 0 && (q.phase == PH_FWD_ST || q.phase == PH_REV_FL)) {
+						OutRecipe dummy;
+						(void) walk_advance<false>(q, true, dummy, st);
+					}
+				}
+			}
+			next = min(filled, next + nidle);
+			__syncwarp();
+		}
+		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) break;
+		bool valid = false, decided = true;
+		if (q.phase != PH_IDLE) {
+			const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
+			decided = is_valid_state_mixed<MapF32U, TEX>(T, walk_pose(q), ph, q.c_, valid);
+		}
+		if (!decided) {  // resolved by k_pipe_select with the fp64 evaluator
+			atomicOr(G.ubits + (mine >> 5), 1u << (mine & 31));
+			q.phase = PH_IDLE;
+		}
+		if (q.phase != PH_IDLE) {
+			OutRecipe out;
+			const int r = walk_advance<false>(q, valid, out, st);
+			if (r) {
+				if (r == 2) atomicOr(G.vbits + (mine >> 5), 1u << (mine & 31));
+				q.phase = PH_IDLE;
+			}
+		}
+	}
+}
+
+__device__ __forceinline__ unsigned pipe_bits(const unsigned *__restrict__ words, int first, int count) {
+	const unsigned long long two = (unsigned long long) words[first >> 5] | ((unsigned long long) words[(first >> 5) + 1] << 32);
+	return (unsigned) (two >> (first & 31)) & (count >= 32 ? 0xffffffffu : ((1u << count) - 1u));
+}
+
+template <typename M>
+__global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, uint64_t seed, uint64_t query0, gbp_plan_params P) {
+	const int lane = threadIdx.x & 31;
+	const int seg = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5);
+	if (seg >= *G.count) return;
+	const int q = G.q[seg], K = P.k_candidates;
+	const double *row = G.rows + (size_t) seg * PIPE_ROW;
+	double s_near[8], R[9], s_rand[8];
+#pragma unroll
+	for (int d = 0; d < 8; ++d) { s_near[d] = row[d]; s_rand[d] = row[17 + d]; }
+#pragma unroll
+	for (int d = 0; d < 9; ++d) R[d] = row[8 + d];
+	const int dir = (int) G.flags[seg] & 1, half = dir == GBP_FORWARD ? 0 : 1, near = G.near[seg];
+	const uint64_t stream = query0 + (uint64_t) q, idx0 = G.idx0[seg];
+	const bool dirs = P.action_direction_sampling != 0;
+	const double *a_from = dir == GBP_FORWARD ? s_near : s_rand, *a_to = dir == GBP_FORWARD ? s_rand : s_near;
+	unsigned vmask = pipe_bits(G.vbits, seg * K, K);
+	const unsigned umask = pipe_bits(G.ubits, seg * K, K);
+	if (umask) {  // candidates the mixed-precision walk could not decide: the exact fp64 walk, one lane each
+		bool ok = false;
+		if (lane < K && ((umask >> lane) & 1u)) {
+			double a[10], sn[8], tn;
+			sample_action(seed, stream, idx0 + (uint64_t) lane, R, dirs, P.action_direction_threshold, a_from, a_to, a);
+			Counters c = {0, 0, 0, 0};
+			ok = validate_pair_seq<M>(Tv, s_near, a, dir, false, sn, tn, c);
+		}
+		vmask |= __ballot_sync(FULL, ok);
+	}
+	long long pair_checks, nn_queries = 1;
+	bool found = false;
+	double sn[8], a[10];
+	const double best0 = state_distance(s_near, s_rand);
+	if (!P.best_of_k) {
+		const int j = vmask ? __ffs(vmask) - 1 : -1;  // the first valid action decides (rrt.cpp:44-47)
+		pair_checks = j < 0 ? K : j + 1;
+		if (j >= 0) {
+			sample_action(seed, stream, idx0 + (uint64_t) j, R, dirs, P.action_direction_threshold, a_from, a_to, a);
+			finish_output(s_near, a, dir == GBP_FORWARD ? OUT_LAND : OUT_REV, 0.0, sn);
+			found = state_distance(sn, s_rand) < best0;  // rrt.cpp:55-66
+		}
+	} else {
+		pair_checks = K;
+		double my_d = INFINITY, my_sn[8], my_a[10];
+		int my_j = 0x7fffffff;
+		if (lane < K && ((vmask >> lane) & 1u)) {
+			sample_action(seed, stream, idx0 + (uint64_t) lane, R, dirs, P.action_direction_threshold, a_from, a_to, my_a);
+			finish_output(s_near, my_a, dir == GBP_FORWARD ? OUT_LAND : OUT_REV, 0.0, my_sn);
+			my_d = state_distance(my_sn, s_rand);
+			my_j = lane;
+		}
+		double bd = my_d;
+		int bj = my_j;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			const double od = __shfl_xor_sync(FULL, bd, o);
+			const int oj = __shfl_xor_sync(FULL, bj, o);
+			if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+		}
+		if (bj != 0x7fffffff && bd < best0) {
+			found = true;
+#pragma unroll
+			for (int d = 0; d < 8; ++d) sn[d] = __shfl_sync(FULL, my_sn[d], bj);
+#pragma unroll
+			for (int d = 0; d < 10; ++d) a[d] = __shfl_sync(FULL, my_a[d], bj);
+		}
+	}
+	int na = S.na[q], nb = S.nb[q];
+	bool solved = false;
+	if (found) {
+		PlanTree Ta = arena_tree(A, q, 0, S.na + q), Tb = arena_tree(A, q, 1, S.nb + q);
+		PlanTree &Tx = half == 0 ? Ta : Tb, &Ty = half == 0 ? Tb : Ta;
+		int &ny = half == 0 ? nb : na;
+		if (lane == 0) plan_push(Tx, near, sn, a);  // rrt.cpp:87-92
+		__syncwarp();
+		++nn_queries;
+		solved = warp_connect<M>(Tv, Ty, ny, sn, dir == GBP_FORWARD ? GBP_REVERSE : GBP_FORWARD, P, lane, pair_checks) == GBP_REACHED;
+	}
+	if (lane == 0) {
+		S.pair_checks[q] += pair_checks;
+		S.nn_queries[q] += nn_queries;
+		const int it = S.it[q];
+		if (solved) { S.status[q] = 1; S.iters[q] = it + 1; }
+		else if (half == 0) S.half[q] = 1;
+		else { S.it[q] = it + 1; S.half[q] = 0; }
+	}
+}
+
+template <typename M>
+__global__ void __launch_bounds__(128) k_pipe_finish(TerrainView Tv, PipeState S, PlanArena A, PlanArena scratch, int64_t Q, gbp_plan_params P,
+													  unsigned long long *__restrict__ next_query, gbp_plan_stats *__restrict__ stats,
+													  double *__restrict__ path_states, double *__restrict__ path_actions, int path_cap, PlanTreeDump dump) {
+	const int lane = threadIdx.x & 31;
+	const int64_t slot = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
+	while (true) {
+		unsigned long long grabbed = 0;
+		if (lane == 0) grabbed = atomicAdd(next_query, 1ull);
+		const int64_t q = (int64_t) __shfl_sync(FULL, grabbed, 0);
+		if (q >= Q) break;
+		PlanTree Ta = arena_tree(A, (int) q, 0, S.na + q), Tb = arena_tree(A, (int) q, 1, S.nb + q);
+		plan_finish<M>(Tv, P, scratch, slot, Ta, Tb, S.na[q], S.nb[q], S.status[q] == 1, S.iters[q], S.pair_checks[q], S.nn_queries[q], q, stats,
+					   path_states, path_actions, path_cap, dump, lane);
+		__syncwarp();
+	}
+}
+
+inline bool plan_pipe_applies(const TerrainView &Tv, const gbp_plan_params &P, int64_t nq) {
+	const char *mode = getenv("GBP_PLAN_MODE");  // "mega" / "pipe": force one form (A/B measurements, tests); results are identical
+	if (P.rrt_star || P.adaptive || P.state_direction_sampling || P.stop_after_solved > 0 || P.k_candidates > 32 || !Tv.mixed_ok || !Tv.uniform) return false;
+	if (mode && !strcmp(mode, "pipe")) return true;
+	if (mode && (!strcmp(mode, "mega") || !strcmp(mode, "step"))) return false;
+	return nq >= 8192;
+}
+
+template <typename M>
+inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+								 const gbp_plan_params &P, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap,
+								 cudaStream_t st, const PlanTreeDump &dump, std::string &err) {
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const size_t cap = (size_t) P.max_vertices, Q = (size_t) nq, per = Q * 2 * cap, K = (size_t) P.k_candidates;
+	const int64_t fin_slots = (int64_t) sms * 4 * 4;
+	const size_t bit_words = (Q * K + 31) / 32 + 2;
+	const size_t n_doubles = per * (8 + 10 + 1 + 1) + Q * 32 * 8 + Q * PIPE_ROW + (size_t) fin_slots * 2 * cap * 18;
+	const size_t n_ll = Q * 4 + 2;  // pair_checks, nn_queries, rs_base, idx0, finish counter
+	const size_t n_ints = per * 3 + Q * 9 + 4 + 2 * bit_words;
+	const size_t need = n_doubles * 8 + n_ll * 8 + n_ints * 4 + Q * 3 + 64;
+	void *mem = nullptr;
+	cudaError_t e;
+	if ((e = cudaMallocAsync(&mem, need, st)) != cudaSuccess) { err = std::string("pipelined planner arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
+	PlanArena A = {}, Sc = {};
+	PipeState S;
+	PipeSegs G;
+	A.cap = Sc.cap = P.max_vertices;
+	double *dp = (double *) mem;
+	A.v = dp; dp += per * 8;
+	A.act = dp; dp += per * 10;
+	A.g = dp; dp += per;
+	A.y = dp; dp += per;
+	S.rs = dp; dp += Q * 32 * 8;
+	G.rows = dp; dp += Q * PIPE_ROW;
+	Sc.pstate = dp; dp += (size_t) fin_slots * 2 * cap * 8;
+	Sc.paction = dp; dp += (size_t) fin_slots * 2 * cap * 10;
+	long long *lp = (long long *) dp;
+	S.pair_checks = lp; lp += Q;
+	S.nn_queries = lp; lp += Q;
+	S.rs_base = lp; lp += Q;
+	G.idx0 = (unsigned long long *) lp; lp += Q;
+	unsigned long long *next_query = (unsigned long long *) lp; lp += 2;
+	int *ip = (int *) lp;
+	A.parent = ip; ip += per;
+	A.child = ip; ip += per;
+	A.sibling = ip; ip += per;
+	S.na = ip; ip += Q;
+	S.nb = ip; ip += Q;
+	S.status = ip; ip += Q;
+	S.it = ip; ip += Q;
+	S.half = ip; ip += Q;
+	S.iters = ip; ip += Q;
+	S.rs_valid = (unsigned *) ip; ip += Q;
+	G.q = ip; ip += Q;
+	G.near = ip; ip += Q;
+	G.count = ip; ip += 4;  // the per-round words: count, then the two bit arrays (one memset per round)
+	G.vbits = (unsigned *) ip; ip += bit_words;
+	G.ubits = (unsigned *) ip; ip += bit_words;
+	unsigned char *bp = (unsigned char *) ip;
+	S.root_valid = bp; bp += 2 * Q;
+	G.flags = bp; bp += Q;
+	const size_t round_bytes = (4 + 2 * bit_words) * 4;
+	static thread_local int *h_count = nullptr;  // pinned
+	if (!h_count && (e = cudaHostAlloc((void **) &h_count, sizeof(int), cudaHostAllocDefault)) != cudaSuccess) {
+		cudaFreeAsync(mem, st);
+		err = std::string("pipelined planner: ") + cudaGetErrorString(e);
+		return GBP_E_CUDA;
+	}
+	const unsigned warp_blocks = (unsigned) ((Q + 3) / 4);
+	const unsigned walk_grid = (unsigned) sms * GBP_WALK_CTAS;
+	k_pipe_init<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, nq, starts, goals, P.max_iters);
+	// a round runs one extend attempt of every running query; a query needs at most 2 * max_iters of them (every random
+	// state valid).  The number of running queries is read back every 32 rounds to stop launching once all are done.
+	const int max_rounds = 2 * P.max_iters + 1;
+	for (int round = 0; round < max_rounds; ++round) {
+		cudaMemsetAsync(G.count, 0, round_bytes, st);
+		k_pipe_prep<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, G, nq, seed, query0, P);
+		if (Tv.ztex) k_walk_seg<true><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
+		else k_walk_seg<false><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
+		k_pipe_select<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, G, seed, query0, P);
+		if ((round & 31) == 31) {
+			cudaMemcpyAsync(h_count, G.count, sizeof(int), cudaMemcpyDeviceToHost, st);
+			if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+			if (*h_count == 0) break;
+		}
+	}
+	cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st);
+	const int64_t fin_warps = (int64_t) Q < fin_slots ? (int64_t) ((Q + 3) / 4 * 4) : fin_slots;
+	k_pipe_finish<M><<<(unsigned) (fin_warps / 4), 128, 0, st>>>(Tv, S, A, Sc, nq, P, next_query, stats, path_states, path_actions, path_cap, dump);
+	e = cudaGetLastError();
+	cudaFreeAsync(mem, st);
+	if (e != cudaSuccess) { err = std::string("pipelined planner: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
+	return GBP_OK;
+}
+
+}  // namespace gbp

@@ -76,7 +76,7 @@ __device__ __forceinline__ int plan_push(PlanTree &T, int parent, const double s
 	return i;
 }
 // updateGYValue (graph_class.cpp:131-138): set (g, y) of `root` and refresh its subtree, stack-free pre-order walk
-__device__ void plan_update_gy(PlanTree &T, int root, double g, double y) {
+static __device__ void plan_update_gy(PlanTree &T, int root, double g, double y) {
 	T.t.g[root] = g;
 	T.t.y[root] = y;
 	int i = T.child[root];

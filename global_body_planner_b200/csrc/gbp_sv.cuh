@@ -62,7 +62,7 @@ __device__ __forceinline__ void sv_sample(uint64_t seed, uint64_t stream, uint64
 	sample_action(seed, stream, cell, R, dir_sampling != 0, dir_thresh, sf, st, a);
 }
 // out of line: called once per 32 candidates with all lanes active; keeps the sampler's registers out of the walk loop
-__device__ __noinline__ void sv_sample_to_ring(uint64_t seed, uint64_t stream, uint64_t cell, const double *R, int dir_sampling, double dir_thresh,
+static __device__ __noinline__ void sv_sample_to_ring(uint64_t seed, uint64_t stream, uint64_t cell, const double *R, int dir_sampling, double dir_thresh,
 												double tvx, double tvy, int dir, double vx, double vy, double *dst) {
 	double a[10];
 	sv_sample(seed, stream, cell, R, dir_sampling, dir_thresh, tvx, tvy, dir, vx, vy, a);
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(128) k_sv_fp64(TerrainView T, SvParams P, int6
 
 // ---- compaction of the verdict bits into the ascending list of valid candidates
 // pass 1: block b counts the set bits of its span of words
-__global__ void __launch_bounds__(256) k_sv_count(const unsigned *__restrict__ bits, int64_t nwords, int64_t span, unsigned long long *__restrict__ sums) {
+static __global__ void __launch_bounds__(256) k_sv_count(const unsigned *__restrict__ bits, int64_t nwords, int64_t span, unsigned long long *__restrict__ sums) {
 	__shared__ unsigned long long part[8];
 	const int64_t lo = blockIdx.x * span, hi = min(nwords, lo + span);
 	unsigned long long c = 0;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) k_sv_count(const unsigned *__restrict__ b
 }
 // pass 2: block b starts at the sum of the blocks before it and lists its set bits in ascending order; block 0 also
 // publishes the call's result words {n_valid, sub-states k, lookups L, NaN probes, OOG, NEAR, rows out of range, 0}
-__global__ void __launch_bounds__(256) k_sv_list(const unsigned *__restrict__ bits, int64_t nwords, int64_t span, const unsigned long long *__restrict__ sums,
+static __global__ void __launch_bounds__(256) k_sv_list(const unsigned *__restrict__ bits, int64_t nwords, int64_t span, const unsigned long long *__restrict__ sums,
 												  int64_t cap, int *__restrict__ index, const unsigned long long *__restrict__ cnt, long long *__restrict__ result) {
 	__shared__ unsigned long long part[8];
 	__shared__ unsigned long long s_base;
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) k_sv_list(const unsigned *__restrict__ bi
 }
 // pass 3: exact rows of the valid candidates: s_new = the landing state (FORWARD, planning_utils.cpp:743-749) or the exact
 // start state (REVERSE, :866-872), t_new = t_s + t_f or t_s, and the sampled action — what rrt.cpp:44-62 goes on to use
-__global__ void __launch_bounds__(128) k_sv_outputs(SvParams P, const long long *__restrict__ result, int64_t cap, const int *__restrict__ index,
+static __global__ void __launch_bounds__(128) k_sv_outputs(SvParams P, const long long *__restrict__ result, int64_t cap, const int *__restrict__ index,
 													 double *__restrict__ s_new, double *__restrict__ t_new, double *__restrict__ action) {
 	__shared__ double sR[9];
 	if (threadIdx.x == 0) grf_rotation(P.normal, sR);

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of the two forms of the batch planner (GBP_PLAN_MODE=mega | step) on bench_plans' configs[4] queries: identical
+"""A/B of the forms of the batch planner (GBP_PLAN_MODE=mega | pipe | step) on bench_plans' configs[4] queries: identical
 statistics required, plans/s of each.  usage: python tools/bench_planner_modes.py [queries [modes]]"""
 import json
 import os
@@ -27,7 +27,7 @@ def main():
     s, g = s[vg == 1][:nq], g[vg == 1][:nq]
     P = gbp.PlanParams(bp.K_CAND, 0, bp.MAX_ITERS, bp.MAX_VERTS, 0, 0, 0)
     out, ref = {}, None
-    for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("mega", "step")):
+    for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("mega", "pipe")):
         os.environ["GBP_PLAN_MODE"] = mode
         st, secs = bp.timed_batch(gbp, torch, None, dev, 0, 1, t, s, g, 11, 0, P)
         out[mode] = bp.batch_summary(st, secs)
