@@ -250,7 +250,7 @@ def timed_batch(gbp, torch, dist, dev, rank, world, t, s, g, seed, query0, P):
     ds = torch.from_numpy(s).to(dev); dg = torch.from_numpy(g).to(dev)
     dstats = torch.zeros(nq * 80, dtype=torch.uint8, device=dev)
     cur = torch.cuda.current_stream().cuda_stream
-    t.plan_batch_dev(min(nq, 2368), ds.data_ptr(), dg.data_ptr(), seed, query0, P, dstats.data_ptr(), cur)  # warm-up
+    t.plan_batch_dev(nq, ds.data_ptr(), dg.data_ptr(), seed, query0, P, dstats.data_ptr(), cur)  # warm-up at full size (the tree arena comes from the stream-ordered pool)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

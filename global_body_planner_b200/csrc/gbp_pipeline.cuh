@@ -48,13 +48,18 @@ struct PipeState {  // per query
 	unsigned *rs_valid;        // isValidState(STANCE) of the batch
 	long long *rs_base;        // first cell of the batch (-1: none yet)
 	unsigned char *root_valid; // [Q][2] isValidState(root, STANCE) of the start-side / goal-side tree
+	int *busy_until;           // [Q] first round that may touch the query again (its connect runs on the second stream meanwhile)
+};
+struct PipeConnects {          // queries whose tree grew in a round: connect requests, double-buffered by round parity
+	int *count;                // [2]
+	int *entry;                // [2][Q]: query * 2 + half
 };
 struct PipeSegs {  // the round's dense segment list
 	double *rows;              // [Q][PIPE_ROW]
 	int *q, *near;             // query, id of s_near in the tree being extended
 	unsigned char *flags;      // bit 0: direction, bit 1: s_near is known valid
 	unsigned long long *idx0;  // ACTION cell of candidate 0: cell * K
-	int *count;                // segments of this round; followed by the valid / undecided bit words
+	int *count;                // [0] segments of this round, [1] running queries whose connect is in flight; followed by the bit words
 	unsigned *vbits, *ubits;
 };
 
@@ -73,17 +78,27 @@ __global__ void __launch_bounds__(128) k_pipe_init(TerrainView Tv, PipeState S, 
 	S.root_valid[2 * q] = is_valid_state_auto<M>(Tv, pose6(s), GBP_STANCE, c) ? 1 : 0;
 	S.root_valid[2 * q + 1] = is_valid_state_auto<M>(Tv, pose6(g), GBP_STANCE, c) ? 1 : 0;
 	S.status[q] = 0; S.it[q] = 0; S.half[q] = 0; S.iters[q] = max_iters; S.pair_checks[q] = 0; S.nn_queries[q] = 0;
-	S.rs_valid[q] = 0; S.rs_base[q] = -1;
+	S.rs_valid[q] = 0; S.rs_base[q] = -1; S.busy_until[q] = 0;
 }
 
 template <typename M>
-__global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int64_t Q, uint64_t seed, uint64_t query0,
-													gbp_plan_params P) {
+__global__ void __launch_bounds__(128, 8) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int64_t Q, uint64_t seed, uint64_t query0,
+													gbp_plan_params P, int round) {
 	const int lane = threadIdx.x & 31;
 	const int64_t q = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
-	if (q >= Q || S.status[q] != 0) return;
+	if (q >= Q) return;
+	// the per-query words are loaded together (one round trip to HBM, not one per word)
+	const int status = S.status[q];
 	int it = S.it[q], half = S.half[q];
 	const int na = S.na[q], nb = S.nb[q];
+	long long rs_base = S.rs_base[q];
+	unsigned rs_valid = S.rs_valid[q];
+	const int busy_until = S.busy_until[q];
+	if (status != 0) return;
+	if (round < busy_until) {  // its connect (k_pipe_connect on the second stream) has this round to finish
+		if (lane == 0) atomicAdd(G.count + 1, 1);
+		return;
+	}
 	while (true) {
 		if (it >= P.max_iters) {  // budget used up
 			if (lane == 0) { S.status[q] = 2; S.iters[q] = P.max_iters; }
@@ -94,7 +109,7 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 			return;
 		}
 		const long long cell = 2ll * it + half, base = cell & ~31ll;
-		if (S.rs_base[q] != base) {  // STATE cells base .. base + 31: lane L draws and checks cell base + L
+		if (rs_base != base) {  // STATE cells base .. base + 31: lane L draws and checks cell base + L
 			double rs[8];
 			sample_state<M>(Tv, seed, query0 + (uint64_t) q, (uint64_t) base + (uint64_t) lane, false, 0.0, false, nullptr, nullptr, rs);
 			Counters c = {0, 0, 0, 0};
@@ -103,9 +118,10 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 #pragma unroll
 			for (int d = 0; d < 4; ++d) o[d] = make_double2(rs[2 * d], rs[2 * d + 1]);
 			if (lane == 0) { S.rs_valid[q] = valid; S.rs_base[q] = base; }
+			rs_valid = valid; rs_base = base;
 			__syncwarp();
 		}
-		const unsigned mask = S.rs_valid[q] >> (unsigned) (cell & 31ll);
+		const unsigned mask = rs_valid >> (unsigned) (cell & 31ll);
 		const long long next = mask ? cell + (__ffs(mask) - 1) : base + 32;  // invalid random states are skipped (rrt_connect.cpp:254)
 		it = (int) (next >> 1); half = (int) (next & 1);
 		if (mask) break;
@@ -115,6 +131,8 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 		return;
 	}
 	const long long cell = 2ll * it + half;
+	int seg = 0;
+	if (lane == 0) seg = atomicAdd(G.count, 1);  // issued here: its round trip overlaps the nearest-neighbour loads
 	double s_rand[8];
 	{
 		const double2 *r = reinterpret_cast<const double2 *>(S.rs + ((size_t) q * 32 + (size_t) (cell & 31ll)) * 8);
@@ -126,11 +144,16 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 	const int near = warp_nearest(Tx.t, nx, s_rand, lane);  // rrt.cpp:78
 	double s_near[8], nn[3], R[9];
 	tree_get(Tx.t, near, s_near);
-	unsigned fl = 0;
-	surface_normal(Tv, s_rand[0], s_rand[1], nn, fl);  // rrt.cpp:25 — at the TARGET sample
-	grf_rotation(nn, R);
-	int seg = 0;
-	if (lane == 0) seg = atomicAdd(G.count, 1);
+	if (Tv.nz3 || Tv.nz3d) {
+		unsigned fl = 0;
+		surface_normal(Tv, s_rand[0], s_rand[1], nn, fl);  // rrt.cpp:25 — at the TARGET sample
+		grf_rotation(nn, R);
+	} else {
+		// a terrain without normal layers has dx = dy = 0 everywhere (fast_terrain_map.cpp:68-72): the interpolated normal is
+		// (0, 0, ~1), its cross product with +z is exactly zero and rotate_grf takes the identity (planning_utils.cpp:213)
+#pragma unroll
+		for (int d = 0; d < 9; ++d) R[d] = (d == 0 || d == 4 || d == 8) ? 1.0 : 0.0;
+	}
 	seg = __shfl_sync(FULL, seg, 0);
 	double *row = G.rows + (size_t) seg * PIPE_ROW;
 	if (lane < 8) row[lane] = s_near[lane];
@@ -244,11 +267,23 @@ __device__ __forceinline__ unsigned pipe_bits(const unsigned *__restrict__ words
 }
 
 template <typename M>
-__global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, uint64_t seed, uint64_t query0, gbp_plan_params P) {
+__global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, PipeConnects C, int64_t Q, uint64_t seed,
+													 uint64_t query0, gbp_plan_params P, int round) {
 	const int lane = threadIdx.x & 31;
 	const int seg = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5);
 	if (seg >= *G.count) return;
 	const int q = G.q[seg], K = P.k_candidates;
+	unsigned vmask = pipe_bits(G.vbits, seg * K, K);
+	const unsigned umask = pipe_bits(G.ubits, seg * K, K);
+	if ((vmask | umask) == 0) {  // every candidate invalid (the usual case): TRAPPED, move on to the next half
+		if (lane == 0) {
+			S.pair_checks[q] += K;
+			S.nn_queries[q] += 1;
+			if (((int) G.flags[seg] & 1) == GBP_FORWARD) S.half[q] = 1;
+			else { S.it[q] += 1; S.half[q] = 0; }
+		}
+		return;
+	}
 	const double *row = G.rows + (size_t) seg * PIPE_ROW;
 	double s_near[8], R[9], s_rand[8];
 #pragma unroll
@@ -259,8 +294,6 @@ __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeStat
 	const uint64_t stream = query0 + (uint64_t) q, idx0 = G.idx0[seg];
 	const bool dirs = P.action_direction_sampling != 0;
 	const double *a_from = dir == GBP_FORWARD ? s_near : s_rand, *a_to = dir == GBP_FORWARD ? s_rand : s_near;
-	unsigned vmask = pipe_bits(G.vbits, seg * K, K);
-	const unsigned umask = pipe_bits(G.ubits, seg * K, K);
 	if (umask) {  // candidates the mixed-precision walk could not decide: the exact fp64 walk, one lane each
 		bool ok = false;
 		if (lane < K && ((umask >> lane) & 1u)) {
@@ -271,7 +304,8 @@ __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeStat
 		}
 		vmask |= __ballot_sync(FULL, ok);
 	}
-	long long pair_checks, nn_queries = 1;
+	long long pair_checks;
+	const long long nn_queries = 1;
 	bool found = false;
 	double sn[8], a[10];
 	const double best0 = state_distance(s_near, s_rand);
@@ -309,24 +343,51 @@ __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeStat
 			for (int d = 0; d < 10; ++d) a[d] = __shfl_sync(FULL, my_a[d], bj);
 		}
 	}
-	int na = S.na[q], nb = S.nb[q];
-	bool solved = false;
-	if (found) {
-		PlanTree Ta = arena_tree(A, q, 0, S.na + q), Tb = arena_tree(A, q, 1, S.nb + q);
-		PlanTree &Tx = half == 0 ? Ta : Tb, &Ty = half == 0 ? Tb : Ta;
-		int &ny = half == 0 ? nb : na;
-		if (lane == 0) plan_push(Tx, near, sn, a);  // rrt.cpp:87-92
-		__syncwarp();
-		++nn_queries;
-		solved = warp_connect<M>(Tv, Ty, ny, sn, dir == GBP_FORWARD ? GBP_REVERSE : GBP_FORWARD, P, lane, pair_checks) == GBP_REACHED;
+	if (found && lane == 0) {
+		PlanTree Tx = arena_tree(A, q, half, (half == 0 ? S.na : S.nb) + q);
+		plan_push(Tx, near, sn, a);  // rrt.cpp:87-92
+		// connect from the other tree (rrt_connect.cpp:261, :296) runs in k_pipe_connect on the second stream while the next
+		// round works on the other queries: this one sits that round out
+		const int par = round & 1;
+		C.entry[(size_t) par * Q + atomicAdd(C.count + par, 1)] = q * 2 + half;
+		S.busy_until[q] = round + 2;
 	}
 	if (lane == 0) {
 		S.pair_checks[q] += pair_checks;
 		S.nn_queries[q] += nn_queries;
-		const int it = S.it[q];
-		if (solved) { S.status[q] = 1; S.iters[q] = it + 1; }
-		else if (half == 0) S.half[q] = 1;
-		else { S.it[q] = it + 1; S.half[q] = 0; }
+		if (!found) {  // TRAPPED: on to the next half (a query that extended is moved on by k_pipe_connect)
+			if (half == 0) S.half[q] = 1;
+			else { S.it[q] += 1; S.half[q] = 0; }
+		}
+	}
+}
+
+// connect (rrt_connect.cpp:98-120) for the queries whose tree grew in round `round`: warps pull requests from the list
+template <typename M>
+__global__ void __launch_bounds__(128, 4) k_pipe_connect(TerrainView Tv, PipeState S, PlanArena A, PipeConnects C, int64_t Q, gbp_plan_params P, int round) {
+	const int lane = threadIdx.x & 31;
+	const int par = round & 1, n = C.count[par];
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int e = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5); e < n; e += warps) {
+		const int code = C.entry[(size_t) par * Q + e], q = code >> 1, half = code & 1;
+		PlanTree Ta = arena_tree(A, q, 0, S.na + q), Tb = arena_tree(A, q, 1, S.nb + q);
+		PlanTree &Tx = half == 0 ? Ta : Tb, &Ty = half == 0 ? Tb : Ta;
+		int na = S.na[q], nb = S.nb[q];
+		const int nx = half == 0 ? na : nb;
+		int &ny = half == 0 ? nb : na;
+		double s_new[8];
+		tree_get(Tx.t, nx - 1, s_new);
+		long long pair_checks = 0;
+		const bool solved = warp_connect<M>(Tv, Ty, ny, s_new, half == 0 ? GBP_REVERSE : GBP_FORWARD, P, lane, pair_checks) == GBP_REACHED;
+		if (lane == 0) {
+			S.pair_checks[q] += pair_checks;
+			S.nn_queries[q] += 1;
+			const int it = S.it[q];
+			if (solved) { S.status[q] = 1; S.iters[q] = it + 1; }
+			else if (half == 0) S.half[q] = 1;
+			else { S.it[q] = it + 1; S.half[q] = 0; }
+		}
+		__syncwarp();
 	}
 }
 
@@ -368,7 +429,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	const size_t bit_words = (Q * K + 31) / 32 + 2;
 	const size_t n_doubles = per * (8 + 10 + 1 + 1) + Q * 32 * 8 + Q * PIPE_ROW + (size_t) fin_slots * 2 * cap * 18;
 	const size_t n_ll = Q * 4 + 2;  // pair_checks, nn_queries, rs_base, idx0, finish counter
-	const size_t n_ints = per * 3 + Q * 9 + 4 + 2 * bit_words;
+	const size_t n_ints = per * 3 + Q * 12 + 8 + 2 * bit_words;
 	const size_t need = n_doubles * 8 + n_ll * 8 + n_ints * 4 + Q * 3 + 64;
 	void *mem = nullptr;
 	cudaError_t e;
@@ -376,6 +437,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	PlanArena A = {}, Sc = {};
 	PipeState S;
 	PipeSegs G;
+	PipeConnects C;
 	A.cap = Sc.cap = P.max_vertices;
 	double *dp = (double *) mem;
 	A.v = dp; dp += per * 8;
@@ -403,39 +465,66 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	S.half = ip; ip += Q;
 	S.iters = ip; ip += Q;
 	S.rs_valid = (unsigned *) ip; ip += Q;
+	S.busy_until = ip; ip += Q;
 	G.q = ip; ip += Q;
 	G.near = ip; ip += Q;
-	G.count = ip; ip += 4;  // the per-round words: count, then the two bit arrays (one memset per round)
+	C.entry = ip; ip += 2 * Q;
+	C.count = ip; ip += 4;
+	G.count = ip; ip += 4;  // the per-round words: counts, then the two bit arrays (one memset per round)
 	G.vbits = (unsigned *) ip; ip += bit_words;
 	G.ubits = (unsigned *) ip; ip += bit_words;
 	unsigned char *bp = (unsigned char *) ip;
 	S.root_valid = bp; bp += 2 * Q;
 	G.flags = bp; bp += Q;
 	const size_t round_bytes = (4 + 2 * bit_words) * 4;
-	static thread_local int *h_count = nullptr;  // pinned
-	if (!h_count && (e = cudaHostAlloc((void **) &h_count, sizeof(int), cudaHostAllocDefault)) != cudaSuccess) {
-		cudaFreeAsync(mem, st);
-		err = std::string("pipelined planner: ") + cudaGetErrorString(e);
-		return GBP_E_CUDA;
+	// host-side resources of the calling thread: a pinned word for the running count, the second stream and its events
+	static thread_local int *h_count = nullptr;
+	static thread_local cudaStream_t sb = nullptr;
+	static thread_local cudaEvent_t ev_sel[2] = {nullptr, nullptr}, ev_con[2] = {nullptr, nullptr};
+	if (!h_count) {
+		e = cudaHostAlloc((void **) &h_count, 2 * sizeof(int), cudaHostAllocDefault);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
+		for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+			e = cudaEventCreateWithFlags(&ev_sel[k], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_con[k], cudaEventDisableTiming);
+		}
+		if (e != cudaSuccess) {
+			if (h_count) { cudaFreeHost(h_count); h_count = nullptr; }
+			cudaFreeAsync(mem, st);
+			err = std::string("pipelined planner: ") + cudaGetErrorString(e);
+			return GBP_E_CUDA;
+		}
 	}
 	const unsigned warp_blocks = (unsigned) ((Q + 3) / 4);
 	const unsigned walk_grid = (unsigned) sms * GBP_WALK_CTAS;
 	k_pipe_init<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, nq, starts, goals, P.max_iters);
-	// a round runs one extend attempt of every running query; a query needs at most 2 * max_iters of them (every random
-	// state valid).  The number of running queries is read back every 32 rounds to stop launching once all are done.
-	const int max_rounds = 2 * P.max_iters + 1;
-	for (int round = 0; round < max_rounds; ++round) {
+	cudaMemsetAsync(C.count, 0, 4 * sizeof(int), st);
+	// A round runs one extend attempt of every running query; a query needs at most 2 * max_iters of them (every random state
+	// valid) plus one idle round per connect.  The number of running queries is read back every 32 rounds to stop launching
+	// once all are done.  Stream `st`: memset, prep, walk, select of round r; stream `sb`: connect of round r, which overlaps
+	// round r + 1 and must be over before round r + 2 (the queries it works on sit round r + 1 out).
+	const int max_rounds = 3 * P.max_iters + 2;
+	int round = 0;
+	for (; round < max_rounds; ++round) {
+		const int par = round & 1;
+		if (round >= 2) cudaStreamWaitEvent(st, ev_con[par], 0);  // connect of round - 2: its queries and its request list are free again
 		cudaMemsetAsync(G.count, 0, round_bytes, st);
-		k_pipe_prep<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, G, nq, seed, query0, P);
+		cudaMemsetAsync(C.count + par, 0, sizeof(int), st);
+		k_pipe_prep<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, G, nq, seed, query0, P, round);
 		if (Tv.ztex) k_walk_seg<true><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
 		else k_walk_seg<false><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
-		k_pipe_select<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, G, seed, query0, P);
+		k_pipe_select<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, G, C, nq, seed, query0, P, round);
+		cudaEventRecord(ev_sel[par], st);
+		cudaStreamWaitEvent(sb, ev_sel[par], 0);
+		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sb>>>(Tv, S, A, C, nq, P, round);
+		cudaEventRecord(ev_con[par], sb);
 		if ((round & 31) == 31) {
-			cudaMemcpyAsync(h_count, G.count, sizeof(int), cudaMemcpyDeviceToHost, st);
+			cudaMemcpyAsync(h_count, G.count, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
 			if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
-			if (*h_count == 0) break;
+			if (h_count[0] + h_count[1] == 0) { ++round; break; }
 		}
 	}
+	for (int k = 0; k < 2 && k < round; ++k) cudaStreamWaitEvent(st, ev_con[k], 0);  // the last connects precede the statistics
 	cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st);
 	const int64_t fin_warps = (int64_t) Q < fin_slots ? (int64_t) ((Q + 3) / 4 * 4) : fin_slots;
 	k_pipe_finish<M><<<(unsigned) (fin_warps / 4), 128, 0, st>>>(Tv, S, A, Sc, nq, P, next_query, stats, path_states, path_actions, path_cap, dump);

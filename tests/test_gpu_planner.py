@@ -167,7 +167,9 @@ def test_stepped_form_is_identical(gbp, monkeypatch):
     assert a["solved"].sum() >= 5
     for k in a.dtype.names:
         assert np.array_equal(a[k], b[k]), k
-    assert np.array_equal(pa_s, pb_s) and np.array_equal(pa_a, pb_a)
+    for i in range(len(S)):  # rows beyond a path's length are not written
+        n = int(a["path_states"][i])
+        assert np.array_equal(pa_s[i, :n], pb_s[i, :n]) and np.array_equal(pa_a[i, :max(n - 1, 0)], pb_a[i, :max(n - 1, 0)])
     for (xa, xb), (ya, yb) in zip(ta, tb):
         for k in xa:
             assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), k
