@@ -59,8 +59,9 @@ struct PipeSegs {  // the round's dense segment list
 	int *q, *near;             // query, id of s_near in the tree being extended
 	unsigned char *flags;      // bit 0: direction, bit 1: s_near is known valid
 	unsigned long long *idx0;  // ACTION cell of candidate 0: cell * K
-	int *count;                // [0] segments of this round, [1] running queries whose connect is in flight; followed by the bit words
+	int *count;                // [0] segments of this round, [1] running queries whose connect is in flight, [2] heavy segments; then the bit words
 	unsigned *vbits, *ubits;
+	int *heavy;                // segments with a valid or an undecided candidate (count in count[2])
 };
 
 template <typename M>
@@ -266,24 +267,30 @@ __device__ __forceinline__ unsigned pipe_bits(const unsigned *__restrict__ words
 	return (unsigned) (two >> (first & 31)) & (count >= 32 ? 0xffffffffu : ((1u << count) - 1u));
 }
 
+// triage, thread per segment: a segment whose candidates are all invalid (98 % of them) is TRAPPED — the query moves on to
+// its next half here; the others go to the heavy list
+static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSegs G, int K) {
+	const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+	if (seg >= G.count[0]) return;
+	const unsigned vmask = pipe_bits(G.vbits, seg * K, K), umask = pipe_bits(G.ubits, seg * K, K);
+	if (vmask | umask) { G.heavy[atomicAdd(G.count + 2, 1)] = seg; return; }
+	const int q = G.q[seg];
+	S.pair_checks[q] += K;
+	S.nn_queries[q] += 1;
+	if (((int) G.flags[seg] & 1) == GBP_FORWARD) S.half[q] = 1;
+	else { S.it[q] += 1; S.half[q] = 0; }
+}
+
 template <typename M>
 __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, PipeConnects C, int64_t Q, uint64_t seed,
 													 uint64_t query0, gbp_plan_params P, int round) {
 	const int lane = threadIdx.x & 31;
-	const int seg = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5);
-	if (seg >= *G.count) return;
+	const int nheavy = G.count[2], warps = (gridDim.x * blockDim.x) >> 5;
+	for (int h = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5); h < nheavy; h += warps) {
+	const int seg = G.heavy[h];
 	const int q = G.q[seg], K = P.k_candidates;
 	unsigned vmask = pipe_bits(G.vbits, seg * K, K);
 	const unsigned umask = pipe_bits(G.ubits, seg * K, K);
-	if ((vmask | umask) == 0) {  // every candidate invalid (the usual case): TRAPPED, move on to the next half
-		if (lane == 0) {
-			S.pair_checks[q] += K;
-			S.nn_queries[q] += 1;
-			if (((int) G.flags[seg] & 1) == GBP_FORWARD) S.half[q] = 1;
-			else { S.it[q] += 1; S.half[q] = 0; }
-		}
-		return;
-	}
 	const double *row = G.rows + (size_t) seg * PIPE_ROW;
 	double s_near[8], R[9], s_rand[8];
 #pragma unroll
@@ -294,15 +301,16 @@ __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeStat
 	const uint64_t stream = query0 + (uint64_t) q, idx0 = G.idx0[seg];
 	const bool dirs = P.action_direction_sampling != 0;
 	const double *a_from = dir == GBP_FORWARD ? s_near : s_rand, *a_to = dir == GBP_FORWARD ? s_rand : s_near;
-	if (umask) {  // candidates the mixed-precision walk could not decide: the exact fp64 walk, one lane each
-		bool ok = false;
-		if (lane < K && ((umask >> lane) & 1u)) {
-			double a[10], sn[8], tn;
-			sample_action(seed, stream, idx0 + (uint64_t) lane, R, dirs, P.action_direction_threshold, a_from, a_to, a);
-			Counters c = {0, 0, 0, 0};
-			ok = validate_pair_seq<M>(Tv, s_near, a, dir, false, sn, tn, c);
-		}
-		vmask |= __ballot_sync(FULL, ok);
+	// first-valid selection only needs the undecided candidates that come before the first valid one
+	const unsigned um0 = (!P.best_of_k && vmask) ? (umask & ((vmask & (0u - vmask)) - 1u)) : umask;
+	for (unsigned um = um0; um; um &= um - 1) {
+		// a candidate the mixed-precision walk could not decide: the pair check again with the exact evaluators, its
+		// sub-states spread over the lanes (validate_pair_warp: same verdict as the sequential walk)
+		const int j = __ffs(um) - 1;
+		double a[10], sn[8], tn;
+		sample_action(seed, stream, idx0 + (uint64_t) j, R, dirs, P.action_direction_threshold, a_from, a_to, a);
+		Counters c = {0, 0, 0, 0};
+		if (validate_pair_warp<M>(Tv, s_near, a, dir, sn, tn, c)) vmask |= 1u << j;
 	}
 	long long pair_checks;
 	const long long nn_queries = 1;
@@ -359,6 +367,8 @@ __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeStat
 			if (half == 0) S.half[q] = 1;
 			else { S.it[q] += 1; S.half[q] = 0; }
 		}
+	}
+	__syncwarp();
 	}
 }
 
@@ -429,7 +439,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	const size_t bit_words = (Q * K + 31) / 32 + 2;
 	const size_t n_doubles = per * (8 + 10 + 1 + 1) + Q * 32 * 8 + Q * PIPE_ROW + (size_t) fin_slots * 2 * cap * 18;
 	const size_t n_ll = Q * 4 + 2;  // pair_checks, nn_queries, rs_base, idx0, finish counter
-	const size_t n_ints = per * 3 + Q * 12 + 8 + 2 * bit_words;
+	const size_t n_ints = per * 3 + Q * 13 + 8 + 2 * bit_words;
 	const size_t need = n_doubles * 8 + n_ll * 8 + n_ints * 4 + Q * 3 + 64;
 	void *mem = nullptr;
 	cudaError_t e;
@@ -468,6 +478,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	S.busy_until = ip; ip += Q;
 	G.q = ip; ip += Q;
 	G.near = ip; ip += Q;
+	G.heavy = ip; ip += Q;
 	C.entry = ip; ip += 2 * Q;
 	C.count = ip; ip += 4;
 	G.count = ip; ip += 4;  // the per-round words: counts, then the two bit arrays (one memset per round)
@@ -513,7 +524,8 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 		k_pipe_prep<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, G, nq, seed, query0, P, round);
 		if (Tv.ztex) k_walk_seg<true><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
 		else k_walk_seg<false><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
-		k_pipe_select<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, G, C, nq, seed, query0, P, round);
+		k_pipe_triage<<<(unsigned) ((Q + 255) / 256), 256, 0, st>>>(S, G, P.k_candidates);
+		k_pipe_select<M><<<(unsigned) sms * 4, 128, 0, st>>>(Tv, S, A, G, C, nq, seed, query0, P, round);
 		cudaEventRecord(ev_sel[par], st);
 		cudaStreamWaitEvent(sb, ev_sel[par], 0);
 		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sb>>>(Tv, S, A, C, nq, P, round);
