@@ -533,10 +533,13 @@ __device__ __forceinline__ bool is_valid_state_fast(const TerrainView &T, const 
 // SMALL offset from it (body rotation, the 9 leg / corner / belly offsets in cell units, the bilinear
 // increment over the cell's first corner) is fp32 on the full-rate FMA pipe, and each clearance margin is
 // assembled in fp64 as (z - f11) - H + (offset - increment).  Error budget < 1e-6 m; any sub-state with a
-// margin below MIXED_MARGIN (1e-5 m), a probe within MIXED_EDGE (2e-5 cells) of a grid line, or a probe
+// margin below MIXED_MARGIN (1e-5 m) or a probe
 // outside the grid is NOT decided here: it is re-evaluated by is_valid_state_fast (fp64, 1e-11 m guard).
 constexpr double MIXED_MARGIN = 1e-5;
-constexpr float MIXED_EDGE = 2e-5f;
+// No guard is needed around grid lines here: the bilinear surface is continuous across a cell edge, so a probe that the fp32
+// cell arithmetic puts in the neighbour of the reference's cell gets the height of the same surface extended by < 1e-6 cells
+// (< 1e-8 m for any slope the |dz| <= 4 m per cell bound admits) — far inside MIXED_MARGIN; and these maps hold no NaN cell,
+// the one thing a cell choice could change.
 
 __device__ __forceinline__ void sincosf_small(float x, float &sn, float &cs) {  // |x| < 1, abs error < 3e-8
 	const float z = x * x;
@@ -573,6 +576,7 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 	const double gx = (s.x - T.x0) * T.inv_dx, gy = (s.y - T.y0) * T.inv_dy;
 	const int ixc = (int) gx, iyc = (int) gy;
 	bool ok = (gx >= (double) T.border) && (gy >= (double) T.border) && (ixc <= T.nx - 2 - T.border) && (iyc <= T.ny - 2 - T.border);
+	ok = ok && (s.z == s.z) && (pitch_bad || fabs(s.pitch) < P_MAX);  // a NaN pose is not decided here (NaN x, y, dx, dy fail the tests above / below)
 	const float fux = (float) (gx - (double) ixc), fuy = (float) (gy - (double) iyc);
 	// body orientation in fp32
 	const float fdx = (float) s.dx, fdy = (float) s.dy, fr2 = fdx * fdx + fdy * fdy;
@@ -605,12 +609,11 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 	const float tbx = (float) (iyc + 1), tby = (float) (ixc + 1);  // texel-footprint centre of the centre cell (exact: < 2^24)
 	int cell[9];
 	float tx[9], ty[9];
-	float ux[9], uy[9], emax = 0.0f;  // emax: largest |u - 0.5| over all probes; u within MIXED_EDGE of a grid line <=> emax > 0.5 - MIXED_EDGE
+	float ux[9], uy[9];
 #pragma unroll
 	for (int p = 0; p < 9; ++p) {
 		const float pxf = fux + ox[p], pyf = fuy + oy[p], flx = floorf(pxf), fly = floorf(pyf);
 		ux[p] = pxf - flx; uy[p] = pyf - fly;
-		emax = fmaxf(emax, fmaxf(fabsf(ux[p] - 0.5f), fabsf(uy[p] - 0.5f)));
 		if (TEX) { tx[p] = tbx + fly; ty[p] = tby + flx; }  // clamp addressing: a lane that is not `ok` reads some cell and is discarded below
 		else cell[p] = ok ? base + (int) flx * T.ny + (int) fly : 0;
 	}
@@ -650,7 +653,7 @@ __device__ __forceinline__ bool is_valid_state_mixed(const TerrainView &T, const
 		bad |= ((m[2 * k + 1] < 0.0) || (stance && m[2 * k] > 0.0)) ? (1u << k) : 0u;
 	}
 	near = near || (fabs(m[8]) < MIXED_MARGIN);
-	if (!ok || near || hard_near || !(emax <= 0.5f - MIXED_EDGE)) return false;
+	if (!ok || near || hard_near) return false;
 	const bool alive0 = !(pitch_bad || speed_bad);
 	const int corners = alive0 ? min(__ffs(bad | 16u), 4) : 0;  // corners the reference evaluates before it returns
 	const bool all_ok = alive0 && bad == 0;

@@ -47,6 +47,7 @@ struct PipeState {  // per query
 	double *rs;                // [Q][32][8] the current batch of 32 STATE cells
 	unsigned *rs_valid;        // isValidState(STANCE) of the batch
 	long long *rs_base;        // first cell of the batch (-1: none yet)
+	long long *rs_want;        // first cell of the batch k_pipe_batch is asked to draw
 	unsigned char *root_valid; // [Q][2] isValidState(root, STANCE) of the start-side / goal-side tree
 	int *busy_until;           // [Q] first round that may touch the query again (its connect runs on the second stream meanwhile)
 };
@@ -79,61 +80,82 @@ __global__ void __launch_bounds__(128) k_pipe_init(TerrainView Tv, PipeState S, 
 	S.root_valid[2 * q] = is_valid_state_auto<M>(Tv, pose6(s), GBP_STANCE, c) ? 1 : 0;
 	S.root_valid[2 * q + 1] = is_valid_state_auto<M>(Tv, pose6(g), GBP_STANCE, c) ? 1 : 0;
 	S.status[q] = 0; S.it[q] = 0; S.half[q] = 0; S.iters[q] = max_iters; S.pair_checks[q] = 0; S.nn_queries[q] = 0;
-	S.rs_valid[q] = 0; S.rs_base[q] = -1; S.busy_until[q] = 0;
+	S.rs_valid[q] = 0; S.rs_base[q] = -1; S.rs_want[q] = 0; S.busy_until[q] = 0;
 }
 
+// STATE cells base .. base + 31 of the queries that ran out of random states: warp per listed query, lane L draws cell
+// base + L and checks it (their validity does not depend on the trees).  Runs on the second stream while the round's walk runs.
 template <typename M>
-__global__ void __launch_bounds__(128, 8) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int64_t Q, uint64_t seed, uint64_t query0,
-													gbp_plan_params P, int round) {
+__global__ void __launch_bounds__(128) k_pipe_batch(TerrainView Tv, PipeState S, const int *__restrict__ list, const int *__restrict__ count, uint64_t seed,
+													 uint64_t query0) {
 	const int lane = threadIdx.x & 31;
-	const int64_t q = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
-	if (q >= Q) return;
-	// the per-query words are loaded together (one round trip to HBM, not one per word)
-	const int status = S.status[q];
-	int it = S.it[q], half = S.half[q];
-	const int na = S.na[q], nb = S.nb[q];
-	long long rs_base = S.rs_base[q];
-	unsigned rs_valid = S.rs_valid[q];
-	const int busy_until = S.busy_until[q];
-	if (status != 0) return;
-	if (round < busy_until) {  // its connect (k_pipe_connect on the second stream) has this round to finish
-		if (lane == 0) atomicAdd(G.count + 1, 1);
-		return;
-	}
-	while (true) {
-		if (it >= P.max_iters) {  // budget used up
-			if (lane == 0) { S.status[q] = 2; S.iters[q] = P.max_iters; }
-			return;
-		}
-		if (na >= A.cap || nb >= A.cap) {  // a tree is full at the start of a half: the query stops unsolved
-			if (lane == 0) { S.status[q] = 2; S.iters[q] = it + 1; }
-			return;
-		}
-		const long long cell = 2ll * it + half, base = cell & ~31ll;
-		if (rs_base != base) {  // STATE cells base .. base + 31: lane L draws and checks cell base + L
-			double rs[8];
-			sample_state<M>(Tv, seed, query0 + (uint64_t) q, (uint64_t) base + (uint64_t) lane, false, 0.0, false, nullptr, nullptr, rs);
-			Counters c = {0, 0, 0, 0};
-			const unsigned valid = __ballot_sync(FULL, is_valid_state_auto<M>(Tv, pose6(rs), GBP_STANCE, c));
-			double2 *o = reinterpret_cast<double2 *>(S.rs + ((size_t) q * 32 + lane) * 8);
+	const int n = *count, warps = (gridDim.x * blockDim.x) >> 5;
+	for (int e = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5); e < n; e += warps) {
+		const int q = list[e];
+		const long long base = S.rs_want[q];
+		double rs[8];
+		sample_state<M>(Tv, seed, query0 + (uint64_t) q, (uint64_t) base + (uint64_t) lane, false, 0.0, false, nullptr, nullptr, rs);
+		Counters c = {0, 0, 0, 0};
+		const unsigned valid = __ballot_sync(FULL, is_valid_state_auto<M>(Tv, pose6(rs), GBP_STANCE, c));
+		double2 *o = reinterpret_cast<double2 *>(S.rs + ((size_t) q * 32 + lane) * 8);
 #pragma unroll
-			for (int d = 0; d < 4; ++d) o[d] = make_double2(rs[2 * d], rs[2 * d + 1]);
-			if (lane == 0) { S.rs_valid[q] = valid; S.rs_base[q] = base; }
-			rs_valid = valid; rs_base = base;
-			__syncwarp();
+		for (int d = 0; d < 4; ++d) o[d] = make_double2(rs[2 * d], rs[2 * d + 1]);
+		if (lane == 0) { S.rs_valid[q] = valid; S.rs_base[q] = base; }
+	}
+}
+
+// THREAD per query: the control flow of a half-iteration up to newConfig's candidates — budget and capacity checks, the next
+// valid random state of the query (invalid ones are skipped, rrt_connect.cpp:254), the nearest neighbour (rrt.cpp:78, a
+// sequential scan of the query's tree: a few dozen vertices), the surface normal at the target (rrt.cpp:25) and its GRF
+// rotation — and the segment row.  A warp per query spent its time on dependent HBM round trips (65 k warps x 3-4 round
+// trips, 100 us per round); 32 queries per warp issue those loads side by side.
+template <typename M>
+__global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int *__restrict__ batch_list,
+													int *__restrict__ batch_count, int64_t Q, gbp_plan_params P, int round) {
+	const int lane = threadIdx.x & 31;
+	const int64_t q = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	bool emit = false;
+	int it = 0, half = 0, na = 0, nb = 0;
+	long long cell = 0;
+	if (q < Q) {
+		const int status = S.status[q];
+		it = S.it[q]; half = S.half[q]; na = S.na[q]; nb = S.nb[q];
+		const long long rs_base = S.rs_base[q];
+		const unsigned rs_valid = S.rs_valid[q];
+		const int busy_until = S.busy_until[q];
+		if (status == 0 && round < busy_until) atomicAdd(G.count + 1, 1);  // its connect or its next batch of random states is in flight
+		else if (status == 0) {
+			if (it >= P.max_iters) { S.status[q] = 2; S.iters[q] = P.max_iters; }  // budget used up
+			else if (na >= A.cap || nb >= A.cap) { S.status[q] = 2; S.iters[q] = it + 1; }  // a tree is full at the start of a half
+			else {
+				cell = 2ll * it + half;
+				const long long base = cell & ~31ll;
+				unsigned mask = rs_base == base ? rs_valid >> (unsigned) (cell & 31ll) : 0u;
+				if (rs_base == base && mask == 0) {  // no valid state left in this batch: the query is at the first cell of the next one
+					cell = base + 32; it = (int) (cell >> 1); half = (int) (cell & 1);
+					S.it[q] = it; S.half[q] = half;
+				}
+				if (mask) {
+					cell += __ffs(mask) - 1;  // invalid random states are skipped (rrt_connect.cpp:254)
+					it = (int) (cell >> 1); half = (int) (cell & 1);
+					if (it >= P.max_iters) { S.status[q] = 2; S.iters[q] = P.max_iters; }
+					else emit = true;
+				} else if (it >= P.max_iters) { S.status[q] = 2; S.iters[q] = P.max_iters; }
+				else {  // the batch holding `cell` is drawn by k_pipe_batch while this round's walk runs; the query sits the round out
+					S.rs_want[q] = cell & ~31ll;
+					S.busy_until[q] = round + 1;
+					batch_list[atomicAdd(batch_count, 1)] = (int) q;
+					atomicAdd(G.count + 1, 1);
+				}
+			}
 		}
-		const unsigned mask = rs_valid >> (unsigned) (cell & 31ll);
-		const long long next = mask ? cell + (__ffs(mask) - 1) : base + 32;  // invalid random states are skipped (rrt_connect.cpp:254)
-		it = (int) (next >> 1); half = (int) (next & 1);
-		if (mask) break;
 	}
-	if (it >= P.max_iters) {
-		if (lane == 0) { S.status[q] = 2; S.iters[q] = P.max_iters; }
-		return;
-	}
-	const long long cell = 2ll * it + half;
+	// dense segment numbers: one atomic per warp
+	const unsigned em = __ballot_sync(FULL, emit);
 	int seg = 0;
-	if (lane == 0) seg = atomicAdd(G.count, 1);  // issued here: its round trip overlaps the nearest-neighbour loads
+	if (lane == 0 && em) seg = atomicAdd(G.count, __popc(em));
+	seg = __shfl_sync(FULL, seg, 0) + __popc(em & ((1u << lane) - 1u));
+	if (!emit) return;
 	double s_rand[8];
 	{
 		const double2 *r = reinterpret_cast<const double2 *>(S.rs + ((size_t) q * 32 + (size_t) (cell & 31ll)) * 8);
@@ -142,10 +164,28 @@ __global__ void __launch_bounds__(128, 8) k_pipe_prep(TerrainView Tv, PipeState 
 	}
 	PlanTree Tx = arena_tree(A, (int) q, half, (half == 0 ? S.na : S.nb) + q);
 	const int nx = half == 0 ? na : nb;
-	const int near = warp_nearest(Tx.t, nx, s_rand, lane);  // rrt.cpp:78
-	double s_near[8], nn[3], R[9];
-	tree_get(Tx.t, near, s_near);
+	// getNearestNeighbor (planner_class.cpp:185-200): ascending id with a strict < keeps the lowest id among equal distances
+	double bd = INFINITY, s_near[8];
+	int near = 0;
+#pragma unroll
+	for (int d = 0; d < 8; ++d) s_near[d] = Tx.t.v[(size_t) d * Tx.t.cap];
+#pragma unroll 2
+	for (int j = 0; j < nx; ++j) {
+		double v[8], sum = 0;
+#pragma unroll
+		for (int d = 0; d < 8; ++d) v[d] = Tx.t.v[(size_t) d * Tx.t.cap + j];
+#pragma unroll
+		for (int d = 0; d < 8; ++d) sum = sum + 1.0 * (v[d] - s_rand[d]) * (v[d] - s_rand[d]);
+		const double dj = sqrt(sum);
+		if (dj < bd) {
+			bd = dj; near = j;
+#pragma unroll
+			for (int d = 0; d < 8; ++d) s_near[d] = v[d];
+		}
+	}
+	double R[9];
 	if (Tv.nz3 || Tv.nz3d) {
+		double nn[3];
 		unsigned fl = 0;
 		surface_normal(Tv, s_rand[0], s_rand[1], nn, fl);  // rrt.cpp:25 — at the TARGET sample
 		grf_rotation(nn, R);
@@ -155,20 +195,19 @@ __global__ void __launch_bounds__(128, 8) k_pipe_prep(TerrainView Tv, PipeState 
 #pragma unroll
 		for (int d = 0; d < 9; ++d) R[d] = (d == 0 || d == 4 || d == 8) ? 1.0 : 0.0;
 	}
-	seg = __shfl_sync(FULL, seg, 0);
-	double *row = G.rows + (size_t) seg * PIPE_ROW;
-	if (lane < 8) row[lane] = s_near[lane];
-	else if (lane < 17) row[lane] = R[lane - 8];
-	else if (lane < 25) row[lane] = s_rand[lane - 17];
-	if (lane == 0) {
-		G.q[seg] = (int) q;
-		G.near[seg] = near;
-		// a tree vertex other than the root is the end state of a fully valid pair check: STANCE-valid by construction
-		const bool known_valid = near != 0 || S.root_valid[2 * q + half] != 0;
-		G.flags[seg] = (unsigned char) ((half == 0 ? GBP_FORWARD : GBP_REVERSE) | (known_valid ? 2 : 0));
-		G.idx0[seg] = (unsigned long long) cell * (unsigned long long) P.k_candidates;
-		S.it[q] = it; S.half[q] = half;
-	}
+	double2 *row = reinterpret_cast<double2 *>(G.rows + (size_t) seg * PIPE_ROW);
+	row[0] = make_double2(s_near[0], s_near[1]); row[1] = make_double2(s_near[2], s_near[3]);
+	row[2] = make_double2(s_near[4], s_near[5]); row[3] = make_double2(s_near[6], s_near[7]);
+	row[4] = make_double2(R[0], R[1]); row[5] = make_double2(R[2], R[3]); row[6] = make_double2(R[4], R[5]); row[7] = make_double2(R[6], R[7]);
+	row[8] = make_double2(R[8], s_rand[0]); row[9] = make_double2(s_rand[1], s_rand[2]); row[10] = make_double2(s_rand[3], s_rand[4]);
+	row[11] = make_double2(s_rand[5], s_rand[6]); row[12] = make_double2(s_rand[7], 0.0);
+	G.q[seg] = (int) q;
+	G.near[seg] = near;
+	// a tree vertex other than the root is the end state of a fully valid pair check: STANCE-valid by construction
+	const bool known_valid = near != 0 || S.root_valid[2 * q + half] != 0;
+	G.flags[seg] = (unsigned char) ((half == 0 ? GBP_FORWARD : GBP_REVERSE) | (known_valid ? 2 : 0));
+	G.idx0[seg] = (unsigned long long) cell * (unsigned long long) P.k_candidates;
+	S.it[q] = it; S.half[q] = half;
 }
 
 // k_walk_sv with per-segment parameters; see the file header.  `count` = segments of this round (device).
@@ -438,8 +477,8 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	const int64_t fin_slots = (int64_t) sms * 4 * 4;
 	const size_t bit_words = (Q * K + 31) / 32 + 2;
 	const size_t n_doubles = per * (8 + 10 + 1 + 1) + Q * 32 * 8 + Q * PIPE_ROW + (size_t) fin_slots * 2 * cap * 18;
-	const size_t n_ll = Q * 4 + 2;  // pair_checks, nn_queries, rs_base, idx0, finish counter
-	const size_t n_ints = per * 3 + Q * 13 + 8 + 2 * bit_words;
+	const size_t n_ll = Q * 5 + 2;  // pair_checks, nn_queries, rs_base, rs_want, idx0, finish counter
+	const size_t n_ints = per * 3 + Q * 15 + 12 + 2 * bit_words;
 	const size_t need = n_doubles * 8 + n_ll * 8 + n_ints * 4 + Q * 3 + 64;
 	void *mem = nullptr;
 	cudaError_t e;
@@ -462,6 +501,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	S.pair_checks = lp; lp += Q;
 	S.nn_queries = lp; lp += Q;
 	S.rs_base = lp; lp += Q;
+	S.rs_want = lp; lp += Q;
 	G.idx0 = (unsigned long long *) lp; lp += Q;
 	unsigned long long *next_query = (unsigned long long *) lp; lp += 2;
 	int *ip = (int *) lp;
@@ -481,6 +521,8 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	G.heavy = ip; ip += Q;
 	C.entry = ip; ip += 2 * Q;
 	C.count = ip; ip += 4;
+	int *batch_list = ip; ip += 2 * Q;  // queries that need their next batch of random states, double-buffered by round parity
+	int *batch_count = ip; ip += 4;
 	G.count = ip; ip += 4;  // the per-round words: counts, then the two bit arrays (one memset per round)
 	G.vbits = (unsigned *) ip; ip += bit_words;
 	G.ubits = (unsigned *) ip; ip += bit_words;
@@ -491,13 +533,15 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	// host-side resources of the calling thread: a pinned word for the running count, the second stream and its events
 	static thread_local int *h_count = nullptr;
 	static thread_local cudaStream_t sb = nullptr;
-	static thread_local cudaEvent_t ev_sel[2] = {nullptr, nullptr}, ev_con[2] = {nullptr, nullptr};
+	static thread_local cudaEvent_t ev_sel[2] = {nullptr, nullptr}, ev_con[2] = {nullptr, nullptr}, ev_prep[2] = {nullptr, nullptr}, ev_bat[2] = {nullptr, nullptr};
 	if (!h_count) {
 		e = cudaHostAlloc((void **) &h_count, 2 * sizeof(int), cudaHostAllocDefault);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
 		for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
 			e = cudaEventCreateWithFlags(&ev_sel[k], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_con[k], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_prep[k], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_bat[k], cudaEventDisableTiming);
 		}
 		if (e != cudaSuccess) {
 			if (h_count) { cudaFreeHost(h_count); h_count = nullptr; }
@@ -509,7 +553,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	const unsigned warp_blocks = (unsigned) ((Q + 3) / 4);
 	const unsigned walk_grid = (unsigned) sms * GBP_WALK_CTAS;
 	k_pipe_init<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, nq, starts, goals, P.max_iters);
-	cudaMemsetAsync(C.count, 0, 4 * sizeof(int), st);
+	cudaMemsetAsync(C.count, 0, 8 * sizeof(int), st);  // connect and batch request counts
 	// A round runs one extend attempt of every running query; a query needs at most 2 * max_iters of them (every random state
 	// valid) plus one idle round per connect.  The number of running queries is read back every 32 rounds to stop launching
 	// once all are done.  Stream `st`: memset, prep, walk, select of round r; stream `sb`: connect of round r, which overlaps
@@ -519,14 +563,22 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	for (; round < max_rounds; ++round) {
 		const int par = round & 1;
 		if (round >= 2) cudaStreamWaitEvent(st, ev_con[par], 0);  // connect of round - 2: its queries and its request list are free again
+		if (round >= 1) cudaStreamWaitEvent(st, ev_bat[par ^ 1], 0);  // the batches drawn for the previous round's requests
 		cudaMemsetAsync(G.count, 0, round_bytes, st);
 		cudaMemsetAsync(C.count + par, 0, sizeof(int), st);
-		k_pipe_prep<M><<<warp_blocks, 128, 0, st>>>(Tv, S, A, G, nq, seed, query0, P, round);
+		cudaMemsetAsync(batch_count + par, 0, sizeof(int), st);
+		k_pipe_prep<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, G, batch_list + (size_t) par * Q, batch_count + par, nq, P, round);
+		cudaEventRecord(ev_prep[par], st);
 		if (Tv.ztex) k_walk_seg<true><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
 		else k_walk_seg<false><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
 		k_pipe_triage<<<(unsigned) ((Q + 255) / 256), 256, 0, st>>>(S, G, P.k_candidates);
 		k_pipe_select<M><<<(unsigned) sms * 4, 128, 0, st>>>(Tv, S, A, G, C, nq, seed, query0, P, round);
 		cudaEventRecord(ev_sel[par], st);
+		// second stream: the batches of random states requested by this round's prep (needed by the next round's prep), then
+		// this round's connects (needed by the prep of the round after next)
+		cudaStreamWaitEvent(sb, ev_prep[par], 0);
+		k_pipe_batch<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, batch_list + (size_t) par * Q, batch_count + par, seed, query0);
+		cudaEventRecord(ev_bat[par], sb);
 		cudaStreamWaitEvent(sb, ev_sel[par], 0);
 		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sb>>>(Tv, S, A, C, nq, P, round);
 		cudaEventRecord(ev_con[par], sb);
