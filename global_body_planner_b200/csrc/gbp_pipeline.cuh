@@ -51,18 +51,24 @@ struct PipeState {  // per query
 	unsigned char *root_valid; // [Q][2] isValidState(root, STANCE) of the start-side / goal-side tree
 	int *busy_until;           // [Q] first round that may touch the query again (its connect runs on the second stream meanwhile)
 };
-struct PipeConnects {          // queries whose tree grew in a round: connect requests, double-buffered by round parity
-	int *count;                // [2]
-	int *entry;                // [2][Q]: query * 2 + half
+// per-round counters (one block per round parity): the kernels of a round on the second stream read them while the first
+// stream is already in the next round
+enum : int { CNT_SEGS = 0, CNT_BUSY = 1, CNT_HEAVY = 2, CNT_CONNECTS = 3, CNT_BATCHES = 4, CNT_WORDS = 8 };
+struct PipeHeavy {             // segments with a valid or an undecided candidate, copied out of the round's segment arrays
+	double *rows;              // [Q][PIPE_ROW]
+	int *q, *near;
+	unsigned char *flags;
+	unsigned long long *idx0;
+	unsigned *vmask, *umask;
+	int *connects;             // [Q] connect requests of the round: query * 2 + half
 };
 struct PipeSegs {  // the round's dense segment list
 	double *rows;              // [Q][PIPE_ROW]
 	int *q, *near;             // query, id of s_near in the tree being extended
 	unsigned char *flags;      // bit 0: direction, bit 1: s_near is known valid
 	unsigned long long *idx0;  // ACTION cell of candidate 0: cell * K
-	int *count;                // [0] segments of this round, [1] running queries whose connect is in flight, [2] heavy segments; then the bit words
-	unsigned *vbits, *ubits;
-	int *heavy;                // segments with a valid or an undecided candidate (count in count[2])
+	int *count;                // the round's counter block (CNT_*)
+	unsigned *vbits, *ubits;   // one bit per candidate; all zero between rounds (k_pipe_triage clears what the walk set)
 };
 
 template <typename M>
@@ -86,10 +92,10 @@ __global__ void __launch_bounds__(128) k_pipe_init(TerrainView Tv, PipeState S, 
 // STATE cells base .. base + 31 of the queries that ran out of random states: warp per listed query, lane L draws cell
 // base + L and checks it (their validity does not depend on the trees).  Runs on the second stream while the round's walk runs.
 template <typename M>
-__global__ void __launch_bounds__(128) k_pipe_batch(TerrainView Tv, PipeState S, const int *__restrict__ list, const int *__restrict__ count, uint64_t seed,
+__global__ void __launch_bounds__(128) k_pipe_batch(TerrainView Tv, PipeState S, const int *__restrict__ list, const int *__restrict__ cnt, uint64_t seed,
 													 uint64_t query0) {
 	const int lane = threadIdx.x & 31;
-	const int n = *count, warps = (gridDim.x * blockDim.x) >> 5;
+	const int n = cnt[CNT_BATCHES], warps = (gridDim.x * blockDim.x) >> 5;
 	for (int e = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5); e < n; e += warps) {
 		const int q = list[e];
 		const long long base = S.rs_want[q];
@@ -110,8 +116,8 @@ __global__ void __launch_bounds__(128) k_pipe_batch(TerrainView Tv, PipeState S,
 // rotation — and the segment row.  A warp per query spent its time on dependent HBM round trips (65 k warps x 3-4 round
 // trips, 100 us per round); 32 queries per warp issue those loads side by side.
 template <typename M>
-__global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int *__restrict__ batch_list,
-													int *__restrict__ batch_count, int64_t Q, gbp_plan_params P, int round) {
+__global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int *__restrict__ batch_list, int64_t Q,
+													gbp_plan_params P, int round) {
 	const int lane = threadIdx.x & 31;
 	const int64_t q = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
 	bool emit = false;
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 		const long long rs_base = S.rs_base[q];
 		const unsigned rs_valid = S.rs_valid[q];
 		const int busy_until = S.busy_until[q];
-		if (status == 0 && round < busy_until) atomicAdd(G.count + 1, 1);  // its connect or its next batch of random states is in flight
+		if (status == 0 && round < busy_until) atomicAdd(G.count + CNT_BUSY, 1);  // its select / connect or its next batch of random states is in flight
 		else if (status == 0) {
 			if (it >= P.max_iters) { S.status[q] = 2; S.iters[q] = P.max_iters; }  // budget used up
 			else if (na >= A.cap || nb >= A.cap) { S.status[q] = 2; S.iters[q] = it + 1; }  // a tree is full at the start of a half
@@ -144,8 +150,8 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 				else {  // the batch holding `cell` is drawn by k_pipe_batch while this round's walk runs; the query sits the round out
 					S.rs_want[q] = cell & ~31ll;
 					S.busy_until[q] = round + 1;
-					batch_list[atomicAdd(batch_count, 1)] = (int) q;
-					atomicAdd(G.count + 1, 1);
+					batch_list[atomicAdd(G.count + CNT_BATCHES, 1)] = (int) q;
+					atomicAdd(G.count + CNT_BUSY, 1);
 				}
 			}
 		}
@@ -153,7 +159,7 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 	// dense segment numbers: one atomic per warp
 	const unsigned em = __ballot_sync(FULL, emit);
 	int seg = 0;
-	if (lane == 0 && em) seg = atomicAdd(G.count, __popc(em));
+	if (lane == 0 && em) seg = atomicAdd(G.count + CNT_SEGS, __popc(em));
 	seg = __shfl_sync(FULL, seg, 0) + __popc(em & ((1u << lane) - 1u));
 	if (!emit) return;
 	double s_rand[8];
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_seg(Terra
 	__shared__ __align__(16) double stash[8][RF_WARPS * 32];
 	__shared__ uint8_t ringD[RF_WARPS][SV_CAP];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const int n = *G.count * K;
+	const int n = G.count[CNT_SEGS] * K;
 	const int warps = (gridDim.x * blockDim.x) >> 5;
 	int per_warp = (n + warps - 1) / warps;
 	per_warp = max(32, (per_warp + 31) / 32 * 32);  // whole bit words per warp
@@ -307,13 +313,28 @@ __device__ __forceinline__ unsigned pipe_bits(const unsigned *__restrict__ words
 }
 
 // triage, thread per segment: a segment whose candidates are all invalid (98 % of them) is TRAPPED — the query moves on to
-// its next half here; the others go to the heavy list
-static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSegs G, int K) {
+// its next half here.  The others are copied to the heavy list for k_pipe_select, which runs on the second stream while the
+// next round works on the other queries (their queries sit that round out), and their candidate bits are cleared.
+static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSegs G, PipeHeavy H, int K, int round) {
 	const int seg = blockIdx.x * blockDim.x + threadIdx.x;
-	if (seg >= G.count[0]) return;
-	const unsigned vmask = pipe_bits(G.vbits, seg * K, K), umask = pipe_bits(G.ubits, seg * K, K);
-	if (vmask | umask) { G.heavy[atomicAdd(G.count + 2, 1)] = seg; return; }
+	if (seg >= G.count[CNT_SEGS]) return;
+	const int first = seg * K;
+	const unsigned vmask = pipe_bits(G.vbits, first, K), umask = pipe_bits(G.ubits, first, K);
 	const int q = G.q[seg];
+	if (vmask | umask) {
+		const int h = atomicAdd(G.count + CNT_HEAVY, 1);
+		const double2 *src = reinterpret_cast<const double2 *>(G.rows + (size_t) seg * PIPE_ROW);
+		double2 *dst = reinterpret_cast<double2 *>(H.rows + (size_t) h * PIPE_ROW);
+#pragma unroll
+		for (int d = 0; d < PIPE_ROW / 2; ++d) dst[d] = src[d];
+		H.q[h] = q; H.near[h] = G.near[seg]; H.flags[h] = G.flags[seg]; H.idx0[h] = G.idx0[seg]; H.vmask[h] = vmask; H.umask[h] = umask;
+		S.busy_until[q] = round + 2;
+		const unsigned long long span = (K >= 32 ? 0xffffffffull : ((1ull << K) - 1ull)) << (first & 31);
+		const unsigned lo = (unsigned) span, hi = (unsigned) (span >> 32);
+		if (vmask) { atomicAnd(G.vbits + (first >> 5), ~lo); if (hi) atomicAnd(G.vbits + (first >> 5) + 1, ~hi); }
+		if (umask) { atomicAnd(G.ubits + (first >> 5), ~lo); if (hi) atomicAnd(G.ubits + (first >> 5) + 1, ~hi); }
+		return;
+	}
 	S.pair_checks[q] += K;
 	S.nn_queries[q] += 1;
 	if (((int) G.flags[seg] & 1) == GBP_FORWARD) S.half[q] = 1;
@@ -321,23 +342,22 @@ static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSeg
 }
 
 template <typename M>
-__global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, PipeConnects C, int64_t Q, uint64_t seed,
-													 uint64_t query0, gbp_plan_params P, int round) {
+__global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeState S, PlanArena A, PipeHeavy H, int *__restrict__ cnt, uint64_t seed,
+													 uint64_t query0, gbp_plan_params P) {
 	const int lane = threadIdx.x & 31;
-	const int nheavy = G.count[2], warps = (gridDim.x * blockDim.x) >> 5;
+	const int nheavy = cnt[CNT_HEAVY], warps = (gridDim.x * blockDim.x) >> 5;
 	for (int h = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5); h < nheavy; h += warps) {
-	const int seg = G.heavy[h];
-	const int q = G.q[seg], K = P.k_candidates;
-	unsigned vmask = pipe_bits(G.vbits, seg * K, K);
-	const unsigned umask = pipe_bits(G.ubits, seg * K, K);
-	const double *row = G.rows + (size_t) seg * PIPE_ROW;
+	const int q = H.q[h], K = P.k_candidates;
+	unsigned vmask = H.vmask[h];
+	const unsigned umask = H.umask[h];
+	const double *row = H.rows + (size_t) h * PIPE_ROW;
 	double s_near[8], R[9], s_rand[8];
 #pragma unroll
 	for (int d = 0; d < 8; ++d) { s_near[d] = row[d]; s_rand[d] = row[17 + d]; }
 #pragma unroll
 	for (int d = 0; d < 9; ++d) R[d] = row[8 + d];
-	const int dir = (int) G.flags[seg] & 1, half = dir == GBP_FORWARD ? 0 : 1, near = G.near[seg];
-	const uint64_t stream = query0 + (uint64_t) q, idx0 = G.idx0[seg];
+	const int dir = (int) H.flags[h] & 1, half = dir == GBP_FORWARD ? 0 : 1, near = H.near[h];
+	const uint64_t stream = query0 + (uint64_t) q, idx0 = H.idx0[h];
 	const bool dirs = P.action_direction_sampling != 0;
 	const double *a_from = dir == GBP_FORWARD ? s_near : s_rand, *a_to = dir == GBP_FORWARD ? s_rand : s_near;
 	// first-valid selection only needs the undecided candidates that come before the first valid one
@@ -393,11 +413,7 @@ __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeStat
 	if (found && lane == 0) {
 		PlanTree Tx = arena_tree(A, q, half, (half == 0 ? S.na : S.nb) + q);
 		plan_push(Tx, near, sn, a);  // rrt.cpp:87-92
-		// connect from the other tree (rrt_connect.cpp:261, :296) runs in k_pipe_connect on the second stream while the next
-		// round works on the other queries: this one sits that round out
-		const int par = round & 1;
-		C.entry[(size_t) par * Q + atomicAdd(C.count + par, 1)] = q * 2 + half;
-		S.busy_until[q] = round + 2;
+		H.connects[atomicAdd(cnt + CNT_CONNECTS, 1)] = q * 2 + half;  // connect from the other tree (rrt_connect.cpp:261, :296): k_pipe_connect, next on this stream
 	}
 	if (lane == 0) {
 		S.pair_checks[q] += pair_checks;
@@ -413,12 +429,12 @@ __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeStat
 
 // connect (rrt_connect.cpp:98-120) for the queries whose tree grew in round `round`: warps pull requests from the list
 template <typename M>
-__global__ void __launch_bounds__(128, 4) k_pipe_connect(TerrainView Tv, PipeState S, PlanArena A, PipeConnects C, int64_t Q, gbp_plan_params P, int round) {
+__global__ void __launch_bounds__(128, 4) k_pipe_connect(TerrainView Tv, PipeState S, PlanArena A, PipeHeavy H, const int *__restrict__ cnt, gbp_plan_params P) {
 	const int lane = threadIdx.x & 31;
-	const int par = round & 1, n = C.count[par];
+	const int n = cnt[CNT_CONNECTS];
 	const int warps = (gridDim.x * blockDim.x) >> 5;
 	for (int e = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5); e < n; e += warps) {
-		const int code = C.entry[(size_t) par * Q + e], q = code >> 1, half = code & 1;
+		const int code = H.connects[e], q = code >> 1, half = code & 1;
 		PlanTree Ta = arena_tree(A, q, 0, S.na + q), Tb = arena_tree(A, q, 1, S.nb + q);
 		PlanTree &Tx = half == 0 ? Ta : Tb, &Ty = half == 0 ? Tb : Ta;
 		int na = S.na[q], nb = S.nb[q];
@@ -476,17 +492,17 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	const size_t cap = (size_t) P.max_vertices, Q = (size_t) nq, per = Q * 2 * cap, K = (size_t) P.k_candidates;
 	const int64_t fin_slots = (int64_t) sms * 4 * 4;
 	const size_t bit_words = (Q * K + 31) / 32 + 2;
-	const size_t n_doubles = per * (8 + 10 + 1 + 1) + Q * 32 * 8 + Q * PIPE_ROW + (size_t) fin_slots * 2 * cap * 18;
-	const size_t n_ll = Q * 5 + 2;  // pair_checks, nn_queries, rs_base, rs_want, idx0, finish counter
-	const size_t n_ints = per * 3 + Q * 15 + 12 + 2 * bit_words;
-	const size_t need = n_doubles * 8 + n_ll * 8 + n_ints * 4 + Q * 3 + 64;
+	const size_t n_doubles = per * (8 + 10 + 1 + 1) + Q * 32 * 8 + 3 * Q * PIPE_ROW + (size_t) fin_slots * 2 * cap * 18;
+	const size_t n_ll = Q * 7 + 2;  // pair_checks, nn_queries, rs_base, rs_want, idx0 (round + 2 heavy buffers), finish counter
+	const size_t n_ints = per * 3 + Q * 21 + 2 * CNT_WORDS + 2 * bit_words;
+	const size_t need = n_doubles * 8 + n_ll * 8 + n_ints * 4 + Q * 5 + 64;
 	void *mem = nullptr;
 	cudaError_t e;
 	if ((e = cudaMallocAsync(&mem, need, st)) != cudaSuccess) { err = std::string("pipelined planner arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
 	PlanArena A = {}, Sc = {};
 	PipeState S;
 	PipeSegs G;
-	PipeConnects C;
+	PipeHeavy H[2];
 	A.cap = Sc.cap = P.max_vertices;
 	double *dp = (double *) mem;
 	A.v = dp; dp += per * 8;
@@ -495,6 +511,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	A.y = dp; dp += per;
 	S.rs = dp; dp += Q * 32 * 8;
 	G.rows = dp; dp += Q * PIPE_ROW;
+	for (int k = 0; k < 2; ++k) { H[k].rows = dp; dp += Q * PIPE_ROW; }
 	Sc.pstate = dp; dp += (size_t) fin_slots * 2 * cap * 8;
 	Sc.paction = dp; dp += (size_t) fin_slots * 2 * cap * 10;
 	long long *lp = (long long *) dp;
@@ -503,6 +520,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	S.rs_base = lp; lp += Q;
 	S.rs_want = lp; lp += Q;
 	G.idx0 = (unsigned long long *) lp; lp += Q;
+	for (int k = 0; k < 2; ++k) { H[k].idx0 = (unsigned long long *) lp; lp += Q; }
 	unsigned long long *next_query = (unsigned long long *) lp; lp += 2;
 	int *ip = (int *) lp;
 	A.parent = ip; ip += per;
@@ -518,27 +536,30 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	S.busy_until = ip; ip += Q;
 	G.q = ip; ip += Q;
 	G.near = ip; ip += Q;
-	G.heavy = ip; ip += Q;
-	C.entry = ip; ip += 2 * Q;
-	C.count = ip; ip += 4;
+	for (int k = 0; k < 2; ++k) {
+		H[k].q = ip; ip += Q;
+		H[k].near = ip; ip += Q;
+		H[k].vmask = (unsigned *) ip; ip += Q;
+		H[k].umask = (unsigned *) ip; ip += Q;
+		H[k].connects = ip; ip += Q;
+	}
 	int *batch_list = ip; ip += 2 * Q;  // queries that need their next batch of random states, double-buffered by round parity
-	int *batch_count = ip; ip += 4;
-	G.count = ip; ip += 4;  // the per-round words: counts, then the two bit arrays (one memset per round)
+	int *cnt = ip; ip += 2 * CNT_WORDS;  // the two counter blocks, then the two bit arrays (zeroed once: triage clears what a round sets)
 	G.vbits = (unsigned *) ip; ip += bit_words;
 	G.ubits = (unsigned *) ip; ip += bit_words;
 	unsigned char *bp = (unsigned char *) ip;
 	S.root_valid = bp; bp += 2 * Q;
 	G.flags = bp; bp += Q;
-	const size_t round_bytes = (4 + 2 * bit_words) * 4;
-	// host-side resources of the calling thread: a pinned word for the running count, the second stream and its events
+	for (int k = 0; k < 2; ++k) { H[k].flags = bp; bp += Q; }
+	// host-side resources of the calling thread: a pinned word pair for the running count, the second stream and its events
 	static thread_local int *h_count = nullptr;
 	static thread_local cudaStream_t sb = nullptr;
-	static thread_local cudaEvent_t ev_sel[2] = {nullptr, nullptr}, ev_con[2] = {nullptr, nullptr}, ev_prep[2] = {nullptr, nullptr}, ev_bat[2] = {nullptr, nullptr};
+	static thread_local cudaEvent_t ev_tri[2] = {nullptr, nullptr}, ev_con[2] = {nullptr, nullptr}, ev_prep[2] = {nullptr, nullptr}, ev_bat[2] = {nullptr, nullptr};
 	if (!h_count) {
 		e = cudaHostAlloc((void **) &h_count, 2 * sizeof(int), cudaHostAllocDefault);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
 		for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-			e = cudaEventCreateWithFlags(&ev_sel[k], cudaEventDisableTiming);
+			e = cudaEventCreateWithFlags(&ev_tri[k], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_con[k], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_prep[k], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_bat[k], cudaEventDisableTiming);
@@ -550,37 +571,36 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 			return GBP_E_CUDA;
 		}
 	}
-	const unsigned warp_blocks = (unsigned) ((Q + 3) / 4);
 	const unsigned walk_grid = (unsigned) sms * GBP_WALK_CTAS;
 	k_pipe_init<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, nq, starts, goals, P.max_iters);
-	cudaMemsetAsync(C.count, 0, 8 * sizeof(int), st);  // connect and batch request counts
+	cudaMemsetAsync(cnt, 0, (2 * CNT_WORDS + 2 * bit_words) * sizeof(int), st);
 	// A round runs one extend attempt of every running query; a query needs at most 2 * max_iters of them (every random state
-	// valid) plus one idle round per connect.  The number of running queries is read back every 32 rounds to stop launching
-	// once all are done.  Stream `st`: memset, prep, walk, select of round r; stream `sb`: connect of round r, which overlaps
-	// round r + 1 and must be over before round r + 2 (the queries it works on sit round r + 1 out).
-	const int max_rounds = 3 * P.max_iters + 2;
+	// valid) plus the rounds it sits out.  The number of running queries is read back every 32 rounds to stop launching once
+	// all are done.
+	//   stream st: prep, walk, triage of round r.
+	//   stream sb: the batches of random states requested by prep(r) (needed by prep(r + 1)); then select + connect for the
+	//              few queries of round r that have a valid or undecided candidate — they overlap round r + 1, which those
+	//              queries sit out, and are over before prep(r + 2).
+	const int max_rounds = 4 * P.max_iters + 4;
 	int round = 0;
 	for (; round < max_rounds; ++round) {
 		const int par = round & 1;
-		if (round >= 2) cudaStreamWaitEvent(st, ev_con[par], 0);  // connect of round - 2: its queries and its request list are free again
+		G.count = cnt + par * CNT_WORDS;
+		if (round >= 2) cudaStreamWaitEvent(st, ev_con[par], 0);  // select + connect of round - 2: its queries, heavy buffers and counters are free again
 		if (round >= 1) cudaStreamWaitEvent(st, ev_bat[par ^ 1], 0);  // the batches drawn for the previous round's requests
-		cudaMemsetAsync(G.count, 0, round_bytes, st);
-		cudaMemsetAsync(C.count + par, 0, sizeof(int), st);
-		cudaMemsetAsync(batch_count + par, 0, sizeof(int), st);
-		k_pipe_prep<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, G, batch_list + (size_t) par * Q, batch_count + par, nq, P, round);
+		if (round >= 2) cudaMemsetAsync(G.count, 0, CNT_WORDS * sizeof(int), st);
+		k_pipe_prep<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, G, batch_list + (size_t) par * Q, nq, P, round);
 		cudaEventRecord(ev_prep[par], st);
 		if (Tv.ztex) k_walk_seg<true><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
 		else k_walk_seg<false><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
-		k_pipe_triage<<<(unsigned) ((Q + 255) / 256), 256, 0, st>>>(S, G, P.k_candidates);
-		k_pipe_select<M><<<(unsigned) sms * 4, 128, 0, st>>>(Tv, S, A, G, C, nq, seed, query0, P, round);
-		cudaEventRecord(ev_sel[par], st);
-		// second stream: the batches of random states requested by this round's prep (needed by the next round's prep), then
-		// this round's connects (needed by the prep of the round after next)
+		k_pipe_triage<<<(unsigned) ((Q + 255) / 256), 256, 0, st>>>(S, G, H[par], P.k_candidates, round);
+		cudaEventRecord(ev_tri[par], st);
 		cudaStreamWaitEvent(sb, ev_prep[par], 0);
-		k_pipe_batch<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, batch_list + (size_t) par * Q, batch_count + par, seed, query0);
+		k_pipe_batch<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, batch_list + (size_t) par * Q, G.count, seed, query0);
 		cudaEventRecord(ev_bat[par], sb);
-		cudaStreamWaitEvent(sb, ev_sel[par], 0);
-		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sb>>>(Tv, S, A, C, nq, P, round);
+		cudaStreamWaitEvent(sb, ev_tri[par], 0);
+		k_pipe_select<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, A, H[par], G.count, seed, query0, P);
+		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sb>>>(Tv, S, A, H[par], G.count, P);
 		cudaEventRecord(ev_con[par], sb);
 		if ((round & 31) == 31) {
 			cudaMemcpyAsync(h_count, G.count, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -588,7 +608,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 			if (h_count[0] + h_count[1] == 0) { ++round; break; }
 		}
 	}
-	for (int k = 0; k < 2 && k < round; ++k) cudaStreamWaitEvent(st, ev_con[k], 0);  // the last connects precede the statistics
+	for (int k = 0; k < 2 && k < round; ++k) cudaStreamWaitEvent(st, ev_con[k], 0);  // the last selects / connects precede the statistics
 	cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st);
 	const int64_t fin_warps = (int64_t) Q < fin_slots ? (int64_t) ((Q + 3) / 4 * 4) : fin_slots;
 	k_pipe_finish<M><<<(unsigned) (fin_warps / 4), 128, 0, st>>>(Tv, S, A, Sc, nq, P, next_query, stats, path_states, path_actions, path_cap, dump);
