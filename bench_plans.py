@@ -307,6 +307,7 @@ def run(gbp, torch, dist, dev, rank, world, q_per_gpu=Q_PER_GPU, cpu_seconds=8.0
                        f"blocks {BLOCK * PITCH:.1f} m, steps U(0,{STEP_H}) m; start/goal 4-8 m apart (SURVEY 8d config 5); K={K_CAND} first-valid, "
                        f"budget {MAX_ITERS} iterations / {MAX_VERTS} vertices per tree"}
     out.update(batch_summary(st, secs))
+    out["planner_form"] = t.plan_batch_form(P, nq)
     out["stats_gather_bytes"] = int(st.nbytes)
     out["separation_3_5m"] = dict(batch_summary(st35, secs35), note="round 1's workload (start/goal 3-5 m apart), same budget, for comparison")
     cfg = {}

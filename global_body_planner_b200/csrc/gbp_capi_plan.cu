@@ -127,6 +127,11 @@ static int plan_dev(const gbp_terrain *t, int64_t nq, const double *starts, cons
 	if (rc) return fail(rc, err);
 	return GBP_OK;
 }
+int gbp_plan_batch_form(const gbp_terrain *t, const gbp_plan_params *p, int64_t nq, int *form) {
+	if (!t || !p || !form) return fail(GBP_E_INVALID, "bad arguments");
+	*form = gbp_plan_pipe_applies(t->view, *p, nq) ? 1 : (plan_step_applies(*p, nq) ? 2 : 0);
+	return GBP_OK;
+}
 int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
 					   const gbp_plan_params *p, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap,
 					   void *stream) {

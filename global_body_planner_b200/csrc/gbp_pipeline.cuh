@@ -53,7 +53,7 @@ struct PipeState {  // per query
 };
 // per-round counters (one block per round parity): the kernels of a round on the second stream read them while the first
 // stream is already in the next round
-enum : int { CNT_SEGS = 0, CNT_BUSY = 1, CNT_HEAVY = 2, CNT_CONNECTS = 3, CNT_BATCHES = 4, CNT_WORDS = 8 };
+enum : int { CNT_SEGS = 0, CNT_BUSY = 1, CNT_HEAVY = 2, CNT_CONNECTS = 3, CNT_BATCHES = 4, CNT_WORK = 5, CNT_WORDS = 8 };
 struct PipeHeavy {             // segments with a valid or an undecided candidate, copied out of the round's segment arrays
 	double *rows;              // [Q][PIPE_ROW]
 	int *q, *near;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) k_pipe_batch(TerrainView Tv, PipeState S,
 	}
 }
 
-// THREAD per query: the control flow of a half-iteration up to newConfig's candidates — budget and capacity checks, the next
+// FOUR LANES per query: the control flow of a half-iteration up to newConfig's candidates — budget and capacity checks, the next
 // valid random state of the query (invalid ones are skipped, rrt_connect.cpp:254), the nearest neighbour (rrt.cpp:78, a
 // sequential scan of the query's tree: a few dozen vertices), the surface normal at the target (rrt.cpp:25) and its GRF
 // rotation — and the segment row.  A warp per query spent its time on dependent HBM round trips (65 k warps x 3-4 round
@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(128) k_pipe_batch(TerrainView Tv, PipeState S,
 template <typename M>
 __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int *__restrict__ batch_list, int64_t Q,
 													gbp_plan_params P, int round) {
-	const int lane = threadIdx.x & 31;
-	const int64_t q = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31, sub = lane & 3;  // 4 lanes per query: they share the control flow and split the tree scan
+	const int64_t q = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 2;
+	const bool lead = sub == 0;
 	bool emit = false;
 	int it = 0, half = 0, na = 0, nb = 0;
 	long long cell = 0;
@@ -129,25 +130,25 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 		const long long rs_base = S.rs_base[q];
 		const unsigned rs_valid = S.rs_valid[q];
 		const int busy_until = S.busy_until[q];
-		if (status == 0 && round < busy_until) atomicAdd(G.count + CNT_BUSY, 1);  // its select / connect or its next batch of random states is in flight
+		if (status == 0 && round < busy_until) { if (lead) atomicAdd(G.count + CNT_BUSY, 1); }  // its select / connect or its next batch of random states is in flight
 		else if (status == 0) {
-			if (it >= P.max_iters) { S.status[q] = 2; S.iters[q] = P.max_iters; }  // budget used up
-			else if (na >= A.cap || nb >= A.cap) { S.status[q] = 2; S.iters[q] = it + 1; }  // a tree is full at the start of a half
+			if (it >= P.max_iters) { if (lead) { S.status[q] = 2; S.iters[q] = P.max_iters; } }  // budget used up
+			else if (na >= A.cap || nb >= A.cap) { if (lead) { S.status[q] = 2; S.iters[q] = it + 1; } }  // a tree is full at the start of a half
 			else {
 				cell = 2ll * it + half;
 				const long long base = cell & ~31ll;
-				unsigned mask = rs_base == base ? rs_valid >> (unsigned) (cell & 31ll) : 0u;
+				const unsigned mask = rs_base == base ? rs_valid >> (unsigned) (cell & 31ll) : 0u;
 				if (rs_base == base && mask == 0) {  // no valid state left in this batch: the query is at the first cell of the next one
 					cell = base + 32; it = (int) (cell >> 1); half = (int) (cell & 1);
-					S.it[q] = it; S.half[q] = half;
+					if (lead) { S.it[q] = it; S.half[q] = half; }
 				}
 				if (mask) {
 					cell += __ffs(mask) - 1;  // invalid random states are skipped (rrt_connect.cpp:254)
 					it = (int) (cell >> 1); half = (int) (cell & 1);
-					if (it >= P.max_iters) { S.status[q] = 2; S.iters[q] = P.max_iters; }
+					if (it >= P.max_iters) { if (lead) { S.status[q] = 2; S.iters[q] = P.max_iters; } }
 					else emit = true;
-				} else if (it >= P.max_iters) { S.status[q] = 2; S.iters[q] = P.max_iters; }
-				else {  // the batch holding `cell` is drawn by k_pipe_batch while this round's walk runs; the query sits the round out
+				} else if (it >= P.max_iters) { if (lead) { S.status[q] = 2; S.iters[q] = P.max_iters; } }
+				else if (lead) {  // the batch holding `cell` is drawn by k_pipe_batch while this round's walk runs; the query sits the round out
 					S.rs_want[q] = cell & ~31ll;
 					S.busy_until[q] = round + 1;
 					batch_list[atomicAdd(G.count + CNT_BATCHES, 1)] = (int) q;
@@ -157,11 +158,12 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 		}
 	}
 	// dense segment numbers: one atomic per warp
-	const unsigned em = __ballot_sync(FULL, emit);
+	const unsigned em = __ballot_sync(FULL, emit && lead);
 	int seg = 0;
 	if (lane == 0 && em) seg = atomicAdd(G.count + CNT_SEGS, __popc(em));
-	seg = __shfl_sync(FULL, seg, 0) + __popc(em & ((1u << lane) - 1u));
-	if (!emit) return;
+	seg = __shfl_sync(FULL, seg, 0) + __popc(em & ((1u << lane) - 1u));  // lanes of a group count the same leaders below them
+	if (!emit) return;  // the 4 lanes of a query leave together
+	const unsigned gmask = 0xfu << (lane & ~3);
 	double s_rand[8];
 	{
 		const double2 *r = reinterpret_cast<const double2 *>(S.rs + ((size_t) q * 32 + (size_t) (cell & 31ll)) * 8);
@@ -170,25 +172,43 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 	}
 	PlanTree Tx = arena_tree(A, (int) q, half, (half == 0 ? S.na : S.nb) + q);
 	const int nx = half == 0 ? na : nb;
-	// getNearestNeighbor (planner_class.cpp:185-200): ascending id with a strict < keeps the lowest id among equal distances
+	// getNearestNeighbor (planner_class.cpp:185-200): (distance, id) argmin — the lowest id among equal distances
 	double bd = INFINITY, s_near[8];
-	int near = 0;
+	int near = 0x7fffffff;
 #pragma unroll
-	for (int d = 0; d < 8; ++d) s_near[d] = Tx.t.v[(size_t) d * Tx.t.cap];
-#pragma unroll 2
-	for (int j = 0; j < nx; ++j) {
+	for (int d = 0; d < 8; ++d) s_near[d] = 0.0;
+	for (int j = sub; j < nx; j += 4) {
 		double v[8], sum = 0;
 #pragma unroll
 		for (int d = 0; d < 8; ++d) v[d] = Tx.t.v[(size_t) d * Tx.t.cap + j];
 #pragma unroll
 		for (int d = 0; d < 8; ++d) sum = sum + 1.0 * (v[d] - s_rand[d]) * (v[d] - s_rand[d]);
 		const double dj = sqrt(sum);
-		if (dj < bd) {
+		if (dj < bd) {  // ids ascend within a lane: a strict < keeps the lowest
 			bd = dj; near = j;
 #pragma unroll
 			for (int d = 0; d < 8; ++d) s_near[d] = v[d];
 		}
 	}
+#pragma unroll
+	for (int o = 1; o < 4; o <<= 1) {
+		const double od = __shfl_xor_sync(gmask, bd, o);
+		const int oj = __shfl_xor_sync(gmask, near, o);
+		double ov[8];
+#pragma unroll
+		for (int d = 0; d < 8; ++d) ov[d] = __shfl_xor_sync(gmask, s_near[d], o);
+		if (od < bd || (od == bd && oj < near)) {
+			bd = od; near = oj;
+#pragma unroll
+			for (int d = 0; d < 8; ++d) s_near[d] = ov[d];
+		}
+	}
+	if (near == 0x7fffffff) {  // no finite distance: the reference's default index 0 (planner_class.cpp:186)
+		near = 0;
+#pragma unroll
+		for (int d = 0; d < 8; ++d) s_near[d] = Tx.t.v[(size_t) d * Tx.t.cap];
+	}
+	if (!lead) return;
 	double R[9];
 	if (Tv.nz3 || Tv.nz3d) {
 		double nn[3];
@@ -225,34 +245,37 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_seg(Terra
 	__shared__ __align__(16) double stash[8][RF_WARPS * 32];
 	__shared__ uint8_t ringD[RF_WARPS][SV_CAP];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	__shared__ int ringI[RF_WARPS][SV_CAP];
 	const int n = G.count[CNT_SEGS] * K;
-	const int warps = (gridDim.x * blockDim.x) >> 5;
-	int per_warp = (n + warps - 1) / warps;
-	per_warp = max(32, (per_warp + 31) / 32 * 32);  // whole bit words per warp
-	const int64_t warp = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5;
-	const int wbase = (int) min(warp * (int64_t) per_warp, (int64_t) n);
-	const int total = min(n - wbase, per_warp);
 	double *const st = &stash[0][threadIdx.x];
 	const uint64_t pol = l2_evict_first_policy();
-	int next = 0, filled = 0;
+	// warps claim batches of 32 candidates from a counter (a round is a few batches per warp: static ranges would leave the
+	// warps with short candidates idle while the longest range finishes)
+	int next = 0, filled = 0;  // candidates handed out / produced by this warp
+	bool exhausted = false;
 	WalkCursor q;
 	q.phase = PH_IDLE;
 	int mine = -1;
 	while (true) {
 		const unsigned need = __ballot_sync(FULL, q.phase == PH_IDLE);
-		if (need && next < total) {
+		if (need && (next < filled || !exhausted)) {
 			const int nidle = __popc(need);
-			if (filled - next < nidle && filled < total && filled - next <= SV_CAP - 32) {
-				const int r = filled + lane;
-				if (r < total) {
-					const int e = r % SV_CAP;
-					const int i = wbase + r;
+			if (filled - next < nidle && !exhausted && filled - next <= SV_CAP - 32) {
+				int base = 0;
+				if (lane == 0) base = atomicAdd(G.count + CNT_WORK, 32);
+				base = __shfl_sync(FULL, base, 0);
+				const int cnt = min(32, n - base);
+				if (cnt <= 0) exhausted = true;
+				if (lane < cnt) {
+					const int e = (filled + lane) % SV_CAP;
+					const int i = base + lane;
 					const int seg = i / K, j = i - seg * K;
 					const double *row = G.rows + (size_t) seg * PIPE_ROW;
 #pragma unroll
 					for (int d = 0; d < 4; ++d) cp_async16_hint(&ringS[wib][e][2 * d], row + 2 * d, pol);
 					const int f = (int) G.flags[seg];
 					ringD[wib][e] = (uint8_t) f;
+					ringI[wib][e] = i;
 					double vx = 0, vy = 0, tvx = 0, tvy = 0;
 					if (dir_sampling) { vx = row[3]; vy = row[4]; tvx = row[17 + 3]; tvy = row[17 + 4]; }
 					sv_sample_to_ring(seed, query0 + (uint64_t) G.q[seg], G.idx0[seg] + (uint64_t) j, row + 8, dir_sampling, dir_thresh, tvx, tvy, f & 1, vx,
@@ -260,7 +283,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_seg(Terra
 				}
 				cp_async_wait_all();
 				__syncwarp();
-				filled = min(total, filled + 32);
+				filled += max(cnt, 0);
 			}
 			if (q.phase == PH_IDLE) {
 				const int rel = next + __popc(need & ((1u << lane) - 1));
@@ -273,7 +296,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_seg(Terra
 					for (int d = 0; d < 4; ++d) { const double2 v = ps[d]; s[2 * d] = v.x; s[2 * d + 1] = v.y; }
 #pragma unroll
 					for (int d = 0; d < 5; ++d) { const double2 v = pa[d]; a[2 * d] = v.x; a[2 * d + 1] = v.y; }
-					mine = wbase + rel;
+					mine = ringI[wib][e];
 					const int f = (int) ringD[wib][e];
 					walk_start(q, s, a, f & 1, st);
 					// the start state's own check (the reference's first sub-state) is not repeated for a vertex known valid
@@ -286,7 +309,10 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_seg(Terra
 			next = min(filled, next + nidle);
 			__syncwarp();
 		}
-		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) break;
+		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) {
+			if (exhausted && next >= filled) break;
+			continue;
+		}
 		bool valid = false, decided = true;
 		if (q.phase != PH_IDLE) {
 			const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
@@ -479,7 +505,7 @@ inline bool plan_pipe_applies(const TerrainView &Tv, const gbp_plan_params &P, i
 	if (P.rrt_star || P.adaptive || P.state_direction_sampling || P.stop_after_solved > 0 || P.k_candidates > 32 || !Tv.mixed_ok || !Tv.uniform) return false;
 	if (mode && !strcmp(mode, "pipe")) return true;
 	if (mode && (!strcmp(mode, "mega") || !strcmp(mode, "step"))) return false;
-	return nq >= 8192;
+	return nq >= 32768;  // a round costs ~0.1 ms whatever the batch size: below ~20 k queries the megakernel's independent warps win
 }
 
 template <typename M>
@@ -553,13 +579,16 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	for (int k = 0; k < 2; ++k) { H[k].flags = bp; bp += Q; }
 	// host-side resources of the calling thread: a pinned word pair for the running count, the second stream and its events
 	static thread_local int *h_count = nullptr;
-	static thread_local cudaStream_t sb = nullptr;
-	static thread_local cudaEvent_t ev_tri[2] = {nullptr, nullptr}, ev_con[2] = {nullptr, nullptr}, ev_prep[2] = {nullptr, nullptr}, ev_bat[2] = {nullptr, nullptr};
+	static thread_local cudaStream_t sb = nullptr, sc = nullptr;
+	static thread_local cudaEvent_t ev_tri[2] = {nullptr, nullptr}, ev_con[2] = {nullptr, nullptr}, ev_prep[2] = {nullptr, nullptr}, ev_bat[2] = {nullptr, nullptr},
+									ev_sel[2] = {nullptr, nullptr};
 	if (!h_count) {
 		e = cudaHostAlloc((void **) &h_count, 2 * sizeof(int), cudaHostAllocDefault);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
 		for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
 			e = cudaEventCreateWithFlags(&ev_tri[k], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_sel[k], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_con[k], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_prep[k], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_bat[k], cudaEventDisableTiming);
@@ -578,35 +607,62 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	// valid) plus the rounds it sits out.  The number of running queries is read back every 32 rounds to stop launching once
 	// all are done.
 	//   stream st: prep, walk, triage of round r.
-	//   stream sb: the batches of random states requested by prep(r) (needed by prep(r + 1)); then select + connect for the
-	//              few queries of round r that have a valid or undecided candidate — they overlap round r + 1, which those
-	//              queries sit out, and are over before prep(r + 2).
+	//   stream sb: the batches of random states requested by prep(r) (needed by prep(r + 1)); then select for the few
+	//              queries of round r that have a valid or undecided candidate.
+	//   stream sc: connect for the queries whose tree grew in select(r).
+	//              Select and connect overlap round r + 1, which their queries sit out, and are over before prep(r + 2).
 	const int max_rounds = 4 * P.max_iters + 4;
 	int round = 0;
+	// GBP_PIPE_TRACE=1: device timestamps of 32 consecutive rounds (after round 640) on the first stream, printed to stderr
+	const bool trace = getenv("GBP_PIPE_TRACE") != nullptr;
+	cudaEvent_t tr[32][4];
+	if (trace) for (auto &r4 : tr) for (auto &ev : r4) cudaEventCreate(&ev);
 	for (; round < max_rounds; ++round) {
 		const int par = round & 1;
+		const bool tr_on = trace && round >= 640 && round < 672;
+		if (tr_on) cudaEventRecord(tr[round - 640][0], st);
 		G.count = cnt + par * CNT_WORDS;
 		if (round >= 2) cudaStreamWaitEvent(st, ev_con[par], 0);  // select + connect of round - 2: its queries, heavy buffers and counters are free again
 		if (round >= 1) cudaStreamWaitEvent(st, ev_bat[par ^ 1], 0);  // the batches drawn for the previous round's requests
 		if (round >= 2) cudaMemsetAsync(G.count, 0, CNT_WORDS * sizeof(int), st);
-		k_pipe_prep<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, G, batch_list + (size_t) par * Q, nq, P, round);
+		if (tr_on) cudaEventRecord(tr[round - 640][1], st);
+		k_pipe_prep<M><<<(unsigned) ((4 * Q + 127) / 128), 128, 0, st>>>(Tv, S, A, G, batch_list + (size_t) par * Q, nq, P, round);
 		cudaEventRecord(ev_prep[par], st);
+		if (tr_on) cudaEventRecord(tr[round - 640][2], st);
 		if (Tv.ztex) k_walk_seg<true><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
 		else k_walk_seg<false><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
 		k_pipe_triage<<<(unsigned) ((Q + 255) / 256), 256, 0, st>>>(S, G, H[par], P.k_candidates, round);
 		cudaEventRecord(ev_tri[par], st);
+		if (tr_on) cudaEventRecord(tr[round - 640][3], st);
 		cudaStreamWaitEvent(sb, ev_prep[par], 0);
 		k_pipe_batch<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, batch_list + (size_t) par * Q, G.count, seed, query0);
 		cudaEventRecord(ev_bat[par], sb);
 		cudaStreamWaitEvent(sb, ev_tri[par], 0);
 		k_pipe_select<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, A, H[par], G.count, seed, query0, P);
-		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sb>>>(Tv, S, A, H[par], G.count, P);
-		cudaEventRecord(ev_con[par], sb);
+		cudaEventRecord(ev_sel[par], sb);
+		cudaStreamWaitEvent(sc, ev_sel[par], 0);
+		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sc>>>(Tv, S, A, H[par], G.count, P);
+		cudaEventRecord(ev_con[par], sc);
 		if ((round & 31) == 31) {
 			cudaMemcpyAsync(h_count, G.count, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
 			if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
 			if (h_count[0] + h_count[1] == 0) { ++round; break; }
 		}
+	}
+	if (trace) {
+		cudaStreamSynchronize(st);
+		if (round >= 672) {
+			float wait = 0, prep = 0, rest = 0, gap = 0, t;
+			for (int r = 0; r < 32; ++r) {
+				cudaEventElapsedTime(&t, tr[r][0], tr[r][1]); wait += t;
+				cudaEventElapsedTime(&t, tr[r][1], tr[r][2]); prep += t;
+				cudaEventElapsedTime(&t, tr[r][2], tr[r][3]); rest += t;
+				if (r + 1 < 32) { cudaEventElapsedTime(&t, tr[r][3], tr[r + 1][0]); gap += t; }
+			}
+			fprintf(stderr, "pipe trace (us per round): waits+memset %.1f, prep %.1f, walk+triage %.1f, round-to-round gap %.1f\n", wait / 32 * 1e3,
+					prep / 32 * 1e3, rest / 32 * 1e3, gap / 31 * 1e3);
+		}
+		for (auto &r4 : tr) for (auto &ev : r4) cudaEventDestroy(ev);
 	}
 	for (int k = 0; k < 2 && k < round; ++k) cudaStreamWaitEvent(st, ev_con[k], 0);  // the last selects / connects precede the statistics
 	cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st);

@@ -348,6 +348,12 @@ int gbp_plan_batch(const gbp_terrain *t, int64_t nq, const double *starts, const
 int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed,
                        uint64_t query0, const gbp_plan_params *params, gbp_plan_stats *stats, double *path_states,
                        double *path_actions, int path_cap, void *stream);
+/* Which form of the batch planner a call with these parameters and this many queries takes: 0 = the megakernel (k_plan_batch:
+ * one warp runs one query's whole search), 1 = the pipelined form (rounds of prep / flattened candidate walk / select /
+ * connect kernels over all queries: large batches of plain fixed-step RRT-Connect on terrains with the mixed-precision
+ * evaluator), 2 = the stepped form (GBP_PLAN_MODE=step).  Results are bit-identical; GBP_PLAN_MODE=mega|pipe|step in the
+ * environment forces a form where it applies (A/B measurements). */
+int gbp_plan_batch_form(const gbp_terrain *t, const gbp_plan_params *params, int64_t nq, int *form);
 /* gbp_plan_batch that also returns every query's two trees as they stand when its search ends (inspection and parity
  * tests: the trees are compared vertex by vertex with the reference's): row ((q * 2 + w) * tree_cap + i) of tree_states
  * [8], tree_actions [10], tree_parent, tree_g, tree_yaw holds vertex i of tree w (0 start side, 1 goal side) of query q;

@@ -152,6 +152,37 @@ def test_stop_after_solved(gbp):
     assert (early["iters"] <= full["iters"]).all() and early["iters"].sum() < full["iters"].sum()
 
 
+def test_pipelined_form_is_identical(gbp, monkeypatch):
+    """GBP_PLAN_MODE=pipe: rounds of k_pipe_prep / k_walk_seg / k_pipe_triage / k_pipe_select / k_pipe_connect over all queries
+    (the form large batches take) against the megakernel — statistics, paths and both trees of every query bit for bit,
+    first-valid and closest-valid selection, directional action sampling, tiny trees (capacity stop) and tiny budgets."""
+    T = load_terrain("synth_mixed"); o = po.Oracle(T)
+    t = gbp.Terrain(T.x, T.y, T.z, T.dx, T.dy, T.dz)
+    s, g = queries(o, T, 24, 5)
+    S, G = np.tile(s, (40, 1)), np.tile(g, (40, 1))
+    for P in (gbp.PlanParams(6, 0, 300, 128, 0, 0, 1), gbp.PlanParams(12, 1, 150, 64, 0, 0, 0),
+              gbp.PlanParams(6, 0, 200, 128, 0, 0, 0, 0, 0, 0, 1, 0, 0.0, 0.4, 1.0, 1.0), gbp.PlanParams(6, 0, 400, 6, 0, 0, 0),
+              gbp.PlanParams(6, 0, 3, 128, 0, 0, 0)):
+        monkeypatch.setenv("GBP_PLAN_MODE", "mega")
+        assert t.plan_batch_form(P, len(S)) == "megakernel"
+        a, pa_s, pa_a, ta = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
+        monkeypatch.setenv("GBP_PLAN_MODE", "pipe")
+        assert t.plan_batch_form(P, len(S)) == "pipelined"
+        b, pb_s, pb_a, tb = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
+        for k in a.dtype.names:
+            assert np.array_equal(a[k], b[k]), k
+        for i in range(len(S)):
+            n = int(a["path_states"][i])
+            assert np.array_equal(pa_s[i, :n], pb_s[i, :n]) and np.array_equal(pa_a[i, :max(n - 1, 0)], pb_a[i, :max(n - 1, 0)])
+        for (xa, xb), (ya, yb) in zip(ta, tb):
+            for k in xa:
+                assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), k
+    monkeypatch.delenv("GBP_PLAN_MODE")
+    assert t.plan_batch_form(gbp.PlanParams(6, 0, 300, 128, 0, 0, 0), 65536) == "pipelined"
+    assert t.plan_batch_form(gbp.PlanParams(6, 0, 300, 128, 0, 0, 0), 1000) == "megakernel"
+    assert t.plan_batch_form(gbp.PlanParams(6, 0, 300, 128, 0, 1, 0), 65536) == "megakernel"  # RRT* stays on the megakernel
+
+
 def test_stepped_form_is_identical(gbp, monkeypatch):
     """GBP_PLAN_MODE=step: one launch per half-iteration over the whole batch (k_step_half) instead of the megakernel — same
     trees, statistics and paths, bit for bit"""
