@@ -129,6 +129,24 @@ def first_solution_rounds(t, start, goal, P, nq, rounds, max_launches=60):
             "path_cost_m_mean": float(np.mean(costs)) if costs else None}
 
 
+def single_search_resident(gbp, t, start, goal, K, best, iters=400, seed=1, query=7):
+    """ONE search resident on the device (gbp_plan_batch with one query): wall clock of the host-pointer call over the extends it ran
+    (the valid random states among the STATE cells it consumed) -> microseconds per extend (+ its connect when the tree grew)."""
+    P = gbp.PlanParams(K, best, iters, 4096, 0, 0, 0)
+    t.plan_batch(start[None], goal[None], seed, 999, gbp.PlanParams(K, best, 3, 4096, 0, 0, 0))  # warm-up
+    dt, st = None, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        st = t.plan_batch(start[None], goal[None], seed, query, P)
+        d = time.perf_counter() - t0
+        dt = d if dt is None else min(dt, d)
+    rs = t.sample_states(seed, query, 0, 2 * int(st["iters"][0]))
+    extends = max(int(t.valid_states(rs, gbp.STANCE)[0].sum()), 1)
+    return {"form": t.plan_batch_form(P, 1), "us_per_extend_and_connect": dt / extends * 1e6, "extends": extends, "iterations": int(st["iters"][0]),
+            "vertices_added": int(st["nv_a"][0] + st["nv_b"][0]) - 2, "validated_actions_per_s": float(st["pair_checks"][0]) / dt,
+            "solved": int(st["solved"][0]), "seconds": dt, "api": "gbp_plan_batch, one query (host pointers; includes the call's upload, launch and read-back)"}
+
+
 def run_rough_k4096(gbp, torch, dev, nq=2368, iters=400, want_cpu=True):
     """BASELINE configs[1]: RRT-Connect on the reference's data/rough_terrain (committed as
     tests/golden/terrain_rough_terrain.npz), 4096 candidate actions per extend (closest valid), start (0,0) ->
@@ -171,7 +189,9 @@ def run_rough_k4096(gbp, torch, dev, nq=2368, iters=400, want_cpu=True):
                    "iterations_to_solve_mean": float(st["iters"][ok].mean()) if ok.any() else None,
                    "path_length_m_mean": float(st["path_length"][ok].mean()) if ok.any() else None,
                    "first_solution": first_solution_rounds(t, start, goal, gbp.PlanParams(4096, 1, iters, 512, 0, 0, 0, 1), 1184, 3, 8),
-                   "single_search": single},
+                   "single_search": single,
+                   "single_search_resident": {"K4096_closest_valid": single_search_resident(gbp, t, start, goal, 4096, 1, iters),
+                                              "K6_first_valid": single_search_resident(gbp, t, start, goal, 6, 0, iters)}},
            "solved_flag": bool(ok.any())}
     if want_cpu:  # the reference's own extend takes 6 candidates (NUM_GEN_STATES): its planner on the same query, all host cores
         out["reference_cpu"] = reference_cpu_planner("rough_terrain", 0, start, goal, 1.0, 25.0)

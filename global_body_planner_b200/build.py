@@ -12,7 +12,8 @@ _COMMON = ["gbp_device.cuh", "gbp_kernels.cuh", "gbp_host.h"]
 UNITS = {"gbp_capi.cu": _COMMON,
          "gbp_capi_validate.cu": _COMMON + ["gbp_walk.cuh", "gbp_sv.cuh"],
          "gbp_capi_plan.cu": _COMMON + ["gbp_planner.cuh"],
-         "gbp_capi_pipeline.cu": _COMMON + ["gbp_planner.cuh", "gbp_walk.cuh", "gbp_sv.cuh", "gbp_pipeline.cuh"]}
+         "gbp_capi_pipeline.cu": _COMMON + ["gbp_planner.cuh", "gbp_walk.cuh", "gbp_sv.cuh", "gbp_pipeline.cuh"],
+         "gbp_capi_wide.cu": _COMMON + ["gbp_planner.cuh", "gbp_wide.cuh"]}
 SOURCES = [os.path.join(CSRC, u) for u in UNITS]
 HEADERS = sorted({os.path.join(CSRC, h) for hs in UNITS.values() for h in hs}) + [PUBLIC_H]
 # -fmad=false: fp64 results must match the reference's x86-64 (no FMA) arithmetic bit for bit.

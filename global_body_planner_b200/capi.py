@@ -392,10 +392,10 @@ class Terrain:
         return (st, ps, pa) if path_cap else st
 
     def plan_batch_form(self, params, nq):
-        """0 megakernel, 1 pipelined, 2 stepped: the form gbp_plan_batch takes for these parameters and this batch size"""
+        """0 megakernel, 1 pipelined, 2 stepped, 3 device-wide: the form gbp_plan_batch takes for these parameters and this batch size"""
         f = C.c_int()
         _check(lib().gbp_plan_batch_form(self.h, C.byref(params), C.c_int64(nq), C.byref(f)))
-        return ("megakernel", "pipelined", "stepped")[f.value]
+        return ("megakernel", "pipelined", "stepped", "device-wide")[f.value]
 
     def plan_batch_trees(self, starts, goals, seed, query0, params, path_cap, tree_cap):
         """gbp_plan_batch_trees -> stats, path states, path actions, list of (tree A, tree B) dicts per query"""

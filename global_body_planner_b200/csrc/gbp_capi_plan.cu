@@ -7,6 +7,10 @@ bool gbp_plan_pipe_applies(const TerrainView &Tv, const gbp_plan_params &P, int6
 int gbp_plan_pipe_launch(const TerrainView &Tv, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
 						 const gbp_plan_params &P, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap, cudaStream_t st,
 						 const PlanTreeDump &dump, std::string &err);
+bool gbp_plan_wide_applies(const gbp_plan_params &P, int64_t nq);
+int gbp_plan_wide_launch(const TerrainView &Tv, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
+						 const gbp_plan_params &P, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap, cudaStream_t st,
+						 const PlanTreeDump &dump, std::string &err);
 
 extern "C" {
 
@@ -119,7 +123,9 @@ static int plan_dev(const gbp_terrain *t, int64_t nq, const double *starts, cons
 					const PlanTreeDump &dump, cudaStream_t st) {
 	keep_pool();
 	std::string err;
-	const int rc = gbp_plan_pipe_applies(t->view, *p, nq)
+	const int rc = gbp_plan_wide_applies(*p, nq)
+		? gbp_plan_wide_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, st, dump, err)
+		: gbp_plan_pipe_applies(t->view, *p, nq)
 		? gbp_plan_pipe_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, st, dump, err)
 		: plan_step_applies(*p, nq)
 		? plan_step_launch(t->view, nq, starts, goals, seed, query0, *p, stats, path_states, path_actions, path_cap, st, dump, err)
@@ -129,7 +135,7 @@ static int plan_dev(const gbp_terrain *t, int64_t nq, const double *starts, cons
 }
 int gbp_plan_batch_form(const gbp_terrain *t, const gbp_plan_params *p, int64_t nq, int *form) {
 	if (!t || !p || !form) return fail(GBP_E_INVALID, "bad arguments");
-	*form = gbp_plan_pipe_applies(t->view, *p, nq) ? 1 : (plan_step_applies(*p, nq) ? 2 : 0);
+	*form = gbp_plan_wide_applies(*p, nq) ? 3 : gbp_plan_pipe_applies(t->view, *p, nq) ? 1 : (plan_step_applies(*p, nq) ? 2 : 0);
 	return GBP_OK;
 }
 int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,

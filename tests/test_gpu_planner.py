@@ -204,3 +204,48 @@ def test_stepped_form_is_identical(gbp, monkeypatch):
     for (xa, xb), (ya, yb) in zip(ta, tb):
         for k in xa:
             assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), k
+
+
+@pytest.mark.parametrize("name", ["synth_mixed", "rough_terrain", "synth_nan"])
+def test_device_wide_form_is_identical(gbp, monkeypatch, name):
+    """GBP_PLAN_MODE=wide: one search at a time on a cooperative grid (k_plan_wide: newConfig's candidates spread over all SMs,
+    one grid barrier per extend, every CTA keeps its own copy of the trees) against the megakernel — statistics, paths and
+    both trees of every query bit for bit: K = 6 first-valid (32 lanes per candidate), closest-valid over 12 / 200 / 2000 / 4096 /
+    8000 / 40000 candidates (32, 16, 8, 4, 1 lanes per candidate; survivors of the first lanes redistributed over the CTA; several passes), post-processing, the fork's directional samplers, a tree
+    capacity stop, a tiny budget, the anytime stop."""
+    T = load_terrain(name); o = po.Oracle(T)
+    t = gbp.Terrain(T.x, T.y, T.z, T.dx, T.dy, T.dz)
+    S, G = queries(o, T, 6, 5)
+    plain = None
+    for P in (gbp.PlanParams(6, 0, 300, 128, 0, 0, 1), gbp.PlanParams(12, 1, 150, 64, 0, 0, 0), gbp.PlanParams(200, 1, 60, 64, 0, 0, 1),
+              gbp.PlanParams(4096, 1, 12, 64, 0, 0, 0), gbp.PlanParams(40000, 1, 3, 64, 0, 0, 0), gbp.PlanParams(2000, 1, 12, 64, 0, 0, 0),
+              gbp.PlanParams(8000, 1, 8, 64, 0, 0, 0), gbp.PlanParams(5000, 0, 8, 64, 0, 0, 0),
+              gbp.PlanParams(6, 0, 200, 128, 0, 0, 0, 0, 1, 1, 1, 1, 0.4, 0.4, 1.0, 0.5), gbp.PlanParams(6, 0, 400, 6, 0, 0, 0),
+              gbp.PlanParams(6, 0, 3, 128, 0, 0, 0), gbp.PlanParams(6, 0, 300, 128, 0, 0, 0, 2)):
+        monkeypatch.setenv("GBP_PLAN_MODE", "mega")
+        assert t.plan_batch_form(P, len(S)) == "megakernel"
+        a, pa_s, pa_a, ta = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
+        monkeypatch.setenv("GBP_PLAN_MODE", "wide")
+        assert t.plan_batch_form(P, len(S)) == "device-wide"
+        b, pb_s, pb_a, tb = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
+        if P.stop_after_solved:  # anytime stop: queries run in order here, so the first `stop_after_solved` that solve are kept
+            want = np.nonzero(plain["solved"])[0][:P.stop_after_solved]
+            assert np.array_equal(np.nonzero(b["solved"])[0], want)
+            last = want[-1] if len(want) == P.stop_after_solved else len(S) - 1
+            assert np.array_equal(b["iters"][:last + 1], plain["iters"][:last + 1]) and not b["iters"][last + 1:].any()
+            continue
+        if plain is None:
+            plain = a
+        for k in a.dtype.names:
+            assert np.array_equal(a[k], b[k]), (k, P.k_candidates)
+        for i in range(len(S)):
+            n = int(a["path_states"][i])
+            assert np.array_equal(pa_s[i, :n], pb_s[i, :n]) and np.array_equal(pa_a[i, :max(n - 1, 0)], pb_a[i, :max(n - 1, 0)])
+        for (xa, xb), (ya, yb) in zip(ta, tb):
+            for k in xa:
+                assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), k
+    monkeypatch.delenv("GBP_PLAN_MODE")
+    assert t.plan_batch_form(gbp.PlanParams(4096, 1, 300, 128, 0, 0, 0), 1) == "device-wide"   # a newConfig wider than the batch
+    assert t.plan_batch_form(gbp.PlanParams(6, 0, 300, 128, 0, 0, 0), 1) == "megakernel"
+    assert t.plan_batch_form(gbp.PlanParams(4096, 1, 300, 128, 0, 0, 0), 2368) == "megakernel"
+    assert t.plan_batch_form(gbp.PlanParams(4096, 1, 300, 128, 0, 1, 0), 1) == "megakernel"    # RRT* stays on the megakernel
