@@ -351,8 +351,11 @@ int gbp_plan_batch_dev(const gbp_terrain *t, int64_t nq, const double *starts, c
 /* Which form of the batch planner a call with these parameters and this many queries takes: 0 = the megakernel (k_plan_batch:
  * one warp runs one query's whole search), 1 = the pipelined form (rounds of prep / flattened candidate walk / select /
  * connect kernels over all queries: large batches of plain fixed-step RRT-Connect on terrains with the mixed-precision
- * evaluator), 2 = the stepped form (GBP_PLAN_MODE=step).  Results are bit-identical; GBP_PLAN_MODE=mega|pipe|step in the
- * environment forces a form where it applies (A/B measurements). */
+ * evaluator), 2 = the stepped form (GBP_PLAN_MODE=step), 3 = the device-wide form (k_plan_wide: one search at a time on a
+ * cooperative grid, the candidates of a newConfig spread over all SMs — batches with fewer queries than a newConfig has
+ * candidates / 256, e.g. ONE search at K = 4096: 18 us per extend + connect instead of 1.3 ms on one warp; plain fixed-step
+ * RRT-Connect).  Results are bit-identical; GBP_PLAN_MODE=mega|pipe|step|wide in the environment forces a form where it
+ * applies (A/B measurements). */
 int gbp_plan_batch_form(const gbp_terrain *t, const gbp_plan_params *params, int64_t nq, int *form);
 /* gbp_plan_batch that also returns every query's two trees as they stand when its search ends (inspection and parity
  * tests: the trees are compared vertex by vertex with the reference's): row ((q * 2 + w) * tree_cap + i) of tree_states
