@@ -246,16 +246,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        vals = []
+        vals, step_ms = [], []
         base = None
         for i in range(args.warmup + args.steps):
+            t_step = time.perf_counter()
             base, _, _ = run_cpu(seed, 100, args.cpu_seconds / 2, cores, "reference")
             if i >= args.warmup:
                 vals.append(base["value"])
+                step_ms.append((time.perf_counter() - t_step) * 1e3)  # a step = one bounded sample of the workload (see cpu_baseline.sample)
         v = float(np.mean(vals))
         base["value"] = v
         line = {"impl": "reference", "metric": "validated_actions_per_s", "value": v, "unit": "validated actions/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
                 "e2e": {"value": v, "unit": "validated actions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
