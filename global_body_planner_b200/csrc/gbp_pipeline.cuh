@@ -508,10 +508,33 @@ inline bool plan_pipe_applies(const TerrainView &Tv, const gbp_plan_params &P, i
 	return nq >= 32768;  // a round costs ~0.1 ms whatever the batch size: below ~20 k queries the megakernel's independent warps win
 }
 
+// What one pipeline needs on the host besides its main stream.  Pooled (gbp_capi_pipeline.cu): a call takes one per group of
+// queries it runs concurrently and gives it back.
+struct PipeHostRes {
+	int *h_count = nullptr;
+	cudaStream_t main = nullptr, sb = nullptr, sc = nullptr;  // main: the stream of a group that does not run on the caller's
+	cudaEvent_t ev_tri[2] = {}, ev_con[2] = {}, ev_prep[2] = {}, ev_bat[2] = {}, ev_sel[2] = {}, done = nullptr;
+	cudaError_t create() {
+		cudaError_t e = cudaHostAlloc((void **) &h_count, 2 * sizeof(int), cudaHostAllocDefault);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+		for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+			e = cudaEventCreateWithFlags(&ev_tri[k], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_sel[k], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_con[k], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_prep[k], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_bat[k], cudaEventDisableTiming);
+		}
+		return e;
+	}
+};
+
 template <typename M>
 inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double *starts, const double *goals, uint64_t seed, uint64_t query0,
 								 const gbp_plan_params &P, gbp_plan_stats *stats, double *path_states, double *path_actions, int path_cap,
-								 cudaStream_t st, const PlanTreeDump &dump, std::string &err) {
+								 cudaStream_t st, const PlanTreeDump &dump, PipeHostRes &R, std::string &err) {
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -577,29 +600,10 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	S.root_valid = bp; bp += 2 * Q;
 	G.flags = bp; bp += Q;
 	for (int k = 0; k < 2; ++k) { H[k].flags = bp; bp += Q; }
-	// host-side resources of the calling thread: a pinned word pair for the running count, the second stream and its events
-	static thread_local int *h_count = nullptr;
-	static thread_local cudaStream_t sb = nullptr, sc = nullptr;
-	static thread_local cudaEvent_t ev_tri[2] = {nullptr, nullptr}, ev_con[2] = {nullptr, nullptr}, ev_prep[2] = {nullptr, nullptr}, ev_bat[2] = {nullptr, nullptr},
-									ev_sel[2] = {nullptr, nullptr};
-	if (!h_count) {
-		e = cudaHostAlloc((void **) &h_count, 2 * sizeof(int), cudaHostAllocDefault);
-		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
-		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
-		for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-			e = cudaEventCreateWithFlags(&ev_tri[k], cudaEventDisableTiming);
-			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_sel[k], cudaEventDisableTiming);
-			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_con[k], cudaEventDisableTiming);
-			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_prep[k], cudaEventDisableTiming);
-			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_bat[k], cudaEventDisableTiming);
-		}
-		if (e != cudaSuccess) {
-			if (h_count) { cudaFreeHost(h_count); h_count = nullptr; }
-			cudaFreeAsync(mem, st);
-			err = std::string("pipelined planner: ") + cudaGetErrorString(e);
-			return GBP_E_CUDA;
-		}
-	}
+	// host-side resources of this pipeline (a pinned word pair for the running count, the two side streams and their events)
+	int *const h_count = R.h_count;
+	const cudaStream_t sb = R.sb, sc = R.sc;
+	cudaEvent_t *const ev_tri = R.ev_tri, *const ev_con = R.ev_con, *const ev_prep = R.ev_prep, *const ev_bat = R.ev_bat, *const ev_sel = R.ev_sel;
 	const unsigned walk_grid = (unsigned) sms * GBP_WALK_CTAS;
 	k_pipe_init<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, nq, starts, goals, P.max_iters);
 	cudaMemsetAsync(cnt, 0, (2 * CNT_WORDS + 2 * bit_words) * sizeof(int), st);

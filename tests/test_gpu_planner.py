@@ -177,6 +177,22 @@ def test_pipelined_form_is_identical(gbp, monkeypatch):
         for (xa, xb), (ya, yb) in zip(ta, tb):
             for k in xa:
                 assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), k
+    # the batch split into 3 groups of queries, each an independent pipeline on its own host thread and streams
+    monkeypatch.setenv("GBP_PIPE_GROUPS", "3")
+    P = gbp.PlanParams(6, 0, 300, 128, 0, 0, 1)
+    c, pc_s, pc_a, tc = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
+    monkeypatch.setenv("GBP_PIPE_GROUPS", "1")
+    d, pd_s, pd_a, td = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
+    monkeypatch.delenv("GBP_PIPE_GROUPS")
+    assert c["solved"].sum() >= 5
+    for k in c.dtype.names:
+        assert np.array_equal(c[k], d[k]), k
+    for i in range(len(S)):
+        n = int(c["path_states"][i])
+        assert np.array_equal(pc_s[i, :n], pd_s[i, :n]) and np.array_equal(pc_a[i, :max(n - 1, 0)], pd_a[i, :max(n - 1, 0)])
+    for (xa, xb), (ya, yb) in zip(tc, td):
+        for k in xa:
+            assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), k
     monkeypatch.delenv("GBP_PLAN_MODE")
     assert t.plan_batch_form(gbp.PlanParams(6, 0, 300, 128, 0, 0, 0), 65536) == "pipelined"
     assert t.plan_batch_form(gbp.PlanParams(6, 0, 300, 128, 0, 0, 0), 1000) == "megakernel"
