@@ -1,4 +1,7 @@
 // extern "C" layer, part 2: isValidStateActionPair[Reverse] for batches (gbp_validate_pairs*, gbp_sample_validate*).
+#include <chrono>
+#include <vector>
+
 #include "gbp_host.h"
 #include "gbp_walk.cuh"
 #include "gbp_sv.cuh"
@@ -235,7 +238,7 @@ static SvParams sv_device_params(const gbp_sv_params &p, const double *table, in
 // candidates [off, off + m) of a call; `bits`, `flags` are the call's arrays (off is a multiple of 32), `redo` = m ints
 static int sv_launch_range(const gbp_terrain *t, const gbp_sv_params &p, const double *table, int64_t rows, const int *idx, const uint8_t *dir, int64_t off,
 						   int64_t m, unsigned *bits, uint8_t *flags, unsigned long long *cnt, int *redo, unsigned long long *redo_count,
-						   cudaStream_t st) {
+						   cudaStream_t st, const unsigned *arrived = nullptr, unsigned long long *work = nullptr) {
 	const SvParams P = sv_device_params(p, table, rows, idx, dir, off);
 	unsigned *b = bits + off / 32;
 	uint8_t *f = flags ? flags + off : nullptr;
@@ -246,7 +249,8 @@ static int sv_launch_range(const gbp_terrain *t, const gbp_sv_params &p, const d
 		per_warp = (per_warp + 31) / 32 * 32;
 		const int64_t warps = (m + per_warp - 1) / per_warp;
 		cudaLaunchConfig_t cfg = {};
-		cfg.gridDim = dim3((unsigned) ((warps + RF_WARPS - 1) / RF_WARPS)); cfg.blockDim = dim3(RF_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+		cfg.gridDim = dim3(arrived ? (unsigned) (sm_count() * GBP_WALK_CTAS) : (unsigned) ((warps + RF_WARPS - 1) / RF_WARPS));
+		cfg.blockDim = dim3(RF_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
 		cudaLaunchAttribute attr[1];
 		cfg.attrs = attr; cfg.numAttrs = 0;
 		if (t->l2_hit_ratio > 0.f && !getenv("GBP_NO_L2_WINDOW")) {
@@ -262,7 +266,8 @@ static int sv_launch_range(const gbp_terrain *t, const gbp_sv_params &p, const d
 			attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
 			cfg.numAttrs = 1;
 		}
-#define GBP_SV_(TEX, AD) CU(cudaLaunchKernelEx(&cfg, k_walk_sv<TEX, AD>, t->view, P, (int) m, (int) per_warp, b, f, cnt, redo, redo_count))
+#define GBP_SV_(TEX, AD) do { if (arrived) CU(cudaLaunchKernelEx(&cfg, k_walk_sv_stream<TEX, AD>, t->view, P, (int) m, arrived, work, b, f, cnt, redo, redo_count)); \
+							  else CU(cudaLaunchKernelEx(&cfg, k_walk_sv<TEX, AD>, t->view, P, (int) m, (int) per_warp, b, f, cnt, redo, redo_count)); } while (0)
 		if (t->view.ztex) { if (p.adaptive) GBP_SV_(true, true); else GBP_SV_(true, false); }
 		else { if (p.adaptive) GBP_SV_(false, true); else GBP_SV_(false, false); }
 #undef GBP_SV_
@@ -356,40 +361,77 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 	if (n == 0) return GBP_OK;
 	if (!state_idx && (p->row0 < 0 || p->row0 + n > table->rows)) return fail(GBP_E_INVALID, "row0 + n exceeds the state table");
 	cudaStream_t st = lib_stream();
+	const bool sv_trace = getenv("GBP_SV_TRACE") != nullptr;  // host timestamps of the call's phases, to stderr
+	const auto sv_t0 = std::chrono::steady_clock::now();
+	auto sv_us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - sv_t0).count(); };
+	double sv_t_alloc = 0, sv_t_issued = 0, sv_t_walks = 0;
 	static thread_local cudaStream_t cs = nullptr;
 	static thread_local cudaEvent_t ev = nullptr;
 	static thread_local long long *h_result = nullptr;  // pinned
 	if (!cs) CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
 	if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 	if (!h_result) CU(cudaHostAlloc((void **) &h_result, 8 * sizeof(long long), cudaHostAllocDefault));
-	const int64_t nwords = (n + 31) / 32, CH = 1 << 21, nch = (n + CH - 1) / CH;
+	// Inputs travel in chunks on a copy stream while the compute stream walks what is already there.  On terrains with the
+	// mixed-precision walk the whole call is ONE launch (k_walk_sv_stream) whose warps wait for the block of inputs they
+	// need: each chunk's copies are followed by a copy that sets its arrival words.  Elsewhere: one launch per chunk.
+	const bool streamed = t->view.mixed_ok && (state_idx || direction) && n >= (2ll << SV_BLOCK_SHIFT) && !getenv("GBP_SV_NO_STREAM");
+	const int64_t BL = 1ll << SV_BLOCK_SHIFT, nblocks = (n + BL - 1) / BL;
+	std::vector<int64_t> chunk_off;  // streamed: 1, 1, 2, 4, 4 ... arrival blocks per chunk (the first copy is the only exposed one)
+	if (streamed) for (int64_t b = 0, w = 1, k = 0; b < nblocks; b += w, ++k, w = std::min<int64_t>(k < 2 ? 1 : 2 * w, 4)) chunk_off.push_back(b * BL);
+	else for (int64_t off = 0; off < n; off += 1 << 21) chunk_off.push_back(off);
+	chunk_off.push_back(n);
+	const int64_t nwords = (n + 31) / 32, nch = (int64_t) chunk_off.size() - 1;
 	const int64_t cap = !valid_index ? 0 : (valid_cap < n ? valid_cap : n);
+	static thread_local unsigned *h_ones = nullptr;  // pinned source of the arrival words
+	if (!h_ones) {
+		CU(cudaHostAlloc((void **) &h_ones, 8 * sizeof(unsigned), cudaHostAllocDefault));
+		for (int k = 0; k < 8; ++k) h_ones[k] = 1u;
+	}
 	Dev scratch(st), d_idx(st), d_dir(st), d_bits(st), d_flags(st), d_index(st), d_res(st), d_sn(st), d_tn(st), d_act(st);
-	CU(scratch.alloc((8 + 1024 + (size_t) nch) * sizeof(unsigned long long) + (size_t) n * sizeof(int)));
-	unsigned long long *cnt = scratch.as<unsigned long long>(), *sums = cnt + 8, *redo_counts = sums + 1024;
-	int *redo = (int *) (redo_counts + nch);
+	const size_t n_words64 = 8 + 1024 + (size_t) nch + 1 + (size_t) (nblocks + 1) / 2;  // counters, block sums, redo counts, work counter, arrival words
+	CU(scratch.alloc(n_words64 * sizeof(unsigned long long) + (size_t) n * sizeof(int)));
+	unsigned long long *cnt = scratch.as<unsigned long long>(), *sums = cnt + 8, *redo_counts = sums + 1024, *work = redo_counts + nch;
+	unsigned *arrived = (unsigned *) (work + 1);
+	int *redo = (int *) (cnt + n_words64);
 	if (state_idx) CU(d_idx.alloc((size_t) n * 4));
 	if (direction) CU(d_dir.alloc((size_t) n));
 	CU(d_bits.alloc((size_t) nwords * 4));
 	if (flags) CU(d_flags.alloc((size_t) n));
 	if (cap) CU(d_index.alloc((size_t) cap * 4));
 	CU(d_res.alloc(8 * sizeof(long long)));
-	CU(cudaMemsetAsync(cnt, 0, (8 + 1024 + (size_t) nch) * sizeof(unsigned long long), st));
+	CU(cudaMemsetAsync(cnt, 0, n_words64 * sizeof(unsigned long long), st));
 	CU(cudaMemsetAsync(d_bits.p, 0, (size_t) nwords * 4, st));
 	CU(cudaEventRecord(ev, st));
 	CU(cudaStreamWaitEvent(cs, ev, 0));  // the copy stream may touch the buffers once they exist in stream order
 	rc = GBP_OK;
+	sv_t_alloc = sv_us();
+	if (streamed)
+		rc = sv_launch_range(t, *p, table->d, table->rows, state_idx ? d_idx.as<int>() : nullptr, direction ? d_dir.as<uint8_t>() : nullptr, 0, n,
+							 d_bits.as<unsigned>(), flags ? d_flags.as<uint8_t>() : nullptr, cnt, redo, redo_counts, st, arrived, work);
+	cudaError_t ce = cudaSuccess;
 	for (int64_t c = 0; c < nch && rc == GBP_OK; ++c) {
-		const int64_t off = c * CH, m = n - off < CH ? n - off : CH;
+		const int64_t off = chunk_off[c], m = chunk_off[c + 1] - off;
 		cudaError_t e = cudaSuccess;
 		if (state_idx) e = cudaMemcpyAsync(d_idx.as<int>() + off, state_idx + off, (size_t) m * 4, cudaMemcpyHostToDevice, cs);
 		if (e == cudaSuccess && direction) e = cudaMemcpyAsync(d_dir.as<uint8_t>() + off, direction + off, (size_t) m, cudaMemcpyHostToDevice, cs);
+		if (streamed) {
+			// a failed copy must not leave the running kernel waiting: its blocks are released all the same, the call fails below
+			const cudaError_t e1 = cudaMemcpyAsync(arrived + off / BL, h_ones, (size_t) ((m + BL - 1) / BL) * sizeof(unsigned), cudaMemcpyHostToDevice, cs);
+			if (e == cudaSuccess) e = e1;
+			if (e != cudaSuccess) {
+				cudaMemsetAsync(arrived, 0xff, (size_t) nblocks * sizeof(unsigned), cs);
+				ce = e;
+				break;
+			}
+			continue;
+		}
 		if (e == cudaSuccess) e = cudaEventRecord(ev, cs);
 		if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
 		if (e != cudaSuccess) { rc = fail(GBP_E_CUDA, std::string("sample_validate copy: ") + cudaGetErrorString(e)); break; }
 		rc = sv_launch_range(t, *p, table->d, table->rows, state_idx ? d_idx.as<int>() : nullptr, direction ? d_dir.as<uint8_t>() : nullptr, off, m,
 							 d_bits.as<unsigned>(), flags ? d_flags.as<uint8_t>() : nullptr, cnt, redo + off, redo_counts + c, st);
 	}
+	if (ce != cudaSuccess) rc = fail(GBP_E_CUDA, std::string("sample_validate copy: ") + cudaGetErrorString(ce));
 	if (rc == GBP_OK) rc = sv_compact(n, d_bits.as<unsigned>(), sums, cap, cap ? d_index.as<int>() : nullptr, cnt, d_res.as<long long>(), st);
 	cudaError_t e = cudaSuccess;
 	if (rc == GBP_OK) {
@@ -397,7 +439,9 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 		if (e == cudaSuccess) e = cudaMemcpyAsync(verdict_bits, d_bits.p, (size_t) nwords * 4, cudaMemcpyDeviceToHost, st);
 		if (e == cudaSuccess && flags) e = cudaMemcpyAsync(flags, d_flags.p, (size_t) n, cudaMemcpyDeviceToHost, st);
 	}
+	sv_t_issued = sv_us();
 	cudaError_t e2 = cudaStreamSynchronize(cs), e3 = cudaStreamSynchronize(st);  // also on failure: no copy of the caller's buffers stays in flight
+	sv_t_walks = sv_us();
 	if (rc != GBP_OK) return rc;
 	if (e != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
 		return fail(GBP_E_CUDA, std::string("sample_validate: ") + cudaGetErrorString(e != cudaSuccess ? e : (e2 != cudaSuccess ? e2 : e3)));
@@ -422,6 +466,9 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 		}
 		CU(cudaStreamSynchronize(st));
 	}
+	if (sv_trace)
+		fprintf(stderr, "gbp_sample_validate trace (us): buffers %.0f, %d chunks issued %.0f, walks + compaction + verdict bits done %.0f, valid rows done %.0f\n",
+				sv_t_alloc, (int) nch, sv_t_issued, sv_t_walks, sv_us());
 	return GBP_OK;
 }
 

@@ -53,6 +53,11 @@ struct PipeState {  // per query
 };
 // per-round counters (one block per round parity): the kernels of a round on the second stream read them while the first
 // stream is already in the next round
+// Rounds a query sits out after triage handed it to select / connect: those run on their own streams while the following
+// rounds work on the other queries, and everything they use (heavy list, counter block, events) exists PIPE_DEPTH times.
+// 2 made prep(r) wait ~17 us per round for connect(r - 2) — select + connect of a round take about as long as a round.
+constexpr int PIPE_DEPTH = 2;
+
 enum : int { CNT_SEGS = 0, CNT_BUSY = 1, CNT_HEAVY = 2, CNT_CONNECTS = 3, CNT_BATCHES = 4, CNT_WORK = 5, CNT_WORDS = 8 };
 struct PipeHeavy {             // segments with a valid or an undecided candidate, copied out of the round's segment arrays
 	double *rows;              // [Q][PIPE_ROW]
@@ -341,7 +346,7 @@ __device__ __forceinline__ unsigned pipe_bits(const unsigned *__restrict__ words
 // triage, thread per segment: a segment whose candidates are all invalid (98 % of them) is TRAPPED — the query moves on to
 // its next half here.  The others are copied to the heavy list for k_pipe_select, which runs on the second stream while the
 // next round works on the other queries (their queries sit that round out), and their candidate bits are cleared.
-static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSegs G, PipeHeavy H, int K, int round) {
+static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSegs G, PipeHeavy H, int K, int round) {  // H: this round's slot
 	const int seg = blockIdx.x * blockDim.x + threadIdx.x;
 	if (seg >= G.count[CNT_SEGS]) return;
 	const int first = seg * K;
@@ -354,7 +359,7 @@ static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSeg
 #pragma unroll
 		for (int d = 0; d < PIPE_ROW / 2; ++d) dst[d] = src[d];
 		H.q[h] = q; H.near[h] = G.near[seg]; H.flags[h] = G.flags[seg]; H.idx0[h] = G.idx0[seg]; H.vmask[h] = vmask; H.umask[h] = umask;
-		S.busy_until[q] = round + 2;
+		S.busy_until[q] = round + PIPE_DEPTH;
 		const unsigned long long span = (K >= 32 ? 0xffffffffull : ((1ull << K) - 1ull)) << (first & 31);
 		const unsigned lo = (unsigned) span, hi = (unsigned) (span >> 32);
 		if (vmask) { atomicAnd(G.vbits + (first >> 5), ~lo); if (hi) atomicAnd(G.vbits + (first >> 5) + 1, ~hi); }
@@ -512,15 +517,16 @@ inline bool plan_pipe_applies(const TerrainView &Tv, const gbp_plan_params &P, i
 // queries it runs concurrently and gives it back.
 struct PipeHostRes {
 	int *h_count = nullptr;
-	cudaStream_t main = nullptr, sb = nullptr, sc = nullptr;  // main: the stream of a group that does not run on the caller's
-	cudaEvent_t ev_tri[2] = {}, ev_con[2] = {}, ev_prep[2] = {}, ev_bat[2] = {}, ev_sel[2] = {}, done = nullptr;
+	cudaStream_t main = nullptr, sb = nullptr, sc = nullptr, sd = nullptr;  // main: the stream of a group that does not run on the caller's
+	cudaEvent_t ev_tri[PIPE_DEPTH] = {}, ev_con[PIPE_DEPTH] = {}, ev_prep[PIPE_DEPTH] = {}, ev_bat[PIPE_DEPTH] = {}, ev_sel[PIPE_DEPTH] = {}, done = nullptr;
 	cudaError_t create() {
 		cudaError_t e = cudaHostAlloc((void **) &h_count, 2 * sizeof(int), cudaHostAllocDefault);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking);
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
-		for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+		for (int k = 0; k < PIPE_DEPTH && e == cudaSuccess; ++k) {
 			e = cudaEventCreateWithFlags(&ev_tri[k], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_sel[k], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_con[k], cudaEventDisableTiming);
@@ -541,17 +547,17 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	const size_t cap = (size_t) P.max_vertices, Q = (size_t) nq, per = Q * 2 * cap, K = (size_t) P.k_candidates;
 	const int64_t fin_slots = (int64_t) sms * 4 * 4;
 	const size_t bit_words = (Q * K + 31) / 32 + 2;
-	const size_t n_doubles = per * (8 + 10 + 1 + 1) + Q * 32 * 8 + 3 * Q * PIPE_ROW + (size_t) fin_slots * 2 * cap * 18;
-	const size_t n_ll = Q * 7 + 2;  // pair_checks, nn_queries, rs_base, rs_want, idx0 (round + 2 heavy buffers), finish counter
-	const size_t n_ints = per * 3 + Q * 21 + 2 * CNT_WORDS + 2 * bit_words;
-	const size_t need = n_doubles * 8 + n_ll * 8 + n_ints * 4 + Q * 5 + 64;
+	const size_t n_doubles = per * (8 + 10 + 1 + 1) + Q * 32 * 8 + (1 + PIPE_DEPTH) * Q * PIPE_ROW + (size_t) fin_slots * 2 * cap * 18;
+	const size_t n_ll = Q * (5 + PIPE_DEPTH) + 2;  // pair_checks, nn_queries, rs_base, rs_want, idx0 (round + the heavy buffers), finish counter
+	const size_t n_ints = per * 3 + Q * (10 + 5 * PIPE_DEPTH + PIPE_DEPTH) + PIPE_DEPTH * CNT_WORDS + 2 * bit_words;
+	const size_t need = n_doubles * 8 + n_ll * 8 + n_ints * 4 + Q * (3 + PIPE_DEPTH) + 64;
 	void *mem = nullptr;
 	cudaError_t e;
 	if ((e = cudaMallocAsync(&mem, need, st)) != cudaSuccess) { err = std::string("pipelined planner arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
 	PlanArena A = {}, Sc = {};
 	PipeState S;
 	PipeSegs G;
-	PipeHeavy H[2];
+	PipeHeavy H[PIPE_DEPTH];
 	A.cap = Sc.cap = P.max_vertices;
 	double *dp = (double *) mem;
 	A.v = dp; dp += per * 8;
@@ -560,7 +566,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	A.y = dp; dp += per;
 	S.rs = dp; dp += Q * 32 * 8;
 	G.rows = dp; dp += Q * PIPE_ROW;
-	for (int k = 0; k < 2; ++k) { H[k].rows = dp; dp += Q * PIPE_ROW; }
+	for (int k = 0; k < PIPE_DEPTH; ++k) { H[k].rows = dp; dp += Q * PIPE_ROW; }
 	Sc.pstate = dp; dp += (size_t) fin_slots * 2 * cap * 8;
 	Sc.paction = dp; dp += (size_t) fin_slots * 2 * cap * 10;
 	long long *lp = (long long *) dp;
@@ -569,7 +575,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	S.rs_base = lp; lp += Q;
 	S.rs_want = lp; lp += Q;
 	G.idx0 = (unsigned long long *) lp; lp += Q;
-	for (int k = 0; k < 2; ++k) { H[k].idx0 = (unsigned long long *) lp; lp += Q; }
+	for (int k = 0; k < PIPE_DEPTH; ++k) { H[k].idx0 = (unsigned long long *) lp; lp += Q; }
 	unsigned long long *next_query = (unsigned long long *) lp; lp += 2;
 	int *ip = (int *) lp;
 	A.parent = ip; ip += per;
@@ -585,36 +591,39 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	S.busy_until = ip; ip += Q;
 	G.q = ip; ip += Q;
 	G.near = ip; ip += Q;
-	for (int k = 0; k < 2; ++k) {
+	for (int k = 0; k < PIPE_DEPTH; ++k) {
 		H[k].q = ip; ip += Q;
 		H[k].near = ip; ip += Q;
 		H[k].vmask = (unsigned *) ip; ip += Q;
 		H[k].umask = (unsigned *) ip; ip += Q;
 		H[k].connects = ip; ip += Q;
 	}
-	int *batch_list = ip; ip += 2 * Q;  // queries that need their next batch of random states, double-buffered by round parity
-	int *cnt = ip; ip += 2 * CNT_WORDS;  // the two counter blocks, then the two bit arrays (zeroed once: triage clears what a round sets)
+	int *batch_list = ip; ip += PIPE_DEPTH * Q;  // queries that need their next batch of random states, one list per slot
+	int *cnt = ip; ip += PIPE_DEPTH * CNT_WORDS;  // the counter blocks, then the two bit arrays (zeroed once: triage clears what a round sets)
 	G.vbits = (unsigned *) ip; ip += bit_words;
 	G.ubits = (unsigned *) ip; ip += bit_words;
 	unsigned char *bp = (unsigned char *) ip;
 	S.root_valid = bp; bp += 2 * Q;
 	G.flags = bp; bp += Q;
-	for (int k = 0; k < 2; ++k) { H[k].flags = bp; bp += Q; }
+	for (int k = 0; k < PIPE_DEPTH; ++k) { H[k].flags = bp; bp += Q; }
 	// host-side resources of this pipeline (a pinned word pair for the running count, the two side streams and their events)
 	int *const h_count = R.h_count;
-	const cudaStream_t sb = R.sb, sc = R.sc;
+	const cudaStream_t sb = R.sb, sc = R.sc, sd = R.sd;
 	cudaEvent_t *const ev_tri = R.ev_tri, *const ev_con = R.ev_con, *const ev_prep = R.ev_prep, *const ev_bat = R.ev_bat, *const ev_sel = R.ev_sel;
-	const unsigned walk_grid = (unsigned) sms * GBP_WALK_CTAS;
+	int walk_ctas = GBP_WALK_CTAS;
+	if (const char *w = getenv("GBP_PIPE_WALK_CTAS")) walk_ctas = atoi(w) > 0 ? atoi(w) : walk_ctas;
+	const unsigned walk_grid = (unsigned) sms * walk_ctas;
 	k_pipe_init<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, nq, starts, goals, P.max_iters);
-	cudaMemsetAsync(cnt, 0, (2 * CNT_WORDS + 2 * bit_words) * sizeof(int), st);
+	cudaMemsetAsync(cnt, 0, (PIPE_DEPTH * CNT_WORDS + 2 * bit_words) * sizeof(int), st);
 	// A round runs one extend attempt of every running query; a query needs at most 2 * max_iters of them (every random state
 	// valid) plus the rounds it sits out.  The number of running queries is read back every 32 rounds to stop launching once
 	// all are done.
 	//   stream st: prep, walk, triage of round r.
-	//   stream sb: the batches of random states requested by prep(r) (needed by prep(r + 1)); then select for the few
-	//              queries of round r that have a valid or undecided candidate.
+	//   stream sd: the batches of random states requested by prep(r) (needed by prep(r + 1)).
+	//   stream sb: select for the few queries of round r that have a valid or undecided candidate.
 	//   stream sc: connect for the queries whose tree grew in select(r).
-	//              Select and connect overlap round r + 1, which their queries sit out, and are over before prep(r + 2).
+	//              Select and connect overlap the next rounds, which their queries sit out, and are over before
+	//              prep(r + PIPE_DEPTH).
 	const int max_rounds = 4 * P.max_iters + 4;
 	int round = 0;
 	// GBP_PIPE_TRACE=1: device timestamps of 32 consecutive rounds (after round 640) on the first stream, printed to stderr
@@ -622,13 +631,13 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	cudaEvent_t tr[32][4];
 	if (trace) for (auto &r4 : tr) for (auto &ev : r4) cudaEventCreate(&ev);
 	for (; round < max_rounds; ++round) {
-		const int par = round & 1;
+		const int par = round % PIPE_DEPTH, prev = (round + PIPE_DEPTH - 1) % PIPE_DEPTH;
 		const bool tr_on = trace && round >= 640 && round < 672;
 		if (tr_on) cudaEventRecord(tr[round - 640][0], st);
 		G.count = cnt + par * CNT_WORDS;
-		if (round >= 2) cudaStreamWaitEvent(st, ev_con[par], 0);  // select + connect of round - 2: its queries, heavy buffers and counters are free again
-		if (round >= 1) cudaStreamWaitEvent(st, ev_bat[par ^ 1], 0);  // the batches drawn for the previous round's requests
-		if (round >= 2) cudaMemsetAsync(G.count, 0, CNT_WORDS * sizeof(int), st);
+		if (round >= PIPE_DEPTH) cudaStreamWaitEvent(st, ev_con[par], 0);  // select + connect of round - PIPE_DEPTH: its queries, heavy buffers and counters are free again
+		if (round >= 1) cudaStreamWaitEvent(st, ev_bat[prev], 0);  // the batches drawn for the previous round's requests
+		if (round >= PIPE_DEPTH) cudaMemsetAsync(G.count, 0, CNT_WORDS * sizeof(int), st);
 		if (tr_on) cudaEventRecord(tr[round - 640][1], st);
 		k_pipe_prep<M><<<(unsigned) ((4 * Q + 127) / 128), 128, 0, st>>>(Tv, S, A, G, batch_list + (size_t) par * Q, nq, P, round);
 		cudaEventRecord(ev_prep[par], st);
@@ -638,9 +647,9 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 		k_pipe_triage<<<(unsigned) ((Q + 255) / 256), 256, 0, st>>>(S, G, H[par], P.k_candidates, round);
 		cudaEventRecord(ev_tri[par], st);
 		if (tr_on) cudaEventRecord(tr[round - 640][3], st);
-		cudaStreamWaitEvent(sb, ev_prep[par], 0);
-		k_pipe_batch<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, batch_list + (size_t) par * Q, G.count, seed, query0);
-		cudaEventRecord(ev_bat[par], sb);
+		cudaStreamWaitEvent(sd, ev_prep[par], 0);
+		k_pipe_batch<M><<<(unsigned) sms * 4, 128, 0, sd>>>(Tv, S, batch_list + (size_t) par * Q, G.count, seed, query0);
+		cudaEventRecord(ev_bat[par], sd);
 		cudaStreamWaitEvent(sb, ev_tri[par], 0);
 		k_pipe_select<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, A, H[par], G.count, seed, query0, P);
 		cudaEventRecord(ev_sel[par], sb);
@@ -668,7 +677,10 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 		}
 		for (auto &r4 : tr) for (auto &ev : r4) cudaEventDestroy(ev);
 	}
-	for (int k = 0; k < 2 && k < round; ++k) cudaStreamWaitEvent(st, ev_con[k], 0);  // the last selects / connects precede the statistics
+	for (int k = 0; k < PIPE_DEPTH && k < round; ++k) {  // the last batches / selects / connects precede the statistics
+		cudaStreamWaitEvent(st, ev_con[k], 0);
+		cudaStreamWaitEvent(st, ev_bat[k], 0);
+	}
 	cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st);
 	const int64_t fin_warps = (int64_t) Q < fin_slots ? (int64_t) ((Q + 3) / 4 * 4) : fin_slots;
 	k_pipe_finish<M><<<(unsigned) (fin_warps / 4), 128, 0, st>>>(Tv, S, A, Sc, nq, P, next_query, stats, path_states, path_actions, path_cap, dump);

@@ -170,6 +170,127 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_sv(Terrai
 	flush_counters(cnt, k, L, np, 0, 0, nvalid);
 }
 
+// k_walk_sv for inputs that are still ARRIVING: the host-pointer call (gbp_sample_validate) launches this kernel ONCE over
+// the whole call and copies row numbers and directions block by block on a second stream, each block followed by a copy
+// that sets the block's word in `arrived`.  Warps claim batches of 32 candidates from a counter, in ascending order, and
+// wait for the block a batch lies in — after the first block the copies run ahead of the walk (5 B against ~0.17 ns of
+// walk per candidate), so nothing waits again.  One launch instead of one per chunk: a launch ends in a tail of one long
+// candidate (~50 us), 8-9 of them were 0.5 ms of a 3.6 ms call.  Verdicts and counters do not depend on which warp walks a
+// candidate.  A block that never arrives (failed copy) ends the wait after ~2^24 polls and is reported in cnt[7].
+constexpr int SV_BLOCK_SHIFT = 19;  // 524,288 candidates per arrival word
+__device__ __forceinline__ unsigned sv_ld_acquire(const unsigned *p) {
+	unsigned v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+template <bool TEX, bool ADAPTIVE>
+__global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_sv_stream(TerrainView T, SvParams P, int n, const unsigned *__restrict__ arrived,
+																				   unsigned long long *__restrict__ work, unsigned *__restrict__ bits,
+																				   uint8_t *__restrict__ flags, unsigned long long *__restrict__ cnt,
+																				   int *__restrict__ redo_idx, unsigned long long *__restrict__ redo_count) {
+	__shared__ __align__(16) double ringS[RF_WARPS][SV_CAP][8];
+	__shared__ __align__(16) double ringA[RF_WARPS][SV_CAP][10];
+	__shared__ __align__(16) double stash[8][RF_WARPS * 32];
+	__shared__ uint8_t ringD[RF_WARPS][SV_CAP];
+	__shared__ int ringI[RF_WARPS][SV_CAP];
+	__shared__ double sR[9];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	if (threadIdx.x == 0) grf_rotation(P.normal, sR);
+	__syncthreads();
+	double *const st = &stash[0][threadIdx.x];
+	const uint64_t pol = l2_evict_first_policy();
+	int next = 0, filled = 0;  // candidates handed out / produced by this warp
+	bool exhausted = false;
+	WalkCursor q;
+	q.phase = PH_IDLE;
+	int mine = -1;
+	unsigned k = 0, L = 0, np = 0, nvalid = 0;
+	while (true) {
+		const unsigned need = __ballot_sync(FULL, q.phase == PH_IDLE);
+		if (need && (next < filled || !exhausted)) {
+			const int nidle = __popc(need);
+			if (filled - next < nidle && !exhausted && filled - next <= SV_CAP - 32) {
+				long long base = 0;
+				if (lane == 0) {
+					base = (long long) atomicAdd(work, 32ull);
+					if (base < n) {  // wait for the block of row numbers / directions this batch lies in
+						unsigned spins = 0;
+						while (sv_ld_acquire(arrived + (base >> SV_BLOCK_SHIFT)) == 0u)
+							if (++spins > (1u << 24)) { atomicAdd(cnt + 7, 1ull); base = n; break; }
+					}
+				}
+				base = __shfl_sync(FULL, base, 0);
+				const int c = (int) min(32ll, (long long) n - base);
+				if (c <= 0) exhausted = true;
+				if (lane < c) {
+					const int e = (filled + lane) % SV_CAP;
+					const int i = (int) base + lane;
+					long long row = P.state_idx ? (long long) __ldcs(P.state_idx + i) : P.row0 + i;
+					if ((unsigned long long) row >= (unsigned long long) P.rows) { row = 0; atomicAdd(cnt + 6, 1ull); }
+					const double *src = P.table + 8 * row;
+#pragma unroll
+					for (int d = 0; d < 4; ++d) cp_async16_hint(&ringS[wib][e][2 * d], src + 2 * d, pol);
+					const int dv = P.dir ? (int) __ldcs(P.dir + i) : P.dir0;
+					ringD[wib][e] = (uint8_t) dv;
+					ringI[wib][e] = i;
+					double vx = 0, vy = 0;
+					if (P.dir_sampling) { vx = __ldg(src + 3); vy = __ldg(src + 4); }
+					sv_sample_to_ring(P.seed, P.stream, P.idx0 + (uint64_t) i, sR, P.dir_sampling, P.dir_thresh, P.target[3], P.target[4], dv, vx, vy, &ringA[wib][e][0]);
+				}
+				cp_async_wait_all();
+				__syncwarp();
+				filled += max(c, 0);
+			}
+			if (q.phase == PH_IDLE) {
+				const int rel = next + __popc(need & ((1u << lane) - 1));
+				if (rel < filled) {
+					const int e = rel % SV_CAP;
+					const double2 *ps = reinterpret_cast<const double2 *>(&ringS[wib][e][0]);
+					const double2 *pa = reinterpret_cast<const double2 *>(&ringA[wib][e][0]);
+					double s[8], a[10];
+#pragma unroll
+					for (int d = 0; d < 4; ++d) { const double2 v = ps[d]; s[2 * d] = v.x; s[2 * d + 1] = v.y; }
+#pragma unroll
+					for (int d = 0; d < 5; ++d) { const double2 v = pa[d]; a[2 * d] = v.x; a[2 * d + 1] = v.y; }
+					mine = ringI[wib][e];
+					walk_start(q, s, a, (int) ringD[wib][e], st);
+					if (P.states_valid && q.t == 0 && (q.phase == PH_FWD_ST || q.phase == PH_REV_FL)) {  // see k_walk_sv
+						OutRecipe dummy;
+						q.c_.substates = 1; q.c_.nanprobes = 5; q.c_.lookups = 9;
+						(void) walk_advance<ADAPTIVE>(q, true, dummy, st);
+					}
+				}
+			}
+			next = min(filled, next + nidle);
+			__syncwarp();  // ring entries are read before a later batch may overwrite them
+		}
+		if (__ballot_sync(FULL, q.phase != PH_IDLE) == 0) {
+			if (exhausted && next >= filled) break;
+			continue;
+		}
+		bool valid = false, decided = true;
+		if (q.phase != PH_IDLE) {
+			const int ph = (q.phase == PH_FWD_FL || q.phase == PH_REV_FL) ? GBP_FLIGHT : GBP_STANCE;
+			decided = is_valid_state_mixed<MapF32U, TEX>(T, walk_pose(q), ph, q.c_, valid);
+		}
+		if (!decided) {  // hand the whole candidate to the fp64 pass
+			redo_idx[atomicAdd(redo_count, 1ull)] = mine;
+			q.phase = PH_IDLE;
+		}
+		if (q.phase != PH_IDLE) {
+			OutRecipe out;
+			const int r = walk_advance<ADAPTIVE>(q, valid, out, st);
+			if (r) {
+				if (r == 2) atomicOr(bits + (mine >> 5), 1u << (mine & 31));
+				if (flags) __stcs(flags + mine, (uint8_t) (r == 2 ? GBP_FLAG_VALID : 0));
+				k += q.c_.substates; L += q.c_.lookups; np += q.c_.nanprobes; nvalid += r == 2 ? 1 : 0;
+				q.phase = PH_IDLE;
+			}
+		}
+	}
+	flush_counters(cnt, k, L, np, 0, 0, nvalid);
+}
+
 // the candidate's inputs, rebuilt from its index (redo pass, general path, output pass)
 __device__ __forceinline__ void sv_candidate(const SvParams &P, const double *R, int64_t i, double s[8], double a[10], int &dir) {
 	long long row = P.state_idx ? (long long) P.state_idx[i] : P.row0 + i;

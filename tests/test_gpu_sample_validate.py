@@ -206,3 +206,30 @@ def test_device_pointer_entry(gbp, env):
     assert_bits_equal(sn.cpu().numpy()[:m], sno[want[:m]], what="s_new (device entry)")
     assert_bits_equal(tn.cpu().numpy()[:m], tno[want[:m]], what="t_new (device entry)")
     assert_bits_equal(ac.cpu().numpy()[:m], a[want[:m]], what="action (device entry)")
+
+
+@pytest.mark.parametrize("promise", [False, True])
+def test_streamed_host_call_matches_chunked_and_oracle(gbp, env, monkeypatch, promise):
+    """gbp_sample_validate on >= 2^20 candidates: ONE launch whose warps wait for the blocks of row numbers / directions the copy
+    stream is still delivering (k_walk_sv_stream) against the launch-per-chunk form (GBP_SV_NO_STREAM) — verdict words, valid
+    rows, work counters — and, on a slice, against the oracle."""
+    name, t, o, T = env
+    n = (1 << 20) + (1 << 19) + 12345  # three arrival blocks, the last one ragged
+    table = vertex_table(o, 60000, seed=5)
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, len(table), n).astype(np.int32)
+    d = rng.integers(0, 2, n).astype(np.uint8)
+    tab = gbp.States(table)
+    p = gbp.sv_params(31, 32, 1000, states_valid=promise)
+    a = t.sample_validate(tab, n, p, state_idx=idx, direction=d, valid_cap=n, want_flags=False)
+    monkeypatch.setenv("GBP_SV_NO_STREAM", "1")
+    b = t.sample_validate(tab, n, p, state_idx=idx, direction=d, valid_cap=n, want_flags=False)
+    monkeypatch.delenv("GBP_SV_NO_STREAM")
+    assert np.array_equal(a["bits"], b["bits"]) and a["n_valid"] == b["n_valid"] and a["counters"] == b["counters"]
+    assert np.array_equal(a["index"], b["index"])
+    assert_bits_equal(a["s_new"], b["s_new"], what="s_new"); assert_bits_equal(a["t_new"], b["t_new"], what="t_new")
+    assert_bits_equal(a["action"], b["action"], what="action")
+    lo, m = (1 << 20) - 3000, 6000  # a slice across the first block boundary
+    acts = o.sample_actions(31, 32, 1000 + lo, m)
+    vo, fo, sno, tno, cnt = o.validate_pairs(table[idx[lo:lo + m]], acts, d[lo:lo + m], nthreads=8)
+    assert np.array_equal(a["verdict"][lo:lo + m], vo)
