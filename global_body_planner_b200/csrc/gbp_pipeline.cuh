@@ -55,7 +55,9 @@ struct PipeState {  // per query
 // stream is already in the next round
 // Rounds a query sits out after triage handed it to select / connect: those run on their own streams while the following
 // rounds work on the other queries, and everything they use (heavy list, counter block, events) exists PIPE_DEPTH times.
-// 2 made prep(r) wait ~17 us per round for connect(r - 2) — select + connect of a round take about as long as a round.
+// With 2, prep(r) waits ~17 us per round for connect(r - 2) (select + connect of a round take about as long as a round);
+// with 3 that wait is 4 us but the queries that grew sit out one more round and the batch needs 13 % more rounds: 0.376 s
+// against 0.358 s on configs[4].
 constexpr int PIPE_DEPTH = 2;
 
 enum : int { CNT_SEGS = 0, CNT_BUSY = 1, CNT_HEAVY = 2, CNT_CONNECTS = 3, CNT_BATCHES = 4, CNT_WORK = 5, CNT_WORDS = 8 };
