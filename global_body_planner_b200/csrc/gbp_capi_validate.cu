@@ -310,11 +310,11 @@ int gbp_sample_validate_dev(const gbp_terrain *t, const double *states_dev, int6
 	if ((valid_s_new || valid_t_new || valid_action) && !valid_index) return fail(GBP_E_INVALID, "valid rows need valid_index");
 	cudaStream_t st = (cudaStream_t) stream;
 	const int64_t nwords = (n + 31) / 32;
-	Dev scratch(st);  // [cnt 7 | redo_count 1 | sums 1024] u64, then the redo list
-	CU(scratch.alloc((8 + 1024) * sizeof(unsigned long long) + (size_t) (n ? n : 1) * sizeof(int)));
-	unsigned long long *cnt = scratch.as<unsigned long long>(), *redo_count = cnt + 7, *sums = cnt + 8;
+	Dev scratch(st);  // [cnt 8 | redo_count 1 | sums 1024] u64, then the redo list
+	CU(scratch.alloc((9 + 1024) * sizeof(unsigned long long) + (size_t) (n ? n : 1) * sizeof(int)));
+	unsigned long long *cnt = scratch.as<unsigned long long>(), *redo_count = cnt + 8, *sums = cnt + 9;
 	int *redo = (int *) (sums + 1024);
-	CU(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), st));
+	CU(cudaMemsetAsync(cnt, 0, 9 * sizeof(unsigned long long), st));
 	if (nwords) CU(cudaMemsetAsync(bits, 0, (size_t) nwords * 4, st));
 	if (n && (rc = sv_launch_range(t, *p, states_dev, table_rows, state_idx_dev, direction_dev, 0, n, bits, flags, cnt, redo, redo_count, st))) return rc;
 	if ((rc = sv_compact(n, bits, sums, valid_index ? valid_cap : 0, valid_index, cnt, (long long *) result_dev, st))) return rc;
@@ -374,7 +374,9 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 	// Inputs travel in chunks on a copy stream while the compute stream walks what is already there.  On terrains with the
 	// mixed-precision walk the whole call is ONE launch (k_walk_sv_stream) whose warps wait for the block of inputs they
 	// need: each chunk's copies are followed by a copy that sets its arrival words.  Elsewhere: one launch per chunk.
-	const bool streamed = t->view.mixed_ok && (state_idx || direction) && n >= (2ll << SV_BLOCK_SHIFT) && !getenv("GBP_SV_NO_STREAM");
+	// (not under CUDA_LAUNCH_BLOCKING: the launch would return only after the kernel, which waits for copies issued after it)
+	const bool streamed = t->view.mixed_ok && (state_idx || direction) && n >= (2ll << SV_BLOCK_SHIFT) && !getenv("GBP_SV_NO_STREAM") &&
+						  !getenv("CUDA_LAUNCH_BLOCKING");
 	const int64_t BL = 1ll << SV_BLOCK_SHIFT, nblocks = (n + BL - 1) / BL;
 	std::vector<int64_t> chunk_off;  // streamed: 1, 1, 2, 4, 4 ... arrival blocks per chunk (the first copy is the only exposed one)
 	if (streamed) for (int64_t b = 0, w = 1, k = 0; b < nblocks; b += w, ++k, w = std::min<int64_t>(k < 2 ? 1 : 2 * w, 4)) chunk_off.push_back(b * BL);
@@ -448,6 +450,7 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 	memcpy(result, h_result, sizeof *result);
 	// row numbers are checked where they are read (a host-side scan of 16 M indices costs more than the whole call): a row
 	// outside the table was read as row 0 and counted; the call's results are void then
+	if (result->reserved[1] > 0) return fail(GBP_E_CUDA, "sample_validate: input blocks did not reach the running kernel (copy stream stalled)");
 	if (result->reserved[0] > 0) return fail(GBP_E_INVALID, "state_idx entry outside the state table");
 	const int64_t rows = result->n_valid < cap ? result->n_valid : cap;
 	if (rows > 0) {

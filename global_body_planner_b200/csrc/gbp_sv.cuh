@@ -394,7 +394,7 @@ static __global__ void __launch_bounds__(256) k_sv_list(const unsigned *__restri
 		if (blockIdx.x == 0) {
 			result[0] = (long long) s;
 			for (int j = 0; j < 5; ++j) result[1 + j] = (long long) cnt[j];
-			result[6] = (long long) cnt[6]; result[7] = 0;
+			result[6] = (long long) cnt[6]; result[7] = (long long) cnt[7];  // [7]: batches of a streamed call whose inputs never arrived
 			s = 0;
 		}
 		s_base = s;

@@ -204,9 +204,12 @@ typedef struct {
 	int64_t n_valid;                             /* valid candidates of the call (may exceed valid_cap) */
 	int64_t substates, lookups, nanprobes;       /* work under the reference's early-exit semantics (k, L, heightIsNan calls) */
 	int64_t oog, near;                           /* candidates flagged GBP_FLAG_OOG / GBP_FLAG_NEAR */
-	int64_t reserved[2];                         /* [0]: row numbers outside the table (results are void when > 0) */
+	int64_t reserved[2];                         /* [0]: row numbers outside the table (results are void when > 0); [1]: internal (0) */
 } gbp_sv_result; /* 64 bytes */
 
+/* HOST pointers.  Row numbers and directions travel in blocks on a copy stream while ONE launch walks the call: its warps
+ * wait for the block their candidates lie in (after the first block the copies run ahead of the walk); verdict bits come
+ * back as one copy, the rows of the valid candidates once their number is known.  GBP_SV_TRACE=1 prints the phases. */
 int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n, const int32_t *state_idx,
                         const uint8_t *direction, const gbp_sv_params *params, uint32_t *verdict_bits, uint8_t *flags,
                         int64_t valid_cap, int32_t *valid_index, double *valid_s_new, double *valid_t_new,
