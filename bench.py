@@ -14,8 +14,9 @@ and a direction byte in, the action sampled in-kernel from the Philox stream sha
 a verdict bit out, and {index, s_new, t_new, action} for the valid candidates only.
 
   value : per-candidate inputs resident in HBM (gbp_sample_validate_dev), CUDA-event timed.
-  e2e   : the same call with HOST buffers (gbp_sample_validate, pinned): row numbers + directions H2D,
-          verdict bits + valid rows D2H inside the timed region; the state table stays resident.
+  e2e   : the same call with HOST buffers (gbp_sample_validate, pinned): one 4-byte word per candidate H2D
+          (row number | direction << 31), verdict bits + valid rows D2H inside the timed region; the state
+          table stays resident.
   dense : the full-fidelity call of round 1 (gbp_validate_pairs[_dev]: explicit fp64 actions in, verdict,
           flags, s_new, t_new for every candidate out) on the same candidates — secondary number and the
           cross-check: the narrow path's bits, rows and work counters must equal it.
@@ -408,8 +409,9 @@ def main():
         hrows = states.cpu().numpy()
         tab = gbp.States(hrows)
         del hrows
-        hidx = torch.empty(n, dtype=torch.int32, pin_memory=True); hidx.copy_(idx)
-        hd = torch.empty(n, dtype=torch.uint8, pin_memory=True); hd.copy_(direction)
+        # one 4-byte word per candidate on the wire: row number | direction << 31 (gbp_sv_params.direction_in_row)
+        hidx = torch.empty(n, dtype=torch.int32, pin_memory=True); hidx.copy_(idx | (direction.to(torch.int32) << 31))
+        sv_wire = gbp.sv_params(seed, stream_id + 1, 0, states_valid=True, direction_in_row=True)
         hbits = torch.empty(nw, dtype=torch.int32, pin_memory=True)
         hvi = torch.empty(cap, dtype=torch.int32, pin_memory=True); hvsn = torch.empty((cap, 8), dtype=torch.float64, pin_memory=True)
         hvtn = torch.empty(cap, dtype=torch.float64, pin_memory=True); hvac = torch.empty((cap, 10), dtype=torch.float64, pin_memory=True)
@@ -417,7 +419,7 @@ def main():
         torch.cuda.synchronize()
 
         def e2e_step():
-            rc = L.gbp_sample_validate(t.h, tab.h, C.c_int64(n), vp(hidx), vp(hd), C.byref(sv), vp(hbits), None, C.c_int64(cap), vp(hvi),
+            rc = L.gbp_sample_validate(t.h, tab.h, C.c_int64(n), vp(hidx), None, C.byref(sv_wire), vp(hbits), None, C.c_int64(cap), vp(hvi),
                                        vp(hvsn), vp(hvtn), vp(hvac), C.byref(hres))
             assert rc == 0, L.gbp_last_error()
 
@@ -435,12 +437,12 @@ def main():
         assert hres.n_valid == n_valid and torch.equal(hbits, bits.cpu()), "e2e verdict bits differ from the resident run"
         assert torch.equal(hvsn[:n_valid].view(torch.int64), vsn[:n_valid].cpu().view(torch.int64)), "e2e valid rows differ from the resident run"
         e2e = {"value": world * n * args.e2e_steps / float(te.item()), "unit": "validated actions/s",
-               "h2d_bytes_per_step": n * (4 + 1), "d2h_bytes_per_step": nw * 4 + n_valid * (4 + 64 + 8 + 80) + 64, "steps": args.e2e_steps,
-               "api": "gbp_sample_validate (host pointers, pinned): 4-byte state-table row + direction byte per candidate in, verdict bit per "
+               "h2d_bytes_per_step": n * 4, "d2h_bytes_per_step": nw * 4 + n_valid * (4 + 64 + 8 + 80) + 64, "steps": args.e2e_steps,
+               "api": "gbp_sample_validate (host pointers, pinned): one 4-byte word per candidate in (state-table row | direction << 31), verdict bit per "
                       "candidate + {index, s_new, t_new, action} per VALID candidate out; state table resident on the device",
                "state_table_bytes_resident": n * 64}
         tab.close()
-        del hidx, hd, hbits, hvi, hvsn, hvtn, hvac
+        del hidx, hbits, hvi, hvsn, hvtn, hvac
         if world == 1 and not args.no_full_e2e:
             # the dense host-pointer call of round 1 (every input and every output crosses PCIe: 219 B per candidate), one step
             hs = torch.empty((n, 8), dtype=torch.float64, pin_memory=True); hs.copy_(states)

@@ -32,7 +32,7 @@ class SvParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("stream", C.c_uint64), ("idx0", C.c_uint64), ("normal", C.c_double * 3),
                 ("adaptive", C.c_int), ("direction0", C.c_int), ("action_direction_sampling", C.c_int),
                 ("action_direction_threshold", C.c_double), ("target", C.c_double * 8), ("row0", C.c_int64),
-                ("start_states_valid", C.c_int), ("reserved", C.c_int)]
+                ("start_states_valid", C.c_int), ("direction_in_row", C.c_int)]
 
 
 class SvResult(C.Structure):
@@ -40,8 +40,9 @@ class SvResult(C.Structure):
                 ("oog", C.c_int64), ("near", C.c_int64), ("reserved", C.c_int64 * 2)]
 
 
-def sv_params(seed, stream, idx0, normal=(0.0, 0.0, 1.0), adaptive=False, direction0=0, target=None, thresh=0.0, row0=0, states_valid=False):
+def sv_params(seed, stream, idx0, normal=(0.0, 0.0, 1.0), adaptive=False, direction0=0, target=None, thresh=0.0, row0=0, states_valid=False, direction_in_row=False):
     p = SvParams()
+    p.direction_in_row = int(direction_in_row)
     p.start_states_valid = int(states_valid)
     p.seed, p.stream, p.idx0 = seed, stream, idx0
     p.normal[:] = [float(v) for v in normal]
@@ -50,6 +51,13 @@ def sv_params(seed, stream, idx0, normal=(0.0, 0.0, 1.0), adaptive=False, direct
     p.action_direction_threshold = float(thresh)
     p.target[:] = [0.0] * 8 if target is None else [float(v) for v in target]
     return p
+
+
+def pack_rows(state_idx, direction):
+    """The one-word wire format of gbp_sample_validate (gbp_sv_params.direction_in_row): row number | direction << 31."""
+    r = np.ascontiguousarray(state_idx, dtype=np.int64)
+    assert r.min(initial=0) >= 0 and r.max(initial=0) < 2 ** 31
+    return (r | (np.asarray(direction, dtype=np.int64) << 31)).astype(np.uint32).view(np.int32)
 
 
 PLAN_STATS_DTYPE = np.dtype([("solved", "i4"), ("iters", "i4"), ("nv_a", "i4"), ("nv_b", "i4"), ("path_states", "i4"),

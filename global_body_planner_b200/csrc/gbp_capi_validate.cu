@@ -224,6 +224,7 @@ static SvParams sv_device_params(const gbp_sv_params &p, const double *table, in
 	P.rows = (long long) rows;
 	P.state_idx = idx ? idx + off : nullptr;
 	P.dir = dir ? dir + off : nullptr;
+	P.dir_packed = p.direction_in_row ? 1 : 0;
 	P.row0 = (long long) (p.row0 + off);
 	P.dir0 = p.direction0;
 	P.seed = p.seed; P.stream = p.stream; P.idx0 = p.idx0 + (uint64_t) off;
@@ -293,10 +294,11 @@ static int sv_compact(int64_t n, const unsigned *bits, unsigned long long *sums,
 	CU(cudaGetLastError());
 	return GBP_OK;
 }
-static int sv_check(const gbp_terrain *t, int64_t n, const gbp_sv_params *p, const void *bits, int64_t valid_cap) {
+static int sv_check(const gbp_terrain *t, int64_t n, const gbp_sv_params *p, const void *bits, int64_t valid_cap, const void *idx, const void *dir) {
 	if (!t || !p || n < 0 || (n && !bits) || valid_cap < 0) return fail(GBP_E_INVALID, "bad arguments");
 	if (n > 0x7fffffff) return fail(GBP_E_INVALID, "at most 2^31-1 candidates per call");
 	if (p->direction0 != GBP_FORWARD && p->direction0 != GBP_REVERSE) return fail(GBP_E_INVALID, "direction0 must be GBP_FORWARD or GBP_REVERSE");
+	if (p->direction_in_row && (!idx || dir)) return fail(GBP_E_INVALID, "direction_in_row needs state_idx and a NULL direction array");
 	return GBP_OK;
 }
 
@@ -304,7 +306,7 @@ int gbp_sample_validate_dev(const gbp_terrain *t, const double *states_dev, int6
 							const gbp_sv_params *p, uint32_t *bits, uint8_t *flags, int64_t valid_cap, int32_t *valid_index, double *valid_s_new,
 							double *valid_t_new, double *valid_action, int64_t *result_dev, void *stream) {
 	int rc;
-	if ((rc = sv_check(t, n, p, bits, valid_cap))) return rc;
+	if ((rc = sv_check(t, n, p, bits, valid_cap, state_idx_dev, direction_dev))) return rc;
 	if (!states_dev || !result_dev || table_rows < 1) return fail(GBP_E_INVALID, "states_dev (table_rows >= 1) and result_dev are required");
 	if (((uintptr_t) states_dev) & 15) return fail(GBP_E_INVALID, "the state table must be 16-byte aligned");
 	if ((valid_s_new || valid_t_new || valid_action) && !valid_index) return fail(GBP_E_INVALID, "valid rows need valid_index");
@@ -331,7 +333,7 @@ int gbp_sample_validate_dev(const gbp_terrain *t, const double *states_dev, int6
 int gbp_sample_validate_walk_dev(const gbp_terrain *t, const double *states_dev, int64_t table_rows, int64_t n, const int32_t *state_idx_dev,
 								 const uint8_t *direction_dev, const gbp_sv_params *p, uint32_t *bits, int64_t *counters8_dev, void *stream) {
 	int rc;
-	if ((rc = sv_check(t, n, p, bits, 0))) return rc;
+	if ((rc = sv_check(t, n, p, bits, 0, state_idx_dev, direction_dev))) return rc;
 	if (!states_dev || !counters8_dev || table_rows < 1) return fail(GBP_E_INVALID, "states_dev (table_rows >= 1) and counters8_dev are required");
 	if (((uintptr_t) states_dev) & 15) return fail(GBP_E_INVALID, "the state table must be 16-byte aligned");
 	cudaStream_t st = (cudaStream_t) stream;
@@ -354,7 +356,7 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 						const gbp_sv_params *p, uint32_t *verdict_bits, uint8_t *flags, int64_t valid_cap, int32_t *valid_index,
 						double *valid_s_new, double *valid_t_new, double *valid_action, gbp_sv_result *result) {
 	int rc;
-	if ((rc = sv_check(t, n, p, verdict_bits, valid_cap))) return rc;
+	if ((rc = sv_check(t, n, p, verdict_bits, valid_cap, state_idx, direction))) return rc;
 	if (!table || !result) return fail(GBP_E_INVALID, "table and result are required");
 	if ((valid_s_new || valid_t_new || valid_action) && !valid_index) return fail(GBP_E_INVALID, "valid rows need valid_index");
 	memset(result, 0, sizeof *result);

@@ -27,7 +27,8 @@ namespace gbp {
 struct SvParams {
 	const double *table;     // [rows][8] start states, AoS, 16-byte aligned (device)
 	const int *state_idx;    // [n] row numbers or null: candidate i starts from row row0 + i
-	const uint8_t *dir;      // [n] directions or null: every candidate uses dir0
+	const uint8_t *dir;      // [n] directions or null: every candidate uses dir0 (or carries its own: dir_packed)
+	int dir_packed;          // state_idx[i] = row | direction << 31: one 4-byte word per candidate on the wire (dir is null then)
 	long long row0;
 	long long rows;          // table size: a row number outside [0, rows) is counted in cnt[6] and read as row 0
 	int dir0;
@@ -38,6 +39,21 @@ struct SvParams {
 	double dir_thresh;
 	double target[8];        // `s` of newConfig (directional sampling only)
 };
+
+// row number and direction of candidate i as the call's wire format carries them.  STREAM = true: read-once loads (the
+// walks); a row outside the table is reported through `bad` and read as row 0.
+template <bool STREAM>
+__device__ __forceinline__ void sv_row_dir(const SvParams &P, int64_t i, long long &row, int &dir, bool &bad) {
+	dir = P.dir0;
+	if (P.state_idx) {
+		const int raw = STREAM ? __ldcs(P.state_idx + i) : P.state_idx[i];
+		if (P.dir_packed) { row = (long long) (raw & 0x7fffffff); dir = (int) ((unsigned) raw >> 31); }
+		else row = (long long) raw;
+	} else row = P.row0 + i;
+	if (P.dir) dir = (int) (STREAM ? __ldcs(P.dir + i) : P.dir[i]);
+	bad = (unsigned long long) row >= (unsigned long long) P.rows;
+	if (bad) row = 0;
+}
 
 constexpr int SV_CAP = 40;  // ring entries per warp: a batch of 32 is produced when at most SV_CAP - 32 are still buffered
 
@@ -104,12 +120,14 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_sv(Terrai
 				if (r < total) {
 					const int e = r % SV_CAP;
 					const int i = wbase + r;
-					long long row = P.state_idx ? (long long) __ldcs(P.state_idx + i) : P.row0 + i;
-					if ((unsigned long long) row >= (unsigned long long) P.rows) { row = 0; atomicAdd(cnt + 6, 1ull); }
+					long long row;
+					int dv;
+					bool bad;
+					sv_row_dir<true>(P, i, row, dv, bad);
+					if (bad) atomicAdd(cnt + 6, 1ull);
 					const double *src = P.table + 8 * row;
 #pragma unroll
 					for (int d = 0; d < 4; ++d) cp_async16_hint(&ringS[wib][e][2 * d], src + 2 * d, pol);
-					const int dv = P.dir ? (int) __ldcs(P.dir + i) : P.dir0;
 					ringD[wib][e] = (uint8_t) dv;
 					double vx = 0, vy = 0;
 					if (P.dir_sampling) { vx = __ldg(src + 3); vy = __ldg(src + 4); }
@@ -225,12 +243,14 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_sv_stream
 				if (lane < c) {
 					const int e = (filled + lane) % SV_CAP;
 					const int i = (int) base + lane;
-					long long row = P.state_idx ? (long long) __ldcs(P.state_idx + i) : P.row0 + i;
-					if ((unsigned long long) row >= (unsigned long long) P.rows) { row = 0; atomicAdd(cnt + 6, 1ull); }
+					long long row;
+					int dv;
+					bool bad;
+					sv_row_dir<true>(P, i, row, dv, bad);
+					if (bad) atomicAdd(cnt + 6, 1ull);
 					const double *src = P.table + 8 * row;
 #pragma unroll
 					for (int d = 0; d < 4; ++d) cp_async16_hint(&ringS[wib][e][2 * d], src + 2 * d, pol);
-					const int dv = P.dir ? (int) __ldcs(P.dir + i) : P.dir0;
 					ringD[wib][e] = (uint8_t) dv;
 					ringI[wib][e] = i;
 					double vx = 0, vy = 0;
@@ -293,10 +313,10 @@ __global__ void __launch_bounds__(RF_WARPS * 32, GBP_WALK_CTAS) k_walk_sv_stream
 
 // the candidate's inputs, rebuilt from its index (redo pass, general path, output pass)
 __device__ __forceinline__ void sv_candidate(const SvParams &P, const double *R, int64_t i, double s[8], double a[10], int &dir) {
-	long long row = P.state_idx ? (long long) P.state_idx[i] : P.row0 + i;
-	if ((unsigned long long) row >= (unsigned long long) P.rows) row = 0;  // counted by the pass that decides the candidate
+	long long row;
+	bool bad;  // counted by the pass that decides the candidate
+	sv_row_dir<false>(P, i, row, dir, bad);
 	load_state(P.table + 8 * row, s);
-	dir = P.dir ? (int) P.dir[i] : P.dir0;
 	sv_sample(P.seed, P.stream, P.idx0 + (uint64_t) i, R, P.dir_sampling, P.dir_thresh, P.target[3], P.target[4], dir, s[3], s[4], a);
 }
 // the fp64 evaluator walked to the verdict (k_validate_redo's loop)
@@ -343,8 +363,11 @@ __global__ void __launch_bounds__(128) k_sv_fp64(TerrainView T, SvParams P, int6
 		double s[8], a[10];
 		int dir;
 		if (!list) {  // the walk has counted the listed ones
-			const long long row = P.state_idx ? (long long) P.state_idx[i] : P.row0 + i;
-			if ((unsigned long long) row >= (unsigned long long) P.rows) atomicAdd(cnt + 6, 1ull);
+			long long row;
+			int d0;
+			bool bad;
+			sv_row_dir<false>(P, i, row, d0, bad);
+			if (bad) atomicAdd(cnt + 6, 1ull);
 		}
 		sv_candidate(P, sR, i, s, a, dir);
 		Counters c = {0, 0, 0, 0};

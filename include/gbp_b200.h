@@ -175,7 +175,8 @@ int gbp_validate_counters(const gbp_terrain *t, int64_t counters6[6]);
  *        result->n_valid is the total.  Any of the valid_* arrays and flags (n bytes, GBP_FLAG_* per candidate) may
  *        be NULL.
  * Verdicts, rows and work counters equal those of gbp_validate_pairs on the same (state, action, direction) triples.
- * Against its 145 B in + 74 B out per candidate this call moves 5 B in + 1 bit out (+ 156 B per valid candidate).
+ * Against its 145 B in + 74 B out per candidate this call moves 5 B (4 B with direction_in_row) in + 1 bit out (+ 156 B
+ * per valid candidate).
  * All scratch is allocated per call on the call's stream: concurrent calls on one terrain handle are safe. */
 typedef struct gbp_states gbp_states; /* device-resident table of start states, rows of 8 doubles */
 int gbp_states_create(int64_t rows, const double *states, gbp_states **out);
@@ -197,7 +198,9 @@ typedef struct {
 	                                      reference re-checks the start state as the first sub-state of EVERY candidate
 	                                      (planning_utils.cpp:718-730, :842-848); with the promise that check is counted
 	                                      (work counters stay the reference's) but not repeated.  0 = evaluate it. */
-	int reserved;
+	int direction_in_row;              /* 1 = state_idx[i] carries candidate i's direction in bit 31 (0 FORWARD, 1 REVERSE) above a 31-bit
+	                                      row number, and `direction` is NULL: ONE 4-byte word per candidate on the wire
+	                                      instead of 5 bytes in two arrays.  0 = rows and directions as separate arrays. */
 } gbp_sv_params;
 
 typedef struct {

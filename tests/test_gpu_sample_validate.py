@@ -48,10 +48,13 @@ def vertex_table(o, rows, seed):
 
 
 def check(gbp, t, o, table, n, seed=5, stream=9, idx0=0, state_idx=None, direction=None, direction0=0, row0=0, adaptive=False,
-          normal=(0.0, 0.0, 1.0), target=None, thresh=0.0, valid_cap=None, states_valid=False):
+          normal=(0.0, 0.0, 1.0), target=None, thresh=0.0, valid_cap=None, states_valid=False, packed=False):
     tab = gbp.States(table)
-    p = gbp.sv_params(seed, stream, idx0, normal, adaptive, direction0, target, thresh, row0, states_valid)
-    r = t.sample_validate(tab, n, p, state_idx, direction, valid_cap=valid_cap)
+    p = gbp.sv_params(seed, stream, idx0, normal, adaptive, direction0, target, thresh, row0, states_valid, direction_in_row=packed)
+    if packed:  # one 4-byte word per candidate: row | direction << 31
+        r = t.sample_validate(tab, n, p, gbp.pack_rows(state_idx, direction), None, valid_cap=valid_cap)
+    else:
+        r = t.sample_validate(tab, n, p, state_idx, direction, valid_cap=valid_cap)
     # the same candidates, spelled out
     rows = np.asarray(state_idx, dtype=np.int64) if state_idx is not None else row0 + np.arange(n)
     s = table[rows]
@@ -97,6 +100,30 @@ def test_vertex_rows_with_repeats(gbp, env):
     d = rng.integers(0, 2, n).astype(np.uint8)
     r = check(gbp, t, o, table, n, state_idx=idx, direction=d)
     assert 0 < r["n_valid"] < n
+
+
+def test_direction_in_row_word(gbp, env):
+    """gbp_sv_params.direction_in_row: rows and directions in ONE 4-byte word per candidate — same verdicts, rows and
+    counters as the two-array form (every map class; fixed and adaptive step; directional sampling reads the direction too)"""
+    name, t, o, T = env
+    table = vertex_table(o, 700, seed=13)
+    rng = np.random.default_rng(13)
+    n = 12000
+    idx = rng.integers(0, len(table), n).astype(np.int32)
+    d = rng.integers(0, 2, n).astype(np.uint8)
+    r = check(gbp, t, o, table, n, state_idx=idx, direction=d, packed=True)
+    assert 0 < r["n_valid"] < n
+    check(gbp, t, o, table, 3000, state_idx=idx[:3000], direction=d[:3000], packed=True, adaptive=True, states_valid=True)
+    target = vertex_table(o, 1, seed=14)[0]
+    check(gbp, t, o, table, 1000, state_idx=idx[:1000], direction=d[:1000], packed=True, target=target, thresh=0.15)
+    # the flag excludes a separate direction array, and needs the row words
+    tab = gbp.States(table)
+    p = gbp.sv_params(1, 2, 3, direction_in_row=True)
+    with pytest.raises(gbp.GbpError):
+        t.sample_validate(tab, 100, p, idx[:100], d[:100])
+    with pytest.raises(gbp.GbpError):
+        t.sample_validate(tab, 100, p, None, None)
+    tab.close()
 
 
 def test_implicit_rows_with_offset_and_constant_direction(gbp, env):
@@ -233,3 +260,9 @@ def test_streamed_host_call_matches_chunked_and_oracle(gbp, env, monkeypatch, pr
     acts = o.sample_actions(31, 32, 1000 + lo, m)
     vo, fo, sno, tno, cnt = o.validate_pairs(table[idx[lo:lo + m]], acts, d[lo:lo + m], nthreads=8)
     assert np.array_equal(a["verdict"][lo:lo + m], vo)
+    # and the one-word wire format (direction in bit 31 of the row word) through the same streamed launch
+    pk = gbp.sv_params(31, 32, 1000, states_valid=promise, direction_in_row=True)
+    c = t.sample_validate(tab, n, pk, state_idx=gbp.pack_rows(idx, d), valid_cap=n, want_flags=False)
+    assert np.array_equal(a["bits"], c["bits"]) and a["n_valid"] == c["n_valid"] and a["counters"] == c["counters"]
+    assert np.array_equal(a["index"], c["index"])
+    assert_bits_equal(a["s_new"], c["s_new"], what="s_new (packed)"); assert_bits_equal(a["action"], c["action"], what="action (packed)")
