@@ -1,11 +1,12 @@
 // The pipelined batch planner: runRRTConnect (rrt_connect.cpp:230-314) for a large batch of independent queries as a
-// sequence of ROUNDS, each advancing every running query by one extend attempt, with the three roles of an extend in three
-// kernels that all queries go through together:
+// sequence of ROUNDS, each advancing every running query by up to B extend attempts (B = 1 .. 8 speculated half-iterations,
+// see k_pipe_prep), with the three roles of an extend in three kernels that all queries go through together:
 //
-//   k_pipe_prep    warp per query: skips the query's invalid random states (rrt_connect.cpp:254; STATE cells are drawn and
-//                  validity-checked 32 at a time), checks the budget and the tree capacity, finds the nearest neighbour
-//                  (rrt.cpp:78), the surface normal at the target (rrt.cpp:25) and its GRF rotation, and appends one SEGMENT
-//                  {s_near, R, s_rand, direction, Philox cell} to the round's dense list
+//   k_pipe_prep    4 lanes per segment: skips the query's invalid random states (rrt_connect.cpp:254; STATE cells are drawn and
+//                  validity-checked 32 at a time, one batch ahead), checks the budget and the tree capacity, and for each of
+//                  the query's next B half-iterations finds the nearest neighbour (rrt.cpp:78), the surface normal at the
+//                  target (rrt.cpp:25) and its GRF rotation, and appends one SEGMENT {s_near, R, s_rand, direction, Philox
+//                  cell} to the round's dense list
 //   k_walk_seg     the candidates of all segments FLATTENED: candidate i = (segment i / K, action j = i % K).  This is
 //                  k_walk_sv (gbp_sv.cuh) with per-segment parameters: a warp produces 32 candidates convergently (state
 //                  row gathered with cp.async while the action is sampled), a lane walks one candidate's sub-states in the
@@ -13,6 +14,7 @@
 //                  start state of a candidate is a tree vertex — valid by construction — so its own check (the reference's
 //                  first sub-state) is not repeated (roots are checked once by k_pipe_init).  Out: one VALID bit and one
 //                  UNDECIDED bit per candidate.
+//   k_pipe_triage  thread per query: counts the leading TRAPPED segments (98 % of all), hands the first other one to select
 //   k_pipe_select  warp per segment: resolves undecided candidates with the fp64 evaluator, takes the first valid action
 //                  in stream order (or the closest valid one), rebuilds its exact end state (finish_output), applies
 //                  newConfig's acceptance (rrt.cpp:55-66), appends the vertex (rrt.cpp:87-92) and runs connect from the
@@ -25,17 +27,20 @@
 // that every warp streams through once per iteration (instruction fetch is 7 of the 15 stall cycles per issue), and the
 // 80-register cap spills 2.7 KB per thread.  Flattened, a lane samples ONE action for ONE candidate (28 warp instructions per
 // candidate instead of 150), the walk is the microbenchmark's 1.2 k-instruction loop (no fetch stalls, 128 registers, no
-// spills), and invalid random states cost nothing: ~1700 rounds instead of 4000 half-iterations.
+// spills), and invalid random states cost nothing: ~2500 rounds instead of 4000 half-iterations at B = 1, ~780 at B = 4.
 // Results are the megakernel's bit for bit (same Philox cells, same arithmetic, same order of tree updates per query):
 // tests/test_gpu_planner.py runs both forms against the oracle and the reference-loop golden.
 // Applies to plain RRT-Connect at the fixed step with K <= 32 on terrains with the mixed-precision evaluator; everything
 // else (RRT*, adaptive step, directional STATE sampling, anytime rounds, K > 32, other map kinds) stays on k_plan_batch.
 #pragma once
+#include <type_traits>
+
 #include "gbp_planner.cuh"
 #include "gbp_sv.cuh"
 
 namespace gbp {
 
+constexpr int PIPE_BATCH = 64;  // STATE cells drawn per request (k_pipe_batch): what a query can consume per round
 constexpr int PIPE_ROW = 26;  // doubles per segment row: s_near[8], R[9], s_rand[8], pad (rows stay 16-byte aligned)
 
 struct PipeState {  // per query
@@ -44,10 +49,10 @@ struct PipeState {  // per query
 	int *it, *half;            // the half-iteration the query is at
 	int *iters;                // started iterations when it stopped
 	long long *pair_checks, *nn_queries;
-	double *rs;                // [Q][32][8] the current batch of 32 STATE cells
-	unsigned *rs_valid;        // isValidState(STANCE) of the batch
-	long long *rs_base;        // first cell of the batch (-1: none yet)
-	long long *rs_want;        // first cell of the batch k_pipe_batch is asked to draw
+	double *rs;                // [Q][2][64][8] two batches of 64 STATE cells: batch b (cells 64 b .. 64 b + 63) lives in slot b & 1
+	unsigned long long *rs_valid;  // [Q][2] isValidState(STANCE) of a batch
+	long long *rs_base;        // [Q][2] first cell of the batch a slot holds (-1: none yet)
+	long long *rs_want;        // [Q] first cell of the batch k_pipe_batch is asked to draw
 	unsigned char *root_valid; // [Q][2] isValidState(root, STANCE) of the start-side / goal-side tree
 	int *busy_until;           // [Q] first round that may touch the query again (its connect runs on the second stream meanwhile)
 };
@@ -55,9 +60,12 @@ struct PipeState {  // per query
 // stream is already in the next round
 // Rounds a query sits out after triage handed it to select / connect: those run on their own streams while the following
 // rounds work on the other queries, and everything they use (heavy list, counter block, events) exists PIPE_DEPTH times.
-// With 2, prep(r) waits ~17 us per round for connect(r - 2) (select + connect of a round take about as long as a round);
-// with 3 that wait is 4 us but the queries that grew sit out one more round and the batch needs 13 % more rounds: 0.376 s
-// against 0.358 s on configs[4].
+// With 2, prep(r) waits 17-37 us per round for connect(r - 2) (a walk holds every SM until its candidates run out: the last
+// connect warps get one in the walk's tail); with 3 that wait is 4 us but the queries that grew sit out one more round and the
+// batch needs 13 % more rounds: 0.376 s against 0.358 s on configs[4].  Releasing each query on its own (release store at the
+// end of its select / connect, acquire load in prep, no wait for the whole of connect(r - 2)) was measured too: no gain at
+// 65,536 queries (0.283 against 0.277 s), slower at 16,384 (0.158 against 0.136 s) — without the wait the side kernels are
+// pushed behind one more walk and their queries come back a round later.
 constexpr int PIPE_DEPTH = 2;
 
 enum : int { CNT_SEGS = 0, CNT_BUSY = 1, CNT_HEAVY = 2, CNT_CONNECTS = 3, CNT_BATCHES = 4, CNT_WORK = 5, CNT_WORDS = 8 };
@@ -69,13 +77,14 @@ struct PipeHeavy {             // segments with a valid or an undecided candidat
 	unsigned *vmask, *umask;
 	int *connects;             // [Q] connect requests of the round: query * 2 + half
 };
-struct PipeSegs {  // the round's dense segment list
-	double *rows;              // [Q][PIPE_ROW]
+struct PipeSegs {  // the round's dense segment list: the segments of a query are consecutive, in cell order
+	double *rows;              // [Q * B][PIPE_ROW]
 	int *q, *near;             // query, id of s_near in the tree being extended
 	unsigned char *flags;      // bit 0: direction, bit 1: s_near is known valid
+	unsigned char *ord;        // position of the segment among its query's segments of this round | (their number - 1) << 4
 	unsigned long long *idx0;  // ACTION cell of candidate 0: cell * K
 	int *count;                // the round's counter block (CNT_*)
-	unsigned *vbits, *ubits;   // one bit per candidate; all zero between rounds (k_pipe_triage clears what the walk set)
+	unsigned *vbits, *ubits;   // one bit per candidate; zeroed at the start of every round
 };
 
 template <typename M>
@@ -93,11 +102,12 @@ __global__ void __launch_bounds__(128) k_pipe_init(TerrainView Tv, PipeState S, 
 	S.root_valid[2 * q] = is_valid_state_auto<M>(Tv, pose6(s), GBP_STANCE, c) ? 1 : 0;
 	S.root_valid[2 * q + 1] = is_valid_state_auto<M>(Tv, pose6(g), GBP_STANCE, c) ? 1 : 0;
 	S.status[q] = 0; S.it[q] = 0; S.half[q] = 0; S.iters[q] = max_iters; S.pair_checks[q] = 0; S.nn_queries[q] = 0;
-	S.rs_valid[q] = 0; S.rs_base[q] = -1; S.rs_want[q] = 0; S.busy_until[q] = 0;
+	S.rs_valid[2 * q] = S.rs_valid[2 * q + 1] = 0; S.rs_base[2 * q] = S.rs_base[2 * q + 1] = -1; S.rs_want[q] = 0; S.busy_until[q] = 0;
 }
 
-// STATE cells base .. base + 31 of the queries that ran out of random states: warp per listed query, lane L draws cell
-// base + L and checks it (their validity does not depend on the trees).  Runs on the second stream while the round's walk runs.
+// STATE cells base .. base + 63 of the queries that ask for random states: warp per listed query, lane L draws cells
+// base + L and base + 32 + L and checks them (their validity does not depend on the trees).  Runs on a side stream while the
+// round's walk runs.
 template <typename M>
 __global__ void __launch_bounds__(128) k_pipe_batch(TerrainView Tv, PipeState S, const int *__restrict__ list, const int *__restrict__ cnt, uint64_t seed,
 													 uint64_t query0) {
@@ -106,115 +116,159 @@ __global__ void __launch_bounds__(128) k_pipe_batch(TerrainView Tv, PipeState S,
 	for (int e = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5); e < n; e += warps) {
 		const int q = list[e];
 		const long long base = S.rs_want[q];
-		double rs[8];
-		sample_state<M>(Tv, seed, query0 + (uint64_t) q, (uint64_t) base + (uint64_t) lane, false, 0.0, false, nullptr, nullptr, rs);
-		Counters c = {0, 0, 0, 0};
-		const unsigned valid = __ballot_sync(FULL, is_valid_state_auto<M>(Tv, pose6(rs), GBP_STANCE, c));
-		double2 *o = reinterpret_cast<double2 *>(S.rs + ((size_t) q * 32 + lane) * 8);
+		const size_t slot = 2 * (size_t) q + (size_t) ((base >> 6) & 1);
+		unsigned long long valid = 0;
+		for (int p = 0; p < 2; ++p) {
+			double rs[8];
+			sample_state<M>(Tv, seed, query0 + (uint64_t) q, (uint64_t) base + (uint64_t) (32 * p + lane), false, 0.0, false, nullptr, nullptr, rs);
+			Counters c = {0, 0, 0, 0};
+			valid |= (unsigned long long) __ballot_sync(FULL, is_valid_state_auto<M>(Tv, pose6(rs), GBP_STANCE, c)) << (32 * p);
+			double2 *o = reinterpret_cast<double2 *>(S.rs + (slot * PIPE_BATCH + 32 * p + lane) * 8);
 #pragma unroll
-		for (int d = 0; d < 4; ++d) o[d] = make_double2(rs[2 * d], rs[2 * d + 1]);
-		if (lane == 0) { S.rs_valid[q] = valid; S.rs_base[q] = base; }
+			for (int d = 0; d < 4; ++d) o[d] = make_double2(rs[2 * d], rs[2 * d + 1]);
+		}
+		if (lane == 0) { S.rs_valid[slot] = valid; S.rs_base[slot] = base; }
 	}
 }
 
-// FOUR LANES per query: the control flow of a half-iteration up to newConfig's candidates — budget and capacity checks, the next
-// valid random state of the query (invalid ones are skipped, rrt_connect.cpp:254), the nearest neighbour (rrt.cpp:78, a
-// sequential scan of the query's tree: a few dozen vertices), the surface normal at the target (rrt.cpp:25) and its GRF
-// rotation — and the segment row.  A warp per query spent its time on dependent HBM round trips (65 k warps x 3-4 round
-// trips, 100 us per round); 32 queries per warp issue those loads side by side.
+// The control flow of a query's next half-iterations up to newConfig's candidates — budget and capacity checks, the next
+// valid random states of the query (invalid ones are skipped, rrt_connect.cpp:254), and per half the nearest neighbour
+// (rrt.cpp:78, a sequential scan of the query's tree: a few dozen vertices), the surface normal at the target (rrt.cpp:25), its
+// GRF rotation and the segment row.
+//
+// SPECULATION over half-iterations: an extend that comes back TRAPPED leaves both trees as they were (rrt.cpp:77-102), the
+// STATE cell of half h is 2 * it + half and its ACTION cells are h * K + j whatever happened before, and 98 % of the extends
+// on these terrains are TRAPPED — so the next B halves of a query are independent unless one of them grows a tree.  A query
+// emits up to B segments per round (its next B valid random states, each with the nearest neighbour in the tree that half
+// extends); k_pipe_triage takes them in order, counts the leading TRAPPED ones, hands the first segment with a valid or an
+// undecided candidate to k_pipe_select and drops the segments after it (they are emitted again, against the grown tree).
+// Same Philox cells, same arithmetic, same order of tree updates: results do not depend on B.  A round then advances a query
+// by up to B halves for one round's worth of launch gaps, waits and prep.
+//
+// 4 * B lanes per query (B = 1, 2, 4, 8, 16): every lane of a query runs the control flow, FOUR LANES per segment share the tree
+// scan.  (A warp per query spent its time on dependent HBM round trips; several queries per warp issue them side by side.)
+// The two batches of 64 STATE cells a query holds are drawn one ahead: a query only sits a round out for random states when
+// it jumps over a whole batch of invalid ones.
 template <typename M>
-__global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int *__restrict__ batch_list, int64_t Q,
-													gbp_plan_params P, int round) {
-	const int lane = threadIdx.x & 31, sub = lane & 3;  // 4 lanes per query: they share the control flow and split the tree scan
-	const int64_t q = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 2;
-	const bool lead = sub == 0;
-	bool emit = false;
-	int it = 0, half = 0, na = 0, nb = 0;
+__global__ void __launch_bounds__(128, 6) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int *__restrict__ batch_list, int64_t Q,
+													gbp_plan_params P, int round, int B, const int *solved_count) {
+	__shared__ int s_cnt[32], s_off[32];
+	const int lane = threadIdx.x & 31, sub = lane & 3;
+	const int lpq = 4 * B;                                   // lanes per query
+	const int qib = (int) threadIdx.x / lpq;                 // query within the block
+	const int j = ((int) threadIdx.x - qib * lpq) >> 2;      // segment within the query
+	const int64_t q = (blockIdx.x * (int64_t) blockDim.x + threadIdx.x) / lpq;
+	const bool lead = sub == 0, qlead = (int) threadIdx.x == qib * lpq;
+	int cnt = 0, na = 0, nb = 0, status = -1, it0 = 0, half0 = 0, busy_until = 0;
 	long long cell = 0;
-	if (q < Q) {
-		const int status = S.status[q];
-		it = S.it[q]; half = S.half[q]; na = S.na[q]; nb = S.nb[q];
-		const long long rs_base = S.rs_base[q];
-		const unsigned rs_valid = S.rs_valid[q];
-		const int busy_until = S.busy_until[q];
-		if (status == 0 && round < busy_until) { if (lead) atomicAdd(G.count + CNT_BUSY, 1); }  // its select / connect or its next batch of random states is in flight
-		else if (status == 0) {
-			if (it >= P.max_iters) { if (lead) { S.status[q] = 2; S.iters[q] = P.max_iters; } }  // budget used up
-			else if (na >= A.cap || nb >= A.cap) { if (lead) { S.status[q] = 2; S.iters[q] = it + 1; } }  // a tree is full at the start of a half
+	unsigned long long m = 0;
+	longlong2 rs_base = make_longlong2(-2, -2);
+	ulonglong2 rs_valid = make_ulonglong2(0ull, 0ull);
+	if (q < Q) {  // every lane of a query reads its state; its first lane writes what changes after the block's barrier below
+		status = S.status[q]; it0 = S.it[q]; half0 = S.half[q]; na = S.na[q]; nb = S.nb[q]; busy_until = S.busy_until[q];
+		rs_base = *reinterpret_cast<const longlong2 *>(S.rs_base + 2 * q);
+		rs_valid = *reinterpret_cast<const ulonglong2 *>(S.rs_valid + 2 * q);
+	}
+	int stop_iters = -1;      // >= 0: the query stops here with this iteration count
+	long long want = -1, jump = -1;  // batch of random states to draw / cell the query jumps to
+	bool busy = false, sit_out = false;
+	if (q < Q && status == 0) {
+		const int it = it0, half = half0;
+		if (round < busy_until) busy = true;  // its select / connect or its next batch of random states is in flight
+		else if (P.stop_after_solved > 0 && *(const volatile int *) solved_count >= P.stop_after_solved) stop_iters = it;  // anytime use: enough queries have solved
+		else if (it >= P.max_iters) stop_iters = P.max_iters;  // budget used up
+		else if (na >= A.cap || nb >= A.cap) stop_iters = it + 1;  // a tree is full at the start of a half
+		else {
+			cell = 2ll * it + half;
+			const long long base = cell & ~63ll, limit = 2ll * P.max_iters;  // cells below `limit` are within the budget
+			const bool odd = ((cell >> 6) & 1) != 0;
+			const long long base0 = odd ? rs_base.y : rs_base.x, base1 = odd ? rs_base.x : rs_base.y;  // the slot `cell` belongs to, the other one
+			const unsigned long long valid0 = odd ? rs_valid.y : rs_valid.x, valid1 = odd ? rs_valid.x : rs_valid.y;
+			if (base0 != base) { want = base; sit_out = true; }  // the batch holding `cell` is drawn by k_pipe_batch while this round's walk runs
 			else {
-				cell = 2ll * it + half;
-				const long long base = cell & ~31ll;
-				const unsigned mask = rs_base == base ? rs_valid >> (unsigned) (cell & 31ll) : 0u;
-				if (rs_base == base && mask == 0) {  // no valid state left in this batch: the query is at the first cell of the next one
-					cell = base + 32; it = (int) (cell >> 1); half = (int) (cell & 1);
-					if (lead) { S.it[q] = it; S.half[q] = half; }
-				}
-				if (mask) {
-					cell += __ffs(mask) - 1;  // invalid random states are skipped (rrt_connect.cpp:254)
-					it = (int) (cell >> 1); half = (int) (cell & 1);
-					if (it >= P.max_iters) { if (lead) { S.status[q] = 2; S.iters[q] = P.max_iters; } }
-					else emit = true;
-				} else if (it >= P.max_iters) { if (lead) { S.status[q] = 2; S.iters[q] = P.max_iters; } }
-				else if (lead) {  // the batch holding `cell` is drawn by k_pipe_batch while this round's walk runs; the query sits the round out
-					S.rs_want[q] = cell & ~31ll;
-					S.busy_until[q] = round + 1;
-					batch_list[atomicAdd(G.count + CNT_BATCHES, 1)] = (int) q;
-					atomicAdd(G.count + CNT_BUSY, 1);
+				const int off = (int) (cell & 63ll);
+				const bool have_next = base1 == base + PIPE_BATCH;
+				// the next 64 cells from `cell` on, as far as their random states are known
+				m = valid0 >> off;
+				if (have_next && off) m |= valid1 << (64 - off);
+				const long long end = have_next ? cell + 64 : base + PIPE_BATCH;  // first cell this round cannot look at
+				if (limit - cell < 64) m &= (1ull << (int) (limit - cell)) - 1ull;
+				if (m == 0) {  // no valid state among them (invalid random states are skipped, rrt_connect.cpp:254)
+					if (end >= limit) stop_iters = P.max_iters;
+					else {
+						jump = end; sit_out = true;
+						if (!have_next) want = end;  // (otherwise `end` lies in the batch already drawn)
+					}
+				} else {
+					cnt = min(B, __popcll(m));
+					if (!have_next && base + PIPE_BATCH < limit) want = base + PIPE_BATCH;  // drawn one batch ahead: ready for the next round
 				}
 			}
 		}
 	}
-	// dense segment numbers: one atomic per warp
-	const unsigned em = __ballot_sync(FULL, emit && lead);
-	int seg = 0;
-	if (lane == 0 && em) seg = atomicAdd(G.count + CNT_SEGS, __popc(em));
-	seg = __shfl_sync(FULL, seg, 0) + __popc(em & ((1u << lane) - 1u));  // lanes of a group count the same leaders below them
-	if (!emit) return;  // the 4 lanes of a query leave together
+	// dense segment numbers, a query's segments consecutive: one atomic per block
+	if (qlead) s_cnt[qib] = cnt;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const int nqb = (int) blockDim.x / lpq;
+		int total = 0;
+		for (int i = 0; i < nqb; ++i) { s_off[i] = total; total += s_cnt[i]; }
+		const int first = total ? atomicAdd(G.count + CNT_SEGS, total) : 0;
+		for (int i = 0; i < nqb; ++i) s_off[i] += first;
+	}
+	if (qlead) {
+		if (stop_iters >= 0) { S.status[q] = 2; S.iters[q] = stop_iters; }
+		if (jump >= 0) { S.it[q] = (int) (jump >> 1); S.half[q] = (int) (jump & 1); }
+		if (want >= 0) {
+			S.rs_want[q] = want;
+			batch_list[atomicAdd(G.count + CNT_BATCHES, 1)] = (int) q;
+		}
+		if (sit_out) S.busy_until[q] = round + 1;
+		if (busy || sit_out) atomicAdd(G.count + CNT_BUSY, 1);
+	}
+	__syncthreads();
+	if (j >= cnt) return;  // the 4 lanes of a segment leave together
+	const int seg = s_off[qib] + j;
+	for (int i = 0; i < j; ++i) m &= m - 1ull;
+	cell += __ffsll((long long) m) - 1;  // the j-th valid random state from `cell` on
+	const int it = (int) (cell >> 1), half = (int) (cell & 1);
 	const unsigned gmask = 0xfu << (lane & ~3);
 	double s_rand[8];
 	{
-		const double2 *r = reinterpret_cast<const double2 *>(S.rs + ((size_t) q * 32 + (size_t) (cell & 31ll)) * 8);
+		const double2 *r = reinterpret_cast<const double2 *>(S.rs + ((2 * (size_t) q + (size_t) ((cell >> 6) & 1)) * PIPE_BATCH + (size_t) (cell & 63ll)) * 8);
 #pragma unroll
 		for (int d = 0; d < 4; ++d) { const double2 v = r[d]; s_rand[2 * d] = v.x; s_rand[2 * d + 1] = v.y; }
 	}
 	PlanTree Tx = arena_tree(A, (int) q, half, (half == 0 ? S.na : S.nb) + q);
 	const int nx = half == 0 ? na : nb;
 	// getNearestNeighbor (planner_class.cpp:185-200): (distance, id) argmin — the lowest id among equal distances
-	double bd = INFINITY, s_near[8];
+	double bd = INFINITY;
 	int near = 0x7fffffff;
+	for (int vi = sub; vi < nx; vi += 8) {  // two vertices per trip: the scan is a chain of HBM round trips (profiles/r2b_pipe_prep_lines.txt), 16 loads in flight halve it
+		const int v2 = vi + 4;
+		const bool two = v2 < nx;
+		const int v2c = two ? v2 : vi;
+		double v[8], w[8], sum = 0, sum2 = 0;
 #pragma unroll
-	for (int d = 0; d < 8; ++d) s_near[d] = 0.0;
-	for (int j = sub; j < nx; j += 4) {
-		double v[8], sum = 0;
-#pragma unroll
-		for (int d = 0; d < 8; ++d) v[d] = Tx.t.v[(size_t) d * Tx.t.cap + j];
+		for (int d = 0; d < 8; ++d) { v[d] = Tx.t.v[(size_t) d * Tx.t.cap + vi]; w[d] = Tx.t.v[(size_t) d * Tx.t.cap + v2c]; }
 #pragma unroll
 		for (int d = 0; d < 8; ++d) sum = sum + 1.0 * (v[d] - s_rand[d]) * (v[d] - s_rand[d]);
-		const double dj = sqrt(sum);
-		if (dj < bd) {  // ids ascend within a lane: a strict < keeps the lowest
-			bd = dj; near = j;
 #pragma unroll
-			for (int d = 0; d < 8; ++d) s_near[d] = v[d];
-		}
+		for (int d = 0; d < 8; ++d) sum2 = sum2 + 1.0 * (w[d] - s_rand[d]) * (w[d] - s_rand[d]);
+		const double dj = sqrt(sum), dj2 = sqrt(sum2);
+		if (dj < bd) { bd = dj; near = vi; }  // ids ascend within a lane: a strict < keeps the lowest
+		if (two && dj2 < bd) { bd = dj2; near = v2; }
 	}
 #pragma unroll
 	for (int o = 1; o < 4; o <<= 1) {
 		const double od = __shfl_xor_sync(gmask, bd, o);
 		const int oj = __shfl_xor_sync(gmask, near, o);
-		double ov[8];
-#pragma unroll
-		for (int d = 0; d < 8; ++d) ov[d] = __shfl_xor_sync(gmask, s_near[d], o);
-		if (od < bd || (od == bd && oj < near)) {
-			bd = od; near = oj;
-#pragma unroll
-			for (int d = 0; d < 8; ++d) s_near[d] = ov[d];
-		}
+		if (od < bd || (od == bd && oj < near)) { bd = od; near = oj; }
 	}
-	if (near == 0x7fffffff) {  // no finite distance: the reference's default index 0 (planner_class.cpp:186)
-		near = 0;
-#pragma unroll
-		for (int d = 0; d < 8; ++d) s_near[d] = Tx.t.v[(size_t) d * Tx.t.cap];
-	}
+	if (near == 0x7fffffff) near = 0;  // no finite distance: the reference's default index 0 (planner_class.cpp:186)
+	double2 *row = reinterpret_cast<double2 *>(G.rows + (size_t) seg * PIPE_ROW);
+	// s_near: each of the 4 lanes fetches and stores a quarter of it (the vertex was just scanned: L1 / L2 hits)
+	row[sub] = make_double2(Tx.t.v[(size_t) (2 * sub) * Tx.t.cap + near], Tx.t.v[(size_t) (2 * sub + 1) * Tx.t.cap + near]);
 	if (!lead) return;
 	double R[9];
 	if (Tv.nz3 || Tv.nz3d) {
@@ -228,9 +282,6 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 #pragma unroll
 		for (int d = 0; d < 9; ++d) R[d] = (d == 0 || d == 4 || d == 8) ? 1.0 : 0.0;
 	}
-	double2 *row = reinterpret_cast<double2 *>(G.rows + (size_t) seg * PIPE_ROW);
-	row[0] = make_double2(s_near[0], s_near[1]); row[1] = make_double2(s_near[2], s_near[3]);
-	row[2] = make_double2(s_near[4], s_near[5]); row[3] = make_double2(s_near[6], s_near[7]);
 	row[4] = make_double2(R[0], R[1]); row[5] = make_double2(R[2], R[3]); row[6] = make_double2(R[4], R[5]); row[7] = make_double2(R[6], R[7]);
 	row[8] = make_double2(R[8], s_rand[0]); row[9] = make_double2(s_rand[1], s_rand[2]); row[10] = make_double2(s_rand[3], s_rand[4]);
 	row[11] = make_double2(s_rand[5], s_rand[6]); row[12] = make_double2(s_rand[7], 0.0);
@@ -239,8 +290,9 @@ __global__ void __launch_bounds__(128) k_pipe_prep(TerrainView Tv, PipeState S, 
 	// a tree vertex other than the root is the end state of a fully valid pair check: STANCE-valid by construction
 	const bool known_valid = near != 0 || S.root_valid[2 * q + half] != 0;
 	G.flags[seg] = (unsigned char) ((half == 0 ? GBP_FORWARD : GBP_REVERSE) | (known_valid ? 2 : 0));
+	G.ord[seg] = (unsigned char) (j | ((cnt - 1) << 4));
 	G.idx0[seg] = (unsigned long long) cell * (unsigned long long) P.k_candidates;
-	S.it[q] = it; S.half[q] = half;
+	(void) it;
 }
 
 // k_walk_sv with per-segment parameters; see the file header.  `count` = segments of this round (device).
@@ -345,33 +397,38 @@ __device__ __forceinline__ unsigned pipe_bits(const unsigned *__restrict__ words
 	return (unsigned) (two >> (first & 31)) & (count >= 32 ? 0xffffffffu : ((1u << count) - 1u));
 }
 
-// triage, thread per segment: a segment whose candidates are all invalid (98 % of them) is TRAPPED — the query moves on to
-// its next half here.  The others are copied to the heavy list for k_pipe_select, which runs on the second stream while the
-// next round works on the other queries (their queries sit that round out), and their candidate bits are cleared.
+// triage, thread per query that emitted segments this round (the thread of its first segment): its segments in cell order.
+// A segment whose candidates are all invalid (98 % of them) is TRAPPED — counted, and the query moves on to the next one.  The
+// first segment with a valid or an undecided candidate is copied to the heavy list for k_pipe_select, which runs on the second
+// stream while the next round works on the other queries (its query sits that round out); the query is left AT that half,
+// the speculated segments after it are dropped.
 static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSegs G, PipeHeavy H, int K, int round) {  // H: this round's slot
-	const int seg = blockIdx.x * blockDim.x + threadIdx.x;
-	if (seg >= G.count[CNT_SEGS]) return;
-	const int first = seg * K;
-	const unsigned vmask = pipe_bits(G.vbits, first, K), umask = pipe_bits(G.ubits, first, K);
-	const int q = G.q[seg];
-	if (vmask | umask) {
-		const int h = atomicAdd(G.count + CNT_HEAVY, 1);
-		const double2 *src = reinterpret_cast<const double2 *>(G.rows + (size_t) seg * PIPE_ROW);
-		double2 *dst = reinterpret_cast<double2 *>(H.rows + (size_t) h * PIPE_ROW);
+	const int seg0 = blockIdx.x * blockDim.x + threadIdx.x;
+	if (seg0 >= G.count[CNT_SEGS]) return;
+	const int ord = (int) G.ord[seg0];
+	if (ord & 15) return;
+	const int cnt = (ord >> 4) + 1, q = G.q[seg0];
+	int trapped = 0;
+	long long cell = 0;
+	for (; trapped < cnt; ++trapped) {
+		const int seg = seg0 + trapped, first = seg * K;
+		const unsigned vmask = pipe_bits(G.vbits, first, K), umask = pipe_bits(G.ubits, first, K);
+		cell = (long long) (G.idx0[seg] / (unsigned long long) K);
+		if (vmask | umask) {
+			const int h = atomicAdd(G.count + CNT_HEAVY, 1);
+			const double2 *src = reinterpret_cast<const double2 *>(G.rows + (size_t) seg * PIPE_ROW);
+			double2 *dst = reinterpret_cast<double2 *>(H.rows + (size_t) h * PIPE_ROW);
 #pragma unroll
-		for (int d = 0; d < PIPE_ROW / 2; ++d) dst[d] = src[d];
-		H.q[h] = q; H.near[h] = G.near[seg]; H.flags[h] = G.flags[seg]; H.idx0[h] = G.idx0[seg]; H.vmask[h] = vmask; H.umask[h] = umask;
-		S.busy_until[q] = round + PIPE_DEPTH;
-		const unsigned long long span = (K >= 32 ? 0xffffffffull : ((1ull << K) - 1ull)) << (first & 31);
-		const unsigned lo = (unsigned) span, hi = (unsigned) (span >> 32);
-		if (vmask) { atomicAnd(G.vbits + (first >> 5), ~lo); if (hi) atomicAnd(G.vbits + (first >> 5) + 1, ~hi); }
-		if (umask) { atomicAnd(G.ubits + (first >> 5), ~lo); if (hi) atomicAnd(G.ubits + (first >> 5) + 1, ~hi); }
-		return;
+			for (int d = 0; d < PIPE_ROW / 2; ++d) dst[d] = src[d];
+			H.q[h] = q; H.near[h] = G.near[seg]; H.flags[h] = G.flags[seg]; H.idx0[h] = G.idx0[seg]; H.vmask[h] = vmask; H.umask[h] = umask;
+			S.busy_until[q] = round + PIPE_DEPTH;
+			break;
+		}
 	}
-	S.pair_checks[q] += K;
-	S.nn_queries[q] += 1;
-	if (((int) G.flags[seg] & 1) == GBP_FORWARD) S.half[q] = 1;
-	else { S.it[q] += 1; S.half[q] = 0; }
+	if (trapped == cnt) cell += 1;  // all TRAPPED: on to the half after the last one; otherwise select / connect move the query on from the heavy half
+	S.pair_checks[q] += (long long) K * trapped;
+	S.nn_queries[q] += trapped;
+	S.it[q] = (int) (cell >> 1); S.half[q] = (int) (cell & 1);
 }
 
 template <typename M>
@@ -462,7 +519,8 @@ __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeStat
 
 // connect (rrt_connect.cpp:98-120) for the queries whose tree grew in round `round`: warps pull requests from the list
 template <typename M>
-__global__ void __launch_bounds__(128, 4) k_pipe_connect(TerrainView Tv, PipeState S, PlanArena A, PipeHeavy H, const int *__restrict__ cnt, gbp_plan_params P) {
+__global__ void __launch_bounds__(128, 4) k_pipe_connect(TerrainView Tv, PipeState S, PlanArena A, PipeHeavy H, const int *__restrict__ cnt, gbp_plan_params P,
+														  int *solved_count) {
 	const int lane = threadIdx.x & 31;
 	const int n = cnt[CNT_CONNECTS];
 	const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -481,7 +539,7 @@ __global__ void __launch_bounds__(128, 4) k_pipe_connect(TerrainView Tv, PipeSta
 			S.pair_checks[q] += pair_checks;
 			S.nn_queries[q] += 1;
 			const int it = S.it[q];
-			if (solved) { S.status[q] = 1; S.iters[q] = it + 1; }
+			if (solved) { S.status[q] = 1; S.iters[q] = it + 1; if (P.stop_after_solved > 0) atomicAdd(solved_count, 1); }
 			else if (half == 0) S.half[q] = 1;
 			else { S.it[q] = it + 1; S.half[q] = 0; }
 		}
@@ -509,10 +567,13 @@ __global__ void __launch_bounds__(128) k_pipe_finish(TerrainView Tv, PipeState S
 
 inline bool plan_pipe_applies(const TerrainView &Tv, const gbp_plan_params &P, int64_t nq) {
 	const char *mode = getenv("GBP_PLAN_MODE");  // "mega" / "pipe": force one form (A/B measurements, tests); results are identical
-	if (P.rrt_star || P.adaptive || P.state_direction_sampling || P.stop_after_solved > 0 || P.k_candidates > 32 || !Tv.mixed_ok || !Tv.uniform) return false;
+	if (P.rrt_star || P.adaptive || P.state_direction_sampling || P.k_candidates > 32 || !Tv.mixed_ok || !Tv.uniform) return false;
 	if (mode && !strcmp(mode, "pipe")) return true;
 	if (mode && (!strcmp(mode, "mega") || !strcmp(mode, "step"))) return false;
-	return nq >= 32768;  // a round costs ~0.1 ms whatever the batch size: below ~20 k queries the megakernel's independent warps win
+	// a round costs ~0.1 ms whatever the batch size: below ~6 k queries the megakernel's independent warps win (configs[4] queries,
+	// megakernel against this form with 8 speculated halves per round: 4,096 queries 0.063 / 0.077 s, 8,192: 0.114 / 0.095 s,
+	// 16,384: 0.218 / 0.134 s)
+	return nq >= 8192;
 }
 
 // What one pipeline needs on the host besides its main stream.  Pooled (gbp_capi_pipeline.cu): a call takes one per group of
@@ -548,66 +609,54 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	const size_t cap = (size_t) P.max_vertices, Q = (size_t) nq, per = Q * 2 * cap, K = (size_t) P.k_candidates;
 	const int64_t fin_slots = (int64_t) sms * 4 * 4;
-	const size_t bit_words = (Q * K + 31) / 32 + 2;
-	const size_t n_doubles = per * (8 + 10 + 1 + 1) + Q * 32 * 8 + (1 + PIPE_DEPTH) * Q * PIPE_ROW + (size_t) fin_slots * 2 * cap * 18;
-	const size_t n_ll = Q * (5 + PIPE_DEPTH) + 2;  // pair_checks, nn_queries, rs_base, rs_want, idx0 (round + the heavy buffers), finish counter
-	const size_t n_ints = per * 3 + Q * (10 + 5 * PIPE_DEPTH + PIPE_DEPTH) + PIPE_DEPTH * CNT_WORDS + 2 * bit_words;
-	const size_t need = n_doubles * 8 + n_ll * 8 + n_ints * 4 + Q * (3 + PIPE_DEPTH) + 64;
-	void *mem = nullptr;
-	cudaError_t e;
-	if ((e = cudaMallocAsync(&mem, need, st)) != cudaSuccess) { err = std::string("pipelined planner arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
+	// segments a query may emit per round (see k_pipe_prep): GBP_PIPE_SPEC = 1, 2, 4 or 8
+	// measured on configs[4] (4-8 m, 2000 iterations), B = 1 / 2 / 4 / 8: 65,536 queries 0.365 / 0.302 / 0.284 / 0.303 s,
+	// 16,384 queries 0.205 / 0.155 / 0.136 / 0.134 s, 8,192: - / - / 0.101 / 0.095 s, 4,096: - / - / 0.085 / 0.077 s
+	int B = nq >= 32768 ? 4 : 8;
+	if (const char *b = getenv("GBP_PIPE_SPEC")) B = atoi(b);
+	B = B >= 16 ? 16 : B >= 8 ? 8 : B >= 4 ? 4 : B >= 2 ? 2 : 1;
+	const size_t QB = Q * (size_t) B;
+	const size_t bit_words = ((QB * K + 31) / 32 + 2 + 3) & ~(size_t) 3;  // a multiple of 16 bytes: vbits, ubits (and the counter blocks before them) stay adjacent in the arena
 	PlanArena A = {}, Sc = {};
 	PipeState S;
 	PipeSegs G;
 	PipeHeavy H[PIPE_DEPTH];
 	A.cap = Sc.cap = P.max_vertices;
-	double *dp = (double *) mem;
-	A.v = dp; dp += per * 8;
-	A.act = dp; dp += per * 10;
-	A.g = dp; dp += per;
-	A.y = dp; dp += per;
-	S.rs = dp; dp += Q * 32 * 8;
-	G.rows = dp; dp += Q * PIPE_ROW;
-	for (int k = 0; k < PIPE_DEPTH; ++k) { H[k].rows = dp; dp += Q * PIPE_ROW; }
-	Sc.pstate = dp; dp += (size_t) fin_slots * 2 * cap * 8;
-	Sc.paction = dp; dp += (size_t) fin_slots * 2 * cap * 10;
-	long long *lp = (long long *) dp;
-	S.pair_checks = lp; lp += Q;
-	S.nn_queries = lp; lp += Q;
-	S.rs_base = lp; lp += Q;
-	S.rs_want = lp; lp += Q;
-	G.idx0 = (unsigned long long *) lp; lp += Q;
-	for (int k = 0; k < PIPE_DEPTH; ++k) { H[k].idx0 = (unsigned long long *) lp; lp += Q; }
-	unsigned long long *next_query = (unsigned long long *) lp; lp += 2;
-	int *ip = (int *) lp;
-	A.parent = ip; ip += per;
-	A.child = ip; ip += per;
-	A.sibling = ip; ip += per;
-	S.na = ip; ip += Q;
-	S.nb = ip; ip += Q;
-	S.status = ip; ip += Q;
-	S.it = ip; ip += Q;
-	S.half = ip; ip += Q;
-	S.iters = ip; ip += Q;
-	S.rs_valid = (unsigned *) ip; ip += Q;
-	S.busy_until = ip; ip += Q;
-	G.q = ip; ip += Q;
-	G.near = ip; ip += Q;
-	for (int k = 0; k < PIPE_DEPTH; ++k) {
-		H[k].q = ip; ip += Q;
-		H[k].near = ip; ip += Q;
-		H[k].vmask = (unsigned *) ip; ip += Q;
-		H[k].umask = (unsigned *) ip; ip += Q;
-		H[k].connects = ip; ip += Q;
-	}
-	int *batch_list = ip; ip += PIPE_DEPTH * Q;  // queries that need their next batch of random states, one list per slot
-	int *cnt = ip; ip += PIPE_DEPTH * CNT_WORDS;  // the counter blocks, then the two bit arrays (zeroed once: triage clears what a round sets)
-	G.vbits = (unsigned *) ip; ip += bit_words;
-	G.ubits = (unsigned *) ip; ip += bit_words;
-	unsigned char *bp = (unsigned char *) ip;
-	S.root_valid = bp; bp += 2 * Q;
-	G.flags = bp; bp += Q;
-	for (int k = 0; k < PIPE_DEPTH; ++k) { H[k].flags = bp; bp += Q; }
+	unsigned long long *next_query = nullptr;
+	int *batch_list = nullptr, *cnt = nullptr, *solved_count = nullptr;
+	// one arena per call: laid out twice by the same code, first to size it, then over the allocation
+	auto layout = [&](char *base) -> size_t {
+		size_t off = 0;
+		auto take = [&](auto *&ptr, size_t n) {
+			typedef typename std::remove_reference<decltype(*ptr)>::type T;
+			off = (off + 15) & ~(size_t) 15;
+			ptr = reinterpret_cast<T *>(base + off);
+			off += n * sizeof(T);
+		};
+		take(A.v, per * 8); take(A.act, per * 10); take(A.g, per); take(A.y, per);
+		take(A.parent, per); take(A.child, per); take(A.sibling, per);
+		take(Sc.pstate, (size_t) fin_slots * 2 * cap * 8); take(Sc.paction, (size_t) fin_slots * 2 * cap * 10);
+		take(S.rs, Q * 2 * PIPE_BATCH * 8); take(S.rs_valid, Q * 2); take(S.rs_base, Q * 2); take(S.rs_want, Q);
+		take(S.pair_checks, Q); take(S.nn_queries, Q);
+		take(S.na, Q); take(S.nb, Q); take(S.status, Q); take(S.it, Q); take(S.half, Q); take(S.iters, Q); take(S.busy_until, Q);
+		take(S.root_valid, 2 * Q);
+		take(G.rows, QB * PIPE_ROW); take(G.idx0, QB); take(G.q, QB); take(G.near, QB); take(G.flags, QB); take(G.ord, QB);
+		for (int k = 0; k < PIPE_DEPTH; ++k) {
+			take(H[k].rows, Q * PIPE_ROW); take(H[k].idx0, Q); take(H[k].q, Q); take(H[k].near, Q); take(H[k].vmask, Q); take(H[k].umask, Q);
+			take(H[k].connects, Q); take(H[k].flags, Q);
+		}
+		take(next_query, 2);
+		take(solved_count, 4);
+		take(batch_list, PIPE_DEPTH * Q);  // queries that need a batch of random states, one list per slot
+		take(cnt, PIPE_DEPTH * CNT_WORDS);  // the counter blocks, then the two bit arrays (one memset)
+		take(G.vbits, bit_words); take(G.ubits, bit_words);
+		return off + 64;
+	};
+	const size_t need = layout(nullptr);
+	void *mem = nullptr;
+	cudaError_t e;
+	if ((e = cudaMallocAsync(&mem, need, st)) != cudaSuccess) { err = std::string("pipelined planner arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
+	layout((char *) mem);
 	// host-side resources of this pipeline (a pinned word pair for the running count, the two side streams and their events)
 	int *const h_count = R.h_count;
 	const cudaStream_t sb = R.sb, sc = R.sc, sd = R.sd;
@@ -617,6 +666,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	const unsigned walk_grid = (unsigned) sms * walk_ctas;
 	k_pipe_init<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, nq, starts, goals, P.max_iters);
 	cudaMemsetAsync(cnt, 0, (PIPE_DEPTH * CNT_WORDS + 2 * bit_words) * sizeof(int), st);
+	cudaMemsetAsync(solved_count, 0, 4 * sizeof(int), st);
 	// A round runs one extend attempt of every running query; a query needs at most 2 * max_iters of them (every random state
 	// valid) plus the rounds it sits out.  The number of running queries is read back every 32 rounds to stop launching once
 	// all are done.
@@ -627,38 +677,42 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	//              Select and connect overlap the next rounds, which their queries sit out, and are over before
 	//              prep(r + PIPE_DEPTH).
 	const int max_rounds = 4 * P.max_iters + 4;
+	const int check_mask = P.stop_after_solved > 0 ? 3 : B > 1 ? 7 : 31;  // rounds between two looks at the running count (a speculating round is several times longer)
 	int round = 0;
-	// GBP_PIPE_TRACE=1: device timestamps of 32 consecutive rounds (after round 640) on the first stream, printed to stderr
+	// GBP_PIPE_TRACE=1: device timestamps of 32 consecutive rounds (from round GBP_PIPE_TRACE on, default 640 / 96 when speculating) on the first stream, printed to stderr
 	const bool trace = getenv("GBP_PIPE_TRACE") != nullptr;
+	const int tr0 = trace && atoi(getenv("GBP_PIPE_TRACE")) > 1 ? atoi(getenv("GBP_PIPE_TRACE")) : (B > 1 ? 96 : 640);
 	cudaEvent_t tr[32][4];
 	if (trace) for (auto &r4 : tr) for (auto &ev : r4) cudaEventCreate(&ev);
 	for (; round < max_rounds; ++round) {
 		const int par = round % PIPE_DEPTH, prev = (round + PIPE_DEPTH - 1) % PIPE_DEPTH;
-		const bool tr_on = trace && round >= 640 && round < 672;
-		if (tr_on) cudaEventRecord(tr[round - 640][0], st);
+		const bool tr_on = trace && round >= tr0 && round < tr0 + 32;
+		if (tr_on) cudaEventRecord(tr[round - tr0][0], st);
 		G.count = cnt + par * CNT_WORDS;
 		if (round >= PIPE_DEPTH) cudaStreamWaitEvent(st, ev_con[par], 0);  // select + connect of round - PIPE_DEPTH: its queries, heavy buffers and counters are free again
 		if (round >= 1) cudaStreamWaitEvent(st, ev_bat[prev], 0);  // the batches drawn for the previous round's requests
 		if (round >= PIPE_DEPTH) cudaMemsetAsync(G.count, 0, CNT_WORDS * sizeof(int), st);
-		if (tr_on) cudaEventRecord(tr[round - 640][1], st);
-		k_pipe_prep<M><<<(unsigned) ((4 * Q + 127) / 128), 128, 0, st>>>(Tv, S, A, G, batch_list + (size_t) par * Q, nq, P, round);
+		if (round >= 1) cudaMemsetAsync(G.vbits, 0, 2 * bit_words * sizeof(int), st);  // the candidate bits of the previous round (vbits and ubits are adjacent)
+		if (tr_on) cudaEventRecord(tr[round - tr0][1], st);
+		k_pipe_prep<M><<<(unsigned) ((4 * QB + 127) / 128), 128, 0, st>>>(Tv, S, A, G, batch_list + (size_t) par * Q, nq, P, round, B, solved_count);
 		cudaEventRecord(ev_prep[par], st);
-		if (tr_on) cudaEventRecord(tr[round - 640][2], st);
-		if (Tv.ztex) k_walk_seg<true><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
-		else k_walk_seg<false><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
-		k_pipe_triage<<<(unsigned) ((Q + 255) / 256), 256, 0, st>>>(S, G, H[par], P.k_candidates, round);
-		cudaEventRecord(ev_tri[par], st);
-		if (tr_on) cudaEventRecord(tr[round - 640][3], st);
+		if (tr_on) cudaEventRecord(tr[round - tr0][2], st);
+		// (queued before or after the walk makes no difference: its blocks get their SMs as walk CTAs retire)
 		cudaStreamWaitEvent(sd, ev_prep[par], 0);
 		k_pipe_batch<M><<<(unsigned) sms * 4, 128, 0, sd>>>(Tv, S, batch_list + (size_t) par * Q, G.count, seed, query0);
 		cudaEventRecord(ev_bat[par], sd);
+		if (Tv.ztex) k_walk_seg<true><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
+		else k_walk_seg<false><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
+		k_pipe_triage<<<(unsigned) ((QB + 255) / 256), 256, 0, st>>>(S, G, H[par], P.k_candidates, round);
+		cudaEventRecord(ev_tri[par], st);
+		if (tr_on) cudaEventRecord(tr[round - tr0][3], st);
 		cudaStreamWaitEvent(sb, ev_tri[par], 0);
 		k_pipe_select<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, A, H[par], G.count, seed, query0, P);
 		cudaEventRecord(ev_sel[par], sb);
 		cudaStreamWaitEvent(sc, ev_sel[par], 0);
-		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sc>>>(Tv, S, A, H[par], G.count, P);
+		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sc>>>(Tv, S, A, H[par], G.count, P, solved_count);
 		cudaEventRecord(ev_con[par], sc);
-		if ((round & 31) == 31) {
+		if ((round & check_mask) == check_mask) {
 			cudaMemcpyAsync(h_count, G.count, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
 			if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
 			if (h_count[0] + h_count[1] == 0) { ++round; break; }
@@ -666,7 +720,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	}
 	if (trace) {
 		cudaStreamSynchronize(st);
-		if (round >= 672) {
+		if (round >= tr0 + 32) {
 			float wait = 0, prep = 0, rest = 0, gap = 0, t;
 			for (int r = 0; r < 32; ++r) {
 				cudaEventElapsedTime(&t, tr[r][0], tr[r][1]); wait += t;

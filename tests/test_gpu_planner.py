@@ -132,9 +132,12 @@ def test_plan_batch_capacity_and_budget(gbp):
     assert (st["nv_a"] <= 4).all() and (st["nv_b"] <= 4).all()
 
 
-def test_stop_after_solved(gbp):
+@pytest.mark.parametrize("mode", ["mega", "pipe"])
+def test_stop_after_solved(gbp, monkeypatch, mode):
     """anytime use (many attempts at one query): the launch ends once `stop_after_solved` attempts have solved; attempts
-    that did solve are unaffected (their own search is deterministic), the others report the work done so far."""
+    that did solve are unaffected (their own search is deterministic), the others report the work done so far.  Both forms
+    of the batch planner (the pipelined one counts solved queries in k_pipe_connect and stops the others in k_pipe_prep)."""
+    monkeypatch.setenv("GBP_PLAN_MODE", mode)
     T = load_terrain("slope"); o = po.Oracle(T)
     t = gbp.Terrain(T.x, T.y, T.z, T.dx, T.dy, T.dz)
     s, g = queries(o, T, 24, 5)
@@ -143,6 +146,7 @@ def test_stop_after_solved(gbp):
     n = 4096
     S, G = np.repeat(s[i][None], n, 0), np.repeat(g[i][None], n, 0)
     full = t.plan_batch(S, G, 1, 1 << 20, gbp.PlanParams(6, 0, 400, 256, 0, 0, 0, 0))
+    assert t.plan_batch_form(gbp.PlanParams(6, 0, 400, 256, 0, 0, 0, 4), n) == {"mega": "megakernel", "pipe": "pipelined"}[mode]
     early = t.plan_batch(S, G, 1, 1 << 20, gbp.PlanParams(6, 0, 400, 256, 0, 0, 0, 4))
     assert full["solved"][0] == 1 and full["solved"].sum() >= 4
     assert 4 <= early["solved"].sum() <= full["solved"].sum()
@@ -168,15 +172,18 @@ def test_pipelined_form_is_identical(gbp, monkeypatch):
         a, pa_s, pa_a, ta = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
         monkeypatch.setenv("GBP_PLAN_MODE", "pipe")
         assert t.plan_batch_form(P, len(S)) == "pipelined"
-        b, pb_s, pb_a, tb = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
-        for k in a.dtype.names:
-            assert np.array_equal(a[k], b[k]), k
-        for i in range(len(S)):
-            n = int(a["path_states"][i])
-            assert np.array_equal(pa_s[i, :n], pb_s[i, :n]) and np.array_equal(pa_a[i, :max(n - 1, 0)], pb_a[i, :max(n - 1, 0)])
-        for (xa, xb), (ya, yb) in zip(ta, tb):
-            for k in xa:
-                assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), k
+        for spec in ("8", "1", "2", "4", "16"):  # half-iterations a query speculates per round (k_pipe_prep): the results do not depend on it
+            monkeypatch.setenv("GBP_PIPE_SPEC", spec)
+            b, pb_s, pb_a, tb = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
+            for k in a.dtype.names:
+                assert np.array_equal(a[k], b[k]), (k, spec)
+            for i in range(len(S)):
+                n = int(a["path_states"][i])
+                assert np.array_equal(pa_s[i, :n], pb_s[i, :n]) and np.array_equal(pa_a[i, :max(n - 1, 0)], pb_a[i, :max(n - 1, 0)])
+            for (xa, xb), (ya, yb) in zip(ta, tb):
+                for k in xa:
+                    assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), (k, spec)
+        monkeypatch.delenv("GBP_PIPE_SPEC")
     # the batch split into 3 groups of queries, each an independent pipeline on its own host thread and streams
     monkeypatch.setenv("GBP_PIPE_GROUPS", "3")
     P = gbp.PlanParams(6, 0, 300, 128, 0, 0, 1)
