@@ -203,10 +203,13 @@ def run_slope_config0(gbp, rounds=8, want_cpu=True):
     height 0.30 m (the fork's 0.375 m start pose is invalid on this map), default parameters
     (config/params.yaml: K = NUM_GEN_STATES = 6, first valid decides, every fork option off)."""
     t, start, goal = shipped_query(gbp, "slope", 0.30)
-    nq = 3552
+    nq = 2048  # the drop-in's defaults (rrt_connect.h): 2048 attempts x 32000 iterations per launch, pipelined form with 16 speculated halves per round
     S, G = np.repeat(start[None], nq, 0), np.repeat(goal[None], nq, 0)
     t.plan_batch(S[:64], G[:64], 1, 0, gbp.PlanParams(6, 0, 10, 2048, 0, 0, 0, 0))  # warm-up
-    gpu = first_solution_rounds(t, start, goal, gbp.PlanParams(6, 0, 8000, 2048, 0, 0, 0, 1), nq, rounds)
+    P = gbp.PlanParams(6, 0, 32000, 2048, 0, 0, 0, 1)
+    t.plan_batch(S, G, 1, 1 << 40, gbp.PlanParams(6, 0, 40, 2048, 0, 0, 0, 1))  # warm-up of the form the timed launches take (its arena comes from the stream's pool)
+    gpu = first_solution_rounds(t, start, goal, P, nq, rounds)
+    gpu["planner_form"] = t.plan_batch_form(P, nq)
     out = {"workload": "data/slope, (0,0)->(8,0), body 0.30 m, K=6 first-valid, default params.yaml (host-pointer C ABI, wall clock)", "gpu": gpu,
            "solved_flag": gpu["calls_solved"] > 0}
     if want_cpu:

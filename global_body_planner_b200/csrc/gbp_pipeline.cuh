@@ -68,7 +68,7 @@ struct PipeState {  // per query
 // pushed behind one more walk and their queries come back a round later.
 constexpr int PIPE_DEPTH = 2;
 
-enum : int { CNT_SEGS = 0, CNT_BUSY = 1, CNT_HEAVY = 2, CNT_CONNECTS = 3, CNT_BATCHES = 4, CNT_WORK = 5, CNT_WORDS = 8 };
+enum : int { CNT_SEGS = 0, CNT_BUSY = 1, CNT_HEAVY = 2, CNT_CONNECTS = 3, CNT_BATCHES = 4, CNT_WORK = 5, CNT_RUNNING = 6, CNT_WORDS = 8 };
 struct PipeHeavy {             // segments with a valid or an undecided candidate, copied out of the round's segment arrays
 	double *rows;              // [Q][PIPE_ROW]
 	int *q, *near;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) k_pipe_batch(TerrainView Tv, PipeState S,
 template <typename M>
 __global__ void __launch_bounds__(128, 6) k_pipe_prep(TerrainView Tv, PipeState S, PlanArena A, PipeSegs G, int *__restrict__ batch_list, int64_t Q,
 													gbp_plan_params P, int round, int B, const int *solved_count) {
-	__shared__ int s_cnt[32], s_off[32];
+	__shared__ int s_cnt[32], s_off[32], s_run[32];
 	const int lane = threadIdx.x & 31, sub = lane & 3;
 	const int lpq = 4 * B;                                   // lanes per query
 	const int qib = (int) threadIdx.x / lpq;                 // query within the block
@@ -207,14 +207,15 @@ __global__ void __launch_bounds__(128, 6) k_pipe_prep(TerrainView Tv, PipeState 
 		}
 	}
 	// dense segment numbers, a query's segments consecutive: one atomic per block
-	if (qlead) s_cnt[qib] = cnt;
+	if (qlead) { s_cnt[qib] = cnt; s_run[qib] = (q < Q && status == 0 && stop_iters < 0) ? 1 : 0; }
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		const int nqb = (int) blockDim.x / lpq;
-		int total = 0;
-		for (int i = 0; i < nqb; ++i) { s_off[i] = total; total += s_cnt[i]; }
+		int total = 0, running = 0;
+		for (int i = 0; i < nqb; ++i) { s_off[i] = total; total += s_cnt[i]; running += s_run[i]; }
 		const int first = total ? atomicAdd(G.count + CNT_SEGS, total) : 0;
 		for (int i = 0; i < nqb; ++i) s_off[i] += first;
+		if (running) atomicAdd(G.count + CNT_RUNNING, running);  // queries still searching (emitting, sitting a round out, or with select / connect in flight)
 	}
 	if (qlead) {
 		if (stop_iters >= 0) { S.status[q] = 2; S.iters[q] = stop_iters; }
@@ -402,7 +403,7 @@ __device__ __forceinline__ unsigned pipe_bits(const unsigned *__restrict__ words
 // first segment with a valid or an undecided candidate is copied to the heavy list for k_pipe_select, which runs on the second
 // stream while the next round works on the other queries (its query sits that round out); the query is left AT that half,
 // the speculated segments after it are dropped.
-static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSegs G, PipeHeavy H, int K, int round) {  // H: this round's slot
+static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSegs G, PipeHeavy H, int K, int round, int *diag) {  // H: this round's slot; diag: GBP_PIPE_TRACE counters or null
 	const int seg0 = blockIdx.x * blockDim.x + threadIdx.x;
 	if (seg0 >= G.count[CNT_SEGS]) return;
 	const int ord = (int) G.ord[seg0];
@@ -422,10 +423,12 @@ static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSeg
 			for (int d = 0; d < PIPE_ROW / 2; ++d) dst[d] = src[d];
 			H.q[h] = q; H.near[h] = G.near[seg]; H.flags[h] = G.flags[seg]; H.idx0[h] = G.idx0[seg]; H.vmask[h] = vmask; H.umask[h] = umask;
 			S.busy_until[q] = round + PIPE_DEPTH;
+			if (diag) { atomicAdd(diag + 2, 1); if (vmask) atomicAdd(diag + 3, 1); atomicAdd(diag + 1, cnt - trapped - 1); }
 			break;
 		}
 	}
 	if (trapped == cnt) cell += 1;  // all TRAPPED: on to the half after the last one; otherwise select / connect move the query on from the heavy half
+	if (diag) atomicAdd(diag, trapped);
 	S.pair_checks[q] += (long long) K * trapped;
 	S.nn_queries[q] += trapped;
 	S.it[q] = (int) (cell >> 1); S.half[q] = (int) (cell & 1);
@@ -433,7 +436,7 @@ static __global__ void __launch_bounds__(256) k_pipe_triage(PipeState S, PipeSeg
 
 template <typename M>
 __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeState S, PlanArena A, PipeHeavy H, int *__restrict__ cnt, uint64_t seed,
-													 uint64_t query0, gbp_plan_params P) {
+													 uint64_t query0, gbp_plan_params P, int *diag) {
 	const int lane = threadIdx.x & 31;
 	const int nheavy = cnt[CNT_HEAVY], warps = (gridDim.x * blockDim.x) >> 5;
 	for (int h = (int) ((blockIdx.x * (int64_t) blockDim.x + threadIdx.x) >> 5); h < nheavy; h += warps) {
@@ -500,6 +503,7 @@ __global__ void __launch_bounds__(128, 4) k_pipe_select(TerrainView Tv, PipeStat
 			for (int d = 0; d < 10; ++d) a[d] = __shfl_sync(FULL, my_a[d], bj);
 		}
 	}
+	if (diag && found && lane == 0) atomicAdd(diag, 1);
 	if (found && lane == 0) {
 		PlanTree Tx = arena_tree(A, q, half, (half == 0 ? S.na : S.nb) + q);
 		plan_push(Tx, near, sn, a);  // rrt.cpp:87-92
@@ -547,6 +551,70 @@ __global__ void __launch_bounds__(128, 4) k_pipe_connect(TerrainView Tv, PipeSta
 	}
 }
 
+// The tail of a batch: the queries still running when most are done are the ones whose trees keep growing, and in the
+// pipeline every vertex costs them a round of their own plus the rounds they sit out (~0.3 ms), while a round costs ~0.1 ms
+// however few queries are left — 1,100 of the 1,900 rounds of configs[4] ran for a few thousand such queries.  Once no more
+// than `resume_at` queries are running, the side streams are drained and each of them continues from its (iteration, half,
+// trees, counters) on a warp of its own with the megakernel's loop (k_plan_batch, gbp_planner.cuh: same cells, same
+// arithmetic, same order of tree updates), where an extend that grows the tree costs what a TRAPPED one does.
+template <typename M>
+__global__ void __launch_bounds__(128, GBP_PLAN_MINBLOCKS) k_pipe_resume(TerrainView Tv, PipeState S, PlanArena A, int64_t Q, uint64_t seed, uint64_t query0,
+																		  gbp_plan_params P, unsigned long long *__restrict__ next_query, int *solved_count) {
+	const int lane = threadIdx.x & 31;
+	const GroupMap gm = make_group_map(P.k_candidates, lane);
+	while (true) {
+		unsigned long long grabbed = 0;
+		if (lane == 0) grabbed = atomicAdd(next_query, 1ull);
+		const int64_t q = (int64_t) __shfl_sync(FULL, grabbed, 0);
+		if (q >= Q) break;
+		if (S.status[q] != 0) continue;
+		PlanTree Ta = arena_tree(A, (int) q, 0, S.na + q), Tb = arena_tree(A, (int) q, 1, S.nb + q);
+		int na = S.na[q], nb = S.nb[q], it = S.it[q], half0 = S.half[q];
+		bool solved = false, full = false;
+		double rs[8];             // this lane's random state of the current batch of 32 STATE cells
+		unsigned rs_valid = 0;
+		long long drawn = -1;     // first cell of that batch
+		long long pair_checks = 0, nn_queries = 0;
+		const uint64_t query = query0 + (uint64_t) q;
+		for (; it < P.max_iters && !solved && !full; ++it) {
+			if (P.stop_after_solved > 0 && __shfl_sync(FULL, *(volatile int *) solved_count, 0) >= P.stop_after_solved) break;
+			for (int half = half0; half < 2 && !solved; ++half) {
+				PlanTree &Tx = half == 0 ? Ta : Tb, &Ty = half == 0 ? Tb : Ta;
+				int &nx = half == 0 ? na : nb, &ny = half == 0 ? nb : na;
+				if (nx >= A.cap || ny >= A.cap) { full = true; break; }
+				const uint64_t cell = 2 * (uint64_t) it + (uint64_t) half;
+				const long long base = (long long) (cell & ~31ull);
+				if (base != drawn) {
+					sample_state<M>(Tv, seed, query, (uint64_t) base + (uint64_t) lane, false, 0.0, false, nullptr, nullptr, rs);
+					Counters c = {0, 0, 0, 0};
+					rs_valid = __ballot_sync(FULL, is_valid_state_auto<M>(Tv, pose6(rs), GBP_STANCE, c));
+					drawn = base;
+				}
+				const int src = (int) (cell & 31ull);
+				if (!((rs_valid >> src) & 1u)) continue;  // rrt_connect.cpp:254
+				double s_rand[8];
+#pragma unroll
+				for (int d = 0; d < 8; ++d) s_rand[d] = __shfl_sync(FULL, rs[d], src);
+				++nn_queries;
+				if (warp_extend<M, false>(Tv, Tx, nx, s_rand, half == 0 ? GBP_FORWARD : GBP_REVERSE, seed, query, cell, P, gm, lane, pair_checks) == GBP_TRAPPED) continue;
+				double s_new[8];
+				tree_get(Tx.t, nx - 1, s_new);
+				++nn_queries;
+				if (warp_connect<M>(Tv, Ty, ny, s_new, half == 0 ? GBP_REVERSE : GBP_FORWARD, P, lane, pair_checks) == GBP_REACHED) solved = true;
+			}
+			half0 = 0;
+		}
+		if (lane == 0) {
+			S.pair_checks[q] += pair_checks;
+			S.nn_queries[q] += nn_queries;
+			S.status[q] = solved ? 1 : 2;
+			S.iters[q] = it;
+			if (solved && P.stop_after_solved > 0) atomicAdd(solved_count, 1);
+		}
+		__syncwarp();
+	}
+}
+
 template <typename M>
 __global__ void __launch_bounds__(128) k_pipe_finish(TerrainView Tv, PipeState S, PlanArena A, PlanArena scratch, int64_t Q, gbp_plan_params P,
 													  unsigned long long *__restrict__ next_query, gbp_plan_stats *__restrict__ stats,
@@ -570,10 +638,11 @@ inline bool plan_pipe_applies(const TerrainView &Tv, const gbp_plan_params &P, i
 	if (P.rrt_star || P.adaptive || P.state_direction_sampling || P.k_candidates > 32 || !Tv.mixed_ok || !Tv.uniform) return false;
 	if (mode && !strcmp(mode, "pipe")) return true;
 	if (mode && (!strcmp(mode, "mega") || !strcmp(mode, "step"))) return false;
-	// a round costs ~0.1 ms whatever the batch size: below ~6 k queries the megakernel's independent warps win (configs[4] queries,
-	// megakernel against this form with 8 speculated halves per round: 4,096 queries 0.063 / 0.077 s, 8,192: 0.114 / 0.095 s,
-	// 16,384: 0.218 / 0.134 s)
-	return nq >= 8192;
+	// a round costs ~0.1 ms whatever the batch size: below ~3 k queries the megakernel's independent warps win (configs[4] queries,
+	// megakernel against this form with 8 speculated halves per round and the tail on k_pipe_resume: 2,048 queries 0.042 / 0.041 s,
+	// 4,096: 0.063 / 0.045 s, 8,192: 0.114 / 0.056 s, 16,384: 0.218 / 0.079 s)
+	if (P.stop_after_solved > 0) return nq >= 2048;  // anytime use (many attempts at one query): depth decides, and 16 speculated halves per round are a 4x shorter iteration than a megakernel warp's (tools/ttfs_sweep.py)
+	return nq >= 4096;
 }
 
 // What one pipeline needs on the host besides its main stream.  Pooled (gbp_capi_pipeline.cu): a call takes one per group of
@@ -583,7 +652,7 @@ struct PipeHostRes {
 	cudaStream_t main = nullptr, sb = nullptr, sc = nullptr, sd = nullptr;  // main: the stream of a group that does not run on the caller's
 	cudaEvent_t ev_tri[PIPE_DEPTH] = {}, ev_con[PIPE_DEPTH] = {}, ev_prep[PIPE_DEPTH] = {}, ev_bat[PIPE_DEPTH] = {}, ev_sel[PIPE_DEPTH] = {}, done = nullptr;
 	cudaError_t create() {
-		cudaError_t e = cudaHostAlloc((void **) &h_count, 2 * sizeof(int), cudaHostAllocDefault);
+		cudaError_t e = cudaHostAlloc((void **) &h_count, CNT_WORDS * sizeof(int), cudaHostAllocDefault);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
@@ -612,7 +681,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	// segments a query may emit per round (see k_pipe_prep): GBP_PIPE_SPEC = 1, 2, 4 or 8
 	// measured on configs[4] (4-8 m, 2000 iterations), B = 1 / 2 / 4 / 8: 65,536 queries 0.365 / 0.302 / 0.284 / 0.303 s,
 	// 16,384 queries 0.205 / 0.155 / 0.136 / 0.134 s, 8,192: - / - / 0.101 / 0.095 s, 4,096: - / - / 0.085 / 0.077 s
-	int B = nq >= 32768 ? 4 : 8;
+	int B = P.stop_after_solved > 0 ? 16 : nq >= 32768 ? 4 : 8;
 	if (const char *b = getenv("GBP_PIPE_SPEC")) B = atoi(b);
 	B = B >= 16 ? 16 : B >= 8 ? 8 : B >= 4 ? 4 : B >= 2 ? 2 : 1;
 	const size_t QB = Q * (size_t) B;
@@ -646,7 +715,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 			take(H[k].connects, Q); take(H[k].flags, Q);
 		}
 		take(next_query, 2);
-		take(solved_count, 4);
+		take(solved_count, 12);  // [0] solved queries (stop_after_solved), [4..7] GBP_PIPE_TRACE: TRAPPED segments, dropped, heavy, heavy with a valid candidate
 		take(batch_list, PIPE_DEPTH * Q);  // queries that need a batch of random states, one list per slot
 		take(cnt, PIPE_DEPTH * CNT_WORDS);  // the counter blocks, then the two bit arrays (one memset)
 		take(G.vbits, bit_words); take(G.ubits, bit_words);
@@ -666,7 +735,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	const unsigned walk_grid = (unsigned) sms * walk_ctas;
 	k_pipe_init<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, nq, starts, goals, P.max_iters);
 	cudaMemsetAsync(cnt, 0, (PIPE_DEPTH * CNT_WORDS + 2 * bit_words) * sizeof(int), st);
-	cudaMemsetAsync(solved_count, 0, 4 * sizeof(int), st);
+	cudaMemsetAsync(solved_count, 0, 12 * sizeof(int), st);
 	// A round runs one extend attempt of every running query; a query needs at most 2 * max_iters of them (every random state
 	// valid) plus the rounds it sits out.  The number of running queries is read back every 32 rounds to stop launching once
 	// all are done.
@@ -677,7 +746,11 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	//              Select and connect overlap the next rounds, which their queries sit out, and are over before
 	//              prep(r + PIPE_DEPTH).
 	const int max_rounds = 4 * P.max_iters + 4;
-	const int check_mask = P.stop_after_solved > 0 ? 3 : B > 1 ? 7 : 31;  // rounds between two looks at the running count (a speculating round is several times longer)
+	const int check_mask = P.stop_after_solved > 0 ? 3 : B > 1 ? 7 : 31;
+	// queries left when the rest of the batch moves to k_pipe_resume: one wave of its warps at most, an eighth of the batch at most
+	int resume_at = (int) std::min<int64_t>((int64_t) sms * 4 * GBP_PLAN_MINBLOCKS, nq / 8);
+	if (const char *r = getenv("GBP_PIPE_RESUME")) resume_at = atoi(r);
+	bool resume = false;  // rounds between two looks at the running count (a speculating round is several times longer)
 	int round = 0;
 	// GBP_PIPE_TRACE=1: device timestamps of 32 consecutive rounds (from round GBP_PIPE_TRACE on, default 640 / 96 when speculating) on the first stream, printed to stderr
 	const bool trace = getenv("GBP_PIPE_TRACE") != nullptr;
@@ -703,19 +776,20 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 		cudaEventRecord(ev_bat[par], sd);
 		if (Tv.ztex) k_walk_seg<true><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
 		else k_walk_seg<false><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
-		k_pipe_triage<<<(unsigned) ((QB + 255) / 256), 256, 0, st>>>(S, G, H[par], P.k_candidates, round);
+		k_pipe_triage<<<(unsigned) ((QB + 255) / 256), 256, 0, st>>>(S, G, H[par], P.k_candidates, round, trace ? solved_count + 4 : nullptr);
 		cudaEventRecord(ev_tri[par], st);
 		if (tr_on) cudaEventRecord(tr[round - tr0][3], st);
 		cudaStreamWaitEvent(sb, ev_tri[par], 0);
-		k_pipe_select<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, A, H[par], G.count, seed, query0, P);
+		k_pipe_select<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, A, H[par], G.count, seed, query0, P, trace ? solved_count + 8 : nullptr);
 		cudaEventRecord(ev_sel[par], sb);
 		cudaStreamWaitEvent(sc, ev_sel[par], 0);
 		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sc>>>(Tv, S, A, H[par], G.count, P, solved_count);
 		cudaEventRecord(ev_con[par], sc);
 		if ((round & check_mask) == check_mask) {
-			cudaMemcpyAsync(h_count, G.count, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
+			cudaMemcpyAsync(h_count, G.count, CNT_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st);
 			if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
-			if (h_count[0] + h_count[1] == 0) { ++round; break; }
+			if (h_count[CNT_RUNNING] == 0) { ++round; break; }
+			if (h_count[CNT_RUNNING] <= resume_at) { ++round; resume = true; break; }
 		}
 	}
 	if (trace) {
@@ -732,10 +806,18 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 					prep / 32 * 1e3, rest / 32 * 1e3, gap / 31 * 1e3);
 		}
 		for (auto &r4 : tr) for (auto &ev : r4) cudaEventDestroy(ev);
+		int d[5] = {};
+		cudaMemcpy(d, solved_count + 4, sizeof d, cudaMemcpyDeviceToHost);
+		fprintf(stderr, "pipe trace: %d rounds, B = %d; segments TRAPPED at triage %d, heavy %d (%d with a valid candidate, the others undecided only), dropped behind a heavy one %d; heavy segments that grew a tree %d\n",
+				round, B, d[0], d[2], d[3], d[1], d[4]);
 	}
 	for (int k = 0; k < PIPE_DEPTH && k < round; ++k) {  // the last batches / selects / connects precede the statistics
 		cudaStreamWaitEvent(st, ev_con[k], 0);
 		cudaStreamWaitEvent(st, ev_bat[k], 0);
+	}
+	if (resume && e == cudaSuccess) {
+		cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st);
+		k_pipe_resume<M><<<(unsigned) sms * GBP_PLAN_MINBLOCKS, 128, 0, st>>>(Tv, S, A, nq, seed, query0, P, next_query, solved_count);
 	}
 	cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st);
 	const int64_t fin_warps = (int64_t) Q < fin_slots ? (int64_t) ((Q + 3) / 4 * 4) : fin_slots;

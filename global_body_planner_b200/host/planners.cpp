@@ -157,6 +157,7 @@ void RRTConnectClass::set_parallel_attempts(int attempts, int iterations, int ve
 	parallel_attempts_ = std::max(1, attempts);
 	iterations_per_attempt_ = std::max(1, iterations);
 	vertices_per_tree_ = std::max(2, vertices);
+	attempts_set_ = true;
 }
 
 int RRTConnectClass::attemptConnect(State s_existing, State s, double t_s, State &s_new, Action &a_new, FastTerrainMap &terrain, int direction) {
@@ -286,12 +287,12 @@ void RRTConnectClass::buildAnytime(FastTerrainMap &terrain, State s_start, State
 	num_vertices = 0;
 	anytime_horizon = poseDistance(s_start, s_goal) / planning_rate_estimate;
 	double cost_so_far = INFTY;
-	const int R = parallel_attempts_, cap = 256;
+	const int R = star && !attempts_set_ ? 3552 : parallel_attempts_, cap = 256;
 	// anytime use of the batch planner: all attempts work on the same query, the round ends once 8 of them have solved
 	// (the 8 shortest raw paths are shortcut below)
 	// the fork's options travel with the batch: directional state / action sampling and the yaw-aware cost run inside the
 	// device planner exactly as the setters configured them (rrt_connect.cpp:246-251, rrt.cpp:34, rrt_connect.cpp:270-274)
-	gbp_plan_params P = {k_candidates_, best_of_k_ ? 1 : 0, iterations_per_attempt_, vertices_per_tree_,
+	gbp_plan_params P = {k_candidates_, best_of_k_ ? 1 : 0, star && !attempts_set_ ? 8000 : iterations_per_attempt_, vertices_per_tree_,
 						 state_action_pair_check_adaptive_step_size_flag_ ? 1 : 0, star ? 1 : 0, 0, 8,
 						 state_direction_sampling_flag_ ? 1 : 0, state_direction_sampling_speed_direction_flag_ ? 1 : 0,
 						 action_direction_sampling_flag_ ? 1 : 0, cost_add_yaw_flag_ ? 1 : 0, state_direction_sampling_probability_threshold_,

@@ -28,7 +28,7 @@ struct GlobalBodyPlannerParams {  // rosparam names: global_body_planner/* and s
 	double body_height = 0.375;              // hard-coded start_z / goal_z of the fork (:214, :219)
 	// B200 additions (no reference counterpart): Philox seed, device searches per anytime round, quiet mode
 	unsigned long long seed = 1;
-	int parallel_attempts = 3552, iterations_per_attempt = 8000, vertices_per_tree = 2048;
+	int parallel_attempts = 2048, iterations_per_attempt = 32000, vertices_per_tree = 2048;  // see rrt_connect.h
 	double max_time_solve = 4000;            // rrt_connect.h:119-120
 	bool verbose = true;                     // the reference prints every statistic to stdout
 };

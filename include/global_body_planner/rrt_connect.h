@@ -35,7 +35,12 @@ protected:
 	double anytime_horizon_init = 0;
 	double horizon_expansion_factor = 1.2;
 	const int max_time_solve = 4000;
-	int parallel_attempts_ = 3552, iterations_per_attempt_ = 8000, vertices_per_tree_ = 2048;  // one wave of warps on 148 SMs (24 per SM); trees as large as the reference's solves (1-2 k vertices)
+	// RRT-Connect rounds run on the pipelined device planner with 16 speculated half-iterations per round: deep attempts find the
+	// first solution soonest (tools/ttfs_sweep.py on data/slope: 2048 x 32000 mean 0.13 s, 4096 x 8000 0.16 s; megakernel
+	// 3552 x 8000 0.29 s).  RRT*-Connect rounds run on the megakernel: one wave of warps on 148 SMs (24 per SM).  Trees as large
+	// as the reference's solves (1-2 k vertices).
+	int parallel_attempts_ = 2048, iterations_per_attempt_ = 32000, vertices_per_tree_ = 2048;
+	bool attempts_set_ = false;  // set_parallel_attempts was called: RRT*-Connect rounds use its values too, otherwise 3552 x 8000
 	double max_time_solve_ = 4000;
 };
 

@@ -172,8 +172,14 @@ def test_pipelined_form_is_identical(gbp, monkeypatch):
         a, pa_s, pa_a, ta = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
         monkeypatch.setenv("GBP_PLAN_MODE", "pipe")
         assert t.plan_batch_form(P, len(S)) == "pipelined"
-        for spec in ("8", "1", "2", "4", "16"):  # half-iterations a query speculates per round (k_pipe_prep): the results do not depend on it
+        # half-iterations a query speculates per round (k_pipe_prep) and the number of running queries at which the rest of the
+        # batch moves to one warp per query (k_pipe_resume; 0: never, 1000000: at the first look): the results do not depend on them
+        for spec, resume in (("8", None), ("1", None), ("2", "0"), ("4", "1000000"), ("16", "40")):
             monkeypatch.setenv("GBP_PIPE_SPEC", spec)
+            if resume is None:
+                monkeypatch.delenv("GBP_PIPE_RESUME", raising=False)
+            else:
+                monkeypatch.setenv("GBP_PIPE_RESUME", resume)
             b, pb_s, pb_a, tb = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
             for k in a.dtype.names:
                 assert np.array_equal(a[k], b[k]), (k, spec)
@@ -184,6 +190,7 @@ def test_pipelined_form_is_identical(gbp, monkeypatch):
                 for k in xa:
                     assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), (k, spec)
         monkeypatch.delenv("GBP_PIPE_SPEC")
+        monkeypatch.delenv("GBP_PIPE_RESUME", raising=False)
     # the batch split into 3 groups of queries, each an independent pipeline on its own host thread and streams
     monkeypatch.setenv("GBP_PIPE_GROUPS", "3")
     P = gbp.PlanParams(6, 0, 300, 128, 0, 0, 1)

@@ -5,5 +5,4 @@ L=gpurun_out/ttfs_pipe.log
 : > $L
 run() { echo "== $*" >> $L; env "${@:2}" timeout 300 python tools/ttfs_sweep.py 8 $1 >> $L 2>&1; }
 run "3552:8000:2048" GBP_PLAN_MODE=mega
-run "2048:8000:2048 4096:8000:2048 8192:8000:2048 4096:16000:2048 2048:32000:2048" GBP_PLAN_MODE=pipe GBP_PIPE_SPEC=16
-run "4096:8000:2048 8192:8000:2048" GBP_PLAN_MODE=pipe GBP_PIPE_SPEC=8
+run "2048:8000:2048 4096:8000:2048 8192:8000:2048 4096:16000:2048 2048:32000:2048 4096:32000:2048 1024:64000:2048" GBP_PLAN_MODE=pipe
