@@ -1,6 +1,7 @@
 // Part 4 of libgbp_b200.so: the pipelined form of the batch planner (gbp_pipeline.cuh), in its own translation unit so
 // that it compiles next to the megakernel instead of after it.  No C entry points: gbp_plan_batch* (gbp_capi_plan.cu)
 // chooses between the forms.
+#include <algorithm>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -61,7 +62,26 @@ int gbp_plan_pipe_launch(const TerrainView &Tv, int64_t nq, const double *starts
 		}
 	int rc = GBP_OK;
 	if (groups == 1) {
-		rc = run_kind(Tv, nq, starts, goals, seed, query0, P, stats, path_states, path_actions, path_cap, st, dump, *R[0], err);
+		// the arena holds both trees of every query at full capacity (plus the round's segment rows): a batch larger than the
+		// device can hold runs as consecutive sub-batches (queries are independent: same results)
+		size_t free_b = 0, total_b = 0;
+		cudaMemGetInfo(&free_b, &total_b);
+		const size_t per_query = (size_t) 2 * (size_t) P.max_vertices * (20 * 8 + 3 * 4) + 16 * (PIPE_ROW * 8 + 32) + PIPE_DEPTH * (PIPE_ROW * 8 + 48) +
+								 2 * PIPE_BATCH * 64 + 512;
+		const size_t budget = std::max(free_b / 10 * 8, total_b / 10 * 4);  // (memory cached in the stream's pool does not show as free)
+		int64_t chunk = std::max<int64_t>(4096, (int64_t) (budget / per_query));
+		if (const char *c = getenv("GBP_PIPE_CHUNK")) chunk = std::max(1, atoi(c));  // tests: queries per sub-batch
+		for (int64_t lo = 0; lo < nq && rc == GBP_OK; lo += chunk) {
+			const int64_t hi = std::min(nq, lo + chunk);
+			PlanTreeDump d = dump;
+			if (d.states) {
+				const size_t rows = (size_t) lo * 2 * d.cap;
+				d.states += rows * 8; d.actions += rows * 10; d.parent += rows; d.g += rows; d.y += rows;
+			}
+			rc = run_kind(Tv, hi - lo, starts + 8 * lo, goals + 8 * lo, seed, query0 + (uint64_t) lo, P, stats + lo,
+						  path_states ? path_states + (size_t) lo * path_cap * 8 : nullptr, path_actions ? path_actions + (size_t) lo * path_cap * 10 : nullptr,
+						  path_cap, st, d, *R[0], err);
+		}
 	} else {
 		// group g runs queries [lo, hi) on its own main stream, after everything the caller queued on st; st then waits for all
 		cudaEvent_t start = R[0]->done;  // borrowed as the fork event: group 0 runs on st itself and does not need its `done`

@@ -678,10 +678,11 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	const size_t cap = (size_t) P.max_vertices, Q = (size_t) nq, per = Q * 2 * cap, K = (size_t) P.k_candidates;
 	const int64_t fin_slots = (int64_t) sms * 4 * 4;
-	// segments a query may emit per round (see k_pipe_prep): GBP_PIPE_SPEC = 1, 2, 4 or 8
-	// measured on configs[4] (4-8 m, 2000 iterations), B = 1 / 2 / 4 / 8: 65,536 queries 0.365 / 0.302 / 0.284 / 0.303 s,
-	// 16,384 queries 0.205 / 0.155 / 0.136 / 0.134 s, 8,192: - / - / 0.101 / 0.095 s, 4,096: - / - / 0.085 / 0.077 s
-	int B = P.stop_after_solved > 0 ? 16 : nq >= 32768 ? 4 : 8;
+	// segments a query may emit per round (see k_pipe_prep): GBP_PIPE_SPEC = 1, 2, 4, 8 or 16
+	// measured on configs[4] (4-8 m, 2000 iterations; profiles/r2b_spec_sweep.txt, r2b_resume_sweep.txt), with the tail on
+	// k_pipe_resume, B = 2 / 4 / 8 / 16: 65,536 queries 0.260 / 0.234 / 0.228 / - s, 16,384 queries - / 0.088 / 0.086 / 0.080 s,
+	// 4,096 queries - / - / 0.046 / 0.043 s
+	int B = nq >= 32768 ? 4 : 16;
 	if (const char *b = getenv("GBP_PIPE_SPEC")) B = atoi(b);
 	B = B >= 16 ? 16 : B >= 8 ? 8 : B >= 4 ? 4 : B >= 2 ? 2 : 1;
 	const size_t QB = Q * (size_t) B;
@@ -750,7 +751,10 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	// queries left when the rest of the batch moves to k_pipe_resume: one wave of its warps at most, an eighth of the batch at most
 	int resume_at = (int) std::min<int64_t>((int64_t) sms * 4 * GBP_PLAN_MINBLOCKS, nq / 8);
 	if (const char *r = getenv("GBP_PIPE_RESUME")) resume_at = atoi(r);
-	bool resume = false;  // rounds between two looks at the running count (a speculating round is several times longer)
+	bool resume = false;
+	// the side kernels are warp-per-item and latency-bound: as many resident warps as their registers allow (80 / 128 per thread)
+	int side_ctas_batch = 6, side_ctas_connect = 4;
+	if (const char *c = getenv("GBP_PIPE_SIDE_CTAS")) { side_ctas_batch = atoi(c) > 0 ? atoi(c) : 4; side_ctas_connect = atoi(c) > 0 ? (atoi(c) + 1) / 2 : 2; }  // rounds between two looks at the running count (a speculating round is several times longer)
 	int round = 0;
 	// GBP_PIPE_TRACE=1: device timestamps of 32 consecutive rounds (from round GBP_PIPE_TRACE on, default 640 / 96 when speculating) on the first stream, printed to stderr
 	const bool trace = getenv("GBP_PIPE_TRACE") != nullptr;
@@ -772,7 +776,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 		if (tr_on) cudaEventRecord(tr[round - tr0][2], st);
 		// (queued before or after the walk makes no difference: its blocks get their SMs as walk CTAs retire)
 		cudaStreamWaitEvent(sd, ev_prep[par], 0);
-		k_pipe_batch<M><<<(unsigned) sms * 4, 128, 0, sd>>>(Tv, S, batch_list + (size_t) par * Q, G.count, seed, query0);
+		k_pipe_batch<M><<<(unsigned) sms * side_ctas_batch, 128, 0, sd>>>(Tv, S, batch_list + (size_t) par * Q, G.count, seed, query0);
 		cudaEventRecord(ev_bat[par], sd);
 		if (Tv.ztex) k_walk_seg<true><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
 		else k_walk_seg<false><<<walk_grid, RF_WARPS * 32, 0, st>>>(Tv, G, P.k_candidates, seed, query0, P.action_direction_sampling, P.action_direction_threshold);
@@ -783,7 +787,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 		k_pipe_select<M><<<(unsigned) sms * 4, 128, 0, sb>>>(Tv, S, A, H[par], G.count, seed, query0, P, trace ? solved_count + 8 : nullptr);
 		cudaEventRecord(ev_sel[par], sb);
 		cudaStreamWaitEvent(sc, ev_sel[par], 0);
-		k_pipe_connect<M><<<(unsigned) sms * 2, 128, 0, sc>>>(Tv, S, A, H[par], G.count, P, solved_count);
+		k_pipe_connect<M><<<(unsigned) sms * side_ctas_connect, 128, 0, sc>>>(Tv, S, A, H[par], G.count, P, solved_count);
 		cudaEventRecord(ev_con[par], sc);
 		if ((round & check_mask) == check_mask) {
 			cudaMemcpyAsync(h_count, G.count, CNT_WORDS * sizeof(int), cudaMemcpyDeviceToHost, st);

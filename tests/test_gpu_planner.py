@@ -191,13 +191,16 @@ def test_pipelined_form_is_identical(gbp, monkeypatch):
                     assert np.array_equal(xa[k], ya[k]) and np.array_equal(xb[k], yb[k]), (k, spec)
         monkeypatch.delenv("GBP_PIPE_SPEC")
         monkeypatch.delenv("GBP_PIPE_RESUME", raising=False)
-    # the batch split into 3 groups of queries, each an independent pipeline on its own host thread and streams
+    # the batch split into 3 groups of queries, each an independent pipeline on its own host thread and streams; and run as
+    # consecutive sub-batches of 300 queries (what a batch larger than the device can hold does)
     monkeypatch.setenv("GBP_PIPE_GROUPS", "3")
     P = gbp.PlanParams(6, 0, 300, 128, 0, 0, 1)
     c, pc_s, pc_a, tc = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
     monkeypatch.setenv("GBP_PIPE_GROUPS", "1")
+    monkeypatch.setenv("GBP_PIPE_CHUNK", "300")
     d, pd_s, pd_a, td = t.plan_batch_trees(S, G, 4, 50, P, path_cap=64, tree_cap=128)
     monkeypatch.delenv("GBP_PIPE_GROUPS")
+    monkeypatch.delenv("GBP_PIPE_CHUNK")
     assert c["solved"].sum() >= 5
     for k in c.dtype.names:
         assert np.array_equal(c[k], d[k]), k
