@@ -64,12 +64,22 @@ int gbp_plan_pipe_launch(const TerrainView &Tv, int64_t nq, const double *starts
 	if (groups == 1) {
 		// the arena holds both trees of every query at full capacity (plus the round's segment rows): a batch larger than the
 		// device can hold runs as consecutive sub-batches (queries are independent: same results)
-		size_t free_b = 0, total_b = 0;
-		cudaMemGetInfo(&free_b, &total_b);
+		// (the device's total memory is read once: cudaMemGetInfo inside a call cost the timed region a sporadic 40 ms)
+		static std::mutex total_mutex;
+		static std::vector<std::pair<int, size_t>> totals;
+		size_t total_b = 0;
+		{
+			std::lock_guard<std::mutex> lock(total_mutex);
+			for (const auto &t : totals) if (t.first == dev) total_b = t.second;
+			if (!total_b) {
+				size_t free_b = 0;
+				if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || !total_b) total_b = (size_t) 64 << 30;
+				totals.emplace_back(dev, total_b);
+			}
+		}
 		const size_t per_query = (size_t) 2 * (size_t) P.max_vertices * (20 * 8 + 3 * 4) + 16 * (PIPE_ROW * 8 + 32) + PIPE_DEPTH * (PIPE_ROW * 8 + 48) +
 								 2 * PIPE_BATCH * 64 + 512;
-		const size_t budget = std::max(free_b / 10 * 8, total_b / 10 * 4);  // (memory cached in the stream's pool does not show as free)
-		int64_t chunk = std::max<int64_t>(4096, (int64_t) (budget / per_query));
+		int64_t chunk = std::max<int64_t>(4096, (int64_t) (total_b / 10 * 4 / per_query));  // sub-batches of at most 40 % of the device
 		if (const char *c = getenv("GBP_PIPE_CHUNK")) chunk = std::max(1, atoi(c));  // tests: queries per sub-batch
 		for (int64_t lo = 0; lo < nq && rc == GBP_OK; lo += chunk) {
 			const int64_t hi = std::min(nq, lo + chunk);

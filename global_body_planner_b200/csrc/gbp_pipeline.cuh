@@ -33,6 +33,7 @@
 // Applies to plain RRT-Connect at the fixed step with K <= 32 on terrains with the mixed-precision evaluator; everything
 // else (RRT*, adaptive step, directional STATE sampling, anytime rounds, K > 32, other map kinds) stays on k_plan_batch.
 #pragma once
+#include <chrono>
 #include <type_traits>
 
 #include "gbp_planner.cuh"
@@ -725,7 +726,10 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	const size_t need = layout(nullptr);
 	void *mem = nullptr;
 	cudaError_t e;
+	const auto host_t0 = std::chrono::steady_clock::now();
+	auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
 	if ((e = cudaMallocAsync(&mem, need, st)) != cudaSuccess) { err = std::string("pipelined planner arena: ") + cudaGetErrorString(e); return GBP_E_CUDA; }
+	const double host_alloc_ms = host_ms();
 	layout((char *) mem);
 	// host-side resources of this pipeline (a pinned word pair for the running count, the two side streams and their events)
 	int *const h_count = R.h_count;
@@ -812,6 +816,7 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 		for (auto &r4 : tr) for (auto &ev : r4) cudaEventDestroy(ev);
 		int d[5] = {};
 		cudaMemcpy(d, solved_count + 4, sizeof d, cudaMemcpyDeviceToHost);
+		fprintf(stderr, "pipe trace (host): arena of %.2f GB allocated in %.2f ms, rounds issued and drained after %.1f ms\n", need / 1e9, host_alloc_ms, host_ms());
 		fprintf(stderr, "pipe trace: %d rounds, B = %d; segments TRAPPED at triage %d, heavy %d (%d with a valid candidate, the others undecided only), dropped behind a heavy one %d; heavy segments that grew a tree %d\n",
 				round, B, d[0], d[2], d[3], d[1], d[4]);
 	}
@@ -820,8 +825,18 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 		cudaStreamWaitEvent(st, ev_bat[k], 0);
 	}
 	if (resume && e == cudaSuccess) {
+		cudaEvent_t r0 = nullptr, r1 = nullptr;
+		if (trace) { cudaEventCreate(&r0); cudaEventCreate(&r1); cudaEventRecord(r0, st); }
 		cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st);
 		k_pipe_resume<M><<<(unsigned) sms * GBP_PLAN_MINBLOCKS, 128, 0, st>>>(Tv, S, A, nq, seed, query0, P, next_query, solved_count);
+		if (trace) {
+			cudaEventRecord(r1, st);
+			cudaEventSynchronize(r1);
+			float ms = 0;
+			cudaEventElapsedTime(&ms, r0, r1);
+			fprintf(stderr, "pipe trace: k_pipe_resume took over %d running queries after round %d: %.2f ms\n", h_count[CNT_RUNNING], round, ms);
+			cudaEventDestroy(r0); cudaEventDestroy(r1);
+		}
 	}
 	cudaMemsetAsync(next_query, 0, sizeof(unsigned long long), st);
 	const int64_t fin_warps = (int64_t) Q < fin_slots ? (int64_t) ((Q + 3) / 4 * 4) : fin_slots;

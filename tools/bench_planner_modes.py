@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the forms of the batch planner (GBP_PLAN_MODE=mega | pipe | step) on bench_plans' configs[4] queries: identical
-statistics required, plans/s of each.  usage: python tools/bench_planner_modes.py [queries [modes]]"""
+statistics required, plans/s of each.  usage: python tools/bench_planner_modes.py [queries [modes [query stream]]]"""
 import json
 import os
 import sys
@@ -20,7 +20,8 @@ def main():
     x, y, z = bp.rough_terrain()
     t = gbp.Terrain(x, y, z)
     valid = lambda q: t.valid_states(q, gbp.STANCE)[0]
-    s, g = bp.make_queries(valid, t.sample_states, 2 * nq, 11, 7000, 4.0, 8.0)
+    stream = int(sys.argv[3]) if len(sys.argv) > 3 else 7000  # bench.py: 7000 + rank
+    s, g = bp.make_queries(valid, t.sample_states, 2 * nq, 11, stream, 4.0, 8.0)
     hs, _ = t.ground_height(s[:, 0], s[:, 1]); hg, _ = t.ground_height(g[:, 0], g[:, 1])
     g[:, 2] = s[:, 2] - hs + hg
     vg = valid(g)
@@ -30,6 +31,9 @@ def main():
     for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("mega", "pipe")):
         os.environ["GBP_PLAN_MODE"] = mode
         st, secs = bp.timed_batch(gbp, torch, None, dev, 0, 1, t, s, g, 11, 0, P)
+        for _ in range(int(os.environ.get("GBP_BENCH_REPEAT", "1")) - 1):  # run-to-run spread of the same batch
+            secs2 = bp.timed_batch(gbp, torch, None, dev, 0, 1, t, s, g, 11, 0, P)[1]
+            print(f"{mode}: repeat {secs2:.4f} s", file=sys.stderr)
         out[mode] = bp.batch_summary(st, secs)
         if ref is None:
             ref = st.copy()
