@@ -381,15 +381,17 @@ int gbp_sample_validate(const gbp_terrain *t, const gbp_states *table, int64_t n
 						  !getenv("CUDA_LAUNCH_BLOCKING");
 	const int64_t BL = 1ll << SV_BLOCK_SHIFT, nblocks = (n + BL - 1) / BL;
 	std::vector<int64_t> chunk_off;  // streamed: 1, 1, 2, 4, 4 ... arrival blocks per chunk (the first copy is the only exposed one)
-	if (streamed) for (int64_t b = 0, w = 1, k = 0; b < nblocks; b += w, ++k, w = std::min<int64_t>(k < 2 ? 1 : 2 * w, 4)) chunk_off.push_back(b * BL);
+	int64_t max_chunk_blocks = 4;
+	if (const char *c = getenv("GBP_SV_CHUNK_BLOCKS")) max_chunk_blocks = std::min(64, std::max(1, atoi(c)));  // A/B runs: larger copies when many ranks share the host
+	if (streamed) for (int64_t b = 0, w = 1, k = 0; b < nblocks; b += w, ++k, w = std::min<int64_t>(k < 2 ? 1 : 2 * w, max_chunk_blocks)) chunk_off.push_back(b * BL);
 	else for (int64_t off = 0; off < n; off += 1 << 21) chunk_off.push_back(off);
 	chunk_off.push_back(n);
 	const int64_t nwords = (n + 31) / 32, nch = (int64_t) chunk_off.size() - 1;
 	const int64_t cap = !valid_index ? 0 : (valid_cap < n ? valid_cap : n);
 	static thread_local unsigned *h_ones = nullptr;  // pinned source of the arrival words
 	if (!h_ones) {
-		CU(cudaHostAlloc((void **) &h_ones, 8 * sizeof(unsigned), cudaHostAllocDefault));
-		for (int k = 0; k < 8; ++k) h_ones[k] = 1u;
+		CU(cudaHostAlloc((void **) &h_ones, 64 * sizeof(unsigned), cudaHostAllocDefault));
+		for (int k = 0; k < 64; ++k) h_ones[k] = 1u;
 	}
 	Dev scratch(st), d_idx(st), d_dir(st), d_bits(st), d_flags(st), d_index(st), d_res(st), d_sn(st), d_tn(st), d_act(st);
 	const size_t n_words64 = 8 + 1024 + (size_t) nch + 1 + (size_t) (nblocks + 1) / 2;  // counters, block sums, redo counts, work counter, arrival words
