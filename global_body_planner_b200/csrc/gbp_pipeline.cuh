@@ -681,9 +681,9 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	const int64_t fin_slots = (int64_t) sms * 4 * 4;
 	// segments a query may emit per round (see k_pipe_prep): GBP_PIPE_SPEC = 1, 2, 4, 8 or 16
 	// measured on configs[4] (4-8 m, 2000 iterations; profiles/r2b_spec_sweep.txt, r2b_resume_sweep.txt), with the tail on
-	// k_pipe_resume, B = 2 / 4 / 8 / 16: 65,536 queries 0.260 / 0.234 / 0.228 / - s, 16,384 queries - / 0.088 / 0.086 / 0.080 s,
-	// 4,096 queries - / - / 0.046 / 0.043 s
-	int B = nq >= 32768 ? 4 : 16;
+	// k_pipe_resume, B = 2 / 4 / 8 / 16: 65,536 queries 0.260 / 0.2266 / 0.2226 / - s, 32,768 queries - / 0.1356 / 0.1257 / - s,
+	// 16,384 queries - / 0.088 / 0.086 / 0.080 s, 4,096 queries - / - / 0.046 / 0.043 s
+	int B = nq >= 32768 ? 8 : 16;
 	if (const char *b = getenv("GBP_PIPE_SPEC")) B = atoi(b);
 	B = B >= 16 ? 16 : B >= 8 ? 8 : B >= 4 ? 4 : B >= 2 ? 2 : 1;
 	const size_t QB = Q * (size_t) B;
