@@ -741,8 +741,8 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	k_pipe_init<M><<<(unsigned) ((Q + 127) / 128), 128, 0, st>>>(Tv, S, A, nq, starts, goals, P.max_iters);
 	cudaMemsetAsync(cnt, 0, (PIPE_DEPTH * CNT_WORDS + 2 * bit_words) * sizeof(int), st);
 	cudaMemsetAsync(solved_count, 0, 12 * sizeof(int), st);
-	// A round runs one extend attempt of every running query; a query needs at most 2 * max_iters of them (every random state
-	// valid) plus the rounds it sits out.  The number of running queries is read back every 32 rounds to stop launching once
+	// A round runs up to B extend attempts of every running query; a query needs at most 2 * max_iters of them (every random
+	// state valid) plus the rounds it sits out.  The number of running queries is read back every few rounds to stop launching once
 	// all are done.
 	//   stream st: prep, walk, triage of round r.
 	//   stream sd: the batches of random states requested by prep(r) (needed by prep(r + 1)).
@@ -751,14 +751,14 @@ inline int plan_pipe_launch_kind(const TerrainView &Tv, int64_t nq, const double
 	//              Select and connect overlap the next rounds, which their queries sit out, and are over before
 	//              prep(r + PIPE_DEPTH).
 	const int max_rounds = 4 * P.max_iters + 4;
-	const int check_mask = P.stop_after_solved > 0 ? 3 : B > 1 ? 7 : 31;
+	const int check_mask = P.stop_after_solved > 0 ? 3 : B > 1 ? 7 : 31;  // rounds between two looks at the running count (a speculating round is several times longer)
 	// queries left when the rest of the batch moves to k_pipe_resume: one wave of its warps at most, an eighth of the batch at most
 	int resume_at = (int) std::min<int64_t>((int64_t) sms * 4 * GBP_PLAN_MINBLOCKS, nq / 8);
 	if (const char *r = getenv("GBP_PIPE_RESUME")) resume_at = atoi(r);
 	bool resume = false;
 	// the side kernels are warp-per-item and latency-bound: as many resident warps as their registers allow (80 / 128 per thread)
 	int side_ctas_batch = 6, side_ctas_connect = 4;
-	if (const char *c = getenv("GBP_PIPE_SIDE_CTAS")) { side_ctas_batch = atoi(c) > 0 ? atoi(c) : 4; side_ctas_connect = atoi(c) > 0 ? (atoi(c) + 1) / 2 : 2; }  // rounds between two looks at the running count (a speculating round is several times longer)
+	if (const char *c = getenv("GBP_PIPE_SIDE_CTAS")) { side_ctas_batch = atoi(c) > 0 ? atoi(c) : 4; side_ctas_connect = atoi(c) > 0 ? (atoi(c) + 1) / 2 : 2; }
 	int round = 0;
 	// GBP_PIPE_TRACE=1: device timestamps of 32 consecutive rounds (from round GBP_PIPE_TRACE on, default 640 / 96 when speculating) on the first stream, printed to stderr
 	const bool trace = getenv("GBP_PIPE_TRACE") != nullptr;
