@@ -55,7 +55,8 @@ public:
 
 private:
 	void adopt(gbp_terrain *t, const char *what);
-	std::shared_ptr<gbp_terrain> dev_;  // copies of a FastTerrainMap share the device terrain (it is immutable)
+	std::shared_ptr<gbp_terrain> dev_;  // copies of a FastTerrainMap share the device terrain: the map data is read-only after loadData; the
+	                                    // handle's only mutable part is the host-pointer staging ring, which the library guards with a mutex
 	std::vector<double> x_data_, y_data_;
 };
 
