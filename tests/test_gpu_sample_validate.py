@@ -36,6 +36,14 @@ def env(gbp, request):
     return request.param, t, po.Oracle(T), T
 
 
+@pytest.fixture(scope="module", params=["synth_mixed", "rough_terrain"])
+def env_sizes(gbp, request):
+    """size handling does not depend on the map: one mixed-precision map and one shipped fp64 map"""
+    T = load_terrain(request.param)
+    t = gbp.Terrain(T.x, T.y, T.z, T.dx, T.dy, T.dz)
+    return request.param, t, po.Oracle(T), T
+
+
 def vertex_table(o, rows, seed):
     """valid STANCE states anywhere on the map (the tree vertices candidates start from)"""
     out, idx0 = [], 0
@@ -134,10 +142,8 @@ def test_implicit_rows_with_offset_and_constant_direction(gbp, env):
 
 
 @pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 40, 63, 64, 65, 72, 73, 1023, 1025, 4100])
-def test_ragged_sizes(gbp, env, n):
-    name, t, o, T = env
-    if name not in ("synth_mixed", "rough_terrain"):
-        pytest.skip("size handling does not depend on the map")
+def test_ragged_sizes(gbp, env_sizes, n):
+    name, t, o, T = env_sizes
     table = vertex_table(o, 4100, seed=6)
     rng = np.random.default_rng(n)
     check(gbp, t, o, table, n, direction=rng.integers(0, 2, n).astype(np.uint8))
