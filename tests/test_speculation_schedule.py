@@ -102,7 +102,7 @@ def test_speculated_halves_equal_the_sequential_planner(name, max_iters, cap):
         P = po.PlanParams(K, 0, max_iters, cap, 0, 0, 0)
         st, _, _, ta, tb = o.plan_ex(start, goal, 4, 50 + qi, P)
         rounds = {}
-        for B in (1, 4, 16):
+        for B in (1, 4, 8, 16):  # 8 and 16 are the shipped depths (from / below 32,768 queries)
             Ta, Tb, solved, iters, nn_queries, rounds[B] = speculative_plan(o, start, goal, 4, 50 + qi, K, max_iters, cap, B)
             assert (solved, iters, len(Ta.states), len(Tb.states), nn_queries) == (bool(st.solved), st.iters, st.nv_a, st.nv_b, st.nn_queries), (qi, B)
             for mine, ref in ((Ta, ta), (Tb, tb)):
