@@ -4,6 +4,9 @@
 //   gbp_plan <csv-dir | create:SEED | default> [--algorithm rrt-connect|rrt-star-connect] [--num-calls N] [--replan-time-limit S]
 //            [--start X Y YAW] [--goal X Y YAW] [--height H] [--seed S] [--gridmap] [--attempts A ITERS VERTS]
 //            [--max-time-solve S] [--adaptive] [--plan-out FILE] [--discrete-out FILE] [--quiet]
+//            [--params FILE]                       the reference's config/params.yaml (rosparam names; later options override it)
+//            [--cost-add-yaw LENGTH_W YAW_W] [--state-direction-sampling P] [--speed-direction] [--action-direction-sampling P]
+//            [--print-params]                      print the resolved parameters and exit (no device needed)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +23,7 @@ int main(int argc, char **argv) {
 	GlobalBodyPlannerParams p;
 	p.goal_position_x = 8.0;  // launch/example.launch: (0, 0) -> (8, 0)
 	bool gridmap = false;
+	bool print_params = false;
 	const char *plan_out = nullptr, *discrete_out = nullptr;
 	for (int i = 2; i < argc; ++i) {
 		auto need = [&](int k) { if (i + k >= argc) { std::fprintf(stderr, "%s needs %d value(s)\n", argv[i], k); std::exit(2); } };
@@ -37,7 +41,36 @@ int main(int argc, char **argv) {
 		else if (!std::strcmp(argv[i], "--plan-out")) { need(1); plan_out = argv[++i]; }
 		else if (!std::strcmp(argv[i], "--discrete-out")) { need(1); discrete_out = argv[++i]; }
 		else if (!std::strcmp(argv[i], "--quiet")) p.verbose = false;
+		else if (!std::strcmp(argv[i], "--params")) {
+			need(1);
+			try { loadParamsYaml(argv[++i], p); } catch (const std::exception &e) { std::fprintf(stderr, "gbp_plan: %s\n", e.what()); return 2; }
+		}
+		else if (!std::strcmp(argv[i], "--cost-add-yaw")) { need(2); p.cost_add_yaw_flag = true; p.cost_add_yaw_length_weight = std::atof(argv[++i]); p.cost_add_yaw_yaw_weight = std::atof(argv[++i]); }
+		else if (!std::strcmp(argv[i], "--state-direction-sampling")) { need(1); p.state_direction_sampling_flag = true; p.state_direction_sampling_probability_threshold = std::atof(argv[++i]); }
+		else if (!std::strcmp(argv[i], "--speed-direction")) p.state_direction_sampling_speed_direction_flag = true;
+		else if (!std::strcmp(argv[i], "--action-direction-sampling")) { need(1); p.action_direction_sampling_flag = true; p.action_direction_sampling_probability_threshold = std::atof(argv[++i]); }
+		else if (!std::strcmp(argv[i], "--print-params")) print_params = true;
 		else { std::fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
+	}
+	if (print_params) {  // rosparam names, one per line
+		std::cout.precision(17);
+		std::cout << "global_body_planner/num_calls " << p.num_calls << "\nglobal_body_planner/replan_time_limit " << p.replan_time_limit
+				  << "\nglobal_body_planner/algorithm " << p.algorithm
+				  << "\nglobal_body_planner/state_action_pair_check_adaptive_step_size_flag " << p.state_action_pair_check_adaptive_step_size_flag
+				  << "\nglobal_body_planner/cost_add_yaw/flag " << p.cost_add_yaw_flag << "\nglobal_body_planner/cost_add_yaw/length_weight "
+				  << p.cost_add_yaw_length_weight << "\nglobal_body_planner/cost_add_yaw/yaw_weight " << p.cost_add_yaw_yaw_weight
+				  << "\nglobal_body_planner/action_direction_sampling/flag " << p.action_direction_sampling_flag
+				  << "\nglobal_body_planner/action_direction_sampling/probability_threshold " << p.action_direction_sampling_probability_threshold
+				  << "\nglobal_body_planner/state_direction_sampling/flag " << p.state_direction_sampling_flag
+				  << "\nglobal_body_planner/state_direction_sampling/probability_threshold " << p.state_direction_sampling_probability_threshold
+				  << "\nglobal_body_planner/state_direction_sampling/speed_direction_flag " << p.state_direction_sampling_speed_direction_flag
+				  << "\nstate_publisher/start_position_x " << p.start_position_x << "\nstate_publisher/start_position_y " << p.start_position_y
+				  << "\nstate_publisher/start_yaw " << p.start_yaw << "\nstate_publisher/goal_position_x " << p.goal_position_x
+				  << "\nstate_publisher/goal_position_y " << p.goal_position_y << "\nstate_publisher/goal_yaw " << p.goal_yaw
+				  << "\nbody_height " << p.body_height << "\nseed " << p.seed << "\nparallel_attempts " << p.parallel_attempts
+				  << "\niterations_per_attempt " << p.iterations_per_attempt << "\nvertices_per_tree " << p.vertices_per_tree
+				  << "\nmax_time_solve " << p.max_time_solve << std::endl;
+		return 0;
 	}
 	try {
 		GlobalBodyPlanner planner(p);

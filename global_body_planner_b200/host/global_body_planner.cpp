@@ -7,6 +7,88 @@
 
 #include "../../include/global_body_planner/global_body_planner.h"
 
+#include <fstream>
+#include <map>
+
+namespace {
+// the YAML subset of the reference's config/params.yaml, flattened to rosparam names ("global_body_planner/cost_add_yaw/flag")
+std::map<std::string, std::string> flatten_yaml(const std::string &path) {
+	std::ifstream f(path);
+	if (!f) throw std::runtime_error("loadParamsYaml: cannot open " + path);
+	std::map<std::string, std::string> out;
+	std::vector<std::pair<int, std::string>> stack;  // (indent, key) of the open mappings
+	std::string line;
+	while (std::getline(f, line)) {
+		bool quoted = false;
+		size_t cut = std::string::npos;
+		for (size_t i = 0; i < line.size(); ++i) {  // a comment starts at a # outside quotes that begins the line or follows a blank
+			if (line[i] == '"' || line[i] == '\'') quoted = !quoted;
+			if (line[i] == '#' && !quoted && (i == 0 || line[i - 1] == ' ' || line[i - 1] == '\t')) { cut = i; break; }
+		}
+		if (cut != std::string::npos) line.erase(cut);
+		while (!line.empty() && (line.back() == ' ' || line.back() == '\t' || line.back() == '\r')) line.pop_back();
+		const size_t indent = line.find_first_not_of(' ');
+		if (indent == std::string::npos || line[indent] == '-') continue;  // blank lines and sequence items (RViz section)
+		const size_t colon = line.find(':', indent);
+		if (colon == std::string::npos) continue;
+		std::string key = line.substr(indent, colon - indent), value = colon + 1 < line.size() ? line.substr(colon + 1) : "";
+		const size_t v0 = value.find_first_not_of(" \t");
+		value = v0 == std::string::npos ? "" : value.substr(v0);
+		if (value.size() >= 2 && (value.front() == '"' || value.front() == '\'') && value.back() == value.front()) value = value.substr(1, value.size() - 2);
+		while (!stack.empty() && stack.back().first >= (int) indent) stack.pop_back();
+		std::string name;
+		for (const auto &s : stack) name += s.second + "/";
+		name += key;
+		if (value.empty()) stack.emplace_back((int) indent, key);
+		else out[name] = value;
+	}
+	return out;
+}
+bool yaml_bool(const std::string &name, const std::string &v) {
+	if (v == "true" || v == "True" || v == "TRUE" || v == "yes" || v == "on") return true;
+	if (v == "false" || v == "False" || v == "FALSE" || v == "no" || v == "off") return false;
+	throw std::runtime_error("loadParamsYaml: " + name + ": '" + v + "' is not a bool");
+}
+double yaml_double(const std::string &name, const std::string &v) {
+	size_t used = 0;
+	double d = 0;
+	try { d = std::stod(v, &used); } catch (const std::exception &) { used = 0; }
+	if (used != v.size() || v.empty()) throw std::runtime_error("loadParamsYaml: " + name + ": '" + v + "' is not a number");
+	return d;
+}
+}  // namespace
+
+std::vector<std::string> loadParamsYaml(const std::string &path, GlobalBodyPlannerParams &p) {
+	const std::map<std::string, std::string> y = flatten_yaml(path);
+	std::vector<std::string> applied;
+	auto has = [&](const char *name) { const bool h = y.count(name) != 0; if (h) applied.push_back(name); return h; };
+	auto B = [&](const char *name, bool &dst) { if (has(name)) dst = yaml_bool(name, y.at(name)); };
+	auto D = [&](const char *name, double &dst) { if (has(name)) dst = yaml_double(name, y.at(name)); };
+	if (has("global_body_planner/num_calls")) p.num_calls = (int) yaml_double("global_body_planner/num_calls", y.at("global_body_planner/num_calls"));
+	D("global_body_planner/replan_time_limit", p.replan_time_limit);
+	if (has("global_body_planner/algorithm")) {
+		p.algorithm = y.at("global_body_planner/algorithm");
+		if (p.algorithm != "rrt-connect" && p.algorithm != "rrt-star-connect")
+			throw std::runtime_error("loadParamsYaml: global_body_planner/algorithm: '" + p.algorithm + "' (rrt-connect | rrt-star-connect)");
+	}
+	B("global_body_planner/state_action_pair_check_adaptive_step_size_flag", p.state_action_pair_check_adaptive_step_size_flag);
+	B("global_body_planner/cost_add_yaw/flag", p.cost_add_yaw_flag);
+	D("global_body_planner/cost_add_yaw/length_weight", p.cost_add_yaw_length_weight);
+	D("global_body_planner/cost_add_yaw/yaw_weight", p.cost_add_yaw_yaw_weight);
+	B("global_body_planner/action_direction_sampling/flag", p.action_direction_sampling_flag);
+	D("global_body_planner/action_direction_sampling/probability_threshold", p.action_direction_sampling_probability_threshold);
+	B("global_body_planner/state_direction_sampling/flag", p.state_direction_sampling_flag);
+	D("global_body_planner/state_direction_sampling/probability_threshold", p.state_direction_sampling_probability_threshold);
+	B("global_body_planner/state_direction_sampling/speed_direction_flag", p.state_direction_sampling_speed_direction_flag);
+	D("state_publisher/start_position_x", p.start_position_x);
+	D("state_publisher/start_position_y", p.start_position_y);
+	D("state_publisher/start_yaw", p.start_yaw);
+	D("state_publisher/goal_position_x", p.goal_position_x);
+	D("state_publisher/goal_position_y", p.goal_position_y);
+	D("state_publisher/goal_yaw", p.goal_yaw);
+	return applied;
+}
+
 GlobalBodyPlanner::GlobalBodyPlanner(const GlobalBodyPlannerParams &params) : p_(params) {
 	robot_start_.fill(0);
 	robot_goal_.fill(0);

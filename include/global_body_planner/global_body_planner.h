@@ -33,6 +33,13 @@ struct GlobalBodyPlannerParams {  // rosparam names: global_body_planner/* and s
 	bool verbose = true;                     // the reference prints every statistic to stdout
 };
 
+// What `rosparam load config/params.yaml` + the launch files give the reference's node: reads the YAML subset that file uses
+// (nested block mappings, scalar values, # comments) and overwrites the fields of `p` whose rosparam names
+// (global_body_planner/*, state_publisher/{start,goal}_*; global_body_planner.cpp:15-28, :181-204, :220-228) appear in it;
+// names it does not know (topics, update rates, the publisher's and RViz's sections) are ignored as the planner node ignores
+// them.  Returns the rosparam names it applied; throws std::runtime_error on an unreadable file or a malformed value.
+std::vector<std::string> loadParamsYaml(const std::string &path, GlobalBodyPlannerParams &p);
+
 class GlobalBodyPlanner {
 public:
 	explicit GlobalBodyPlanner(const GlobalBodyPlannerParams &params);
